@@ -1,0 +1,817 @@
+/* ORACLE -- test infrastructure, NOT product code.  Plain C (+OpenMP) restatement of the CPU
+ * algorithm of DuneCopasi's CG-P1 hot path.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this.
+ *
+ * PARITY STATUS: the reference cannot be compiled here (needs ~10 DUNE modules incl. an unpinned
+ * dune-pdelab branch, .ci/setup_dune:55-74), so this restatement is pinned only by the reference's
+ * own coarse known-answer system tests (test/gauss.ini:53-55, test/exp.ini:33-35,
+ * test/poisson.ini:29-32, test/two_disks.ini:13-19,57-59) and by element-level identities
+ * (tests/test_oracle_kat.py).  Per-entry residual/Jacobian parity against the real reference is
+ * "parity unpinned".
+ *
+ * What each function follows (paths relative to /root/reference):
+ *   orc_eval                 byte-code walk ~ src/dune/copasi/parser/mu.cc:214-219 (muParser VM);
+ *                            ExprTk/SymEngine evaluate the same grammar as ASTs.
+ *   orc_residual_volume      dune/copasi/model/diffusion_reaction/local_operator.hh:417-491
+ *   orc_jacobian_volume      local_operator.hh:541-707 (analytic), :713-765 (numerical, FD)
+ *                            sink = CSR (matrix based) or PseudoJacobian :90-108 (matrix free apply)
+ *   orc_residual_skeleton    local_operator.hh:777-971, :1398-1415
+ *   orc_jacobian_skeleton    local_operator.hh:973-1199, :1354-1396, :1417-1452
+ *   quadrature / basis       dune-geometry simplex rules of order 2, dune-localfunctions P1
+ *                            (third party, values as listed in SURVEY.md App. A.3)
+ *   orc_bicgstab / orc_cg    dune-istl BiCGSTABSolver / CGSolver operation order (third party,
+ *                            SURVEY.md App. C.1), built by dune/copasi/solver/istl/factory/iterative.hh:36-73
+ *   preconditioners          dune-istl SeqJac; dune/copasi/solver/istl/block_jacobi.hh:46-128
+ *
+ * Conscious deviation (documented in DESIGN.md): for a species that lives only on the *other*
+ * side of an interface facet the reference pairs the other element's coefficients with this
+ * element's shape functions by local index (local_operator.hh:903-916), which is only correct when
+ * both elements number the shared vertices identically.  The oracle (and the product) evaluate the
+ * geometrically intended value: the P1 trace of the other side's field on the facet.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct {
+  int32_t dim;
+  int64_t nv;
+  const double* coords;      /* [nv*dim] */
+  int64_t ne;
+  const int32_t* elems;      /* [ne*(dim+1)] */
+  const int32_t* elem_comp;  /* [ne] compartment id or -1 */
+  int32_t nkeys;
+  const double* cell_data;   /* [nkeys*ne] */
+  const int64_t* elem_dof;   /* [ne*(dim+1)] dof of species 0 at local vertex a (own compartment) */
+  /* interface + boundary facets */
+  int64_t nf;
+  const int64_t* f_in;       /* inside element */
+  const int64_t* f_out;      /* outside element or -1 */
+  const int32_t* f_lin;      /* local index of the vertex opposite to the facet in f_in */
+  const int32_t* f_lout;
+} OrcMesh;
+
+enum { K_REACTION = 0, K_REACTION_JAC, K_STORAGE, K_STORAGE_JAC, K_DIFF, K_DIFF_JAC, K_OUTFLOW,
+       K_OUTFLOW_JAC, K_NKIND };
+
+typedef struct {
+  int32_t ncomp, nspec;
+  const int32_t* spec_comp;     /* [nspec] */
+  const int32_t* spec_local;    /* [nspec] index inside its compartment */
+  const int32_t* comp_ptr;      /* [ncomp+1] */
+  const int32_t* comp_spec;     /* species ids grouped by compartment */
+  int32_t nterms;
+  const int32_t* terms;         /* [nterms*5] kind,i,j,k,prog ; sorted by (i,kind) */
+  const int32_t* tptr;          /* [nspec*K_NKIND+1] */
+  const int32_t* prog_ptr;      /* [nprog+1] in ints */
+  const int32_t* code;
+  const int32_t* const_ptr;     /* [nprog] */
+  const double* consts;
+  int32_t nslots, spec_base;
+} OrcModel;
+
+enum { SLOT_TIME = 0, SLOT_INTFAC, SLOT_ENTVOL, SLOT_INVOL, SLOT_INBND, SLOT_INSKEL, SLOT_POS = 6,
+       SLOT_NORMAL = 9, SLOT_CELL = 12 };
+
+/* ---------------------------------------------------------------- expression VM */
+static double f1(int id, double a) {
+  switch (id) {
+    case 0: return sqrt(a); case 1: return exp(a); case 2: return log(a); case 3: return sin(a);
+    case 4: return cos(a); case 5: return tan(a); case 6: return fabs(a); case 7: return floor(a);
+    case 8: return ceil(a); case 9: return tanh(a); case 10: return sinh(a); case 11: return cosh(a);
+    case 12: return asin(a); case 13: return acos(a); case 14: return atan(a); case 15: return log10(a);
+    case 16: return log2(a); case 17: return (a > 0) - (a < 0); case 18: return exp2(a);
+    case 19: return round(a);
+  }
+  return NAN;
+}
+static double f2(int id, double a, double b) {
+  switch (id) {
+    case 0: return a < b ? a : b; case 1: return a > b ? a : b; case 2: return atan2(a, b);
+    case 3: return pow(a, b);
+  }
+  return NAN;
+}
+
+double orc_eval(const int32_t* code, int n, const double* consts, const double* ctx) {
+  double st[64];
+  int sp = 0;
+  for (int pc = 0; pc < n; pc += 2) {
+    int op = code[pc], arg = code[pc + 1];
+    switch (op) {
+      case 0: st[sp++] = consts[arg]; break;
+      case 1: st[sp++] = ctx[arg]; break;
+      case 2: sp--; st[sp - 1] += st[sp]; break;
+      case 3: sp--; st[sp - 1] -= st[sp]; break;
+      case 4: sp--; st[sp - 1] *= st[sp]; break;
+      case 5: sp--; st[sp - 1] /= st[sp]; break;
+      case 6: sp--; st[sp - 1] = pow(st[sp - 1], st[sp]); break;
+      case 7: st[sp - 1] = -st[sp - 1]; break;
+      case 8: sp--; st[sp - 1] = st[sp - 1] < st[sp]; break;
+      case 9: sp--; st[sp - 1] = st[sp - 1] > st[sp]; break;
+      case 10: sp--; st[sp - 1] = st[sp - 1] <= st[sp]; break;
+      case 11: sp--; st[sp - 1] = st[sp - 1] >= st[sp]; break;
+      case 12: sp--; st[sp - 1] = st[sp - 1] == st[sp]; break;
+      case 13: sp--; st[sp - 1] = st[sp - 1] != st[sp]; break;
+      case 14: sp--; st[sp - 1] = (st[sp - 1] != 0.0) && (st[sp] != 0.0); break;
+      case 15: sp--; st[sp - 1] = (st[sp - 1] != 0.0) || (st[sp] != 0.0); break;
+      case 16: st[sp - 1] = (st[sp - 1] == 0.0); break;
+      case 17: sp -= 2; st[sp - 1] = (st[sp - 1] != 0.0) ? st[sp] : st[sp + 1]; break;
+      case 18: st[sp - 1] = f1(arg, st[sp - 1]); break;
+      case 19: sp--; st[sp - 1] = f2(arg, st[sp - 1], st[sp]); break;
+      case 20: sp--; st[sp - 1] = fmod(st[sp - 1], st[sp]); break;
+    }
+  }
+  return st[0];
+}
+
+static inline double run(const OrcModel* P, int prog, const double* ctx) {
+  return orc_eval(P->code + P->prog_ptr[prog], P->prog_ptr[prog + 1] - P->prog_ptr[prog],
+                  P->consts + P->const_ptr[prog], ctx);
+}
+
+void orc_eval_many(const OrcModel* P, int prog, int64_t n, const double* ctxs, double* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = run(P, prog, ctxs + i * P->nslots);
+}
+
+/* ---------------------------------------------------------------- quadrature (order 2) */
+#define QA 0.585410196624968515
+#define QB 0.138196601125010504
+static const double Q2[3][2] = {{4. / 6., 1. / 6.}, {1. / 6., 4. / 6.}, {1. / 6., 1. / 6.}};
+static const double Q3[4][3] = {{QA, QB, QB}, {QB, QA, QB}, {QB, QB, QA}, {QB, QB, QB}};
+static const double Q1[2] = {0.5 - 0.28867513459481288225, 0.5 + 0.28867513459481288225};
+
+static int quad(int dim, double pts[][3], double* wts) {
+  if (dim == 1) { for (int q = 0; q < 2; ++q) { pts[q][0] = Q1[q]; wts[q] = 0.5; } return 2; }
+  if (dim == 2) { for (int q = 0; q < 3; ++q) { pts[q][0] = Q2[q][0]; pts[q][1] = Q2[q][1]; wts[q] = 1. / 6.; } return 3; }
+  for (int q = 0; q < 4; ++q) { for (int k = 0; k < 3; ++k) pts[q][k] = Q3[q][k]; wts[q] = 1. / 24.; }
+  return 4;
+}
+
+/* P1 reference basis at xi: phi0 = 1 - sum xi, phi_i = xi_{i-1} */
+static void p1(int dim, const double* xi, double* phi) {
+  double s = 0;
+  for (int k = 0; k < dim; ++k) { phi[k + 1] = xi[k]; s += xi[k]; }
+  phi[0] = 1.0 - s;
+}
+
+/* geometry of a simplex: corners X[nd][dim]; returns det, fills grads[nd][dim] (global gradients) */
+static double simplex_geo(int dim, double X[4][3], double G[4][3]) {
+  double B[3][3], Bi[3][3], det;
+  for (int k = 0; k < dim; ++k) for (int c = 0; c < dim; ++c) B[c][k] = X[k + 1][c] - X[0][c];
+  /* x = x0 + B xi ;  grad phi_a = B^{-T} grad_ref phi_a */
+  if (dim == 2) {
+    det = B[0][0] * B[1][1] - B[0][1] * B[1][0];
+    Bi[0][0] = B[1][1] / det; Bi[0][1] = -B[0][1] / det;
+    Bi[1][0] = -B[1][0] / det; Bi[1][1] = B[0][0] / det;
+  } else {
+    double c00 = B[1][1] * B[2][2] - B[1][2] * B[2][1];
+    double c01 = B[1][2] * B[2][0] - B[1][0] * B[2][2];
+    double c02 = B[1][0] * B[2][1] - B[1][1] * B[2][0];
+    det = B[0][0] * c00 + B[0][1] * c01 + B[0][2] * c02;
+    Bi[0][0] = c00 / det; Bi[1][0] = c01 / det; Bi[2][0] = c02 / det;
+    Bi[0][1] = (B[0][2] * B[2][1] - B[0][1] * B[2][2]) / det;
+    Bi[1][1] = (B[0][0] * B[2][2] - B[0][2] * B[2][0]) / det;
+    Bi[2][1] = (B[0][1] * B[2][0] - B[0][0] * B[2][1]) / det;
+    Bi[0][2] = (B[0][1] * B[1][2] - B[0][2] * B[1][1]) / det;
+    Bi[1][2] = (B[0][2] * B[1][0] - B[0][0] * B[1][2]) / det;
+    Bi[2][2] = (B[0][0] * B[1][1] - B[0][1] * B[1][0]) / det;
+  }
+  /* grad phi_{k+1} = row k of B^{-1}; grad phi_0 = -sum */
+  for (int c = 0; c < dim; ++c) G[0][c] = 0;
+  for (int k = 0; k < dim; ++k)
+    for (int c = 0; c < dim; ++c) { G[k + 1][c] = Bi[k][c]; G[0][c] -= Bi[k][c]; }
+  return det;
+}
+
+static inline void atomic_add(double* p, double v, int par) {
+  if (par) {
+#pragma omp atomic
+    *p += v;
+  } else
+    *p += v;
+}
+
+/* ---------------------------------------------------------------- sinks for Jacobian entries */
+typedef struct {
+  int mode;                 /* 0: CSR add, 1: y += v * z[col]  (PseudoJacobian) */
+  const int64_t* rowptr; const int32_t* colidx; double* vals;
+  const double* z; double* y;
+  int par;
+} Sink;
+
+static inline void sink_add(const Sink* S, int64_t row, int64_t col, double v) {
+  if (S->mode == 1) { atomic_add(&S->y[row], v * S->z[col], S->par); return; }
+  int64_t lo = S->rowptr[row], hi = S->rowptr[row + 1] - 1;
+  while (lo <= hi) {
+    int64_t mid = (lo + hi) >> 1;
+    int32_t c = S->colidx[mid];
+    if (c == col) { atomic_add(&S->vals[mid], v, S->par); return; }
+    if (c < col) lo = mid + 1; else hi = mid - 1;
+  }
+  abort(); /* entry outside the pattern: pattern builder and Jacobian disagree */
+}
+
+#define TERMS(P, g, kind, t0, t1) \
+  int t0 = (P)->tptr[(g) * K_NKIND + (kind)], t1 = (P)->tptr[(g) * K_NKIND + (kind) + 1]
+
+static void load_element(const OrcMesh* M, int64_t e, double X[4][3]) {
+  int nd = M->dim + 1;
+  for (int a = 0; a < nd; ++a) {
+    int64_t v = M->elems[e * nd + a];
+    for (int c = 0; c < 3; ++c) X[a][c] = c < M->dim ? M->coords[v * M->dim + c] : 0.0;
+  }
+}
+
+static void set_cell(const OrcMesh* M, int64_t e, double* ctx) {
+  for (int k = 0; k < M->nkeys; ++k) ctx[SLOT_CELL + k] = M->cell_data[(int64_t)k * M->ne + e];
+}
+
+/* values + gradients of all species of compartment c at a point with basis values phi */
+static void eval_fields(const OrcMesh* M, const OrcModel* P, int c, int64_t e, const double* x,
+                        const double* phi, double G[4][3], double* ctx) {
+  int nd = M->dim + 1;
+  for (int t = P->comp_ptr[c]; t < P->comp_ptr[c + 1]; ++t) {
+    int g = P->comp_spec[t], s = P->spec_local[g];
+    double val = 0, gr[3] = {0, 0, 0};
+    for (int a = 0; a < nd; ++a) {
+      double xa = x[M->elem_dof[e * nd + a] + s];
+      val += xa * phi[a];
+      for (int k = 0; k < M->dim; ++k) gr[k] += xa * G[a][k];
+    }
+    double* slot = ctx + P->spec_base + 4 * g;
+    slot[0] = val; slot[1] = gr[0]; slot[2] = gr[1]; slot[3] = gr[2];
+  }
+}
+
+/* ---------------------------------------------------------------- volume residual
+ * form 0 = stiffness (reaction, diffusion), 1 = mass (storage).  r += w * R_form(x)          */
+void orc_residual_volume(const OrcMesh* M, const OrcModel* P, int form, double time, double w,
+                         const double* x, double* r, int par) {
+  const int dim = M->dim, nd = dim + 1;
+  double qp[4][3], qw[4];
+  const int nq = quad(dim, qp, qw);
+  double fact = dim == 2 ? 2.0 : 6.0;
+#pragma omp parallel if (par)
+  {
+    double* ctx = (double*)calloc(P->nslots, sizeof(double));
+#pragma omp for schedule(static)
+    for (int64_t e = 0; e < M->ne; ++e) {
+      int c = M->elem_comp[e];
+      if (c < 0) continue;
+      double X[4][3], G[4][3], loc[16][4];
+      load_element(M, e, X);
+      double det = simplex_geo(dim, X, G);
+      ctx[SLOT_TIME] = time; ctx[SLOT_ENTVOL] = fabs(det) / fact; ctx[SLOT_INVOL] = 1;
+      set_cell(M, e, ctx);
+      int ns = P->comp_ptr[c + 1] - P->comp_ptr[c];
+      for (int s = 0; s < ns; ++s) for (int a = 0; a < nd; ++a) loc[s][a] = 0;
+      for (int q = 0; q < nq; ++q) {
+        double phi[4];
+        p1(dim, qp[q], phi);
+        for (int k = 0; k < 3; ++k) {
+          double p = 0;
+          for (int a = 0; a < nd; ++a) p += phi[a] * X[a][k];
+          ctx[SLOT_POS + k] = p;
+        }
+        double factor = qw[q] * fabs(det);
+        ctx[SLOT_INTFAC] = factor;
+        eval_fields(M, P, c, e, x, phi, G, ctx);
+        for (int t = P->comp_ptr[c]; t < P->comp_ptr[c + 1]; ++t) {
+          int g = P->comp_spec[t], s = P->spec_local[g];
+          double scalar = 0, flux[3] = {0, 0, 0};
+          if (form == 0) {
+            TERMS(P, g, K_REACTION, r0, r1);
+            if (r1 > r0) scalar = -run(P, P->terms[r0 * 5 + 4], ctx);
+            TERMS(P, g, K_DIFF, d0, d1);
+            for (int d = d0; d < d1; ++d) {
+              int j = P->terms[d * 5 + 2];
+              double D = run(P, P->terms[d * 5 + 4], ctx);
+              const double* gj = ctx + P->spec_base + 4 * j + 1;
+              for (int k = 0; k < dim; ++k) flux[k] -= D * gj[k];
+            }
+          } else {
+            TERMS(P, g, K_STORAGE, s0, s1);
+            if (s1 > s0) scalar += ctx[P->spec_base + 4 * g] * run(P, P->terms[s0 * 5 + 4], ctx);
+          }
+          for (int a = 0; a < nd; ++a) {
+            double fl = 0;
+            for (int k = 0; k < dim; ++k) fl += flux[k] * G[a][k];
+            loc[s][a] += (scalar * phi[a] - fl) * factor;
+          }
+        }
+      }
+      for (int s = 0; s < ns; ++s)
+        for (int a = 0; a < nd; ++a) atomic_add(&r[M->elem_dof[e * nd + a] + s], w * loc[s][a], par);
+      ctx[SLOT_INVOL] = 0;
+    }
+    free(ctx);
+  }
+}
+
+/* ---------------------------------------------------------------- volume Jacobian (analytic)   */
+static void jacobian_volume(const OrcMesh* M, const OrcModel* P, int form, double time, double w,
+                            const double* x, const Sink* S) {
+  const int dim = M->dim, nd = dim + 1;
+  double qp[4][3], qw[4];
+  const int nq = quad(dim, qp, qw);
+  double fact = dim == 2 ? 2.0 : 6.0;
+#pragma omp parallel if (S->par)
+  {
+    double* ctx = (double*)calloc(P->nslots, sizeof(double));
+#pragma omp for schedule(static)
+    for (int64_t e = 0; e < M->ne; ++e) {
+      int c = M->elem_comp[e];
+      if (c < 0) continue;
+      double X[4][3], G[4][3];
+      load_element(M, e, X);
+      double det = simplex_geo(dim, X, G);
+      ctx[SLOT_TIME] = time; ctx[SLOT_ENTVOL] = fabs(det) / fact; ctx[SLOT_INVOL] = 1;
+      set_cell(M, e, ctx);
+      const int64_t* ed = M->elem_dof + e * nd;
+      for (int q = 0; q < nq; ++q) {
+        double phi[4];
+        p1(dim, qp[q], phi);
+        for (int k = 0; k < 3; ++k) {
+          double p = 0;
+          for (int a = 0; a < nd; ++a) p += phi[a] * X[a][k];
+          ctx[SLOT_POS + k] = p;
+        }
+        double factor = qw[q] * fabs(det);
+        ctx[SLOT_INTFAC] = factor;
+        eval_fields(M, P, c, e, x, phi, G, ctx);
+        for (int t = P->comp_ptr[c]; t < P->comp_ptr[c + 1]; ++t) {
+          int g = P->comp_spec[t], si = P->spec_local[g];
+          if (form == 0) {
+            TERMS(P, g, K_REACTION, r0, r1);
+            if (r1 > r0) {
+              TERMS(P, g, K_REACTION_JAC, j0, j1);
+              for (int jt = j0; jt < j1; ++jt) {
+                int wrt = P->terms[jt * 5 + 2], sj = P->spec_local[wrt];
+                double jac = run(P, P->terms[jt * 5 + 4], ctx);
+                for (int a = 0; a < nd; ++a)
+                  for (int b = 0; b < nd; ++b)
+                    sink_add(S, ed[a] + si, ed[b] + sj, w * (-jac * phi[a] * phi[b] * factor));
+              }
+            }
+            TERMS(P, g, K_DIFF, d0, d1);
+            for (int d = d0; d < d1; ++d) {
+              int wrt = P->terms[d * 5 + 2], sj = P->spec_local[wrt];
+              double D = run(P, P->terms[d * 5 + 4], ctx);
+              for (int a = 0; a < nd; ++a) {
+                for (int b = 0; b < nd; ++b) {
+                  double v = 0;
+                  for (int k = 0; k < dim; ++k) v += D * G[a][k] * G[b][k];
+                  sink_add(S, ed[a] + si, ed[b] + sj, w * v * factor);
+                }
+              }
+              /* non-linear diffusion d D_ij / d u_k -- literal restatement incl. the index
+                 transposition and the use of grad u_k (local_operator.hh:688-700) */
+              TERMS(P, g, K_DIFF_JAC, e0, e1);
+              for (int et = e0; et < e1; ++et) {
+                if (P->terms[et * 5 + 2] != wrt) continue;
+                int kk = P->terms[et * 5 + 3], sk = P->spec_local[kk];
+                double dD = run(P, P->terms[et * 5 + 4], ctx);
+                const double* gk = ctx + P->spec_base + 4 * kk + 1;
+                for (int a = 0; a < nd; ++a)
+                  for (int b = 0; b < nd; ++b) {
+                    double v = 0;
+                    for (int k = 0; k < dim; ++k) v += dD * gk[k] * G[b][k];
+                    sink_add(S, ed[a] + si, ed[b] + sk, w * phi[a] * v * factor);
+                  }
+              }
+            }
+          } else {
+            TERMS(P, g, K_STORAGE, s0, s1);
+            if (s1 > s0) {
+              double stg = run(P, P->terms[s0 * 5 + 4], ctx);
+              for (int a = 0; a < nd; ++a)
+                for (int b = 0; b < nd; ++b)
+                  sink_add(S, ed[a] + si, ed[b] + si, w * stg * phi[a] * phi[b] * factor);
+              TERMS(P, g, K_STORAGE_JAC, j0, j1);
+              for (int jt = j0; jt < j1; ++jt) {
+                int wrt = P->terms[jt * 5 + 2], sj = P->spec_local[wrt];
+                double jac = run(P, P->terms[jt * 5 + 4], ctx);
+                double val = ctx[P->spec_base + 4 * g];
+                for (int a = 0; a < nd; ++a)
+                  for (int b = 0; b < nd; ++b)
+                    sink_add(S, ed[a] + si, ed[b] + sj, w * jac * val * phi[a] * phi[b] * factor);
+              }
+            }
+          }
+        }
+      }
+      ctx[SLOT_INVOL] = 0;
+    }
+    free(ctx);
+  }
+}
+
+void orc_jacobian_volume(const OrcMesh* M, const OrcModel* P, int form, double time, double w,
+                         const double* x, const int64_t* rowptr, const int32_t* colidx,
+                         double* vals, int par) {
+  Sink S = {0, rowptr, colidx, vals, 0, 0, par};
+  jacobian_volume(M, P, form, time, w, x, &S);
+}
+
+/* matrix-free y += w * J_form(x) z  (local_operator.hh:510-524 via PseudoJacobian) */
+void orc_jacobian_apply_volume(const OrcMesh* M, const OrcModel* P, int form, double time,
+                               double w, const double* x, const double* z, double* y, int par) {
+  Sink S = {1, 0, 0, 0, z, y, par};
+  jacobian_volume(M, P, form, time, w, x, &S);
+}
+
+/* numerical (finite difference) volume Jacobian, local_operator.hh:713-765:
+ * delta = eps (1 + |x_j|), one-sided, column by column on the element's local vector.  */
+void orc_jacobian_volume_numerical(const OrcMesh* M, const OrcModel* P, int form, double time,
+                                   double w, double eps, const double* x, const int64_t* rowptr,
+                                   const int32_t* colidx, double* vals) {
+  const int dim = M->dim, nd = dim + 1;
+  Sink S = {0, rowptr, colidx, vals, 0, 0, 0};
+  /* element-local evaluation through a one-element sub-mesh view */
+  for (int64_t e = 0; e < M->ne; ++e) {
+    int c = M->elem_comp[e];
+    if (c < 0) continue;
+    int ns = P->comp_ptr[c + 1] - P->comp_ptr[c];
+    OrcMesh one = *M;
+    int64_t ldof[4];
+    double xl[64], down[64], up[64];
+    for (int a = 0; a < nd; ++a) {
+      ldof[a] = (int64_t)a * ns;
+      for (int s = 0; s < ns; ++s) xl[a * ns + s] = x[M->elem_dof[e * nd + a] + s];
+    }
+    one.ne = 1; one.elems = M->elems + e * nd; one.elem_comp = M->elem_comp + e;
+    one.elem_dof = ldof; one.nf = 0;
+    /* cell data of element e must be seen at local index 0 */
+    double cd[32];
+    for (int k = 0; k < M->nkeys; ++k) cd[k] = M->cell_data[(int64_t)k * M->ne + e];
+    one.cell_data = cd;
+    memset(down, 0, sizeof(down));
+    orc_residual_volume(&one, P, form, time, 1.0, xl, down, 0);
+    for (int b = 0; b < nd; ++b)
+      for (int sj = 0; sj < ns; ++sj) {
+        int col = b * ns + sj;
+        double keep = xl[col], delta = eps * (1.0 + fabs(keep));
+        xl[col] += delta;
+        memset(up, 0, sizeof(up));
+        orc_residual_volume(&one, P, form, time, 1.0, xl, up, 0);
+        for (int a = 0; a < nd; ++a)
+          for (int si = 0; si < ns; ++si) {
+            int row = a * ns + si;
+            double v = (up[row] - down[row]) / delta;
+            if (v != 0.0 || 1) {
+              /* only entries inside the pattern are stored (implicit build mode drops none in the
+                 reference because the FD Jacobian is dense per element; we mirror by skipping
+                 exact zeros outside the pattern) */
+              int64_t R = M->elem_dof[e * nd + a] + si, C = M->elem_dof[e * nd + b] + sj;
+              int64_t lo = rowptr[R], hi = rowptr[R + 1] - 1, hit = -1;
+              while (lo <= hi) {
+                int64_t mid = (lo + hi) >> 1;
+                if (colidx[mid] == C) { hit = mid; break; }
+                if (colidx[mid] < C) lo = mid + 1; else hi = mid - 1;
+              }
+              if (hit >= 0) vals[hit] += w * v;
+              else if (v != 0.0) abort();
+            }
+          }
+        xl[col] = keep;
+      }
+  }
+  (void)S;
+}
+
+/* ---------------------------------------------------------------- skeleton / boundary
+ * Facet f between e_i (compartment ci) and e_o (co != ci), or boundary facet (e_o = -1).
+ * Disjoint compartments: a species of ci fires outflow.<co> on an interface facet and
+ * outflow.<ci> on a boundary facet (local_operator.hh:839-852).                               */
+typedef struct {
+  double Xi[4][3], Gi[4][3], Xo[4][3], Go[4][3];
+  double area, normal[3];
+  int fv_i[3], fv_o[3]; /* local indices of the facet vertices in e_i / matching ones in e_o */
+} FacetGeo;
+
+static void facet_geo(const OrcMesh* M, int64_t f, FacetGeo* F) {
+  const int dim = M->dim, nd = dim + 1;
+  int64_t ei = M->f_in[f], eo = M->f_out[f];
+  int mi = M->f_lin[f];
+  load_element(M, ei, F->Xi);
+  simplex_geo(dim, F->Xi, F->Gi);
+  int n = 0;
+  for (int a = 0; a < nd; ++a) if (a != mi) F->fv_i[n++] = a;
+  if (eo >= 0) {
+    load_element(M, eo, F->Xo);
+    simplex_geo(dim, F->Xo, F->Go);
+    for (int k = 0; k < dim; ++k) {
+      int32_t gv = M->elems[ei * nd + F->fv_i[k]];
+      F->fv_o[k] = -1;
+      for (int a = 0; a < nd; ++a) if (M->elems[eo * nd + a] == gv) F->fv_o[k] = a;
+    }
+  }
+  /* outer unit normal of the inside element: -grad(phi_m)/|grad(phi_m)| */
+  double nn = 0;
+  for (int k = 0; k < dim; ++k) nn += F->Gi[mi][k] * F->Gi[mi][k];
+  nn = sqrt(nn);
+  for (int k = 0; k < 3; ++k) F->normal[k] = k < dim ? -F->Gi[mi][k] / nn : 0.0;
+  if (dim == 2) {
+    double dx = F->Xi[F->fv_i[1]][0] - F->Xi[F->fv_i[0]][0], dy = F->Xi[F->fv_i[1]][1] - F->Xi[F->fv_i[0]][1];
+    F->area = sqrt(dx * dx + dy * dy);
+  } else {
+    double u[3], v[3];
+    for (int k = 0; k < 3; ++k) {
+      u[k] = F->Xi[F->fv_i[1]][k] - F->Xi[F->fv_i[0]][k];
+      v[k] = F->Xi[F->fv_i[2]][k] - F->Xi[F->fv_i[0]][k];
+    }
+    double cx = u[1] * v[2] - u[2] * v[1], cy = u[2] * v[0] - u[0] * v[2], cz = u[0] * v[1] - u[1] * v[0];
+    F->area = 0.5 * sqrt(cx * cx + cy * cy + cz * cz);
+  }
+}
+
+/* fill ctx with every species of both sides at the facet point with facet barycentrics lam */
+static void facet_fields(const OrcMesh* M, const OrcModel* P, int64_t f, const FacetGeo* F,
+                         const double* lam, const double* x, double* ctx) {
+  const int dim = M->dim, nd = dim + 1;
+  for (int side = 0; side < 2; ++side) {
+    int64_t e = side == 0 ? M->f_in[f] : M->f_out[f];
+    if (e < 0) continue;
+    int c = M->elem_comp[e];
+    if (c < 0) continue;
+    double phi[4] = {0, 0, 0, 0};
+    const int* fv = side == 0 ? F->fv_i : F->fv_o;
+    for (int k = 0; k < dim; ++k) phi[fv[k]] = lam[k];
+    double(*G)[3] = side == 0 ? (double(*)[3])F->Gi : (double(*)[3])F->Go;
+    eval_fields(M, P, c, e, x, phi, G, ctx);
+    (void)nd;
+  }
+}
+
+static int facet_quad(int dim, double lam[][3], double* wts) {
+  /* rule of order 2 on the (dim-1)-simplex, expressed in facet barycentric coordinates */
+  if (dim == 2) {
+    for (int q = 0; q < 2; ++q) { lam[q][0] = 1.0 - Q1[q]; lam[q][1] = Q1[q]; wts[q] = 0.5; }
+    return 2;
+  }
+  for (int q = 0; q < 3; ++q) {
+    lam[q][0] = 1.0 - Q2[q][0] - Q2[q][1]; lam[q][1] = Q2[q][0]; lam[q][2] = Q2[q][1];
+    wts[q] = 1. / 6.;
+  }
+  return 3;
+}
+
+/* mode 0: residual r += w*T ; mode 1: jacobian into sink */
+static void skeleton(const OrcMesh* M, const OrcModel* P, double time, double w, const double* x,
+                     double* r, const Sink* S, int mode) {
+  const int dim = M->dim, nd = dim + 1;
+  double lam[3][3], qw[3];
+  const int nq = facet_quad(dim, lam, qw);
+  double* ctx = (double*)calloc(P->nslots, sizeof(double));
+  for (int64_t f = 0; f < M->nf; ++f) {
+    int64_t ei = M->f_in[f], eo = M->f_out[f];
+    int ci = M->elem_comp[ei], co = eo >= 0 ? M->elem_comp[eo] : -1;
+    if (eo >= 0 && ci == co) continue;
+    FacetGeo F;
+    facet_geo(M, f, &F);
+    double ie = dim == 2 ? F.area : 2.0 * F.area; /* integrationElement of the facet map */
+    for (int side = 0; side < 2; ++side) {
+      int64_t e = side == 0 ? ei : eo;
+      int cs = side == 0 ? ci : co;            /* own compartment */
+      int ct = eo >= 0 ? (side == 0 ? co : ci) : ci; /* outflow target compartment */
+      if (e < 0 || cs < 0 || ct < 0) continue;
+      const int* fv = side == 0 ? F.fv_i : F.fv_o;
+      for (int q = 0; q < nq; ++q) {
+        memset(ctx, 0, sizeof(double) * P->nslots);
+        ctx[SLOT_TIME] = time; ctx[SLOT_ENTVOL] = F.area;
+        ctx[SLOT_INBND] = eo < 0; ctx[SLOT_INSKEL] = eo >= 0;
+        for (int k = 0; k < M->nkeys; ++k) ctx[SLOT_CELL + k] = M->cell_data[(int64_t)k * M->ne + e];
+        for (int k = 0; k < 3; ++k) {
+          double p = 0;
+          for (int a = 0; a < dim; ++a) p += lam[q][a] * F.Xi[F.fv_i[a]][k];
+          ctx[SLOT_POS + k] = p;
+          ctx[SLOT_NORMAL + k] = side == 0 ? F.normal[k] : -F.normal[k];
+        }
+        double factor = qw[q] * ie;
+        ctx[SLOT_INTFAC] = factor;
+        facet_fields(M, P, f, &F, lam[q], x, ctx);
+        for (int t = P->comp_ptr[cs]; t < P->comp_ptr[cs + 1]; ++t) {
+          int g = P->comp_spec[t], si = P->spec_local[g];
+          TERMS(P, g, K_OUTFLOW, o0, o1);
+          for (int ot = o0; ot < o1; ++ot) {
+            if (P->terms[ot * 5 + 2] != ct) continue;
+            if (mode == 0) {
+              double T = run(P, P->terms[ot * 5 + 4], ctx);
+              for (int k = 0; k < dim; ++k)
+                r[M->elem_dof[e * nd + fv[k]] + si] += w * T * lam[q][k] * factor;
+            } else {
+              TERMS(P, g, K_OUTFLOW_JAC, j0, j1);
+              for (int jt = j0; jt < j1; ++jt) {
+                if (P->terms[jt * 5 + 2] != ct) continue;
+                int wrt = P->terms[jt * 5 + 3], sj = P->spec_local[wrt], cw = P->spec_comp[wrt];
+                double jac = run(P, P->terms[jt * 5 + 4], ctx);
+                /* block choice: the side where the wrt species lives (local_operator.hh:1129-1131) */
+                int64_t ew; const int* fw;
+                if (cw == cs) { ew = e; fw = fv; }
+                else if (eo >= 0 && cw == (side == 0 ? co : ci)) { ew = side == 0 ? eo : ei; fw = side == 0 ? F.fv_o : F.fv_i; }
+                else continue;
+                for (int a = 0; a < dim; ++a)
+                  for (int b = 0; b < dim; ++b)
+                    sink_add(S, M->elem_dof[e * nd + fv[a]] + si, M->elem_dof[ew * nd + fw[b]] + sj,
+                             w * jac * lam[q][a] * lam[q][b] * factor);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  free(ctx);
+}
+
+void orc_residual_skeleton(const OrcMesh* M, const OrcModel* P, double time, double w,
+                           const double* x, double* r) {
+  skeleton(M, P, time, w, x, r, 0, 0);
+}
+void orc_jacobian_skeleton(const OrcMesh* M, const OrcModel* P, double time, double w,
+                           const double* x, const int64_t* rowptr, const int32_t* colidx, double* vals) {
+  Sink S = {0, rowptr, colidx, vals, 0, 0, 0};
+  skeleton(M, P, time, w, x, 0, &S, 1);
+}
+void orc_jacobian_apply_skeleton(const OrcMesh* M, const OrcModel* P, double time, double w,
+                                 const double* x, const double* z, double* y) {
+  Sink S = {1, 0, 0, 0, z, y, 0};
+  skeleton(M, P, time, w, x, 0, &S, 1);
+}
+
+/* ---------------------------------------------------------------- linear algebra (dune-istl order) */
+void orc_spmv(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* vals,
+              const double* x, double* y, int par) {
+#pragma omp parallel for schedule(static) if (par)
+  for (int64_t i = 0; i < n; ++i) {
+    double s = 0;
+    for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k) s += vals[k] * x[colidx[k]];
+    y[i] = s;
+  }
+}
+
+static double dot(int64_t n, const double* a, const double* b, int par) {
+  double s = 0;
+#pragma omp parallel for reduction(+ : s) schedule(static) if (par)
+  for (int64_t i = 0; i < n; ++i) s += a[i] * b[i];
+  return s;
+}
+
+/* preconditioner: kind 0 none (Richardson w=1), 1 Jacobi (SeqJac, 1 sweep from v=0: v = w D^-1 d),
+ * 2 BlockJacobi with node blocks of size bs (block_jacobi.hh:46-128 with iterations=1: v = w Dblk^-1 d) */
+typedef struct { int kind, bs; double relax; double* dinv; int64_t n; } Prec;
+
+static void prec_setup(Prec* Pc, int64_t n, const int64_t* rowptr, const int32_t* colidx,
+                       const double* vals) {
+  Pc->n = n;
+  if (Pc->kind == 1) {
+    Pc->dinv = (double*)malloc(sizeof(double) * n);
+    for (int64_t i = 0; i < n; ++i) {
+      double d = 0;
+      for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k) if (colidx[k] == i) d = vals[k];
+      Pc->dinv[i] = 1.0 / d;
+    }
+  } else if (Pc->kind == 2) {
+    int bs = Pc->bs;
+    int64_t nb = n / bs;
+    Pc->dinv = (double*)malloc(sizeof(double) * nb * bs * bs);
+    for (int64_t I = 0; I < nb; ++I) {
+      double A[19 * 19], B[19 * 19];
+      for (int a = 0; a < bs; ++a)
+        for (int b = 0; b < bs; ++b) {
+          double d = 0;
+          int64_t row = I * bs + a, col = I * bs + b;
+          for (int64_t k = rowptr[row]; k < rowptr[row + 1]; ++k) if (colidx[k] == col) d = vals[k];
+          A[a * bs + b] = d; B[a * bs + b] = a == b;
+        }
+      /* Gauss-Jordan with partial pivoting (FieldMatrix::invert, dense_inverse.hh:9-37) */
+      for (int p = 0; p < bs; ++p) {
+        int piv = p;
+        for (int i2 = p + 1; i2 < bs; ++i2) if (fabs(A[i2 * bs + p]) > fabs(A[piv * bs + p])) piv = i2;
+        if (piv != p)
+          for (int j = 0; j < bs; ++j) {
+            double t = A[p * bs + j]; A[p * bs + j] = A[piv * bs + j]; A[piv * bs + j] = t;
+            t = B[p * bs + j]; B[p * bs + j] = B[piv * bs + j]; B[piv * bs + j] = t;
+          }
+        double ip = 1.0 / A[p * bs + p];
+        for (int j = 0; j < bs; ++j) { A[p * bs + j] *= ip; B[p * bs + j] *= ip; }
+        for (int i2 = 0; i2 < bs; ++i2) if (i2 != p) {
+          double fct = A[i2 * bs + p];
+          for (int j = 0; j < bs; ++j) { A[i2 * bs + j] -= fct * A[p * bs + j]; B[i2 * bs + j] -= fct * B[p * bs + j]; }
+        }
+      }
+      memcpy(Pc->dinv + I * bs * bs, B, sizeof(double) * bs * bs);
+    }
+  } else
+    Pc->dinv = 0;
+}
+
+static void prec_apply(const Prec* Pc, const double* d, double* v) {
+  int64_t n = Pc->n;
+  if (Pc->kind == 0) { for (int64_t i = 0; i < n; ++i) v[i] = d[i]; }
+  else if (Pc->kind == 1) { for (int64_t i = 0; i < n; ++i) v[i] = Pc->relax * Pc->dinv[i] * d[i]; }
+  else {
+    int bs = Pc->bs;
+    for (int64_t I = 0; I < n / bs; ++I)
+      for (int a = 0; a < bs; ++a) {
+        double s = 0;
+        for (int b = 0; b < bs; ++b) s += Pc->dinv[I * bs * bs + a * bs + b] * d[I * bs + b];
+        v[I * bs + a] = Pc->relax * s;
+      }
+  }
+}
+
+typedef struct { int32_t iterations_x2; int32_t converged; double reduction; double norm0; } OrcResult;
+
+/* dune-istl BiCGSTABSolver::apply.  On exit x holds the solution; b is consumed. */
+void orc_bicgstab(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* vals,
+                  double* x, double* b, double reduction, int maxit, int prec_kind, int bs,
+                  double relax, int par, OrcResult* res) {
+  Prec Pc = {prec_kind, bs, relax, 0, 0};
+  prec_setup(&Pc, n, rowptr, colidx, vals);
+  double *r = b, *rt = malloc(8 * n), *p = calloc(n, 8), *v = calloc(n, 8), *t = malloc(8 * n),
+         *y = malloc(8 * n);
+  orc_spmv(n, rowptr, colidx, vals, x, t, par);
+  for (int64_t i = 0; i < n; ++i) { r[i] -= t[i]; rt[i] = r[i]; }
+  double norm0 = sqrt(dot(n, r, r, par)), norm = norm0;
+  double rho = 1, alpha = 1, omega = 1, rho_new, h;
+  double it = 0;
+  res->converged = 0; res->norm0 = norm0;
+  if (norm0 < 1e-30) { res->converged = 1; res->iterations_x2 = 0; res->reduction = 0; goto done; }
+  for (it = 0.5; it < maxit; it += 0.5) {
+    rho_new = dot(n, rt, r, par);
+    if (fabs(rho) <= 1e-80 || fabs(omega) <= 1e-80) break;
+    if (it < 1) { for (int64_t i = 0; i < n; ++i) p[i] = r[i]; }
+    else {
+      double beta = (rho_new / rho) * (alpha / omega);
+      for (int64_t i = 0; i < n; ++i) p[i] = r[i] + beta * (p[i] - omega * v[i]);
+    }
+    prec_apply(&Pc, p, y);
+    orc_spmv(n, rowptr, colidx, vals, y, v, par);
+    h = dot(n, rt, v, par);
+    if (fabs(h) < 1e-80) break;
+    alpha = rho_new / h;
+    for (int64_t i = 0; i < n; ++i) { x[i] += alpha * y[i]; r[i] -= alpha * v[i]; }
+    norm = sqrt(dot(n, r, r, par));
+    if (norm < reduction * norm0 || norm < 1e-30) { res->converged = 1; break; }
+    it += 0.5;
+    prec_apply(&Pc, r, y);
+    orc_spmv(n, rowptr, colidx, vals, y, t, par);
+    omega = dot(n, t, r, par) / dot(n, t, t, par);
+    for (int64_t i = 0; i < n; ++i) { x[i] += omega * y[i]; r[i] -= omega * t[i]; }
+    rho = rho_new;
+    norm = sqrt(dot(n, r, r, par));
+    if (norm < reduction * norm0 || norm < 1e-30) { res->converged = 1; break; }
+  }
+  res->iterations_x2 = (int32_t)(2 * it + 0.5);
+  res->reduction = norm / norm0;
+done:
+  free(rt); free(p); free(v); free(t); free(y); free(Pc.dinv);
+}
+
+/* dune-istl CGSolver::apply: preconditioned CG, convergence on ||r||_2 */
+void orc_cg(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* vals, double* x,
+            double* b, double reduction, int maxit, int prec_kind, int bs, double relax, int par,
+            OrcResult* res) {
+  Prec Pc = {prec_kind, bs, relax, 0, 0};
+  prec_setup(&Pc, n, rowptr, colidx, vals);
+  double *r = b, *p = malloc(8 * n), *q = malloc(8 * n);
+  orc_spmv(n, rowptr, colidx, vals, x, q, par);
+  for (int64_t i = 0; i < n; ++i) r[i] -= q[i];
+  double norm0 = sqrt(dot(n, r, r, par)), norm = norm0;
+  res->converged = 0; res->norm0 = norm0; res->iterations_x2 = 0; res->reduction = 1;
+  if (norm0 < 1e-30) { res->converged = 1; res->reduction = 0; goto done; }
+  prec_apply(&Pc, r, p);
+  double rholast = dot(n, p, r, par);
+  int i = 1;
+  for (; i <= maxit; ++i) {
+    orc_spmv(n, rowptr, colidx, vals, p, q, par);
+    double alpha = dot(n, p, q, par);
+    double lambda = rholast / alpha;
+    for (int64_t k = 0; k < n; ++k) { x[k] += lambda * p[k]; r[k] -= lambda * q[k]; }
+    norm = sqrt(dot(n, r, r, par));
+    if (norm < reduction * norm0 || norm < 1e-30) { res->converged = 1; break; }
+    prec_apply(&Pc, r, q);
+    double rho = dot(n, q, r, par);
+    double beta = rho / rholast;
+    for (int64_t k = 0; k < n; ++k) p[k] = q[k] + beta * p[k];
+    rholast = rho;
+  }
+  res->iterations_x2 = 2 * (i <= maxit ? i : maxit);
+  res->reduction = norm / norm0;
+done:
+  free(p); free(q); free(Pc.dinv);
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
