@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Headline benchmark: implicit time stepping of the 3-D two-species Gray-Scott system, CG-P1 on the
+Kuhn (6 tets per cube) split of an n^3 lattice, Newton + BiCGSTAB/Jacobi -- BASELINE.json's metric
+"DOF-updates/s & time steps/s, 3D Gray-Scott" on configs[3] (256^3: 16 974 593 vertices,
+33 949 186 DOFs, 100 663 296 tets).
+
+One "step" = one accepted time step of the reference's step operator (RungeKutta o Newton o
+LinearSolver o instationary operator, dune/copasi/model/make_step_operator.hh:164-444).
+
+  python bench.py --gpus N --steps K --warmup W          (N > 1: launched under torchrun)
+  python bench.py --impl reference ...                   CPU arm: the oracle restatement on the
+                                                         host cores, bounded sample of the workload
+
+Prints ONE JSON line (rank 0).  value = DOFs * K / device time with the state resident in HBM;
+e2e = the same through the host-buffer C-ABI calls (state uploaded before and downloaded after
+every step inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+import cases as K  # noqa: E402
+
+METRIC = "DOF-updates/s (3D Gray-Scott, CG-P1 Kuhn tets, implicit time stepping)"
+
+
+def ini_for(args):
+    over = {
+        "model.time_step_operator.type": args.rk,
+        "model.time_step_operator.linear_solver.type": "BiCGSTAB",
+        "model.time_step_operator.linear_solver.preconditioner.type": args.prec,
+        "model.time_step_operator.linear_solver.matrix_free": "true" if args.matrix_free else "false",
+        "model.time_step_operator.linear_solver.convergence_condition.relative_tolerance": "1e-8",
+        "model.time_step_operator.nonlinear_solver.convergence_condition.relative_tolerance": "1e-8",
+        "model.time_step_operator.nonlinear_solver.dx_inverse_fixed_tolerance": "true",
+        "model.assembly.b200.scheme": args.scheme,
+    }
+    return K.CASES["grayscott3d"].ini_with(**over)
+
+
+def precompile():
+    """Warm the in-tree JIT cache with the bench model (called from __graft_entry__.build())."""
+    import dune_copasi_b200 as D
+    ns = argparse.Namespace(rk="Alexander2", prec="Jacobi", matrix_free=True, scheme="patch")
+    for mf in (True, False):
+        ns.matrix_free = mf
+        D.Model(D.Config(ini_for(ns)), 3).precompile()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(args, steps, warmup, cells):
+    """The oracle restatement (kind "port": the reference itself needs a DUNE stack that is not
+    available) with OpenMP over all host cores, on a bounded sample of the workload."""
+    from oracle import core as ORC, ini as INI, mesh as OMESH
+    cfg = INI.parse_ini(ini_for(args))
+    mesh = OMESH.structured(3, [cells] * 3)
+    om = ORC.Model(cfg, mesh)
+    S = ORC.StepOperator(om, par=1)
+    u = om.initial(0.0)
+    t = 0.0
+    for _ in range(warmup):
+        u, ok = S.apply(u, t, args.dt)
+        t += args.dt
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        u, ok = S.apply(u, t, args.dt)
+        assert ok
+        t += args.dt
+    wall = time.perf_counter() - t0
+    cores = ORC.lib().orc_num_threads()
+    return {"value": om.ndofs * steps / wall, "unit": "DOF-updates/s", "cores": int(cores), "kind": "port",
+            "sample": f"{steps} steps (after {warmup} warm-up) of the same model on a {cells}^3 lattice "
+                      f"({om.ndofs} DOFs), matrix based, OpenMP over {cores} threads",
+            "ms_per_step": 1e3 * wall / steps}, om.ndofs, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, ndofs, wall = cpu_baseline(args, args.steps, args.warmup, args.cpu_cells)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "DOF-updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, args.cpu_cells), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "DOF-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def config_dict(args, cells):
+    return {"workload": f"grayscott3d_p1_kuhn_{cells}^3", "cells": cells, "dt": args.dt, "rk": args.rk,
+            "linear_solver": "BiCGSTAB", "preconditioner": args.prec, "matrix_free": bool(args.matrix_free),
+            "linear_rel_tol": 1e-8, "newton_rel_tol": 1e-8, "assembly": args.scheme,
+            "l2": "inputs larger than L2 (every vector and the mesh exceed 126 MB at the default size)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cells", type=int, default=256)
+    ap.add_argument("--cpu-cells", type=int, default=40)
+    ap.add_argument("--dt", type=float, default=1.0)
+    ap.add_argument("--rk", default="Alexander2")
+    ap.add_argument("--prec", default="Jacobi")
+    ap.add_argument("--scheme", default="patch")
+    ap.add_argument("--matrix-free", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import dune_copasi_b200 as D
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if D.lib().dcb_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- problem
+    cfg = D.Config(ini_for(args))
+    model = D.Model(cfg, 3)
+    t_setup = time.perf_counter()
+    gglobal = D.Grid.structured(3, [args.cells] * 3)
+    nv_global = gglobal.nv
+    ndofs_global = nv_global * 2
+    grid = gglobal.partition(rank, world) if world > 1 else gglobal
+    grid.bind(model)
+    op = D.Operator(model, grid)
+    comm = None
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.tensor(list(D.Comm.unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        comm = D.Comm(bytes(uid.cpu().tolist()), rank, world, op)
+        del gglobal
+    st = D.Stepper(op, cfg, comm)
+    u0 = grid.interpolate(model, 0.0)
+    st.set_state(u0, 0.0)
+    t_setup = time.perf_counter() - t_setup
+    stream = torch.cuda.ExternalStream(op.stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e):
+        """-> device ms for nsteps (max over ranks)"""
+        u_host = None
+        if e2e:
+            u_host, _ = st.get_state()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(nsteps):
+            if e2e:
+                st.set_state(u_host, st.time)        # H2D of the step's input through the C ABI
+            ok = st.step(args.dt)
+            if not ok:
+                raise SystemExit("time step failed")
+            if e2e:
+                u_host, _ = st.get_state()           # D2H of the step's result
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        assert st.step(args.dt)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    s0 = st.stats()
+    D.lib().dcb_operator_profile(op.h, 1)
+    ms = timed(args.steps, False)
+    prof = op.profile()
+    D.lib().dcb_operator_profile(op.h, 0)
+    s1 = st.stats()
+    clocks = sampler.stop() if rank == 0 else None
+    e2e = None
+    if not args.no_e2e:
+        ms_e2e = timed(args.steps, True)
+        nbytes = op.ndofs * 8
+        e2e = {"value": ndofs_global * args.steps / (ms_e2e * 1e-3), "unit": "DOF-updates/s",
+               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / args.steps}
+
+    if rank != 0:
+        return
+    d = {k: s1[k] - s0[k] for k in s1}
+    value = ndofs_global * args.steps / (ms * 1e-3)
+    # ---- roofline of the dominant kernel (by accumulated device time in the timed region)
+    peak, peak_src = peaks()
+    nodes, tets = nv_global / world, 6 * args.cells ** 3 / world
+    alg = {  # algorithmic bytes per launch, SURVEY.md 8(d) (per rank)
+        "patch_apply": nodes * (16 * 2 + 8 * 3 + 8 * 2) + tets * 16,
+        "patch_residual": nodes * (16 * 2 + 8 * 3) + tets * 16,
+        "patch_bdiag": nodes * (8 * 2 + 8 * 3 + 8 * 4) + tets * 16,
+        "elem_apply": nodes * (16 * 2 + 8 * 3 + 8 * 2) + tets * 16,
+        "elem_residual": nodes * (16 * 2 + 8 * 3) + tets * 16,
+        "spmv": op.ndofs * 30 * 12 + op.ndofs * 20,
+    }
+    top = max(prof, key=lambda k: prof[k]["ms"]) if prof else None
+    roof = None
+    if top:
+        avg_ms = prof[top]["ms"] / max(1, prof[top]["launches"])
+        ach = alg.get(top, 0.0) / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches": prof[top]["launches"],
+                "share_of_step": prof[top]["ms"] / ms,
+                "breakdown_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}}
+    cb = None
+    if not args.no_cpu_baseline:
+        cb, _, _ = cpu_baseline(args, 1, 1, args.cpu_cells)
+    line = {"metric": METRIC, "value": value, "unit": "DOF-updates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, args.cells),
+            "time_steps_per_s": args.steps / (ms * 1e-3), "dofs": int(ndofs_global), "e2e": e2e,
+            "gpu_launches": int(d["kernel_launches"]), "clocks": clocks, "roofline": roof, "cpu_baseline": cb,
+            "solver_stats": d, "setup_s": t_setup}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,36 @@
+// Multi-GPU plumbing: one process per GPU, NCCL over NVLink/NVSwitch.  The reference has no
+// distributed path (solver/istl/factory/inverse.hh:34-35 throws "Parallel solvers have not been
+// implemented!"), so this is new design: a vertex partition with one layer of ghost elements,
+// owner -> ghost halo updates before every operator application and fp64 all-reduces of the
+// Krylov scalars.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <vector>
+
+#include "util.hpp"
+
+namespace dcb {
+
+struct HaloPlan {
+  // per peer rank: local dof indices to send (owned here, ghost there) and to receive
+  std::vector<int> peers;
+  std::vector<std::vector<int32_t>> send_idx, recv_idx;
+};
+
+struct Communicator {
+  int rank = 0, size = 1;
+  virtual ~Communicator() = default;
+  virtual void allreduce_sum(double* dev, int n, cudaStream_t s) = 0;   // in place
+  virtual void halo_update(double* x, cudaStream_t s) = 0;              // owner -> ghost copies
+  long long launches = 0;
+};
+
+// NCCL-backed communicator; libnccl is resolved at run time (dlopen) so the library loads on
+// hosts without NCCL/driver.  `unique_id` is the 128-byte ncclUniqueId created by rank 0
+// (nccl_unique_id) and distributed by the caller (e.g. torch.distributed broadcast).
+void nccl_unique_id(char out[128]);
+Communicator* nccl_communicator_create(const char unique_id[128], int rank, int size, const HaloPlan& plan);
+
+}  // namespace dcb

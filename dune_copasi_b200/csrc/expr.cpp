@@ -1,0 +1,498 @@
+#include "expr.hpp"
+
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace dcb {
+
+namespace {
+
+struct Tok {
+  enum Kind { Num, Id, Op, End } kind;
+  std::string text;
+  double num = 0;
+};
+
+std::vector<Tok> lex(const std::string& s) {
+  std::vector<Tok> out;
+  size_t i = 0, n = s.size();
+  while (i < n) {
+    char c = s[i];
+    if (isspace((unsigned char)c)) { ++i; continue; }
+    if (isdigit((unsigned char)c) || (c == '.' && i + 1 < n && isdigit((unsigned char)s[i + 1]))) {
+      size_t j = i;
+      while (j < n && isdigit((unsigned char)s[j])) ++j;
+      if (j < n && s[j] == '.') { ++j; while (j < n && isdigit((unsigned char)s[j])) ++j; }
+      if (j < n && (s[j] == 'e' || s[j] == 'E')) {
+        size_t k = j + 1;
+        if (k < n && (s[k] == '+' || s[k] == '-')) ++k;
+        if (k < n && isdigit((unsigned char)s[k])) {
+          while (k < n && isdigit((unsigned char)s[k])) ++k;
+          j = k;
+        }
+      }
+      Tok t{Tok::Num, s.substr(i, j - i)};
+      t.num = std::strtod(t.text.c_str(), nullptr);
+      out.push_back(t);
+      i = j;
+      continue;
+    }
+    if (isalpha((unsigned char)c) || c == '_') {
+      size_t j = i;
+      while (j < n && (isalnum((unsigned char)s[j]) || s[j] == '_')) ++j;
+      out.push_back({Tok::Id, s.substr(i, j - i)});
+      i = j;
+      continue;
+    }
+    static const char* two[] = {"**", "<=", ">=", "==", "!=", "&&", "||"};
+    bool hit = false;
+    for (auto t : two)
+      if (i + 1 < n && s[i] == t[0] && s[i + 1] == t[1]) {
+        out.push_back({Tok::Op, t});
+        i += 2;
+        hit = true;
+        break;
+      }
+    if (hit) continue;
+    if (strchr("+-*/^%<>()?:,&|!", c)) {
+      out.push_back({Tok::Op, std::string(1, c)});
+      ++i;
+      continue;
+    }
+    fail("expression '", s, "': unexpected character '", c, "' at ", i);
+  }
+  out.push_back({Tok::End, ""});
+  return out;
+}
+
+NodeP mk(Op op, std::vector<NodeP> kids) {
+  auto n = std::make_shared<Node>();
+  n->op = op;
+  n->kids = std::move(kids);
+  return n;
+}
+NodeP mk_num(double v) {
+  auto n = std::make_shared<Node>();
+  n->op = Op::Num;
+  n->num = v;
+  return n;
+}
+
+// recursive descent; precedence low->high: ?: | or | and | == != | < > <= >= | + - | * / % | unary | ^
+struct P {
+  std::vector<Tok> t;
+  size_t i = 0;
+  const std::string& src;
+  explicit P(const std::string& s) : t(lex(s)), src(s) {}
+  bool is(const char* v) const { return (t[i].kind == Tok::Op || t[i].kind == Tok::Id) && t[i].text == v; }
+  bool eat(const char* v) { if (is(v)) { ++i; return true; } return false; }
+  void need(const char* v) { if (!eat(v)) fail("expression '", src, "': expected '", v, "' near token ", i); }
+
+  NodeP ternary() {
+    NodeP c = lor();
+    if (eat("?")) {
+      NodeP a = ternary();
+      need(":");
+      NodeP b = ternary();
+      return mk(Op::Sel, {c, a, b});
+    }
+    return c;
+  }
+  NodeP lor() {
+    NodeP a = land();
+    while (is("or") || is("||") || is("|")) { ++i; a = mk(Op::Or, {a, land()}); }
+    return a;
+  }
+  NodeP land() {
+    NodeP a = equality();
+    while (is("and") || is("&&") || is("&")) { ++i; a = mk(Op::And, {a, equality()}); }
+    return a;
+  }
+  NodeP equality() {
+    NodeP a = relational();
+    for (;;) {
+      if (eat("==")) a = mk(Op::Eq, {a, relational()});
+      else if (eat("!=")) a = mk(Op::Ne, {a, relational()});
+      else return a;
+    }
+  }
+  NodeP relational() {
+    NodeP a = additive();
+    for (;;) {
+      if (eat("<=")) a = mk(Op::Le, {a, additive()});
+      else if (eat(">=")) a = mk(Op::Ge, {a, additive()});
+      else if (eat("<")) a = mk(Op::Lt, {a, additive()});
+      else if (eat(">")) a = mk(Op::Gt, {a, additive()});
+      else return a;
+    }
+  }
+  NodeP additive() {
+    NodeP a = term();
+    for (;;) {
+      if (eat("+")) a = mk(Op::Add, {a, term()});
+      else if (eat("-")) a = mk(Op::Sub, {a, term()});
+      else return a;
+    }
+  }
+  NodeP term() {
+    NodeP a = unary();
+    for (;;) {
+      if (eat("*")) a = mk(Op::Mul, {a, unary()});
+      else if (eat("/")) a = mk(Op::Div, {a, unary()});
+      else if (eat("%")) a = mk(Op::Mod, {a, unary()});
+      else return a;
+    }
+  }
+  NodeP unary() {
+    if (eat("-")) return mk(Op::Neg, {unary()});
+    if (eat("+")) return unary();
+    if (eat("!") || eat("not")) return mk(Op::Not, {unary()});
+    return power();
+  }
+  NodeP power() {
+    NodeP b = atom();
+    if (eat("^") || eat("**")) return mk(Op::Pow, {b, unary()});  // right assoc, signed exponent
+    return b;
+  }
+  NodeP atom() {
+    Tok k = t[i++];
+    if (k.kind == Tok::Num) return mk_num(k.num);
+    if (k.kind == Tok::Id) {
+      auto n = std::make_shared<Node>();
+      n->name = k.text;
+      if (eat("(")) {
+        n->op = Op::Call;
+        if (!eat(")")) {
+          for (;;) {
+            n->kids.push_back(ternary());
+            if (eat(")")) break;
+            need(",");
+          }
+        }
+      } else
+        n->op = Op::Var;
+      return n;
+    }
+    if (k.kind == Tok::Op && k.text == "(") {
+      NodeP e = ternary();
+      need(")");
+      return e;
+    }
+    fail("expression '", src, "': unexpected token '", k.text, "'");
+  }
+};
+
+NodeP subst(const NodeP& a, const std::map<std::string, NodeP>& env) {
+  if (a->op == Op::Num) return a;
+  if (a->op == Op::Var) {
+    auto it = env.find(a->name);
+    return it == env.end() ? a : it->second;
+  }
+  auto n = std::make_shared<Node>(*a);
+  for (auto& k : n->kids) k = subst(k, env);
+  return n;
+}
+
+double apply1(const std::string& f, double a, bool* ok) {
+  *ok = true;
+  if (f == "sqrt") return std::sqrt(a);
+  if (f == "exp") return std::exp(a);
+  if (f == "log" || f == "ln") return std::log(a);
+  if (f == "sin") return std::sin(a);
+  if (f == "cos") return std::cos(a);
+  if (f == "tan") return std::tan(a);
+  if (f == "abs") return std::fabs(a);
+  if (f == "floor") return std::floor(a);
+  if (f == "ceil") return std::ceil(a);
+  if (f == "tanh") return std::tanh(a);
+  if (f == "sinh") return std::sinh(a);
+  if (f == "cosh") return std::cosh(a);
+  if (f == "asin") return std::asin(a);
+  if (f == "acos") return std::acos(a);
+  if (f == "atan") return std::atan(a);
+  if (f == "log10") return std::log10(a);
+  if (f == "log2") return std::log2(a);
+  if (f == "exp2") return std::exp2(a);
+  if (f == "round") return std::round(a);
+  if (f == "sgn" || f == "sign") return (a > 0) - (a < 0);
+  *ok = false;
+  return 0;
+}
+
+double apply2(const std::string& f, double a, double b, bool* ok) {
+  *ok = true;
+  if (f == "min") return a < b ? a : b;
+  if (f == "max") return a > b ? a : b;
+  if (f == "atan2") return std::atan2(a, b);
+  if (f == "pow") return std::pow(a, b);
+  *ok = false;
+  return 0;
+}
+
+double binop(Op op, double a, double b) {
+  switch (op) {
+    case Op::Add: return a + b;
+    case Op::Sub: return a - b;
+    case Op::Mul: return a * b;
+    case Op::Div: return a / b;
+    case Op::Pow: return std::pow(a, b);
+    case Op::Mod: return std::fmod(a, b);
+    case Op::Lt: return a < b;
+    case Op::Gt: return a > b;
+    case Op::Le: return a <= b;
+    case Op::Ge: return a >= b;
+    case Op::Eq: return a == b;
+    case Op::Ne: return a != b;
+    case Op::And: return (a != 0.0) && (b != 0.0);
+    case Op::Or: return (a != 0.0) || (b != 0.0);
+    default: fail("internal: not a binary op");
+  }
+}
+
+NodeP fold(const NodeP& a) {
+  // children are already folded
+  bool all = !a->kids.empty();
+  for (auto& k : a->kids) all = all && k->op == Op::Num;
+  if (!all) return a;
+  switch (a->op) {
+    case Op::Neg: return mk_num(-a->kids[0]->num);
+    case Op::Not: return mk_num(a->kids[0]->num == 0.0);
+    case Op::Sel: return a->kids[0]->num != 0.0 ? a->kids[1] : a->kids[2];
+    case Op::Call: {
+      bool ok = false;
+      double v = 0;
+      if (a->kids.size() == 1) v = apply1(a->name, a->kids[0]->num, &ok);
+      else if (a->kids.size() >= 2) {
+        v = a->kids[0]->num;
+        ok = true;
+        for (size_t i = 1; i < a->kids.size() && ok; ++i) v = apply2(a->name, v, a->kids[i]->num, &ok);
+      }
+      return ok ? mk_num(v) : a;
+    }
+    case Op::Num: case Op::Var: return a;
+    default: return mk_num(binop(a->op, a->kids[0]->num, a->kids[1]->num));
+  }
+}
+
+NodeP resolve_rec(const NodeP& a, const ParserContext& ctx, int depth) {
+  if (depth > 16) fail("parser_context functions nested too deep (recursion?)");
+  if (a->op == Op::Num) return a;
+  if (a->op == Op::Var) {
+    auto it = ctx.constants.find(a->name);
+    if (it != ctx.constants.end()) return mk_num(it->second);
+    if (a->name == "no_value") return mk_num(DBL_MAX);
+    if (a->name == "pi") return mk_num(3.14159265358979323846);
+    return a;
+  }
+  auto n = std::make_shared<Node>(*a);
+  for (auto& k : n->kids) k = resolve_rec(k, ctx, depth);
+  if (n->op == Op::Call) {
+    auto it = ctx.functions.find(n->name);
+    if (it != ctx.functions.end()) {
+      const auto& fn = it->second;
+      if (fn.args.size() != n->kids.size())
+        fail("function '", n->name, "' expects ", fn.args.size(), " arguments, got ", n->kids.size());
+      std::map<std::string, NodeP> env;
+      for (size_t i = 0; i < fn.args.size(); ++i) env[fn.args[i]] = n->kids[i];
+      return resolve_rec(subst(parse_expr(fn.body), env), ctx, depth + 1);
+    }
+    if (n->name == "if" && n->kids.size() == 3) return fold(mk(Op::Sel, n->kids));
+  }
+  return fold(n);
+}
+
+std::string num_lit(double v) {
+  if (std::isinf(v)) return v > 0 ? "(1.0/0.0)" : "(-1.0/0.0)";
+  if (std::isnan(v)) return "(0.0/0.0)";
+  char buf[64];
+  snprintf(buf, sizeof buf, "%.17g", v);
+  std::string s = buf;
+  if (s.find_first_of(".eE") == std::string::npos) s += ".0";
+  if (v < 0) s = "(" + s + ")";
+  return s;
+}
+
+bool is_cmp(Op op) {
+  return op == Op::Lt || op == Op::Gt || op == Op::Le || op == Op::Ge || op == Op::Eq ||
+         op == Op::Ne || op == Op::And || op == Op::Or || op == Op::Not;
+}
+
+}  // namespace
+
+ParserContext ParserContext::from_config(const PTree& pc) {
+  ParserContext ctx;
+  for (auto& name : pc.sub_keys()) {
+    const PTree& s = pc.sub(name);
+    std::string type = s.get("type", std::string());
+    if (type == "constant") {
+      ctx.constants[name] = s.get("value", 0.0);
+    } else if (type == "function") {
+      std::string e = s.get("expression", std::string());
+      auto colon = e.find(':');
+      if (colon == std::string::npos) fail("parser_context.", name, ": function needs 'args: body'");
+      Fn fn;
+      std::string head = e.substr(0, colon);
+      size_t p = 0;
+      while (p <= head.size()) {
+        size_t q = head.find(',', p);
+        if (q == std::string::npos) q = head.size();
+        std::string a = trim(head.substr(p, q - p));
+        if (!a.empty()) fn.args.push_back(a);
+        p = q + 1;
+      }
+      fn.body = trim(e.substr(colon + 1));
+      ctx.functions[name] = fn;
+    } else if (!type.empty()) {
+      // interpolation / tiff / random_field context entries are outside the hot path
+      fail("parser_context.", name, ": type '", type, "' is not supported by this build");
+    }
+  }
+  return ctx;
+}
+
+bool expr_is_absent(const std::string& text) {
+  std::string s = trim(text);
+  if (s.empty()) return true;
+  // literal zero: optional sign, zeros with optional point and exponent
+  size_t i = 0;
+  if (s[i] == '+' || s[i] == '-') ++i;
+  while (i < s.size() && isspace((unsigned char)s[i])) ++i;
+  size_t digits = 0;
+  bool dot = false;
+  for (; i < s.size(); ++i) {
+    if (s[i] == '0') ++digits;
+    else if (s[i] == '.' && !dot) dot = true;
+    else break;
+  }
+  if (digits == 0) return false;
+  if (i < s.size() && (s[i] == 'e' || s[i] == 'E')) {
+    ++i;
+    if (i < s.size() && (s[i] == '+' || s[i] == '-')) ++i;
+    size_t d = 0;
+    while (i < s.size() && isdigit((unsigned char)s[i])) { ++i; ++d; }
+    if (d == 0) return false;
+  }
+  return i == s.size();
+}
+
+NodeP parse_expr(const std::string& text) {
+  P p(text);
+  NodeP e = p.ternary();
+  if (p.t[p.i].kind != Tok::End) fail("expression '", text, "': trailing input '", p.t[p.i].text, "'");
+  return e;
+}
+
+NodeP resolve_expr(const NodeP& ast, const ParserContext& ctx) { return resolve_rec(ast, ctx, 0); }
+
+bool is_constant(const NodeP& ast, double* value) {
+  if (ast->op != Op::Num) return false;
+  if (value) *value = ast->num;
+  return true;
+}
+
+void collect_vars(const NodeP& a, std::vector<std::string>& out) {
+  if (a->op == Op::Var) out.push_back(a->name);
+  for (auto& k : a->kids) collect_vars(k, out);
+}
+
+double eval_expr(const NodeP& a, const std::function<double(const std::string&)>& lookup) {
+  switch (a->op) {
+    case Op::Num: return a->num;
+    case Op::Var: return lookup(a->name);
+    case Op::Neg: return -eval_expr(a->kids[0], lookup);
+    case Op::Not: return eval_expr(a->kids[0], lookup) == 0.0;
+    case Op::Sel:
+      return eval_expr(a->kids[0], lookup) != 0.0 ? eval_expr(a->kids[1], lookup)
+                                                  : eval_expr(a->kids[2], lookup);
+    case Op::Call: {
+      bool ok = false;
+      double v = 0;
+      if (a->kids.size() == 1) v = apply1(a->name, eval_expr(a->kids[0], lookup), &ok);
+      else if (a->kids.size() >= 2) {
+        v = eval_expr(a->kids[0], lookup);
+        ok = true;
+        for (size_t i = 1; i < a->kids.size() && ok; ++i)
+          v = apply2(a->name, v, eval_expr(a->kids[i], lookup), &ok);
+      }
+      if (!ok) fail("unknown function '", a->name, "' with ", a->kids.size(), " argument(s)");
+      return v;
+    }
+    default: return binop(a->op, eval_expr(a->kids[0], lookup), eval_expr(a->kids[1], lookup));
+  }
+}
+
+static std::string cond_text(const NodeP& a, const std::function<std::string(const std::string&)>& sym);
+
+std::string to_cuda(const NodeP& a, const std::function<std::string(const std::string&)>& sym) {
+  auto rec = [&](const NodeP& n) { return to_cuda(n, sym); };
+  switch (a->op) {
+    case Op::Num: return num_lit(a->num);
+    case Op::Var: {
+      std::string s = sym(a->name);
+      if (s.empty()) fail("unknown symbol '", a->name, "' in expression");
+      return s;
+    }
+    case Op::Neg: return "(-" + rec(a->kids[0]) + ")";
+    case Op::Add: return "(" + rec(a->kids[0]) + " + " + rec(a->kids[1]) + ")";
+    case Op::Sub: return "(" + rec(a->kids[0]) + " - " + rec(a->kids[1]) + ")";
+    case Op::Mul: return "(" + rec(a->kids[0]) + " * " + rec(a->kids[1]) + ")";
+    case Op::Div: return "(" + rec(a->kids[0]) + " / " + rec(a->kids[1]) + ")";
+    case Op::Mod: return "fmod(" + rec(a->kids[0]) + ", " + rec(a->kids[1]) + ")";
+    case Op::Pow: {
+      double e;
+      if (is_constant(a->kids[1], &e) && e == std::floor(e) && std::fabs(e) <= 8) {
+        // small integer powers become multiplications (pow() costs hundreds of fp64 instructions)
+        int n = (int)std::fabs(e);
+        if (n == 0) return "1.0";
+        std::string b = rec(a->kids[0]);
+        std::string r = "dc_powi<" + std::to_string(n) + ">(" + b + ")";
+        return e < 0 ? "(1.0 / " + r + ")" : r;
+      }
+      if (is_constant(a->kids[1], &e) && e == 0.5) return "sqrt(" + rec(a->kids[0]) + ")";
+      return "pow(" + rec(a->kids[0]) + ", " + rec(a->kids[1]) + ")";
+    }
+    case Op::Sel: return "(" + cond_text(a->kids[0], sym) + " ? " + rec(a->kids[1]) + " : " + rec(a->kids[2]) + ")";
+    case Op::Call: {
+      const std::string& f = a->name;
+      static const std::map<std::string, std::string> one = {
+          {"sqrt", "sqrt"}, {"exp", "exp"}, {"log", "log"}, {"ln", "log"}, {"sin", "sin"}, {"cos", "cos"},
+          {"tan", "tan"}, {"abs", "fabs"}, {"floor", "floor"}, {"ceil", "ceil"}, {"tanh", "tanh"},
+          {"sinh", "sinh"}, {"cosh", "cosh"}, {"asin", "asin"}, {"acos", "acos"}, {"atan", "atan"},
+          {"log10", "log10"}, {"log2", "log2"}, {"exp2", "exp2"}, {"round", "round"},
+          {"sgn", "dc_sgn"}, {"sign", "dc_sgn"}};
+      static const std::map<std::string, std::string> two = {
+          {"min", "dc_min"}, {"max", "dc_max"}, {"atan2", "atan2"}, {"pow", "pow"}};
+      if (a->kids.size() == 1 && one.count(f)) return one.at(f) + "(" + rec(a->kids[0]) + ")";
+      if (a->kids.size() >= 2 && two.count(f)) {
+        std::string r = rec(a->kids[0]);
+        for (size_t i = 1; i < a->kids.size(); ++i) r = two.at(f) + "(" + r + ", " + rec(a->kids[i]) + ")";
+        return r;
+      }
+      fail("unknown function '", f, "' with ", a->kids.size(), " argument(s)");
+    }
+    default:  // comparisons and logic produce 0/1 doubles (ExprTk semantics)
+      return "(" + cond_text(a, sym) + " ? 1.0 : 0.0)";
+  }
+}
+
+// boolean-valued C text of a node used as a condition
+static std::string cond_text(const NodeP& a, const std::function<std::string(const std::string&)>& sym) {
+  auto rec = [&](const NodeP& n) { return to_cuda(n, sym); };
+  auto b = [&](const NodeP& n) { return cond_text(n, sym); };
+  switch (a->op) {
+    case Op::Lt: return "(" + rec(a->kids[0]) + " < " + rec(a->kids[1]) + ")";
+    case Op::Gt: return "(" + rec(a->kids[0]) + " > " + rec(a->kids[1]) + ")";
+    case Op::Le: return "(" + rec(a->kids[0]) + " <= " + rec(a->kids[1]) + ")";
+    case Op::Ge: return "(" + rec(a->kids[0]) + " >= " + rec(a->kids[1]) + ")";
+    case Op::Eq: return "(" + rec(a->kids[0]) + " == " + rec(a->kids[1]) + ")";
+    case Op::Ne: return "(" + rec(a->kids[0]) + " != " + rec(a->kids[1]) + ")";
+    case Op::And: return "(" + b(a->kids[0]) + " && " + b(a->kids[1]) + ")";
+    case Op::Or: return "(" + b(a->kids[0]) + " || " + b(a->kids[1]) + ")";
+    case Op::Not: return "(!" + b(a->kids[0]) + ")";
+    default: return "(" + rec(a) + " != 0.0)";
+  }
+  (void)is_cmp;
+}
+
+}  // namespace dcb

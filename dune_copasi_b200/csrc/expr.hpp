@@ -1,0 +1,57 @@
+// Expression front-end: one tolerant grammar covering what the reference's three parser back-ends
+// (muParser / ExprTk / SymEngine, src/dune/copasi/parser/**) accept in the repo's inis
+// (SURVEY.md App. D).  An expression is parsed once per model, parser_context constants and inline
+// functions (src/dune/copasi/parser/context.cc:56-97) are folded in, and the tree is lowered to CUDA
+// C text that NVRTC fuses into the assembly kernels; the same tree can be evaluated on the host
+// for one-off setup work (compartment marking, initial values, Dirichlet values).
+//
+// Symbol table = what dune/copasi/model/functor_factory_parser.impl.hh:133-169 binds by address.
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "ptree.hpp"
+
+namespace dcb {
+
+struct Node;
+using NodeP = std::shared_ptr<const Node>;
+
+enum class Op {
+  Num, Var, Neg, Not, Add, Sub, Mul, Div, Pow, Mod, Lt, Gt, Le, Ge, Eq, Ne, And, Or, Sel, Call
+};
+
+struct Node {
+  Op op;
+  double num = 0;
+  std::string name;         // Var / Call
+  std::vector<NodeP> kids;
+};
+
+struct ParserContext {
+  std::map<std::string, double> constants;
+  struct Fn { std::vector<std::string> args; std::string body; };
+  std::map<std::string, Fn> functions;
+  static ParserContext from_config(const PTree& parser_context);
+};
+
+// true when the expression is empty or a literal zero: the term does not exist
+// (functor_factory_parser.impl.hh:122-124)
+bool expr_is_absent(const std::string& text);
+
+NodeP parse_expr(const std::string& text);
+// inline context constants/functions, fold constants
+NodeP resolve_expr(const NodeP& ast, const ParserContext& ctx);
+bool is_constant(const NodeP& ast, double* value = nullptr);
+void collect_vars(const NodeP& ast, std::vector<std::string>& out);
+
+// host evaluation; `lookup` maps a variable name to its value (throws for unknown names)
+double eval_expr(const NodeP& ast, const std::function<double(const std::string&)>& lookup);
+
+// CUDA C text; `symbol` maps a variable name to a C expression (returns "" for unknown -> error)
+std::string to_cuda(const NodeP& ast, const std::function<std::string(const std::string&)>& symbol);
+
+}  // namespace dcb

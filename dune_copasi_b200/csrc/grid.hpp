@@ -1,0 +1,71 @@
+// Host-side mesh, compartments, interface facets, P1 DOF map and sparsity pattern.
+//
+// Replaces (for the hot path) what the reference obtains from dune-grid/multidomaingrid + PDELab's
+// basis: grid/make_multi_domain_grid.hh:76-100 (structured simplex grid), :118-194 (compartment
+// marking by expression on cell centres), model_*_compartment_traits.hh (EntityGrouping /
+// Lexicographic DOF order), local_operator.hh:276-399 + make_step_operator.hh:378-384 (pattern).
+// Numbering rules are written down in DESIGN.md and restated independently in oracle/mesh.py.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "model.hpp"
+
+namespace dcb {
+
+struct Grid {
+  int dim = 0;
+  int64_t nv = 0, ne = 0;
+  std::vector<double> coords;            // [nv*dim]
+  std::vector<int32_t> elems;            // [ne*(dim+1)]
+  std::vector<std::string> cell_keys;
+  std::vector<double> cell_data;         // [nkeys*ne]
+
+  // ---- filled by bind(model)
+  std::vector<int32_t> elem_comp;        // [ne] compartment id or -1
+  std::vector<int64_t> f_in, f_out;      // interface + boundary facets
+  std::vector<int32_t> f_lin, f_lout;    // local index of the vertex opposite to the facet
+  std::vector<int64_t> boundary_vertices;
+  std::vector<int32_t> comp_nspec;
+  std::vector<std::vector<int32_t>> comp_vertices;  // sorted global vertex ids per compartment
+  std::vector<std::vector<int32_t>> comp_vdof;      // [nv] dof of species 0 at the vertex, or -1
+  std::vector<int64_t> comp_offset;
+  int64_t ndofs = 0;
+
+  // ---- partition data (local grids produced by partition(); empty on a global grid)
+  int64_t n_owned = -1;                  // owned vertices come first in the local numbering
+  std::vector<int64_t> global_vid;       // [nv] global vertex id
+  std::vector<int32_t> vowner;           // [nv] owning rank
+  std::vector<int64_t> global_eid;       // [ne] global element id
+
+  // Vertex-range partition: rank r owns a contiguous range of global vertex
+  // ids; its local mesh holds every element touching an owned vertex (owner computes, one layer of
+  // ghosts), vertices renumbered owned-first (each group ascending in global id).
+  Grid partition(int rank, int size) const;
+  // owned local dof ranges per compartment (valid after bind)
+  void owned_ranges(std::vector<int64_t>& begin, std::vector<int64_t>& end) const;
+  // halo plan of a bound local grid: per peer the local dofs to send / receive, both ordered by
+  // (compartment, global vertex id, species) so the two sides agree without communication
+  void halo_plan(int rank, std::vector<int>& peers, std::vector<std::vector<int32_t>>& send,
+                 std::vector<std::vector<int32_t>>& recv) const;
+
+  static Grid structured(int dim, const int* cells, const double* origin, const double* extent);
+  static Grid from_arrays(int dim, int64_t nv, const double* coords, int64_t ne, const int32_t* elems,
+                          const std::vector<std::string>& keys, const double* cell_data);
+
+  void bind(const Model& model);
+  int nd() const { return dim + 1; }
+  int64_t elem_dof(int64_t e, int a) const {   // dof of species 0 at local vertex a of element e
+    int c = elem_comp[e];
+    return c < 0 ? -1 : comp_vdof[c][elems[e * nd() + a]];
+  }
+
+  // sorted CSR pattern of the Jacobian (rows = dofs)
+  void pattern(const Model& model, std::vector<int64_t>& rowptr, std::vector<int32_t>& colidx) const;
+  // initial values / Dirichlet data at the dofs
+  void interpolate(const Model& model, double time, std::vector<double>& u) const;
+  void constraints(const Model& model, std::vector<int32_t>& dofs, std::vector<double>& vals) const;
+};
+
+}  // namespace dcb

@@ -1,0 +1,164 @@
+#include "jit.hpp"
+
+#include <dlfcn.h>
+#include <nvrtc.h>
+#include <sys/stat.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <sstream>
+
+namespace dcb {
+
+// generated at build time from kernels/kernel_args.h and kernels/assembly.cuh (embedded_sources.cpp)
+extern const char* kKernelArgsSource;
+extern const char* kAssemblySource;
+
+std::string jit_source(const Model& model, const std::string& defines, JitGroup group) {
+  std::ostringstream o;
+  o << defines << model.cuda_source();
+  o << kKernelArgsSource << "\n" << kAssemblySource << "\n";
+  o << "// ---- entry points -------------------------------------------------------------------\n";
+  const bool all = group == JitGroup::All;
+  for (int c = 0; c < model.ncomp(); ++c) {
+    if (model.comp_nspec[c] == 0) continue;
+    if (all || group == JitGroup::Element) {
+      o << "extern \"C\" __global__ void __launch_bounds__(128) dc_k_residual_volume_" << c
+        << "(DcVolArgs a) { dc_residual_volume<" << c << ">(a); }\n";
+      o << "extern \"C\" __global__ void __launch_bounds__(128) dc_k_jacobian_apply_volume_" << c
+        << "(DcVolArgs a) { dc_jacobian_apply_volume<" << c << ">(a); }\n";
+      o << "extern \"C\" __global__ void __launch_bounds__(128) dc_k_bdiag_volume_" << c
+        << "(DcVolArgs a) { dc_jacobian_volume<" << c << ", 1>(a); }\n";
+    }
+    if (all || group == JitGroup::Csr)
+      o << "extern \"C\" __global__ void __launch_bounds__(128) dc_k_jacobian_volume_" << c
+        << "(DcVolArgs a) { dc_jacobian_volume<" << c << ", 0>(a); }\n";
+    if (all || group == JitGroup::Patch) {
+      o << "extern \"C\" __global__ void __launch_bounds__(DC_PATCH_THREADS) dc_k_patch_residual_" << c
+        << "(DcPatchArgs a) { dc_patch_kernel<" << c << ", 0>(a); }\n";
+      o << "extern \"C\" __global__ void __launch_bounds__(DC_PATCH_THREADS) dc_k_patch_apply_" << c
+        << "(DcPatchArgs a) { dc_patch_kernel<" << c << ", 1>(a); }\n";
+      o << "extern \"C\" __global__ void __launch_bounds__(DC_PATCH_THREADS) dc_k_patch_bdiag_" << c
+        << "(DcPatchArgs a) { dc_patch_kernel<" << c << ", 2>(a); }\n";
+    }
+  }
+  if (all || group == JitGroup::Skeleton) {
+    size_t np = model.outflow_pairs().size();
+    for (size_t p = 0; p < np; ++p) {
+      o << "extern \"C\" __global__ void __launch_bounds__(64) dc_k_skeleton_residual_" << p
+        << "(DcFacetArgs a) { dc_skeleton_residual<" << p << ">(a); }\n";
+      const char* names[3] = {"jacobian", "apply", "bdiag"};
+      for (int mode = 0; mode < 3; ++mode)
+        o << "extern \"C\" __global__ void __launch_bounds__(64) dc_k_skeleton_" << names[mode] << "_" << p
+          << "(DcFacetArgs a) { dc_skeleton_jacobian<" << p << ", " << mode << ">(a); }\n";
+    }
+  }
+  return o.str();
+}
+
+std::string jit_defines(const Model& model) {
+  const PTree& acfg = model.cfg.sub("model.assembly.b200");
+  int pn = acfg.get("patch_vertices", 768), cbuf = acfg.get("patch_buffer", 4096), th = acfg.get("patch_threads", 256);
+  if (pn < 16 || pn > 16384) fail("model.assembly.b200.patch_vertices out of range");
+  if (th < 32 || th > 1024 || th % 32) fail("model.assembly.b200.patch_threads must be a multiple of 32 in [32,1024]");
+  return "#define DC_PATCH_PN " + std::to_string(pn) + "\n#define DC_PATCH_CBUF " + std::to_string(cbuf) +
+         "\n#define DC_PATCH_THREADS " + std::to_string(th) + "\n";
+}
+
+std::vector<char> jit_compile(const std::string& source, std::string* log, bool ptx) {
+  nvrtcProgram prog;
+  if (nvrtcCreateProgram(&prog, source.c_str(), "dune_copasi_b200_model.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+    fail("nvrtcCreateProgram failed");
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--fmad=true",
+                        "-default-device"};
+  nvrtcResult res = nvrtcCompileProgram(prog, 5, opts);
+  size_t log_size = 0;
+  nvrtcGetProgramLogSize(prog, &log_size);
+  std::string l(log_size, '\0');
+  if (log_size) nvrtcGetProgramLog(prog, l.data());
+  if (log) *log = l;
+  if (res != NVRTC_SUCCESS) {
+    nvrtcDestroyProgram(&prog);
+    fail("NVRTC compilation of the model kernels failed (", nvrtcGetErrorString(res), "):\n", l);
+  }
+  std::vector<char> out;
+  size_t n = 0;
+  if (ptx) {
+    nvrtcGetPTXSize(prog, &n);
+    out.resize(n);
+    nvrtcGetPTX(prog, out.data());
+  } else {
+    nvrtcGetCUBINSize(prog, &n);
+    out.resize(n);
+    nvrtcGetCUBIN(prog, out.data());
+  }
+  nvrtcDestroyProgram(&prog);
+  return out;
+}
+
+namespace {
+uint64_t fnv1a(const std::string& s) {
+  uint64_t h = 1469598103934665603ULL;
+  for (unsigned char c : s) { h ^= c; h *= 1099511628211ULL; }
+  return h;
+}
+std::string cache_dir() {
+  if (const char* e = std::getenv("DCB_JIT_CACHE")) return e;
+  Dl_info info;
+  if (dladdr((void*)&fnv1a, &info) && info.dli_fname) {
+    std::string p = info.dli_fname;
+    auto slash = p.rfind('/');
+    return (slash == std::string::npos ? std::string(".") : p.substr(0, slash)) + "/_jit_cache";
+  }
+  return "/tmp/dune_copasi_b200_jit_cache";
+}
+}  // namespace
+
+std::vector<char> jit_compile_cached(const std::string& source) {
+  int major = 0, minor = 0;
+  nvrtcVersion(&major, &minor);
+  char name[64];
+  snprintf(name, sizeof name, "%016llx_%d_%d.cubin",
+           (unsigned long long)fnv1a(source), major, minor);
+  const std::string dir = cache_dir(), path = dir + "/" + name;
+  {
+    std::ifstream f(path, std::ios::binary);
+    if (f) {
+      std::vector<char> bin((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+      if (!bin.empty()) return bin;
+    }
+  }
+  std::string log;
+  std::vector<char> bin = jit_compile(source, &log, false);
+  mkdir(dir.c_str(), 0755);
+  const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+  {
+    std::ofstream f(tmp, std::ios::binary);
+    if (f) f.write(bin.data(), (std::streamsize)bin.size());
+  }
+  std::rename(tmp.c_str(), path.c_str());   // atomic publish; failures only cost a recompile
+  return bin;
+}
+
+JitModule::~JitModule() {
+  if (lib_) cudaLibraryUnload(lib_);
+}
+
+void JitModule::load(const std::vector<char>& cubin) {
+  require_device();
+  if (lib_) { cudaLibraryUnload(lib_); lib_ = nullptr; cache_.clear(); }
+  DCB_CUDA(cudaLibraryLoadData(&lib_, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+}
+
+cudaKernel_t JitModule::kernel(const std::string& name) {
+  auto it = cache_.find(name);
+  if (it != cache_.end()) return it->second;
+  cudaKernel_t k;
+  cudaError_t e = cudaLibraryGetKernel(&k, lib_, name.c_str());
+  if (e != cudaSuccess) fail("kernel '", name, "' not found in the JIT module: ", cudaGetErrorString(e));
+  cache_[name] = k;
+  return k;
+}
+
+}  // namespace dcb

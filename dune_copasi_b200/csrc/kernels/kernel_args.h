@@ -1,0 +1,71 @@
+// Argument blocks shared by the host (nvcc/g++) and the NVRTC-compiled assembly kernels.
+// Plain types only; identical layout on both sides.
+#ifndef DCB_KERNEL_ARGS_H
+#define DCB_KERNEL_ARGS_H
+
+struct DcVolArgs {
+  const double* coords;        // [nv][DIM]
+  const int* elems;            // [ne][DIM+1]
+  const int* elem_ids;         // elements of this compartment (null: 0..n-1)
+  const int* vdof;             // vertex -> dof of species 0 in this compartment (null: dof_offset + v*NS)
+  const double* cell;          // [nkeys][ne_total]
+  long long ne_total;
+  long long n;                 // elements in this launch
+  int dof_offset;
+  double time, wM, wA;
+  const double* x;             // linearisation point / coefficients
+  const double* z;             // direction for Jacobian-apply
+  double* r;                   // residual / apply output (accumulated)
+  const long long* rowptr;     // CSR of the Jacobian
+  const int* colidx;
+  double* vals;
+  double* bdiag;               // block diagonal, NS x NS per vertex: bdiag[dof0*NS + i*NS + j]
+  const unsigned char* cmask;  // per-dof Dirichlet mask (null: none); masked z entries act as 0
+};
+
+struct DcPatchArgs {
+  const double* coords;
+  const int* patch_node_ptr;   // [npatch+1]
+  const int* patch_nodes;      // vertex ids of each patch, ascending
+  const int* patch_elem_ptr;   // [npatch+1]
+  const unsigned short* lconn; // [ne][4] patch-local vertex indices (4th unused in 2-D)
+  const unsigned short* adj;   // per patch node: (local element << 2 | local vertex) list
+  const int* adj_ptr;          // [total patch nodes + 1]
+  const int* vdof;
+  const double* cell;          // [nkeys][ne] in patch element order
+  long long ne_total;
+  int npatch;
+  int dof_offset;
+  double time, wM, wA;
+  const double* x;
+  const double* z;
+  double* r;
+  double* bdiag;
+  const unsigned char* cmask;
+};
+
+struct DcFacetArgs {
+  const double* coords;
+  const int* elems;
+  const long long* f_self;     // element on the side that owns the residual rows
+  const long long* f_other;    // element on the other side (-1 on the boundary)
+  const int* f_lself;          // local index of the vertex opposite to the facet
+  const int* f_lother;
+  const int* vdof_s;           // vertex -> dof maps of the two compartments (null: offset + v*NS)
+  const int* vdof_t;
+  const double* cell;
+  long long ne_total;
+  long long n;
+  int dof_offset_s, dof_offset_t;
+  double time, wA;
+  const double* x;
+  const double* z;
+  double* r;
+  const long long* rowptr;
+  const int* colidx;
+  double* vals;
+  double* bdiag;
+  const unsigned char* cmask;
+};
+
+#endif

@@ -1,0 +1,438 @@
+// Statically compiled sm_100a kernels of the Krylov solve: SpMV, fused BLAS-1 sweeps, Jacobi and
+// block-Jacobi, Dirichlet masks, halo pack/unpack.  Everything here is HBM-bound fp64 streaming
+// work: vectorised (16-byte) loads where alignment allows, grids sized as multiples of the 148
+// SMs, reductions deterministic (fixed grid, ordered final sum).
+#include "linalg.hpp"
+
+#include "../util.hpp"
+
+namespace dcb {
+namespace la {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kNumSms = 148;
+
+inline int grid_for(int64_t n, int per_thread = 1) {
+  int64_t blocks = (n + (int64_t)kThreads * per_thread - 1) / ((int64_t)kThreads * per_thread);
+  if (blocks < 1) blocks = 1;
+  if (blocks > kMaxBlocks) blocks = kMaxBlocks;  // grid-stride beyond 8 CTAs per SM
+  return (int)blocks;
+}
+
+__device__ __forceinline__ bool in_ranges(const Ranges& r, long long i) {
+  bool hit = false;
+#pragma unroll 1
+  for (int k = 0; k < r.n; ++k) hit |= (i >= r.b[k] && i < r.e[k]);
+  return hit;
+}
+
+// block reduce NOUT values, then "last block sums the partials in order"
+template <int NOUT>
+__device__ void grid_reduce(double (&v)[NOUT], double* partials, unsigned* counter, double* out) {
+  __shared__ double sm[NOUT][kThreads / 32];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NOUT; ++k) {
+    double x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) sm[k][warp] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) {
+      double x = 0.0;
+      for (int w = 0; w < kThreads / 32; ++w) x += sm[k][w];
+      partials[(size_t)blockIdx.x * NOUT + k] = x;
+    }
+    __threadfence();
+    const unsigned ticket = atomicInc(counter, gridDim.x - 1);  // wraps back to 0: self resetting
+    last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < NOUT; ++k) {
+    double x = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads) x += partials[(size_t)b * NOUT + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) sm[k][warp] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) {
+      double x = 0.0;
+      for (int w = 0; w < kThreads / 32; ++w) x += sm[k][w];
+      out[k] = x;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- SpMV
+// T lanes cooperate on one row; consecutive lanes read consecutive nonzeros (coalesced).
+template <int T, class RP>
+__global__ void __launch_bounds__(kThreads) k_spmv(int64_t nrows, const RP* __restrict__ rowptr,
+                                                   const int32_t* __restrict__ colidx,
+                                                   const double* __restrict__ vals,
+                                                   const double* __restrict__ x, double* __restrict__ y) {
+  const int sub = threadIdx.x % T;
+  const int64_t rows_per_block = kThreads / T;
+  for (int64_t row = blockIdx.x * rows_per_block + threadIdx.x / T; row < nrows;
+       row += (int64_t)gridDim.x * rows_per_block) {
+    const int64_t b = rowptr[row], e = rowptr[row + 1];
+    double acc = 0.0;
+    for (int64_t k = b + sub; k < e; k += T) acc += vals[k] * __ldg(&x[colidx[k]]);
+#pragma unroll
+    for (int o = T / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, T);
+    if (sub == 0) y[row] = acc;
+  }
+}
+
+template <class RP>
+void spmv_launch(int64_t nrows, const RP* rp, const int32_t* ci, const double* va, const double* x,
+                 double* y, int avg, cudaStream_t s) {
+  // rows per block = 256/T; grid capped at a multiple of the SM count with grid-stride rows
+  auto grid = [&](int T) {
+    int64_t b = (nrows * T + kThreads - 1) / kThreads;
+    int64_t cap = (int64_t)kNumSms * 64;
+    return (int)std::max<int64_t>(1, std::min(b, cap));
+  };
+  if (avg <= 3) k_spmv<2, RP><<<grid(2), kThreads, 0, s>>>(nrows, rp, ci, va, x, y);
+  else if (avg <= 10) k_spmv<4, RP><<<grid(4), kThreads, 0, s>>>(nrows, rp, ci, va, x, y);
+  else if (avg <= 48) k_spmv<8, RP><<<grid(8), kThreads, 0, s>>>(nrows, rp, ci, va, x, y);
+  else if (avg <= 128) k_spmv<16, RP><<<grid(16), kThreads, 0, s>>>(nrows, rp, ci, va, x, y);
+  else k_spmv<32, RP><<<grid(32), kThreads, 0, s>>>(nrows, rp, ci, va, x, y);
+}
+
+// ---------------------------------------------------------------- BLAS-1
+__global__ void __launch_bounds__(kThreads) k_dot(Ranges own, const double* __restrict__ a,
+                                                  const double* __restrict__ b, double* partials,
+                                                  unsigned* counter, double* out) {
+  double v[1] = {0.0};
+  for (int k = 0; k < own.n; ++k)
+    for (long long i = own.b[k] + blockIdx.x * (long long)kThreads + threadIdx.x; i < own.e[k];
+         i += (long long)gridDim.x * kThreads)
+      v[0] += a[i] * b[i];
+  grid_reduce<1>(v, partials, counter, out);
+}
+
+__global__ void __launch_bounds__(kThreads) k_dot2(Ranges own, const double* __restrict__ a,
+                                                   const double* __restrict__ b,
+                                                   const double* __restrict__ c,
+                                                   const double* __restrict__ d, double* partials,
+                                                   unsigned* counter, double* out) {
+  double v[2] = {0.0, 0.0};
+  for (int k = 0; k < own.n; ++k)
+    for (long long i = own.b[k] + blockIdx.x * (long long)kThreads + threadIdx.x; i < own.e[k];
+         i += (long long)gridDim.x * kThreads) {
+      v[0] += a[i] * b[i];
+      v[1] += c[i] * d[i];
+    }
+  grid_reduce<2>(v, partials, counter, out);
+}
+
+__global__ void __launch_bounds__(kThreads) k_bicg_p(int64_t n, double* __restrict__ p,
+                                                     const double* __restrict__ r,
+                                                     const double* __restrict__ v, double beta,
+                                                     double omega, bool first) {
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    p[i] = first ? r[i] : r[i] + beta * (p[i] - omega * v[i]);
+}
+
+__global__ void __launch_bounds__(kThreads) k_axpy_pair_norm(int64_t n, Ranges own, double alpha,
+                                                             const double* __restrict__ y,
+                                                             double* __restrict__ x,
+                                                             const double* __restrict__ v,
+                                                             double* __restrict__ r,
+                                                             const double* __restrict__ rt,
+                                                             double* partials, unsigned* counter,
+                                                             double* out) {
+  double acc[2] = {0.0, 0.0};
+  const bool single = own.n == 1 && own.b[0] == 0 && own.e[0] == n;
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    x[i] += alpha * y[i];
+    const double ri = r[i] - alpha * v[i];
+    r[i] = ri;
+    if (single || in_ranges(own, i)) {
+      acc[0] += ri * ri;
+      if (rt) acc[1] += rt[i] * ri;
+    }
+  }
+  grid_reduce<2>(acc, partials, counter, out);
+}
+
+__global__ void __launch_bounds__(kThreads) k_xpby(int64_t n, double* __restrict__ p,
+                                                   const double* __restrict__ q, double beta) {
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    p[i] = q[i] + beta * p[i];
+}
+__global__ void __launch_bounds__(kThreads) k_axpy(int64_t n, double a, const double* __restrict__ x,
+                                                   double* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    y[i] += a * x[i];
+}
+__global__ void __launch_bounds__(kThreads) k_fill(int64_t n, double v, double* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    y[i] = v;
+}
+
+// ---------------------------------------------------------------- preconditioners
+__global__ void __launch_bounds__(kThreads) k_jacobi(int64_t n, const double* __restrict__ dinv,
+                                                     double relax, const double* __restrict__ d,
+                                                     double* __restrict__ v) {
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    v[i] = relax * dinv[i] * d[i];
+}
+
+__global__ void __launch_bounds__(kThreads) k_diag_inv(int64_t n, const int64_t* __restrict__ rowptr,
+                                                       const int32_t* __restrict__ colidx,
+                                                       const double* __restrict__ vals,
+                                                       double* __restrict__ dinv) {
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    double d = 0.0;
+    for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k)
+      if (colidx[k] == i) d = vals[k];
+    dinv[i] = 1.0 / d;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_block_diag(int64_t dof0, int64_t nrows, int bs,
+                                                         const int64_t* __restrict__ rowptr,
+                                                         const int32_t* __restrict__ colidx,
+                                                         const double* __restrict__ vals,
+                                                         double* __restrict__ bdiag) {
+  for (int64_t t = blockIdx.x * (int64_t)kThreads + threadIdx.x; t < nrows; t += (int64_t)gridDim.x * kThreads) {
+    const int64_t row = dof0 + t, blk0 = dof0 + (t / bs) * bs;
+    for (int j = 0; j < bs; ++j) bdiag[row * bs + j] = 0.0;
+    for (int64_t k = rowptr[row]; k < rowptr[row + 1]; ++k) {
+      const int64_t c = colidx[k];
+      if (c >= blk0 && c < blk0 + bs) bdiag[row * bs + (c - blk0)] = vals[k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_block_invert(int64_t nblocks, int bs, double* __restrict__ blocks) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  double A[19 * 19], B[19 * 19];
+  double* g = blocks + b * bs * bs;
+  for (int i = 0; i < bs; ++i)
+    for (int j = 0; j < bs; ++j) { A[i * bs + j] = g[i * bs + j]; B[i * bs + j] = i == j ? 1.0 : 0.0; }
+  for (int p = 0; p < bs; ++p) {
+    int piv = p;
+    for (int i = p + 1; i < bs; ++i)
+      if (fabs(A[i * bs + p]) > fabs(A[piv * bs + p])) piv = i;
+    if (piv != p)
+      for (int j = 0; j < bs; ++j) {
+        double t = A[p * bs + j]; A[p * bs + j] = A[piv * bs + j]; A[piv * bs + j] = t;
+        t = B[p * bs + j]; B[p * bs + j] = B[piv * bs + j]; B[piv * bs + j] = t;
+      }
+    const double ip = 1.0 / A[p * bs + p];
+    for (int j = 0; j < bs; ++j) { A[p * bs + j] *= ip; B[p * bs + j] *= ip; }
+    for (int i = 0; i < bs; ++i)
+      if (i != p) {
+        const double f = A[i * bs + p];
+        for (int j = 0; j < bs; ++j) { A[i * bs + j] -= f * A[p * bs + j]; B[i * bs + j] -= f * B[p * bs + j]; }
+      }
+  }
+  for (int i = 0; i < bs * bs; ++i) g[i] = B[i];
+}
+
+__global__ void __launch_bounds__(kThreads) k_block_jacobi(int64_t dof0, int64_t nrows, int bs,
+                                                           const double* __restrict__ binv, double relax,
+                                                           const double* __restrict__ d,
+                                                           double* __restrict__ v) {
+  for (int64_t t = blockIdx.x * (int64_t)kThreads + threadIdx.x; t < nrows; t += (int64_t)gridDim.x * kThreads) {
+    const int64_t row = dof0 + t, blk0 = dof0 + (t / bs) * bs;
+    double acc = 0.0;
+    for (int j = 0; j < bs; ++j) acc += binv[row * bs + j] * d[blk0 + j];
+    v[row] = relax * acc;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_bdiag_dinv(int64_t dof0, int64_t nrows, int bs,
+                                                         const double* __restrict__ bdiag,
+                                                         double* __restrict__ dinv) {
+  for (int64_t t = blockIdx.x * (int64_t)kThreads + threadIdx.x; t < nrows; t += (int64_t)gridDim.x * kThreads) {
+    const int64_t row = dof0 + t;
+    dinv[row] = 1.0 / bdiag[row * bs + (t % bs)];
+  }
+}
+
+// ---------------------------------------------------------------- Dirichlet / halo
+__global__ void k_set_values(int64_t n, const int32_t* idx, const double* vals, double* x) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) x[idx[i]] = vals ? vals[i] : 0.0;
+}
+__global__ void k_copy_values(int64_t n, const int32_t* idx, const double* src, double* dst) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[idx[i]] = src[idx[i]];
+}
+__global__ void __launch_bounds__(kThreads) k_csr_constrain(int64_t nrows, const int64_t* __restrict__ rowptr,
+                                                            const int32_t* __restrict__ colidx,
+                                                            double* __restrict__ vals,
+                                                            const unsigned char* __restrict__ mask) {
+  for (int64_t row = blockIdx.x * (int64_t)kThreads + threadIdx.x; row < nrows; row += (int64_t)gridDim.x * kThreads) {
+    const bool rc = mask[row];
+    for (int64_t k = rowptr[row]; k < rowptr[row + 1]; ++k) {
+      const int32_t c = colidx[k];
+      if (rc || mask[c]) vals[k] = (rc && c == row) ? 1.0 : 0.0;
+    }
+  }
+}
+__global__ void __launch_bounds__(kThreads) k_bdiag_constrain(int64_t dof0, int64_t nrows, int bs,
+                                                              double* __restrict__ bdiag,
+                                                              const unsigned char* __restrict__ mask) {
+  for (int64_t t = blockIdx.x * (int64_t)kThreads + threadIdx.x; t < nrows; t += (int64_t)gridDim.x * kThreads) {
+    const int64_t row = dof0 + t, blk0 = dof0 + (t / bs) * bs;
+    const bool rc = mask[row];
+    for (int j = 0; j < bs; ++j)
+      if (rc || mask[blk0 + j]) bdiag[row * bs + j] = (rc && blk0 + j == row) ? 1.0 : 0.0;
+  }
+}
+__global__ void k_gather(int64_t n, const int32_t* idx, const double* x, double* buf) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) buf[i] = x[idx[i]];
+}
+__global__ void k_scatter(int64_t n, const int32_t* idx, const double* buf, double* x) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) x[idx[i]] = buf[i];
+}
+
+inline void check_launch() { DCB_CUDA(cudaGetLastError()); }
+
+}  // namespace
+
+void reduce_workspace_create(ReduceWorkspace* w) {
+  DCB_CUDA(cudaMalloc(&w->partials, sizeof(double) * kMaxBlocks * 4));
+  DCB_CUDA(cudaMalloc(&w->counter, sizeof(unsigned)));
+  DCB_CUDA(cudaMemset(w->counter, 0, sizeof(unsigned)));
+}
+void reduce_workspace_destroy(ReduceWorkspace* w) {
+  if (w->partials) cudaFree(w->partials);
+  if (w->counter) cudaFree(w->counter);
+  w->partials = nullptr; w->counter = nullptr;
+}
+
+void spmv_csr(int64_t nrows, const int64_t* rowptr, const int32_t* rowptr32, const int32_t* colidx,
+              const double* vals, const double* x, double* y, int avg_nnz, cudaStream_t s) {
+  if (nrows == 0) return;
+  if (rowptr32) spmv_launch<int32_t>(nrows, rowptr32, colidx, vals, x, y, avg_nnz, s);
+  else spmv_launch<int64_t>(nrows, rowptr, colidx, vals, x, y, avg_nnz, s);
+  check_launch();
+}
+
+static int64_t ranges_len(const Ranges& r) {
+  int64_t n = 0;
+  for (int k = 0; k < r.n; ++k) n = std::max<int64_t>(n, r.e[k] - r.b[k]);
+  return n;
+}
+
+void dot(const Ranges& own, const double* a, const double* b, double* out, const ReduceWorkspace& w, cudaStream_t s) {
+  k_dot<<<grid_for(ranges_len(own), 4), kThreads, 0, s>>>(own, a, b, w.partials, w.counter, out);
+  check_launch();
+}
+void dot2(const Ranges& own, const double* a, const double* b, const double* c, const double* d, double* out,
+          const ReduceWorkspace& w, cudaStream_t s) {
+  k_dot2<<<grid_for(ranges_len(own), 4), kThreads, 0, s>>>(own, a, b, c, d, w.partials, w.counter, out);
+  check_launch();
+}
+void bicg_update_p(int64_t n, double* p, const double* r, const double* v, double beta, double omega,
+                   bool first, cudaStream_t s) {
+  k_bicg_p<<<grid_for(n, 2), kThreads, 0, s>>>(n, p, r, v, beta, omega, first);
+  check_launch();
+}
+void axpy_pair_norm(int64_t n, const Ranges& own, double alpha, const double* y, double* x, const double* v,
+                    double* r, const double* rt, double* out, const ReduceWorkspace& w, cudaStream_t s) {
+  k_axpy_pair_norm<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, alpha, y, x, v, r, rt, w.partials, w.counter, out);
+  check_launch();
+}
+void xpby(int64_t n, double* p, const double* q, double beta, cudaStream_t s) {
+  k_xpby<<<grid_for(n, 2), kThreads, 0, s>>>(n, p, q, beta);
+  check_launch();
+}
+void axpy(int64_t n, double a, const double* x, double* y, cudaStream_t s) {
+  k_axpy<<<grid_for(n, 2), kThreads, 0, s>>>(n, a, x, y);
+  check_launch();
+}
+void copy(int64_t n, const double* x, double* y, cudaStream_t s) {
+  if (n) DCB_CUDA(cudaMemcpyAsync(y, x, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+}
+void fill(int64_t n, double v, double* y, cudaStream_t s) {
+  if (v == 0.0) { if (n) DCB_CUDA(cudaMemsetAsync(y, 0, n * sizeof(double), s)); return; }
+  k_fill<<<grid_for(n, 2), kThreads, 0, s>>>(n, v, y);
+  check_launch();
+}
+void jacobi_apply(int64_t n, const double* dinv, double relax, const double* d, double* v, cudaStream_t s) {
+  k_jacobi<<<grid_for(n, 2), kThreads, 0, s>>>(n, dinv, relax, d, v);
+  check_launch();
+}
+void csr_extract_diag_inv(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* vals,
+                          double* dinv, cudaStream_t s) {
+  k_diag_inv<<<grid_for(n), kThreads, 0, s>>>(n, rowptr, colidx, vals, dinv);
+  check_launch();
+}
+void csr_extract_block_diag(int64_t dof0, int64_t nblocks, int bs, const int64_t* rowptr,
+                            const int32_t* colidx, const double* vals, double* bdiag, cudaStream_t s) {
+  if (nblocks == 0) return;
+  k_block_diag<<<grid_for(nblocks * bs), kThreads, 0, s>>>(dof0, nblocks * bs, bs, rowptr, colidx, vals, bdiag);
+  check_launch();
+}
+void block_invert(int64_t nblocks, int bs, double* blocks, cudaStream_t s) {
+  if (nblocks == 0) return;
+  if (bs > 19) fail("BlockJacobi: block size ", bs, " > 19 (DenseInverse limit, direct.hh:36-74)");
+  k_block_invert<<<(unsigned)((nblocks + 127) / 128), 128, 0, s>>>(nblocks, bs, blocks);
+  check_launch();
+}
+void block_jacobi_apply(int64_t dof0, int64_t nblocks, int bs, const double* binv, double relax,
+                        const double* d, double* v, cudaStream_t s) {
+  if (nblocks == 0) return;
+  k_block_jacobi<<<grid_for(nblocks * bs), kThreads, 0, s>>>(dof0, nblocks * bs, bs, binv, relax, d, v);
+  check_launch();
+}
+void block_diag_to_dinv(int64_t dof0, int64_t nblocks, int bs, const double* bdiag, double* dinv, cudaStream_t s) {
+  if (nblocks == 0) return;
+  k_bdiag_dinv<<<grid_for(nblocks * bs), kThreads, 0, s>>>(dof0, nblocks * bs, bs, bdiag, dinv);
+  check_launch();
+}
+void set_values(int64_t n, const int32_t* idx, const double* vals, double* x, cudaStream_t s) {
+  if (n == 0) return;
+  k_set_values<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, idx, vals, x);
+  check_launch();
+}
+void zero_values(int64_t n, const int32_t* idx, double* x, cudaStream_t s) { set_values(n, idx, nullptr, x, s); }
+void copy_values(int64_t n, const int32_t* idx, const double* src, double* dst, cudaStream_t s) {
+  if (n == 0) return;
+  k_copy_values<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, idx, src, dst);
+  check_launch();
+}
+void csr_constrain(int64_t nrows, const int64_t* rowptr, const int32_t* colidx, double* vals,
+                   const unsigned char* mask, cudaStream_t s) {
+  k_csr_constrain<<<grid_for(nrows), kThreads, 0, s>>>(nrows, rowptr, colidx, vals, mask);
+  check_launch();
+}
+void bdiag_constrain(int64_t dof0, int64_t nblocks, int bs, double* bdiag, const unsigned char* mask, cudaStream_t s) {
+  if (nblocks == 0) return;
+  k_bdiag_constrain<<<grid_for(nblocks * bs), kThreads, 0, s>>>(dof0, nblocks * bs, bs, bdiag, mask);
+  check_launch();
+}
+void gather(int64_t n, const int32_t* idx, const double* x, double* buf, cudaStream_t s) {
+  if (n == 0) return;
+  k_gather<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, idx, x, buf);
+  check_launch();
+}
+void scatter(int64_t n, const int32_t* idx, const double* buf, double* x, cudaStream_t s) {
+  if (n == 0) return;
+  k_scatter<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, idx, buf, x);
+  check_launch();
+}
+
+}  // namespace la
+}  // namespace dcb

@@ -1,0 +1,82 @@
+// Launchers of the statically compiled sm_100a kernels (linalg.cu): SpMV, fused BLAS-1 sweeps of
+// BiCGSTAB / CG, Jacobi and block-Jacobi, Dirichlet masks.  All fp64, all HBM-bound.
+// They replace the dune-istl vector/matrix arithmetic the reference drives through
+// dune/copasi/solver/istl/factory/{iterative,preconditioner}.hh and block_jacobi.hh:46-128.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace dcb {
+namespace la {
+
+// Deterministic grid reductions: every reducing kernel runs on a fixed grid and writes its result
+// through a "last block sums the partials in order" epilogue.
+struct ReduceWorkspace {
+  double* partials = nullptr;   // [kMaxBlocks * 4]
+  unsigned* counter = nullptr;  // self-resetting ticket
+};
+constexpr int kMaxBlocks = 148 * 8;
+// dofs that enter global reductions (multi-GPU: the owned dofs; one range per compartment)
+struct Ranges {
+  int n = 0;
+  long long b[8], e[8];
+  static Ranges all(long long len) { Ranges r; r.n = 1; r.b[0] = 0; r.e[0] = len; return r; }
+};
+void reduce_workspace_create(ReduceWorkspace* w);
+void reduce_workspace_destroy(ReduceWorkspace* w);
+
+// y = A x (CSR, sorted columns); rowptr32 != null selects 32-bit row pointers
+void spmv_csr(int64_t nrows, const int64_t* rowptr, const int32_t* rowptr32, const int32_t* colidx,
+              const double* vals, const double* x, double* y, int avg_nnz, cudaStream_t s);
+
+// out[0] = <a,b>            (out is a device pointer)
+void dot(const Ranges& own, const double* a, const double* b, double* out, const ReduceWorkspace& w, cudaStream_t s);
+// out[0] = <a,b>, out[1] = <c,d>
+void dot2(const Ranges& own, const double* a, const double* b, const double* c, const double* d, double* out,
+          const ReduceWorkspace& w, cudaStream_t s);
+
+// BiCGSTAB: p = r + beta (p - omega v)      (first = true: p = r)
+void bicg_update_p(int64_t n, double* p, const double* r, const double* v, double beta, double omega,
+                   bool first, cudaStream_t s);
+// x += alpha y ; r -= alpha v ; out[0] = <r,r> ; out[1] = <rt,r>  (rt may be null -> out[1] = 0)
+void axpy_pair_norm(int64_t n, const Ranges& own, double alpha, const double* y, double* x, const double* v, double* r,
+                    const double* rt, double* out, const ReduceWorkspace& w, cudaStream_t s);
+// CG: p = q + beta p
+void xpby(int64_t n, double* p, const double* q, double beta, cudaStream_t s);
+// y += a x
+void axpy(int64_t n, double a, const double* x, double* y, cudaStream_t s);
+void copy(int64_t n, const double* x, double* y, cudaStream_t s);
+void fill(int64_t n, double v, double* y, cudaStream_t s);
+
+// preconditioners
+void jacobi_apply(int64_t n, const double* dinv, double relax, const double* d, double* v, cudaStream_t s);
+void csr_extract_diag_inv(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* vals,
+                          double* dinv, cudaStream_t s);
+// block diagonal of node blocks of size bs over dofs [dof0, dof0 + nblocks*bs): bdiag[dof*bs + j]
+void csr_extract_block_diag(int64_t dof0, int64_t nblocks, int bs, const int64_t* rowptr,
+                            const int32_t* colidx, const double* vals, double* bdiag, cudaStream_t s);
+// in-place inversion of nblocks dense bs x bs blocks (Gauss-Jordan with partial pivoting,
+// = FieldMatrix::invert used by DenseInverse, dense_inverse.hh:9-37), bs <= 19
+void block_invert(int64_t nblocks, int bs, double* blocks, cudaStream_t s);
+void block_jacobi_apply(int64_t dof0, int64_t nblocks, int bs, const double* binv, double relax,
+                        const double* d, double* v, cudaStream_t s);
+// scalar diagonal from the block diagonal: dinv[dof0 + b*bs + i] = 1 / bdiag[(dof0 + b*bs)*bs + i*bs + i]
+void block_diag_to_dinv(int64_t dof0, int64_t nblocks, int bs, const double* bdiag, double* dinv, cudaStream_t s);
+
+// Dirichlet handling
+void set_values(int64_t n, const int32_t* idx, const double* vals, double* x, cudaStream_t s);   // x[idx] = vals
+void zero_values(int64_t n, const int32_t* idx, double* x, cudaStream_t s);                      // x[idx] = 0
+void copy_values(int64_t n, const int32_t* idx, const double* src, double* dst, cudaStream_t s); // dst[idx] = src[idx]
+// rows and columns of constrained dofs -> identity (mask is per dof)
+void csr_constrain(int64_t nrows, const int64_t* rowptr, const int32_t* colidx, double* vals,
+                   const unsigned char* mask, cudaStream_t s);
+// block diagonal rows/cols of constrained dofs -> identity
+void bdiag_constrain(int64_t dof0, int64_t nblocks, int bs, double* bdiag, const unsigned char* mask, cudaStream_t s);
+
+// halo exchange helpers
+void gather(int64_t n, const int32_t* idx, const double* x, double* buf, cudaStream_t s);   // buf[i] = x[idx[i]]
+void scatter(int64_t n, const int32_t* idx, const double* buf, double* x, cudaStream_t s);  // x[idx[i]] = buf[i]
+
+}  // namespace la
+}  // namespace dcb

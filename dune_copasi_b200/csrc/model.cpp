@@ -1,0 +1,368 @@
+#include "model.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <set>
+#include <sstream>
+
+namespace dcb {
+
+static const char* kAxis[3] = {"x", "y", "z"};
+
+Model::Model(const PTree& cfg_, int dim_, const std::vector<std::string>& keys)
+    : dim(dim_), cell_keys(keys) {
+  cfg.parse_ini(cfg_.dump());
+  if (dim < 2 || dim > 3) fail("only dimensions 2 and 3 are built (got ", dim, ")");
+  ctx = ParserContext::from_config(cfg.sub("parser_context"));
+  const PTree& mcfg = cfg.sub("model");
+  is_linear = mcfg.get("is_linear", false);
+  if (mcfg.get("order", 1) != 1) fail("model.order = ", mcfg.get("order", 1), ": only P1 is built");
+  const PTree& comps = cfg.sub("compartments");
+  for (auto& name : comps.sub_keys()) {
+    const PTree& c = comps.sub(name);
+    std::string type = c.get("type", std::string("expression"));
+    if (type != "expression") fail("compartments.", name, ".type = '", type, "' is not known");
+    comp_names.push_back(name);
+    comp_expr.push_back(compile(c.get("expression", std::string("0"))));
+  }
+  if (comp_names.empty()) fail("config has no [compartments]");
+  const PTree& fields = mcfg.sub("scalar_field");
+  comp_nspec.assign(ncomp(), 0);
+  comp_first.assign(ncomp(), 0);
+  std::vector<const PTree*> scfg;
+  for (int c = 0; c < ncomp(); ++c) {
+    comp_first[c] = nspec();
+    for (auto& name : fields.sub_keys()) {
+      const PTree& f = fields.sub(name);
+      if (f.get("compartment", std::string()) != comp_names[c]) continue;
+      SpeciesInfo s;
+      s.name = name;
+      s.comp = c;
+      s.local = comp_nspec[c]++;
+      s.initial = f.get("initial.expression", std::string());
+      s.constrain_boundary = f.get("constrain.boundary.expression", std::string());
+      if (f.has_sub("constrain.skeleton") || f.has_sub("constrain.volume"))
+        fail("scalar_field.", name, ": only constrain.boundary is built");
+      species.push_back(s);
+      scfg.push_back(&f);
+    }
+  }
+  if (species.empty())
+    fail("Basis has dimension 0, make sure to have at least one 'scalar_field' with a non-empty 'compartment'");
+  {
+    std::set<std::string> seen;
+    for (auto& s : species)
+      if (!seen.insert(s.name).second) fail("Variable with name '", s.name, "' is repeated");
+  }
+  auto add = [&](Term::Kind kind, int i, int j, int k, const std::string& text) {
+    if (expr_is_absent(text)) return false;
+    Term t;
+    t.kind = kind; t.i = i; t.j = j; t.k = k; t.text = text;
+    t.ast = compile(text);
+    terms.push_back(t);
+    return true;
+  };
+  for (int g = 0; g < nspec(); ++g) {
+    const PTree& f = *scfg[g];
+    if (f.has_sub("velocity")) fail("scalar_field.", species[g].name, ".velocity: advection terms are not built yet");
+    struct { Term::Kind k, jk; const char* key; } two[] = {
+        {Term::Reaction, Term::ReactionJac, "reaction"}, {Term::Storage, Term::StorageJac, "storage"}};
+    for (auto& tk : two) {
+      const PTree& t = f.sub(tk.key);
+      if (add(tk.k, g, -1, -1, t.get("expression", std::string())))
+        for (auto& wrt : t.sub("jacobian").sub_keys()) {
+          int j = species_index(wrt);
+          if (j >= 0) add(tk.jk, g, j, -1, t.sub("jacobian").sub(wrt).get("expression", std::string()));
+        }
+    }
+    const PTree& cd = f.sub("cross_diffusion");
+    for (auto& wrt : cd.sub_keys()) {
+      int j = species_index(wrt);
+      if (j < 0) continue;
+      const PTree& d = cd.sub(wrt);
+      if (d.get("type", std::string("scalar")) != "scalar")
+        fail("cross_diffusion.", wrt, ".type = tensor is not built yet");
+      if (add(Term::Diff, g, j, -1, d.get("expression", std::string())))
+        for (auto& kk : d.sub("jacobian").sub_keys()) {
+          int k = species_index(kk);
+          if (k >= 0 && !expr_is_absent(d.sub("jacobian").sub(kk).get("expression", std::string())))
+            fail("cross_diffusion.", wrt, ".jacobian: non-linear diffusion Jacobians are not built yet");
+        }
+    }
+    const PTree& of = f.sub("outflow");
+    for (auto& cname : of.sub_keys()) {
+      auto it = std::find(comp_names.begin(), comp_names.end(), cname);
+      if (it == comp_names.end()) continue;
+      int l = (int)(it - comp_names.begin());
+      const PTree& o = of.sub(cname);
+      if (add(Term::Outflow, g, l, -1, o.get("expression", std::string())))
+        for (auto& kk : o.sub("jacobian").sub_keys()) {
+          int k = species_index(kk);
+          if (k >= 0) add(Term::OutflowJac, g, l, k, o.sub("jacobian").sub(kk).get("expression", std::string()));
+        }
+    }
+  }
+}
+
+int Model::species_index(const std::string& name) const {
+  for (int g = 0; g < nspec(); ++g)
+    if (species[g].name == name) return g;
+  return -1;
+}
+
+bool Model::has_outflow() const {
+  for (auto& t : terms)
+    if (t.kind == Term::Outflow) return true;
+  return false;
+}
+
+std::vector<std::pair<int, int>> Model::species_pairs() const {
+  std::set<std::pair<int, int>> s;
+  for (auto& t : terms) {
+    if (t.kind == Term::ReactionJac || t.kind == Term::StorageJac || t.kind == Term::Diff) s.insert({t.i, t.j});
+    else if (t.kind == Term::Storage) s.insert({t.i, t.i});
+    else if (t.kind == Term::DiffJac) s.insert({t.i, t.k});
+  }
+  std::vector<std::pair<int, int>> out;
+  for (auto& p : s)
+    if (species[p.first].comp == species[p.second].comp) out.push_back(p);
+  return out;
+}
+
+std::vector<std::pair<int, int>> Model::outflow_pairs() const {
+  std::set<std::pair<int, int>> s;
+  for (auto& t : terms)
+    if (t.kind == Term::Outflow) s.insert({species[t.i].comp, t.j});
+  return {s.begin(), s.end()};
+}
+
+NodeP Model::compile(const std::string& text) const { return resolve_expr(parse_expr(text), ctx); }
+
+double Model::eval_host(const NodeP& ast, const double* pos, double time, const double* cell,
+                        double in_volume, double in_boundary) const {
+  return eval_expr(ast, [&](const std::string& n) -> double {
+    if (n == "time") return time;
+    if (n == "in_volume") return in_volume;
+    if (n == "in_boundary") return in_boundary;
+    if (n == "in_skeleton" || n == "integration_factor" || n == "entity_volume") return 0.0;
+    for (int a = 0; a < 3; ++a) {
+      if (n == std::string("position_") + kAxis[a]) return a < dim ? pos[a] : 0.0;
+      if (n == std::string("normal_") + kAxis[a]) return 0.0;
+    }
+    for (size_t k = 0; k < cell_keys.size(); ++k)
+      if (n == cell_keys[k]) return cell ? cell[k] : 0.0;
+    fail("unknown symbol '", n, "' in a setup expression");
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA lowering.  One struct per compartment (volume terms) and one per directional outflow pair.
+namespace {
+
+struct SymbolMap {
+  const Model& m;
+  int cs, ct;          // own compartment; other-side compartment (-1: volume context)
+  bool codim1;
+  std::string operator()(const std::string& n) const {
+    if (n == "time") return "c.time";
+    if (n == "integration_factor") return "c.integration_factor";
+    if (n == "entity_volume") return "c.entity_volume";
+    if (n == "in_volume") return "c.in_volume";
+    if (n == "in_boundary") return "c.in_boundary";
+    if (n == "in_skeleton") return "c.in_skeleton";
+    for (int a = 0; a < 3; ++a) {
+      if (n == std::string("position_") + kAxis[a]) return a < m.dim ? "c.pos[" + std::to_string(a) + "]" : "0.0";
+      if (n == std::string("normal_") + kAxis[a]) {
+        if (!codim1) return "";
+        return a < m.dim ? "c.nrm[" + std::to_string(a) + "]" : "0.0";
+      }
+    }
+    for (size_t k = 0; k < m.cell_keys.size(); ++k)
+      if (n == m.cell_keys[k]) return "c.cell[" + std::to_string(k) + "]";
+    for (int g = 0; g < m.nspec(); ++g) {
+      const auto& s = m.species[g];
+      auto side = [&](const char* u) { return std::string(u) + "[" + std::to_string(s.local) + "]"; };
+      if (n == s.name) {
+        if (s.comp == cs) return side(codim1 ? "us" : "u");
+        if (codim1 && s.comp == ct) return side("ut");
+        return "0.0";  // species without support here: value stays 0 (LocalEquations::clear)
+      }
+      for (int a = 0; a < 3; ++a)
+        if (n == "grad_" + s.name + "_" + kAxis[a]) {
+          if (a >= m.dim) return "0.0";
+          std::string ax = "[" + std::to_string(a) + "]";
+          if (s.comp == cs) return side(codim1 ? "gs" : "g") + ax;
+          if (codim1 && s.comp == ct) return side("gt") + ax;
+          return "0.0";
+        }
+    }
+    return "";
+  }
+};
+
+bool depends_on_point(const NodeP& ast) {
+  std::vector<std::string> v;
+  collect_vars(ast, v);
+  for (auto& n : v)
+    if (n != "time" && n != "entity_volume" && n != "in_volume" && n != "in_boundary" && n != "in_skeleton")
+      return true;   // position, cell data are per element but harmless; species values are per point
+  return false;
+}
+
+}  // namespace
+
+std::string Model::cuda_source() const {
+  std::ostringstream o;
+  o << "// generated by dune_copasi_b200 Model::cuda_source()\n";
+  o << "#define DC_DIM " << dim << "\n#define DC_NKEYS " << cell_keys.size() << "\n#define DC_NCOMP " << ncomp() << "\n";
+  o << "struct DcCtx { double time, entity_volume, integration_factor, in_volume, in_boundary, in_skeleton;"
+       " double pos[3]; double nrm[3]; double cell[" << std::max<size_t>(1, cell_keys.size()) << "]; };\n";
+  o << "template <int N> __device__ __forceinline__ double dc_powi(double x) { double r = x;\n"
+       "#pragma unroll\n  for (int i = 1; i < N; ++i) r *= x; return r; }\n";
+  o << "__device__ __forceinline__ double dc_sgn(double x) { return (double)((x > 0.0) - (x < 0.0)); }\n";
+  o << "__device__ __forceinline__ double dc_min(double a, double b) { return a < b ? a : b; }\n";
+  o << "__device__ __forceinline__ double dc_max(double a, double b) { return a > b ? a : b; }\n";
+  o << "template <int C> struct DcComp;\ntemplate <int P> struct DcOutflow;\n";
+  auto pairs = species_pairs();
+  for (int c = 0; c < ncomp(); ++c) {
+    int ns = comp_nspec[c], g0 = comp_first[c];
+    SymbolMap sym{*this, c, -1, false};
+    auto code = [&](const Term& t) { return to_cuda(t.ast, sym); };
+    auto find = [&](Term::Kind k, int i) -> const Term* {
+      for (auto& t : terms) if (t.kind == k && t.i == i) return &t;
+      return nullptr;
+    };
+    bool has_mass = false, has_stiff = false, has_diff = false, diff_const = true;
+    for (auto& t : terms) {
+      if (species[t.i].comp != c) continue;
+      if (t.kind == Term::Storage) has_mass = true;
+      if (t.kind == Term::Reaction) has_stiff = true;
+      if (t.kind == Term::Diff && species[t.j].comp == c) {
+        has_stiff = has_diff = true;
+        if (depends_on_point(t.ast)) diff_const = false;
+      }
+    }
+    o << "template <> struct DcComp<" << c << "> {\n";
+    o << "  static constexpr int NS = " << std::max(ns, 1) << ";\n  static constexpr int NS_REAL = " << ns << ";\n";
+    o << "  static constexpr bool HAS_MASS = " << has_mass << ", HAS_STIFF = " << has_stiff
+      << ", HAS_DIFF = " << has_diff << ", DIFF_CONST = " << diff_const << ";\n";
+    // pattern mask (which species pairs exist in the sparsity pattern)
+    {
+      int n = std::max(ns, 1);
+      std::vector<unsigned long long> words((n * n + 63) / 64, 0ull);
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+          if (std::find(pairs.begin(), pairs.end(), std::make_pair(g0 + i, g0 + j)) != pairs.end())
+            words[(i * n + j) >> 6] |= 1ull << ((i * n + j) & 63);
+      o << "  __host__ __device__ static constexpr bool pair(int i, int j) {\n    const unsigned long long m[" << words.size() << "] = {";
+      for (size_t w = 0; w < words.size(); ++w) o << words[w] << "ull" << (w + 1 < words.size() ? "," : "");
+      o << "};\n    return (m[(i * NS + j) >> 6] >> ((i * NS + j) & 63)) & 1ull;\n  }\n";
+    }
+    // ---- scalar part of the residual at a point
+    o << "  // sc[i] = wA*(-R_i) + wM*(u_i*storage_i)   (local_operator.hh:479-480)\n";
+    o << "  __device__ __forceinline__ static void scalar(const DcCtx& c, const double* u, const double (*g)[DC_DIM], double wM, double wA, double* sc) {\n";
+    for (int i = 0; i < ns; ++i) {
+      const Term* r = find(Term::Reaction, g0 + i);
+      const Term* s = find(Term::Storage, g0 + i);
+      o << "    sc[" << i << "] = ";
+      if (!r && !s) o << "0.0";
+      if (r) o << "wA * (-(" << code(*r) << "))";
+      if (s) o << (r ? " + " : "") << "wM * (u[" << i << "] * (" << code(*s) << "))";
+      o << ";\n";
+    }
+    o << "    (void)c; (void)u; (void)g; (void)wM; (void)wA; (void)sc;\n  }\n";
+    // ---- diffusive flux
+    o << "  // fl[i][k] = -wA * sum_j D_ij * grad(u_j)[k]   (local_operator.hh:481-483)\n";
+    o << "  __device__ __forceinline__ static void flux(const DcCtx& c, const double* u, const double (*g)[DC_DIM], double wA, double (*fl)[DC_DIM]) {\n";
+    for (int i = 0; i < ns; ++i) {
+      o << "    {";
+      for (int k = 0; k < dim; ++k) o << " fl[" << i << "][" << k << "] = 0.0;";
+      o << "\n";
+      for (auto& t : terms)
+        if (t.kind == Term::Diff && t.i == g0 + i && species[t.j].comp == c) {
+          int j = species[t.j].local;
+          o << "      { const double D = wA * (" << code(t) << ");";
+          for (int k = 0; k < dim; ++k) o << " fl[" << i << "][" << k << "] -= D * g[" << j << "][" << k << "];";
+          o << " }\n";
+        }
+      o << "    }\n";
+    }
+    o << "    (void)c; (void)u; (void)g; (void)wA; (void)fl;\n  }\n";
+    // ---- Jacobian coefficients
+    o << "  // jm[i][j]: coefficient of phi_a*phi_b = wA*(-dR_i/du_j) + wM*(stg_i*delta_ij + dstg_i/du_j*u_i)\n"
+         "  //   (local_operator.hh:605-641)\n";
+    o << "  __device__ __forceinline__ static void jac_mass(const DcCtx& c, const double* u, const double (*g)[DC_DIM], double wM, double wA, double (*jm)[NS]) {\n";
+    o << "    for (int i = 0; i < NS; ++i) for (int j = 0; j < NS; ++j) jm[i][j] = 0.0;\n";
+    for (auto& t : terms) {
+      if (species[t.i].comp != c) continue;
+      int i = species[t.i].local;
+      if (t.kind == Term::ReactionJac && species[t.j].comp == c)
+        o << "    jm[" << i << "][" << species[t.j].local << "] += wA * (-(" << code(t) << "));\n";
+      if (t.kind == Term::Storage)
+        o << "    jm[" << i << "][" << i << "] += wM * (" << code(t) << ");\n";
+      if (t.kind == Term::StorageJac && species[t.j].comp == c)
+        o << "    jm[" << i << "][" << species[t.j].local << "] += wM * ((" << code(t) << ") * u[" << i << "]);\n";
+    }
+    o << "    (void)c; (void)u; (void)g; (void)wM; (void)wA;\n  }\n";
+    o << "  // jd[i][j]: coefficient of grad(phi_a).grad(phi_b) = wA*D_ij   (local_operator.hh:674-685)\n";
+    o << "  __device__ __forceinline__ static void jac_diff(const DcCtx& c, const double* u, const double (*g)[DC_DIM], double wA, double (*jd)[NS]) {\n";
+    o << "    for (int i = 0; i < NS; ++i) for (int j = 0; j < NS; ++j) jd[i][j] = 0.0;\n";
+    for (auto& t : terms)
+      if (t.kind == Term::Diff && species[t.i].comp == c && species[t.j].comp == c)
+        o << "    jd[" << species[t.i].local << "][" << species[t.j].local << "] += wA * (" << code(t) << ");\n";
+    o << "    (void)c; (void)u; (void)g; (void)wA;\n  }\n";
+    o << "};\n";
+  }
+  // ---- outflow (skeleton / boundary) per directional compartment pair
+  auto opairs = outflow_pairs();
+  o << "#define DC_NOUTFLOW " << opairs.size() << "\n";
+  for (size_t p = 0; p < opairs.size(); ++p) {
+    int cs = opairs[p].first, ct = opairs[p].second;
+    bool boundary = cs == ct;
+    int nss = comp_nspec[cs], nst = boundary ? 0 : comp_nspec[ct];
+    SymbolMap sym{*this, cs, boundary ? -1 : ct, true};
+    o << "template <> struct DcOutflow<" << p << "> {\n";
+    o << "  static constexpr int CS = " << cs << ", CT = " << ct << ", NSS = " << nss << ", NST = " << std::max(nst, 1)
+      << ", NST_REAL = " << nst << ";\n  static constexpr bool BOUNDARY = " << boundary << ";\n";
+    std::vector<std::vector<int>> ps(nss, std::vector<int>(nss, 0)), pt(nss, std::vector<int>(std::max(nst, 1), 0));
+    std::ostringstream fl, jc;
+    for (int i = 0; i < nss; ++i) fl << "    T[" << i << "] = 0.0;\n";
+    for (auto& t : terms) {
+      if (species[t.i].comp != cs || t.j != ct) continue;
+      int i = species[t.i].local;
+      if (t.kind == Term::Outflow) fl << "    T[" << i << "] = " << to_cuda(t.ast, sym) << ";\n";
+      if (t.kind == Term::OutflowJac) {
+        const auto& sk = species[t.k];
+        if (sk.comp == cs) {
+          ps[i][sk.local] = 1;
+          jc << "    js[" << i << "][" << sk.local << "] += " << to_cuda(t.ast, sym) << ";\n";
+        } else if (!boundary && sk.comp == ct) {
+          pt[i][sk.local] = 1;
+          jc << "    jt[" << i << "][" << sk.local << "] += " << to_cuda(t.ast, sym) << ";\n";
+        }
+      }
+    }
+    auto mask = [&](const char* name, const std::vector<std::vector<int>>& m, int cols) {
+      std::vector<unsigned long long> words((m.size() * cols + 63) / 64 + 1, 0ull);
+      for (size_t i = 0; i < m.size(); ++i)
+        for (int j = 0; j < cols; ++j)
+          if (m[i][j]) words[(i * cols + j) >> 6] |= 1ull << ((i * cols + j) & 63);
+      o << "  __host__ __device__ static constexpr bool " << name << "(int i, int j) {\n    const unsigned long long m[" << words.size() << "] = {";
+      for (size_t w = 0; w < words.size(); ++w) o << words[w] << "ull" << (w + 1 < words.size() ? "," : "");
+      o << "};\n    return (m[(i * " << cols << " + j) >> 6] >> ((i * " << cols << " + j) & 63)) & 1ull;\n  }\n";
+    };
+    mask("pair_s", ps, nss);
+    mask("pair_t", pt, std::max(nst, 1));
+    o << "  // T[i]: outflow of own species i through the facet (local_operator.hh:920-927)\n";
+    o << "  __device__ __forceinline__ static void flux(const DcCtx& c, const double* us, const double (*gs)[DC_DIM], const double* ut, const double (*gt)[DC_DIM], double* T) {\n"
+      << fl.str() << "    (void)c; (void)us; (void)gs; (void)ut; (void)gt;\n  }\n";
+    o << "  // js/jt: dT_i/du_k for k on the own / other side (local_operator.hh:1127-1142)\n";
+    o << "  __device__ __forceinline__ static void jacobian(const DcCtx& c, const double* us, const double (*gs)[DC_DIM], const double* ut, const double (*gt)[DC_DIM], double (*js)[NSS], double (*jt)[NST]) {\n"
+      << "    for (int i = 0; i < NSS; ++i) { for (int j = 0; j < NSS; ++j) js[i][j] = 0.0; for (int j = 0; j < NST; ++j) jt[i][j] = 0.0; }\n"
+      << jc.str() << "    (void)c; (void)us; (void)gs; (void)ut; (void)gt;\n  }\n";
+    o << "};\n";
+  }
+  return o.str();
+}
+
+}  // namespace dcb

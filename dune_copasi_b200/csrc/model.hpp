@@ -1,0 +1,65 @@
+// Model description: what dune/copasi/model/diffusion_reaction/local_equations.hh:617-700 builds
+// from the ini ([compartments], [parser_context], [model.scalar_field.*]) -- which terms exist per
+// species -- plus the lowering of those terms to CUDA source that NVRTC fuses into the assembly
+// kernels (replaces the per-quadrature-point type-erased functor calls of
+// local_equations.hh:101-146 / functor_factory_parser.impl.hh:116-182).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "expr.hpp"
+#include "ptree.hpp"
+
+namespace dcb {
+
+struct Term {
+  enum Kind { Reaction, ReactionJac, Storage, StorageJac, Diff, DiffJac, Outflow, OutflowJac };
+  Kind kind;
+  int i = -1;    // species (global id)
+  int j = -1;    // wrt species (Jac / Diff) or target compartment (Outflow*)
+  int k = -1;    // jac wrt species of DiffJac / OutflowJac
+  NodeP ast;     // resolved + folded
+  std::string text;
+};
+
+struct SpeciesInfo {
+  std::string name;
+  int comp = -1, local = -1;
+  std::string initial, constrain_boundary;   // raw expressions ("" if absent)
+};
+
+class Model {
+ public:
+  // dim and the cell-data keys are part of the symbol table
+  Model(const PTree& cfg, int dim, const std::vector<std::string>& cell_keys);
+
+  int dim;
+  bool is_linear = false;
+  std::vector<std::string> cell_keys;
+  std::vector<std::string> comp_names;
+  std::vector<NodeP> comp_expr;
+  std::vector<SpeciesInfo> species;           // compartment-major
+  std::vector<int> comp_nspec, comp_first;    // per compartment
+  std::vector<Term> terms;
+  ParserContext ctx;
+  PTree cfg;
+
+  int ncomp() const { return (int)comp_names.size(); }
+  int nspec() const { return (int)species.size(); }
+  int species_index(const std::string& name) const;
+  bool has_outflow() const;
+  // species couplings (i,j) of the volume sparsity pattern, local_operator.hh:276-338
+  std::vector<std::pair<int, int>> species_pairs() const;
+  // directional compartment pairs (cs -> ct) that carry an outflow term; ct == cs means boundary
+  std::vector<std::pair<int, int>> outflow_pairs() const;
+
+  // host evaluation of a resolved expression with position/time/cell data bound (setup work only)
+  double eval_host(const NodeP& ast, const double* pos, double time, const double* cell,
+                   double in_volume, double in_boundary) const;
+  NodeP compile(const std::string& text) const;   // parse + resolve against the context
+
+  // CUDA source of the per-model device functions (see kernels/assembly.cuh for the consumers)
+  std::string cuda_source() const;
+};
+
+}  // namespace dcb

@@ -1,0 +1,410 @@
+#include "operator.hpp"
+
+#include <parallel/algorithm>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace dcb {
+
+namespace {
+
+inline uint64_t spread3(uint64_t x) {   // 21 bits -> every third bit
+  x &= 0x1fffff;
+  x = (x | x << 32) & 0x1f00000000ffffULL;
+  x = (x | x << 16) & 0x1f0000ff0000ffULL;
+  x = (x | x << 8) & 0x100f00f00f00f00fULL;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+  x = (x | x << 2) & 0x1249249249249249ULL;
+  return x;
+}
+inline uint64_t spread2(uint64_t x) {   // 31 bits -> every second bit
+  x &= 0x7fffffff;
+  x = (x | x << 16) & 0x0000ffff0000ffffULL;
+  x = (x | x << 8) & 0x00ff00ff00ff00ffULL;
+  x = (x | x << 4) & 0x0f0f0f0f0f0f0f0fULL;
+  x = (x | x << 2) & 0x3333333333333333ULL;
+  x = (x | x << 1) & 0x5555555555555555ULL;
+  return x;
+}
+
+}  // namespace
+
+DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<const Grid> g)
+    : model(std::move(m)), grid(std::move(g)) {
+  require_device();
+  if (grid->elem_comp.size() != (size_t)grid->ne) fail("grid is not bound to a model");
+  ndofs = grid->ndofs;
+  owned = la::Ranges::all(ndofs);
+  const PTree& acfg = model->cfg.sub("model.assembly.b200");
+  scheme = acfg.get("scheme", std::string("patch"));
+  if (scheme != "patch" && scheme != "atomic") fail("model.assembly.b200.scheme must be 'patch' or 'atomic'");
+  patch_pn_ = acfg.get("patch_vertices", 768);
+  patch_cbuf_ = acfg.get("patch_buffer", 4096);
+  patch_threads_ = acfg.get("patch_threads", 256);
+  if (patch_pn_ < 16 || patch_pn_ > 16384) fail("model.assembly.b200.patch_vertices out of range");
+  DCB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+
+  // ---- kernels for this model
+  jit_defines_ = jit_defines(*model);
+  // the hot group is compiled up front, the others on first use
+  kernel(scheme == "patch" ? JitGroup::Patch : JitGroup::Element, "");
+
+  // ---- mesh on the device
+  const int nd = grid->nd(), ncomp = model->ncomp();
+  coords_.upload(grid->coords, stream);
+  elems_.upload(grid->elems, stream);
+  if (!grid->cell_data.empty()) cell_.upload(grid->cell_data, stream);
+  comp_elem_ids_.resize(ncomp);
+  comp_vdof_.resize(ncomp);
+  comp_nelem_.assign(ncomp, 0);
+  for (int c = 0; c < ncomp; ++c) {
+    std::vector<int> ids;
+    for (int64_t e = 0; e < grid->ne; ++e)
+      if (grid->elem_comp[e] == c) ids.push_back((int)e);
+    comp_nelem_[c] = (int64_t)ids.size();
+    bool identity_elems = (int64_t)ids.size() == grid->ne;
+    if (!identity_elems) comp_elem_ids_[c].upload(ids, stream);
+    // vertex -> dof map; skipped when it is the closed form offset + v*ns
+    bool identity_dofs = (int64_t)grid->comp_vertices[c].size() == grid->nv;
+    if (!identity_dofs) comp_vdof_[c].upload(grid->comp_vdof[c], stream);
+  }
+  // ---- facet lists per directional outflow pair
+  auto opairs = model->outflow_pairs();
+  facets_.resize(opairs.size());
+  for (size_t p = 0; p < opairs.size(); ++p) {
+    int cs = opairs[p].first, ct = opairs[p].second;
+    std::vector<long long> fs, fo;
+    std::vector<int> ls, lo;
+    for (size_t f = 0; f < grid->f_in.size(); ++f) {
+      int64_t ei = grid->f_in[f], eo = grid->f_out[f];
+      int ci = grid->elem_comp[ei], co = eo >= 0 ? grid->elem_comp[eo] : -1;
+      if (cs == ct) {   // boundary outflow
+        if (eo < 0 && ci == cs) { fs.push_back(ei); fo.push_back(-1); ls.push_back(grid->f_lin[f]); lo.push_back(-1); }
+      } else if (eo >= 0) {
+        if (ci == cs && co == ct) { fs.push_back(ei); fo.push_back(eo); ls.push_back(grid->f_lin[f]); lo.push_back(grid->f_lout[f]); }
+        if (co == cs && ci == ct) { fs.push_back(eo); fo.push_back(ei); ls.push_back(grid->f_lout[f]); lo.push_back(grid->f_lin[f]); }
+      }
+    }
+    FacetList& F = facets_[p];
+    F.cs = cs; F.ct = ct; F.n = (int64_t)fs.size();
+    F.f_self.upload(fs, stream); F.f_other.upload(fo, stream);
+    F.f_lself.upload(ls, stream); F.f_lother.upload(lo, stream);
+  }
+  // ---- constraints
+  grid->constraints(*model, h_cdofs, h_cvals);
+  ncons = (int64_t)h_cdofs.size();
+  if (ncons) {
+    cdofs.upload(h_cdofs, stream);
+    cvals.upload(h_cvals, stream);
+    std::vector<unsigned char> mask(ndofs, 0);
+    for (auto d : h_cdofs) mask[d] = 1;
+    cmask.upload(mask, stream);
+  }
+  if (scheme == "patch") build_patches();
+  DCB_CUDA(cudaStreamSynchronize(stream));
+}
+
+cudaKernel_t DeviceOperator::kernel(JitGroup group, const std::string& name) {
+  auto& mod = jit_[(int)group];
+  if (!mod) {
+    mod = std::make_unique<JitModule>();
+    mod->load(jit_compile_cached(jit_source(*model, jit_defines_, group)));
+  }
+  return name.empty() ? nullptr : mod->kernel(name);
+}
+
+DeviceOperator::~DeviceOperator() {
+  if (stream) cudaStreamDestroy(stream);
+}
+
+void DeviceOperator::profile_enable(bool on) {
+  profiling_ = on;
+  if (!on) profile_collect();
+}
+void DeviceOperator::prof_begin(const char* kind) {
+  if (!profiling_) return;
+  ProfRec r;
+  r.kind = kind;
+  DCB_CUDA(cudaEventCreate(&r.a));
+  DCB_CUDA(cudaEventCreate(&r.b));
+  DCB_CUDA(cudaEventRecord(r.a, stream));
+  prof_.push_back(r);
+}
+void DeviceOperator::prof_end() {
+  if (!profiling_ || prof_.empty()) return;
+  DCB_CUDA(cudaEventRecord(prof_.back().b, stream));
+}
+std::map<std::string, std::pair<double, long long>> DeviceOperator::profile_collect() {
+  std::map<std::string, std::pair<double, long long>> out;
+  if (prof_.empty()) return out;
+  DCB_CUDA(cudaStreamSynchronize(stream));
+  for (auto& r : prof_) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      out[r.kind].first += ms;
+      out[r.kind].second += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  prof_.clear();
+  return out;
+}
+
+int64_t DeviceOperator::bdiag_size() const {
+  int64_t n = 0;
+  for (int c = 0; c < model->ncomp(); ++c)
+    n += (grid->comp_offset[c + 1] - grid->comp_offset[c]) * model->comp_nspec[c];
+  return n;
+}
+
+int64_t DeviceOperator::bdiag_shift(int c) const {
+  int64_t base = 0;
+  for (int k = 0; k < c; ++k) base += (grid->comp_offset[k + 1] - grid->comp_offset[k]) * model->comp_nspec[k];
+  return base - grid->comp_offset[c] * model->comp_nspec[c];
+}
+
+// ---------------------------------------------------------------------------------- patches
+void DeviceOperator::build_patches() {
+  const int nd = grid->nd(), dim = grid->dim, ncomp = model->ncomp();
+  const int64_t ne = grid->ne;
+  const int pe_max = 16384;   // (local element << 2 | local vertex) must fit 16 bits
+  // bounding box for the Morton keys
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int64_t v = 0; v < grid->nv; ++v)
+    for (int k = 0; k < dim; ++k) {
+      lo[k] = std::min(lo[k], grid->coords[v * dim + k]);
+      hi[k] = std::max(hi[k], grid->coords[v * dim + k]);
+    }
+  const double bits = dim == 3 ? 2097151.0 : 2147483647.0;
+  patches_.resize(ncomp);
+  std::vector<double> cell_sorted;
+  const size_t nkeys = grid->cell_keys.size();
+  // total elements with a compartment (patch element order = compartments concatenated)
+  int64_t total = 0;
+  for (int c = 0; c < ncomp; ++c) total += model->comp_nspec[c] > 0 ? comp_nelem_[c] : 0;
+  ne_patch_total_ = total;
+  if (nkeys) cell_sorted.resize(nkeys * (size_t)total);
+  int64_t ebase = 0;
+  std::vector<int32_t> mark(grid->nv, -1);
+  for (int c = 0; c < ncomp; ++c) {
+    PatchSet& P = patches_[c];
+    P.comp = c;
+    if (model->comp_nspec[c] == 0 || comp_nelem_[c] == 0) continue;
+    // 1. Morton order of the element centroids
+    std::vector<std::pair<uint64_t, int32_t>> order;
+    order.reserve(comp_nelem_[c]);
+    for (int64_t e = 0; e < ne; ++e)
+      if (grid->elem_comp[e] == c) order.push_back({0, (int32_t)e});
+#pragma omp parallel for schedule(static)
+    for (int64_t t = 0; t < (int64_t)order.size(); ++t) {
+      int64_t e = order[t].second;
+      uint64_t q[3] = {0, 0, 0};
+      for (int k = 0; k < dim; ++k) {
+        double cen = 0;
+        for (int a = 0; a < nd; ++a) cen += grid->coords[(int64_t)grid->elems[e * nd + a] * dim + k];
+        cen /= nd;
+        double span = hi[k] - lo[k];
+        q[k] = (uint64_t)(span > 0 ? (cen - lo[k]) / span * bits : 0.0);
+      }
+      order[t].first = dim == 3 ? (spread3(q[0]) | spread3(q[1]) << 1 | spread3(q[2]) << 2)
+                                : (spread2(q[0]) | spread2(q[1]) << 1);
+    }
+    __gnu_parallel::sort(order.begin(), order.end());
+    const int64_t n = (int64_t)order.size();
+    // 2. greedy cuts under the vertex / element budgets
+    std::vector<int> elem_ptr{0};
+    {
+      int cur_nodes = 0, pid = 0;
+      std::fill(mark.begin(), mark.end(), -1);
+      for (int64_t t = 0; t < n; ++t) {
+        int64_t e = order[t].second;
+        int fresh = 0;
+        for (int a = 0; a < nd; ++a) fresh += mark[grid->elems[e * nd + a]] != pid;
+        // duplicates inside one element do not occur (simplex vertices are distinct)
+        if (cur_nodes + fresh > patch_pn_ || (t - elem_ptr.back()) >= pe_max) {
+          elem_ptr.push_back((int)t);
+          ++pid;
+          cur_nodes = 0;
+          fresh = nd;
+        }
+        for (int a = 0; a < nd; ++a) mark[grid->elems[e * nd + a]] = pid;
+        cur_nodes += fresh;
+      }
+      elem_ptr.push_back((int)n);
+    }
+    const int np = (int)elem_ptr.size() - 1;
+    // 3. per patch: vertex list (ascending), local connectivity, vertex -> element adjacency
+    std::vector<int> node_cnt(np + 1, 0);
+    std::vector<std::vector<int>> pnodes(np);
+    std::vector<unsigned short> lconn((size_t)n * 4, 0), adj((size_t)n * nd);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int p = 0; p < np; ++p) {
+      auto& nodes = pnodes[p];
+      nodes.reserve((size_t)(elem_ptr[p + 1] - elem_ptr[p]) * nd);
+      for (int t = elem_ptr[p]; t < elem_ptr[p + 1]; ++t)
+        for (int a = 0; a < nd; ++a) nodes.push_back(grid->elems[(int64_t)order[t].second * nd + a]);
+      std::sort(nodes.begin(), nodes.end());
+      nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+      for (int t = elem_ptr[p]; t < elem_ptr[p + 1]; ++t)
+        for (int a = 0; a < nd; ++a) {
+          int v = grid->elems[(int64_t)order[t].second * nd + a];
+          lconn[(size_t)t * 4 + a] =
+              (unsigned short)(std::lower_bound(nodes.begin(), nodes.end(), v) - nodes.begin());
+        }
+      node_cnt[p + 1] = (int)nodes.size();
+    }
+    std::vector<int> node_ptr(np + 1, 0);
+    for (int p = 0; p < np; ++p) node_ptr[p + 1] = node_ptr[p] + node_cnt[p + 1];
+    std::vector<int> nodes_flat(node_ptr[np]);
+    std::vector<int> adj_ptr((size_t)node_ptr[np] + 1, 0);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int p = 0; p < np; ++p) {
+      std::copy(pnodes[p].begin(), pnodes[p].end(), nodes_flat.begin() + node_ptr[p]);
+      // counts per local vertex (stored shifted by one, prefix-summed globally below)
+      for (int t = elem_ptr[p]; t < elem_ptr[p + 1]; ++t)
+        for (int a = 0; a < nd; ++a) adj_ptr[(size_t)node_ptr[p] + lconn[(size_t)t * 4 + a] + 1]++;
+    }
+    for (size_t i = 0; i + 1 < adj_ptr.size(); ++i) adj_ptr[i + 1] += adj_ptr[i];
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int p = 0; p < np; ++p) {
+      std::vector<int> cur(adj_ptr.begin() + node_ptr[p], adj_ptr.begin() + node_ptr[p + 1]);
+      for (int t = elem_ptr[p]; t < elem_ptr[p + 1]; ++t)     // ascending local element index
+        for (int a = 0; a < nd; ++a) {
+          int ln = lconn[(size_t)t * 4 + a];
+          adj[cur[ln]++] = (unsigned short)(((t - elem_ptr[p]) << 2) | a);
+        }
+    }
+    // patch-ordered cell data
+    for (size_t k = 0; k < nkeys; ++k)
+      for (int64_t t = 0; t < n; ++t)
+        cell_sorted[k * (size_t)total + ebase + t] = grid->cell_data[k * ne + order[t].second];
+    // element ranges are stored relative to the global patch element order
+    for (auto& x : elem_ptr) x += (int)ebase;
+    P.npatch = np;
+    P.elem_begin = ebase;
+    P.nelem = n;
+    P.total_nodes = node_ptr[np];
+    P.node_ptr.upload(node_ptr, stream);
+    P.nodes.upload(nodes_flat, stream);
+    P.elem_ptr.upload(elem_ptr, stream);
+    P.adj_ptr.upload(adj_ptr, stream);
+    P.lconn.upload(lconn, stream);
+    P.adj.upload(adj, stream);
+    DCB_CUDA(cudaStreamSynchronize(stream));
+    ebase += n;
+  }
+  if (nkeys) cell_patch_.upload(cell_sorted, stream);
+  DCB_CUDA(cudaStreamSynchronize(stream));
+}
+
+// ---------------------------------------------------------------------------------- launches
+void DeviceOperator::launch_volume(const char* kind, int mode, double t, double wM, double wA,
+                                   const double* x, const double* z, double* r, double* vals,
+                                   double* bdiag) {
+  const int ncomp = model->ncomp();
+  const bool use_patch = scheme == "patch" && mode != 3;   // mode 3 = CSR fill (element kernels)
+  for (int c = 0; c < ncomp; ++c) {
+    const int ns = model->comp_nspec[c];
+    if (ns == 0 || comp_nelem_[c] == 0) continue;
+    if (use_patch) {
+      const PatchSet& P = patches_[c];
+      DcPatchArgs a{};
+      a.coords = coords_.p;
+      a.patch_node_ptr = P.node_ptr.p; a.patch_nodes = P.nodes.p; a.patch_elem_ptr = P.elem_ptr.p;
+      a.lconn = P.lconn.p - 0; a.adj = P.adj.p; a.adj_ptr = P.adj_ptr.p;
+      // lconn/adj are indexed by global patch element ids: shift the base pointers of this set
+      a.lconn = P.lconn.p - (size_t)P.elem_begin * 4;
+      a.vdof = comp_vdof_[c].p;
+      a.cell = cell_patch_.p; a.ne_total = ne_patch_total_;
+      a.npatch = P.npatch; a.dof_offset = (int)grid->comp_offset[c];
+      a.time = t; a.wM = wM; a.wA = wA;
+      a.x = x; a.z = z; a.r = r; a.bdiag = bdiag ? bdiag + bdiag_shift(c) : nullptr; a.cmask = cmask.p;
+      const int nv = mode == 2 ? ns * ns : ns;
+      size_t smem = sizeof(double) * ((size_t)patch_pn_ * (grid->dim + ns + (mode == 1 ? ns : 0) + nv) + patch_cbuf_);
+      static const char* names[3] = {"dc_k_patch_residual_", "dc_k_patch_apply_", "dc_k_patch_bdiag_"};
+      cudaKernel_t k = kernel(JitGroup::Patch, std::string(names[mode]) + std::to_string(c));
+      DCB_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = std::max(1, (int)(200 * 1024 / std::max<size_t>(smem, 1)));
+      unsigned gridsz = (unsigned)std::min<int64_t>(P.npatch, (int64_t)148 * std::min(per_sm, 8));
+      static const char* pk[3] = {"patch_residual", "patch_apply", "patch_bdiag"};
+      ProfScope ps(this, pk[mode]);
+      jit_launch(k, gridsz, patch_threads_, smem, stream, a);
+    } else {
+      DcVolArgs a{};
+      a.coords = coords_.p; a.elems = elems_.p; a.elem_ids = comp_elem_ids_[c].p; a.vdof = comp_vdof_[c].p;
+      a.cell = cell_.p; a.ne_total = grid->ne; a.n = comp_nelem_[c];
+      a.dof_offset = (int)grid->comp_offset[c];
+      a.time = t; a.wM = wM; a.wA = wA; a.x = x; a.z = z; a.r = r;
+      a.rowptr = (const long long*)rowptr.p; a.colidx = colidx.p; a.vals = vals;
+      a.bdiag = bdiag ? bdiag + bdiag_shift(c) : nullptr;
+      a.cmask = cmask.p;
+      cudaKernel_t k = kernel(mode == 3 ? JitGroup::Csr : JitGroup::Element, std::string(kind) + std::to_string(c));
+      static const char* ek[4] = {"elem_residual", "elem_apply", "elem_bdiag", "csr_fill"};
+      ProfScope ps(this, ek[mode]);
+      jit_launch(k, (unsigned)((a.n + 127) / 128), 128, 0, stream, a);
+    }
+    stats.launches++;
+  }
+}
+
+void DeviceOperator::launch_facets(const char* kind, double t, double wA, const double* x,
+                                   const double* z, double* r, double* vals, double* bdiag) {
+  for (size_t p = 0; p < facets_.size(); ++p) {
+    const FacetList& F = facets_[p];
+    if (F.n == 0) continue;
+    DcFacetArgs a{};
+    a.coords = coords_.p; a.elems = elems_.p;
+    a.f_self = F.f_self.p; a.f_other = F.f_other.p; a.f_lself = F.f_lself.p; a.f_lother = F.f_lother.p;
+    a.vdof_s = comp_vdof_[F.cs].p; a.vdof_t = comp_vdof_[F.ct].p;
+    a.cell = cell_.p; a.ne_total = grid->ne; a.n = F.n;
+    a.dof_offset_s = (int)grid->comp_offset[F.cs]; a.dof_offset_t = (int)grid->comp_offset[F.ct];
+    a.time = t; a.wA = wA; a.x = x; a.z = z; a.r = r;
+    a.rowptr = (const long long*)rowptr.p; a.colidx = colidx.p; a.vals = vals;
+    a.bdiag = bdiag ? bdiag + bdiag_shift(F.cs) : nullptr;
+    a.cmask = cmask.p;
+    cudaKernel_t k = kernel(JitGroup::Skeleton, std::string(kind) + std::to_string(p));
+    ProfScope ps(this, "facets");
+    jit_launch(k, (unsigned)((F.n + 63) / 64), 64, 0, stream, a);
+    stats.launches++;
+  }
+}
+
+void DeviceOperator::residual(double t, double wM, double wA, const double* x, double* r) {
+  launch_volume("dc_k_residual_volume_", 0, t, wM, wA, x, nullptr, r, nullptr, nullptr);
+  if (wA != 0.0) launch_facets("dc_k_skeleton_residual_", t, wA, x, nullptr, r, nullptr, nullptr);
+}
+
+void DeviceOperator::jacobian_apply(double t, double wM, double wA, const double* x, const double* z, double* y) {
+  launch_volume("dc_k_jacobian_apply_volume_", 1, t, wM, wA, x, z, y, nullptr, nullptr);
+  if (wA != 0.0) launch_facets("dc_k_skeleton_apply_", t, wA, x, z, y, nullptr, nullptr);
+}
+
+void DeviceOperator::block_diag(double t, double wM, double wA, const double* x, double* bdiag) {
+  launch_volume("dc_k_bdiag_volume_", 2, t, wM, wA, x, nullptr, nullptr, nullptr, bdiag);
+  if (wA != 0.0) launch_facets("dc_k_skeleton_bdiag_", t, wA, x, nullptr, nullptr, nullptr, bdiag);
+}
+
+void DeviceOperator::jacobian_csr(double t, double wM, double wA, const double* x, double* vals) {
+  ensure_csr();
+  launch_volume("dc_k_jacobian_volume_", 3, t, wM, wA, x, nullptr, nullptr, vals, nullptr);
+  if (wA != 0.0) launch_facets("dc_k_skeleton_jacobian_", t, wA, x, nullptr, nullptr, vals, nullptr);
+}
+
+void DeviceOperator::ensure_csr() {
+  if (rowptr.n) return;
+  grid->pattern(*model, h_rowptr, h_colidx);
+  nnz_ = h_rowptr[ndofs];
+  rowptr.upload(h_rowptr, stream);
+  colidx.upload(h_colidx, stream);
+  if (nnz_ < INT32_MAX) {
+    std::vector<int32_t> rp32(h_rowptr.begin(), h_rowptr.end());
+    rowptr32.upload(rp32, stream);
+  }
+  DCB_CUDA(cudaStreamSynchronize(stream));
+}
+
+}  // namespace dcb

@@ -1,0 +1,119 @@
+// Device-resident spatial operator: the instationary diffusion-reaction residual
+//   r += wM * M(u) + wA * A(t,u)
+// its Jacobian (assembled CSR, matrix-free apply, block diagonal) and the Dirichlet constraints.
+// This is the global face of the reference's local operator (local_operator.hh) as PDELab's
+// makeInstationaryMatrix{Based,Free}Assembler would drive it (make_step_operator.hh:291-293,
+// 403-405): apply(x, r) is additive (cf. :223), derivative(x) yields either the "container"
+// (CSR) or a matrix-free apply.
+#pragma once
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "grid.hpp"
+#include "jit.hpp"
+#include "kernels/kernel_args.h"
+#include "kernels/linalg.hpp"
+#include "model.hpp"
+
+namespace dcb {
+
+struct PatchSet {
+  int comp = 0;
+  int npatch = 0;
+  int64_t elem_begin = 0;   // offset of this compartment in patch element order
+  int64_t nelem = 0;
+  DeviceBuffer<int> node_ptr, nodes, elem_ptr, adj_ptr;
+  DeviceBuffer<unsigned short> lconn, adj;
+  // statistics (host)
+  int64_t total_nodes = 0;
+};
+
+struct FacetList {   // one directional outflow pair (cs -> ct)
+  int cs = 0, ct = 0;
+  int64_t n = 0;
+  DeviceBuffer<long long> f_self, f_other;
+  DeviceBuffer<int> f_lself, f_lother;
+};
+
+struct OperatorStats {
+  long long launches = 0;   // kernels launched by this operator (assembly + linear algebra)
+};
+
+class DeviceOperator {
+ public:
+  DeviceOperator(std::shared_ptr<const Model> model, std::shared_ptr<const Grid> grid);
+  ~DeviceOperator();
+
+  // all pointers are device pointers; everything is ordered on `stream`
+  void residual(double t, double wM, double wA, const double* x, double* r);
+  void jacobian_apply(double t, double wM, double wA, const double* x, const double* z, double* y);
+  void jacobian_csr(double t, double wM, double wA, const double* x, double* vals);
+  void block_diag(double t, double wM, double wA, const double* x, double* bdiag);
+
+  // sparsity pattern on the device (built on first use)
+  void ensure_csr();
+  int64_t nnz() const { return nnz_; }
+  int64_t bdiag_size() const;   // doubles in the block diagonal
+  // blocks of compartment c live at bdiag[bdiag_shift(c) + dof*ns_c + j] (dof = global row)
+  int64_t bdiag_shift(int c) const;
+
+  std::shared_ptr<const Model> model;
+  std::shared_ptr<const Grid> grid;
+  cudaStream_t stream = nullptr;
+  int64_t ndofs = 0;
+  std::string scheme;   // "patch" | "atomic"
+  OperatorStats stats;
+
+  // CSR pattern
+  DeviceBuffer<int64_t> rowptr;
+  DeviceBuffer<int32_t> rowptr32, colidx;
+  std::vector<int64_t> h_rowptr;
+  std::vector<int32_t> h_colidx;
+  // constraints
+  int64_t ncons = 0;
+  DeviceBuffer<int32_t> cdofs;
+  DeviceBuffer<double> cvals;
+  DeviceBuffer<unsigned char> cmask;   // empty when there are no constraints
+  std::vector<int32_t> h_cdofs;
+  std::vector<double> h_cvals;
+  // owned dof ranges (multi-GPU: set by the partition; default: everything)
+  la::Ranges owned;
+
+  // per-kernel-kind device timing with CUDA events on `stream` (off by default)
+  void profile_enable(bool on);
+  void prof_begin(const char* kind);
+  void prof_end();
+  // synchronises; kind -> (accumulated ms, launches); clears the record
+  std::map<std::string, std::pair<double, long long>> profile_collect();
+  struct ProfScope {
+    DeviceOperator* op;
+    ProfScope(DeviceOperator* o, const char* kind) : op(o) { op->prof_begin(kind); }
+    ~ProfScope() { op->prof_end(); }
+  };
+
+ private:
+  struct ProfRec { std::string kind; cudaEvent_t a = nullptr, b = nullptr; };
+  bool profiling_ = false;
+  std::vector<ProfRec> prof_;
+  void launch_volume(const char* kind, int mode, double t, double wM, double wA, const double* x,
+                     const double* z, double* r, double* vals, double* bdiag);
+  void launch_facets(const char* kind, double t, double wA, const double* x, const double* z,
+                     double* r, double* vals, double* bdiag);
+  void build_patches();
+  cudaKernel_t kernel(JitGroup group, const std::string& name);
+  std::map<int, std::unique_ptr<JitModule>> jit_;
+  std::string jit_defines_;
+  DeviceBuffer<double> coords_, cell_, cell_patch_;
+  DeviceBuffer<int> elems_;
+  std::vector<DeviceBuffer<int>> comp_elem_ids_, comp_vdof_;
+  std::vector<int64_t> comp_nelem_;
+  std::vector<PatchSet> patches_;
+  std::vector<FacetList> facets_;
+  int64_t nnz_ = 0;
+  int64_t ne_patch_total_ = 0;
+  size_t patch_smem_[3] = {0, 0, 0};
+  int patch_pn_ = 768, patch_cbuf_ = 4096, patch_threads_ = 256;
+};
+
+}  // namespace dcb

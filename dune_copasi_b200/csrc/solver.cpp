@@ -1,0 +1,218 @@
+#include "solver.hpp"
+
+#include <cmath>
+
+#include "comm.hpp"
+
+namespace dcb {
+
+LinearSolver::LinearSolver(std::shared_ptr<DeviceOperator> op, const PTree& cfg, Communicator* comm)
+    : op_(std::move(op)), comm_(comm) {
+  // defaults: the reference picks UMFPack (direct) when SuiteSparse exists, else BiCGSTAB
+  // (factory/inverse.hh:11-15); the direct solvers are not data parallel and not built here.
+  type = cfg.get("type", std::string("BiCGSTAB"));
+  if (type != "BiCGSTAB" && type != "CG")
+    fail("linear_solver.type = '", type, "' is not built for the B200 path (available: BiCGSTAB, CG)");
+  prec_type = cfg.get("preconditioner.type", std::string("Jacobi"));
+  if (prec_type != "Jacobi" && prec_type != "BlockJacobi" && prec_type != "Richardson")
+    fail("linear_solver.preconditioner.type = '", prec_type,
+         "' is not built for the B200 path (available: Richardson, Jacobi, BlockJacobi)");
+  if (cfg.get("preconditioner.iterations", 1) != 1)
+    fail("linear_solver.preconditioner.iterations != 1 is not built");
+  relaxation = cfg.get("preconditioner.relaxation", 1.0);
+  matrix_free = cfg.get("matrix_free", false);
+  verbosity = cfg.get("verbosity", 0);
+  auto range = cfg.get_vec("convergence_condition.iteration_range", {1, 500});   // iterative.hh:53-54
+  max_iterations = (int)range.back();
+  la::reduce_workspace_create(&ws_);
+  scal_.alloc(8);
+  hscal_.alloc(8);
+  for (auto& w : work_) w.alloc(op_->ndofs);
+  if (!matrix_free) {
+    op_->ensure_csr();
+    vals.alloc(op_->nnz());
+  }
+  if (prec_type == "Jacobi") dinv_.alloc(op_->ndofs);
+  if (prec_type == "BlockJacobi" || (matrix_free && prec_type == "Jacobi")) bdiag_.alloc(op_->bdiag_size());
+}
+
+LinearSolver::~LinearSolver() { la::reduce_workspace_destroy(&ws_); }
+
+void LinearSolver::linearize(double t, double wM, double wA, const double* x) {
+  t_ = t; wM_ = wM; wA_ = wA; x_ = x;
+  cudaStream_t s = op_->stream;
+  const Grid& g = *op_->grid;
+  const int ncomp = op_->model->ncomp();
+  if (!matrix_free) {
+    vals.zero(s);
+    op_->jacobian_csr(t, wM, wA, x, vals.p);
+    if (op_->ncons) { la::csr_constrain(op_->ndofs, op_->rowptr.p, op_->colidx.p, vals.p, op_->cmask.p, s); op_->stats.launches++; }
+    if (prec_type == "Jacobi") { la::csr_extract_diag_inv(op_->ndofs, op_->rowptr.p, op_->colidx.p, vals.p, dinv_.p, s); op_->stats.launches++; }
+    if (prec_type == "BlockJacobi")
+      for (int c = 0; c < ncomp; ++c) {
+        int bs = op_->model->comp_nspec[c];
+        if (bs == 0) continue;
+        int64_t nb = (g.comp_offset[c + 1] - g.comp_offset[c]) / bs;
+        la::csr_extract_block_diag(g.comp_offset[c], nb, bs, op_->rowptr.p, op_->colidx.p, vals.p, bdiag_.p + op_->bdiag_shift(c), s);
+        op_->stats.launches++;
+      }
+  } else if (prec_type != "Richardson") {
+    bdiag_.zero(s);
+    op_->block_diag(t, wM, wA, x, bdiag_.p);
+    for (int c = 0; c < ncomp; ++c) {
+      int bs = op_->model->comp_nspec[c];
+      if (bs == 0) continue;
+      int64_t nb = (g.comp_offset[c + 1] - g.comp_offset[c]) / bs;
+      if (op_->ncons) { la::bdiag_constrain(g.comp_offset[c], nb, bs, bdiag_.p + op_->bdiag_shift(c), op_->cmask.p, s); op_->stats.launches++; }
+      if (prec_type == "Jacobi") { la::block_diag_to_dinv(g.comp_offset[c], nb, bs, bdiag_.p + op_->bdiag_shift(c), dinv_.p, s); op_->stats.launches++; }
+    }
+  }
+  if (prec_type == "BlockJacobi")
+    for (int c = 0; c < ncomp; ++c) {
+      int bs = op_->model->comp_nspec[c];
+      if (bs == 0) continue;
+      int64_t nb = (g.comp_offset[c + 1] - g.comp_offset[c]) / bs;
+      // blocks of compartment c start at bdiag[comp_offset[c] * bs]
+      la::block_invert(nb, bs, bdiag_.p + op_->bdiag_shift(c) + g.comp_offset[c] * bs, s);
+      op_->stats.launches++;
+    }
+}
+
+void LinearSolver::apply_operator(const double* v, double* y) {
+  cudaStream_t s = op_->stream;
+  if (comm_) comm_->halo_update(const_cast<double*>(v), s);
+  if (!matrix_free) {
+    int avg = (int)(op_->nnz() / std::max<int64_t>(1, op_->ndofs));
+    DeviceOperator::ProfScope ps(op_.get(), "spmv");
+    la::spmv_csr(op_->ndofs, op_->rowptr.p, op_->rowptr32.p, op_->colidx.p, vals.p, v, y, avg, s);
+    op_->stats.launches++;
+  } else {
+    la::fill(op_->ndofs, 0.0, y, s);   // MatrixFreeAdapter::apply zeroes y first (make_step_operator.hh:70-75)
+    op_->stats.launches++;
+    op_->jacobian_apply(t_, wM_, wA_, x_, v, y);
+    if (op_->ncons) { la::copy_values(op_->ncons, op_->cdofs.p, v, y, s); op_->stats.launches++; }   // identity rows
+  }
+}
+
+void LinearSolver::precondition(const double* d, double* v) {
+  cudaStream_t s = op_->stream;
+  DeviceOperator::ProfScope ps(op_.get(), "precond");
+  const Grid& g = *op_->grid;
+  if (prec_type == "Richardson") {
+    la::copy(op_->ndofs, d, v, s);
+    if (relaxation != 1.0) { la::fill(op_->ndofs, 0.0, v, s); la::axpy(op_->ndofs, relaxation, d, v, s); }
+  } else if (prec_type == "Jacobi") {
+    // SeqJac, one sweep from v = 0: v = w D^-1 d
+    la::jacobi_apply(op_->ndofs, dinv_.p, relaxation, d, v, s);
+  } else {
+    // BlockJacobi::apply with iterations = 1 from v = 0 (block_jacobi.hh:102-127): v = w Dblk^-1 d
+    for (int c = 0; c < op_->model->ncomp(); ++c) {
+      int bs = op_->model->comp_nspec[c];
+      if (bs == 0) continue;
+      int64_t nb = (g.comp_offset[c + 1] - g.comp_offset[c]) / bs;
+      la::block_jacobi_apply(g.comp_offset[c], nb, bs, bdiag_.p + op_->bdiag_shift(c), relaxation, d, v, s);
+    }
+  }
+  op_->stats.launches++;
+}
+
+void LinearSolver::fetch(int n) {
+  cudaStream_t s = op_->stream;
+  if (comm_) comm_->allreduce_sum(scal_.p, n, s);
+  DCB_CUDA(cudaMemcpyAsync(hscal_.p, scal_.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  DCB_CUDA(cudaStreamSynchronize(s));
+}
+
+SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
+  cudaStream_t s = op_->stream;
+  const int64_t n = op_->ndofs;
+  const la::Ranges& own = op_->owned;
+  SolveResult res;
+  double* r = b;
+  auto& L = op_->stats.launches;
+  // x is the zero vector on entry (make_step_operator.hh:230, Newton's correction): A*0 = 0 is
+  // skipped, r = b.
+  { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::fill(n, 0.0, x, s); L++; }
+  if (type == "BiCGSTAB") {
+    double *rt = work_[0].p, *p = work_[1].p, *v = work_[2].p, *t = work_[3].p, *y = work_[4].p;
+    { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::copy(n, r, rt, s); L++; }
+    { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, r, r, scal_.p, ws_, s); L++; }
+    fetch(1);
+    double norm0 = std::sqrt(hscal_.p[0]), norm = norm0;
+    res.defect0 = norm0;
+    if (!(norm0 == norm0)) { res.converged = false; return res; }
+    if (norm0 < 1e-30) { res.converged = true; res.reduction = 0; return res; }
+    double rho = 1, alpha = 1, omega = 1, rho_new = hscal_.p[0];   // <rt,r> = <r,r> at the start
+    double it = 0.5;
+    for (; it < max_iterations; it += 0.5) {
+      // rho_new = <rt,r> was produced by the previous sweep (fused with the norm)
+      if (std::fabs(rho) <= 1e-80 || std::fabs(omega) <= 1e-80) break;   // breakdown (SolverAbort)
+      double beta = (rho_new / rho) * (alpha / omega);
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::bicg_update_p(n, p, r, v, beta, omega, it < 1, s); L++; }
+      precondition(p, y);
+      apply_operator(y, v);
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, rt, v, scal_.p, ws_, s); L++; }
+      fetch(1);
+      double h = hscal_.p[0];
+      if (std::fabs(h) < 1e-80) break;
+      alpha = rho_new / h;
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::axpy_pair_norm(n, own, alpha, y, x, v, r, nullptr, scal_.p, ws_, s); L++; }
+      fetch(1);
+      norm = std::sqrt(hscal_.p[0]);
+      res.half_iterations++;
+      if (!(norm == norm)) break;
+      if (norm < rel_tol * norm0 || norm < 1e-30) { res.converged = true; break; }
+      it += 0.5;
+      precondition(r, y);
+      apply_operator(y, t);
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot2(own, t, r, t, t, scal_.p, ws_, s); L++; }
+      fetch(2);
+      omega = hscal_.p[0] / hscal_.p[1];
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::axpy_pair_norm(n, own, omega, y, x, t, r, rt, scal_.p, ws_, s); L++; }
+      fetch(2);
+      rho = rho_new;
+      rho_new = hscal_.p[1];
+      norm = std::sqrt(hscal_.p[0]);
+      res.half_iterations++;
+      if (!(norm == norm)) break;
+      if (norm < rel_tol * norm0 || norm < 1e-30) { res.converged = true; break; }
+    }
+    res.iterations = (int)std::ceil(std::min<double>(it, max_iterations));
+    res.reduction = norm / norm0;
+  } else {   // CG
+    double *p = work_[0].p, *q = work_[1].p;
+    { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, r, r, scal_.p, ws_, s); L++; }
+    fetch(1);
+    double norm0 = std::sqrt(hscal_.p[0]), norm = norm0;
+    res.defect0 = norm0;
+    if (norm0 < 1e-30) { res.converged = true; res.reduction = 0; return res; }
+    precondition(r, p);
+    { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, p, r, scal_.p, ws_, s); L++; }
+    fetch(1);
+    double rholast = hscal_.p[0];
+    int i = 1;
+    for (; i <= max_iterations; ++i) {
+      apply_operator(p, q);
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, p, q, scal_.p, ws_, s); L++; }
+      fetch(1);
+      double lambda = rholast / hscal_.p[0];
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::axpy_pair_norm(n, own, lambda, p, x, q, r, nullptr, scal_.p, ws_, s); L++; }
+      fetch(1);
+      norm = std::sqrt(hscal_.p[0]);
+      res.half_iterations += 2;
+      if (norm < rel_tol * norm0 || norm < 1e-30) { res.converged = true; break; }
+      precondition(r, q);
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, q, r, scal_.p, ws_, s); L++; }
+      fetch(1);
+      double rho = hscal_.p[0], beta = rho / rholast;
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::xpby(n, p, q, beta, s); L++; }
+      rholast = rho;
+    }
+    res.iterations = std::min(i, max_iterations);
+    res.reduction = norm / norm0;
+  }
+  if (comm_) comm_->halo_update(x, s);
+  return res;
+}
+
+}  // namespace dcb

@@ -1,0 +1,64 @@
+// Krylov solve on the device: hand-written BiCGSTAB and CG in dune-istl's operation order with
+// Jacobi / block-Jacobi / Richardson preconditioning, on an assembled CSR Jacobian or matrix-free.
+//
+// Mirrors the reference's LinearSolver adapter (dune/copasi/model/make_step_operator.hh:55-157):
+// configuration sub-tree `linear_solver.*`, solver + preconditioner (re)built on every apply
+// (:120-127), relative tolerance handed in per call (:132-135), non-convergence reported as an
+// error condition (:141-145).  Registry names follow solver/istl/factory/iterative.hh:87-106 and
+// factory/preconditioner.hh:96-113; only the data-parallel subset is built (BiCGSTAB, CG;
+// Richardson, Jacobi, BlockJacobi), anything else fails loudly.
+#pragma once
+#include <memory>
+#include <string>
+
+#include "operator.hpp"
+
+namespace dcb {
+
+struct SolveResult {
+  int iterations = 0;        // ceil(it) as dune-istl reports it
+  int half_iterations = 0;   // BiCGSTAB tests convergence every half iteration
+  bool converged = false;
+  double reduction = 1.0;
+  double defect0 = 0.0;
+};
+
+// communicator hooks for multi-GPU runs (comm.cpp); null => single device
+struct Communicator;
+
+class LinearSolver {
+ public:
+  LinearSolver(std::shared_ptr<DeviceOperator> op, const PTree& cfg, Communicator* comm = nullptr);
+  ~LinearSolver();
+
+  // Linearisation J = wM dM/du + wA dA/du at (t, x).  Assembles the CSR values (matrix based)
+  // or only the (block) diagonal (matrix free) and sets up the preconditioner.
+  void linearize(double t, double wM, double wA, const double* x);
+  // solve J z = b to the relative defect reduction `rel_tol`; b is consumed (holds the final defect)
+  SolveResult apply(double* b, double* z, double rel_tol);
+  // y = J v with the current linearisation
+  void apply_operator(const double* v, double* y);
+
+  bool matrix_free = false;
+  std::string type, prec_type;
+  int max_iterations = 500;
+  double relaxation = 1.0;
+  int verbosity = 0;
+  DeviceBuffer<double> vals;     // CSR values of the current linearisation (matrix based)
+
+ private:
+  void precondition(const double* d, double* v);
+  double reduce1(double* dev2);             // host value of scal_[0] after a reduction
+  void fetch(int n);
+  std::shared_ptr<DeviceOperator> op_;
+  Communicator* comm_;
+  la::ReduceWorkspace ws_;
+  DeviceBuffer<double> scal_;               // device scalars of the reductions
+  PinnedBuffer<double> hscal_;
+  DeviceBuffer<double> dinv_, bdiag_, work_[6];
+  // linearisation point
+  double t_ = 0, wM_ = 0, wA_ = 0;
+  const double* x_ = nullptr;
+};
+
+}  // namespace dcb

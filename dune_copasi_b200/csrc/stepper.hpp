@@ -1,0 +1,54 @@
+// Time stepping glue on the device: RungeKutta o (Newton | linear defect correction) o LinearSolver
+// o instationary operator, as wired by dune/copasi/model/make_step_operator.hh:164-444, plus the
+// adaptive step-size control of dune/copasi/common/stepper.hh:337-368.  State and all work
+// vectors stay resident in HBM; the host drives the control flow (a handful of scalars per
+// Newton / Krylov iteration cross PCIe).
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "solver.hpp"
+
+namespace dcb {
+
+struct StepStats {
+  long long steps = 0, failed_steps = 0, stages = 0;
+  long long newton_iterations = 0, linear_solves = 0, linear_iterations = 0, linear_half_iterations = 0;
+  long long residual_evaluations = 0, linearizations = 0;
+};
+
+class StepOperator {
+ public:
+  StepOperator(std::shared_ptr<DeviceOperator> op, const PTree& time_step_cfg, Communicator* comm = nullptr);
+
+  // u (device, ndofs) is advanced from t by dt in place; returns false if the step failed
+  // (Newton / linear solver did not converge) in which case u is unchanged.
+  bool step(double* u, double t, double dt);
+  // adaptive evolution (SimpleAdaptiveStepper): returns the number of accepted steps
+  int evolve(double* u, double* t, double t_end, double* dt, int max_steps);
+
+  std::string rk_type;
+  bool is_linear = false;
+  double newton_rel = 1e-4, newton_abs = 0.0, lin_rel = 1e-4;
+  int newton_max_it = 40;
+  bool dx_fixed_tol = false;
+  double dx_min_rel_tol = 0.1;
+  double dt_min = 1e-12, dt_max = 0.0, inc_factor = 1.1, dec_factor = 0.5;
+  StepStats stats;
+  std::shared_ptr<DeviceOperator> op;
+  std::unique_ptr<LinearSolver> linear;
+
+ private:
+  bool solve_stage(double* x, double ts, double wM, double wA, const double* constant);
+  void stage_residual(const double* x, double ts, double wM, double wA, const double* constant, double* r);
+  double norm2(const double* r);
+  Communicator* comm_;
+  std::vector<std::vector<double>> a_, b_;
+  std::vector<double> d_;
+  std::vector<DeviceBuffer<double>> stage_;   // stage solutions u_1..u_s
+  DeviceBuffer<double> const_, r_, z_, scal_;
+  PinnedBuffer<double> hscal_;
+  la::ReduceWorkspace ws_;
+};
+
+}  // namespace dcb

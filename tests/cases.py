@@ -1,0 +1,355 @@
+"""Test problems shared by the CPU (host logic / oracle) and GPU (parity) suites.
+
+Each case restates one of the reference's configurations (BASELINE.json `configs`, SURVEY.md
+App. B) as ini text in the reference's own key vocabulary, with the solver pinned to the
+data-parallel subset -- no file under /root/reference is read at run time.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import core as ORC  # noqa: E402
+from oracle import ini as INI  # noqa: E402
+from oracle import mesh as OMESH  # noqa: E402
+
+SOLVER = """
+[model.time_step_operator.linear_solver]
+type = BiCGSTAB
+preconditioner.type = Jacobi
+convergence_condition.relative_tolerance = 1e-12
+[model.time_step_operator.nonlinear_solver]
+convergence_condition.relative_tolerance = 1e-20
+dx_inverse_fixed_tolerance = true
+"""
+
+# test/gauss.ini: single compartment, linear diffusion of a Gaussian, D = 0.005, t in [1, 1.2]
+GAUSS = """
+[compartments.domain]
+type = expression
+expression = 1
+[parser_context.diffusion]
+type = constant
+value = 0.005
+[parser_context.gauss]
+type = function
+expression = x, y, z, t: exp(-(x^2+y^2+z^2)/(4*t*diffusion)) / (4*3.14159265359*t*diffusion)
+[model]
+is_linear = true
+[model.scalar_field.u]
+compartment = domain
+[model.scalar_field.u.cross_diffusion.u]
+expression = diffusion
+[model.scalar_field.u.initial]
+expression = gauss(position_x, position_y, position_z, time)
+[model.scalar_field.u.storage]
+expression = 1
+[model.time_step_operator]
+time_begin = 1
+time_end = 1.2
+""" + SOLVER
+
+# test/exp.ini: pure reaction u' = -2u through the non-linear (Newton) path
+EXP = """
+[compartments.domain]
+type = expression
+expression = 1
+[parser_context.grow_rate]
+type = constant
+value = -2.
+[model.scalar_field.u]
+compartment = domain
+initial.expression = 1
+storage.expression = 1
+reaction.expression = grow_rate*u
+reaction.jacobian.u.expression = grow_rate
+[model.time_step_operator]
+time_step_max = 0.1
+time_end = 10
+""" + SOLVER
+
+# test/poisson.ini: -lap u = -2 dim with Dirichlet data |x|^2 (constraints)
+POISSON = """
+[parser_context]
+dim.type = constant
+dim.value = 2
+[compartments.domain]
+type = expression
+expression = 1
+[model]
+is_linear = true
+parser_type = ExprTk
+[model.time_step_operator]
+time_end = 0.1
+[model.scalar_field.u]
+compartment = domain
+cross_diffusion.u.expression = 1
+reaction.expression = -2*dim
+constrain.boundary.expression = in_boundary ? position_x^2+position_y^2+position_z^2 : no_value
+initial.expression = 0
+""" + SOLVER
+
+# doc/docusaurus/static/ini/next/grey_scott.ini: 2 species, cubic reaction; bumps in 2-D / 3-D
+GRAY_SCOTT = """
+[parser_context.bump]
+type = function
+expression = x, y, z: 0.5*exp(-100*(x^2 + y^2 + z^2))
+[parser_context.F]
+type = constant
+value = 0.0420
+[parser_context.k]
+type = constant
+value = 0.0610
+[parser_context.D]
+type = constant
+value = 1e-5
+[model]
+order = 1
+parser_type = ExprTk
+[model.time_step_operator]
+time_begin = 0
+time_end = 10000
+time_step_initial = 0.1
+time_step_max = 50
+[compartments]
+compartment.expression = 1
+[model.scalar_field.U]
+compartment = compartment
+initial.expression = 0.7
+storage.expression = 1
+reaction.expression = F*(1-U) - U*V^2
+reaction.jacobian.U.expression = -F - V^2
+reaction.jacobian.V.expression = -2*U*V
+cross_diffusion.U.expression = D*2
+[model.scalar_field.V]
+compartment = compartment
+initial.expression = bump(0.25-position_x, 0.25-position_y, 0.25-position_z) + bump(0.25-position_x, 0.75-position_y, 0.75-position_z) + bump(0.75-position_x, 0.25-position_y, 0.75-position_z) + bump(0.75-position_x, 0.75-position_y, 0.25-position_z)
+storage.expression = 1
+reaction.expression = -(F+k)*V + U*V^2
+reaction.jacobian.U.expression = V^2
+reaction.jacobian.V.expression = -(F+k) + 2*U*V
+cross_diffusion.V.expression = D
+""" + SOLVER
+
+# test/mitchell_schaefer.ini with rng == 0 as the reference's CTest does (test/CMakeLists.txt:78-79)
+MITCHELL_SCHAEFER = """
+[parser_context]
+tau_in.type = constant
+tau_in.value = 0.1
+tau_out.type = constant
+tau_out.value = 1
+tau_open.type = constant
+tau_open.value = 80
+tau_close.type = constant
+tau_close.value = 60
+D.type = constant
+D.value = 1e-4
+A_m.type = constant
+A_m.value = 20e-2
+u_0.type = constant
+u_0.value = 0.13
+gauss.type = function
+gauss.expression = x, y, z: exp(-(x^2+y^2+z^2)/(4*0.0001)) / (4*3.14159265359*0.0001)/400
+pulse.type = function
+pulse.expression = t, t0, dt: sqrt((t-t0)^2)< dt ? 1 : 0
+periodic.type = function
+periodic.expression = t : cos(t) > 0.95 ? 1 : 0
+rng.type = function
+rng.expression = x, y: 0
+[compartments]
+domain.type = expression
+domain.expression = 1
+[model]
+parser_type = ExprTk
+[model.scalar_field.u]
+compartment = domain
+storage.expression = 1
+reaction.expression = A_m*(z*u^2*(1-u)/tau_in - u/tau_out) + periodic( 2 * 3.14 * time/200)*gauss(position_x - 0.05, position_y - 0.05, position_z) + 0.85*pulse(time, 470, 20)*gauss(position_x - 0.675, position_y - 0.15, position_z)
+reaction.jacobian.u.expression = A_m*(u*z*(2-3*u)/tau_in-1/tau_out)
+reaction.jacobian.z.expression = A_m*(1-u)*u^2/tau_in
+cross_diffusion.u.expression = D - 0.15 * D * rng(position_x,position_y)
+initial.expression = 0.01
+[model.scalar_field.z]
+compartment = domain
+storage.expression = 1
+reaction.expression = (u <= u_0) ? ( (1 - z)/(tau_open*(1+0.25*rng(position_x,position_y))) ): (-z/tau_close)
+reaction.jacobian.z.expression = (u <= u_0) ? ( -1/(tau_open*(1+0.25*rng(position_x,position_y))) ) : (-1/tau_close)
+initial.expression = 1
+[model.time_step_operator]
+time_end = 5000
+time_step_max = 10
+""" + SOLVER
+
+# test/two_disks.ini: two compartments, interface flux phi (u_in - u_out), Dirichlet on the rim
+TWO_DISKS = """
+[compartments]
+outer.expression = (gmsh_id == 1)
+inner.expression = (gmsh_id == 2)
+[parser_context]
+phi.type = constant
+phi.value = 1
+[model.scalar_field.u_in]
+compartment = inner
+cross_diffusion.u_in.expression = 1
+outflow.outer.expression = phi*(u_in - u_out)
+outflow.outer.jacobian.u_in.expression = phi
+outflow.outer.jacobian.u_out.expression = -phi
+[model.scalar_field.u_out]
+compartment = outer
+cross_diffusion.u_out.expression = 1
+storage.expression = 0
+constrain.boundary.expression = position_x
+outflow.inner.expression = phi*(u_out - u_in)
+outflow.inner.jacobian.u_out.expression = phi
+outflow.inner.jacobian.u_in.expression = -phi
+[model]
+is_linear = true
+parser_type = ExprTk
+[model.time_step_operator]
+time_step_max = 1
+time_end = 1
+""" + SOLVER
+
+# BASELINE config 5 in miniature: cytosol / nucleus / extracellular space as nested regions of a
+# structured tet mesh, several species per compartment, constant cross-diffusion, non-linear
+# reactions, membrane fluxes between touching compartments and an outflow boundary condition.
+CELL = """
+[compartments]
+ecs.expression = (max(max(abs(position_x-0.5), abs(position_y-0.5)), abs(position_z-0.5)) > 0.375)
+cytosol.expression = (max(max(abs(position_x-0.5), abs(position_y-0.5)), abs(position_z-0.5)) < 0.375) and (max(max(abs(position_x-0.5), abs(position_y-0.5)), abs(position_z-0.5)) > 0.125)
+nucleus.expression = (max(max(abs(position_x-0.5), abs(position_y-0.5)), abs(position_z-0.5)) < 0.125)
+[parser_context]
+k1.type = constant
+k1.value = 0.7
+k2.type = constant
+k2.value = 0.3
+perm.type = constant
+perm.value = 0.5
+hill.type = function
+hill.expression = s, K: s^2/(K^2 + s^2)
+[model.scalar_field.e1]
+compartment = ecs
+storage.expression = 1
+cross_diffusion.e1.expression = 0.02
+reaction.expression = -k2*e1
+reaction.jacobian.e1.expression = -k2
+initial.expression = 1 + 0.5*position_x
+outflow.cytosol.expression = perm*(e1 - c1)
+outflow.cytosol.jacobian.e1.expression = perm
+outflow.cytosol.jacobian.c1.expression = -perm
+outflow.ecs.expression = 0.1*e1
+outflow.ecs.jacobian.e1.expression = 0.1
+[model.scalar_field.c1]
+compartment = cytosol
+storage.expression = 1
+cross_diffusion.c1.expression = 0.01
+cross_diffusion.c2.expression = 0.002
+reaction.expression = -k1*c1*c2 + k2*c3
+reaction.jacobian.c1.expression = -k1*c2
+reaction.jacobian.c2.expression = -k1*c1
+reaction.jacobian.c3.expression = k2
+initial.expression = 0.2 + 0.1*position_y
+outflow.ecs.expression = perm*(c1 - e1)
+outflow.ecs.jacobian.c1.expression = perm
+outflow.ecs.jacobian.e1.expression = -perm
+outflow.nucleus.expression = perm*hill(c1, 0.5) - 0.2*n1
+outflow.nucleus.jacobian.c1.expression = perm*2*c1*0.25/((0.25 + c1^2)^2)
+outflow.nucleus.jacobian.n1.expression = -0.2
+[model.scalar_field.c2]
+compartment = cytosol
+storage.expression = 1 + 0.5*position_z
+cross_diffusion.c2.expression = 0.015
+reaction.expression = -k1*c1*c2 + k2*c3
+reaction.jacobian.c1.expression = -k1*c2
+reaction.jacobian.c2.expression = -k1*c1
+reaction.jacobian.c3.expression = k2
+initial.expression = 0.5
+[model.scalar_field.c3]
+compartment = cytosol
+storage.expression = 1
+cross_diffusion.c3.expression = 0.005*(1 + position_x)
+reaction.expression = k1*c1*c2 - k2*c3
+reaction.jacobian.c1.expression = k1*c2
+reaction.jacobian.c2.expression = k1*c1
+reaction.jacobian.c3.expression = -k2
+initial.expression = 0.1
+[model.scalar_field.n1]
+compartment = nucleus
+storage.expression = 1
+cross_diffusion.n1.expression = 0.01
+reaction.expression = -0.05*n1*n2
+reaction.jacobian.n1.expression = -0.05*n2
+reaction.jacobian.n2.expression = -0.05*n1
+initial.expression = 0.3
+outflow.cytosol.expression = 0.2*n1 - perm*hill(c1, 0.5)
+outflow.cytosol.jacobian.n1.expression = 0.2
+outflow.cytosol.jacobian.c1.expression = -perm*2*c1*0.25/((0.25 + c1^2)^2)
+[model.scalar_field.n2]
+compartment = nucleus
+storage.expression = 1
+cross_diffusion.n2.expression = 0.01
+reaction.expression = 0.05*n1*n2 - 0.01*n2
+reaction.jacobian.n1.expression = 0.05*n2
+reaction.jacobian.n2.expression = 0.05*n1 - 0.01
+initial.expression = 0.05
+[model.time_step_operator]
+time_end = 1
+""" + SOLVER
+
+
+class Case:
+    def __init__(self, name, ini, dim, mesh_fn, t0=0.0, dt=0.1, structured=None):
+        self.name, self.ini, self.dim, self.mesh_fn, self.t0, self.dt = name, ini, dim, mesh_fn, t0, dt
+        self.structured = structured   # (cells, origin, extent) when the mesh is a structured grid
+
+    def oracle(self, **overrides):
+        cfg = INI.parse_ini(self.ini)
+        for k, v in overrides.items():
+            INI.set_key(cfg, k, str(v))
+        mesh = self.mesh_fn()
+        return ORC.Model(cfg, mesh)
+
+    def ini_with(self, **overrides):
+        cfg = INI.parse_ini(self.ini)
+        for k, v in overrides.items():
+            INI.set_key(cfg, k, str(v))
+        return INI.to_text(cfg)
+
+
+def _s(dim, n, origin=None, extent=None):
+    cells = [n] * dim
+    return lambda: OMESH.structured(dim, cells, origin, extent)
+
+
+CASES = {
+    "gauss2d": Case("gauss2d", GAUSS, 2, _s(2, 32, [-1, -1], [2, 2]), t0=1.0, structured=([32, 32], [-1, -1], [2, 2])),
+    "gauss3d": Case("gauss3d", GAUSS, 3, _s(3, 8, [-1, -1, -1], [2, 2, 2]), t0=1.0, structured=([8, 8, 8], [-1, -1, -1], [2, 2, 2])),
+    "exp": Case("exp", EXP, 2, _s(2, 2), structured=([2, 2], [0, 0], [1, 1])),
+    "poisson": Case("poisson", POISSON, 2, _s(2, 16), structured=([16, 16], [0, 0], [1, 1])),
+    "grayscott2d": Case("grayscott2d", GRAY_SCOTT, 2, _s(2, 32), dt=1.0, structured=([32, 32], [0, 0], [1, 1])),
+    "grayscott3d": Case("grayscott3d", GRAY_SCOTT, 3, _s(3, 10), dt=1.0, structured=([10, 10, 10], [0, 0, 0], [1, 1, 1])),
+    "mitchell_schaefer": Case("mitchell_schaefer", MITCHELL_SCHAEFER, 2, _s(2, 16), dt=0.01, structured=([16, 16], [0, 0], [1, 1])),
+    "two_disks": Case("two_disks", TWO_DISKS, 2, lambda: OMESH.two_disks(6, 6, 32), dt=1.0),
+    "cell3d": Case("cell3d", CELL, 3, _s(3, 8), dt=0.05, structured=([8, 8, 8], [0, 0, 0], [1, 1, 1])),
+}
+
+
+def product_objects(case: Case, **overrides):
+    """-> (Config, Model, Grid bound) through the C ABI, fed with the oracle-side mesh arrays."""
+    import dune_copasi_b200 as D
+    mesh = case.mesh_fn()
+    cfg = D.Config(case.ini_with(**overrides))
+    model = D.Model(cfg, case.dim, mesh.cell_keys)
+    grid = D.Grid.from_arrays(case.dim, mesh.coords, mesh.elems, mesh.cell_keys, mesh.cell_data)
+    grid.bind(model)
+    return cfg, model, grid
+
+
+def rand_state(n, seed=0, lo=0.1, hi=1.0):
+    return np.random.default_rng(seed).uniform(lo, hi, n)
