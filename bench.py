@@ -48,6 +48,9 @@ def ini_for(args):
         "model.time_step_operator.nonlinear_solver.dx_inverse_fixed_tolerance": "true",
         "model.assembly.b200.scheme": args.scheme,
     }
+    for kv in filter(None, getattr(args, "b200", "").split(",")):
+        k, v = kv.split("=")
+        over["model.assembly.b200." + k] = v
     return K.CASES["grayscott3d"].ini_with(**over)
 
 
@@ -163,6 +166,7 @@ def main():
     ap.add_argument("--prec", default="Jacobi")
     ap.add_argument("--scheme", default="patch")
     ap.add_argument("--matrix-free", type=int, default=1)
+    ap.add_argument("--b200", default="", help="model.assembly.b200.* overrides, e.g. patch_elements=768,patch_min_blocks=4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

@@ -35,11 +35,11 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
       o << "extern \"C\" __global__ void __launch_bounds__(128) dc_k_jacobian_volume_" << c
         << "(DcVolArgs a) { dc_jacobian_volume<" << c << ", 0>(a); }\n";
     if (all || group == JitGroup::Patch) {
-      o << "extern \"C\" __global__ void __launch_bounds__(DC_PATCH_THREADS) dc_k_patch_residual_" << c
+      o << "extern \"C\" __global__ void __launch_bounds__(DC_PATCH_THREADS, DC_PATCH_MINB) dc_k_patch_residual_" << c
         << "(DcPatchArgs a) { dc_patch_kernel<" << c << ", 0>(a); }\n";
-      o << "extern \"C\" __global__ void __launch_bounds__(DC_PATCH_THREADS) dc_k_patch_apply_" << c
+      o << "extern \"C\" __global__ void __launch_bounds__(DC_PATCH_THREADS, DC_PATCH_MINB) dc_k_patch_apply_" << c
         << "(DcPatchArgs a) { dc_patch_kernel<" << c << ", 1>(a); }\n";
-      o << "extern \"C\" __global__ void __launch_bounds__(DC_PATCH_THREADS) dc_k_patch_bdiag_" << c
+      o << "extern \"C\" __global__ void __launch_bounds__(DC_PATCH_THREADS, DC_PATCH_MINB) dc_k_patch_bdiag_" << c
         << "(DcPatchArgs a) { dc_patch_kernel<" << c << ", 2>(a); }\n";
     }
   }
@@ -59,11 +59,10 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
 
 std::string jit_defines(const Model& model) {
   const PTree& acfg = model.cfg.sub("model.assembly.b200");
-  int pn = acfg.get("patch_vertices", 768), cbuf = acfg.get("patch_buffer", 4096), th = acfg.get("patch_threads", 256);
-  if (pn < 16 || pn > 16384) fail("model.assembly.b200.patch_vertices out of range");
+  int th = acfg.get("patch_threads", 256), minb = acfg.get("patch_min_blocks", 3);
   if (th < 32 || th > 1024 || th % 32) fail("model.assembly.b200.patch_threads must be a multiple of 32 in [32,1024]");
-  return "#define DC_PATCH_PN " + std::to_string(pn) + "\n#define DC_PATCH_CBUF " + std::to_string(cbuf) +
-         "\n#define DC_PATCH_THREADS " + std::to_string(th) + "\n";
+  if (minb < 1 || minb > 8) fail("model.assembly.b200.patch_min_blocks out of range");
+  return "#define DC_PATCH_THREADS " + std::to_string(th) + "\n#define DC_PATCH_MINB " + std::to_string(minb) + "\n";
 }
 
 std::vector<char> jit_compile(const std::string& source, std::string* log, bool ptx) {

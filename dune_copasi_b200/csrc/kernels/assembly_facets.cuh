@@ -1,0 +1,248 @@
+// ---- facets: transmission conditions / outflow boundary ------------------------------------------
+// One thread per (facet, side) entry of the list built for the directional pair P (CS -> CT).
+template <int P>
+struct DcFacet {
+  typedef DcOutflow<P> O;
+  static constexpr int NSS = O::NSS, NST = O::NST;
+  double Xs[DC_ND][DC_DIM], Gs[DC_ND][DC_DIM], Gt[DC_ND][DC_DIM];
+  int fs[DC_DIM], ft[DC_DIM];       // local indices of the facet vertices on both sides
+  int dofs[DC_DIM], doft[DC_DIM];   // dof of species 0 at the facet vertices
+  double xs[NSS][DC_DIM], xt[NST][DC_DIM];  // coefficients at the facet vertices
+  double gs[NSS][DC_DIM], gt[NST][DC_DIM];  // gradients (element-wise constants)
+  double area, ie;
+  DcCtx c;
+
+  __device__ __forceinline__ bool load(const DcFacetArgs& a, long long* fout) {
+    const long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (f >= a.n) return false;
+    *fout = f;
+    const long long es = a.f_self[f], et = a.f_other[f];
+    const int ms = a.f_lself[f];
+    int vs[DC_ND];
+    double xall[NSS][DC_ND];
+#pragma unroll
+    for (int k = 0; k < DC_ND; ++k) {
+      vs[k] = a.elems[es * DC_ND + k];
+#pragma unroll
+      for (int cc = 0; cc < DC_DIM; ++cc) Xs[k][cc] = a.coords[(long long)vs[k] * DC_DIM + cc];
+      const int d = a.vdof_s ? a.vdof_s[vs[k]] : a.dof_offset_s + vs[k] * NSS;
+#pragma unroll
+      for (int s = 0; s < NSS; ++s) xall[s][k] = a.x[d + s];
+    }
+    dc_geometry(Xs, Gs);
+#pragma unroll
+    for (int s = 0; s < NSS; ++s)
+#pragma unroll
+      for (int k = 0; k < DC_DIM; ++k) {
+        double acc = 0.0;
+#pragma unroll
+        for (int b = 0; b < DC_ND; ++b) acc += xall[s][b] * Gs[b][k];
+        gs[s][k] = acc;
+      }
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < DC_ND; ++k)
+      if (k != ms) {
+        if (n < DC_DIM) {
+          fs[n] = k;
+          dofs[n] = a.vdof_s ? a.vdof_s[vs[k]] : a.dof_offset_s + vs[k] * NSS;
+#pragma unroll
+          for (int s = 0; s < NSS; ++s) xs[s][n] = xall[s][k];
+        }
+        ++n;
+      }
+    // other side
+#pragma unroll
+    for (int s = 0; s < NST; ++s)
+#pragma unroll
+      for (int k = 0; k < DC_DIM; ++k) { xt[s][k] = 0.0; gt[s][k] = 0.0; }
+    if (!O::BOUNDARY && et >= 0) {
+      double Xt[DC_ND][DC_DIM], xtall[NST][DC_ND];
+      int vt[DC_ND];
+#pragma unroll
+      for (int k = 0; k < DC_ND; ++k) {
+        vt[k] = a.elems[et * DC_ND + k];
+#pragma unroll
+        for (int cc = 0; cc < DC_DIM; ++cc) Xt[k][cc] = a.coords[(long long)vt[k] * DC_DIM + cc];
+        const int d = a.vdof_t ? a.vdof_t[vt[k]] : a.dof_offset_t + vt[k] * O::NST_REAL;
+#pragma unroll
+        for (int s = 0; s < O::NST_REAL; ++s) xtall[s][k] = a.x[d + s];
+      }
+      dc_geometry(Xt, Gt);
+#pragma unroll
+      for (int s = 0; s < O::NST_REAL; ++s)
+#pragma unroll
+        for (int k = 0; k < DC_DIM; ++k) {
+          double acc = 0.0;
+#pragma unroll
+          for (int b = 0; b < DC_ND; ++b) acc += xtall[s][b] * Gt[b][k];
+          gt[s][k] = acc;
+        }
+      // match the facet vertices by global id
+#pragma unroll
+      for (int m = 0; m < DC_DIM; ++m) {
+        const int gv = vs[fs[m]];
+        ft[m] = 0;
+#pragma unroll
+        for (int k = 0; k < DC_ND; ++k)
+          if (vt[k] == gv) ft[m] = k;
+        doft[m] = a.vdof_t ? a.vdof_t[gv] : a.dof_offset_t + gv * O::NST_REAL;
+#pragma unroll
+        for (int s = 0; s < O::NST_REAL; ++s) xt[s][m] = xtall[s][ft[m]];
+      }
+    }
+    // facet measure and unit outer normal of the own side: -grad(phi_m)/|grad(phi_m)|
+    double nn = 0.0;
+#pragma unroll
+    for (int k = 0; k < DC_DIM; ++k) nn += Gs[ms][k] * Gs[ms][k];
+    nn = sqrt(nn);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c.nrm[k] = k < DC_DIM ? -Gs[ms][k < DC_DIM ? k : 0] / nn : 0.0;
+#if DC_DIM == 2
+    {
+      const double dx = Xs[fs[1]][0] - Xs[fs[0]][0], dy = Xs[fs[1]][1] - Xs[fs[0]][1];
+      area = sqrt(dx * dx + dy * dy);
+      ie = area;
+    }
+#else
+    {
+      double u[3], v[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { u[k] = Xs[fs[1]][k] - Xs[fs[0]][k]; v[k] = Xs[fs[2]][k] - Xs[fs[0]][k]; }
+      const double cx = u[1] * v[2] - u[2] * v[1], cy = u[2] * v[0] - u[0] * v[2], cz = u[0] * v[1] - u[1] * v[0];
+      area = 0.5 * sqrt(cx * cx + cy * cy + cz * cz);
+      ie = 2.0 * area;
+    }
+#endif
+    c.time = a.time;
+    c.entity_volume = area;
+    c.in_volume = 0.0;
+    c.in_boundary = O::BOUNDARY ? 1.0 : 0.0;
+    c.in_skeleton = O::BOUNDARY ? 0.0 : 1.0;
+    c.pos[2] = 0.0;
+#pragma unroll
+    for (int k = 0; k < DC_NKEYS; ++k) c.cell[k] = a.cell[(long long)k * a.ne_total + es];
+    return true;
+  }
+
+  // facet quadrature (order 2) in facet barycentric coordinates
+  __device__ __forceinline__ static double lam(int q, int m) {
+#if DC_DIM == 2
+    const double g = 0.28867513459481288225;
+    return (m == 0) == (q == 0) ? 0.5 + g : 0.5 - g;
+#else
+    return (q == 0 && m == 1) || (q == 1 && m == 2) || (q == 2 && m == 0) ? (4.0 / 6.0) : (1.0 / 6.0);
+#endif
+  }
+  __device__ __forceinline__ static double qw() { return DC_DIM == 2 ? 0.5 : 1.0 / 6.0; }
+
+  __device__ __forceinline__ double point(int q, double* us, double* ut) {
+#pragma unroll
+    for (int k = 0; k < DC_DIM; ++k) {
+      double p = 0.0;
+#pragma unroll
+      for (int m = 0; m < DC_DIM; ++m) p += lam(q, m) * Xs[fs[m]][k];
+      c.pos[k] = p;
+    }
+#pragma unroll
+    for (int s = 0; s < NSS; ++s) {
+      double v = 0.0;
+#pragma unroll
+      for (int m = 0; m < DC_DIM; ++m) v += xs[s][m] * lam(q, m);
+      us[s] = v;
+    }
+#pragma unroll
+    for (int s = 0; s < NST; ++s) {
+      double v = 0.0;
+#pragma unroll
+      for (int m = 0; m < DC_DIM; ++m) v += xt[s][m] * lam(q, m);
+      ut[s] = v;
+    }
+    const double factor = qw() * ie;
+    c.integration_factor = factor;
+    return factor;
+  }
+};
+
+template <int P>
+__device__ __forceinline__ void dc_skeleton_residual(const DcFacetArgs& a) {
+  typedef DcOutflow<P> O;
+  DcFacet<P> F;
+  long long f;
+  if (!F.load(a, &f)) return;
+  double loc[O::NSS][DC_DIM];
+#pragma unroll
+  for (int s = 0; s < O::NSS; ++s)
+#pragma unroll
+    for (int m = 0; m < DC_DIM; ++m) loc[s][m] = 0.0;
+#pragma unroll
+  for (int q = 0; q < DC_DIM; ++q) {
+    double us[O::NSS], ut[O::NST], T[O::NSS];
+    const double factor = F.point(q, us, ut);
+    O::flux(F.c, us, F.gs, ut, F.gt, T);
+#pragma unroll
+    for (int s = 0; s < O::NSS; ++s)
+#pragma unroll
+      for (int m = 0; m < DC_DIM; ++m) loc[s][m] += a.wA * T[s] * F.lam(q, m) * factor;
+  }
+#pragma unroll
+  for (int s = 0; s < O::NSS; ++s)
+#pragma unroll
+    for (int m = 0; m < DC_DIM; ++m) dc_atomic_add(&a.r[F.dofs[m] + s], loc[s][m]);
+}
+
+// MODE 0: CSR values; 1: y += J z; 2: block diagonal
+template <int P, int MODE>
+__device__ __forceinline__ void dc_skeleton_jacobian(const DcFacetArgs& a) {
+  typedef DcOutflow<P> O;
+  DcFacet<P> F;
+  long long f;
+  if (!F.load(a, &f)) return;
+#pragma unroll 1
+  for (int q = 0; q < DC_DIM; ++q) {
+    double us[O::NSS], ut[O::NST], js[O::NSS][O::NSS], jt[O::NSS][O::NST];
+    const double factor = F.point(q, us, ut);
+    O::jacobian(F.c, us, F.gs, ut, F.gt, js, jt);
+#pragma unroll 1
+    for (int i = 0; i < O::NSS; ++i)
+#pragma unroll 1
+      for (int ma = 0; ma < DC_DIM; ++ma) {
+        const int row = F.dofs[ma] + i;
+        double acc = 0.0;
+#pragma unroll 1
+        for (int mb = 0; mb < DC_DIM; ++mb) {
+          const double w = a.wA * F.lam(q, ma) * F.lam(q, mb) * factor;
+#pragma unroll 1
+          for (int j = 0; j < O::NSS; ++j) {
+            if (!O::pair_s(i, j)) continue;
+            const int col = F.dofs[mb] + j;
+            const double v = js[i][j] * w;
+            if (MODE == 0) {
+              const long long p = dc_csr_find(a.rowptr, a.colidx, row, col);
+              if (p >= 0) dc_atomic_add(&a.vals[p], v);
+            } else if (MODE == 1) {
+              acc += v * ((a.cmask && a.cmask[col]) ? 0.0 : a.z[col]);
+            } else if (ma == mb) {
+              dc_atomic_add(&a.bdiag[(long long)F.dofs[ma] * O::NSS + i * O::NSS + j], v);
+            }
+          }
+          if (!O::BOUNDARY && MODE != 2) {
+#pragma unroll 1
+            for (int j = 0; j < O::NST_REAL; ++j) {
+              if (!O::pair_t(i, j)) continue;
+              const int col = F.doft[mb] + j;
+              const double v = jt[i][j] * w;
+              if (MODE == 0) {
+                const long long p = dc_csr_find(a.rowptr, a.colidx, row, col);
+                if (p >= 0) dc_atomic_add(&a.vals[p], v);
+              } else {
+                acc += v * ((a.cmask && a.cmask[col]) ? 0.0 : a.z[col]);
+              }
+            }
+          }
+        }
+        if (MODE == 1) dc_atomic_add(&a.r[row], acc);
+      }
+  }
+}
+

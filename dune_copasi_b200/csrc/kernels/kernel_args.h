@@ -36,6 +36,7 @@ struct DcPatchArgs {
   long long ne_total;
   int npatch;
   int dof_offset;
+  int max_nodes, max_elems;    // patch budgets (shared-memory layout)
   double time, wM, wA;
   const double* x;
   const double* z;

@@ -41,10 +41,12 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
   const PTree& acfg = model->cfg.sub("model.assembly.b200");
   scheme = acfg.get("scheme", std::string("patch"));
   if (scheme != "patch" && scheme != "atomic") fail("model.assembly.b200.scheme must be 'patch' or 'atomic'");
-  patch_pn_ = acfg.get("patch_vertices", 768);
-  patch_cbuf_ = acfg.get("patch_buffer", 4096);
+  patch_pn_ = acfg.get("patch_vertices", 256);
+  patch_pe_ = acfg.get("patch_elements", 512);
   patch_threads_ = acfg.get("patch_threads", 256);
+  patch_smem_kb_ = acfg.get("patch_smem_kb", 64);
   if (patch_pn_ < 16 || patch_pn_ > 16384) fail("model.assembly.b200.patch_vertices out of range");
+  if (patch_pe_ < 16 || patch_pe_ > 16383) fail("model.assembly.b200.patch_elements out of range");
   DCB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
 
   // ---- kernels for this model
@@ -171,7 +173,6 @@ int64_t DeviceOperator::bdiag_shift(int c) const {
 void DeviceOperator::build_patches() {
   const int nd = grid->nd(), dim = grid->dim, ncomp = model->ncomp();
   const int64_t ne = grid->ne;
-  const int pe_max = 16384;   // (local element << 2 | local vertex) must fit 16 bits
   // bounding box for the Morton keys
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
   for (int64_t v = 0; v < grid->nv; ++v)
@@ -194,6 +195,19 @@ void DeviceOperator::build_patches() {
     PatchSet& P = patches_[c];
     P.comp = c;
     if (model->comp_nspec[c] == 0 || comp_nelem_[c] == 0) continue;
+    // budgets: the element-result buffer of the apply kernel (nd*ns doubles per element) plus the
+    // staged vertex data must fit the shared-memory budget that keeps several CTAs per SM
+    {
+      const int ns = model->comp_nspec[c];
+      int pe = patch_pe_, pn = patch_pn_;
+      auto bytes = [&](int pe_, int pn_) {
+        return 8.0 * (pn_ * (dim + 2 * ns) + (double)nd * ns * pe_) + 2.0 * (pe_ * nd + pn_ + 1);
+      };
+      while (pe > 32 && bytes(pe, pn) > patch_smem_kb_ * 1024.0) { pe = pe * 3 / 4; pn = std::max(32, pn * 3 / 4); }
+      P.max_elems = pe;
+      P.max_nodes = pn;
+    }
+    const int pe_max = P.max_elems, pn_max = P.max_nodes;
     // 1. Morton order of the element centroids
     std::vector<std::pair<uint64_t, int32_t>> order;
     order.reserve(comp_nelem_[c]);
@@ -225,7 +239,7 @@ void DeviceOperator::build_patches() {
         int fresh = 0;
         for (int a = 0; a < nd; ++a) fresh += mark[grid->elems[e * nd + a]] != pid;
         // duplicates inside one element do not occur (simplex vertices are distinct)
-        if (cur_nodes + fresh > patch_pn_ || (t - elem_ptr.back()) >= pe_max) {
+        if (cur_nodes + fresh > pn_max || (t - elem_ptr.back()) >= pe_max) {
           elem_ptr.push_back((int)t);
           ++pid;
           cur_nodes = 0;
@@ -301,6 +315,13 @@ void DeviceOperator::build_patches() {
   DCB_CUDA(cudaStreamSynchronize(stream));
 }
 
+size_t DeviceOperator::patch_smem(const PatchSet& P, int ns, int mode) const {
+  const int nv = mode == 2 ? ns * ns : ns, nd = grid->nd();
+  size_t doubles = (size_t)P.max_nodes * (grid->dim + ns + (mode == 1 ? ns : 0)) + (size_t)nd * nv * P.max_elems;
+  size_t shorts = (size_t)P.max_elems * nd + P.max_nodes + 1;
+  return doubles * 8 + ((shorts * 2 + 15) / 16) * 16;
+}
+
 // ---------------------------------------------------------------------------------- launches
 void DeviceOperator::launch_volume(const char* kind, int mode, double t, double wM, double wA,
                                    const double* x, const double* z, double* r, double* vals,
@@ -310,7 +331,9 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
   for (int c = 0; c < ncomp; ++c) {
     const int ns = model->comp_nspec[c];
     if (ns == 0 || comp_nelem_[c] == 0) continue;
-    if (use_patch) {
+    // the block-diagonal buffer grows with ns^2: fall back to the element kernel when it cannot be staged
+    const bool patch_here = use_patch && patch_smem(patches_[c], ns, mode) <= 200 * 1024;
+    if (patch_here) {
       const PatchSet& P = patches_[c];
       DcPatchArgs a{};
       a.coords = coords_.p;
@@ -323,13 +346,15 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       a.npatch = P.npatch; a.dof_offset = (int)grid->comp_offset[c];
       a.time = t; a.wM = wM; a.wA = wA;
       a.x = x; a.z = z; a.r = r; a.bdiag = bdiag ? bdiag + bdiag_shift(c) : nullptr; a.cmask = cmask.p;
-      const int nv = mode == 2 ? ns * ns : ns;
-      size_t smem = sizeof(double) * ((size_t)patch_pn_ * (grid->dim + ns + (mode == 1 ? ns : 0) + nv) + patch_cbuf_);
+      a.max_nodes = P.max_nodes; a.max_elems = P.max_elems;
+      const size_t smem = patch_smem(P, ns, mode);
       static const char* names[3] = {"dc_k_patch_residual_", "dc_k_patch_apply_", "dc_k_patch_bdiag_"};
       cudaKernel_t k = kernel(JitGroup::Patch, std::string(names[mode]) + std::to_string(c));
       DCB_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int per_sm = std::max(1, (int)(200 * 1024 / std::max<size_t>(smem, 1)));
-      unsigned gridsz = (unsigned)std::min<int64_t>(P.npatch, (int64_t)148 * std::min(per_sm, 8));
+      // persistent grid: a multiple of the 148 SMs x resident CTAs (shared memory / thread limits)
+      int per_sm = std::max(1, (int)(220 * 1024 / (smem + 1024)));
+      per_sm = std::min(per_sm, std::max(1, 2048 / patch_threads_));
+      unsigned gridsz = (unsigned)std::min<int64_t>(P.npatch, (int64_t)148 * per_sm);
       static const char* pk[3] = {"patch_residual", "patch_apply", "patch_bdiag"};
       ProfScope ps(this, pk[mode]);
       jit_launch(k, gridsz, patch_threads_, smem, stream, a);

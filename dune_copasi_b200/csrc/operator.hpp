@@ -23,6 +23,7 @@ struct PatchSet {
   int npatch = 0;
   int64_t elem_begin = 0;   // offset of this compartment in patch element order
   int64_t nelem = 0;
+  int max_nodes = 0, max_elems = 0;   // budgets the patches of this compartment were cut with
   DeviceBuffer<int> node_ptr, nodes, elem_ptr, adj_ptr;
   DeviceBuffer<unsigned short> lconn, adj;
   // statistics (host)
@@ -112,8 +113,8 @@ class DeviceOperator {
   std::vector<FacetList> facets_;
   int64_t nnz_ = 0;
   int64_t ne_patch_total_ = 0;
-  size_t patch_smem_[3] = {0, 0, 0};
-  int patch_pn_ = 768, patch_cbuf_ = 4096, patch_threads_ = 256;
+  size_t patch_smem(const PatchSet& P, int ns, int mode) const;
+  int patch_pn_ = 256, patch_pe_ = 512, patch_threads_ = 256, patch_smem_kb_ = 64;
 };
 
 }  // namespace dcb

@@ -159,7 +159,7 @@ def test_bicgstab_iteration_counts_match_oracle():
     import dune_copasi_b200 as D
     case, om, cfg, model, grid, op = make("grayscott2d")
     x = K.rand_state(om.ndofs, 10)
-    t, wM, wA = 0.0, 1.0, 1.0
+    t, wM, wA = 0.0, 1.0, 0.1
     lcfg = D.Config("type = BiCGSTAB\npreconditioner.type = Jacobi\n")
     solver = D.Solver(op, lcfg)
     solver.linearize(t, wM, wA, x)
