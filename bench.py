@@ -220,7 +220,9 @@ def main():
         """-> device ms for nsteps (max over ranks)"""
         u_host = None
         if e2e:
-            u_host, _ = st.get_state()
+            # host buffers of the step's input/result live in pinned memory
+            u_host = torch.empty(op.ndofs, dtype=torch.float64).pin_memory().numpy()
+            st.get_state(u_host)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -231,7 +233,7 @@ def main():
             if not ok:
                 raise SystemExit("time step failed")
             if e2e:
-                u_host, _ = st.get_state()           # D2H of the step's result
+                st.get_state(u_host)                 # D2H of the step's result
         e1.record(stream)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
@@ -258,7 +260,21 @@ def main():
         e2e = {"value": ndofs_global * args.steps / (ms_e2e * 1e-3), "unit": "DOF-updates/s",
                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / args.steps}
 
+    def shutdown():
+        # every rank tears down in the same order: library objects (their NCCL communicator)
+        # first, then torch's process group
+        nonlocal st, comm, op
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        st = None
+        comm = None
+        op = None
+        if dist is not None:
+            dist.destroy_process_group()
+
     if rank != 0:
+        shutdown()
         return
     d = {k: s1[k] - s0[k] for k in s1}
     value = ndofs_global * args.steps / (ms * 1e-3)
@@ -283,17 +299,17 @@ def main():
                 "share_of_step": prof[top]["ms"] / ms,
                 "breakdown_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}}
     cb = None
-    if not args.no_cpu_baseline:
-        cb, _, _ = cpu_baseline(args, 1, 1, args.cpu_cells)
     line = {"metric": METRIC, "value": value, "unit": "DOF-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, args.cells),
             "time_steps_per_s": args.steps / (ms * 1e-3), "dofs": int(ndofs_global), "e2e": e2e,
             "gpu_launches": int(d["kernel_launches"]), "clocks": clocks, "roofline": roof, "cpu_baseline": cb,
             "solver_stats": d, "setup_s": t_setup}
-    print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    shutdown()
+    if not args.no_cpu_baseline:
+        # the CPU arm runs after the GPUs are released (rank 0 only)
+        line["cpu_baseline"], _, _ = cpu_baseline(args, 1, 1, args.cpu_cells)
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -109,6 +109,10 @@ SYMBOLS = {
     "dcb_grid_num_owned_vertices": (C.c_int64, [_P]),
     "dcb_grid_get_global_vertex_ids": (C.c_int, [_P, _I64]),
     "dcb_grid_get_vertex_owner": (C.c_int, [_P, _I32]),
+    "dcb_grid_get_global_element_ids": (C.c_int, [_P, _I64]),
+    "dcb_grid_halo_num_peers": (C.c_int, [_P, C.c_int]),
+    "dcb_grid_halo_peer": (C.c_int, [_P, C.c_int, C.c_int, _I32, _I64, _I64]),
+    "dcb_grid_halo_lists": (C.c_int, [_P, C.c_int, C.c_int, _I32, _I32]),
     "dcb_comm_create": (_P, [C.c_char_p, C.c_int, C.c_int, _P]),
     "dcb_comm_destroy": (None, [_P]),
     "dcb_operator_owned_ranges": (C.c_int, [_P, _I64, _I64, C.c_int]),
@@ -260,6 +264,22 @@ class Grid:
 
     def partition(self, rank, size):
         return Grid(lib().dcb_grid_partition(self.h, rank, size))
+
+    def global_element_ids(self):
+        out = np.empty(self.ne, dtype=np.int64)
+        lib().dcb_grid_get_global_element_ids(self.h, out.ctypes.data_as(_I64))
+        return out
+
+    def halo_plan(self, rank):
+        """-> [(peer, send dof indices, recv dof indices)]"""
+        out = []
+        for k in range(lib().dcb_grid_halo_num_peers(self.h, rank)):
+            peer, ns, nr = C.c_int32(), C.c_int64(), C.c_int64()
+            lib().dcb_grid_halo_peer(self.h, rank, k, C.byref(peer), C.byref(ns), C.byref(nr))
+            s, r = np.empty(ns.value, np.int32), np.empty(nr.value, np.int32)
+            lib().dcb_grid_halo_lists(self.h, rank, k, s.ctypes.data_as(_I32), r.ctypes.data_as(_I32))
+            out.append((peer.value, s, r))
+        return out
 
     n_owned = property(lambda s: lib().dcb_grid_num_owned_vertices(s.h))
 
@@ -431,8 +451,8 @@ class Stepper:
         u = _f64(u)
         _check(lib().dcb_stepper_set_state(self.h, _d(u), time))
 
-    def get_state(self):
-        u = np.empty(self.op.ndofs)
+    def get_state(self, out=None):
+        u = np.empty(self.op.ndofs) if out is None else out
         t = C.c_double()
         _check(lib().dcb_stepper_get_state(self.h, _d(u), C.byref(t)))
         return u, t.value

@@ -401,6 +401,30 @@ int dcb_grid_get_vertex_owner(const dcb_grid* g, int32_t* owner) {
   std::memcpy(owner, g->g->vowner.data(), g->g->vowner.size() * 4);
   return 0;
 }
+int dcb_grid_get_global_element_ids(const dcb_grid* g, int64_t* eids) {
+  std::memcpy(eids, g->g->global_eid.data(), g->g->global_eid.size() * 8);
+  return 0;
+}
+int dcb_grid_halo_num_peers(const dcb_grid* g, int rank) {
+  std::vector<int> peers; std::vector<std::vector<int32_t>> s, r;
+  g->g->halo_plan(rank, peers, s, r);
+  return (int)peers.size();
+}
+int dcb_grid_halo_peer(const dcb_grid* g, int rank, int k, int32_t* peer, int64_t* nsend, int64_t* nrecv) {
+  std::vector<int> peers; std::vector<std::vector<int32_t>> s, r;
+  g->g->halo_plan(rank, peers, s, r);
+  if (k < 0 || k >= (int)peers.size()) return 1;
+  *peer = peers[k]; *nsend = (int64_t)s[k].size(); *nrecv = (int64_t)r[k].size();
+  return 0;
+}
+int dcb_grid_halo_lists(const dcb_grid* g, int rank, int k, int32_t* send, int32_t* recv) {
+  std::vector<int> peers; std::vector<std::vector<int32_t>> s, r;
+  g->g->halo_plan(rank, peers, s, r);
+  if (k < 0 || k >= (int)peers.size()) return 1;
+  std::memcpy(send, s[k].data(), s[k].size() * 4);
+  std::memcpy(recv, r[k].data(), r[k].size() * 4);
+  return 0;
+}
 dcb_comm* dcb_comm_create(const char id[128], int rank, int size, dcb_operator* o) {
   return guard_new<dcb_comm>([&] {
     HaloPlan plan;

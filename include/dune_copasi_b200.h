@@ -170,6 +170,12 @@ dcb_grid* dcb_grid_partition(const dcb_grid* global, int rank, int size);
 int64_t dcb_grid_num_owned_vertices(const dcb_grid* local);
 int dcb_grid_get_global_vertex_ids(const dcb_grid* local, int64_t* gids);
 int dcb_grid_get_vertex_owner(const dcb_grid* local, int32_t* owner);
+int dcb_grid_get_global_element_ids(const dcb_grid* local, int64_t* eids);
+/* halo plan of a bound local grid (also what dcb_comm_create uses): peer k of `rank`, and the local
+ * dof indices sent to / received from it, both ordered by (compartment, global vertex, species) */
+int dcb_grid_halo_num_peers(const dcb_grid* local, int rank);
+int dcb_grid_halo_peer(const dcb_grid* local, int rank, int k, int32_t* peer, int64_t* nsend, int64_t* nrecv);
+int dcb_grid_halo_lists(const dcb_grid* local, int rank, int k, int32_t* send, int32_t* recv);
 /* communicator for a bound local grid (halo plan derived from the partition) */
 dcb_comm* dcb_comm_create(const char id[128], int rank, int size, dcb_operator* op);
 void dcb_comm_destroy(dcb_comm*);

@@ -1,0 +1,68 @@
+"""The C-ABI library loads on a CPU-only host, exports every symbol include/dune_copasi_b200.h
+declares, and refuses to compute without a CUDA device (no silent CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases as K
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "dune_copasi_b200.h")
+LIB = os.path.join(ROOT, "dune_copasi_b200", "libdune_copasi_b200.so")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dcb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    from dune_copasi_b200 import capi
+    names = declared_symbols()
+    assert len(names) >= 60
+    lib = ctypes.CDLL(LIB)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert sorted(capi.SYMBOLS) == names, set(capi.SYMBOLS) ^ set(names)
+    exported = subprocess.check_output(["nm", "-D", "--defined-only", LIB], text=True)
+    exp = sorted(set(re.findall(r" T (dcb_[a-z0-9_]+)", exported)))
+    assert exp == names, set(exp) ^ set(names)
+
+
+def test_no_torch_types_and_extern_c():
+    text = open(HEADER).read()
+    assert 'extern "C"' in text and "torch" not in text.lower() and "std::" not in text
+
+
+def test_config_roundtrip_and_overrides():
+    import dune_copasi_b200 as D
+    cfg = D.Config("[a.b]\nc = 1 # comment\nd.e = x y z\n[f]\ng=2\n")
+    cfg.set("a.b.c", "3").set("new.key", "v")
+    dump = cfg.dump()
+    assert "a.b.c = 3" in dump and "a.b.d.e = x y z" in dump and "f.g = 2" in dump and "new.key = v" in dump
+
+
+@pytest.mark.skipif(__import__("dune_copasi_b200").lib().dcb_device_count() > 0, reason="needs a host without GPU")
+def test_compute_entry_points_fail_loudly_without_gpu():
+    import dune_copasi_b200 as D
+    cfg, model, grid = K.product_objects(K.CASES["exp"])
+    with pytest.raises(D.DcbError, match="no CUDA device"):
+        D.Operator(model, grid)
+
+
+def test_library_does_not_link_the_oracle():
+    deps = subprocess.check_output(["ldd", LIB], text=True)
+    assert "oracle" not in deps
+    syms = subprocess.check_output(["nm", "-D", LIB], text=True)
+    assert "orc_" not in syms
+    # the product package never imports the oracle
+    for dp, _, fs in os.walk(os.path.join(ROOT, "dune_copasi_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cpp", ".hpp", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dp, f), errors="ignore").read()
+                assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f

@@ -1,0 +1,219 @@
+"""Pins the oracle: the reference's own known-answer system tests and
+element-level identities (section 8c item 7).  The reference asserts these through
+[model.reduce] *.error.expression thresholds in its inis; thresholds are quoted below.
+CPU only."""
+import math
+
+import numpy as np
+import pytest
+
+import cases as K
+from oracle import core as ORC
+from oracle import expr as E
+from oracle import mesh as OMESH
+
+
+def test_gauss_kat():
+    # test/gauss.ini:43,50,53-55: u_max <= 1/(4 pi D), u_min >= -1e-2, ||u - gauss||_L2 <= 0.50 at t = 1.2
+    om = K.CASES["gauss2d"].oracle(**{"model.time_step_operator.linear_solver.convergence_condition.relative_tolerance": 1e-10})
+    S = ORC.StepOperator(om)
+    u, t, n = ORC.evolve(S, om.initial(1.0), 1.0, 1.2, 0.1)
+    D = 0.005
+    exact = lambda pos, t: np.exp(-(pos ** 2).sum(-1) / (4 * t * D)) / (4 * np.pi * t * D)  # noqa: E731
+    assert n == 2 and abs(t - 1.2) < 1e-12
+    assert u.max() <= 1 / (4 * 3.14159265359 * D)
+    assert u.min() >= -1e-2
+    assert ORC.reduce_l2(om, u, "u", exact, t) <= 0.50
+
+
+def test_exp_kat():
+    # test/exp.ini:33-35: ||u - exp(-2 t)||_L2 <= 5e-3 at t = 10 (Newton path, dt_max = 0.1)
+    om = K.CASES["exp"].oracle()
+    S = ORC.StepOperator(om)
+    u, t, n = ORC.evolve(S, om.initial(0.0), 0.0, 10.0, 0.1, dt_max=0.1)
+    assert n == 100
+    err = ORC.reduce_l2(om, u, "u", lambda pos, t: np.exp(-2 * t) + 0 * pos[..., 0], t)
+    assert err <= 5e-3
+    assert S.stats["newton_its"] >= n          # the non-linear path was exercised
+
+
+def test_poisson_kat():
+    # test/poisson.ini:29-32: L2 error against |x|^2 warns above 1e-2 (fails above 2)
+    om = K.CASES["poisson"].oracle()
+    S = ORC.StepOperator(om)
+    assert S.cdofs.size == 4 * 16
+    u, t, n = ORC.evolve(S, om.initial(0.0), 0.0, 0.1, 0.1)
+    err = ORC.reduce_l2(om, u, "u", lambda pos, t: (pos ** 2).sum(-1), t)
+    assert err <= 1e-2
+    # Dirichlet values are met exactly
+    assert np.allclose(u[S.cdofs], S.cvals, rtol=0, atol=1e-14)
+
+
+def test_two_disks_kat():
+    # test/two_disks.ini:13-19,47-59: |u| <= 2; squared L2 error against the analytic two
+    # compartment solution warns above 1e-3 (key typo => no sqrt)
+    om = K.CASES["two_disks"].oracle()
+    m = om.mesh
+    assert om.names == ["u_out", "u_in"] and (m.f_out >= 0).sum() == 32 and (m.f_out < 0).sum() == 32
+    S = ORC.StepOperator(om)
+    u, t, n = ORC.evolve(S, om.initial(0.0), 0.0, 1.0, 1.0, dt_max=1.0)
+    phi = 1.0
+
+    def uin(pos, t):
+        x, y = pos[..., 0], pos[..., 1]
+        return 2 * 4 / (8 * phi + 5) * phi * np.hypot(x, y) * np.cos(np.arctan2(y, x))
+
+    def uout(pos, t):
+        x, y = pos[..., 0], pos[..., 1]
+        r = np.hypot(x, y)
+        return 4 * (r * (2 * phi + 1) + 1 / r) * np.cos(np.arctan2(y, x)) / (8 * phi + 5)
+
+    e2 = ORC.reduce_l2(om, u, "u_in", uin, t) ** 2 + ORC.reduce_l2(om, u, "u_out", uout, t) ** 2
+    assert n == 1 and np.abs(u).max() <= 2.0 + 1e-12
+    assert e2 <= 1e-3
+    # error decreases under refinement (consistency of the transmission terms)
+    case = K.Case("td_fine", K.TWO_DISKS, 2, lambda: OMESH.two_disks(12, 12, 64), dt=1.0)
+    om2 = case.oracle()
+    S2 = ORC.StepOperator(om2)
+    u2, t2, _ = ORC.evolve(S2, om2.initial(0.0), 0.0, 1.0, 1.0, dt_max=1.0)
+    e2f = ORC.reduce_l2(om2, u2, "u_in", uin, t2) ** 2 + ORC.reduce_l2(om2, u2, "u_out", uout, t2) ** 2
+    assert e2f < 0.3 * e2
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_p1_element_identities(dim):
+    """P1 mass |T|(1+delta_ab)/((d+1)(d+2)) and stiffness |T| grad phi_a . D grad phi_b are
+    integrated exactly by the order-2 rule: Jacobian of 'storage = 1' / 'cross_diffusion = D'."""
+    rng = np.random.default_rng(dim)
+    X = rng.uniform(-1, 1, (dim + 1, dim))
+    mesh = OMESH.Mesh(dim=dim, coords=X, elems=np.arange(dim + 1, dtype=np.int32)[None, :])
+    D = 0.37
+    ini = f"""
+[compartments]
+dom.expression = 1
+[model.scalar_field.u]
+compartment = dom
+storage.expression = 1
+cross_diffusion.u.expression = {D}
+"""
+    from oracle import ini as INI
+    om = ORC.Model(INI.parse_ini(ini), mesh)
+    rp, ci = om.pattern()
+    assert rp[-1] == (dim + 1) ** 2
+    x = rng.uniform(0, 1, dim + 1)
+    B = (X[1:] - X[0]).T
+    vol = abs(np.linalg.det(B)) / math.factorial(dim)
+    G = np.vstack([-np.linalg.inv(B).sum(axis=0), np.linalg.inv(B)])
+    mass = np.zeros(ci.size)
+    om.jacobian(1, 0.0, 1.0, x, rp, ci, mass)
+    stiff = np.zeros(ci.size)
+    om.jacobian(0, 0.0, 1.0, x, rp, ci, stiff)
+    Mref = vol * (1 + np.eye(dim + 1)) / ((dim + 1) * (dim + 2))
+    Kref = vol * D * (G @ G.T)
+    assert np.allclose(mass.reshape(dim + 1, dim + 1), Mref, rtol=1e-13, atol=1e-15)
+    assert np.allclose(stiff.reshape(dim + 1, dim + 1), Kref, rtol=1e-12, atol=1e-14)
+    # residual of the linear operator = matrix times coefficients; matrix-free apply agrees too
+    r = np.zeros(dim + 1)
+    om.residual(1, 0.0, 1.0, x, r)
+    om.residual(0, 0.0, 1.0, x, r)
+    assert np.allclose(r, (Mref + Kref) @ x, rtol=1e-12, atol=1e-14)
+    y = np.zeros(dim + 1)
+    om.jacobian_apply(1, 0.0, 1.0, x, x, y)
+    om.jacobian_apply(0, 0.0, 1.0, x, x, y)
+    assert np.allclose(y, r, rtol=1e-12, atol=1e-14)
+
+
+def test_numerical_jacobian_matches_analytic():
+    # local_operator.hh:713-765 (one-sided FD, eps (1+|x|)) against the analytic entries :541-707
+    om = K.CASES["grayscott2d"].oracle()
+    rp, ci = om.pattern()
+    x = K.rand_state(om.ndofs, 3)
+    ana = np.zeros(ci.size)
+    om.jacobian(0, 0.0, 1.0, x, rp, ci, ana)
+    num = np.zeros(ci.size)
+    om.jacobian(0, 0.0, 1.0, x, rp, ci, num, numerical=True)
+    assert np.linalg.norm(num - ana) / np.linalg.norm(ana) < 1e-5
+
+
+def test_jacobian_is_derivative_of_residual():
+    """Analytic Jacobian entries of every case are consistent with its residual (central FD)."""
+    for name in ("mitchell_schaefer", "cell3d", "two_disks"):
+        om = K.CASES[name].oracle()
+        rp, ci = om.pattern()
+        x = K.rand_state(om.ndofs, 5)
+        z = K.rand_state(om.ndofs, 6, -1, 1)
+        t = K.CASES[name].t0
+        y = np.zeros(om.ndofs)
+        om.jacobian_apply(1, t, 1.0, x, z, y)
+        om.jacobian_apply(0, t, 0.5, x, z, y)
+        h = 1e-6
+        rp_, rm_ = np.zeros(om.ndofs), np.zeros(om.ndofs)
+        for r, s in ((rp_, +h), (rm_, -h)):
+            om.residual(1, t, 1.0, x + s * z, r)
+            om.residual(0, t, 0.5, x + s * z, r)
+        fd = (rp_ - rm_) / (2 * h)
+        assert np.linalg.norm(fd - y) / np.linalg.norm(y) < 1e-6, name
+        # assembled matrix times z equals the matrix-free apply
+        vals = np.zeros(ci.size)
+        om.jacobian(1, t, 1.0, x, rp, ci, vals)
+        om.jacobian(0, t, 0.5, x, rp, ci, vals)
+        import scipy.sparse as sp
+        A = sp.csr_matrix((vals, ci, rp), shape=(om.ndofs, om.ndofs))
+        assert np.linalg.norm(A @ z - y) / np.linalg.norm(y) < 1e-13, name
+
+
+EXPRS = [
+    ("2^-1 + -2^2", {}, 0.5 - 4.0),
+    ("x^2*y - 3*x/y", {"x": 1.5, "y": -0.5}, 1.5 ** 2 * -0.5 - 3 * 1.5 / -0.5),
+    ("(x > y) ? x : y", {"x": 1.0, "y": 2.0}, 2.0),
+    ("x <= 1 and y >= 2 or x == 5", {"x": 1.0, "y": 2.0}, 1.0),
+    ("max(x, y, 3) + min(x, y)", {"x": 1.0, "y": 2.0}, 4.0),
+    ("sqrt((x-y)^2) < 0.5 ? 1 : 0", {"x": 1.0, "y": 1.2}, 1.0),
+    ("exp(-(x^2+y^2)/(4*0.1)) / (4*3.14159265359*0.1)", {"x": 0.3, "y": 0.4}, math.exp(-0.25 / 0.4) / (4 * 3.14159265359 * 0.1)),
+    ("atan2(y, x) + cos(x)*sin(y) - abs(-x)", {"x": 0.3, "y": 0.4}, math.atan2(0.4, 0.3) + math.cos(0.3) * math.sin(0.4) - 0.3),
+    ("1e-5*2 + 20e-2 + .5", {}, 2e-5 + 0.2 + 0.5),
+    ("no_value", {}, E.DBL_MAX),
+]
+
+
+@pytest.mark.parametrize("text,env,want", EXPRS)
+def test_expression_semantics(text, env, want):
+    """Grammar subset used by the reference's inis: C VM and python evaluator agree
+    with hand-computed values."""
+    names = sorted(env)
+    sym = E.Symbols(2, names)
+    code, consts = E.compile_expr(text, sym)
+    ctx = np.zeros((1, sym.nslots))
+    for n in names:
+        ctx[0, sym.table[n]] = env[n]
+    got = ORC.eval_program(code, consts, ctx)[0]
+    assert got == pytest.approx(want, rel=1e-15, abs=1e-300)
+    ast = E.resolve(E.Parser(text).parse(), E.Context())
+    assert E.py_eval(ast, env) == pytest.approx(want, rel=1e-15)
+
+
+def test_absent_terms():
+    # functor_factory_parser.impl.hh:122-124: empty / literal zero removes the term
+    for s in ("", "0", "0.0", " 0. ", "0e0", "-0", "+0.00"):
+        assert E.is_absent(s), s
+    for s in ("1", "0.1", "x", "0*x", "1e-300"):
+        assert not E.is_absent(s), s
+    om = K.CASES["two_disks"].oracle()
+    kinds = {(int(k), om.names[i]) for k, i, *_ in om.terms}
+    assert (ORC.K_STORAGE, "u_out") not in kinds      # storage.expression = 0 (two_disks.ini:31)
+
+
+def test_context_functions_and_constants():
+    from oracle import ini as INI
+    ctx = E.Context.from_config(INI.parse_ini("""
+[parser_context]
+a.type = constant
+a.value = 2.5
+f.type = function
+f.expression = s, t: a*s + t^2
+""")["parser_context"])
+    sym = E.Symbols(2, ["u"])
+    code, consts = E.compile_expr("f(u, 3) + a", sym, ctx)
+    c = np.zeros((1, sym.nslots))
+    c[0, sym.table["u"]] = 4.0
+    assert ORC.eval_program(code, consts, c)[0] == 2.5 * 4 + 9 + 2.5
