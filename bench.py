@@ -57,7 +57,7 @@ def ini_for(args):
 def precompile():
     """Warm the in-tree JIT cache with the bench model (called from __graft_entry__.build())."""
     import dune_copasi_b200 as D
-    ns = argparse.Namespace(rk="Alexander2", prec="Jacobi", matrix_free=True, scheme="patch")
+    ns = argparse.Namespace(rk="Alexander2", prec="Jacobi", matrix_free=True, scheme="auto", b200="")
     for mf in (True, False):
         ns.matrix_free = mf
         D.Model(D.Config(ini_for(ns)), 3).precompile()
@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--dt", type=float, default=1.0)
     ap.add_argument("--rk", default="Alexander2")
     ap.add_argument("--prec", default="Jacobi")
-    ap.add_argument("--scheme", default="patch")
+    ap.add_argument("--scheme", default="auto")
     ap.add_argument("--matrix-free", type=int, default=1)
     ap.add_argument("--b200", default="", help="model.assembly.b200.* overrides, e.g. patch_elements=768,patch_min_blocks=4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -288,6 +288,10 @@ def main():
         "elem_apply": nodes * (16 * 2 + 8 * 3 + 8 * 2) + tets * 16,
         "elem_residual": nodes * (16 * 2 + 8 * 3) + tets * 16,
         "spmv": op.ndofs * 30 * 12 + op.ndofs * 20,
+        # structured-implicit variant: no connectivity, no coordinates (32 B/vertex)
+        "struct_residual": nodes * (16 * 2),
+        "struct_apply": nodes * (16 * 2 + 8 * 2),
+        "struct_bdiag": nodes * (8 * 2 + 8 * 4),
     }
     top = max(prof, key=lambda k: prof[k]["ms"]) if prof else None
     roof = None

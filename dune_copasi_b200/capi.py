@@ -107,6 +107,7 @@ SYMBOLS = {
     "dcb_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "dcb_grid_partition": (_P, [_P, C.c_int, C.c_int]),
     "dcb_grid_num_owned_vertices": (C.c_int64, [_P]),
+    "dcb_grid_owned_vertex_range": (C.c_int, [_P, _I64, _I64]),
     "dcb_grid_get_global_vertex_ids": (C.c_int, [_P, _I64]),
     "dcb_grid_get_vertex_owner": (C.c_int, [_P, _I32]),
     "dcb_grid_get_global_element_ids": (C.c_int, [_P, _I64]),
@@ -282,6 +283,11 @@ class Grid:
         return out
 
     n_owned = property(lambda s: lib().dcb_grid_num_owned_vertices(s.h))
+
+    def owned_vertex_range(self):
+        b, e = C.c_int64(), C.c_int64()
+        lib().dcb_grid_owned_vertex_range(self.h, C.byref(b), C.byref(e))
+        return b.value, e.value
 
     def global_vertex_ids(self):
         out = np.empty(self.nv, dtype=np.int64)

@@ -151,7 +151,7 @@ int64_t dcb_model_compile(dcb_model* m, int kind, char* out, size_t cap) {
 int dcb_model_precompile(dcb_model* m) {
   return guard([&] {
     std::string defs = jit_defines(*m->m);
-    for (JitGroup g : {JitGroup::Patch, JitGroup::Element, JitGroup::Csr, JitGroup::Skeleton})
+    for (JitGroup g : {JitGroup::Patch, JitGroup::Element, JitGroup::Csr, JitGroup::Skeleton, JitGroup::Structured})
       jit_compile_cached(jit_source(*m->m, defs, g));
   });
 }
@@ -393,6 +393,11 @@ dcb_grid* dcb_grid_partition(const dcb_grid* global, int rank, int size) {
   });
 }
 int64_t dcb_grid_num_owned_vertices(const dcb_grid* g) { return g->g->n_owned; }
+int dcb_grid_owned_vertex_range(const dcb_grid* g, int64_t* begin, int64_t* end) {
+  *begin = g->g->n_owned < 0 ? 0 : g->g->owned_begin;
+  *end = g->g->n_owned < 0 ? g->g->nv : g->g->owned_begin + g->g->n_owned;
+  return 0;
+}
 int dcb_grid_get_global_vertex_ids(const dcb_grid* g, int64_t* gids) {
   std::memcpy(gids, g->g->global_vid.data(), g->g->global_vid.size() * 8);
   return 0;

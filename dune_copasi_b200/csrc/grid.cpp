@@ -10,18 +10,33 @@ namespace dcb {
 
 Grid Grid::structured(int dim, const int* cells, const double* origin, const double* extent) {
   if (dim < 2 || dim > 3) fail("structured grid: dim must be 2 or 3");
+  for (int a = 0; a < dim; ++a)
+    if (cells[a] < 1) fail("structured grid: cells must be >= 1");
+  Grid g = structured_box(dim, cells, origin, extent, 0, cells[dim - 1]);
+  for (int a = 0; a < dim; ++a) { g.s_origin_exact_[a] = origin[a]; g.s_extent_exact_[a] = extent[a]; }
+  return g;
+}
+
+// cube layers [layer_lo, layer_hi) along the last axis of the global lattice `cells`
+Grid Grid::structured_box(int dim, const int* cells, const double* origin, const double* extent,
+                          int layer_lo, int layer_hi) {
   Grid g;
   g.dim = dim;
-  int64_t nc[3] = {1, 1, 1}, nvs[3] = {1, 1, 1};
+  g.is_structured = true;
+  int64_t ncg[3] = {1, 1, 1}, nc[3] = {1, 1, 1}, nvs[3] = {1, 1, 1}, off[3] = {0, 0, 0};
+  for (int a = 0; a < dim; ++a) ncg[a] = nc[a] = cells[a];
+  nc[dim - 1] = layer_hi - layer_lo;
+  off[dim - 1] = layer_lo;
   for (int a = 0; a < dim; ++a) {
-    if (cells[a] < 1) fail("structured grid: cells must be >= 1");
-    nc[a] = cells[a];
-    nvs[a] = cells[a] + 1;
+    nvs[a] = nc[a] + 1;
+    g.s_cells[a] = (int)nc[a];
+    g.s_h[a] = extent[a] / (double)ncg[a];
+    g.s_origin[a] = origin[a] + extent[a] * ((double)off[a] / (double)ncg[a]);
   }
   g.nv = nvs[0] * nvs[1] * nvs[2];
   int nperm = dim == 2 ? 2 : 6;
   g.ne = nc[0] * nc[1] * nc[2] * nperm;
-  if (g.nv > INT32_MAX || g.ne * (dim + 1) / (dim + 1) > (int64_t)INT32_MAX * 4) fail("structured grid too large");
+  if (g.nv > INT32_MAX || g.ne > (int64_t)INT32_MAX) fail("structured grid too large for one device");
   g.coords.resize(g.nv * dim);
 #pragma omp parallel for schedule(static)
   for (int64_t k = 0; k < nvs[2]; ++k)
@@ -29,8 +44,9 @@ Grid Grid::structured(int dim, const int* cells, const double* origin, const dou
       for (int64_t i = 0; i < nvs[0]; ++i) {
         int64_t v = i + nvs[0] * (j + nvs[1] * k);
         int64_t idx[3] = {i, j, k};
+        // the global formula, so that a slab carries bit-identical coordinates
         for (int a = 0; a < dim; ++a)
-          g.coords[v * dim + a] = origin[a] + extent[a] * ((double)idx[a] / (double)nc[a]);
+          g.coords[v * dim + a] = origin[a] + extent[a] * ((double)(idx[a] + off[a]) / (double)ncg[a]);
       }
   // Kuhn simplices: walk from the lowest corner along the axes in the order of the
   // lexicographically enumerated permutations of (0..dim-1)
@@ -176,7 +192,7 @@ void Grid::bind(const Model& model) {
       // only if it has an owned vertex (then all elements around it are local); faces made of
       // ghosts only lie on the partition cut and feed ghost rows, which are never used.
       bool real = n_owned < 0;
-      for (int k = 0; k < dim && !real; ++k) real = recs[i].v[k] < n_owned;
+      for (int k = 0; k < dim && !real; ++k) real = owns(recs[i].v[k]);
       if (real) {
         for (int k = 0; k < dim; ++k) isb[recs[i].v[k]] = 1;
         if (elem_comp[recs[i].e] >= 0) fs.push_back({recs[i].e, -1, recs[i].l, -1});
@@ -327,6 +343,41 @@ void Grid::constraints(const Model& model, std::vector<int32_t>& dofs, std::vect
 Grid Grid::partition(int rank, int size) const {
   if (size < 1 || rank < 0 || rank >= size) fail("partition: bad rank/size");
   const int ndl = nd();
+  if (is_structured && global_vid.empty()) {
+    // slabs of vertex planes along the last axis
+    const int L = dim - 1;
+    const int64_t nplanes = s_cells[L] + 1;
+    if (size > nplanes) fail("partition: more ranks than vertex planes");
+    auto pbeg = [&](int r) { return nplanes * r / size; };
+    const int64_t p0 = pbeg(rank), p1 = pbeg(rank + 1);
+    const int lo = (int)std::max<int64_t>(p0 - 1, 0), hi = (int)std::min<int64_t>(p1, s_cells[L]);
+    double extent[3];
+    for (int a = 0; a < dim; ++a) extent[a] = s_h[a] * s_cells[a];
+    // s_origin/extent of a global grid are the creation arguments
+    Grid l = structured_box(dim, s_cells, s_origin_exact_, s_extent_exact_, lo, hi);
+    int64_t plane = 1;
+    for (int a = 0; a < L; ++a) plane *= s_cells[a] + 1;
+    int64_t cubes_per_layer = 1;
+    for (int a = 0; a < L; ++a) cubes_per_layer *= s_cells[a];
+    l.global_vid.resize(l.nv);
+    l.vowner.resize(l.nv);
+    for (int64_t v = 0; v < l.nv; ++v) {
+      l.global_vid[v] = v + (int64_t)lo * plane;
+      int64_t pl = v / plane + lo;
+      int r = (int)((pl + 1) * size / nplanes);
+      if (r > size - 1) r = size - 1;
+      while (r > 0 && pl < pbeg(r)) --r;
+      while (r < size - 1 && pl >= pbeg(r + 1)) ++r;
+      l.vowner[v] = r;
+    }
+    l.owned_begin = (p0 - lo) * plane;
+    l.n_owned = (p1 - p0) * plane;
+    l.global_eid.resize(l.ne);
+    const int nperm = dim == 2 ? 2 : 6;
+    for (int64_t e = 0; e < l.ne; ++e) l.global_eid[e] = e + (int64_t)lo * cubes_per_layer * nperm;
+    (void)extent;
+    return l;
+  }
   auto vbeg = [&](int r) { return (int64_t)((__int128)nv * r / size); };
   auto owner_of = [&](int64_t v) {
     int r = (int)((__int128)(v + 1) * size / nv);
@@ -357,6 +408,7 @@ Grid Grid::partition(int rank, int size) const {
   int64_t nl = 0;
   for (int64_t v = vb; v < ve; ++v) { g2l[v] = (int32_t)nl++; l.global_vid.push_back(v); }
   l.n_owned = nl;
+  l.owned_begin = 0;
   for (int64_t v = 0; v < nv; ++v)
     if (used[v] && (v < vb || v >= ve)) { g2l[v] = (int32_t)nl++; l.global_vid.push_back(v); }
   l.nv = nl;
@@ -383,12 +435,15 @@ void Grid::owned_ranges(std::vector<int64_t>& begin, std::vector<int64_t>& end) 
   begin.clear();
   end.clear();
   for (size_t c = 0; c < comp_vertices.size(); ++c) {
-    int64_t nown = (int64_t)comp_vertices[c].size();
-    if (n_owned >= 0)
-      nown = std::lower_bound(comp_vertices[c].begin(), comp_vertices[c].end(), (int32_t)n_owned) -
+    int64_t first = 0, last = (int64_t)comp_vertices[c].size();
+    if (n_owned >= 0) {
+      first = std::lower_bound(comp_vertices[c].begin(), comp_vertices[c].end(), (int32_t)owned_begin) -
+              comp_vertices[c].begin();
+      last = std::lower_bound(comp_vertices[c].begin(), comp_vertices[c].end(), (int32_t)(owned_begin + n_owned)) -
              comp_vertices[c].begin();
-    begin.push_back(comp_offset[c]);
-    end.push_back(comp_offset[c] + nown * comp_nspec[c]);
+    }
+    begin.push_back(comp_offset[c] + first * comp_nspec[c]);
+    end.push_back(comp_offset[c] + last * comp_nspec[c]);
   }
 }
 

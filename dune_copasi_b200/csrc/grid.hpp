@@ -33,8 +33,16 @@ struct Grid {
   std::vector<int64_t> comp_offset;
   int64_t ndofs = 0;
 
+  // ---- structured simplex grids keep their lattice (implicit-geometry kernels)
+  bool is_structured = false;
+  int s_cells[3] = {1, 1, 1};            // cells of this (local) box
+  double s_origin[3] = {0, 0, 0}, s_h[3] = {1, 1, 1};
+  double s_origin_exact_[3] = {0, 0, 0}, s_extent_exact_[3] = {1, 1, 1};   // creation arguments (global grid)
+
   // ---- partition data (local grids produced by partition(); empty on a global grid)
-  int64_t n_owned = -1;                  // owned vertices come first in the local numbering
+  int64_t n_owned = -1;                  // number of owned vertices (-1: not a partitioned grid)
+  int64_t owned_begin = 0;               // owned vertices are the local ids [owned_begin, owned_begin + n_owned)
+  bool owns(int64_t v) const { return n_owned < 0 || (v >= owned_begin && v < owned_begin + n_owned); }
   std::vector<int64_t> global_vid;       // [nv] global vertex id
   std::vector<int32_t> vowner;           // [nv] owning rank
   std::vector<int64_t> global_eid;       // [ne] global element id
@@ -42,7 +50,11 @@ struct Grid {
   // Vertex-range partition: rank r owns a contiguous range of global vertex
   // ids; its local mesh holds every element touching an owned vertex (owner computes, one layer of
   // ghosts), vertices renumbered owned-first (each group ascending in global id).
+  // Structured grids are cut into slabs of vertex planes along the last axis instead, so that every
+  // local mesh is again a structured box (owned planes in the middle, one ghost plane per side).
   Grid partition(int rank, int size) const;
+  static Grid structured_box(int dim, const int* cells, const double* origin, const double* extent,
+                             int layer_lo, int layer_hi);
   // owned local dof ranges per compartment (valid after bind)
   void owned_ranges(std::vector<int64_t>& begin, std::vector<int64_t>& end) const;
   // halo plan of a bound local grid: per peer the local dofs to send / receive, both ordered by

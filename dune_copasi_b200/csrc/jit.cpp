@@ -14,6 +14,7 @@ namespace dcb {
 // generated at build time from kernels/kernel_args.h and kernels/assembly.cuh (embedded_sources.cpp)
 extern const char* kKernelArgsSource;
 extern const char* kAssemblySource;
+extern const char* kStructuredSource;
 
 std::string jit_source(const Model& model, const std::string& defines, JitGroup group) {
   std::ostringstream o;
@@ -41,6 +42,16 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
         << "(DcPatchArgs a) { dc_patch_kernel<" << c << ", 1>(a); }\n";
       o << "extern \"C\" __global__ void __launch_bounds__(DC_PATCH_THREADS, DC_PATCH_MINB) dc_k_patch_bdiag_" << c
         << "(DcPatchArgs a) { dc_patch_kernel<" << c << ", 2>(a); }\n";
+    }
+  }
+  if (all || group == JitGroup::Structured) {
+    o << kStructuredSource << "\n";
+    for (int c = 0; c < model.ncomp(); ++c) {
+      if (model.comp_nspec[c] == 0 || !model.diffusion_is_constant(c)) continue;
+      const char* names[3] = {"residual", "apply", "bdiag"};
+      for (int mode = 0; mode < 3; ++mode)
+        o << "extern \"C\" __global__ void __launch_bounds__(128) dc_k_struct_" << names[mode] << "_" << c
+          << "(DcStructArgs a) { dc_structured_kernel<" << c << ", " << mode << ">(a); }\n";
     }
   }
   if (all || group == JitGroup::Skeleton) {

@@ -45,6 +45,19 @@ struct DcPatchArgs {
   const unsigned char* cmask;
 };
 
+struct DcStructArgs {
+  int n[3];                    // cells per axis of the (local) box
+  double h[3], origin[3];
+  long long ncells;
+  int dof_offset;
+  double time, wM, wA;
+  const double* x;
+  const double* z;
+  double* r;
+  double* bdiag;
+  const unsigned char* cmask;
+};
+
 struct DcFacetArgs {
   const double* coords;
   const int* elems;

@@ -116,6 +116,14 @@ bool Model::has_outflow() const {
   return false;
 }
 
+static bool depends_on_point(const NodeP& ast);
+
+bool Model::diffusion_is_constant(int c) const {
+  for (auto& t : terms)
+    if (t.kind == Term::Diff && species[t.i].comp == c && species[t.j].comp == c && depends_on_point(t.ast)) return false;
+  return true;
+}
+
 std::vector<std::pair<int, int>> Model::species_pairs() const {
   std::set<std::pair<int, int>> s;
   for (auto& t : terms) {
@@ -200,7 +208,9 @@ struct SymbolMap {
   }
 };
 
-bool depends_on_point(const NodeP& ast) {
+}  // namespace
+
+static bool depends_on_point(const NodeP& ast) {
   std::vector<std::string> v;
   collect_vars(ast, v);
   for (auto& n : v)
@@ -209,7 +219,7 @@ bool depends_on_point(const NodeP& ast) {
   return false;
 }
 
-}  // namespace
+
 
 std::string Model::cuda_source() const {
   std::ostringstream o;

@@ -48,6 +48,8 @@ class Model {
   int nspec() const { return (int)species.size(); }
   int species_index(const std::string& name) const;
   bool has_outflow() const;
+  // no diffusion coefficient of compartment c depends on the quadrature point (position, fields)
+  bool diffusion_is_constant(int c) const;
   // species couplings (i,j) of the volume sparsity pattern, local_operator.hh:276-338
   std::vector<std::pair<int, int>> species_pairs() const;
   // directional compartment pairs (cs -> ct) that carry an outflow term; ct == cs means boundary

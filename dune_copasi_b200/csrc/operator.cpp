@@ -39,8 +39,28 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
   ndofs = grid->ndofs;
   owned = la::Ranges::all(ndofs);
   const PTree& acfg = model->cfg.sub("model.assembly.b200");
-  scheme = acfg.get("scheme", std::string("patch"));
-  if (scheme != "patch" && scheme != "atomic") fail("model.assembly.b200.scheme must be 'patch' or 'atomic'");
+  scheme = acfg.get("scheme", std::string("auto"));
+  if (scheme != "auto" && scheme != "structured" && scheme != "patch" && scheme != "atomic")
+    fail("model.assembly.b200.scheme must be 'auto', 'structured', 'patch' or 'atomic'");
+  {
+    // the implicit-geometry kernels apply to structured simplex grids whose cells all belong to
+    // one compartment, without cell data and with point-independent diffusion coefficients
+    bool ok = grid->is_structured && grid->cell_keys.empty();
+    int full = -1;
+    for (int c = 0; c < model->ncomp() && ok; ++c) {
+      int64_t n = 0;
+      for (int64_t e = 0; e < grid->ne; ++e) n += grid->elem_comp[e] == c;
+      if (n == grid->ne && model->comp_nspec[c] > 0) full = c;
+      else if (n != 0 && model->comp_nspec[c] > 0) ok = false;
+    }
+    ok = ok && full >= 0 && model->diffusion_is_constant(full) &&
+         (int64_t)grid->comp_vertices[full].size() == grid->nv;
+    if (scheme == "structured" && !ok)
+      fail("model.assembly.b200.scheme = structured needs a structured single-compartment grid without cell data");
+    // measured on B200 (profiles/): element-per-thread + fp64 RED atomics beats the patch kernels
+    if (scheme == "auto") scheme = ok ? "structured" : "atomic";
+    struct_comp_ = ok ? full : -1;
+  }
   patch_pn_ = acfg.get("patch_vertices", 256);
   patch_pe_ = acfg.get("patch_elements", 512);
   patch_threads_ = acfg.get("patch_threads", 256);
@@ -52,7 +72,7 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
   // ---- kernels for this model
   jit_defines_ = jit_defines(*model);
   // the hot group is compiled up front, the others on first use
-  kernel(scheme == "patch" ? JitGroup::Patch : JitGroup::Element, "");
+  kernel(scheme == "patch" ? JitGroup::Patch : scheme == "structured" ? JitGroup::Structured : JitGroup::Element, "");
 
   // ---- mesh on the device
   const int nd = grid->nd(), ncomp = model->ncomp();
@@ -331,6 +351,27 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
   for (int c = 0; c < ncomp; ++c) {
     const int ns = model->comp_nspec[c];
     if (ns == 0 || comp_nelem_[c] == 0) continue;
+    if (scheme == "structured" && mode != 3 && c == struct_comp_) {
+      DcStructArgs a{};
+      a.ncells = 1;
+      for (int k = 0; k < 3; ++k) {
+        a.n[k] = k < grid->dim ? grid->s_cells[k] : 1;
+        a.h[k] = grid->s_h[k];
+        a.origin[k] = grid->s_origin[k];
+        a.ncells *= a.n[k];
+      }
+      a.dof_offset = (int)grid->comp_offset[c];
+      a.time = t; a.wM = wM; a.wA = wA; a.x = x; a.z = z; a.r = r;
+      a.bdiag = bdiag ? bdiag + bdiag_shift(c) : nullptr;
+      a.cmask = cmask.p;
+      static const char* sn[3] = {"dc_k_struct_residual_", "dc_k_struct_apply_", "dc_k_struct_bdiag_"};
+      static const char* sk[3] = {"struct_residual", "struct_apply", "struct_bdiag"};
+      cudaKernel_t k = kernel(JitGroup::Structured, std::string(sn[mode]) + std::to_string(c));
+      ProfScope ps(this, sk[mode]);
+      jit_launch(k, (unsigned)((a.ncells + 127) / 128), 128, 0, stream, a);
+      stats.launches++;
+      continue;
+    }
     // the block-diagonal buffer grows with ns^2: fall back to the element kernel when it cannot be staged
     const bool patch_here = use_patch && patch_smem(patches_[c], ns, mode) <= 200 * 1024;
     if (patch_here) {

@@ -114,6 +114,7 @@ class DeviceOperator {
   int64_t nnz_ = 0;
   int64_t ne_patch_total_ = 0;
   size_t patch_smem(const PatchSet& P, int ns, int mode) const;
+  int struct_comp_ = -1;   // compartment handled by the structured kernels
   int patch_pn_ = 256, patch_pe_ = 512, patch_threads_ = 256, patch_smem_kb_ = 64;
 };
 

@@ -168,6 +168,9 @@ int dcb_nccl_unique_id(char id[128]);
  * vertices first, then one layer of ghosts).  Maps are retrievable below. */
 dcb_grid* dcb_grid_partition(const dcb_grid* global, int rank, int size);
 int64_t dcb_grid_num_owned_vertices(const dcb_grid* local);
+/* owned vertices are the local ids [begin, end): a prefix for the general partition, the middle
+ * planes of the slab for structured grids */
+int dcb_grid_owned_vertex_range(const dcb_grid* local, int64_t* begin, int64_t* end);
 int dcb_grid_get_global_vertex_ids(const dcb_grid* local, int64_t* gids);
 int dcb_grid_get_vertex_owner(const dcb_grid* local, int32_t* owner);
 int dcb_grid_get_global_element_ids(const dcb_grid* local, int64_t* eids);

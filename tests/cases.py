@@ -346,9 +346,19 @@ def product_objects(case: Case, **overrides):
     mesh = case.mesh_fn()
     cfg = D.Config(case.ini_with(**overrides))
     model = D.Model(cfg, case.dim, mesh.cell_keys)
-    grid = D.Grid.from_arrays(case.dim, mesh.coords, mesh.elems, mesh.cell_keys, mesh.cell_data)
+    grid = product_grid(case, mesh)
     grid.bind(model)
     return cfg, model, grid
+
+
+def product_grid(case: Case, mesh=None):
+    """Structured cases go through the product's own generator (bit-identical arrays, see
+    tests/test_host_parity.py) so that the implicit-geometry kernels are eligible."""
+    import dune_copasi_b200 as D
+    if case.structured:
+        return D.Grid.structured(case.dim, *case.structured)
+    mesh = mesh or case.mesh_fn()
+    return D.Grid.from_arrays(case.dim, mesh.coords, mesh.elems, mesh.cell_keys, mesh.cell_data)
 
 
 def rand_state(n, seed=0, lo=0.1, hi=1.0):

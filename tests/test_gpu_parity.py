@@ -31,7 +31,7 @@ def make(case_name, **over):
     return case, om, cfg, model, grid, op
 
 
-@pytest.mark.parametrize("scheme", ["patch", "atomic"])
+@pytest.mark.parametrize("scheme", ["auto", "patch", "atomic"])
 @pytest.mark.parametrize("name", ALL)
 def test_residual(name, scheme):
     case, om, cfg, model, grid, op = make(name, **{"model.assembly.b200.scheme": scheme})
@@ -69,7 +69,7 @@ def test_jacobian_csr(name):
     assert rel(got, ref) <= OP_TOL, (name, rel(got, ref))
 
 
-@pytest.mark.parametrize("scheme", ["patch", "atomic"])
+@pytest.mark.parametrize("scheme", ["auto", "patch", "atomic"])
 @pytest.mark.parametrize("name", ALL)
 def test_jacobian_apply(name, scheme):
     case, om, cfg, model, grid, op = make(name, **{"model.assembly.b200.scheme": scheme})
@@ -92,7 +92,7 @@ def test_jacobian_apply(name, scheme):
     assert rel(got, ref) <= OP_TOL, (name, scheme, rel(got, ref))
 
 
-@pytest.mark.parametrize("scheme", ["patch", "atomic"])
+@pytest.mark.parametrize("scheme", ["auto", "patch", "atomic"])
 @pytest.mark.parametrize("name", ["grayscott3d", "cell3d", "two_disks", "gauss2d"])
 def test_block_diagonal(name, scheme):
     case, om, cfg, model, grid, op = make(name, **{"model.assembly.b200.scheme": scheme})
@@ -218,3 +218,56 @@ def test_time_steps_match_oracle(name, rk, nsteps, matrix_free):
     assert rel(got, u) <= FIELD_TOL, (name, rk, matrix_free, rel(got, u))
     stats = st.stats()
     assert stats["steps"] == nsteps and stats["kernel_launches"] > 0
+
+
+def test_adaptive_evolve_matches_oracle_and_kat():
+    """SimpleAdaptiveStepper (common/stepper.hh:337-368): dt grows by 1.1, snaps to t_end; the
+    gauss known answer (test/gauss.ini:43-55) holds for the GPU trajectory as well."""
+    import dune_copasi_b200 as D
+    case, om, cfg, model, grid, op = make("gauss2d")
+    S = K.ORC.StepOperator(om)
+    uo, to, no = K.ORC.evolve(S, om.initial(1.0), 1.0, 1.2, 0.07)
+    st = D.Stepper(op, cfg)
+    st.set_state(grid.interpolate(model, 1.0), 1.0)
+    n, dt_next = st.evolve(1.2, 0.07)
+    got, tg = st.get_state()
+    assert n == no and abs(tg - 1.2) < 1e-12 and abs(to - 1.2) < 1e-12
+    assert rel(got, uo) <= FIELD_TOL
+    Dc = 0.005
+    exact = lambda pos, t: np.exp(-(pos ** 2).sum(-1) / (4 * t * Dc)) / (4 * np.pi * t * Dc)  # noqa: E731
+    assert K.ORC.reduce_l2(om, got, "u", exact, tg) <= 0.50
+    assert got.max() <= 1 / (4 * 3.14159265359 * Dc) and got.min() >= -1e-2
+
+
+def test_empty_and_ragged_inputs():
+    """Compartments without cells / cells without compartment / single element meshes."""
+    import dune_copasi_b200 as D
+    ini = """
+[compartments]
+left.expression = position_x < 0.3
+nowhere.expression = position_x > 5
+[model.scalar_field.a]
+compartment = left
+storage.expression = 1
+cross_diffusion.a.expression = 0.1
+reaction.expression = -a^2
+reaction.jacobian.a.expression = -2*a
+[model.scalar_field.b]
+compartment = nowhere
+storage.expression = 1
+"""
+    case = K.Case("ragged", ini + K.SOLVER, 2, lambda: K.OMESH.structured(2, [10, 10]), structured=([10, 10], [0, 0], [1, 1]))
+    om = case.oracle()
+    cfg, model, grid = K.product_objects(case)
+    op = D.Operator(model, grid)
+    x = K.rand_state(om.ndofs, 1)
+    ref = np.zeros(om.ndofs)
+    om.residual(1, 0.0, 1.0, x, ref)
+    om.residual(0, 0.0, 0.3, x, ref)
+    assert rel(op.residual(0.0, 1.0, 0.3, x), ref) <= OP_TOL
+    st = D.Stepper(op, cfg)
+    st.set_state(x, 0.0)
+    assert st.step(0.1)
+    S = K.ORC.StepOperator(om)
+    u, ok = S.apply(x, 0.0, 0.1)
+    assert ok and rel(st.get_state()[0], u) <= FIELD_TOL

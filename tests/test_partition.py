@@ -23,13 +23,16 @@ def _free_port():
     return p
 
 
-def _local_problem(case, rank, size):
+def _local_problem(case, rank, size, structured=False):
     import dune_copasi_b200 as D
     from oracle import core as ORC, ini as INI, mesh as OMESH
     gmesh = case.mesh_fn()
     cfg = D.Config(case.ini)
     model = D.Model(cfg, case.dim, gmesh.cell_keys)
-    gglob = D.Grid.from_arrays(case.dim, gmesh.coords, gmesh.elems, gmesh.cell_keys, gmesh.cell_data)
+    if structured:
+        gglob = K.product_grid(case, gmesh)      # slab partition of the structured box
+    else:
+        gglob = D.Grid.from_arrays(case.dim, gmesh.coords, gmesh.elems, gmesh.cell_keys, gmesh.cell_data)
     gloc = gglob.partition(rank, size)
     gloc.bind(model)
     # the oracle on the same local arrays (cell data restricted through the element ids is not
@@ -62,7 +65,7 @@ def _global_dofs(om_glob, om_loc, gids):
     return out
 
 
-def _worker(rank, size, port, name, q):
+def _worker(rank, size, port, name, structured, q):
     import torch.distributed as dist
     try:
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -70,12 +73,15 @@ def _worker(rank, size, port, name, q):
         import torch
         case = K.CASES[name]
         om = case.oracle()                      # serial reference
-        model, gloc, oml = _local_problem(case, rank, size)
+        model, gloc, oml = _local_problem(case, rank, size, structured)
         gids = gloc.global_vertex_ids()
         owner = gloc.vertex_owner()
-        n_owned = gloc.n_owned
-        assert (owner[:n_owned] == rank).all() and (owner[n_owned:] != rank).all()
-        assert np.all(np.diff(gids[:n_owned]) == 1) and np.all(np.diff(gids[n_owned:]) > 0)
+        ob, oe = gloc.owned_vertex_range()
+        assert oe - ob == gloc.n_owned
+        is_owned = np.zeros(gloc.nv, dtype=bool)
+        is_owned[ob:oe] = True
+        assert (owner[is_owned] == rank).all() and (owner[~is_owned] != rank).all()
+        assert np.all(np.diff(gids[ob:oe]) == 1) and len(np.unique(gids)) == gids.size
         assert gloc.ndofs == oml.ndofs and np.array_equal(gloc.elem_dof(), oml.mesh.elem_dof)
         l2g = _global_dofs(om, oml, gids)
         # owned dof ranges: contiguous per compartment, and exactly the dofs on owned vertices
@@ -84,7 +90,7 @@ def _worker(rank, size, port, name, q):
             ns = oml.comp_nspec[c]
             lv = oml.mesh.comp_vertices[c]
             for s in range(ns):
-                owned_mask[oml.mesh.comp_offset[c] + np.arange(lv.size) * ns + s] = lv < n_owned
+                owned_mask[oml.mesh.comp_offset[c] + np.arange(lv.size) * ns + s] = is_owned[lv]
         x_glob = K.rand_state(om.ndofs, 42)
         x = x_glob[l2g].copy()
         # ---- halo update over gloo following the product's plan
@@ -127,13 +133,14 @@ def _worker(rank, size, port, name, q):
         raise
 
 
-@pytest.mark.parametrize("name,size", [("grayscott3d", 2), ("cell3d", 2), ("grayscott2d", 3), ("two_disks", 2)])
-def test_partition_halo_gloo(name, size):
+@pytest.mark.parametrize("name,size,structured", [("grayscott3d", 2, False), ("cell3d", 2, False), ("grayscott2d", 3, False),
+                                                  ("two_disks", 2, False), ("grayscott3d", 3, True), ("cell3d", 2, True)])
+def test_partition_halo_gloo(name, size, structured):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, size, port, name, q)) for r in range(size)]
+    procs = [ctx.Process(target=_worker, args=(r, size, port, name, structured, q)) for r in range(size)]
     for p in procs:
         p.start()
     results = [q.get(timeout=240) for _ in procs]
@@ -143,14 +150,19 @@ def test_partition_halo_gloo(name, size):
         assert msg == "ok", f"rank {rank}: {msg}"
 
 
-def test_owned_ranges_match_mask():
-    import dune_copasi_b200 as D
+@pytest.mark.parametrize("structured", [False, True])
+def test_owned_ranges_are_contiguous_per_compartment(structured):
     case = K.CASES["cell3d"]
+    total = 0
     for rank in range(3):
-        model, gloc, oml = _local_problem(case, rank, 3)
-        n_owned = gloc.n_owned
-        # same rule as Grid::owned_ranges: owned vertices come first in every compartment
+        model, gloc, oml = _local_problem(case, rank, 3, structured)
+        ob, oe = gloc.owned_vertex_range()
+        # Grid::owned_ranges: the owned dofs of a compartment are one contiguous range
         for c in range(oml.ncomp):
             lv = oml.mesh.comp_vertices[c]
-            k = int(np.searchsorted(lv, n_owned))
-            assert (lv[:k] < n_owned).all() and (lv[k:] >= n_owned).all()
+            owned = (lv >= ob) & (lv < oe)
+            idx = np.nonzero(owned)[0]
+            if idx.size:
+                assert idx[-1] - idx[0] + 1 == idx.size
+            total += int(owned.sum()) * oml.comp_nspec[c]
+    assert total == case.oracle().ndofs

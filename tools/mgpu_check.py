@@ -35,7 +35,7 @@ def main():
     gmesh = case.mesh_fn()
     cfg = D.Config(case.ini_with(**over))
     model = D.Model(cfg, case.dim, gmesh.cell_keys)
-    gglob = D.Grid.from_arrays(case.dim, gmesh.coords, gmesh.elems, gmesh.cell_keys, gmesh.cell_data)
+    gglob = K.product_grid(case, gmesh)     # structured cases -> slab partition + structured kernels
     grid = gglob.partition(rank, world)
     grid.bind(model)
     op = D.Operator(model, grid)
@@ -53,7 +53,8 @@ def main():
     om = case.oracle(**over) if rank == 0 else None
     gids = grid.global_vertex_ids()
     ranges = op.owned_ranges()
-    payload = [gids[:grid.n_owned], [u[b:e] for b, e in ranges], grid.elem_compartment(), grid.elements()]
+    ob, oe = grid.owned_vertex_range()
+    payload = [gids, (ob, oe), [u[b:e] for b, e in ranges], grid.elem_compartment(), grid.elements()]
     gathered = [None] * world
     dist.gather_object(payload, gathered if rank == 0 else None, dst=0)
     ok = True
@@ -67,16 +68,15 @@ def main():
             tt += case.dt
         got = np.full(om.ndofs, np.nan)
         mg = om.mesh
-        for r, (g_owned, vals, ecomp, elems) in enumerate(gathered):
-            n_owned = g_owned.size
+        for r, (gid_all, (ob, oe), vals, ecomp, elems) in enumerate(gathered):
             for c in range(om.ncomp):
                 ns = om.comp_nspec[c]
                 if ns == 0:
                     continue
                 # local vertices of compartment c that are owned, ascending local id == ascending gid
                 lv = np.unique(elems[ecomp == c])
-                lv = lv[lv < n_owned]
-                gv = g_owned[lv]
+                lv = lv[(lv >= ob) & (lv < oe)]
+                gv = gid_all[lv]
                 pos = np.searchsorted(mg.comp_vertices[c], gv)
                 for s in range(ns):
                     got[mg.comp_offset[c] + pos * ns + s] = vals[c][s::ns]
