@@ -134,14 +134,14 @@ int dcb_model_num_species(const dcb_model* m) { return m->m->nspec(); }
 const char* dcb_model_species_name(const dcb_model* m, int s) { return m->m->species.at(s).name.c_str(); }
 int dcb_model_species_compartment(const dcb_model* m, int s) { return m->m->species.at(s).comp; }
 const char* dcb_model_cuda_source(dcb_model* m) {
-  if (guard([&] { m->source = jit_source(*m->m); })) return nullptr;
+  if (guard([&] { m->source = jit_source(*m->m, jit_defines(*m->m)); })) return nullptr;
   return m->source.c_str();
 }
 int64_t dcb_model_compile(dcb_model* m, int kind, char* out, size_t cap) {
   int64_t n = -1;
   guard([&] {
     std::string log;
-    std::vector<char> bin = jit_compile(jit_source(*m->m), &log, kind == 1);
+    std::vector<char> bin = jit_compile(jit_source(*m->m, jit_defines(*m->m)), &log, kind == 1);
     n = (int64_t)bin.size();
     if (out && cap) std::memcpy(out, bin.data(), std::min(cap, bin.size()));
   });

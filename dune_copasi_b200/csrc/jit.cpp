@@ -50,7 +50,7 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
       if (model.comp_nspec[c] == 0 || !model.diffusion_is_constant(c)) continue;
       const char* names[3] = {"residual", "apply", "bdiag"};
       for (int mode = 0; mode < 3; ++mode)
-        o << "extern \"C\" __global__ void __launch_bounds__(128) dc_k_struct_" << names[mode] << "_" << c
+        o << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, DC_STRUCT_MINB) dc_k_struct_" << names[mode] << "_" << c
           << "(DcStructArgs a) { dc_structured_kernel<" << c << ", " << mode << ">(a); }\n";
     }
   }
@@ -73,7 +73,12 @@ std::string jit_defines(const Model& model) {
   int th = acfg.get("patch_threads", 256), minb = acfg.get("patch_min_blocks", 3);
   if (th < 32 || th > 1024 || th % 32) fail("model.assembly.b200.patch_threads must be a multiple of 32 in [32,1024]");
   if (minb < 1 || minb > 8) fail("model.assembly.b200.patch_min_blocks out of range");
-  return "#define DC_PATCH_THREADS " + std::to_string(th) + "\n#define DC_PATCH_MINB " + std::to_string(minb) + "\n";
+  // 64 threads x 6 resident CTAs measured best on B200 (profiles/r01_struct_sweep.txt)
+  int sth = acfg.get("struct_threads", 64), sminb = acfg.get("struct_min_blocks", 6);
+  if (sth < 32 || sth > 1024 || sth % 32) fail("model.assembly.b200.struct_threads must be a multiple of 32 in [32,1024]");
+  if (sminb < 1 || sminb > 16) fail("model.assembly.b200.struct_min_blocks out of range");
+  return "#define DC_PATCH_THREADS " + std::to_string(th) + "\n#define DC_PATCH_MINB " + std::to_string(minb) +
+         "\n#define DC_STRUCT_THREADS " + std::to_string(sth) + "\n#define DC_STRUCT_MINB " + std::to_string(sminb) + "\n";
 }
 
 std::vector<char> jit_compile(const std::string& source, std::string* log, bool ptx) {

@@ -4,11 +4,16 @@
 //
 // One thread integrates one lattice cell = dim! Kuhn simplices.  The 2^dim corner values are
 // loaded once (coalesced along x) instead of (dim+1) gathers per simplex, no coordinates and no
-// connectivity are read, the gradients along a Kuhn path are plain edge differences:
-//     du/dx_{p_t} = (u_{t+1} - u_t) / h_{p_t},   |det| = prod h,
-// and the cell's contributions are pre-summed per corner before one fp64 reduction per corner
-// value.  Same weak form, same quadrature points and weights as DcElem.
-// MODE 0: residual, 1: Jacobian apply, 2: block diagonal.
+// connectivity are read, and the cell's contributions are pre-summed per corner before one fp64
+// reduction per corner value.  fp64 is the bound of this kernel, so the arithmetic is folded:
+//  * mass/reaction part per simplex with the symmetric-rule identities of DcElem, accumulated
+//    straight into the corner sums;
+//  * diffusion part per *cell*: along a Kuhn path the gradient components are edge differences
+//    du/dx_k = (u(m|k) - u(m))/h_k, and every lattice edge (m -> m|k) is used by
+//    |m|! (d-1-|m|)! of the d! paths, so the cell's stiffness action is a sum over its
+//    d 2^(d-1) edges instead of d! simplices x d path edges.
+// Same weak form, quadrature points and weights as DcElem (requires point-independent diffusion
+// coefficients, which the host checks).  MODE 0: residual, 1: Jacobian apply, 2: block diagonal.
 #if DC_DIM == 2
 #define DC_NPERM 2
 #define DC_NCORN 4
@@ -27,6 +32,15 @@ __device__ __forceinline__ constexpr int dc_corner(int p, int k) {
   int m = 0;
   for (int t = 0; t < k; ++t) m |= 1 << dc_perm(p, t);
   return m;
+}
+// number of Kuhn paths through the lattice edge that leaves corner m: |m|! (d-1-|m|)!
+__device__ __forceinline__ constexpr int dc_edge_paths(int m) {
+  int bits = 0;
+  for (int k = 0; k < DC_DIM; ++k) bits += (m >> k) & 1;
+  int a = 1, b = 1;
+  for (int i = 2; i <= bits; ++i) a *= i;
+  for (int i = 2; i <= DC_DIM - 1 - bits; ++i) b *= i;
+  return a * b;
 }
 
 template <int C, int MODE>
@@ -71,6 +85,7 @@ __device__ __forceinline__ void dc_structured_kernel(const DcStructArgs& a) {
 #pragma unroll
   for (int k = 0; k < DC_DIM; ++k) { adet *= a.h[k]; rh[k] = 1.0 / a.h[k]; }
   const double f = DC_QW * adet, vol = adet / DC_FACT;
+  const double ABf = DC_PAB * f, Bf = DC_PB * f;
   DcCtx c;
   c.time = a.time; c.entity_volume = vol; c.integration_factor = f;
   c.in_volume = 1.0; c.in_boundary = 0.0; c.in_skeleton = 0.0;
@@ -79,17 +94,16 @@ __device__ __forceinline__ void dc_structured_kernel(const DcStructArgs& a) {
 #pragma unroll
   for (int k = 0; k < DC_DIM; ++k) x0[k] = a.origin[k] + idx[k] * a.h[k];
 
+  // ---- mass / reaction part, simplex by simplex
 #pragma unroll
   for (int p = 0; p < DC_NPERM; ++p) {
-    // vertex k of this simplex sits at corner dc_corner(p,k); its coordinates are x0 + h on the
-    // axes stepped so far
-    double xl[NS][DC_ND], S[NS], gu[NS][DC_DIM];
+    double xl[NS][DC_ND], BS[NS], gu[NS][DC_DIM];
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       double t = 0.0;
 #pragma unroll
       for (int k = 0; k < DC_ND; ++k) { xl[s][k] = U[dc_corner(p, k)][s]; t += xl[s][k]; }
-      S[s] = t;
+      BS[s] = DC_PB * t;
 #pragma unroll
       for (int k = 0; k < DC_DIM; ++k) gu[s][dc_perm(p, k)] = (xl[s][k + 1] - xl[s][k]) * rh[dc_perm(p, k)];
     }
@@ -98,7 +112,6 @@ __device__ __forceinline__ void dc_structured_kernel(const DcStructArgs& a) {
 #pragma unroll
     for (int t = 0; t < DC_DIM; ++t) XS[dc_perm(p, t)] = DC_ND * x0[dc_perm(p, t)] + (DC_DIM - t) * a.h[dc_perm(p, t)];
     auto set_pos = [&](int q) {
-      // X of vertex v: x0 + h on axes p_0..p_{v-1}
 #pragma unroll
       for (int k = 0; k < DC_DIM; ++k) {
         const int v = DC_VQ(q);
@@ -108,7 +121,6 @@ __device__ __forceinline__ void dc_structured_kernel(const DcStructArgs& a) {
         c.pos[k] = DC_PB * XS[k] + DC_PAB * (x0[k] + (stepped ? a.h[k] : 0.0));
       }
     };
-    double loc[NV == NS ? NS : 1][DC_ND];
     if (MODE == 0) {
       double T[NS];
 #pragma unroll
@@ -118,45 +130,29 @@ __device__ __forceinline__ void dc_structured_kernel(const DcStructArgs& a) {
         double u[NS], sc[NS];
         set_pos(q);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) u[s] = DC_PB * S[s] + DC_PAB * xl[s][DC_VQ(q)];
+        for (int s = 0; s < NS; ++s) u[s] = BS[s] + DC_PAB * xl[s][DC_VQ(q)];
         M::scalar(c, u, gu, a.wM, a.wA, sc);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) { T[s] += sc[s]; loc[s][DC_VQ(q)] = DC_PAB * sc[s]; }
-      }
-#pragma unroll
-      for (int s = 0; s < NS; ++s)
-#pragma unroll
-        for (int k = 0; k < DC_ND; ++k) loc[s][k] = (loc[s][k] + DC_PB * T[s]) * f;
-      if (M::HAS_DIFF) {
-        double u0[NS], fl[NS][DC_DIM];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) u0[s] = 0.0;
-#pragma unroll
-        for (int k = 0; k < DC_DIM; ++k) c.pos[k] = XS[k] / DC_ND;
-        M::flux(c, u0, gu, a.wA, fl);
-#pragma unroll
         for (int s = 0; s < NS; ++s) {
-          // fl . grad(phi_k) |T| with grad(phi_0) = -e_{p0}/h, grad(phi_t) = e_{p(t-1)}/h - e_{pt}/h
-          double w[DC_DIM];
-#pragma unroll
-          for (int t = 0; t < DC_DIM; ++t) w[t] = fl[s][dc_perm(p, t)] * rh[dc_perm(p, t)] * vol;
-          loc[s][0] += w[0];
-#pragma unroll
-          for (int t = 1; t < DC_DIM; ++t) loc[s][t] -= w[t - 1] - w[t];
-          loc[s][DC_DIM] -= w[DC_DIM - 1];
+          T[s] += sc[s];
+          acc[dc_corner(p, DC_VQ(q))][s] += ABf * sc[s];
         }
       }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const double bt = Bf * T[s];
+#pragma unroll
+        for (int k = 0; k < DC_ND; ++k) acc[dc_corner(p, k)][s] += bt;
+      }
     } else if (MODE == 1) {
-      double zl[NS][DC_ND], ZS[NS], gz[NS][DC_DIM], T[NS];
+      double zl[NS][DC_ND], BZ[NS], T[NS];
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         double t = 0.0;
 #pragma unroll
         for (int k = 0; k < DC_ND; ++k) { zl[s][k] = Z[dc_corner(p, k)][s]; t += zl[s][k]; }
-        ZS[s] = t;
+        BZ[s] = DC_PB * t;
         T[s] = 0.0;
-#pragma unroll
-        for (int k = 0; k < DC_DIM; ++k) gz[s][dc_perm(p, k)] = (zl[s][k + 1] - zl[s][k]) * rh[dc_perm(p, k)];
       }
 #pragma unroll
       for (int q = 0; q < DC_NQ; ++q) {
@@ -164,8 +160,8 @@ __device__ __forceinline__ void dc_structured_kernel(const DcStructArgs& a) {
         set_pos(q);
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
-          u[s] = DC_PB * S[s] + DC_PAB * xl[s][DC_VQ(q)];
-          zq[s] = DC_PB * ZS[s] + DC_PAB * zl[s][DC_VQ(q)];
+          u[s] = BS[s] + DC_PAB * xl[s][DC_VQ(q)];
+          zq[s] = BZ[s] + DC_PAB * zl[s][DC_VQ(q)];
         }
         M::jac_mass(c, u, gu, a.wM, a.wA, jm);
 #pragma unroll
@@ -175,85 +171,86 @@ __device__ __forceinline__ void dc_structured_kernel(const DcStructArgs& a) {
           for (int j = 0; j < NS; ++j)
             if (M::pair(i, j)) w += jm[i][j] * zq[j];
           T[i] += w;
-          loc[i][DC_VQ(q)] = DC_PAB * w;
+          acc[dc_corner(p, DC_VQ(q))][i] += ABf * w;
         }
       }
 #pragma unroll
-      for (int i = 0; i < NS; ++i)
+      for (int i = 0; i < NS; ++i) {
+        const double bt = Bf * T[i];
 #pragma unroll
-        for (int k = 0; k < DC_ND; ++k) loc[i][k] = (loc[i][k] + DC_PB * T[i]) * f;
-      if (M::HAS_DIFF) {
-        double u0[NS], jd[NS][NS];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) u0[s] = 0.0;
-#pragma unroll
-        for (int k = 0; k < DC_DIM; ++k) c.pos[k] = XS[k] / DC_ND;
-        M::jac_diff(c, u0, gu, a.wA, jd);
-#pragma unroll
-        for (int i = 0; i < NS; ++i) {
-          double w[DC_DIM];
-#pragma unroll
-          for (int t = 0; t < DC_DIM; ++t) {
-            double fl = 0.0;
-#pragma unroll
-            for (int j = 0; j < NS; ++j)
-              if (M::pair(i, j)) fl += jd[i][j] * gz[j][dc_perm(p, t)];
-            w[t] = fl * rh[dc_perm(p, t)] * vol;
-          }
-          loc[i][0] -= w[0];
-#pragma unroll
-          for (int t = 1; t < DC_DIM; ++t) loc[i][t] += w[t - 1] - w[t];
-          loc[i][DC_DIM] += w[DC_DIM - 1];
-        }
+        for (int k = 0; k < DC_ND; ++k) acc[dc_corner(p, k)][i] += bt;
       }
-    }
-    if (MODE != 2) {
-#pragma unroll
-      for (int k = 0; k < DC_ND; ++k)
-#pragma unroll
-        for (int s = 0; s < NS; ++s) acc[dc_corner(p, k)][s] += loc[s][k];
     } else {
-      double JS[NS][NS], JV[DC_ND][NS][NS], DD[NS][NS];
+      double JS[NS][NS], JV[DC_ND][NS][NS];
 #pragma unroll
       for (int i = 0; i < NS; ++i)
 #pragma unroll
-        for (int j = 0; j < NS; ++j) { JS[i][j] = 0.0; DD[i][j] = 0.0; }
+        for (int j = 0; j < NS; ++j) JS[i][j] = 0.0;
 #pragma unroll
       for (int q = 0; q < DC_NQ; ++q) {
         double u[NS];
         set_pos(q);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) u[s] = DC_PB * S[s] + DC_PAB * xl[s][DC_VQ(q)];
+        for (int s = 0; s < NS; ++s) u[s] = BS[s] + DC_PAB * xl[s][DC_VQ(q)];
         M::jac_mass(c, u, gu, a.wM, a.wA, JV[DC_VQ(q)]);
 #pragma unroll
         for (int i = 0; i < NS; ++i)
 #pragma unroll
           for (int j = 0; j < NS; ++j) JS[i][j] += JV[DC_VQ(q)][i][j];
       }
-      if (M::HAS_DIFF) {
-        double u0[NS];
 #pragma unroll
-        for (int s = 0; s < NS; ++s) u0[s] = 0.0;
-#pragma unroll
-        for (int k = 0; k < DC_DIM; ++k) c.pos[k] = XS[k] / DC_ND;
-        M::jac_diff(c, u0, gu, a.wA, DD);
-      }
-#pragma unroll
-      for (int k = 0; k < DC_ND; ++k) {
-        // |grad phi_k|^2
-        double gg = 0.0;
-        if (k > 0) gg += rh[dc_perm(p, k - 1)] * rh[dc_perm(p, k - 1)];
-        if (k < DC_DIM) gg += rh[dc_perm(p, k)] * rh[dc_perm(p, k)];
+      for (int k = 0; k < DC_ND; ++k)
 #pragma unroll
         for (int i = 0; i < NS; ++i)
 #pragma unroll
           for (int j = 0; j < NS; ++j)
             if (M::pair(i, j))
               acc[dc_corner(p, k)][i * NS + j] +=
-                  (DC_PB * DC_PB * JS[i][j] + (DC_PA * DC_PA - DC_PB * DC_PB) * JV[k][i][j]) * f + DD[i][j] * gg * vol;
-      }
+                  (DC_PB * DC_PB * JS[i][j] + (DC_PA * DC_PA - DC_PB * DC_PB) * JV[k][i][j]) * f;
     }
   }
+
+  // ---- diffusion part, lattice edge by lattice edge
+  if (M::HAS_DIFF) {
+    double u0[NS], g0[NS][DC_DIM], jd[NS][NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      u0[s] = 0.0;
+#pragma unroll
+      for (int k = 0; k < DC_DIM; ++k) g0[s][k] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < DC_DIM; ++k) c.pos[k] = x0[k] + 0.5 * a.h[k];
+    M::jac_diff(c, u0, g0, a.wA, jd);   // jd[i][j] = wA * D_ij (point independent)
+#pragma unroll
+    for (int m = 0; m < DC_NCORN; ++m)
+#pragma unroll
+      for (int k = 0; k < DC_DIM; ++k) {
+        if ((m >> k) & 1) continue;
+        const int m2 = m | (1 << k);
+        const double wgt = dc_edge_paths(m) * vol * rh[k] * rh[k];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          if (MODE == 2) {
+#pragma unroll
+            for (int j = 0; j < NS; ++j)
+              if (M::pair(i, j)) {
+                acc[m][i * NS + j] += wgt * jd[i][j];
+                acc[m2][i * NS + j] += wgt * jd[i][j];
+              }
+          } else {
+            double d = 0.0;
+#pragma unroll
+            for (int j = 0; j < NS; ++j)
+              if (M::pair(i, j)) d += jd[i][j] * (MODE == 0 ? (U[m2][j] - U[m][j]) : (Z[m2][j] - Z[m][j]));
+            d *= wgt;
+            acc[m2][i] += d;
+            acc[m][i] -= d;
+          }
+        }
+      }
+  }
+
   // ---- one reduction per corner value
 #pragma unroll
   for (int m = 0; m < DC_NCORN; ++m) {

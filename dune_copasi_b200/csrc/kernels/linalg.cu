@@ -168,6 +168,60 @@ __global__ void __launch_bounds__(kThreads) k_axpy_pair_norm(int64_t n, Ranges o
   grid_reduce<2>(acc, partials, counter, out);
 }
 
+// ---- fused BiCGSTAB sweeps (Jacobi folded into the producing kernel when dinv != null) ----------
+// p = r + beta (p - omega v) ; y = relax * dinv * p
+__global__ void __launch_bounds__(kThreads) k_bicg_p_prec(int64_t n, double* __restrict__ p,
+                                                          const double* __restrict__ r,
+                                                          const double* __restrict__ v, double beta,
+                                                          double omega, bool first,
+                                                          const double* __restrict__ dinv, double relax,
+                                                          double* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    const double pi = first ? r[i] : r[i] + beta * (p[i] - omega * v[i]);
+    p[i] = pi;
+    if (dinv) y[i] = relax * dinv[i] * pi;
+  }
+}
+// r -= alpha v ; out[0] = <r,r> ; y2 = relax * dinv * r
+__global__ void __launch_bounds__(kThreads) k_bicg_r_prec(int64_t n, Ranges own, double alpha,
+                                                          const double* __restrict__ v,
+                                                          double* __restrict__ r,
+                                                          const double* __restrict__ dinv, double relax,
+                                                          double* __restrict__ y2, double* partials,
+                                                          unsigned* counter, double* out) {
+  double acc[1] = {0.0};
+  const bool single = own.n == 1 && own.b[0] == 0 && own.e[0] == n;
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    const double ri = r[i] - alpha * v[i];
+    r[i] = ri;
+    if (dinv) y2[i] = relax * dinv[i] * ri;
+    if (single || in_ranges(own, i)) acc[0] += ri * ri;
+  }
+  grid_reduce<1>(acc, partials, counter, out);
+}
+// x += alpha y1 + omega y2 ; r -= omega t ; out[0] = <r,r> ; out[1] = <rt,r>
+__global__ void __launch_bounds__(kThreads) k_bicg_final(int64_t n, Ranges own, double alpha,
+                                                         const double* __restrict__ y1, double omega,
+                                                         const double* __restrict__ y2,
+                                                         double* __restrict__ x,
+                                                         const double* __restrict__ t,
+                                                         double* __restrict__ r,
+                                                         const double* __restrict__ rt, double* partials,
+                                                         unsigned* counter, double* out) {
+  double acc[2] = {0.0, 0.0};
+  const bool single = own.n == 1 && own.b[0] == 0 && own.e[0] == n;
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    x[i] = (x[i] + alpha * y1[i]) + omega * y2[i];
+    const double ri = r[i] - omega * t[i];
+    r[i] = ri;
+    if (single || in_ranges(own, i)) {
+      acc[0] += ri * ri;
+      acc[1] += rt[i] * ri;
+    }
+  }
+  grid_reduce<2>(acc, partials, counter, out);
+}
+
 __global__ void __launch_bounds__(kThreads) k_xpby(int64_t n, double* __restrict__ p,
                                                    const double* __restrict__ q, double beta) {
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
@@ -352,6 +406,22 @@ void bicg_update_p(int64_t n, double* p, const double* r, const double* v, doubl
 void axpy_pair_norm(int64_t n, const Ranges& own, double alpha, const double* y, double* x, const double* v,
                     double* r, const double* rt, double* out, const ReduceWorkspace& w, cudaStream_t s) {
   k_axpy_pair_norm<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, alpha, y, x, v, r, rt, w.partials, w.counter, out);
+  check_launch();
+}
+void bicg_p_prec(int64_t n, double* p, const double* r, const double* v, double beta, double omega, bool first,
+                 const double* dinv, double relax, double* y, cudaStream_t s) {
+  k_bicg_p_prec<<<grid_for(n, 2), kThreads, 0, s>>>(n, p, r, v, beta, omega, first, dinv, relax, y);
+  check_launch();
+}
+void bicg_r_prec(int64_t n, const Ranges& own, double alpha, const double* v, double* r, const double* dinv,
+                 double relax, double* y2, double* out, const ReduceWorkspace& w, cudaStream_t s) {
+  k_bicg_r_prec<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, alpha, v, r, dinv, relax, y2, w.partials, w.counter, out);
+  check_launch();
+}
+void bicg_final(int64_t n, const Ranges& own, double alpha, const double* y1, double omega, const double* y2,
+                double* x, const double* t, double* r, const double* rt, double* out, const ReduceWorkspace& w,
+                cudaStream_t s) {
+  k_bicg_final<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, alpha, y1, omega, y2, x, t, r, rt, w.partials, w.counter, out);
   check_launch();
 }
 void xpby(int64_t n, double* p, const double* q, double beta, cudaStream_t s) {

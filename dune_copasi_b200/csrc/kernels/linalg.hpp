@@ -42,6 +42,17 @@ void bicg_update_p(int64_t n, double* p, const double* r, const double* v, doubl
 // x += alpha y ; r -= alpha v ; out[0] = <r,r> ; out[1] = <rt,r>  (rt may be null -> out[1] = 0)
 void axpy_pair_norm(int64_t n, const Ranges& own, double alpha, const double* y, double* x, const double* v, double* r,
                     const double* rt, double* out, const ReduceWorkspace& w, cudaStream_t s);
+// fused BiCGSTAB sweeps; dinv == null skips the folded Jacobi application
+// p = r + beta (p - omega v) ; y = relax dinv p
+void bicg_p_prec(int64_t n, double* p, const double* r, const double* v, double beta, double omega, bool first,
+                 const double* dinv, double relax, double* y, cudaStream_t s);
+// r -= alpha v ; out[0] = <r,r> ; y2 = relax dinv r
+void bicg_r_prec(int64_t n, const Ranges& own, double alpha, const double* v, double* r, const double* dinv,
+                 double relax, double* y2, double* out, const ReduceWorkspace& w, cudaStream_t s);
+// x += alpha y1 + omega y2 ; r -= omega t ; out[0] = <r,r> ; out[1] = <rt,r>
+void bicg_final(int64_t n, const Ranges& own, double alpha, const double* y1, double omega, const double* y2,
+                double* x, const double* t, double* r, const double* rt, double* out, const ReduceWorkspace& w,
+                cudaStream_t s);
 // CG: p = q + beta p
 void xpby(int64_t n, double* p, const double* q, double beta, cudaStream_t s);
 // y += a x

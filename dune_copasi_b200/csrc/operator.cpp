@@ -368,7 +368,8 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       static const char* sk[3] = {"struct_residual", "struct_apply", "struct_bdiag"};
       cudaKernel_t k = kernel(JitGroup::Structured, std::string(sn[mode]) + std::to_string(c));
       ProfScope ps(this, sk[mode]);
-      jit_launch(k, (unsigned)((a.ncells + 127) / 128), 128, 0, stream, a);
+      const int sth = model->cfg.sub("model.assembly.b200").get("struct_threads", 64);
+      jit_launch(k, (unsigned)((a.ncells + sth - 1) / sth), sth, 0, stream, a);
       stats.launches++;
       continue;
     }

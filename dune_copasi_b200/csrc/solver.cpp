@@ -134,7 +134,9 @@ SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
   // skipped, r = b.
   { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::fill(n, 0.0, x, s); L++; }
   if (type == "BiCGSTAB") {
-    double *rt = work_[0].p, *p = work_[1].p, *v = work_[2].p, *t = work_[3].p, *y = work_[4].p;
+    double *rt = work_[0].p, *p = work_[1].p, *v = work_[2].p, *t = work_[3].p, *y = work_[4].p, *y2 = work_[5].p;
+    // Jacobi is folded into the sweeps that produce its argument; other preconditioners run on their own
+    const double* fold = prec_type == "Jacobi" ? dinv_.p : nullptr;
     { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::copy(n, r, rt, s); L++; }
     { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, r, r, scal_.p, ws_, s); L++; }
     fetch(1);
@@ -144,31 +146,34 @@ SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
     if (norm0 < 1e-30) { res.converged = true; res.reduction = 0; return res; }
     double rho = 1, alpha = 1, omega = 1, rho_new = hscal_.p[0];   // <rt,r> = <r,r> at the start
     double it = 0.5;
+    bool pending = false;   // x += alpha*y of the first half step is applied together with the second
     for (; it < max_iterations; it += 0.5) {
       // rho_new = <rt,r> was produced by the previous sweep (fused with the norm)
       if (std::fabs(rho) <= 1e-80 || std::fabs(omega) <= 1e-80) break;   // breakdown (SolverAbort)
       double beta = (rho_new / rho) * (alpha / omega);
-      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::bicg_update_p(n, p, r, v, beta, omega, it < 1, s); L++; }
-      precondition(p, y);
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::bicg_p_prec(n, p, r, v, beta, omega, it < 1, fold, relaxation, y, s); L++; }
+      if (!fold) precondition(p, y);
       apply_operator(y, v);
       { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, rt, v, scal_.p, ws_, s); L++; }
       fetch(1);
       double h = hscal_.p[0];
       if (std::fabs(h) < 1e-80) break;
       alpha = rho_new / h;
-      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::axpy_pair_norm(n, own, alpha, y, x, v, r, nullptr, scal_.p, ws_, s); L++; }
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::bicg_r_prec(n, own, alpha, v, r, fold, relaxation, y2, scal_.p, ws_, s); L++; }
+      pending = true;
       fetch(1);
       norm = std::sqrt(hscal_.p[0]);
       res.half_iterations++;
       if (!(norm == norm)) break;
       if (norm < rel_tol * norm0 || norm < 1e-30) { res.converged = true; break; }
       it += 0.5;
-      precondition(r, y);
-      apply_operator(y, t);
+      if (!fold) precondition(r, y2);
+      apply_operator(y2, t);
       { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot2(own, t, r, t, t, scal_.p, ws_, s); L++; }
       fetch(2);
       omega = hscal_.p[0] / hscal_.p[1];
-      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::axpy_pair_norm(n, own, omega, y, x, t, r, rt, scal_.p, ws_, s); L++; }
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::bicg_final(n, own, alpha, y, omega, y2, x, t, r, rt, scal_.p, ws_, s); L++; }
+      pending = false;
       fetch(2);
       rho = rho_new;
       rho_new = hscal_.p[1];
@@ -177,6 +182,7 @@ SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
       if (!(norm == norm)) break;
       if (norm < rel_tol * norm0 || norm < 1e-30) { res.converged = true; break; }
     }
+    if (pending) { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::axpy(n, alpha, y, x, s); L++; }
     res.iterations = (int)std::ceil(std::min<double>(it, max_iterations));
     res.reduction = norm / norm0;
   } else {   // CG
