@@ -48,8 +48,8 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
     o << kStructuredSource << "\n";
     for (int c = 0; c < model.ncomp(); ++c) {
       if (model.comp_nspec[c] == 0 || !model.diffusion_is_constant(c)) continue;
-      const char* names[3] = {"residual", "apply", "bdiag"};
-      for (int mode = 0; mode < 3; ++mode)
+      const char* names[4] = {"residual", "apply", "bdiag", "diag"};
+      for (int mode = 0; mode < 4; ++mode)
         o << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, DC_STRUCT_MINB) dc_k_struct_" << names[mode] << "_" << c
           << "(DcStructArgs a) { dc_structured_kernel<" << c << ", " << mode << ">(a); }\n";
     }

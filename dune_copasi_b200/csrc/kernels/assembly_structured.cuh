@@ -13,7 +13,8 @@
 //    |m|! (d-1-|m|)! of the d! paths, so the cell's stiffness action is a sum over its
 //    d 2^(d-1) edges instead of d! simplices x d path edges.
 // Same weak form, quadrature points and weights as DcElem (requires point-independent diffusion
-// coefficients, which the host checks).  MODE 0: residual, 1: Jacobian apply, 2: block diagonal.
+// coefficients, which the host checks).  MODE 0: residual, 1: Jacobian apply, 2: block diagonal
+// (ns x ns per vertex, block-Jacobi), 3: scalar diagonal into a dof-indexed vector (Jacobi).
 #if DC_DIM == 2
 #define DC_NPERM 2
 #define DC_NCORN 4
@@ -204,8 +205,8 @@ __device__ __forceinline__ void dc_structured_kernel(const DcStructArgs& a) {
         for (int i = 0; i < NS; ++i)
 #pragma unroll
           for (int j = 0; j < NS; ++j)
-            if (M::pair(i, j))
-              acc[dc_corner(p, k)][i * NS + j] +=
+            if (M::pair(i, j) && (MODE == 2 || i == j))
+              acc[dc_corner(p, k)][MODE == 2 ? i * NS + j : i] +=
                   (DC_PB * DC_PB * JS[i][j] + (DC_PA * DC_PA - DC_PB * DC_PB) * JV[k][i][j]) * f;
     }
   }
@@ -238,6 +239,11 @@ __device__ __forceinline__ void dc_structured_kernel(const DcStructArgs& a) {
                 acc[m][i * NS + j] += wgt * jd[i][j];
                 acc[m2][i * NS + j] += wgt * jd[i][j];
               }
+          } else if (MODE == 3) {
+            if (M::pair(i, i)) {
+              acc[m][i] += wgt * jd[i][i];
+              acc[m2][i] += wgt * jd[i][i];
+            }
           } else {
             double d = 0.0;
 #pragma unroll
@@ -257,6 +263,9 @@ __device__ __forceinline__ void dc_structured_kernel(const DcStructArgs& a) {
     if (MODE == 2) {
 #pragma unroll
       for (int s = 0; s < NV; ++s) dc_atomic_add(&a.bdiag[dof[m] * NS + s], acc[m][s]);
+    } else if (MODE == 3) {   // scalar diagonal, vector layout
+#pragma unroll
+      for (int s = 0; s < NS; ++s) dc_atomic_add(&a.bdiag[dof[m] + s], acc[m][s]);
     } else {
 #pragma unroll
       for (int s = 0; s < NS; ++s) dc_atomic_add(&a.r[dof[m] + s], acc[m][s]);

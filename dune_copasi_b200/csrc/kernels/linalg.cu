@@ -320,6 +320,12 @@ __global__ void __launch_bounds__(kThreads) k_bdiag_dinv(int64_t dof0, int64_t n
   }
 }
 
+__global__ void __launch_bounds__(kThreads) k_invert_diag(int64_t n, double* __restrict__ d,
+                                                          const unsigned char* __restrict__ mask) {
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    d[i] = (mask && mask[i]) ? 1.0 : 1.0 / d[i];
+}
+
 // ---------------------------------------------------------------- Dirichlet / halo
 __global__ void k_set_values(int64_t n, const int32_t* idx, const double* vals, double* x) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -470,6 +476,10 @@ void block_jacobi_apply(int64_t dof0, int64_t nblocks, int bs, const double* bin
 void block_diag_to_dinv(int64_t dof0, int64_t nblocks, int bs, const double* bdiag, double* dinv, cudaStream_t s) {
   if (nblocks == 0) return;
   k_bdiag_dinv<<<grid_for(nblocks * bs), kThreads, 0, s>>>(dof0, nblocks * bs, bs, bdiag, dinv);
+  check_launch();
+}
+void invert_diag(int64_t n, double* d, const unsigned char* mask, cudaStream_t s) {
+  k_invert_diag<<<grid_for(n, 2), kThreads, 0, s>>>(n, d, mask);
   check_launch();
 }
 void set_values(int64_t n, const int32_t* idx, const double* vals, double* x, cudaStream_t s) {

@@ -75,6 +75,9 @@ void block_jacobi_apply(int64_t dof0, int64_t nblocks, int bs, const double* bin
 // scalar diagonal from the block diagonal: dinv[dof0 + b*bs + i] = 1 / bdiag[(dof0 + b*bs)*bs + i*bs + i]
 void block_diag_to_dinv(int64_t dof0, int64_t nblocks, int bs, const double* bdiag, double* dinv, cudaStream_t s);
 
+// d[i] = mask[i] ? 1 : 1/d[i]   (mask may be null)
+void invert_diag(int64_t n, double* d, const unsigned char* mask, cudaStream_t s);
+
 // Dirichlet handling
 void set_values(int64_t n, const int32_t* idx, const double* vals, double* x, cudaStream_t s);   // x[idx] = vals
 void zero_values(int64_t n, const int32_t* idx, double* x, cudaStream_t s);                      // x[idx] = 0

@@ -351,6 +351,7 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
   for (int c = 0; c < ncomp; ++c) {
     const int ns = model->comp_nspec[c];
     if (ns == 0 || comp_nelem_[c] == 0) continue;
+    if (mode == 4 && !(scheme == "structured" && c == struct_comp_)) continue;   // scalar diagonal: structured only
     if (scheme == "structured" && mode != 3 && c == struct_comp_) {
       DcStructArgs a{};
       a.ncells = 1;
@@ -362,10 +363,10 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       }
       a.dof_offset = (int)grid->comp_offset[c];
       a.time = t; a.wM = wM; a.wA = wA; a.x = x; a.z = z; a.r = r;
-      a.bdiag = bdiag ? bdiag + bdiag_shift(c) : nullptr;
+      a.bdiag = bdiag ? (mode == 4 ? bdiag : bdiag + bdiag_shift(c)) : nullptr;
       a.cmask = cmask.p;
-      static const char* sn[3] = {"dc_k_struct_residual_", "dc_k_struct_apply_", "dc_k_struct_bdiag_"};
-      static const char* sk[3] = {"struct_residual", "struct_apply", "struct_bdiag"};
+      static const char* sn[5] = {"dc_k_struct_residual_", "dc_k_struct_apply_", "dc_k_struct_bdiag_", "", "dc_k_struct_diag_"};
+      static const char* sk[5] = {"struct_residual", "struct_apply", "struct_bdiag", "", "struct_diag"};
       cudaKernel_t k = kernel(JitGroup::Structured, std::string(sn[mode]) + std::to_string(c));
       ProfScope ps(this, sk[mode]);
       const int sth = model->cfg.sub("model.assembly.b200").get("struct_threads", 64);
@@ -453,6 +454,12 @@ void DeviceOperator::jacobian_apply(double t, double wM, double wA, const double
 void DeviceOperator::block_diag(double t, double wM, double wA, const double* x, double* bdiag) {
   launch_volume("dc_k_bdiag_volume_", 2, t, wM, wA, x, nullptr, nullptr, nullptr, bdiag);
   if (wA != 0.0) launch_facets("dc_k_skeleton_bdiag_", t, wA, x, nullptr, nullptr, nullptr, bdiag);
+}
+
+bool DeviceOperator::scalar_diag(double t, double wM, double wA, const double* x, double* diag) {
+  if (scheme != "structured" || !facets_.empty() || model->ncomp() != 1) return false;
+  launch_volume("", 4, t, wM, wA, x, nullptr, nullptr, nullptr, diag);
+  return true;
 }
 
 void DeviceOperator::jacobian_csr(double t, double wM, double wA, const double* x, double* vals) {

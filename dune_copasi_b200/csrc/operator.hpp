@@ -51,6 +51,9 @@ class DeviceOperator {
   void jacobian_apply(double t, double wM, double wA, const double* x, const double* z, double* y);
   void jacobian_csr(double t, double wM, double wA, const double* x, double* vals);
   void block_diag(double t, double wM, double wA, const double* x, double* bdiag);
+  // scalar diagonal straight into a dof-indexed vector (structured scheme without facet terms);
+  // returns false when unsupported -- callers then derive it from block_diag
+  bool scalar_diag(double t, double wM, double wA, const double* x, double* diag);
 
   // sparsity pattern on the device (built on first use)
   void ensure_csr();

@@ -56,6 +56,10 @@ void LinearSolver::linearize(double t, double wM, double wA, const double* x) {
         la::csr_extract_block_diag(g.comp_offset[c], nb, bs, op_->rowptr.p, op_->colidx.p, vals.p, bdiag_.p + op_->bdiag_shift(c), s);
         op_->stats.launches++;
       }
+  } else if (prec_type == "Jacobi" && (dinv_.zero(s), op_->scalar_diag(t, wM, wA, x, dinv_.p))) {
+    // scalar diagonal assembled directly (no ns x ns blocks), then inverted in place
+    la::invert_diag(op_->ndofs, dinv_.p, op_->cmask.p, s);
+    op_->stats.launches++;
   } else if (prec_type != "Richardson") {
     bdiag_.zero(s);
     op_->block_diag(t, wM, wA, x, bdiag_.p);
