@@ -51,7 +51,8 @@ def ini_for(args):
     for kv in filter(None, getattr(args, "b200", "").split(",")):
         k, v = kv.split("=")
         over["model.assembly.b200." + k] = v
-    return K.CASES["grayscott3d"].ini_with(**over)
+    case = "cell3d" if getattr(args, "workload", "grayscott") == "cell" else "grayscott3d"
+    return K.CASES[case].ini_with(**over)
 
 
 def precompile():
@@ -64,10 +65,13 @@ def precompile():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  The
+    sampler runs from before the warm-up; begin()/end() bracket the timed region and only rows that
+    arrived inside it (or, for very short regions, the nearest ones) are summarised."""
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -75,28 +79,40 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc:
+            time.sleep(0.12)
             self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        rows = [(t, r) for t, r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        inside = [r for t, r in rows if self.t0 is not None and self.t0 <= t <= self.t1 + 0.06]
+        if not inside and rows and self.t0 is not None:
+            mid = 0.5 * (self.t0 + self.t1)
+            inside = [min(rows, key=lambda tr: abs(tr[0] - mid))[1]]
+        sm = [float(r[1]) for r in inside]
+        mx = [float(r[2]) for r in inside]
+        pw = [float(r[3]) for r in inside if r[3].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w": float(np.median(pw)) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def peaks():
@@ -104,6 +120,16 @@ def peaks():
     if os.path.exists(path):
         return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic(kernel, cells, world):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel
+    from the committed `ncu --set full` capture of this workload (profiles/ncu_traffic.json), or
+    None when that configuration has not been captured."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get(f"{kernel}@{cells}^3/n{world}")
 
 
 def cpu_baseline(args, steps, warmup, cells):
@@ -147,7 +173,8 @@ def run_reference(args):
 
 
 def config_dict(args, cells):
-    return {"workload": f"grayscott3d_p1_kuhn_{cells}^3", "cells": cells, "dt": args.dt, "rk": args.rk,
+    name = "cell3d_3comp_6species" if getattr(args, "workload", "grayscott") == "cell" else "grayscott3d"
+    return {"workload": f"{name}_p1_kuhn_{cells}^3", "cells": cells, "dt": args.dt, "rk": args.rk,
             "linear_solver": "BiCGSTAB", "preconditioner": args.prec, "matrix_free": bool(args.matrix_free),
             "linear_rel_tol": 1e-8, "newton_rel_tol": 1e-8, "assembly": args.scheme,
             "l2": "inputs larger than L2 (every vector and the mesh exceed 126 MB at the default size)"}
@@ -166,6 +193,9 @@ def main():
     ap.add_argument("--prec", default="Jacobi")
     ap.add_argument("--scheme", default="auto")
     ap.add_argument("--matrix-free", type=int, default=1)
+    ap.add_argument("--workload", default="grayscott", choices=["grayscott", "cell"],
+                    help="grayscott: BASELINE configs[3] (headline); cell: 3-compartment / 6-species cell model "
+                         "(configs[4] in miniature, general unstructured kernels)")
     ap.add_argument("--b200", default="", help="model.assembly.b200.* overrides, e.g. patch_elements=768,patch_min_blocks=4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -192,7 +222,6 @@ def main():
     t_setup = time.perf_counter()
     gglobal = D.Grid.structured(3, [args.cells] * 3)
     nv_global = gglobal.nv
-    ndofs_global = nv_global * 2
     grid = gglobal.partition(rank, world) if world > 1 else gglobal
     grid.bind(model)
     op = D.Operator(model, grid)
@@ -204,6 +233,10 @@ def main():
         dist.broadcast(uid, 0)
         comm = D.Comm(bytes(uid.cpu().tolist()), rank, world, op)
         del gglobal
+    owned = torch.tensor([sum(e - b for b, e in op.owned_ranges())], dtype=torch.int64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(owned)
+    ndofs_global = int(owned.item())
     st = D.Stepper(op, cfg, comm)
     u0 = grid.interpolate(model, 0.0)
     st.set_state(u0, 0.0)
@@ -241,14 +274,16 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(args.warmup):
-        assert st.step(args.dt)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        assert st.step(args.dt)
     s0 = st.stats()
     D.lib().dcb_operator_profile(op.h, 1)
+    sampler.begin()
     ms = timed(args.steps, False)
+    sampler.end()
     prof = op.profile()
     D.lib().dcb_operator_profile(op.h, 0)
     s1 = st.stats()
@@ -299,7 +334,8 @@ def main():
         avg_ms = prof[top]["ms"] / max(1, prof[top]["launches"])
         ach = alg.get(top, 0.0) / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches": prof[top]["launches"],
+                "traffic": measured_traffic(top, args.cells, world), "algorithmic_bytes": alg.get(top, 0.0),
+                "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches": prof[top]["launches"],
                 "share_of_step": prof[top]["ms"] / ms,
                 "breakdown_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}}
     cb = None

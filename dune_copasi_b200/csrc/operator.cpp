@@ -83,12 +83,9 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
   comp_vdof_.resize(ncomp);
   comp_nelem_.assign(ncomp, 0);
   for (int c = 0; c < ncomp; ++c) {
-    std::vector<int> ids;
-    for (int64_t e = 0; e < grid->ne; ++e)
-      if (grid->elem_comp[e] == c) ids.push_back((int)e);
-    comp_nelem_[c] = (int64_t)ids.size();
-    bool identity_elems = (int64_t)ids.size() == grid->ne;
-    if (!identity_elems) comp_elem_ids_[c].upload(ids, stream);
+    int64_t n = 0;
+    for (int64_t e = 0; e < grid->ne; ++e) n += grid->elem_comp[e] == c;
+    comp_nelem_[c] = n;
     // vertex -> dof map; skipped when it is the closed form offset + v*ns
     bool identity_dofs = (int64_t)grid->comp_vertices[c].size() == grid->nv;
     if (!identity_dofs) comp_vdof_[c].upload(grid->comp_vdof[c], stream);
@@ -126,6 +123,31 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
     cmask.upload(mask, stream);
   }
   if (scheme == "patch") build_patches();
+  DCB_CUDA(cudaStreamSynchronize(stream));
+}
+
+// element lists of the element-per-thread kernels, built on first use.  Default: the mesh's own
+// element order -- measured on B200 (128^3 Kuhn grid, apply kernel): mesh order 0.47 ms, Morton
+// order 0.74 ms, because consecutive lanes then gather consecutive vertices (coalesced) whereas
+// Morton order scatters the lanes of a warp.  model.assembly.b200.element_order = morton is kept
+// for meshes whose file order has no locality at all.
+void DeviceOperator::ensure_element_order() {
+  if (elem_order_ready_) return;
+  elem_order_ready_ = true;
+  const bool morton = model->cfg.sub("model.assembly.b200").get("element_order", std::string("natural")) == "morton";
+  for (int c = 0; c < model->ncomp(); ++c) {
+    if (model->comp_nspec[c] == 0 || comp_nelem_[c] == 0) continue;
+    std::vector<int> ids;
+    if (morton) {
+      auto order = morton_order(c);
+      ids.resize(order.size());
+      for (size_t t = 0; t < order.size(); ++t) ids[t] = order[t].second;
+    } else if (comp_nelem_[c] != grid->ne) {
+      for (int64_t e = 0; e < grid->ne; ++e)
+        if (grid->elem_comp[e] == c) ids.push_back((int)e);
+    }
+    if (!ids.empty()) comp_elem_ids_[c].upload(ids, stream);
+  }
   DCB_CUDA(cudaStreamSynchronize(stream));
 }
 
@@ -190,10 +212,11 @@ int64_t DeviceOperator::bdiag_shift(int c) const {
 }
 
 // ---------------------------------------------------------------------------------- patches
-void DeviceOperator::build_patches() {
-  const int nd = grid->nd(), dim = grid->dim, ncomp = model->ncomp();
+// elements of compartment c sorted along the Morton (Z-order) curve of their centroids: neighbours
+// in the list are neighbours in space, which is what keeps vertex data in L1/L2 between elements
+std::vector<std::pair<uint64_t, int32_t>> DeviceOperator::morton_order(int c) const {
+  const int nd = grid->nd(), dim = grid->dim;
   const int64_t ne = grid->ne;
-  // bounding box for the Morton keys
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
   for (int64_t v = 0; v < grid->nv; ++v)
     for (int k = 0; k < dim; ++k) {
@@ -201,6 +224,31 @@ void DeviceOperator::build_patches() {
       hi[k] = std::max(hi[k], grid->coords[v * dim + k]);
     }
   const double bits = dim == 3 ? 2097151.0 : 2147483647.0;
+  std::vector<std::pair<uint64_t, int32_t>> order;
+  order.reserve(comp_nelem_[c]);
+  for (int64_t e = 0; e < ne; ++e)
+    if (grid->elem_comp[e] == c) order.push_back({0, (int32_t)e});
+#pragma omp parallel for schedule(static)
+  for (int64_t t = 0; t < (int64_t)order.size(); ++t) {
+    int64_t e = order[t].second;
+    uint64_t q[3] = {0, 0, 0};
+    for (int k = 0; k < dim; ++k) {
+      double cen = 0;
+      for (int a = 0; a < nd; ++a) cen += grid->coords[(int64_t)grid->elems[e * nd + a] * dim + k];
+      cen /= nd;
+      double span = hi[k] - lo[k];
+      q[k] = (uint64_t)(span > 0 ? (cen - lo[k]) / span * bits : 0.0);
+    }
+    order[t].first = dim == 3 ? (spread3(q[0]) | spread3(q[1]) << 1 | spread3(q[2]) << 2)
+                              : (spread2(q[0]) | spread2(q[1]) << 1);
+  }
+  __gnu_parallel::sort(order.begin(), order.end());
+  return order;
+}
+
+void DeviceOperator::build_patches() {
+  const int nd = grid->nd(), dim = grid->dim, ncomp = model->ncomp();
+  const int64_t ne = grid->ne;
   patches_.resize(ncomp);
   std::vector<double> cell_sorted;
   const size_t nkeys = grid->cell_keys.size();
@@ -229,25 +277,7 @@ void DeviceOperator::build_patches() {
     }
     const int pe_max = P.max_elems, pn_max = P.max_nodes;
     // 1. Morton order of the element centroids
-    std::vector<std::pair<uint64_t, int32_t>> order;
-    order.reserve(comp_nelem_[c]);
-    for (int64_t e = 0; e < ne; ++e)
-      if (grid->elem_comp[e] == c) order.push_back({0, (int32_t)e});
-#pragma omp parallel for schedule(static)
-    for (int64_t t = 0; t < (int64_t)order.size(); ++t) {
-      int64_t e = order[t].second;
-      uint64_t q[3] = {0, 0, 0};
-      for (int k = 0; k < dim; ++k) {
-        double cen = 0;
-        for (int a = 0; a < nd; ++a) cen += grid->coords[(int64_t)grid->elems[e * nd + a] * dim + k];
-        cen /= nd;
-        double span = hi[k] - lo[k];
-        q[k] = (uint64_t)(span > 0 ? (cen - lo[k]) / span * bits : 0.0);
-      }
-      order[t].first = dim == 3 ? (spread3(q[0]) | spread3(q[1]) << 1 | spread3(q[2]) << 2)
-                                : (spread2(q[0]) | spread2(q[1]) << 1);
-    }
-    __gnu_parallel::sort(order.begin(), order.end());
+    std::vector<std::pair<uint64_t, int32_t>> order = morton_order(c);
     const int64_t n = (int64_t)order.size();
     // 2. greedy cuts under the vertex / element budgets
     std::vector<int> elem_ptr{0};
@@ -402,6 +432,7 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       ProfScope ps(this, pk[mode]);
       jit_launch(k, gridsz, patch_threads_, smem, stream, a);
     } else {
+      ensure_element_order();
       DcVolArgs a{};
       a.coords = coords_.p; a.elems = elems_.p; a.elem_ids = comp_elem_ids_[c].p; a.vdof = comp_vdof_[c].p;
       a.cell = cell_.p; a.ne_total = grid->ne; a.n = comp_nelem_[c];

@@ -105,6 +105,9 @@ class DeviceOperator {
   void launch_facets(const char* kind, double t, double wA, const double* x, const double* z,
                      double* r, double* vals, double* bdiag);
   void build_patches();
+  void ensure_element_order();
+  bool elem_order_ready_ = false;
+  std::vector<std::pair<uint64_t, int32_t>> morton_order(int c) const;
   cudaKernel_t kernel(JitGroup group, const std::string& name);
   std::map<int, std::unique_ptr<JitModule>> jit_;
   std::string jit_defines_;
