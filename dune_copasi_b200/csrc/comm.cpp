@@ -74,24 +74,31 @@ struct NcclCommunicator : Communicator {
     DCB_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclSum, comm, s));
     launches++;
   }
+  // contiguous index lists (slab partitions of structured grids: whole vertex planes) are sent
+  // and received in place, without pack / unpack kernels
+  std::vector<long long> send_off, recv_off;   // >= 0: contiguous range starting there
+
   void halo_update(double* x, cudaStream_t s) override {
     const size_t np = plan.peers.size();
     if (np == 0) return;
-    for (size_t k = 0; k < np; ++k) {
-      la::gather((int64_t)send_idx[k].n, send_idx[k].p, x, send_buf[k].p, s);
-      launches++;
-    }
+    for (size_t k = 0; k < np; ++k)
+      if (send_off[k] < 0 && send_idx[k].n) {
+        la::gather((int64_t)send_idx[k].n, send_idx[k].p, x, send_buf[k].p, s);
+        launches++;
+      }
     DCB_NCCL(nccl().GroupStart());
     for (size_t k = 0; k < np; ++k) {
-      if (send_buf[k].n) DCB_NCCL(nccl().Send(send_buf[k].p, send_buf[k].n, ncclFloat64, plan.peers[k], comm, s));
-      if (recv_buf[k].n) DCB_NCCL(nccl().Recv(recv_buf[k].p, recv_buf[k].n, ncclFloat64, plan.peers[k], comm, s));
+      const size_t ns = plan.send_idx[k].size(), nr = plan.recv_idx[k].size();
+      if (ns) DCB_NCCL(nccl().Send(send_off[k] >= 0 ? x + send_off[k] : send_buf[k].p, ns, ncclFloat64, plan.peers[k], comm, s));
+      if (nr) DCB_NCCL(nccl().Recv(recv_off[k] >= 0 ? x + recv_off[k] : recv_buf[k].p, nr, ncclFloat64, plan.peers[k], comm, s));
     }
     DCB_NCCL(nccl().GroupEnd());
     launches++;
-    for (size_t k = 0; k < np; ++k) {
-      la::scatter((int64_t)recv_idx[k].n, recv_idx[k].p, recv_buf[k].p, x, s);
-      launches++;
-    }
+    for (size_t k = 0; k < np; ++k)
+      if (recv_off[k] < 0 && recv_idx[k].n) {
+        la::scatter((int64_t)recv_idx[k].n, recv_idx[k].p, recv_buf[k].p, x, s);
+        launches++;
+      }
   }
 };
 
@@ -114,11 +121,23 @@ Communicator* nccl_communicator_create(const char unique_id[128], int rank, int 
   DCB_NCCL(nccl().CommInitRank(&c->comm, size, id, rank));
   const size_t np = plan.peers.size();
   c->send_idx.resize(np); c->recv_idx.resize(np); c->send_buf.resize(np); c->recv_buf.resize(np);
+  auto contiguous = [](const std::vector<int32_t>& idx) -> long long {
+    for (size_t i = 1; i < idx.size(); ++i)
+      if (idx[i] != idx[0] + (int32_t)i) return -1;
+    return idx.empty() ? -1 : idx[0];
+  };
+  c->send_off.resize(np); c->recv_off.resize(np);
   for (size_t k = 0; k < np; ++k) {
-    c->send_idx[k].upload(plan.send_idx[k]);
-    c->recv_idx[k].upload(plan.recv_idx[k]);
-    c->send_buf[k].alloc(plan.send_idx[k].size());
-    c->recv_buf[k].alloc(plan.recv_idx[k].size());
+    c->send_off[k] = contiguous(plan.send_idx[k]);
+    c->recv_off[k] = contiguous(plan.recv_idx[k]);
+    if (c->send_off[k] < 0) {
+      c->send_idx[k].upload(plan.send_idx[k]);
+      c->send_buf[k].alloc(plan.send_idx[k].size());
+    }
+    if (c->recv_off[k] < 0) {
+      c->recv_idx[k].upload(plan.recv_idx[k]);
+      c->recv_buf[k].alloc(plan.recv_idx[k].size());
+    }
   }
   DCB_CUDA(cudaDeviceSynchronize());
   return c;

@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(kThreads) k_bicg_p_prec(int64_t n, double* __r
   }
 }
 // r -= alpha v ; out[0] = <r,r> ; y2 = relax * dinv * r
-__global__ void __launch_bounds__(kThreads) k_bicg_r_prec(int64_t n, Ranges own, double alpha,
+__global__ void __launch_bounds__(kThreads) k_bicg_r_prec(int64_t n, Ranges own, double rho_new,
+                                                          const double* __restrict__ hptr,
                                                           const double* __restrict__ v,
                                                           double* __restrict__ r,
                                                           const double* __restrict__ dinv, double relax,
@@ -191,6 +192,7 @@ __global__ void __launch_bounds__(kThreads) k_bicg_r_prec(int64_t n, Ranges own,
                                                           unsigned* counter, double* out) {
   double acc[1] = {0.0};
   const bool single = own.n == 1 && own.b[0] == 0 && own.e[0] == n;
+  const double alpha = rho_new / *hptr;   // alpha = rho'/<rt,v> from the device-resident reduction
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
     const double ri = r[i] - alpha * v[i];
     r[i] = ri;
@@ -200,8 +202,10 @@ __global__ void __launch_bounds__(kThreads) k_bicg_r_prec(int64_t n, Ranges own,
   grid_reduce<1>(acc, partials, counter, out);
 }
 // x += alpha y1 + omega y2 ; r -= omega t ; out[0] = <r,r> ; out[1] = <rt,r>
-__global__ void __launch_bounds__(kThreads) k_bicg_final(int64_t n, Ranges own, double alpha,
-                                                         const double* __restrict__ y1, double omega,
+__global__ void __launch_bounds__(kThreads) k_bicg_final(int64_t n, Ranges own, double rho_new,
+                                                         const double* __restrict__ hptr,
+                                                         const double* __restrict__ trtt,
+                                                         const double* __restrict__ y1,
                                                          const double* __restrict__ y2,
                                                          double* __restrict__ x,
                                                          const double* __restrict__ t,
@@ -210,6 +214,7 @@ __global__ void __launch_bounds__(kThreads) k_bicg_final(int64_t n, Ranges own, 
                                                          unsigned* counter, double* out) {
   double acc[2] = {0.0, 0.0};
   const bool single = own.n == 1 && own.b[0] == 0 && own.e[0] == n;
+  const double alpha = rho_new / *hptr, omega = trtt[0] / trtt[1];
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
     x[i] = (x[i] + alpha * y1[i]) + omega * y2[i];
     const double ri = r[i] - omega * t[i];
@@ -419,15 +424,15 @@ void bicg_p_prec(int64_t n, double* p, const double* r, const double* v, double 
   k_bicg_p_prec<<<grid_for(n, 2), kThreads, 0, s>>>(n, p, r, v, beta, omega, first, dinv, relax, y);
   check_launch();
 }
-void bicg_r_prec(int64_t n, const Ranges& own, double alpha, const double* v, double* r, const double* dinv,
-                 double relax, double* y2, double* out, const ReduceWorkspace& w, cudaStream_t s) {
-  k_bicg_r_prec<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, alpha, v, r, dinv, relax, y2, w.partials, w.counter, out);
+void bicg_r_prec(int64_t n, const Ranges& own, double rho_new, const double* hptr, const double* v, double* r,
+                 const double* dinv, double relax, double* y2, double* out, const ReduceWorkspace& w, cudaStream_t s) {
+  k_bicg_r_prec<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, rho_new, hptr, v, r, dinv, relax, y2, w.partials, w.counter, out);
   check_launch();
 }
-void bicg_final(int64_t n, const Ranges& own, double alpha, const double* y1, double omega, const double* y2,
-                double* x, const double* t, double* r, const double* rt, double* out, const ReduceWorkspace& w,
-                cudaStream_t s) {
-  k_bicg_final<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, alpha, y1, omega, y2, x, t, r, rt, w.partials, w.counter, out);
+void bicg_final(int64_t n, const Ranges& own, double rho_new, const double* hptr, const double* trtt, const double* y1,
+                const double* y2, double* x, const double* t, double* r, const double* rt, double* out,
+                const ReduceWorkspace& w, cudaStream_t s) {
+  k_bicg_final<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, rho_new, hptr, trtt, y1, y2, x, t, r, rt, w.partials, w.counter, out);
   check_launch();
 }
 void xpby(int64_t n, double* p, const double* q, double beta, cudaStream_t s) {

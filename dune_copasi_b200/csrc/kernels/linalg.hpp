@@ -46,13 +46,15 @@ void axpy_pair_norm(int64_t n, const Ranges& own, double alpha, const double* y,
 // p = r + beta (p - omega v) ; y = relax dinv p
 void bicg_p_prec(int64_t n, double* p, const double* r, const double* v, double beta, double omega, bool first,
                  const double* dinv, double relax, double* y, cudaStream_t s);
+// The step lengths are formed on the device from the (all-reduced) device-resident sums, so the
+// host does not have to wait for them: alpha = rho_new / *hptr, omega = trtt[0] / trtt[1].
 // r -= alpha v ; out[0] = <r,r> ; y2 = relax dinv r
-void bicg_r_prec(int64_t n, const Ranges& own, double alpha, const double* v, double* r, const double* dinv,
-                 double relax, double* y2, double* out, const ReduceWorkspace& w, cudaStream_t s);
+void bicg_r_prec(int64_t n, const Ranges& own, double rho_new, const double* hptr, const double* v, double* r,
+                 const double* dinv, double relax, double* y2, double* out, const ReduceWorkspace& w, cudaStream_t s);
 // x += alpha y1 + omega y2 ; r -= omega t ; out[0] = <r,r> ; out[1] = <rt,r>
-void bicg_final(int64_t n, const Ranges& own, double alpha, const double* y1, double omega, const double* y2,
-                double* x, const double* t, double* r, const double* rt, double* out, const ReduceWorkspace& w,
-                cudaStream_t s);
+void bicg_final(int64_t n, const Ranges& own, double rho_new, const double* hptr, const double* trtt, const double* y1,
+                const double* y2, double* x, const double* t, double* r, const double* rt, double* out,
+                const ReduceWorkspace& w, cudaStream_t s);
 // CG: p = q + beta p
 void xpby(int64_t n, double* p, const double* q, double beta, cudaStream_t s);
 // y += a x

@@ -120,6 +120,14 @@ void LinearSolver::precondition(const double* d, double* v) {
   op_->stats.launches++;
 }
 
+// all-reduce scal_[first, first+count) and bring scal_[0, total) to the host
+void LinearSolver::fetch_slots(int first, int count, int total) {
+  cudaStream_t s = op_->stream;
+  if (comm_) comm_->allreduce_sum(scal_.p + first, count, s);
+  DCB_CUDA(cudaMemcpyAsync(hscal_.p, scal_.p, sizeof(double) * total, cudaMemcpyDeviceToHost, s));
+  DCB_CUDA(cudaStreamSynchronize(s));
+}
+
 void LinearSolver::fetch(int n) {
   cudaStream_t s = op_->stream;
   if (comm_) comm_->allreduce_sum(scal_.p, n, s);
@@ -158,27 +166,27 @@ SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
       { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::bicg_p_prec(n, p, r, v, beta, omega, it < 1, fold, relaxation, y, s); L++; }
       if (!fold) precondition(p, y);
       apply_operator(y, v);
-      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, rt, v, scal_.p, ws_, s); L++; }
-      fetch(1);
-      double h = hscal_.p[0];
-      if (std::fabs(h) < 1e-80) break;
-      alpha = rho_new / h;
-      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::bicg_r_prec(n, own, alpha, v, r, fold, relaxation, y2, scal_.p, ws_, s); L++; }
+      // <rt,v> stays on the device (slot 2); alpha is formed inside the next sweep
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, rt, v, scal_.p + 2, ws_, s); L++; }
+      if (comm_) comm_->allreduce_sum(scal_.p + 2, 1, s);
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::bicg_r_prec(n, own, rho_new, scal_.p + 2, v, r, fold, relaxation, y2, scal_.p, ws_, s); L++; }
       pending = true;
-      fetch(1);
+      fetch_slots(0, 1, 4);          // all-reduce the norm, read norm and <rt,v> back
+      double h = hscal_.p[2];
+      alpha = rho_new / h;
       norm = std::sqrt(hscal_.p[0]);
       res.half_iterations++;
-      if (!(norm == norm)) break;
+      if (std::fabs(h) < 1e-80 || !(norm == norm)) break;
       if (norm < rel_tol * norm0 || norm < 1e-30) { res.converged = true; break; }
       it += 0.5;
       if (!fold) precondition(r, y2);
       apply_operator(y2, t);
-      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot2(own, t, r, t, t, scal_.p, ws_, s); L++; }
-      fetch(2);
-      omega = hscal_.p[0] / hscal_.p[1];
-      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::bicg_final(n, own, alpha, y, omega, y2, x, t, r, rt, scal_.p, ws_, s); L++; }
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot2(own, t, r, t, t, scal_.p + 4, ws_, s); L++; }
+      if (comm_) comm_->allreduce_sum(scal_.p + 4, 2, s);
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::bicg_final(n, own, rho_new, scal_.p + 2, scal_.p + 4, y, y2, x, t, r, rt, scal_.p, ws_, s); L++; }
       pending = false;
-      fetch(2);
+      fetch_slots(0, 2, 6);
+      omega = hscal_.p[4] / hscal_.p[5];
       rho = rho_new;
       rho_new = hscal_.p[1];
       norm = std::sqrt(hscal_.p[0]);

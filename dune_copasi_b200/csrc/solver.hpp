@@ -50,6 +50,7 @@ class LinearSolver {
   void precondition(const double* d, double* v);
   double reduce1(double* dev2);             // host value of scal_[0] after a reduction
   void fetch(int n);
+  void fetch_slots(int first, int count, int total);
   std::shared_ptr<DeviceOperator> op_;
   Communicator* comm_;
   la::ReduceWorkspace ws_;
