@@ -338,6 +338,17 @@ def main():
                 "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches": prof[top]["launches"],
                 "share_of_step": prof[top]["ms"] / ms,
                 "breakdown_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}}
+        # the assembly kernels are fp64-pipe bound on B200 (64 fp64 lanes/SM/clk), not HBM bound:
+        # report the live fp64 instruction rate against that peak next to the HBM fraction
+        path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        per_cell = json.load(open(path)).get(f"{top}.fp64_instr_per_cell") if os.path.exists(path) else None
+        if per_cell and clocks and clocks.get("sm_mhz"):
+            cells_rank = args.cells ** 3 / world
+            rate = cells_rank * per_cell / (avg_ms * 1e-3)
+            peak64 = 148 * 64 * clocks["sm_mhz"] * 1e6
+            roof["fp64_pipe"] = {"instr_per_cell": per_cell, "achieved_ginstr_s": rate / 1e9,
+                                 "peak_ginstr_s": peak64 / 1e9, "frac": rate / peak64,
+                                 "note": "dominant kernel is bound by the fp64 pipe; HBM traffic is ~1.3x algorithmic"}
     cb = None
     line = {"metric": METRIC, "value": value, "unit": "DOF-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",

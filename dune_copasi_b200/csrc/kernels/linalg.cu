@@ -325,6 +325,29 @@ __global__ void __launch_bounds__(kThreads) k_bdiag_dinv(int64_t dof0, int64_t n
   }
 }
 
+__global__ void __launch_bounds__(kThreads) k_axpy_dev(int64_t n, const double* __restrict__ coef, double sign,
+                                                       const double* __restrict__ x, double* __restrict__ y) {
+  const double a = sign * *coef;
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    y[i] += a * x[i];
+}
+__global__ void __launch_bounds__(kThreads) k_normalize_dev(int64_t n, const double* __restrict__ src,
+                                                            const double* __restrict__ norm2,
+                                                            double* __restrict__ dst) {
+  const double a = 1.0 / sqrt(*norm2);
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    dst[i] = src[i] * a;
+}
+__global__ void __launch_bounds__(kThreads) k_scale(int64_t n, double a, double* __restrict__ x) {
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    x[i] *= a;
+}
+__global__ void __launch_bounds__(kThreads) k_sub(int64_t n, const double* __restrict__ a,
+                                                  const double* __restrict__ b, double* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    y[i] = a[i] - b[i];
+}
+
 __global__ void __launch_bounds__(kThreads) k_invert_diag(int64_t n, double* __restrict__ d,
                                                           const unsigned char* __restrict__ mask) {
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
@@ -481,6 +504,22 @@ void block_jacobi_apply(int64_t dof0, int64_t nblocks, int bs, const double* bin
 void block_diag_to_dinv(int64_t dof0, int64_t nblocks, int bs, const double* bdiag, double* dinv, cudaStream_t s) {
   if (nblocks == 0) return;
   k_bdiag_dinv<<<grid_for(nblocks * bs), kThreads, 0, s>>>(dof0, nblocks * bs, bs, bdiag, dinv);
+  check_launch();
+}
+void axpy_dev(int64_t n, const double* coef, double sign, const double* x, double* y, cudaStream_t s) {
+  k_axpy_dev<<<grid_for(n, 2), kThreads, 0, s>>>(n, coef, sign, x, y);
+  check_launch();
+}
+void normalize_dev(int64_t n, const double* src, const double* norm2, double* dst, cudaStream_t s) {
+  k_normalize_dev<<<grid_for(n, 2), kThreads, 0, s>>>(n, src, norm2, dst);
+  check_launch();
+}
+void scale(int64_t n, double a, double* x, cudaStream_t s) {
+  k_scale<<<grid_for(n, 2), kThreads, 0, s>>>(n, a, x);
+  check_launch();
+}
+void sub(int64_t n, const double* a, const double* b, double* y, cudaStream_t s) {
+  k_sub<<<grid_for(n, 2), kThreads, 0, s>>>(n, a, b, y);
   check_launch();
 }
 void invert_diag(int64_t n, double* d, const unsigned char* mask, cudaStream_t s) {

@@ -55,6 +55,15 @@ void bicg_r_prec(int64_t n, const Ranges& own, double rho_new, const double* hpt
 void bicg_final(int64_t n, const Ranges& own, double rho_new, const double* hptr, const double* trtt, const double* y1,
                 const double* y2, double* x, const double* t, double* r, const double* rt, double* out,
                 const ReduceWorkspace& w, cudaStream_t s);
+// GMRES (modified Gram-Schmidt) with device-resident coefficients:
+// y += sign * (*coef) * x
+void axpy_dev(int64_t n, const double* coef, double sign, const double* x, double* y, cudaStream_t s);
+// dst = src / sqrt(*norm2)
+void normalize_dev(int64_t n, const double* src, const double* norm2, double* dst, cudaStream_t s);
+// x *= a
+void scale(int64_t n, double a, double* x, cudaStream_t s);
+// y = a - b
+void sub(int64_t n, const double* a, const double* b, double* y, cudaStream_t s);
 // CG: p = q + beta p
 void xpby(int64_t n, double* p, const double* q, double beta, cudaStream_t s);
 // y += a x

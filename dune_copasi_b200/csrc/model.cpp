@@ -17,6 +17,13 @@ Model::Model(const PTree& cfg_, int dim_, const std::vector<std::string>& keys)
   const PTree& mcfg = cfg.sub("model");
   is_linear = mcfg.get("is_linear", false);
   if (mcfg.get("order", 1) != 1) fail("model.order = ", mcfg.get("order", 1), ": only P1 is built");
+  {
+    std::string jt = mcfg.get("jacobian.type", std::string("analytical"));
+    if (jt != "analytical" && jt != "numerical")
+      fail("The option 'model.jacobian.type' must be either 'analytical' or 'numerical'");
+    numerical_jacobian = jt == "numerical" && !is_linear;
+    fd_epsilon = mcfg.get("jacobian.epsilon", 1e-7);
+  }
   const PTree& comps = cfg.sub("compartments");
   for (auto& name : comps.sub_keys()) {
     const PTree& c = comps.sub(name);
@@ -102,6 +109,8 @@ Model::Model(const PTree& cfg_, int dim_, const std::vector<std::string>& keys)
         }
     }
   }
+  if (numerical_jacobian && has_outflow())
+    fail("model.jacobian.type = numerical with outflow terms (local_operator.hh:1205-1343) is not built");
 }
 
 int Model::species_index(const std::string& name) const {
@@ -225,6 +234,11 @@ std::string Model::cuda_source() const {
   std::ostringstream o;
   o << "// generated by dune_copasi_b200 Model::cuda_source()\n";
   o << "#define DC_DIM " << dim << "\n#define DC_NKEYS " << cell_keys.size() << "\n#define DC_NCOMP " << ncomp() << "\n";
+  {
+    char eps[64];
+    snprintf(eps, sizeof eps, "%.17g", fd_epsilon);
+    o << "#define DC_NUMJAC " << (numerical_jacobian ? 1 : 0) << "\n#define DC_FD_EPS " << eps << "\n";
+  }
   o << "struct DcCtx { double time, entity_volume, integration_factor, in_volume, in_boundary, in_skeleton;"
        " double pos[3]; double nrm[3]; double cell[" << std::max<size_t>(1, cell_keys.size()) << "]; };\n";
   o << "template <int N> __device__ __forceinline__ double dc_powi(double x) { double r = x;\n"

@@ -35,6 +35,10 @@ class Model {
 
   int dim;
   bool is_linear = false;
+  // model.jacobian.type = numerical: finite differences with model.jacobian.epsilon
+  // (local_operator.hh:193-202, 713-765); linear operators always use the analytic path (:234-235)
+  bool numerical_jacobian = false;
+  double fd_epsilon = 1e-7;
   std::vector<std::string> cell_keys;
   std::vector<std::string> comp_names;
   std::vector<NodeP> comp_expr;

@@ -382,7 +382,9 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
     const int ns = model->comp_nspec[c];
     if (ns == 0 || comp_nelem_[c] == 0) continue;
     if (mode == 4 && !(scheme == "structured" && c == struct_comp_)) continue;   // scalar diagonal: structured only
-    if (scheme == "structured" && mode != 3 && c == struct_comp_) {
+    // finite-difference Jacobians (model.jacobian.type = numerical) live in the element kernels
+    const bool fd = model->numerical_jacobian && mode != 0;
+    if (scheme == "structured" && mode != 3 && c == struct_comp_ && !fd) {
       DcStructArgs a{};
       a.ncells = 1;
       for (int k = 0; k < 3; ++k) {
@@ -405,7 +407,7 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       continue;
     }
     // the block-diagonal buffer grows with ns^2: fall back to the element kernel when it cannot be staged
-    const bool patch_here = use_patch && patch_smem(patches_[c], ns, mode) <= 200 * 1024;
+    const bool patch_here = use_patch && !fd && patch_smem(patches_[c], ns, mode) <= 200 * 1024;
     if (patch_here) {
       const PatchSet& P = patches_[c];
       DcPatchArgs a{};
@@ -488,7 +490,7 @@ void DeviceOperator::block_diag(double t, double wM, double wA, const double* x,
 }
 
 bool DeviceOperator::scalar_diag(double t, double wM, double wA, const double* x, double* diag) {
-  if (scheme != "structured" || !facets_.empty() || model->ncomp() != 1) return false;
+  if (scheme != "structured" || !facets_.empty() || model->ncomp() != 1 || model->numerical_jacobian) return false;
   launch_volume("", 4, t, wM, wA, x, nullptr, nullptr, nullptr, diag);
   return true;
 }

@@ -1,6 +1,8 @@
 #include "solver.hpp"
 
+#include <algorithm>
 #include <cmath>
+#include <vector>
 
 #include "comm.hpp"
 
@@ -11,8 +13,10 @@ LinearSolver::LinearSolver(std::shared_ptr<DeviceOperator> op, const PTree& cfg,
   // defaults: the reference picks UMFPack (direct) when SuiteSparse exists, else BiCGSTAB
   // (factory/inverse.hh:11-15); the direct solvers are not data parallel and not built here.
   type = cfg.get("type", std::string("BiCGSTAB"));
-  if (type != "BiCGSTAB" && type != "CG")
-    fail("linear_solver.type = '", type, "' is not built for the B200 path (available: BiCGSTAB, CG)");
+  if (type != "BiCGSTAB" && type != "CG" && type != "RestartedGMRes")
+    fail("linear_solver.type = '", type, "' is not built for the B200 path (available: BiCGSTAB, CG, RestartedGMRes)");
+  restart = cfg.get("restart", 40);   // iterative.hh:64
+  if (type == "RestartedGMRes" && (restart < 1 || restart > 500)) fail("linear_solver.restart = ", restart, " is out of range [1, 500]");
   prec_type = cfg.get("preconditioner.type", std::string("Jacobi"));
   if (prec_type != "Jacobi" && prec_type != "BlockJacobi" && prec_type != "Richardson")
     fail("linear_solver.preconditioner.type = '", prec_type,
@@ -25,9 +29,12 @@ LinearSolver::LinearSolver(std::shared_ptr<DeviceOperator> op, const PTree& cfg,
   auto range = cfg.get_vec("convergence_condition.iteration_range", {1, 500});   // iterative.hh:53-54
   max_iterations = (int)range.back();
   la::reduce_workspace_create(&ws_);
-  scal_.alloc(8);
-  hscal_.alloc(8);
-  for (auto& w : work_) w.alloc(op_->ndofs);
+  const bool gmres = type == "RestartedGMRes";
+  scal_.alloc(gmres ? std::max(8, restart + 2) : 8);
+  hscal_.alloc(gmres ? std::max(8, restart + 2) : 8);
+  const int nwork = type == "BiCGSTAB" ? 6 : 2;
+  for (int k = 0; k < nwork; ++k) work_[k].alloc(op_->ndofs);
+  if (gmres) basis_.alloc((int64_t)(restart + 1) * op_->ndofs);   // Krylov basis v_0 .. v_m
   if (!matrix_free) {
     op_->ensure_csr();
     vals.alloc(op_->nnz());
@@ -196,6 +203,89 @@ SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
     }
     if (pending) { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::axpy(n, alpha, y, x, s); L++; }
     res.iterations = (int)std::ceil(std::min<double>(it, max_iterations));
+    res.reduction = norm / norm0;
+  } else if (type == "RestartedGMRes") {
+    // dune-istl RestartedGMResSolver: left preconditioned GMRES(m), modified Gram-Schmidt, Givens
+    // rotations on the host; convergence on the preconditioned defect.  The Gram-Schmidt
+    // coefficients stay on the device (slot k = <v_k,w>, slot i+1 = <w,w>) and are read back once
+    // per iteration for the Hessenberg column.
+    const int m = restart;
+    auto V = [&](int k) { return basis_.p + (int64_t)k * n; };
+    double *w = work_[0].p, *tmp = work_[1].p;
+    std::vector<double> H((size_t)(m + 1) * m, 0.0), sv(m + 1, 0.0), cs(m, 0.0), sn(m, 0.0), yv(m, 0.0);
+    auto Hh = [&](int rr, int cc) -> double& { return H[(size_t)rr * m + cc]; };
+    auto givens_apply = [](double& dx, double& dy, double c, double sgn) {
+      double tt = c * dx + sgn * dy;
+      dy = -sgn * dx + c * dy;
+      dx = tt;
+    };
+    precondition(b, V(0));
+    { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, V(0), V(0), scal_.p, ws_, s); L++; }
+    fetch(1);
+    double norm0 = std::sqrt(hscal_.p[0]), norm = norm0;
+    res.defect0 = norm0;
+    if (!(norm0 == norm0)) { res.converged = false; return res; }
+    if (norm0 < 1e-30) { res.converged = true; res.reduction = 0; return res; }
+    int j = 1;
+    while (j <= max_iterations && !res.converged) {
+      int i = 0;
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::scale(n, 1.0 / norm, V(0), s); L++; }
+      sv[0] = norm;
+      for (int k = 1; k < m + 1; ++k) sv[k] = 0.0;
+      for (i = 0; i < m && j <= max_iterations && !res.converged; ++i, ++j) {
+        apply_operator(V(i), V(i + 1));
+        precondition(V(i + 1), w);
+        for (int k = 0; k < i + 1; ++k) {
+          DeviceOperator::ProfScope ps(op_.get(), "blas1");
+          la::dot(own, V(k), w, scal_.p + k, ws_, s);
+          if (comm_) comm_->allreduce_sum(scal_.p + k, 1, s);
+          la::axpy_dev(n, scal_.p + k, -1.0, V(k), w, s);
+          L += 2;
+        }
+        {
+          DeviceOperator::ProfScope ps(op_.get(), "blas1");
+          la::dot(own, w, w, scal_.p + i + 1, ws_, s);
+          if (comm_) comm_->allreduce_sum(scal_.p + i + 1, 1, s);
+          la::normalize_dev(n, w, scal_.p + i + 1, V(i + 1), s);
+          L += 2;
+        }
+        DCB_CUDA(cudaMemcpyAsync(hscal_.p, scal_.p, sizeof(double) * (i + 2), cudaMemcpyDeviceToHost, s));
+        DCB_CUDA(cudaStreamSynchronize(s));
+        for (int k = 0; k < i + 1; ++k) Hh(k, i) = hscal_.p[k];
+        double hn = std::sqrt(hscal_.p[i + 1]);
+        Hh(i + 1, i) = hn;
+        res.half_iterations += 2;
+        if (!(hn == hn) || std::fabs(hn) < 1e-80) { j = max_iterations + 1; break; }   // breakdown (SolverAbort)
+        for (int k = 0; k < i; ++k) givens_apply(Hh(k, i), Hh(k + 1, i), cs[k], sn[k]);
+        {
+          double dx = Hh(i, i), dy = Hh(i + 1, i);
+          if (std::fabs(dy) < 1e-300) { cs[i] = 1.0; sn[i] = 0.0; }
+          else if (std::fabs(dx) < 1e-300) { cs[i] = 0.0; sn[i] = 1.0; }
+          else { double nrm = std::sqrt(dx * dx + dy * dy); cs[i] = dx / nrm; sn[i] = dy / nrm; }
+        }
+        givens_apply(Hh(i, i), Hh(i + 1, i), cs[i], sn[i]);
+        givens_apply(sv[i], sv[i + 1], cs[i], sn[i]);
+        norm = std::fabs(sv[i + 1]);
+        if (norm < rel_tol * norm0 || norm < 1e-30) res.converged = true;
+      }
+      // x += sum_k y_k v_k with H y = s (upper triangular after the rotations)
+      for (int a = i - 1; a >= 0; --a) {
+        double acc = sv[a];
+        for (int c2 = a + 1; c2 < i; ++c2) acc -= Hh(a, c2) * yv[c2];
+        yv[a] = acc / Hh(a, a);
+      }
+      for (int a = 0; a < i; ++a) { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::axpy(n, yv[a], V(a), x, s); L++; }
+      if (!res.converged && j < max_iterations) {
+        // restart from the true preconditioned defect
+        apply_operator(x, tmp);
+        { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::sub(n, b, tmp, w, s); L++; }
+        precondition(w, V(0));
+        { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, V(0), V(0), scal_.p, ws_, s); L++; }
+        fetch(1);
+        norm = std::sqrt(hscal_.p[0]);
+      }
+    }
+    res.iterations = j - 1;
     res.reduction = norm / norm0;
   } else {   // CG
     double *p = work_[0].p, *q = work_[1].p;

@@ -1,12 +1,13 @@
-// Krylov solve on the device: hand-written BiCGSTAB and CG in dune-istl's operation order with
-// Jacobi / block-Jacobi / Richardson preconditioning, on an assembled CSR Jacobian or matrix-free.
+// Krylov solve on the device: hand-written BiCGSTAB, CG and restarted GMRES in dune-istl's operation
+// order with Jacobi / block-Jacobi / Richardson preconditioning, on an assembled CSR Jacobian or
+// matrix-free.
 //
 // Mirrors the reference's LinearSolver adapter (dune/copasi/model/make_step_operator.hh:55-157):
 // configuration sub-tree `linear_solver.*`, solver + preconditioner (re)built on every apply
 // (:120-127), relative tolerance handed in per call (:132-135), non-convergence reported as an
 // error condition (:141-145).  Registry names follow solver/istl/factory/iterative.hh:87-106 and
-// factory/preconditioner.hh:96-113; only the data-parallel subset is built (BiCGSTAB, CG;
-// Richardson, Jacobi, BlockJacobi), anything else fails loudly.
+// factory/preconditioner.hh:96-113; only the data-parallel subset is built (BiCGSTAB, CG,
+// RestartedGMRes; Richardson, Jacobi, BlockJacobi), anything else fails loudly.
 #pragma once
 #include <memory>
 #include <string>
@@ -42,6 +43,7 @@ class LinearSolver {
   bool matrix_free = false;
   std::string type, prec_type;
   int max_iterations = 500;
+  int restart = 40;              // RestartedGMRes: Krylov space dimension between restarts
   double relaxation = 1.0;
   int verbosity = 0;
   DeviceBuffer<double> vals;     // CSR values of the current linearisation (matrix based)
@@ -56,7 +58,7 @@ class LinearSolver {
   la::ReduceWorkspace ws_;
   DeviceBuffer<double> scal_;               // device scalars of the reductions
   PinnedBuffer<double> hscal_;
-  DeviceBuffer<double> dinv_, bdiag_, work_[6];
+  DeviceBuffer<double> dinv_, bdiag_, work_[6], basis_;
   // linearisation point
   double t_ = 0, wM_ = 0, wA_ = 0;
   const double* x_ = nullptr;

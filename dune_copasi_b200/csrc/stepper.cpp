@@ -18,8 +18,33 @@ StepOperator::StepOperator(std::shared_ptr<DeviceOperator> o, const PTree& cfg, 
     a_ = {{-1.0, 1.0, 0.0}, {-1.0, 0.0, 1.0}};
     b_ = {{0.0, al, 0.0}, {0.0, 1.0 - al, al}};
     d_ = {0.0, al, 1.0};
+  } else if (rk_type == "ExplicitEuler") {
+    a_ = {{-1.0, 1.0}};
+    b_ = {{1.0, 0.0}};
+    d_ = {0.0, 1.0};
+  } else if (rk_type == "Heun") {
+    a_ = {{-1.0, 1.0, 0.0}, {-0.5, -0.5, 1.0}};
+    b_ = {{1.0, 0.0, 0.0}, {0.0, 0.5, 0.0}};
+    d_ = {0.0, 1.0, 1.0};
+  } else if (rk_type == "Shu3") {
+    a_ = {{-1.0, 1.0, 0.0, 0.0}, {-0.75, -0.25, 1.0, 0.0}, {-1.0 / 3.0, 0.0, -2.0 / 3.0, 1.0}};
+    b_ = {{1.0, 0.0, 0.0, 0.0}, {0.0, 0.25, 0.0, 0.0}, {0.0, 0.0, 2.0 / 3.0, 0.0}};
+    d_ = {0.0, 1.0, 0.5, 1.0};
+  } else if (rk_type == "RungeKutta4") {
+    a_ = {{-1.0, 1.0, 0.0, 0.0, 0.0}, {-1.0, 0.0, 1.0, 0.0, 0.0}, {-1.0, 0.0, 0.0, 1.0, 0.0}, {-1.0, 0.0, 0.0, 0.0, 1.0}};
+    b_ = {{0.5, 0.0, 0.0, 0.0, 0.0}, {0.0, 0.5, 0.0, 0.0, 0.0}, {0.0, 0.0, 1.0, 0.0, 0.0},
+          {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0, 0.0}};
+    d_ = {0.0, 0.5, 0.5, 1.0, 1.0};
+  } else if (rk_type == "Alexander3") {
+    const double al = 0.4358665215;
+    const double b1 = -(6.0 * al * al - 16.0 * al + 1.0) / 4.0, b2 = (6.0 * al * al - 20.0 * al + 5.0) / 4.0;
+    a_ = {{-1.0, 1.0, 0.0, 0.0}, {-1.0, 0.0, 1.0, 0.0}, {-1.0, 0.0, 0.0, 1.0}};
+    b_ = {{0.0, al, 0.0, 0.0}, {0.0, (1.0 - al) / 2.0, al, 0.0}, {0.0, b1, b2, al}};
+    d_ = {0.0, al, (1.0 + al) / 2.0, 1.0};
   } else {
-    fail("time_step_operator.type = '", rk_type, "' is not built (available: ImplicitEuler, Alexander2)");
+    // FractionalStepTheta of make_step_operator.hh:434-435 is the one table not restated
+    fail("time_step_operator.type = '", rk_type,
+         "' is not built (available: ExplicitEuler, ImplicitEuler, Heun, Shu3, RungeKutta4, Alexander2, Alexander3)");
   }
   is_linear = op->model->is_linear;
   const PTree& ls = cfg.sub("linear_solver");

@@ -107,6 +107,9 @@ class Model:
         self.ncomp, self.nspec = len(self.comp_names), len(self.species)
         self.comp_nspec = [sum(1 for s in self.species if s.comp == c) for c in range(self.ncomp)]
         self.is_linear = str(mcfg.get("is_linear", "false")).lower() in ("true", "1", "yes")
+        # local_operator.hh:193-202, 234-235: numerical (FD) Jacobian unless the operator is linear
+        self.numerical = INI.get(mcfg, "jacobian.type", "analytical") == "numerical" and not self.is_linear
+        self.fd_eps = float(INI.get(mcfg, "jacobian.epsilon", 1e-7))
         self.sym = E.Symbols(mesh.dim, self.names, mesh.cell_keys)
         # --- compartments on the mesh (make_multi_domain_grid.hh:118-155)
         self._mark_compartments()
@@ -410,6 +413,12 @@ def linear_solve(rowptr, colidx, vals, b, cfg: dict, rel_tol: float, par=0):
     maxit = int(str(INI.get(cfg, "convergence_condition.iteration_range", "1 500")).split()[-1])
     res = CResult()
     L = lib()
+    if typ == "RestartedGMRes":
+        restart = int(cfg.get("restart", 40))          # factory/iterative.hh:64
+        L.orc_gmres(C.c_int64(n), _p(rowptr, C.c_int64), _p(colidx, C.c_int32), _p(vals, C.c_double),
+                    _p(z, C.c_double), _p(rhs, C.c_double), C.c_double(rel_tol), C.c_int(maxit), C.c_int(restart),
+                    C.c_int(kind), C.c_int(bs), C.c_double(relax), C.c_int(par), C.byref(res))
+        return z, res
     fn = {"BiCGSTAB": L.orc_bicgstab, "CG": L.orc_cg}[typ]
     fn(C.c_int64(n), _p(rowptr, C.c_int64), _p(colidx, C.c_int32), _p(vals, C.c_double),
        _p(z, C.c_double), _p(rhs, C.c_double), C.c_double(rel_tol), C.c_int(maxit), C.c_int(kind),
@@ -425,6 +434,29 @@ def rk_table(name: str):
         al = 1.0 - math.sqrt(2.0) / 2.0
         return (np.array([[-1.0, 1.0, 0.0], [-1.0, 0.0, 1.0]]),
                 np.array([[0.0, al, 0.0], [0.0, 1.0 - al, al]]), np.array([0.0, al, 1.0]))
+    # explicit schemes: the stage system only carries the mass form (b_ii = 0)
+    if name == "ExplicitEuler":
+        return np.array([[-1.0, 1.0]]), np.array([[1.0, 0.0]]), np.array([0.0, 1.0])
+    if name == "Heun":
+        return (np.array([[-1.0, 1.0, 0.0], [-0.5, -0.5, 1.0]]),
+                np.array([[1.0, 0.0, 0.0], [0.0, 0.5, 0.0]]), np.array([0.0, 1.0, 1.0]))
+    if name == "Shu3":
+        return (np.array([[-1.0, 1.0, 0.0, 0.0], [-0.75, -0.25, 1.0, 0.0], [-1.0 / 3.0, 0.0, -2.0 / 3.0, 1.0]]),
+                np.array([[1.0, 0.0, 0.0, 0.0], [0.0, 0.25, 0.0, 0.0], [0.0, 0.0, 2.0 / 3.0, 0.0]]),
+                np.array([0.0, 1.0, 0.5, 1.0]))
+    if name == "RungeKutta4":
+        return (np.array([[-1.0, 1.0, 0.0, 0.0, 0.0], [-1.0, 0.0, 1.0, 0.0, 0.0], [-1.0, 0.0, 0.0, 1.0, 0.0],
+                          [-1.0, 0.0, 0.0, 0.0, 1.0]]),
+                np.array([[0.5, 0.0, 0.0, 0.0, 0.0], [0.0, 0.5, 0.0, 0.0, 0.0], [0.0, 0.0, 1.0, 0.0, 0.0],
+                          [1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0, 0.0]]),
+                np.array([0.0, 0.5, 0.5, 1.0, 1.0]))
+    if name == "Alexander3":
+        al = 0.4358665215
+        b1 = -(6.0 * al * al - 16.0 * al + 1.0) / 4.0
+        b2 = (6.0 * al * al - 20.0 * al + 5.0) / 4.0
+        return (np.array([[-1.0, 1.0, 0.0, 0.0], [-1.0, 0.0, 1.0, 0.0], [-1.0, 0.0, 0.0, 1.0]]),
+                np.array([[0.0, al, 0.0, 0.0], [0.0, (1.0 - al) / 2.0, al, 0.0], [0.0, b1, b2, al]]),
+                np.array([0.0, al, (1.0 + al) / 2.0, 1.0]))
     raise NotImplementedError(name)
 
 
@@ -460,10 +492,11 @@ class StepOperator:
 
     def _stage_jacobian(self, u, t, wM, wA):
         vals = np.zeros(self.colidx.size)
+        num, eps = self.model.numerical, self.model.fd_eps
         if wM != 0.0:
-            self.model.jacobian(1, t, wM, u, self.rowptr, self.colidx, vals, self.par)
+            self.model.jacobian(1, t, wM, u, self.rowptr, self.colidx, vals, self.par, numerical=num, eps=eps)
         if wA != 0.0:
-            self.model.jacobian(0, t, wA, u, self.rowptr, self.colidx, vals, self.par)
+            self.model.jacobian(0, t, wA, u, self.rowptr, self.colidx, vals, self.par, numerical=num, eps=eps)
         self._constrain_matrix(vals)
         return vals
 

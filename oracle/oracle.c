@@ -808,6 +808,92 @@ done:
   free(p); free(q); free(Pc.dinv);
 }
 
+/* dune-istl RestartedGMResSolver::apply (third party; used by the reference's own inis through
+ * solver/istl/factory/iterative.hh:64, restart default 40): left preconditioned GMRES(m), modified
+ * Gram-Schmidt, Givens rotations, convergence on the preconditioned defect ||W^-1 (b - A x)||. */
+static void givens_gen(double dx, double dy, double* cs, double* sn) {
+  double ndx = fabs(dx), ndy = fabs(dy);
+  if (ndy < 1e-300) { *cs = 1.0; *sn = 0.0; }
+  else if (ndx < 1e-300) { *cs = 0.0; *sn = 1.0; }
+  else { double nrm = sqrt(dx * dx + dy * dy); *cs = dx / nrm; *sn = dy / nrm; }
+}
+static void givens_apply(double* dx, double* dy, double cs, double sn) {
+  double t = cs * (*dx) + sn * (*dy);
+  *dy = -sn * (*dx) + cs * (*dy);
+  *dx = t;
+}
+
+void orc_gmres(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* vals, double* x,
+               double* b, double reduction, int maxit, int restart, int prec_kind, int bs, double relax,
+               int par, OrcResult* res) {
+  Prec Pc = {prec_kind, bs, relax, 0, 0};
+  prec_setup(&Pc, n, rowptr, colidx, vals);
+  const int m = restart;
+  double* V = malloc(sizeof(double) * (size_t)(m + 1) * n);
+  double *w = malloc(8 * n), *b2 = malloc(8 * n), *tmp = malloc(8 * n);
+  double* H = calloc((size_t)(m + 1) * m, 8);
+  double *s = calloc(m + 1, 8), *cs = calloc(m, 8), *sn = calloc(m, 8), *yv = calloc(m, 8);
+#define Hh(r, c) H[(size_t)(r) * m + (c)]
+  memcpy(b2, b, 8 * n);
+  orc_spmv(n, rowptr, colidx, vals, x, tmp, par);
+  for (int64_t i = 0; i < n; ++i) b[i] -= tmp[i];
+  prec_apply(&Pc, b, V);
+  double norm = sqrt(dot(n, V, V, par)), norm0 = norm;
+  res->norm0 = norm0; res->converged = 0; res->iterations_x2 = 0; res->reduction = 1;
+  if (norm0 < 1e-30) { res->converged = 1; res->reduction = 0; goto done; }
+  int j = 1;
+  while (j <= maxit && !res->converged) {
+    int i = 0;
+    for (int64_t k = 0; k < n; ++k) V[k] *= 1.0 / norm;
+    s[0] = norm;
+    for (i = 1; i < m + 1; ++i) s[i] = 0.0;
+    for (i = 0; i < m && j <= maxit && !res->converged; ++i, ++j) {
+      double* vi = V + (size_t)i * n;
+      double* vn = V + (size_t)(i + 1) * n;
+      orc_spmv(n, rowptr, colidx, vals, vi, vn, par);
+      prec_apply(&Pc, vn, w);
+      for (int k = 0; k < i + 1; ++k) {
+        double* vk = V + (size_t)k * n;
+        double h = dot(n, vk, w, par);
+        Hh(k, i) = h;
+        for (int64_t q = 0; q < n; ++q) w[q] -= h * vk[q];
+      }
+      double hn = sqrt(dot(n, w, w, par));
+      Hh(i + 1, i) = hn;
+      if (fabs(hn) < 1e-80) { j = maxit + 1; break; }   /* breakdown: dune-istl throws SolverAbort */
+      for (int64_t q = 0; q < n; ++q) vn[q] = w[q] * (1.0 / hn);
+      for (int k = 0; k < i; ++k) givens_apply(&Hh(k, i), &Hh(k + 1, i), cs[k], sn[k]);
+      givens_gen(Hh(i, i), Hh(i + 1, i), &cs[i], &sn[i]);
+      givens_apply(&Hh(i, i), &Hh(i + 1, i), cs[i], sn[i]);
+      givens_apply(&s[i], &s[i + 1], cs[i], sn[i]);
+      norm = fabs(s[i + 1]);
+      if (norm < reduction * norm0 || norm < 1e-30) res->converged = 1;
+    }
+    /* update: solve the triangular system, x += sum y_k v_k */
+    for (int a = i - 1; a >= 0; --a) {
+      double acc = s[a];
+      for (int c2 = a + 1; c2 < i; ++c2) acc -= Hh(a, c2) * yv[c2];
+      yv[a] = acc / Hh(a, a);
+    }
+    for (int a = 0; a < i; ++a) {
+      const double* va = V + (size_t)a * n;
+      for (int64_t q = 0; q < n; ++q) x[q] += yv[a] * va[q];
+    }
+    if (!res->converged && j < maxit) {
+      memcpy(b, b2, 8 * n);
+      orc_spmv(n, rowptr, colidx, vals, x, tmp, par);
+      for (int64_t q = 0; q < n; ++q) b[q] -= tmp[q];
+      prec_apply(&Pc, b, V);
+      norm = sqrt(dot(n, V, V, par));
+    }
+  }
+  res->iterations_x2 = 2 * (j - 1);
+  res->reduction = norm / norm0;
+done:
+#undef Hh
+  free(V); free(w); free(b2); free(tmp); free(H); free(s); free(cs); free(sn); free(yv); free(Pc.dinv);
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

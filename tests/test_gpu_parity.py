@@ -190,9 +190,43 @@ def test_cg_matches_oracle():
     assert rel(z, zo) <= 1e-9
 
 
+@pytest.mark.parametrize("matrix_free", [False, True])
+@pytest.mark.parametrize("restart", [40, 5])
+@pytest.mark.parametrize("name,prec", [("grayscott2d", "Jacobi"), ("grayscott3d", "BlockJacobi"), ("cell3d", "Jacobi"),
+                                       ("two_disks", "Jacobi")])
+def test_gmres_matches_oracle(name, prec, restart, matrix_free):
+    """RestartedGMRes in dune-istl's order (left preconditioning, modified Gram-Schmidt, Givens):
+    same iteration count as the restatement, with and without restarts."""
+    import dune_copasi_b200 as D
+    case, om, cfg, model, grid, op = make(name)
+    x = K.rand_state(om.ndofs, 14)
+    t, wM, wA = case.t0, 1.0, 0.1
+    lcfg = D.Config(f"type = RestartedGMRes\nrestart = {restart}\npreconditioner.type = {prec}\n"
+                    f"matrix_free = {'true' if matrix_free else 'false'}\n")
+    solver = D.Solver(op, lcfg)
+    solver.linearize(t, wM, wA, x)
+    b = K.rand_state(om.ndofs, 15, -1.0, 1.0)
+    cd, _ = om.constraints()
+    b[cd] = 0.0
+    z, res = solver.solve(b, 1e-10)
+    S = K.ORC.StepOperator(om)
+    vals = S._stage_jacobian(x, t, wM, wA)
+    zo, ro = K.ORC.linear_solve(S.rowptr, S.colidx, vals, b,
+                                {"type": "RestartedGMRes", "restart": restart,
+                                 "preconditioner": {"type": prec, "block_size": int(om.comp_nspec[0])}}, 1e-10)
+    # GMRES(5) stagnates on two_disks: then both sides must run out of iterations the same way
+    assert bool(res.converged) == bool(ro.converged), (res.reduction, ro.reduction)
+    assert res.converged or (name, restart) == ("two_disks", 5)
+    assert res.half_iterations == ro.iterations_x2, (res.half_iterations, ro.iterations_x2)
+    assert abs(res.reduction - ro.reduction) <= 1e-2 * ro.reduction
+    assert rel(z, zo) <= (1e-8 if res.converged else 1e-5), rel(z, zo)
+
+
 STEP_CASES = [("gauss2d", "Alexander2", 2), ("gauss3d", "ImplicitEuler", 2), ("exp", "Alexander2", 5),
               ("poisson", "ImplicitEuler", 1), ("grayscott2d", "Alexander2", 3), ("grayscott3d", "ImplicitEuler", 2),
-              ("mitchell_schaefer", "Alexander2", 3), ("two_disks", "Alexander2", 1), ("cell3d", "Alexander2", 2)]
+              ("mitchell_schaefer", "Alexander2", 3), ("two_disks", "Alexander2", 1), ("cell3d", "Alexander2", 2),
+              ("grayscott2d", "ExplicitEuler", 2), ("grayscott2d", "Heun", 2), ("grayscott2d", "Shu3", 2),
+              ("grayscott2d", "RungeKutta4", 2), ("mitchell_schaefer", "Alexander3", 2)]
 
 
 @pytest.mark.parametrize("matrix_free", [False, True])
@@ -218,6 +252,43 @@ def test_time_steps_match_oracle(name, rk, nsteps, matrix_free):
     assert rel(got, u) <= FIELD_TOL, (name, rk, matrix_free, rel(got, u))
     stats = st.stats()
     assert stats["steps"] == nsteps and stats["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("name", ["grayscott2d", "grayscott3d", "mitchell_schaefer"])
+def test_numerical_jacobian(name):
+    """model.jacobian.type = numerical (local_operator.hh:713-765): one-sided differences with
+    delta = eps (1 + |x|).  Differences of O(1e-16)/delta are amplified, hence the looser 1e-6."""
+    import dune_copasi_b200 as D
+    import scipy.sparse as sp
+    over = {"model.jacobian.type": "numerical"}
+    case, om, cfg, model, grid, op = make(name, **over)
+    assert om.numerical
+    x = K.rand_state(om.ndofs, 21)
+    z = K.rand_state(om.ndofs, 22, -1.0, 1.0)
+    t, wM, wA = case.t0, 1.0, 0.5 * case.dt
+    rp, ci = om.pattern()
+    ref = np.zeros(ci.size)
+    om.jacobian(1, t, wM, x, rp, ci, ref, numerical=True)
+    om.jacobian(0, t, wA, x, rp, ci, ref, numerical=True)
+    got = op.jacobian(t, wM, wA, x)
+    assert rel(got, ref) <= 1e-6, rel(got, ref)
+    A = sp.csr_matrix((ref, ci, rp), shape=(om.ndofs, om.ndofs))
+    assert rel(op.jacobian_apply(t, wM, wA, x, z), A @ z) <= 1e-6
+    # and it is close to the analytic Jacobian
+    ana = np.zeros(ci.size)
+    om.jacobian(1, t, wM, x, rp, ci, ana)
+    om.jacobian(0, t, wA, x, rp, ci, ana)
+    assert rel(got, ana) <= 1e-5
+    # Newton with the FD Jacobian reaches the same fields (matrix based and matrix free)
+    for mf in ("false", "true"):
+        over2 = dict(over, **{"model.time_step_operator.linear_solver.matrix_free": mf})
+        case, om, cfg, model, grid, op = make(name, **over2)
+        S = K.ORC.StepOperator(om)
+        u, ok = S.apply(om.initial(case.t0), case.t0, case.dt)
+        st = D.Stepper(op, cfg)
+        st.set_state(grid.interpolate(model, case.t0), case.t0)
+        assert ok and st.step(case.dt)
+        assert rel(st.get_state()[0], u) <= 1e-8
 
 
 def test_adaptive_evolve_matches_oracle_and_kat():

@@ -80,6 +80,25 @@ def test_two_disks_kat():
     assert e2f < 0.3 * e2
 
 
+@pytest.mark.parametrize("rk,order", [("ExplicitEuler", 1), ("ImplicitEuler", 1), ("Heun", 2), ("Alexander2", 2),
+                                      ("Shu3", 3), ("Alexander3", 3), ("RungeKutta4", 4)])
+def test_runge_kutta_tables_have_their_order(rk, order):
+    """PDELab's RK parameter tables (third party, restated in SURVEY App. C.2 / oracle.core.rk_table):
+    on u' = -2u (test/exp.ini) the error at t = 1 must shrink with the scheme's order."""
+    errs = []
+    for dt in (0.1, 0.05):
+        om = K.CASES["exp"].oracle(**{"model.time_step_operator.type": rk})
+        S = ORC.StepOperator(om)
+        u, t = om.initial(0.0), 0.0
+        for _ in range(int(round(1.0 / dt))):
+            u, ok = S.apply(u, t, dt)
+            assert ok
+            t += dt
+        errs.append(abs(u[0] - math.exp(-2.0)))
+    rate = math.log2(errs[0] / errs[1])
+    assert abs(rate - order) < 0.35, (rk, errs, rate)
+
+
 @pytest.mark.parametrize("dim", [2, 3])
 def test_p1_element_identities(dim):
     """P1 mass |T|(1+delta_ab)/((d+1)(d+2)) and stiffness |T| grad phi_a . D grad phi_b are
