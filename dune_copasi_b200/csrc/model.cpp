@@ -71,7 +71,19 @@ Model::Model(const PTree& cfg_, int dim_, const std::vector<std::string>& keys)
   };
   for (int g = 0; g < nspec(); ++g) {
     const PTree& f = *scfg[g];
-    if (f.has_sub("velocity")) fail("scalar_field.", species[g].name, ".velocity: advection terms are not built yet");
+    {
+      // velocity.<axis>.expression, velocity.jacobian.<wrt>.<axis>.expression (local_equations.hh:663-669)
+      const PTree& v = f.sub("velocity");
+      bool active = false;
+      for (int a = 0; a < dim; ++a) active |= add(Term::Vel, g, a, -1, v.sub(kAxis[a]).get("expression", std::string()));
+      if (active)
+        for (auto& wrt : v.sub("jacobian").sub_keys()) {
+          int k = species_index(wrt);
+          if (k < 0) continue;
+          for (int a = 0; a < dim; ++a)
+            add(Term::VelJac, g, k, a, v.sub("jacobian").sub(wrt).sub(kAxis[a]).get("expression", std::string()));
+        }
+    }
     struct { Term::Kind k, jk; const char* key; } two[] = {
         {Term::Reaction, Term::ReactionJac, "reaction"}, {Term::Storage, Term::StorageJac, "storage"}};
     for (auto& tk : two) {
@@ -87,13 +99,24 @@ Model::Model(const PTree& cfg_, int dim_, const std::vector<std::string>& keys)
       int j = species_index(wrt);
       if (j < 0) continue;
       const PTree& d = cd.sub(wrt);
-      if (d.get("type", std::string("scalar")) != "scalar")
-        fail("cross_diffusion.", wrt, ".type = tensor is not built yet");
-      if (add(Term::Diff, g, j, -1, d.get("expression", std::string())))
+      // `type` = scalar | tensor is read for the function and again for each jacobian entry
+      auto diffusion = [&](const PTree& t, Term::Kind ks, Term::Kind kt, int kk) {
+        std::string type = t.get("type", std::string("scalar"));
+        if (type == "scalar") return add(ks, g, j, kk, t.get("expression", std::string()));
+        if (type != "tensor") fail("not known type 'scalar_value.", species[g].name, ".cross_diffusion.type = ", type, "'");
+        bool active = false;
+        for (int r = 0; r < dim; ++r)
+          for (int c = 0; c < dim; ++c) {
+            std::string key = std::string(kAxis[r]) + kAxis[c];
+            if (t.has_sub(key))
+              active |= add(kt, g, j, 3 * r + c + (kk >= 0 ? 9 * kk : 0), t.sub(key).get("expression", std::string()));
+          }
+        return active;
+      };
+      if (diffusion(d, Term::Diff, Term::DiffT, -1))
         for (auto& kk : d.sub("jacobian").sub_keys()) {
           int k = species_index(kk);
-          if (k >= 0 && !expr_is_absent(d.sub("jacobian").sub(kk).get("expression", std::string())))
-            fail("cross_diffusion.", wrt, ".jacobian: non-linear diffusion Jacobians are not built yet");
+          if (k >= 0) diffusion(d.sub("jacobian").sub(kk), Term::DiffJac, Term::DiffTJac, k);
         }
     }
     const PTree& of = f.sub("outflow");
@@ -127,7 +150,16 @@ bool Model::has_outflow() const {
 
 static bool depends_on_point(const NodeP& ast);
 
+bool Model::has_extended_terms(int c) const {
+  for (auto& t : terms)
+    if (species[t.i].comp == c && (t.kind == Term::Vel || t.kind == Term::VelJac || t.kind == Term::DiffT ||
+                                   t.kind == Term::DiffTJac || t.kind == Term::DiffJac))
+      return true;
+  return false;
+}
+
 bool Model::diffusion_is_constant(int c) const {
+  if (has_extended_terms(c)) return false;
   for (auto& t : terms)
     if (t.kind == Term::Diff && species[t.i].comp == c && species[t.j].comp == c && depends_on_point(t.ast)) return false;
   return true;
@@ -136,9 +168,12 @@ bool Model::diffusion_is_constant(int c) const {
 std::vector<std::pair<int, int>> Model::species_pairs() const {
   std::set<std::pair<int, int>> s;
   for (auto& t : terms) {
-    if (t.kind == Term::ReactionJac || t.kind == Term::StorageJac || t.kind == Term::Diff) s.insert({t.i, t.j});
-    else if (t.kind == Term::Storage) s.insert({t.i, t.i});
+    if (t.kind == Term::ReactionJac || t.kind == Term::StorageJac || t.kind == Term::Diff || t.kind == Term::DiffT ||
+        t.kind == Term::VelJac)
+      s.insert({t.i, t.j});
+    else if (t.kind == Term::Storage || t.kind == Term::Vel) s.insert({t.i, t.i});   // velocity: :304-307
     else if (t.kind == Term::DiffJac) s.insert({t.i, t.k});
+    else if (t.kind == Term::DiffTJac) s.insert({t.i, t.k / 9});
   }
   std::vector<std::pair<int, int>> out;
   for (auto& p : s)
@@ -265,11 +300,14 @@ std::string Model::cuda_source() const {
         has_stiff = has_diff = true;
         if (depends_on_point(t.ast)) diff_const = false;
       }
+      if (t.kind == Term::Vel || (t.kind == Term::DiffT && species[t.j].comp == c)) has_stiff = has_diff = true;
     }
+    const bool has_ext = has_extended_terms(c);
+    if (has_ext) diff_const = false;   // fluxes are evaluated point by point
     o << "template <> struct DcComp<" << c << "> {\n";
     o << "  static constexpr int NS = " << std::max(ns, 1) << ";\n  static constexpr int NS_REAL = " << ns << ";\n";
     o << "  static constexpr bool HAS_MASS = " << has_mass << ", HAS_STIFF = " << has_stiff
-      << ", HAS_DIFF = " << has_diff << ", DIFF_CONST = " << diff_const << ";\n";
+      << ", HAS_DIFF = " << has_diff << ", DIFF_CONST = " << diff_const << ", HAS_EXT = " << has_ext << ";\n";
     // pattern mask (which species pairs exist in the sparsity pattern)
     {
       int n = std::max(ns, 1);
@@ -308,6 +346,13 @@ std::string Model::cuda_source() const {
           o << "      { const double D = wA * (" << code(t) << ");";
           for (int k = 0; k < dim; ++k) o << " fl[" << i << "][" << k << "] -= D * g[" << j << "][" << k << "];";
           o << " }\n";
+        } else if (t.kind == Term::DiffT && t.i == g0 + i && species[t.j].comp == c) {
+          // tensor diffusion: out[r] = sum_c D[r][c] in[c]
+          o << "      fl[" << i << "][" << t.k / 3 << "] -= wA * (" << code(t) << ") * g[" << species[t.j].local << "]["
+            << t.k % 3 << "];\n";
+        } else if (t.kind == Term::Vel && t.i == g0 + i) {
+          // advection: flux += velocity * u_i  (local_operator.hh:481)
+          o << "      fl[" << i << "][" << t.j << "] += wA * (" << code(t) << ") * u[" << i << "];\n";
         }
       o << "    }\n";
     }
@@ -334,6 +379,46 @@ std::string Model::cuda_source() const {
     for (auto& t : terms)
       if (t.kind == Term::Diff && species[t.i].comp == c && species[t.j].comp == c)
         o << "    jd[" << species[t.i].local << "][" << species[t.j].local << "] += wA * (" << code(t) << ");\n";
+    o << "    (void)c; (void)u; (void)g; (void)wA;\n  }\n";
+    // ---- general (extended) Jacobian coefficients, consumed by dc_ext_jacobian only
+    o << "  // DT[i][j][r][c]: (DT grad(phi_a)) . grad(phi_b), scalar coefficients on the diagonal (local_operator.hh:674-685)\n";
+    o << "  __device__ __noinline__ static void jac_diff_t(const DcCtx& c, const double* u, const double (*g)[DC_DIM], double wA, double (*DT)[NS][DC_DIM][DC_DIM]) {\n";
+    o << "    for (int i = 0; i < NS; ++i) for (int j = 0; j < NS; ++j) for (int r = 0; r < DC_DIM; ++r) for (int s = 0; s < DC_DIM; ++s) DT[i][j][r][s] = 0.0;\n";
+    if (has_ext)
+      for (auto& t : terms) {
+        if (species[t.i].comp != c || (t.kind != Term::Diff && t.kind != Term::DiffT) || species[t.j].comp != c) continue;
+        int i = species[t.i].local;
+        if (t.kind == Term::Diff) {
+          o << "    { const double D = wA * (" << code(t) << ");";
+          for (int k = 0; k < dim; ++k) o << " DT[" << i << "][" << species[t.j].local << "][" << k << "][" << k << "] += D;";
+          o << " }\n";
+        } else if (t.kind == Term::DiffT) {
+          o << "    DT[" << i << "][" << species[t.j].local << "][" << t.k / 3 << "][" << t.k % 3 << "] += wA * (" << code(t) << ");\n";
+        }
+      }
+    o << "    (void)c; (void)u; (void)g; (void)wA;\n  }\n";
+    o << "  // W[i][k][r]: coefficient of phi_a * d(phi_b)/dx_r -- advection (local_operator.hh:643-671) and\n"
+         "  //   dD_ij/du_k grad(u_k) (:688-700), with the index roles exactly as written there\n";
+    o << "  __device__ __noinline__ static void jac_ext(const DcCtx& c, const double* u, const double (*g)[DC_DIM], double wA, double (*W)[NS][DC_DIM]) {\n";
+    o << "    for (int i = 0; i < NS; ++i) for (int k = 0; k < NS; ++k) for (int r = 0; r < DC_DIM; ++r) W[i][k][r] = 0.0;\n";
+    if (has_ext)
+      for (auto& t : terms) {
+        if (species[t.i].comp != c) continue;
+        int i = species[t.i].local;
+        if (t.kind == Term::Vel) {
+          o << "    W[" << i << "][" << i << "][" << t.j << "] -= wA * (" << code(t) << ");\n";
+        } else if (t.kind == Term::VelJac && species[t.j].comp == c) {
+          o << "    W[" << i << "][" << species[t.j].local << "][" << t.k << "] -= wA * (" << code(t) << ") * u[" << i << "];\n";
+        } else if (t.kind == Term::DiffJac && species[t.k].comp == c) {
+          int k = species[t.k].local;
+          o << "    { const double dD = wA * (" << code(t) << ");";
+          for (int r = 0; r < dim; ++r) o << " W[" << i << "][" << k << "][" << r << "] += dD * g[" << k << "][" << r << "];";
+          o << " }\n";
+        } else if (t.kind == Term::DiffTJac && species[t.k / 9].comp == c) {
+          int k = species[t.k / 9].local, r = (t.k % 9) / 3, cc = t.k % 3;
+          o << "    W[" << i << "][" << k << "][" << r << "] += wA * (" << code(t) << ") * g[" << k << "][" << cc << "];\n";
+        }
+      }
     o << "    (void)c; (void)u; (void)g; (void)wA;\n  }\n";
     o << "};\n";
   }

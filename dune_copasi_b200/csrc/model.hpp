@@ -13,11 +13,14 @@
 namespace dcb {
 
 struct Term {
-  enum Kind { Reaction, ReactionJac, Storage, StorageJac, Diff, DiffJac, Outflow, OutflowJac };
+  // Diff / DiffJac: scalar diffusion D_ij and dD_ij/du_k; DiffT / DiffTJac: one entry [r][c] of a
+  // tensor diffusion and of its derivative (make_tensor_apply, functor_factory_parser.impl.hh:65-112);
+  // Vel / VelJac: one component of the advection velocity and of its derivative (make_vector :36-61)
+  enum Kind { Reaction, ReactionJac, Storage, StorageJac, Diff, DiffJac, Outflow, OutflowJac, Vel, VelJac, DiffT, DiffTJac };
   Kind kind;
   int i = -1;    // species (global id)
-  int j = -1;    // wrt species (Jac / Diff) or target compartment (Outflow*)
-  int k = -1;    // jac wrt species of DiffJac / OutflowJac
+  int j = -1;    // wrt species (Jac / Diff*) or target compartment (Outflow*) or axis (Vel)
+  int k = -1;    // jac wrt species of DiffJac / OutflowJac; axis of VelJac; 3r+c of DiffT; 9k+3r+c of DiffTJac
   NodeP ast;     // resolved + folded
   std::string text;
 };
@@ -54,6 +57,9 @@ class Model {
   bool has_outflow() const;
   // no diffusion coefficient of compartment c depends on the quadrature point (position, fields)
   bool diffusion_is_constant(int c) const;
+  // compartment c carries advection, tensor diffusion or diffusion-Jacobian terms: they are
+  // assembled by the general element kernels only (experimental in the reference, CHANGELOG !83)
+  bool has_extended_terms(int c) const;
   // species couplings (i,j) of the volume sparsity pattern, local_operator.hh:276-338
   std::vector<std::pair<int, int>> species_pairs() const;
   // directional compartment pairs (cs -> ct) that carry an outflow term; ct == cs means boundary

@@ -383,7 +383,8 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
     if (ns == 0 || comp_nelem_[c] == 0) continue;
     if (mode == 4 && !(scheme == "structured" && c == struct_comp_)) continue;   // scalar diagonal: structured only
     // finite-difference Jacobians (model.jacobian.type = numerical) live in the element kernels
-    const bool fd = model->numerical_jacobian && mode != 0;
+    // ... and so do the general analytic Jacobians of advection / tensor / dD/du terms
+    const bool fd = (model->numerical_jacobian || model->has_extended_terms(c)) && mode != 0;
     if (scheme == "structured" && mode != 3 && c == struct_comp_ && !fd) {
       DcStructArgs a{};
       a.ncells = 1;

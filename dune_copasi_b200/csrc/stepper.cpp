@@ -41,10 +41,17 @@ StepOperator::StepOperator(std::shared_ptr<DeviceOperator> o, const PTree& cfg, 
     a_ = {{-1.0, 1.0, 0.0, 0.0}, {-1.0, 0.0, 1.0, 0.0}, {-1.0, 0.0, 0.0, 1.0}};
     b_ = {{0.0, al, 0.0, 0.0}, {0.0, (1.0 - al) / 2.0, al, 0.0}, {0.0, b1, b2, al}};
     d_ = {0.0, al, (1.0 + al) / 2.0, 1.0};
+  } else if (rk_type == "FractionalStepTheta") {
+    // make_step_operator.hh:434-435: sub-steps theta, 1-2theta, theta; implicit weight alpha*theta
+    const double th = 1.0 - 0.5 * std::sqrt(2.0), alpha = 2.0 - std::sqrt(2.0), beta = 1.0 - alpha;
+    a_ = {{-1.0, 1.0, 0.0, 0.0}, {0.0, -1.0, 1.0, 0.0}, {0.0, 0.0, -1.0, 1.0}};
+    b_ = {{beta * th, alpha * th, 0.0, 0.0}, {0.0, alpha * (1.0 - 2.0 * th), alpha * th, 0.0},
+          {0.0, 0.0, beta * th, alpha * th}};
+    d_ = {0.0, th, 1.0 - th, 1.0};
   } else {
-    // FractionalStepTheta of make_step_operator.hh:434-435 is the one table not restated
     fail("time_step_operator.type = '", rk_type,
-         "' is not built (available: ExplicitEuler, ImplicitEuler, Heun, Shu3, RungeKutta4, Alexander2, Alexander3)");
+         "' is not built (available: ExplicitEuler, ImplicitEuler, Heun, Shu3, RungeKutta4, Alexander2, "
+         "FractionalStepTheta, Alexander3)");
   }
   is_linear = op->model->is_linear;
   const PTree& ls = cfg.sub("linear_solver");

@@ -30,7 +30,9 @@ from . import mesh as MESH
 HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-K_REACTION, K_REACTION_JAC, K_STORAGE, K_STORAGE_JAC, K_DIFF, K_DIFF_JAC, K_OUTFLOW, K_OUTFLOW_JAC, K_NKIND = range(9)
+(K_REACTION, K_REACTION_JAC, K_STORAGE, K_STORAGE_JAC, K_DIFF, K_DIFF_JAC, K_OUTFLOW, K_OUTFLOW_JAC,
+ K_VEL, K_VEL_JAC, K_DIFF_T, K_DIFF_T_JAC, K_NKIND) = range(13)
+AXES = "xyz"
 
 
 def build_lib(force=False):
@@ -137,12 +139,26 @@ class Model:
                             add(jkind, g, idx[wrt], -1, jc.get("expression"))
             for wrt, dc in INI.sub(sc, "cross_diffusion").items():
                 if wrt in idx and isinstance(dc, dict):
-                    if dc.get("type", "scalar") != "scalar":
-                        raise NotImplementedError("tensor diffusion (SURVEY 8f #4)")
-                    if add(K_DIFF, g, idx[wrt], -1, dc.get("expression")):
+                    # make_tensor_apply (functor_factory_parser.impl.hh:65-112): `type` = scalar | tensor,
+                    # read separately for the function and for each of its jacobian entries
+                    def diffusion(cfgd, kind_s, kind_t, kk):
+                        typ = cfgd.get("type", "scalar")
+                        if typ == "scalar":
+                            return add(kind_s, g, idx[wrt], kk if kk >= 0 else -1, cfgd.get("expression"))
+                        if typ != "tensor":
+                            raise ValueError(f"not known type 'scalar_value.{sp.name}.cross_diffusion.type = {typ}'")
+                        active = False
+                        for r in range(mesh.dim):
+                            for c in range(mesh.dim):
+                                ent = cfgd.get(AXES[r] + AXES[c])
+                                if isinstance(ent, dict):
+                                    code3 = 3 * r + c + (9 * kk if kk >= 0 else 0)
+                                    active |= add(kind_t, g, idx[wrt], code3, ent.get("expression"))
+                        return active
+                    if diffusion(dc, K_DIFF, K_DIFF_T, -1):
                         for k, jc in INI.sub(dc, "jacobian").items():
                             if k in idx and isinstance(jc, dict):
-                                add(K_DIFF_JAC, g, idx[wrt], idx[k], jc.get("expression"))
+                                diffusion(jc, K_DIFF_JAC, K_DIFF_T_JAC, idx[k])
             for cname, oc in INI.sub(sc, "outflow").items():
                 if cname in self.comp_names and isinstance(oc, dict):
                     l = self.comp_names.index(cname)
@@ -150,8 +166,21 @@ class Model:
                         for k, jc in INI.sub(oc, "jacobian").items():
                             if k in idx and isinstance(jc, dict):
                                 add(K_OUTFLOW_JAC, g, l, idx[k], jc.get("expression"))
-            if "velocity" in sc:
-                raise NotImplementedError("velocity terms (SURVEY 8f #4)")
+            # velocity.<axis>.expression (make_vector, functor_factory_parser.impl.hh:36-61) with
+            # velocity.jacobian.<wrt>.<axis>.expression (local_equations.hh:663-669)
+            vc = INI.sub(sc, "velocity")
+            active = False
+            for ax in range(mesh.dim):
+                ent = vc.get(AXES[ax])
+                if isinstance(ent, dict):
+                    active |= add(K_VEL, g, ax, -1, ent.get("expression"))
+            if active:
+                for k, jc in INI.sub(vc, "jacobian").items():
+                    if k in idx and isinstance(jc, dict):
+                        for ax in range(mesh.dim):
+                            ent = jc.get(AXES[ax])
+                            if isinstance(ent, dict):
+                                add(K_VEL_JAC, g, idx[k], ax, ent.get("expression"))
         terms.sort(key=lambda t: (t[1], t[0]))
         self.terms = np.asarray(terms, dtype=np.int32).reshape(-1, 5)
         tptr = np.zeros(self.nspec * K_NKIND + 1, dtype=np.int32)
@@ -294,10 +323,16 @@ class Model:
                 pairs.add((i, j))
             elif kind == K_STORAGE:
                 pairs.add((i, i))
-            elif kind == K_DIFF:
+            elif kind in (K_DIFF, K_DIFF_T):
                 pairs.add((i, j))
             elif kind == K_DIFF_JAC:
                 pairs.add((i, k))
+            elif kind == K_DIFF_T_JAC:
+                pairs.add((i, k // 9))
+            elif kind == K_VEL:                 # local_operator.hh:304-307
+                pairs.add((i, i))
+            elif kind == K_VEL_JAC:             # :308-313
+                pairs.add((i, j))
         return sorted(p for p in pairs if self.species[p[0]].comp == self.species[p[1]].comp)
 
     def pattern(self):
@@ -457,6 +492,16 @@ def rk_table(name: str):
         return (np.array([[-1.0, 1.0, 0.0, 0.0], [-1.0, 0.0, 1.0, 0.0], [-1.0, 0.0, 0.0, 1.0]]),
                 np.array([[0.0, al, 0.0, 0.0], [0.0, (1.0 - al) / 2.0, al, 0.0], [0.0, b1, b2, al]]),
                 np.array([0.0, al, (1.0 + al) / 2.0, 1.0]))
+    if name == "FractionalStepTheta":
+        # PDELab::FractionalStepParameter (third party; make_step_operator.hh:434-435): three
+        # sub-steps theta, 1-2theta, theta with the implicit weight alpha*theta in each
+        th = 1.0 - 0.5 * math.sqrt(2.0)
+        alpha = 2.0 - math.sqrt(2.0)
+        beta = 1.0 - alpha
+        return (np.array([[-1.0, 1.0, 0.0, 0.0], [0.0, -1.0, 1.0, 0.0], [0.0, 0.0, -1.0, 1.0]]),
+                np.array([[beta * th, alpha * th, 0.0, 0.0], [0.0, alpha * (1.0 - 2.0 * th), alpha * th, 0.0],
+                          [0.0, 0.0, beta * th, alpha * th]]),
+                np.array([0.0, th, 1.0 - th, 1.0]))
     raise NotImplementedError(name)
 
 

@@ -55,8 +55,12 @@ typedef struct {
   const int32_t* f_lout;
 } OrcMesh;
 
+/* term kinds; (i, j, k) per kind:
+ *   K_DIFF (i, wrt j, -)            scalar D_ij            K_DIFF_JAC (i, wrt j, k)          dD_ij/du_k
+ *   K_DIFF_T (i, wrt j, 3r+c)       tensor entry D_ij[r][c] K_DIFF_T_JAC (i, wrt j, 9k+3r+c)  its derivative
+ *   K_VEL (i, axis, -)              velocity component      K_VEL_JAC (i, wrt k, axis)        d vel/du_k   */
 enum { K_REACTION = 0, K_REACTION_JAC, K_STORAGE, K_STORAGE_JAC, K_DIFF, K_DIFF_JAC, K_OUTFLOW,
-       K_OUTFLOW_JAC, K_NKIND };
+       K_OUTFLOW_JAC, K_VEL, K_VEL_JAC, K_DIFF_T, K_DIFF_T_JAC, K_NKIND };
 
 typedef struct {
   int32_t ncomp, nspec;
@@ -294,6 +298,17 @@ void orc_residual_volume(const OrcMesh* M, const OrcModel* P, int form, double t
               const double* gj = ctx + P->spec_base + 4 * j + 1;
               for (int k = 0; k < dim; ++k) flux[k] -= D * gj[k];
             }
+            /* tensor diffusion: out[r] = sum_c D[r][c] in[c]  (functor_factory_parser.impl.hh:79-107) */
+            TERMS(P, g, K_DIFF_T, t0, t1);
+            for (int d = t0; d < t1; ++d) {
+              int j = P->terms[d * 5 + 2], rr = P->terms[d * 5 + 3] / 3, cc = P->terms[d * 5 + 3] % 3;
+              double D = run(P, P->terms[d * 5 + 4], ctx);
+              flux[rr] -= D * ctx[P->spec_base + 4 * j + 1 + cc];
+            }
+            /* advection: flux += velocity * u_i  (local_operator.hh:481) */
+            TERMS(P, g, K_VEL, v0, v1);
+            for (int d = v0; d < v1; ++d)
+              flux[P->terms[d * 5 + 2]] += run(P, P->terms[d * 5 + 4], ctx) * ctx[P->spec_base + 4 * g];
           } else {
             TERMS(P, g, K_STORAGE, s0, s1);
             if (s1 > s0) scalar += ctx[P->spec_base + 4 * g] * run(P, P->terms[s0 * 5 + 4], ctx);
@@ -369,21 +384,59 @@ static void jacobian_volume(const OrcMesh* M, const OrcModel* P, int form, doubl
                   sink_add(S, ed[a] + si, ed[b] + sj, w * v * factor);
                 }
               }
-              /* non-linear diffusion d D_ij / d u_k -- literal restatement incl. the index
-                 transposition and the use of grad u_k (local_operator.hh:688-700) */
-              TERMS(P, g, K_DIFF_JAC, e0, e1);
-              for (int et = e0; et < e1; ++et) {
-                if (P->terms[et * 5 + 2] != wrt) continue;
-                int kk = P->terms[et * 5 + 3], sk = P->spec_local[kk];
-                double dD = run(P, P->terms[et * 5 + 4], ctx);
-                const double* gk = ctx + P->spec_base + 4 * kk + 1;
-                for (int a = 0; a < nd; ++a)
-                  for (int b = 0; b < nd; ++b) {
-                    double v = 0;
-                    for (int k = 0; k < dim; ++k) v += dD * gk[k] * G[b][k];
-                    sink_add(S, ed[a] + si, ed[b] + sk, w * phi[a] * v * factor);
-                  }
-              }
+            }
+            /* non-linear diffusion d D_ij / d u_k -- literal restatement incl. the index
+               transposition and the use of grad u_k (local_operator.hh:688-700) */
+            TERMS(P, g, K_DIFF_JAC, e0, e1);
+            for (int et = e0; et < e1; ++et) {
+              int kk = P->terms[et * 5 + 3], sk = P->spec_local[kk];
+              double dD = run(P, P->terms[et * 5 + 4], ctx);
+              const double* gk = ctx + P->spec_base + 4 * kk + 1;
+              for (int a = 0; a < nd; ++a)
+                for (int b = 0; b < nd; ++b) {
+                  double v = 0;
+                  for (int k = 0; k < dim; ++k) v += dD * gk[k] * G[b][k];
+                  sink_add(S, ed[a] + si, ed[b] + sk, w * phi[a] * v * factor);
+                }
+            }
+            /* tensor diffusion, entry by entry: (D grad phi_a) . grad phi_b -- the tensor acts on the
+               TEST gradient as written at local_operator.hh:679-684 */
+            TERMS(P, g, K_DIFF_T, t0, t1);
+            for (int d = t0; d < t1; ++d) {
+              int wrt = P->terms[d * 5 + 2], sj = P->spec_local[wrt];
+              int rr = P->terms[d * 5 + 3] / 3, cc = P->terms[d * 5 + 3] % 3;
+              double D = run(P, P->terms[d * 5 + 4], ctx);
+              for (int a = 0; a < nd; ++a)
+                for (int b = 0; b < nd; ++b)
+                  sink_add(S, ed[a] + si, ed[b] + sj, w * (D * G[a][cc] * G[b][rr]) * factor);
+            }
+            TERMS(P, g, K_DIFF_T_JAC, u0, u1);
+            for (int d = u0; d < u1; ++d) {
+              int code3 = P->terms[d * 5 + 3], kk = code3 / 9, rr = (code3 % 9) / 3, cc = code3 % 3;
+              int sk = P->spec_local[kk];
+              double dD = run(P, P->terms[d * 5 + 4], ctx);
+              double gkc = ctx[P->spec_base + 4 * kk + 1 + cc];
+              for (int a = 0; a < nd; ++a)
+                for (int b = 0; b < nd; ++b)
+                  sink_add(S, ed[a] + si, ed[b] + sk, w * phi[a] * (dD * gkc * G[b][rr]) * factor);
+            }
+            /* advection (local_operator.hh:643-671), literal incl. the roles of the indices:
+               entry (test a, trial b) = -phi_a (vel . grad phi_b) */
+            TERMS(P, g, K_VEL, v0, v1);
+            for (int d = v0; d < v1; ++d) {
+              int ax = P->terms[d * 5 + 2];
+              double vel = run(P, P->terms[d * 5 + 4], ctx);
+              for (int a = 0; a < nd; ++a)
+                for (int b = 0; b < nd; ++b)
+                  sink_add(S, ed[a] + si, ed[b] + si, w * (-(vel * phi[a]) * G[b][ax]) * factor);
+            }
+            TERMS(P, g, K_VEL_JAC, w0, w1);
+            for (int d = w0; d < w1; ++d) {
+              int kk = P->terms[d * 5 + 2], ax = P->terms[d * 5 + 3], sk = P->spec_local[kk];
+              double adv = run(P, P->terms[d * 5 + 4], ctx) * ctx[P->spec_base + 4 * g];
+              for (int a = 0; a < nd; ++a)
+                for (int b = 0; b < nd; ++b)
+                  sink_add(S, ed[a] + si, ed[b] + sk, w * (-phi[a] * (adv * G[b][ax])) * factor);
             }
           } else {
             TERMS(P, g, K_STORAGE, s0, s1);

@@ -303,6 +303,53 @@ time_end = 1
 """ + SOLVER
 
 
+# Synthetic: every volume term of local_operator.hh:417-707 the inis above do not reach -- advection
+# (velocity.{x,y,z} with a jacobian), tensor diffusion, solution dependent diffusion with its
+# jacobian entries (scalar and tensor), a storage coefficient with a jacobian.
+ADVECTION = """
+[compartments.domain]
+type = expression
+expression = 1
+[model.scalar_field.u]
+compartment = domain
+initial.expression = 0.5 + 0.3*sin(3*position_x)*cos(2*position_y)
+storage.expression = 1 + 0.1*v
+storage.jacobian.v.expression = 0.1
+reaction.expression = -u*v + 0.1
+reaction.jacobian.u.expression = -v
+reaction.jacobian.v.expression = -u
+velocity.x.expression = 0.3*v
+velocity.y.expression = -0.2 + 0.1*position_x
+velocity.jacobian.v.x.expression = 0.3
+[model.scalar_field.u.cross_diffusion.u]
+type = tensor
+xx.expression = 0.01*(1 + u)
+xy.expression = 0.002
+yx.expression = 0.001*u
+yy.expression = 0.02
+zz.expression = 0.015
+jacobian.u.type = tensor
+jacobian.u.xx.expression = 0.01
+jacobian.u.yx.expression = 0.001
+[model.scalar_field.u.cross_diffusion.v]
+expression = 0.003
+[model.scalar_field.v]
+compartment = domain
+initial.expression = 0.4 + 0.2*cos(2*position_x + position_y)
+storage.expression = 1
+reaction.expression = u*v - 0.3*v
+reaction.jacobian.u.expression = v
+reaction.jacobian.v.expression = u - 0.3
+velocity.x.expression = 0.1
+velocity.z.expression = 0.05*u
+velocity.jacobian.u.z.expression = 0.05
+cross_diffusion.v.expression = 0.01*(1 + u^2)
+cross_diffusion.v.jacobian.u.expression = 0.02*u
+[model.time_step_operator]
+time_end = 1
+""" + SOLVER
+
+
 class Case:
     def __init__(self, name, ini, dim, mesh_fn, t0=0.0, dt=0.1, structured=None):
         self.name, self.ini, self.dim, self.mesh_fn, self.t0, self.dt = name, ini, dim, mesh_fn, t0, dt
@@ -337,6 +384,8 @@ CASES = {
     "mitchell_schaefer": Case("mitchell_schaefer", MITCHELL_SCHAEFER, 2, _s(2, 16), dt=0.01, structured=([16, 16], [0, 0], [1, 1])),
     "two_disks": Case("two_disks", TWO_DISKS, 2, lambda: OMESH.two_disks(6, 6, 32), dt=1.0),
     "cell3d": Case("cell3d", CELL, 3, _s(3, 8), dt=0.05, structured=([8, 8, 8], [0, 0, 0], [1, 1, 1])),
+    "advection2d": Case("advection2d", ADVECTION, 2, _s(2, 12), dt=0.05, structured=([12, 12], [0, 0], [1, 1])),
+    "advection3d": Case("advection3d", ADVECTION, 3, _s(3, 5), dt=0.05, structured=([5, 5, 5], [0, 0, 0], [1, 1, 1])),
 }
 
 

@@ -226,7 +226,9 @@ STEP_CASES = [("gauss2d", "Alexander2", 2), ("gauss3d", "ImplicitEuler", 2), ("e
               ("poisson", "ImplicitEuler", 1), ("grayscott2d", "Alexander2", 3), ("grayscott3d", "ImplicitEuler", 2),
               ("mitchell_schaefer", "Alexander2", 3), ("two_disks", "Alexander2", 1), ("cell3d", "Alexander2", 2),
               ("grayscott2d", "ExplicitEuler", 2), ("grayscott2d", "Heun", 2), ("grayscott2d", "Shu3", 2),
-              ("grayscott2d", "RungeKutta4", 2), ("mitchell_schaefer", "Alexander3", 2)]
+              ("grayscott2d", "RungeKutta4", 2), ("mitchell_schaefer", "Alexander3", 2),
+              ("grayscott2d", "FractionalStepTheta", 2), ("advection2d", "Alexander2", 2),
+              ("advection3d", "ImplicitEuler", 2)]
 
 
 @pytest.mark.parametrize("matrix_free", [False, True])

@@ -83,8 +83,8 @@ def test_configuration_errors_are_loud():
         D.Model(D.Config(base.replace("grow_rate*u", "grow_rate*undefined_name")), 2).cuda_source()
     with pytest.raises(D.DcbError, match="repeated|compartment"):
         D.Model(D.Config("[model.scalar_field.u]\ncompartment = x\n"), 2)
-    with pytest.raises(D.DcbError, match="tensor"):
-        D.Model(D.Config(base + "\n[model.scalar_field.u.cross_diffusion.u]\ntype = tensor\nexpression = 1\n"), 2)
+    with pytest.raises(D.DcbError, match="not known type"):
+        D.Model(D.Config(base + "\n[model.scalar_field.u.cross_diffusion.u]\ntype = matrix\nexpression = 1\n"), 2)
     # overlapping compartments are refused at bind time
     cfg = D.Config("[compartments]\na.expression = 1\nb.expression = 1\n[model.scalar_field.u]\ncompartment = a\nstorage.expression = 1\n")
     model = D.Model(cfg, 2)
@@ -105,7 +105,7 @@ def test_generated_cuda_matches_oracle_vm():
         cfg, model, grid = K.product_objects(case)
         src = model.cuda_source().split("// Argument blocks shared")[0]
         dim = case.dim
-        body = ["#include <cmath>\n#include <cstdio>\nusing namespace std;\n#define __device__\n#define __host__\n#define __forceinline__ inline\n", src,
+        body = ["#include <cmath>\n#include <cstdio>\nusing namespace std;\n#define __device__\n#define __host__\n#define __forceinline__ inline\n#define __noinline__\n", src,
                 "int main(){ DcCtx c{}; double u[16], g[16][DC_DIM], sc[16], jm[16][16];\n"]
         # one sample point per compartment
         samples = []

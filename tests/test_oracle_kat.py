@@ -10,6 +10,7 @@ import pytest
 import cases as K
 from oracle import core as ORC
 from oracle import expr as E
+from oracle import ini as INI
 from oracle import mesh as OMESH
 
 
@@ -81,7 +82,8 @@ def test_two_disks_kat():
 
 
 @pytest.mark.parametrize("rk,order", [("ExplicitEuler", 1), ("ImplicitEuler", 1), ("Heun", 2), ("Alexander2", 2),
-                                      ("Shu3", 3), ("Alexander3", 3), ("RungeKutta4", 4)])
+                                      ("FractionalStepTheta", 2), ("Shu3", 3), ("Alexander3", 3),
+                                      ("RungeKutta4", 4)])
 def test_runge_kutta_tables_have_their_order(rk, order):
     """PDELab's RK parameter tables (third party, restated in SURVEY App. C.2 / oracle.core.rk_table):
     on u' = -2u (test/exp.ini) the error at t = 1 must shrink with the scheme's order."""
@@ -97,6 +99,55 @@ def test_runge_kutta_tables_have_their_order(rk, order):
         errs.append(abs(u[0] - math.exp(-2.0)))
     rate = math.log2(errs[0] / errs[1])
     assert abs(rate - order) < 0.35, (rk, errs, rate)
+
+
+@pytest.mark.parametrize("name", ["advection2d", "advection3d"])
+def test_extended_terms_jacobian_is_the_vertex_swapped_derivative(name):
+    """Advection, tensor diffusion and dD/du terms (local_operator.hh:643-700).  The residual is pinned
+    by finite differences: as the reference writes its analytic entries with the test index on the
+    trial factor, the analytic block (test a, trial b) must equal the true derivative with the two
+    vertices swapped (species kept), and the mass form is symmetric."""
+    import scipy.sparse as sp
+    over = {"model.scalar_field.v.cross_diffusion.v.expression": "0.01*(1+v^2)",     # dD/du_k with k == wrt only:
+            "model.scalar_field.v.cross_diffusion.v.jacobian.u.expression": "0",     # the k != wrt entry uses grad u_k
+            "model.scalar_field.v.cross_diffusion.v.jacobian.v.expression": "0.02*v"}
+    om = K.CASES[name].oracle(**over)
+    rowptr, colidx = om.pattern()
+    n, ns = om.ndofs, 2
+    x = K.rand_state(n, 3)
+    for form in (0, 1):
+        va, vf = np.zeros(colidx.size), np.zeros(colidx.size)
+        om.jacobian(form, 0.3, 1.0, x, rowptr, colidx, va)
+        om.jacobian(form, 0.3, 1.0, x, rowptr, colidx, vf, numerical=True, eps=1e-7)
+        A = sp.csr_matrix((va, colidx, rowptr), shape=(n, n)).toarray().reshape(n // ns, ns, n // ns, ns)
+        F = sp.csr_matrix((vf, colidx, rowptr), shape=(n, n)).toarray().reshape(n // ns, ns, n // ns, ns)
+        assert np.abs(A - F.transpose(2, 1, 0, 3)).max() <= 1e-6 * np.abs(F).max()
+        if form == 0:
+            assert np.abs(A - F).max() > 1e-2 * np.abs(F).max()      # ... and it is not the derivative itself
+    # matrix-free application == assembled matrix
+    z, y, va = K.rand_state(n, 4, -1, 1), np.zeros(n), np.zeros(colidx.size)
+    om.jacobian_apply(0, 0.3, 1.0, x, z, y)
+    om.jacobian(0, 0.3, 1.0, x, rowptr, colidx, va)
+    assert np.abs(sp.csr_matrix((va, colidx, rowptr), shape=(n, n)) @ z - y).max() <= 1e-13 * np.abs(y).max()
+
+
+def test_advection_element_identity():
+    """Constant velocity w on one simplex: r_a = -|T| mean(u) (w . grad phi_a), exact under the order-2 rule."""
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-1, 1, (3, 2))
+    mesh = OMESH.Mesh(dim=2, coords=X, elems=np.arange(3, dtype=np.int32)[None, :])
+    cfg = INI.parse_ini("[compartments.domain]\nexpression = 1\n[model.scalar_field.u]\ncompartment = domain\n"
+                        "velocity.x.expression = 0.7\nvelocity.y.expression = -0.4\n")
+    om = ORC.Model(cfg, mesh)
+    u = rng.uniform(0.5, 1.5, 3)
+    r = np.zeros(3)
+    om.residual(0, 0.0, 1.0, u, r)
+    B = np.array([X[1] - X[0], X[2] - X[0]]).T
+    area = abs(np.linalg.det(B)) / 2
+    Ginv = np.linalg.inv(B)                     # rows: grad phi_1, grad phi_2
+    G = np.vstack([-Ginv.sum(axis=0), Ginv])
+    expect = -area * u.mean() * (G @ np.array([0.7, -0.4]))
+    assert np.abs(r - expect).max() <= 1e-14
 
 
 @pytest.mark.parametrize("dim", [2, 3])
