@@ -162,6 +162,24 @@ struct DcFacet {
     c.integration_factor = factor;
     return factor;
   }
+
+  // own-side facet residual loc[s][m] = wA sum_q T_s lam_m factor   (local_operator.hh:920-927)
+  __device__ __forceinline__ void residual(double wA, double (*loc)[DC_DIM]) {
+#pragma unroll
+    for (int s = 0; s < NSS; ++s)
+#pragma unroll
+      for (int m = 0; m < DC_DIM; ++m) loc[s][m] = 0.0;
+#pragma unroll
+    for (int q = 0; q < DC_DIM; ++q) {
+      double us[NSS], ut[NST], T[NSS];
+      const double factor = point(q, us, ut);
+      O::flux(c, us, gs, ut, gt, T);
+#pragma unroll
+      for (int s = 0; s < NSS; ++s)
+#pragma unroll
+        for (int m = 0; m < DC_DIM; ++m) loc[s][m] += wA * T[s] * lam(q, m) * factor;
+    }
+  }
 };
 
 template <int P>
@@ -171,24 +189,50 @@ __device__ __forceinline__ void dc_skeleton_residual(const DcFacetArgs& a) {
   long long f;
   if (!F.load(a, &f)) return;
   double loc[O::NSS][DC_DIM];
-#pragma unroll
-  for (int s = 0; s < O::NSS; ++s)
-#pragma unroll
-    for (int m = 0; m < DC_DIM; ++m) loc[s][m] = 0.0;
-#pragma unroll
-  for (int q = 0; q < DC_DIM; ++q) {
-    double us[O::NSS], ut[O::NST], T[O::NSS];
-    const double factor = F.point(q, us, ut);
-    O::flux(F.c, us, F.gs, ut, F.gt, T);
-#pragma unroll
-    for (int s = 0; s < O::NSS; ++s)
-#pragma unroll
-      for (int m = 0; m < DC_DIM; ++m) loc[s][m] += a.wA * T[s] * F.lam(q, m) * factor;
-  }
+  F.residual(a.wA, loc);
 #pragma unroll
   for (int s = 0; s < O::NSS; ++s)
 #pragma unroll
     for (int m = 0; m < DC_DIM; ++m) dc_atomic_add(&a.r[F.dofs[m] + s], loc[s][m]);
+}
+
+// Numerical skeleton / boundary Jacobian (local_operator.hh:1205-1343): one-sided differences of
+// the own-side facet residual with respect to the coefficients of both sides at the facet's
+// vertices, delta = eps (1 + |x|).  `sink(i, ma, other, j, mb, value)`: other = 0 own-side column.
+// Only the species pairs of the skeleton pattern are kept.
+template <int P, class Sink>
+__device__ __noinline__ void dc_fd_skeleton(DcFacet<P>& F, double wA, Sink sink) {
+  typedef DcOutflow<P> O;
+  double down[O::NSS][DC_DIM], up[O::NSS][DC_DIM];
+  F.residual(wA, down);
+#pragma unroll 1
+  for (int side = 0; side < (O::BOUNDARY ? 1 : 2); ++side) {
+    const int nsp = side == 0 ? O::NSS : O::NST_REAL;
+#pragma unroll 1
+    for (int j = 0; j < nsp; ++j)
+#pragma unroll 1
+      for (int mb = 0; mb < DC_DIM; ++mb) {
+        double* coef = side == 0 ? &F.xs[j][mb] : &F.xt[j][mb];
+        double* grad = side == 0 ? F.gs[j] : F.gt[j];
+        const double* shape = side == 0 ? F.Gs[F.fs[mb]] : F.Gt[F.ft[mb]];
+        const double keep = *coef;
+        double gkeep[DC_DIM];
+        const double delta = DC_FD_EPS * (1.0 + fabs(keep));
+        *coef = keep + delta;
+#pragma unroll
+        for (int k = 0; k < DC_DIM; ++k) { gkeep[k] = grad[k]; grad[k] += delta * shape[k]; }
+        F.residual(wA, up);
+#pragma unroll 1
+        for (int i = 0; i < O::NSS; ++i) {
+          if (side == 0 ? !O::pair_s(i, j) : !O::pair_t(i, j)) continue;
+#pragma unroll 1
+          for (int ma = 0; ma < DC_DIM; ++ma) sink(i, ma, side, j, mb, (up[i][ma] - down[i][ma]) / delta);
+        }
+        *coef = keep;
+#pragma unroll
+        for (int k = 0; k < DC_DIM; ++k) grad[k] = gkeep[k];
+      }
+  }
 }
 
 // MODE 0: CSR values; 1: y += J z; 2: block diagonal
@@ -198,6 +242,21 @@ __device__ __forceinline__ void dc_skeleton_jacobian(const DcFacetArgs& a) {
   DcFacet<P> F;
   long long f;
   if (!F.load(a, &f)) return;
+  if (DC_NUMJAC) {
+    dc_fd_skeleton<P>(F, a.wA, [&](int i, int ma, int other, int j, int mb, double v) {
+      const int row = F.dofs[ma] + i;
+      const int col = (other ? F.doft[mb] : F.dofs[mb]) + j;
+      if (MODE == 0) {
+        const long long p = dc_csr_find(a.rowptr, a.colidx, row, col);
+        if (p >= 0) dc_atomic_add(&a.vals[p], v);
+      } else if (MODE == 1) {
+        dc_atomic_add(&a.r[row], v * ((a.cmask && a.cmask[col]) ? 0.0 : a.z[col]));
+      } else if (!other && ma == mb) {
+        dc_atomic_add(&a.bdiag[(long long)F.dofs[ma] * O::NSS + i * O::NSS + j], v);
+      }
+    });
+    return;
+  }
 #pragma unroll 1
   for (int q = 0; q < DC_DIM; ++q) {
     double us[O::NSS], ut[O::NST], js[O::NSS][O::NSS], jt[O::NSS][O::NST];

@@ -132,8 +132,6 @@ Model::Model(const PTree& cfg_, int dim_, const std::vector<std::string>& keys)
         }
     }
   }
-  if (numerical_jacobian && has_outflow())
-    fail("model.jacobian.type = numerical with outflow terms (local_operator.hh:1205-1343) is not built");
 }
 
 int Model::species_index(const std::string& name) const {

@@ -21,8 +21,8 @@ LinearSolver::LinearSolver(std::shared_ptr<DeviceOperator> op, const PTree& cfg,
   if (prec_type != "Jacobi" && prec_type != "BlockJacobi" && prec_type != "Richardson")
     fail("linear_solver.preconditioner.type = '", prec_type,
          "' is not built for the B200 path (available: Richardson, Jacobi, BlockJacobi)");
-  if (cfg.get("preconditioner.iterations", 1) != 1)
-    fail("linear_solver.preconditioner.iterations != 1 is not built");
+  prec_iterations = cfg.get("preconditioner.iterations", 1);
+  if (prec_iterations < 1) fail("linear_solver.preconditioner.iterations must be >= 1");
   relaxation = cfg.get("preconditioner.relaxation", 1.0);
   matrix_free = cfg.get("matrix_free", false);
   verbosity = cfg.get("verbosity", 0);
@@ -34,6 +34,8 @@ LinearSolver::LinearSolver(std::shared_ptr<DeviceOperator> op, const PTree& cfg,
   hscal_.alloc(gmres ? std::max(8, restart + 2) : 8);
   const int nwork = type == "BiCGSTAB" ? 6 : 2;
   for (int k = 0; k < nwork; ++k) work_[k].alloc(op_->ndofs);
+  if (prec_iterations > 1 && prec_type != "Richardson")
+    for (auto& w : sweep_) w.alloc(op_->ndofs);
   if (gmres) basis_.alloc((int64_t)(restart + 1) * op_->ndofs);   // Krylov basis v_0 .. v_m
   if (!matrix_free) {
     op_->ensure_csr();
@@ -105,7 +107,27 @@ void LinearSolver::apply_operator(const double* v, double* y) {
   }
 }
 
+// v = 0, then `prec_iterations` sweeps (preconditioner.iterations):
+//   Jacobi (dune-istl SeqJac):  v += w D^-1 (d - A v), old iterate in every row;
+//   BlockJacobi (block_jacobi.hh:102-127 as written): the copy of the right-hand side is modified
+//   cumulatively, b_k = b_{k-1} - A v_{k-1} -- the true defect for the first two sweeps only.
 void LinearSolver::precondition(const double* d, double* v) {
+  precondition_sweep(d, v);
+  if (prec_iterations <= 1 || prec_type == "Richardson") return;
+  cudaStream_t s = op_->stream;
+  const int64_t n = op_->ndofs;
+  double *b = sweep_[0].p, *t = sweep_[1].p, *c = sweep_[2].p;
+  auto& L = op_->stats.launches;
+  if (prec_type == "BlockJacobi") { la::copy(n, d, b, s); L++; }
+  for (int it = 1; it < prec_iterations; ++it) {
+    apply_operator(v, t);
+    { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::sub(n, prec_type == "Jacobi" ? d : b, t, b, s); L++; }
+    precondition_sweep(b, c);
+    { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::axpy(n, 1.0, c, v, s); L++; }
+  }
+}
+
+void LinearSolver::precondition_sweep(const double* d, double* v) {
   cudaStream_t s = op_->stream;
   DeviceOperator::ProfScope ps(op_.get(), "precond");
   const Grid& g = *op_->grid;
@@ -155,7 +177,7 @@ SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
   if (type == "BiCGSTAB") {
     double *rt = work_[0].p, *p = work_[1].p, *v = work_[2].p, *t = work_[3].p, *y = work_[4].p, *y2 = work_[5].p;
     // Jacobi is folded into the sweeps that produce its argument; other preconditioners run on their own
-    const double* fold = prec_type == "Jacobi" ? dinv_.p : nullptr;
+    const double* fold = prec_type == "Jacobi" && prec_iterations == 1 ? dinv_.p : nullptr;
     { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::copy(n, r, rt, s); L++; }
     { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, r, r, scal_.p, ws_, s); L++; }
     fetch(1);

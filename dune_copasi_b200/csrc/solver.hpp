@@ -45,11 +45,13 @@ class LinearSolver {
   int max_iterations = 500;
   int restart = 40;              // RestartedGMRes: Krylov space dimension between restarts
   double relaxation = 1.0;
+  int prec_iterations = 1;       // preconditioner.iterations (sweeps per application)
   int verbosity = 0;
   DeviceBuffer<double> vals;     // CSR values of the current linearisation (matrix based)
 
  private:
   void precondition(const double* d, double* v);
+  void precondition_sweep(const double* d, double* v);   // one sweep from v = 0
   double reduce1(double* dev2);             // host value of scal_[0] after a reduction
   void fetch(int n);
   void fetch_slots(int first, int count, int total);
@@ -58,7 +60,7 @@ class LinearSolver {
   la::ReduceWorkspace ws_;
   DeviceBuffer<double> scal_;               // device scalars of the reductions
   PinnedBuffer<double> hscal_;
-  DeviceBuffer<double> dinv_, bdiag_, work_[6], basis_;
+  DeviceBuffer<double> dinv_, bdiag_, work_[6], basis_, sweep_[3];
   // linearisation point
   double t_ = 0, wM_ = 0, wA_ = 0;
   const double* x_ = nullptr;

@@ -402,7 +402,12 @@ class Model:
             L.orc_jacobian_volume(C.byref(self.cmesh), C.byref(self.cmodel), C.c_int(form), C.c_double(time),
                                   C.c_double(w), _p(x, C.c_double), _p(rowptr, C.c_int64),
                                   _p(colidx, C.c_int32), _p(vals, C.c_double), C.c_int(par))
-        if form == 0 and self.has_outflow:
+        if form == 0 and self.has_outflow and numerical:
+            L.orc_jacobian_skeleton_numerical(C.byref(self.cmesh), C.byref(self.cmodel), C.c_double(time),
+                                              C.c_double(w), C.c_double(eps), C.c_int64(self.ndofs),
+                                              _p(x, C.c_double), _p(rowptr, C.c_int64),
+                                              _p(colidx, C.c_int32), _p(vals, C.c_double))
+        elif form == 0 and self.has_outflow:
             L.orc_jacobian_skeleton(C.byref(self.cmesh), C.byref(self.cmodel), C.c_double(time),
                                     C.c_double(w), _p(x, C.c_double), _p(rowptr, C.c_int64),
                                     _p(colidx, C.c_int32), _p(vals, C.c_double))
@@ -448,6 +453,7 @@ def linear_solve(rowptr, colidx, vals, b, cfg: dict, rel_tol: float, par=0):
     maxit = int(str(INI.get(cfg, "convergence_condition.iteration_range", "1 500")).split()[-1])
     res = CResult()
     L = lib()
+    L.orc_set_preconditioner_iterations(C.c_int(int(pc.get("iterations", 1))))   # preconditioner.hh:96-113
     if typ == "RestartedGMRes":
         restart = int(cfg.get("restart", 40))          # factory/iterative.hh:64
         L.orc_gmres(C.c_int64(n), _p(rowptr, C.c_int64), _p(colidx, C.c_int32), _p(vals, C.c_double),

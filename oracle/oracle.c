@@ -615,13 +615,13 @@ static int facet_quad(int dim, double lam[][3], double* wts) {
 }
 
 /* mode 0: residual r += w*T ; mode 1: jacobian into sink */
-static void skeleton(const OrcMesh* M, const OrcModel* P, double time, double w, const double* x,
-                     double* r, const Sink* S, int mode) {
+static void skeleton_range(const OrcMesh* M, const OrcModel* P, double time, double w, const double* x,
+                           double* r, const Sink* S, int mode, int64_t f_begin, int64_t f_end) {
   const int dim = M->dim, nd = dim + 1;
   double lam[3][3], qw[3];
   const int nq = facet_quad(dim, lam, qw);
   double* ctx = (double*)calloc(P->nslots, sizeof(double));
-  for (int64_t f = 0; f < M->nf; ++f) {
+  for (int64_t f = f_begin; f < f_end; ++f) {
     int64_t ei = M->f_in[f], eo = M->f_out[f];
     int ci = M->elem_comp[ei], co = eo >= 0 ? M->elem_comp[eo] : -1;
     if (eo >= 0 && ci == co) continue;
@@ -682,6 +682,11 @@ static void skeleton(const OrcMesh* M, const OrcModel* P, double time, double w,
   free(ctx);
 }
 
+static void skeleton(const OrcMesh* M, const OrcModel* P, double time, double w, const double* x,
+                     double* r, const Sink* S, int mode) {
+  skeleton_range(M, P, time, w, x, r, S, mode, 0, M->nf);
+}
+
 void orc_residual_skeleton(const OrcMesh* M, const OrcModel* P, double time, double w,
                            const double* x, double* r) {
   skeleton(M, P, time, w, x, r, 0, 0);
@@ -695,6 +700,61 @@ void orc_jacobian_apply_skeleton(const OrcMesh* M, const OrcModel* P, double tim
                                  const double* x, const double* z, double* y) {
   Sink S = {1, 0, 0, 0, z, y, 0};
   skeleton(M, P, time, w, x, 0, &S, 1);
+}
+
+/* numerical skeleton / boundary Jacobian, local_operator.hh:1205-1343: one-sided differences of the
+ * facet residual, column by column over the coefficients of both sides, delta = eps (1 + |x_col|).
+ * Columns are the dofs at the facet's vertices (the links of the skeleton pattern); entries
+ * outside the pattern are dropped.  Deviation: for out-side columns the reference sizes delta
+ * with `coeff_in` read at the out-side node (:1298), an index mix-up; the out-side coefficient
+ * itself is used here.  `n` = number of dofs. */
+void orc_jacobian_skeleton_numerical(const OrcMesh* M, const OrcModel* P, double time, double w, double eps,
+                                     int64_t n, const double* x, const int64_t* rowptr,
+                                     const int32_t* colidx, double* vals) {
+  const int dim = M->dim, nd = dim + 1;
+  double* xw = (double*)malloc(8 * n);
+  double* down = (double*)calloc(n, 8);
+  double* up = (double*)calloc(n, 8);
+  memcpy(xw, x, 8 * n);
+  for (int64_t f = 0; f < M->nf; ++f) {
+    int64_t ei = M->f_in[f], eo = M->f_out[f];
+    int ci = M->elem_comp[ei], co = eo >= 0 ? M->elem_comp[eo] : -1;
+    if (eo >= 0 && ci == co) continue;
+    int64_t dofs[2 * 3 * 32];
+    int nd_f = 0;
+    for (int side = 0; side < 2; ++side) {
+      int64_t e = side == 0 ? ei : eo;
+      int c = side == 0 ? ci : co;
+      if (e < 0 || c < 0) continue;
+      int m = side == 0 ? M->f_lin[f] : M->f_lout[f];
+      int ns = P->comp_ptr[c + 1] - P->comp_ptr[c];
+      for (int a = 0; a < nd; ++a)
+        if (a != m)
+          for (int s = 0; s < ns; ++s) dofs[nd_f++] = M->elem_dof[e * nd + a] + s;
+    }
+    for (int k = 0; k < nd_f; ++k) down[dofs[k]] = 0.0;
+    skeleton_range(M, P, time, 1.0, xw, down, 0, 0, f, f + 1);
+    for (int cidx = 0; cidx < nd_f; ++cidx) {
+      int64_t col = dofs[cidx];
+      double keep = xw[col], delta = eps * (1.0 + fabs(keep));
+      xw[col] = keep + delta;
+      for (int k = 0; k < nd_f; ++k) up[dofs[k]] = 0.0;
+      skeleton_range(M, P, time, 1.0, xw, up, 0, 0, f, f + 1);
+      for (int k = 0; k < nd_f; ++k) {
+        int64_t row = dofs[k];
+        double v = (up[row] - down[row]) / delta;
+        if (v == 0.0) continue;
+        int64_t lo = rowptr[row], hi = rowptr[row + 1] - 1;
+        while (lo <= hi) {
+          int64_t mid = (lo + hi) >> 1;
+          if (colidx[mid] == col) { vals[mid] += w * v; break; }
+          if (colidx[mid] < col) lo = mid + 1; else hi = mid - 1;
+        }
+      }
+      xw[col] = keep;
+    }
+  }
+  free(xw); free(down); free(up);
 }
 
 /* ---------------------------------------------------------------- linear algebra (dune-istl order) */
@@ -717,11 +777,19 @@ static double dot(int64_t n, const double* a, const double* b, int par) {
 
 /* preconditioner: kind 0 none (Richardson w=1), 1 Jacobi (SeqJac, 1 sweep from v=0: v = w D^-1 d),
  * 2 BlockJacobi with node blocks of size bs (block_jacobi.hh:46-128 with iterations=1: v = w Dblk^-1 d) */
-typedef struct { int kind, bs; double relax; double* dinv; int64_t n; } Prec;
+typedef struct {
+  int kind, bs; double relax; double* dinv; int64_t n;
+  int iters; const int64_t* rowptr; const int32_t* colidx; const double* vals;   /* sweeps > 1 */
+} Prec;
+
+/* `preconditioner.iterations` of the next solver calls (kept out of the solver signatures) */
+static int g_prec_iters = 1;
+void orc_set_preconditioner_iterations(int iters) { g_prec_iters = iters < 1 ? 1 : iters; }
 
 static void prec_setup(Prec* Pc, int64_t n, const int64_t* rowptr, const int32_t* colidx,
                        const double* vals) {
   Pc->n = n;
+  Pc->iters = g_prec_iters; Pc->rowptr = rowptr; Pc->colidx = colidx; Pc->vals = vals;
   if (Pc->kind == 1) {
     Pc->dinv = (double*)malloc(sizeof(double) * n);
     for (int64_t i = 0; i < n; ++i) {
@@ -764,7 +832,29 @@ static void prec_setup(Prec* Pc, int64_t n, const int64_t* rowptr, const int32_t
     Pc->dinv = 0;
 }
 
+static void prec_sweep(const Prec* Pc, const double* d, double* v);
+
+/* v = 0, then `iters` sweeps.
+ * Jacobi = dune-istl SeqJac: v += w D^-1 (d - A v) with the old iterate in every row.
+ * BlockJacobi = block_jacobi.hh:102-127 as written: the right-hand side copy is modified
+ * cumulatively, b_k = b_{k-1} - A v_{k-1}, which is the true defect only for the first two sweeps. */
 static void prec_apply(const Prec* Pc, const double* d, double* v) {
+  prec_sweep(Pc, d, v);
+  if (Pc->iters <= 1 || Pc->kind == 0) return;
+  int64_t n = Pc->n;
+  double *b = malloc(8 * n), *t = malloc(8 * n), *c = malloc(8 * n);
+  memcpy(b, d, 8 * n);
+  for (int it = 1; it < Pc->iters; ++it) {
+    orc_spmv(n, Pc->rowptr, Pc->colidx, Pc->vals, v, t, 0);
+    if (Pc->kind == 1) for (int64_t i = 0; i < n; ++i) b[i] = d[i] - t[i];
+    else for (int64_t i = 0; i < n; ++i) b[i] -= t[i];
+    prec_sweep(Pc, b, c);
+    for (int64_t i = 0; i < n; ++i) v[i] += c[i];
+  }
+  free(b); free(t); free(c);
+}
+
+static void prec_sweep(const Prec* Pc, const double* d, double* v) {
   int64_t n = Pc->n;
   if (Pc->kind == 0) { for (int64_t i = 0; i < n; ++i) v[i] = d[i]; }
   else if (Pc->kind == 1) { for (int64_t i = 0; i < n; ++i) v[i] = Pc->relax * Pc->dinv[i] * d[i]; }
@@ -785,7 +875,7 @@ typedef struct { int32_t iterations_x2; int32_t converged; double reduction; dou
 void orc_bicgstab(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* vals,
                   double* x, double* b, double reduction, int maxit, int prec_kind, int bs,
                   double relax, int par, OrcResult* res) {
-  Prec Pc = {prec_kind, bs, relax, 0, 0};
+  Prec Pc = {prec_kind, bs, relax, 0, 0, 1, 0, 0, 0};
   prec_setup(&Pc, n, rowptr, colidx, vals);
   double *r = b, *rt = malloc(8 * n), *p = calloc(n, 8), *v = calloc(n, 8), *t = malloc(8 * n),
          *y = malloc(8 * n);
@@ -831,7 +921,7 @@ done:
 void orc_cg(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* vals, double* x,
             double* b, double reduction, int maxit, int prec_kind, int bs, double relax, int par,
             OrcResult* res) {
-  Prec Pc = {prec_kind, bs, relax, 0, 0};
+  Prec Pc = {prec_kind, bs, relax, 0, 0, 1, 0, 0, 0};
   prec_setup(&Pc, n, rowptr, colidx, vals);
   double *r = b, *p = malloc(8 * n), *q = malloc(8 * n);
   orc_spmv(n, rowptr, colidx, vals, x, q, par);
@@ -879,7 +969,7 @@ static void givens_apply(double* dx, double* dy, double cs, double sn) {
 void orc_gmres(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* vals, double* x,
                double* b, double reduction, int maxit, int restart, int prec_kind, int bs, double relax,
                int par, OrcResult* res) {
-  Prec Pc = {prec_kind, bs, relax, 0, 0};
+  Prec Pc = {prec_kind, bs, relax, 0, 0, 1, 0, 0, 0};
   prec_setup(&Pc, n, rowptr, colidx, vals);
   const int m = restart;
   double* V = malloc(sizeof(double) * (size_t)(m + 1) * n);

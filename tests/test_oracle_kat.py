@@ -131,6 +131,19 @@ def test_extended_terms_jacobian_is_the_vertex_swapped_derivative(name):
     assert np.abs(sp.csr_matrix((va, colidx, rowptr), shape=(n, n)) @ z - y).max() <= 1e-13 * np.abs(y).max()
 
 
+@pytest.mark.parametrize("name", ["cell3d", "two_disks"])
+def test_numerical_skeleton_jacobian_matches_analytic(name):
+    """Finite differences of the facet residual (local_operator.hh:1205-1343) reproduce the analytic
+    transmission Jacobian (:973-1199) -- pins the residual/Jacobian pair of the outflow terms."""
+    om = K.CASES[name].oracle()
+    rowptr, colidx = om.pattern()
+    x = K.rand_state(om.ndofs, 6)
+    va, vf = np.zeros(colidx.size), np.zeros(colidx.size)
+    om.jacobian(0, 0.2, 1.0, x, rowptr, colidx, va)
+    om.jacobian(0, 0.2, 1.0, x, rowptr, colidx, vf, numerical=True, eps=1e-7)
+    assert np.abs(va - vf).max() <= 2e-6 * np.abs(va).max()
+
+
 def test_advection_element_identity():
     """Constant velocity w on one simplex: r_a = -|T| mean(u) (w . grad phi_a), exact under the order-2 rule."""
     rng = np.random.default_rng(5)
