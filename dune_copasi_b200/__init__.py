@@ -3,4 +3,5 @@
 The product is the C++/CUDA library ``libdune_copasi_b200.so`` (include/dune_copasi_b200.h);
 this package only holds its sources, the in-tree build and a ctypes binding of the C ABI.
 """
-from .capi import (Comm, Config, DcbError, Grid, Model, Operator, Solver, Stepper, lib)  # noqa: F401
+from .capi import (Comm, Config, DcbError, Grid, Model, Operator, Reducer, ReductionError, Solver,  # noqa: F401
+                   Stepper, lib)

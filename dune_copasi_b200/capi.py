@@ -104,6 +104,13 @@ SYMBOLS = {
     "dcb_stepper_step": (C.c_int, [_P, C.c_double, C.POINTER(C.c_int)]),
     "dcb_stepper_evolve": (C.c_int, [_P, C.c_double, _D, C.c_int, C.POINTER(C.c_int)]),
     "dcb_stepper_stats": (C.c_int, [_P, C.POINTER(StepStats)]),
+    "dcb_reducer_create": (_P, [_P, _P, _P]),
+    "dcb_reducer_destroy": (None, [_P]),
+    "dcb_reducer_num_keys": (C.c_int, [_P]),
+    "dcb_reducer_key": (C.c_char_p, [_P, C.c_int]),
+    "dcb_reducer_apply": (C.c_int, [_P, C.c_double, _D, _D, _I32]),
+    "dcb_reducer_apply_dev": (C.c_int, [_P, C.c_double, _P, _D, _I32]),
+    "dcb_model_precompile_reduce": (C.c_int, [_P, _P]),
     "dcb_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "dcb_grid_partition": (_P, [_P, C.c_int, C.c_int]),
     "dcb_grid_num_owned_vertices": (C.c_int64, [_P]),
@@ -322,8 +329,10 @@ class Model:
             raise DcbError(lib().dcb_last_error().decode())
         return s.decode()
 
-    def precompile(self):
+    def precompile(self, reduce_config: "Config | None" = None):
         _check(lib().dcb_model_precompile(self.h))
+        if reduce_config is not None:
+            _check(lib().dcb_model_precompile_reduce(self.h, reduce_config.h))
 
     def compile(self, ptx=False) -> bytes:
         n = lib().dcb_model_compile(self.h, 1 if ptx else 0, None, 0)
@@ -490,3 +499,43 @@ class Stepper:
     def __del__(self):
         if getattr(self, "h", None) and _lib is not None:
             _lib.dcb_stepper_destroy(self.h)
+
+
+class ReductionError(DcbError):
+    """An error.expression of [model.reduce] fired (the reference's ReductionError, reduce.hh:36)."""
+
+
+class Reducer:
+    """[model.reduce] functionals; `apply` returns {key: value} and raises ReductionError like the
+    reference when an error expression fires (values and statuses stay readable in .values/.status)."""
+
+    def __init__(self, op: Operator, config: Config, comm: Comm | None = None):
+        self.op = op
+        self.h = _ptr(lib().dcb_reducer_create(op.h, config.h, comm.h if comm else None), "reducer")
+        n = lib().dcb_reducer_num_keys(self.h)
+        self.keys = [lib().dcb_reducer_key(self.h, k).decode() for k in range(n)]
+        self.values, self.status = {}, {}
+
+    def _finish(self, rc, vals, stat, raise_on_error):
+        if rc == 1:
+            raise DcbError(lib().dcb_last_error().decode())
+        self.values = dict(zip(self.keys, vals.tolist()))
+        self.status = dict(zip(self.keys, stat.tolist()))
+        if rc == 2 and raise_on_error:
+            raise ReductionError(lib().dcb_last_error().decode())
+        return self.values
+
+    def apply(self, time, x, raise_on_error=True):
+        x = _f64(x)
+        vals, stat = np.zeros(len(self.keys)), np.zeros(len(self.keys), dtype=np.int32)
+        rc = lib().dcb_reducer_apply(self.h, time, _d(x), _d(vals), stat.ctypes.data_as(_I32))
+        return self._finish(rc, vals, stat, raise_on_error)
+
+    def apply_dev(self, time, x_dev, raise_on_error=True):
+        vals, stat = np.zeros(len(self.keys)), np.zeros(len(self.keys), dtype=np.int32)
+        rc = lib().dcb_reducer_apply_dev(self.h, time, x_dev, _d(vals), stat.ctypes.data_as(_I32))
+        return self._finish(rc, vals, stat, raise_on_error)
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.dcb_reducer_destroy(self.h)

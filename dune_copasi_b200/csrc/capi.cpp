@@ -9,6 +9,7 @@
 #include "jit.hpp"
 #include "model.hpp"
 #include "operator.hpp"
+#include "reduce.hpp"
 #include "solver.hpp"
 #include "stepper.hpp"
 
@@ -39,6 +40,11 @@ struct dcb_stepper {
   dcb_operator* op;
   DeviceBuffer<double> u;
   double time = 0;
+};
+struct dcb_reducer {
+  std::unique_ptr<Reducer> r;
+  dcb_operator* op;
+  DeviceBuffer<double> x;
 };
 
 namespace {
@@ -381,6 +387,47 @@ int dcb_stepper_stats(const dcb_stepper* s, dcb_step_stats* o) {
   o->residual_evaluations = st.residual_evaluations; o->linearizations = st.linearizations;
   o->kernel_launches = s->op->op->stats.launches;
   return 0;
+}
+
+// ---- reduce
+dcb_reducer* dcb_reducer_create(dcb_operator* o, const dcb_config* cfg, dcb_comm* comm) {
+  return guard_new<dcb_reducer>([&] {
+    auto* r = new dcb_reducer();
+    r->op = o;
+    r->r = std::make_unique<Reducer>(o->op, cfg->tree, comm ? comm->c.get() : nullptr);
+    return r;
+  });
+}
+void dcb_reducer_destroy(dcb_reducer* r) { delete r; }
+int dcb_reducer_num_keys(const dcb_reducer* r) { return r->r->size(); }
+const char* dcb_reducer_key(const dcb_reducer* r, int k) {
+  return k >= 0 && k < r->r->size() ? r->r->key(k).c_str() : nullptr;
+}
+static int reducer_apply(dcb_reducer* r, double time, const double* x_dev, double* values, int32_t* status) {
+  int rc = 0;
+  int g = guard([&] {
+    auto out = r->r->apply(time, x_dev, false);
+    std::string msg;
+    for (size_t k = 0; k < out.size(); ++k) {
+      if (values) values[k] = out[k].value;
+      if (status) status[k] = out[k].status;
+      if (out[k].status == 2) rc = 2;
+    }
+    if (rc == 2) g_error = r->r->last_error;   // the reference's ReductionError text (reduce.hh:241-247)
+  });
+  return g ? 1 : rc;
+}
+int dcb_reducer_apply_dev(dcb_reducer* r, double time, const double* x_dev, double* values, int32_t* status) {
+  return reducer_apply(r, time, x_dev, values, status);
+}
+int dcb_reducer_apply(dcb_reducer* r, double time, const double* x_host, double* values, int32_t* status) {
+  int g = guard([&] {
+    r->x.upload(x_host, r->op->op->ndofs, r->op->op->stream);
+  });
+  return g ? 1 : reducer_apply(r, time, r->x.p, values, status);
+}
+int dcb_model_precompile_reduce(dcb_model* m, const dcb_config* cfg) {
+  return guard([&] { Reducer::precompile(*m->m, cfg->tree); });
 }
 
 // ---- multi GPU

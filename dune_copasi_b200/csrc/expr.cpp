@@ -320,6 +320,23 @@ bool is_cmp(Op op) {
 
 }  // namespace
 
+ParserContext::Fn parse_function_expression(const std::string& e, const std::string& what) {
+  auto colon = e.find(':');
+  if (colon == std::string::npos) fail(what, ": function needs 'args: body'");
+  ParserContext::Fn fn;
+  std::string head = e.substr(0, colon);
+  size_t p = 0;
+  while (p <= head.size()) {
+    size_t q = head.find(',', p);
+    if (q == std::string::npos) q = head.size();
+    std::string a = trim(head.substr(p, q - p));
+    if (!a.empty()) fn.args.push_back(a);
+    p = q + 1;
+  }
+  fn.body = trim(e.substr(colon + 1));
+  return fn;
+}
+
 ParserContext ParserContext::from_config(const PTree& pc) {
   ParserContext ctx;
   for (auto& name : pc.sub_keys()) {
@@ -328,21 +345,7 @@ ParserContext ParserContext::from_config(const PTree& pc) {
     if (type == "constant") {
       ctx.constants[name] = s.get("value", 0.0);
     } else if (type == "function") {
-      std::string e = s.get("expression", std::string());
-      auto colon = e.find(':');
-      if (colon == std::string::npos) fail("parser_context.", name, ": function needs 'args: body'");
-      Fn fn;
-      std::string head = e.substr(0, colon);
-      size_t p = 0;
-      while (p <= head.size()) {
-        size_t q = head.find(',', p);
-        if (q == std::string::npos) q = head.size();
-        std::string a = trim(head.substr(p, q - p));
-        if (!a.empty()) fn.args.push_back(a);
-        p = q + 1;
-      }
-      fn.body = trim(e.substr(colon + 1));
-      ctx.functions[name] = fn;
+      ctx.functions[name] = parse_function_expression(s.get("expression", std::string()), "parser_context." + name);
     } else if (!type.empty()) {
       // interpolation / tiff / random_field context entries are outside the hot path
       fail("parser_context.", name, ": type '", type, "' is not supported by this build");

@@ -38,6 +38,9 @@ struct ParserContext {
   static ParserContext from_config(const PTree& parser_context);
 };
 
+// "a, b: body" (ParserContext::parse_function_expression, src/dune/copasi/parser/context.cc)
+ParserContext::Fn parse_function_expression(const std::string& text, const std::string& what);
+
 // true when the expression is empty or a literal zero: the term does not exist
 // (functor_factory_parser.impl.hh:122-124)
 bool expr_is_absent(const std::string& text);

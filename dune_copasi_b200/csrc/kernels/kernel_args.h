@@ -82,4 +82,19 @@ struct DcFacetArgs {
   const unsigned char* cmask;
 };
 
+struct DcReduceArgs {
+  const double* coords;
+  const int* elems;
+  const int* elem_ids;         // elements of this launch (one compartment, or the cells outside all)
+  const int* vdof;             // vertex -> dof of species 0 of the compartment (null: offset + v*NS)
+  const double* cell;
+  long long ne_total;
+  long long n;
+  int dof_offset;
+  double time;
+  const double* x;
+  const double* init;          // [DC_NRED] start value of every functional (its neutral element)
+  double* partials;            // [gridDim.x][DC_NRED]
+};
+
 #endif

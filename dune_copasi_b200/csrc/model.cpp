@@ -252,6 +252,11 @@ struct SymbolMap {
 
 }  // namespace
 
+std::string Model::lower_volume(const NodeP& ast, int c) const {
+  SymbolMap sym{*this, (c >= 0 && c < ncomp()) ? c : -2, -1, false};
+  return to_cuda(ast, sym);
+}
+
 static bool depends_on_point(const NodeP& ast) {
   std::vector<std::string> v;
   collect_vars(ast, v);

@@ -72,6 +72,9 @@ class Model {
 
   // CUDA source of the per-model device functions (see kernels/assembly.cuh for the consumers)
   std::string cuda_source() const;
+  // CUDA text of one resolved expression in the volume context of compartment c (symbols `c`, `u`,
+  // `g` as in DcComp<C>::scalar); species without support there read 0, c outside [0, ncomp) = no compartment
+  std::string lower_volume(const NodeP& ast, int c) const;
 };
 
 }  // namespace dcb

@@ -97,6 +97,7 @@ class DeviceOperator {
   };
 
  private:
+  friend class Reducer;   // [model.reduce] functionals read the device-resident mesh
   struct ProfRec { std::string kind; cudaEvent_t a = nullptr, b = nullptr; };
   bool profiling_ = false;
   std::vector<ProfRec> prof_;

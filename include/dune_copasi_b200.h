@@ -15,9 +15,10 @@
  *   dcb_grid_pattern       <- basisToPattern + patternToMatrix       make_step_operator.hh:378-384
  *                             = localAssemblePattern{Volume,Skeleton,Boundary}     :276-399
  *   dcb_solver_*           <- LinearSolver::apply                    make_step_operator.hh:102-146
- *                             (dune-istl BiCGSTAB/CG + Jacobi/BlockJacobi, solver/istl/**)
+ *                             (dune-istl BiCGSTAB/CG/RestartedGMRes + Jacobi/BlockJacobi, solver/istl/**)
  *   dcb_stepper_*          <- PDELab::OneStep (RungeKutta o Newton)  make_step_operator.hh:408-443,
  *                             SimpleAdaptiveStepper                  common/stepper.hh:337-368
+ *   dcb_reducer_*          <- DiffusionReaction::reduce              diffusion_reaction/reduce.hh:38-285
  *
  * wM / wA are the Runge-Kutta weights of the mass form (Form::Mass, storage terms) and of the
  * stiffness form (Form::Stiffness, reaction + diffusion + outflow), local_operator.hh:143-147:
@@ -46,6 +47,7 @@ typedef struct dcb_model dcb_model;
 typedef struct dcb_operator dcb_operator;
 typedef struct dcb_solver dcb_solver;
 typedef struct dcb_stepper dcb_stepper;
+typedef struct dcb_reducer dcb_reducer;
 typedef struct dcb_comm dcb_comm;
 
 typedef struct {
@@ -161,6 +163,21 @@ int dcb_stepper_step(dcb_stepper*, double dt, int* ok);
 /* adaptive evolution to t_end with at most max_steps accepted steps */
 int dcb_stepper_evolve(dcb_stepper*, double t_end, double* dt, int max_steps, int* accepted);
 int dcb_stepper_stats(const dcb_stepper*, dcb_step_stats*);
+
+/* ---- [model.reduce] functionals (config = the whole ini): per key evaluation / reduction /
+ *      transformation / error / warn expressions over an order-4 quadrature of every cell,
+ *      dune/copasi/model/diffusion_reaction/reduce.hh:38-285.  values[k] is the transformed result of
+ *      key k, status[k] = 0 fine, 1 warn.expression fired, 2 error.expression fired.  The apply calls
+ *      return 2 when an error expression fired (dcb_last_error() holds the reference's
+ *      ReductionError text), 1 on any other failure. ---- */
+dcb_reducer* dcb_reducer_create(dcb_operator*, const dcb_config*, dcb_comm*);
+void dcb_reducer_destroy(dcb_reducer*);
+int dcb_reducer_num_keys(const dcb_reducer*);
+const char* dcb_reducer_key(const dcb_reducer*, int k);
+int dcb_reducer_apply(dcb_reducer*, double time, const double* x_host, double* values, int32_t* status);
+int dcb_reducer_apply_dev(dcb_reducer*, double time, const double* x_dev, double* values, int32_t* status);
+/* compile the reduce kernels of (model, config) into the on-disk JIT cache (no GPU needed) */
+int dcb_model_precompile_reduce(dcb_model*, const dcb_config*);
 
 /* ---- multi-GPU: one process per GPU, NCCL ---- */
 int dcb_nccl_unique_id(char id[128]);

@@ -431,9 +431,8 @@ def eval_program(code, consts, ctx: np.ndarray) -> np.ndarray:
     ctx = np.ascontiguousarray(ctx, dtype=np.float64)
     out = np.empty(ctx.shape[0])
     n, ns = ctx.shape
-    for i in range(n):   # small n in tests; the hot loops call the VM from C
-        out[i] = L.orc_eval(_p(code, C.c_int32), C.c_int(code.size), _p(consts, C.c_double),
-                            _p(ctx[i], C.c_double))
+    L.orc_eval_rows(_p(code, C.c_int32), C.c_int(code.size), _p(consts, C.c_double), _p(ctx, C.c_double),
+                    C.c_int64(n), C.c_int64(ns), _p(out, C.c_double))
     return out
 
 
@@ -692,3 +691,105 @@ def reduce_l2(model: Model, u, species: str, exact, time: float):
     pos = np.einsum("qa,ead->eqd", phi, X)
     ex = exact(pos, time)
     return math.sqrt(float((((uh - ex) ** 2) * w[None, :] * det[:, None]).sum()))
+
+
+# ---------------------------------------------------------------------- [model.reduce] (general)
+def _reduce_rule(dim):
+    """Quadrature of the reduce functionals in barycentric coordinates (weights sum to the reference
+    volume).  dune-geometry's order-4 tables are third party and absent from the reference tree
+    (parity unpinned): triangle = 6-point rule of degree 4 (Dunavant), tetrahedron = 15-point rule
+    of degree 5 (Stroud T3:5-1) -- the same tables as kernels/reduce.cuh."""
+    if dim == 2:
+        lam, w = [], []
+        for a, wt in ((0.445948490915965, 0.223381589678011), (0.091576213509771, 0.109951743655322)):
+            for odd in range(3):
+                lam.append([1 - 2 * a if k == odd else a for k in range(3)])
+                w.append(0.5 * wt)
+        return np.asarray(lam), np.asarray(w)
+    s15 = math.sqrt(15.0)
+    lam, w = [[0.25] * 4], [(16.0 / 135.0) / 6.0]
+    for a, wt in (((7 - s15) / 34, (2665 + 14 * s15) / 37800), ((7 + s15) / 34, (2665 - 14 * s15) / 37800)):
+        for odd in range(4):
+            lam.append([1 - 3 * a if k == odd else a for k in range(4)])
+            w.append(wt / 6.0)
+    b = (10 - 2 * s15) / 40
+    for i0 in range(4):
+        for i1 in range(i0 + 1, 4):
+            lam.append([b if k in (i0, i1) else 0.5 - b for k in range(4)])
+            w.append((10.0 / 189.0) / 6.0)
+    return np.asarray(lam), np.asarray(w)
+
+
+def _function(text, ctx, nargs, what):
+    head, body = text.split(":", 1)
+    args = [a.strip() for a in head.split(",") if a.strip()]
+    if len(args) != nargs:
+        raise ValueError(f"{what} must have exactly {nargs} argument(s)")
+    ast = E.resolve(E.Parser(body.strip()).parse(), ctx)
+    return lambda *v: E.py_eval(ast, dict(zip(args, v)))
+
+
+def reduce(model: Model, u, time: float, cfg: dict | None = None):
+    """reduce.hh:38-285, sequential path: for every cell and quadrature point
+    value = reduction(evaluation(), value) from `initial.value`; the gather step applies the
+    reduction once more against `initial.value` (:205-210); then transformation / error / warn.
+    Returns (values, status) with status 0 fine / 1 warn / 2 error."""
+    rc = INI.sub(INI.sub(cfg if cfg is not None else model.cfg, "model"), "reduce")
+    keys = [(k, v) for k, v in rc.items() if isinstance(v, dict)]
+    m = model.mesh
+    dim, nd = m.dim, m.dim + 1
+    lam, w = _reduce_rule(dim)
+    nq = w.size
+    X = m.coords[m.elems]                                        # [ne, nd, dim]
+    Bm = np.transpose(X[:, 1:, :] - X[:, :1, :], (0, 2, 1))      # columns = edges
+    det = np.abs(np.linalg.det(Bm))
+    Binv = np.linalg.inv(Bm)                                     # rows = grad of xi_k
+    G = np.concatenate([-Binv.sum(axis=1, keepdims=True), Binv], axis=1)   # [ne, nd, dim]
+    sym = model.sym
+    ctx = np.zeros((m.ne, nq, sym.nslots))
+    ctx[..., E.SLOT_TIME] = time
+    ctx[..., E.SLOT_INTFAC] = w[None, :] * det[:, None]
+    ctx[..., E.SLOT_ENTVOL] = (det / (2.0 if dim == 2 else 6.0))[:, None]
+    ctx[..., E.SLOT_INVOL] = 1.0
+    ctx[..., E.SLOT_POS:E.SLOT_POS + dim] = np.einsum("qa,ead->eqd", lam, X)
+    for k in range(len(m.cell_keys)):
+        ctx[..., E.SLOT_CELL + k] = m.cell_data[k][:, None]
+    for g, sp in enumerate(model.species):
+        sel = m.elem_comp == sp.comp
+        xl = u[m.elem_dof[sel] + sp.local]                       # [nsel, nd]
+        base = sym.spec_base + 4 * g
+        ctx[sel, :, base] = xl @ lam.T
+        ctx[sel, :, base + 1:base + 1 + dim] = np.einsum("ea,ead->ed", xl, G[sel])[:, None, :]
+    rows = ctx.reshape(-1, sym.nslots)
+    values, status = {}, {}
+    for key, sub in keys:
+        init = float(INI.get(sub, "initial.value", 0.0))
+        ev = INI.get(sub, "evaluation.expression", None)
+        if ev is None or E.is_absent(ev):
+            vals = np.zeros(rows.shape[0])
+        else:
+            code, consts = E.compile_expr(ev, sym, model.ctx)
+            vals = eval_program(code, consts, rows)
+        red = INI.get(sub, "reduction.expression", None)
+        if red is None:
+            total = init + float(vals.sum())
+            total = total + init
+        else:
+            op = _function(red, model.ctx, 2, "Reduction arguments")
+            total = init
+            for v in vals:
+                total = op(float(v), total)
+            total = op(total, init)
+        tr = INI.get(sub, "transformation.expression", None)
+        if tr is not None:
+            total = _function(tr, model.ctx, 1, "Warning function")(total)
+        st = 0
+        nz = lambda v: abs(v) > 1e-8 * max(1.0, abs(v))   # noqa: E731  FloatCmp::ne(v, 0)
+        er = INI.get(sub, "error.expression", None)
+        wa = INI.get(sub, "warn.expression", None)
+        if er is not None and nz(_function(er, model.ctx, 1, "Error function")(total)):
+            st = 2
+        elif wa is not None and nz(_function(wa, model.ctx, 1, "Warning function")(total)):
+            st = 1
+        values[key], status[key] = total, st
+    return values, status

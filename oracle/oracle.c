@@ -138,6 +138,12 @@ static inline double run(const OrcModel* P, int prog, const double* ctx) {
                   P->consts + P->const_ptr[prog], ctx);
 }
 
+/* one stand-alone program on many contexts (rows of `nslots` doubles) */
+void orc_eval_rows(const int32_t* code, int n, const double* consts, const double* ctxs, int64_t nrows,
+                   int64_t nslots, double* out) {
+  for (int64_t i = 0; i < nrows; ++i) out[i] = orc_eval(code, n, consts, ctxs + i * nslots);
+}
+
 void orc_eval_many(const OrcModel* P, int prog, int64_t n, const double* ctxs, double* out) {
   for (int64_t i = 0; i < n; ++i) out[i] = run(P, prog, ctxs + i * P->nslots);
 }

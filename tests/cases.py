@@ -350,6 +350,90 @@ time_end = 1
 """ + SOLVER
 
 
+# [model.reduce] sections: the assertions of the reference's system tests in its own vocabulary
+# (test/gauss.ini:38-55, exp.ini:25-35, poisson.ini:27-32, two_disks.ini:45-60, mitchell_schaefer.ini:84-104)
+REDUCE = {
+    "gauss": """
+[model.reduce]
+u_max.evaluation.expression = u
+u_max.reduction.expression = init, val: max(init, val)
+u_max.initial.value = -1e100
+u_max.error.expression = arg: arg > 1/(4*3.14159265359*diffusion)
+u_min.evaluation.expression = u
+u_min.reduction.expression = init, val: min(init, val)
+u_min.initial.value = 1e100
+u_min.warn.expression = arg: arg < 0
+u_min.error.expression = arg: arg < -1e-2
+u_error.evaluation.expression = (u - gauss(position_x, position_y, position_z, time))^2 * integration_factor
+u_error.transformation.expression = arg: sqrt(arg)
+u_error.error.expression = arg: arg > 0.50
+""",
+    "exp": """
+[model.reduce]
+u_mass_analytic.evaluation.expression = exp(grow_rate*time)
+u_max.evaluation.expression = u
+u_max.reduction.expression = init, val: max(init, val)
+u_max.initial.value = -1e100
+u_error.evaluation.expression = (u - exp(grow_rate*time))^2 * integration_factor
+u_error.transformation.expression = arg: sqrt(arg)
+u_error.error.expression = arg: arg > 5e-3
+""",
+    "poisson": """
+[model.reduce]
+u_error.evaluation.expression = (u - (position_x^2+position_y^2+position_z^2))^2 * integration_factor
+u_error.transformation.expression = arg: sqrt(arg)
+u_error.warn.expression = arg: arg > 1e-2
+u_error.error.expression = arg: arg > 2e-0
+""",
+    "two_disks": """
+[parser_context.u_in_analytic]
+type = function
+expression = x, y: 8*phi*x/(8*phi + 5)
+[parser_context.u_out_analytic]
+type = function
+expression = x, y: 4*((2*phi + 1) + 1/(x^2 + y^2))*x/(8*phi + 5)
+[model.reduce]
+u_max.evaluation.expression = max(u_in, u_out)
+u_max.reduction.expression = init, val: max(init, val)
+u_max.initial.value = -1e100
+u_max.error.expression = arg: arg > 2
+u_min.evaluation.expression = min(u_in, u_out)
+u_min.reduction.expression = init, val: min(init, val)
+u_min.initial.value = 1e100
+u_min.error.expression = arg: arg < -2
+u_error.evaluation.expression = ((sqrt(position_x^2+position_y^2) < 1) ? (u_in - u_in_analytic(position_x, position_y))^2 : (u_out - u_out_analytic(position_x, position_y))^2) * integration_factor
+u_error.transformation.expression = arg: sqrt(arg)
+u_error.warn.expression = arg: arg > 1e-3
+""",
+    "mitchell_schaefer": """
+[model.reduce]
+u_max.evaluation.expression = u
+u_max.reduction.expression = init, val: max(init, val)
+u_max.initial.value = -1e100
+u_max.warn.expression = arg: arg > 1
+u_min.evaluation.expression = u
+u_min.reduction.expression = init, val: min(init, val)
+u_min.initial.value = 1e100
+u_min.warn.expression = arg: arg < 0
+z_max.evaluation.expression = z
+z_max.reduction.expression = init, val: max(init, val)
+z_max.initial.value = -1e100
+z_max.warn.expression = arg: arg > 1
+u_mass.evaluation.expression = u * integration_factor
+grad_energy.evaluation.expression = (grad_u_x^2 + grad_u_y^2) * integration_factor
+""",
+    "cell3d": """
+[model.reduce]
+c1_mass.evaluation.expression = c1 * integration_factor
+n1_max.evaluation.expression = n1
+n1_max.reduction.expression = a, b: max(a, b)
+n1_max.initial.value = -1e100
+volume.evaluation.expression = integration_factor
+cells.evaluation.expression = integration_factor / entity_volume
+""",
+}
+
+
 class Case:
     def __init__(self, name, ini, dim, mesh_fn, t0=0.0, dt=0.1, structured=None):
         self.name, self.ini, self.dim, self.mesh_fn, self.t0, self.dt = name, ini, dim, mesh_fn, t0, dt
@@ -375,15 +459,15 @@ def _s(dim, n, origin=None, extent=None):
 
 
 CASES = {
-    "gauss2d": Case("gauss2d", GAUSS, 2, _s(2, 32, [-1, -1], [2, 2]), t0=1.0, structured=([32, 32], [-1, -1], [2, 2])),
-    "gauss3d": Case("gauss3d", GAUSS, 3, _s(3, 8, [-1, -1, -1], [2, 2, 2]), t0=1.0, structured=([8, 8, 8], [-1, -1, -1], [2, 2, 2])),
-    "exp": Case("exp", EXP, 2, _s(2, 2), structured=([2, 2], [0, 0], [1, 1])),
-    "poisson": Case("poisson", POISSON, 2, _s(2, 16), structured=([16, 16], [0, 0], [1, 1])),
+    "gauss2d": Case("gauss2d", GAUSS + REDUCE["gauss"], 2, _s(2, 32, [-1, -1], [2, 2]), t0=1.0, structured=([32, 32], [-1, -1], [2, 2])),
+    "gauss3d": Case("gauss3d", GAUSS + REDUCE["gauss"], 3, _s(3, 8, [-1, -1, -1], [2, 2, 2]), t0=1.0, structured=([8, 8, 8], [-1, -1, -1], [2, 2, 2])),
+    "exp": Case("exp", EXP + REDUCE["exp"], 2, _s(2, 2), structured=([2, 2], [0, 0], [1, 1])),
+    "poisson": Case("poisson", POISSON + REDUCE["poisson"], 2, _s(2, 16), structured=([16, 16], [0, 0], [1, 1])),
     "grayscott2d": Case("grayscott2d", GRAY_SCOTT, 2, _s(2, 32), dt=1.0, structured=([32, 32], [0, 0], [1, 1])),
     "grayscott3d": Case("grayscott3d", GRAY_SCOTT, 3, _s(3, 10), dt=1.0, structured=([10, 10, 10], [0, 0, 0], [1, 1, 1])),
-    "mitchell_schaefer": Case("mitchell_schaefer", MITCHELL_SCHAEFER, 2, _s(2, 16), dt=0.01, structured=([16, 16], [0, 0], [1, 1])),
-    "two_disks": Case("two_disks", TWO_DISKS, 2, lambda: OMESH.two_disks(6, 6, 32), dt=1.0),
-    "cell3d": Case("cell3d", CELL, 3, _s(3, 8), dt=0.05, structured=([8, 8, 8], [0, 0, 0], [1, 1, 1])),
+    "mitchell_schaefer": Case("mitchell_schaefer", MITCHELL_SCHAEFER + REDUCE["mitchell_schaefer"], 2, _s(2, 16), dt=0.01, structured=([16, 16], [0, 0], [1, 1])),
+    "two_disks": Case("two_disks", TWO_DISKS + REDUCE["two_disks"], 2, lambda: OMESH.two_disks(6, 6, 32), dt=1.0),
+    "cell3d": Case("cell3d", CELL + REDUCE["cell3d"], 3, _s(3, 8), dt=0.05, structured=([8, 8, 8], [0, 0, 0], [1, 1, 1])),
     "advection2d": Case("advection2d", ADVECTION, 2, _s(2, 12), dt=0.05, structured=([12, 12], [0, 0], [1, 1])),
     "advection3d": Case("advection3d", ADVECTION, 3, _s(3, 5), dt=0.05, structured=([5, 5, 5], [0, 0, 0], [1, 1, 1])),
 }

@@ -326,6 +326,42 @@ def test_numerical_jacobian(name):
         assert rel(st.get_state()[0], u) <= 1e-8
 
 
+@pytest.mark.parametrize("name", ["gauss2d", "gauss3d", "exp", "poisson", "two_disks", "mitchell_schaefer", "cell3d"])
+def test_reduce_matches_oracle(name):
+    """[model.reduce] functionals (reduce.hh:38-285) on the device: sums to rounding, max / min
+    exactly (same quadrature points), warn / error statuses as the oracle."""
+    import dune_copasi_b200 as D
+    case, om, cfg, model, grid, op = make(name)
+    red = D.Reducer(op, cfg)
+    for seed, t in ((None, case.t0), (40, case.t0 + 0.37)):
+        x = om.initial(t) if seed is None else K.rand_state(om.ndofs, seed, -0.5, 1.5)
+        ref, ref_status = K.ORC.reduce(om, x, t)
+        got = red.apply(t, x, raise_on_error=False)
+        assert list(got) == list(ref)
+        for key in ref:
+            scale = max(abs(ref[key]), 1e-300)
+            assert abs(got[key] - ref[key]) <= 1e-11 * scale, (key, got[key], ref[key])
+            assert red.status[key] == ref_status[key], (key, red.status[key], ref_status[key])
+
+
+def test_reduce_error_expression_raises_like_the_reference():
+    import dune_copasi_b200 as D
+    over = {"model.reduce.u_error.error.expression": "arg: arg > 1e-9"}
+    case, om, cfg, model, grid, op = make("gauss2d", **over)
+    red = D.Reducer(op, cfg)
+    x = om.initial(case.t0) + 1e-3
+    with pytest.raises(D.ReductionError, match="Reduction on the token 'u_error' raised an error"):
+        red.apply(case.t0, x)
+    assert red.status["u_error"] == 2 and red.status["u_max"] == 0
+    # the reference's own assertion of test/gauss.ini holds on the GPU trajectory
+    case, om, cfg, model, grid, op = make("gauss2d")
+    st = D.Stepper(op, cfg)
+    st.set_state(grid.interpolate(model, 1.0), 1.0)
+    st.evolve(1.2, 0.1)
+    vals = D.Reducer(op, cfg).apply_dev(st.time, st.state_dev())
+    assert vals["u_error"] <= 0.50 and vals["u_min"] >= -1e-2
+
+
 def test_adaptive_evolve_matches_oracle_and_kat():
     """SimpleAdaptiveStepper (common/stepper.hh:337-368): dt grows by 1.1, snaps to t_end; the
     gauss known answer (test/gauss.ini:43-55) holds for the GPU trajectory as well."""

@@ -92,6 +92,21 @@ def test_configuration_errors_are_loud():
         D.Grid.structured(2, [2, 2]).bind(model)
 
 
+def test_reduce_kernels_compile_without_a_gpu_and_errors_are_loud():
+    import dune_copasi_b200 as D
+    for name in ("gauss2d", "two_disks", "cell3d"):
+        cfg, model, grid = K.product_objects(K.CASES[name])
+        model.precompile(reduce_config=cfg)       # NVRTC -> sm_100a cubin in the JIT cache
+    bad = K.CASES["exp"].ini_with(**{"model.reduce.u_max.reduction.expression": "a, b, c: max(a, b)"})
+    cfg = D.Config(bad)
+    with pytest.raises(D.DcbError, match="Reduction arguments must be exactly 2"):
+        D.Model(cfg, 2).precompile(reduce_config=cfg)
+    bad = K.CASES["exp"].ini_with(**{"model.reduce.u_max.evaluation.expression": "u + nonsense"})
+    cfg = D.Config(bad)
+    with pytest.raises(D.DcbError, match="unknown symbol"):
+        D.Model(cfg, 2).precompile(reduce_config=cfg)
+
+
 def test_generated_cuda_matches_oracle_vm():
     """The expression lowering (Model::cuda_source) is plain C++ once the CUDA qualifiers are
     defined away: compile it with g++ and compare the point functions of every case with the

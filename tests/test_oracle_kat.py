@@ -144,6 +144,38 @@ def test_numerical_skeleton_jacobian_matches_analytic(name):
     assert np.abs(va - vf).max() <= 2e-6 * np.abs(va).max()
 
 
+@pytest.mark.parametrize("name,t0,t_end,dt", [("gauss2d", 1.0, 1.2, 0.1), ("exp", 0.0, 1.0, 0.1), ("poisson", 0.0, 0.1, 0.1),
+                                              ("two_disks", 0.0, 1.0, 1.0)])
+def test_reference_reduce_assertions_hold(name, t0, t_end, dt):
+    """The reference's system tests pass when no `error.expression` of [model.reduce] fires
+    (reduce.hh:230-249; thresholds restated in cases.REDUCE): the oracle trajectory satisfies them."""
+    om = K.CASES[name].oracle()
+    S = ORC.StepOperator(om)
+    u, t, _ = ORC.evolve(S, om.initial(t0), t0, t_end, dt)
+    values, status = ORC.reduce(om, u, t)
+    assert all(s != 2 for s in status.values()), (values, status)
+    assert values["u_error"] > 0.0
+
+
+def test_reduce_quadrature_and_semantics():
+    """Order-4 rule: exact for quartics; default reduction = sum; `initial.value` enters once per
+    partial and once in the gather step (reduce.hh:124, 205-210)."""
+    import itertools
+    from math import factorial as f
+    for dim in (2, 3):
+        lam, w = ORC._reduce_rule(dim)
+        for e in itertools.product(range(5), repeat=dim):
+            if sum(e) <= 4:
+                exact = np.prod([f(k) for k in e]) / f(sum(e) + dim)
+                assert abs((w * np.prod(lam[:, 1:] ** np.array(e), axis=1)).sum() - exact) < 1e-15
+    om = K.CASES["cell3d"].oracle()
+    values, _ = ORC.reduce(om, om.initial(0.0), 0.0)
+    assert abs(values["volume"] - 1.0) < 1e-13 and abs(values["cells"] - om.mesh.ne) < 1e-9
+    cfg = INI.parse_ini("[model.reduce]\nv.evaluation.expression = integration_factor\nv.initial.value = 0.25\n")
+    values, _ = ORC.reduce(om, om.initial(0.0), 0.0, cfg)
+    assert abs(values["v"] - 1.5) < 1e-13
+
+
 def test_advection_element_identity():
     """Constant velocity w on one simplex: r_a = -|T| mean(u) (w . grad phi_a), exact under the order-2 rule."""
     rng = np.random.default_rng(5)
