@@ -15,7 +15,8 @@ def _ngpus():
     return D.lib().dcb_device_count()
 
 
-@pytest.mark.parametrize("name,mf", [("grayscott3d", "1"), ("grayscott3d", "0"), ("cell3d", "1"), ("two_disks", "0")])
+@pytest.mark.parametrize("name,mf", [("grayscott3d", "1"), ("grayscott3d", "0"), ("cell3d", "1"), ("two_disks", "0"),
+                                     ("gauss3d", "1"), ("advection3d", "0")])
 def test_two_rank_time_stepping_matches_serial_oracle(name, mf):
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")

@@ -49,6 +49,9 @@ def main():
     for _ in range(nsteps):
         assert st.step(case.dt), "step failed"
     u, t = st.get_state()
+    # [model.reduce] over the partition: every rank obtains the global values
+    red = D.Reducer(op, cfg, comm)
+    red_vals = red.apply_dev(st.time, st.state_dev(), raise_on_error=False) if red.keys else {}
     # gather (global vertex id, compartment-major dof values) of the owned dofs on rank 0
     om = case.oracle(**over) if rank == 0 else None
     gids = grid.global_vertex_ids()
@@ -84,6 +87,12 @@ def main():
         err = np.linalg.norm(got - uref) / np.linalg.norm(uref)
         print(f"mgpu_check {name} world={world} steps={nsteps} matrix_free={mf}: rel L2 err {err:.3e}")
         ok = err <= 1e-10
+        if red_vals:
+            ref_vals, _ = K.ORC.reduce(om, uref, tt)
+            for key, v in ref_vals.items():
+                dv = abs(red_vals[key] - v) / max(abs(v), 1e-300)
+                print(f"  reduce {key}: {red_vals[key]:.12g} (serial oracle {v:.12g}, rel diff {dv:.2e})")
+                ok = ok and dv <= 1e-9
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
