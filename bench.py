@@ -51,6 +51,9 @@ def ini_for(args):
     for kv in filter(None, getattr(args, "b200", "").split(",")):
         k, v = kv.split("=")
         over["model.assembly.b200." + k] = v
+    for kv in filter(None, getattr(args, "set", "").split(",")):
+        k, v = kv.split("=")
+        over[k] = v
     case = "cell3d" if getattr(args, "workload", "grayscott") == "cell" else "grayscott3d"
     return K.CASES[case].ini_with(**over)
 
@@ -197,6 +200,7 @@ def main():
                     help="grayscott: BASELINE configs[3] (headline); cell: 3-compartment / 6-species cell model "
                          "(configs[4] in miniature, general unstructured kernels)")
     ap.add_argument("--b200", default="", help="model.assembly.b200.* overrides, e.g. patch_elements=768,patch_min_blocks=4")
+    ap.add_argument("--set", default="", help="any ini key overrides, e.g. model.time_step_operator.linear_solver.b200.speculation=false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

@@ -169,13 +169,27 @@ __global__ void __launch_bounds__(kThreads) k_axpy_pair_norm(int64_t n, Ranges o
 }
 
 // ---- fused BiCGSTAB sweeps (Jacobi folded into the producing kernel when dinv != null) ----------
+// Every step length is formed on the device from the (all-reduced) device-resident sums, in the
+// operation order of the host formulas of dune-istl, so that the host never has to wait for a
+// scalar before it can enqueue the next sweep:
+//   rho_new = <rt,r> of this iteration, rho = the one before, h = <rt,v>, trtt = (<t,r>, <t,t>)
+//   alpha = rho / h (of the same iteration), omega = tr / tt, beta = (rho_new / rho) * (alpha / omega)
 // p = r + beta (p - omega v) ; y = relax * dinv * p
 __global__ void __launch_bounds__(kThreads) k_bicg_p_prec(int64_t n, double* __restrict__ p,
                                                           const double* __restrict__ r,
-                                                          const double* __restrict__ v, double beta,
-                                                          double omega, bool first,
+                                                          const double* __restrict__ v,
+                                                          const double* __restrict__ rho_new_p,
+                                                          const double* __restrict__ rho_p,
+                                                          const double* __restrict__ hptr,
+                                                          const double* __restrict__ trtt, bool first,
                                                           const double* __restrict__ dinv, double relax,
                                                           double* __restrict__ y) {
+  double beta = 0.0, omega = 0.0;
+  if (!first) {
+    const double rho = *rho_p, alpha = rho / *hptr;
+    omega = trtt[0] / trtt[1];
+    beta = (*rho_new_p / rho) * (alpha / omega);
+  }
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
     const double pi = first ? r[i] : r[i] + beta * (p[i] - omega * v[i]);
     p[i] = pi;
@@ -183,7 +197,8 @@ __global__ void __launch_bounds__(kThreads) k_bicg_p_prec(int64_t n, double* __r
   }
 }
 // r -= alpha v ; out[0] = <r,r> ; y2 = relax * dinv * r
-__global__ void __launch_bounds__(kThreads) k_bicg_r_prec(int64_t n, Ranges own, double rho_new,
+__global__ void __launch_bounds__(kThreads) k_bicg_r_prec(int64_t n, Ranges own,
+                                                          const double* __restrict__ rho_p,
                                                           const double* __restrict__ hptr,
                                                           const double* __restrict__ v,
                                                           double* __restrict__ r,
@@ -192,7 +207,7 @@ __global__ void __launch_bounds__(kThreads) k_bicg_r_prec(int64_t n, Ranges own,
                                                           unsigned* counter, double* out) {
   double acc[1] = {0.0};
   const bool single = own.n == 1 && own.b[0] == 0 && own.e[0] == n;
-  const double alpha = rho_new / *hptr;   // alpha = rho'/<rt,v> from the device-resident reduction
+  const double alpha = *rho_p / *hptr;   // alpha = rho'/<rt,v> from the device-resident reductions
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
     const double ri = r[i] - alpha * v[i];
     r[i] = ri;
@@ -201,22 +216,24 @@ __global__ void __launch_bounds__(kThreads) k_bicg_r_prec(int64_t n, Ranges own,
   }
   grid_reduce<1>(acc, partials, counter, out);
 }
-// x += alpha y1 + omega y2 ; r -= omega t ; out[0] = <r,r> ; out[1] = <rt,r>
-__global__ void __launch_bounds__(kThreads) k_bicg_final(int64_t n, Ranges own, double rho_new,
+// xout = xin + alpha y1 + omega y2 ; r -= omega t ; out[0] = <r,r> ; out[1] = <rt,r>
+__global__ void __launch_bounds__(kThreads) k_bicg_final(int64_t n, Ranges own,
+                                                         const double* __restrict__ rho_p,
                                                          const double* __restrict__ hptr,
                                                          const double* __restrict__ trtt,
                                                          const double* __restrict__ y1,
                                                          const double* __restrict__ y2,
-                                                         double* __restrict__ x,
+                                                         const double* __restrict__ xin,
+                                                         double* __restrict__ xout,
                                                          const double* __restrict__ t,
                                                          double* __restrict__ r,
                                                          const double* __restrict__ rt, double* partials,
                                                          unsigned* counter, double* out) {
   double acc[2] = {0.0, 0.0};
   const bool single = own.n == 1 && own.b[0] == 0 && own.e[0] == n;
-  const double alpha = rho_new / *hptr, omega = trtt[0] / trtt[1];
+  const double alpha = *rho_p / *hptr, omega = trtt[0] / trtt[1];
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-    x[i] = (x[i] + alpha * y1[i]) + omega * y2[i];
+    xout[i] = (xin[i] + alpha * y1[i]) + omega * y2[i];
     const double ri = r[i] - omega * t[i];
     r[i] = ri;
     if (single || in_ranges(own, i)) {
@@ -442,20 +459,21 @@ void axpy_pair_norm(int64_t n, const Ranges& own, double alpha, const double* y,
   k_axpy_pair_norm<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, alpha, y, x, v, r, rt, w.partials, w.counter, out);
   check_launch();
 }
-void bicg_p_prec(int64_t n, double* p, const double* r, const double* v, double beta, double omega, bool first,
-                 const double* dinv, double relax, double* y, cudaStream_t s) {
-  k_bicg_p_prec<<<grid_for(n, 2), kThreads, 0, s>>>(n, p, r, v, beta, omega, first, dinv, relax, y);
+void bicg_p_prec(int64_t n, double* p, const double* r, const double* v, const double* rho_new, const double* rho,
+                 const double* hptr, const double* trtt, bool first, const double* dinv, double relax, double* y,
+                 cudaStream_t s) {
+  k_bicg_p_prec<<<grid_for(n, 2), kThreads, 0, s>>>(n, p, r, v, rho_new, rho, hptr, trtt, first, dinv, relax, y);
   check_launch();
 }
-void bicg_r_prec(int64_t n, const Ranges& own, double rho_new, const double* hptr, const double* v, double* r,
+void bicg_r_prec(int64_t n, const Ranges& own, const double* rho, const double* hptr, const double* v, double* r,
                  const double* dinv, double relax, double* y2, double* out, const ReduceWorkspace& w, cudaStream_t s) {
-  k_bicg_r_prec<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, rho_new, hptr, v, r, dinv, relax, y2, w.partials, w.counter, out);
+  k_bicg_r_prec<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, rho, hptr, v, r, dinv, relax, y2, w.partials, w.counter, out);
   check_launch();
 }
-void bicg_final(int64_t n, const Ranges& own, double rho_new, const double* hptr, const double* trtt, const double* y1,
-                const double* y2, double* x, const double* t, double* r, const double* rt, double* out,
-                const ReduceWorkspace& w, cudaStream_t s) {
-  k_bicg_final<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, rho_new, hptr, trtt, y1, y2, x, t, r, rt, w.partials, w.counter, out);
+void bicg_final(int64_t n, const Ranges& own, const double* rho, const double* hptr, const double* trtt, const double* y1,
+                const double* y2, const double* xin, double* xout, const double* t, double* r, const double* rt,
+                double* out, const ReduceWorkspace& w, cudaStream_t s) {
+  k_bicg_final<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, rho, hptr, trtt, y1, y2, xin, xout, t, r, rt, w.partials, w.counter, out);
   check_launch();
 }
 void xpby(int64_t n, double* p, const double* q, double beta, cudaStream_t s) {

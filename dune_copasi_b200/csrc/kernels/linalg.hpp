@@ -42,19 +42,22 @@ void bicg_update_p(int64_t n, double* p, const double* r, const double* v, doubl
 // x += alpha y ; r -= alpha v ; out[0] = <r,r> ; out[1] = <rt,r>  (rt may be null -> out[1] = 0)
 void axpy_pair_norm(int64_t n, const Ranges& own, double alpha, const double* y, double* x, const double* v, double* r,
                     const double* rt, double* out, const ReduceWorkspace& w, cudaStream_t s);
-// fused BiCGSTAB sweeps; dinv == null skips the folded Jacobi application
-// p = r + beta (p - omega v) ; y = relax dinv p
-void bicg_p_prec(int64_t n, double* p, const double* r, const double* v, double beta, double omega, bool first,
-                 const double* dinv, double relax, double* y, cudaStream_t s);
-// The step lengths are formed on the device from the (all-reduced) device-resident sums, so the
-// host does not have to wait for them: alpha = rho_new / *hptr, omega = trtt[0] / trtt[1].
+// fused BiCGSTAB sweeps; dinv == null skips the folded Jacobi application.
+// Every step length is formed on the device from the (all-reduced) device-resident sums, so the
+// host can enqueue the next sweep without waiting for a scalar:
+//   rho = <rt,r> at the start of the iteration, hptr = <rt,v>, trtt = (<t,r>, <t,t>):
+//   alpha = rho / h, omega = tr / tt, beta = (rho_new / rho) * (alpha / omega)  (dune-istl's order)
+// p = r + beta (p - omega v) ; y = relax dinv p      (rho, hptr, trtt: those of the previous iteration)
+void bicg_p_prec(int64_t n, double* p, const double* r, const double* v, const double* rho_new, const double* rho,
+                 const double* hptr, const double* trtt, bool first, const double* dinv, double relax, double* y,
+                 cudaStream_t s);
 // r -= alpha v ; out[0] = <r,r> ; y2 = relax dinv r
-void bicg_r_prec(int64_t n, const Ranges& own, double rho_new, const double* hptr, const double* v, double* r,
+void bicg_r_prec(int64_t n, const Ranges& own, const double* rho, const double* hptr, const double* v, double* r,
                  const double* dinv, double relax, double* y2, double* out, const ReduceWorkspace& w, cudaStream_t s);
-// x += alpha y1 + omega y2 ; r -= omega t ; out[0] = <r,r> ; out[1] = <rt,r>
-void bicg_final(int64_t n, const Ranges& own, double rho_new, const double* hptr, const double* trtt, const double* y1,
-                const double* y2, double* x, const double* t, double* r, const double* rt, double* out,
-                const ReduceWorkspace& w, cudaStream_t s);
+// xout = xin + alpha y1 + omega y2 ; r -= omega t ; out[0] = <r,r> ; out[1] = <rt,r>
+void bicg_final(int64_t n, const Ranges& own, const double* rho, const double* hptr, const double* trtt, const double* y1,
+                const double* y2, const double* xin, double* xout, const double* t, double* r, const double* rt,
+                double* out, const ReduceWorkspace& w, cudaStream_t s);
 // GMRES (modified Gram-Schmidt) with device-resident coefficients:
 // y += sign * (*coef) * x
 void axpy_dev(int64_t n, const double* coef, double sign, const double* x, double* y, cudaStream_t s);

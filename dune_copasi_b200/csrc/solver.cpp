@@ -26,14 +26,19 @@ LinearSolver::LinearSolver(std::shared_ptr<DeviceOperator> op, const PTree& cfg,
   relaxation = cfg.get("preconditioner.relaxation", 1.0);
   matrix_free = cfg.get("matrix_free", false);
   verbosity = cfg.get("verbosity", 0);
+  speculation = cfg.get("b200.speculation", true);
   auto range = cfg.get_vec("convergence_condition.iteration_range", {1, 500});   // iterative.hh:53-54
   max_iterations = (int)range.back();
   la::reduce_workspace_create(&ws_);
   const bool gmres = type == "RestartedGMRes";
-  scal_.alloc(gmres ? std::max(8, restart + 2) : 8);
-  hscal_.alloc(gmres ? std::max(8, restart + 2) : 8);
+  scal_.alloc(gmres ? std::max(16, restart + 2) : 16);
+  hscal_.alloc(gmres ? std::max(16, restart + 2) : 16);
   const int nwork = type == "BiCGSTAB" ? 6 : 2;
   for (int k = 0; k < nwork; ++k) work_[k].alloc(op_->ndofs);
+  if (type == "BiCGSTAB") {
+    xalt_.alloc(op_->ndofs);   // alternate iterate (speculative half steps, see apply)
+    for (auto& e : ev_) DCB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   if (prec_iterations > 1 && prec_type != "Richardson")
     for (auto& w : sweep_) w.alloc(op_->ndofs);
   if (gmres) basis_.alloc((int64_t)(restart + 1) * op_->ndofs);   // Krylov basis v_0 .. v_m
@@ -45,7 +50,11 @@ LinearSolver::LinearSolver(std::shared_ptr<DeviceOperator> op, const PTree& cfg,
   if (prec_type == "BlockJacobi" || (matrix_free && prec_type == "Jacobi")) bdiag_.alloc(op_->bdiag_size());
 }
 
-LinearSolver::~LinearSolver() { la::reduce_workspace_destroy(&ws_); }
+LinearSolver::~LinearSolver() {
+  la::reduce_workspace_destroy(&ws_);
+  for (auto& e : ev_)
+    if (e) cudaEventDestroy(e);
+}
 
 void LinearSolver::linearize(double t, double wM, double wA, const double* x) {
   t_ = t; wM_ = wM; wA_ = wA; x_ = x;
@@ -175,32 +184,69 @@ SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
   // skipped, r = b.
   { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::fill(n, 0.0, x, s); L++; }
   if (type == "BiCGSTAB") {
+    // dune-istl BiCGSTABSolver::apply, run one half step ahead of the host: every step length is
+    // formed on the device (kernels/linalg.cu), so the host only needs the defect norm to decide on
+    // convergence.  While it waits for the norm of half step k, half step k+1 is already queued;
+    // if k turns out to be the last one, the speculative work is dropped: the first half step never
+    // touches x and the second writes its iterate into the alternate buffer.
+    // Device scalars: s[0] = |r|^2 after the first half, s[2] = <rt,v>, s[4..5] = (<t,r>, <t,t>),
+    // pair k at s[8+2k] = (|r|^2 after the second half, <rt,r>) of the iterations with parity k.
     double *rt = work_[0].p, *p = work_[1].p, *v = work_[2].p, *t = work_[3].p, *y = work_[4].p, *y2 = work_[5].p;
+    double* sc = scal_.p;
+    auto pair = [&](int it_index) { return sc + 8 + 2 * (it_index & 1); };   // it_index may be -1
     // Jacobi is folded into the sweeps that produce its argument; other preconditioners run on their own
     const double* fold = prec_type == "Jacobi" && prec_iterations == 1 ? dinv_.p : nullptr;
     { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::copy(n, r, rt, s); L++; }
-    { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, r, r, scal_.p, ws_, s); L++; }
-    fetch(1);
+    // <rt,r> = <r,r> at the start: stored where iteration 0 looks for its rho
+    { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, r, r, pair(-1) + 1, ws_, s); L++; }
+    if (comm_) comm_->allreduce_sum(pair(-1) + 1, 1, s);
+    DCB_CUDA(cudaMemcpyAsync(hscal_.p, pair(-1) + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+    DCB_CUDA(cudaStreamSynchronize(s));
     double norm0 = std::sqrt(hscal_.p[0]), norm = norm0;
     res.defect0 = norm0;
     if (!(norm0 == norm0)) { res.converged = false; return res; }
     if (norm0 < 1e-30) { res.converged = true; res.reduction = 0; return res; }
-    double rho = 1, alpha = 1, omega = 1, rho_new = hscal_.p[0];   // <rt,r> = <r,r> at the start
-    double it = 0.5;
-    bool pending = false;   // x += alpha*y of the first half step is applied together with the second
-    for (; it < max_iterations; it += 0.5) {
-      // rho_new = <rt,r> was produced by the previous sweep (fused with the norm)
-      if (std::fabs(rho) <= 1e-80 || std::fabs(omega) <= 1e-80) break;   // breakdown (SolverAbort)
-      double beta = (rho_new / rho) * (alpha / omega);
-      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::bicg_p_prec(n, p, r, v, beta, omega, it < 1, fold, relaxation, y, s); L++; }
+    double rho = 1, alpha = 1, omega = 1, rho_new = hscal_.p[0];
+    double *x_cur = x, *x_alt = xalt_.p;
+    auto first_half = [&](int i) {
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1");
+        la::bicg_p_prec(n, p, r, v, pair(i - 1) + 1, pair(i - 2) + 1, sc + 2, sc + 4, i == 0, fold, relaxation, y, s); L++; }
       if (!fold) precondition(p, y);
       apply_operator(y, v);
-      // <rt,v> stays on the device (slot 2); alpha is formed inside the next sweep
-      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, rt, v, scal_.p + 2, ws_, s); L++; }
-      if (comm_) comm_->allreduce_sum(scal_.p + 2, 1, s);
-      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::bicg_r_prec(n, own, rho_new, scal_.p + 2, v, r, fold, relaxation, y2, scal_.p, ws_, s); L++; }
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, rt, v, sc + 2, ws_, s); L++; }
+      if (comm_) comm_->allreduce_sum(sc + 2, 1, s);
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1");
+        la::bicg_r_prec(n, own, pair(i - 1) + 1, sc + 2, v, r, fold, relaxation, y2, sc, ws_, s); L++; }
+      if (comm_) comm_->allreduce_sum(sc, 1, s);
+      DCB_CUDA(cudaMemcpyAsync(hscal_.p, sc, sizeof(double) * 3, cudaMemcpyDeviceToHost, s));
+      DCB_CUDA(cudaEventRecord(ev_[0], s));
+    };
+    auto second_half = [&](int i, const double* xin, double* xout) {
+      if (!fold) precondition(r, y2);
+      apply_operator(y2, t);
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot2(own, t, r, t, t, sc + 4, ws_, s); L++; }
+      if (comm_) comm_->allreduce_sum(sc + 4, 2, s);
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1");
+        la::bicg_final(n, own, pair(i - 1) + 1, sc + 2, sc + 4, y, y2, xin, xout, t, r, rt, pair(i), ws_, s); L++; }
+      if (comm_) comm_->allreduce_sum(pair(i), 2, s);
+      DCB_CUDA(cudaMemcpyAsync(hscal_.p + 4, sc + 4, sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
+      DCB_CUDA(cudaEventRecord(ev_[1], s));
+    };
+    // work ahead only while the last known defect is two orders above the target: the half steps
+    // right before convergence are the ones whose speculative successor would be thrown away
+    auto speculate = [&](double known_norm) { return speculation && known_norm >= 100.0 * rel_tol * norm0; };
+    double it = 0.5;
+    bool pending = false;   // x += alpha*y of the first half step is applied together with the second
+    int i = 0;
+    bool queued = false;    // first half of iteration i already enqueued
+    for (; it < max_iterations; it += 0.5, ++i) {
+      if (std::fabs(rho) <= 1e-80 || std::fabs(omega) <= 1e-80) break;   // breakdown (SolverAbort)
+      if (!queued) first_half(i);
+      queued = false;
+      const bool ahead = speculate(norm);
+      if (ahead) second_half(i, x_cur, x_alt);            // speculative
+      DCB_CUDA(cudaEventSynchronize(ev_[0]));
       pending = true;
-      fetch_slots(0, 1, 4);          // all-reduce the norm, read norm and <rt,v> back
       double h = hscal_.p[2];
       alpha = rho_new / h;
       norm = std::sqrt(hscal_.p[0]);
@@ -208,22 +254,22 @@ SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
       if (std::fabs(h) < 1e-80 || !(norm == norm)) break;
       if (norm < rel_tol * norm0 || norm < 1e-30) { res.converged = true; break; }
       it += 0.5;
-      if (!fold) precondition(r, y2);
-      apply_operator(y2, t);
-      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot2(own, t, r, t, t, scal_.p + 4, ws_, s); L++; }
-      if (comm_) comm_->allreduce_sum(scal_.p + 4, 2, s);
-      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::bicg_final(n, own, rho_new, scal_.p + 2, scal_.p + 4, y, y2, x, t, r, rt, scal_.p, ws_, s); L++; }
+      if (!ahead) second_half(i, x_cur, x_alt);
+      if (it + 0.5 < max_iterations && speculate(norm)) { first_half(i + 1); queued = true; }   // speculative
+      DCB_CUDA(cudaEventSynchronize(ev_[1]));
       pending = false;
-      fetch_slots(0, 2, 6);
+      std::swap(x_cur, x_alt);                            // the iterate of this iteration
+      const double* pr = hscal_.p + 8 + 2 * (i & 1);
       omega = hscal_.p[4] / hscal_.p[5];
       rho = rho_new;
-      rho_new = hscal_.p[1];
-      norm = std::sqrt(hscal_.p[0]);
+      rho_new = pr[1];
+      norm = std::sqrt(pr[0]);
       res.half_iterations++;
       if (!(norm == norm)) break;
       if (norm < rel_tol * norm0 || norm < 1e-30) { res.converged = true; break; }
     }
-    if (pending) { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::axpy(n, alpha, y, x, s); L++; }
+    if (pending) { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::axpy(n, alpha, y, x_cur, s); L++; }
+    if (x_cur != x) { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::copy(n, x_cur, x, s); L++; }
     res.iterations = (int)std::ceil(std::min<double>(it, max_iterations));
     res.reduction = norm / norm0;
   } else if (type == "RestartedGMRes") {

@@ -47,6 +47,9 @@ class LinearSolver {
   double relaxation = 1.0;
   int prec_iterations = 1;       // preconditioner.iterations (sweeps per application)
   int verbosity = 0;
+  // linear_solver.b200.speculation: BiCGSTAB enqueues the next half step before the host has seen
+  // the defect norm of the current one (results are identical either way)
+  bool speculation = true;
   DeviceBuffer<double> vals;     // CSR values of the current linearisation (matrix based)
 
  private:
@@ -60,7 +63,8 @@ class LinearSolver {
   la::ReduceWorkspace ws_;
   DeviceBuffer<double> scal_;               // device scalars of the reductions
   PinnedBuffer<double> hscal_;
-  DeviceBuffer<double> dinv_, bdiag_, work_[6], basis_, sweep_[3];
+  DeviceBuffer<double> dinv_, bdiag_, work_[6], basis_, sweep_[3], xalt_;
+  cudaEvent_t ev_[2] = {nullptr, nullptr};   // first / second half step of BiCGSTAB reached the host buffers
   // linearisation point
   double t_ = 0, wM_ = 0, wA_ = 0;
   const double* x_ = nullptr;

@@ -15,7 +15,7 @@
  *   dcb_grid_pattern       <- basisToPattern + patternToMatrix       make_step_operator.hh:378-384
  *                             = localAssemblePattern{Volume,Skeleton,Boundary}     :276-399
  *   dcb_solver_*           <- LinearSolver::apply                    make_step_operator.hh:102-146
- *                             (dune-istl BiCGSTAB/CG/RestartedGMRes + Jacobi/BlockJacobi, solver/istl/**)
+ *                             (dune-istl BiCGSTAB/CG/RestartedGMRes + Jacobi/BlockJacobi, solver/istl/)
  *   dcb_stepper_*          <- PDELab::OneStep (RungeKutta o Newton)  make_step_operator.hh:408-443,
  *                             SimpleAdaptiveStepper                  common/stepper.hh:337-368
  *   dcb_reducer_*          <- DiffusionReaction::reduce              diffusion_reaction/reduce.hh:38-285
