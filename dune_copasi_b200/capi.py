@@ -73,6 +73,7 @@ SYMBOLS = {
     "dcb_grid_get_facets": (C.c_int, [_P, _I64, _I64, _I32, _I32]),
     "dcb_grid_pattern": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32]),
     "dcb_grid_interpolate": (C.c_int, [_P, _P, C.c_double, _D]),
+    "dcb_grid_write_vtk": (C.c_int, [_P, _P, _D, C.c_double, C.c_char_p, C.c_int]),
     "dcb_grid_constraints": (C.c_int64, [_P, _P, _I32, _D, C.c_int64]),
     "dcb_operator_create": (_P, [_P, _P]),
     "dcb_operator_destroy": (None, [_P]),
@@ -260,6 +261,10 @@ class Grid:
         u = np.empty(self.ndofs)
         _check(lib().dcb_grid_interpolate(self.h, model.h, time, _d(u)))
         return u
+
+    def write_vtk(self, model, u, time, path, append=True):
+        u = _f64(u)
+        _check(lib().dcb_grid_write_vtk(self.h, model.h, _d(u), time, str(path).encode(), 1 if append else 0))
 
     def constraints(self, model):
         n = lib().dcb_grid_constraints(self.h, model.h, None, None, 0)

@@ -2,6 +2,7 @@
 #include "../../include/dune_copasi_b200.h"
 
 #include <cstring>
+#include <map>
 #include <memory>
 
 #include "comm.hpp"
@@ -21,6 +22,7 @@ struct dcb_grid {
   std::shared_ptr<Grid> g;
   std::vector<int64_t> rowptr;
   std::vector<int32_t> colidx;
+  std::map<std::string, std::vector<double>> vtk_timesteps;   // per output path, as Model::_writer_timesteps
 };
 struct dcb_comm { std::unique_ptr<Communicator> c; };
 struct dcb_operator {
@@ -387,6 +389,11 @@ int dcb_stepper_stats(const dcb_stepper* s, dcb_step_stats* o) {
   o->residual_evaluations = st.residual_evaluations; o->linearizations = st.linearizations;
   o->kernel_launches = s->op->op->stats.launches;
   return 0;
+}
+
+// ---- output
+int dcb_grid_write_vtk(dcb_grid* g, const dcb_model* m, const double* u_host, double time, const char* path, int append) {
+  return guard([&] { write_vtk(*g->g, *m->m, u_host, time, path, append != 0, g->vtk_timesteps[path]); });
 }
 
 // ---- reduce

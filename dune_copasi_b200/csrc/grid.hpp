@@ -80,4 +80,9 @@ struct Grid {
   void constraints(const Model& model, std::vector<int32_t>& dofs, std::vector<double>& vals) const;
 };
 
+// VTK output (vtk.cpp): "<path>/<stem>-<compartment>-<00000>.vtu" + "<path>/<stem>-<compartment>.pvd";
+// `timesteps` holds the stamps already written under `path` and is cleared unless `append`
+void write_vtk(const Grid& grid, const Model& model, const double* u, double time, const std::string& path,
+               bool append, std::vector<double>& timesteps);
+
 }  // namespace dcb

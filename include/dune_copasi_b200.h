@@ -117,6 +117,10 @@ int dcb_grid_get_facets(const dcb_grid*, int64_t* f_in, int64_t* f_out, int32_t*
 int dcb_grid_pattern(dcb_grid*, const dcb_model*, int64_t* nrows, int64_t* nnz, int64_t* rowptr,
                      int32_t* colidx);
 int dcb_grid_interpolate(const dcb_grid*, const dcb_model*, double time, double* u);
+/* Model::write_vtk (diffusion_reaction/model_multi_compartment.impl.hh:218-300): per compartment
+ * "<path>/<stem>-<compartment>-<00000>.vtu" with one vertex-data array per species, and
+ * "<path>/<stem>-<compartment>.pvd"; append = 0 restarts the time sequence of `path` */
+int dcb_grid_write_vtk(dcb_grid*, const dcb_model*, const double* u_host, double time, const char* path, int append);
 int64_t dcb_grid_constraints(const dcb_grid*, const dcb_model*, int32_t* dofs, double* vals, int64_t cap);
 
 /* ---- device operator ---- */

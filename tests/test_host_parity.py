@@ -92,6 +92,41 @@ def test_configuration_errors_are_loud():
         D.Grid.structured(2, [2, 2]).bind(model)
 
 
+def test_vtk_output_round_trips(tmp_path):
+    """Model::write_vtk layout (model_multi_compartment.impl.hh:218-300): one .vtu per compartment and
+    stamp with a vertex array per species, a .pvd per compartment; values read back exactly."""
+    import xml.etree.ElementTree as ET
+    case = K.CASES["two_disks"]
+    om = case.oracle()
+    cfg, model, grid = K.product_objects(case)
+    out = tmp_path / "run" / "two_disks"
+    u = K.rand_state(om.ndofs, 3)
+    grid.write_vtk(model, u, 0.0, out, append=False)
+    grid.write_vtk(model, 2.0 * u, 0.5, out, append=True)
+    names = sorted(p.name for p in out.iterdir())
+    assert names == ["two_disks-inner-00000.vtu", "two_disks-inner-00001.vtu", "two_disks-inner.pvd",
+                     "two_disks-outer-00000.vtu", "two_disks-outer-00001.vtu", "two_disks-outer.pvd"]
+    m = om.mesh
+    for c, cname in enumerate(om.comp_names):
+        piece = ET.parse(out / f"two_disks-{cname}-00001.vtu").getroot().find("UnstructuredGrid/Piece")
+        verts = m.comp_vertices[c]
+        assert int(piece.get("NumberOfPoints")) == len(verts)
+        assert int(piece.get("NumberOfCells")) == int((m.elem_comp == c).sum())
+        arrays = {a.get("Name"): np.array(a.text.split(), dtype=float) for a in piece.iter("DataArray")}
+        sp = [s for s in om.species if s.comp == c]
+        for s in sp:
+            expect = 2.0 * u[m.comp_offset[c] + np.arange(len(verts)) * len(sp) + s.local]
+            assert np.array_equal(arrays[s.name], expect)
+        assert np.array_equal(arrays["Coordinates"].reshape(-1, 3)[:, :2], m.coords[verts])
+        conn = arrays["connectivity"].astype(int).reshape(-1, 3)
+        assert np.array_equal(np.asarray(verts)[conn], m.elems[m.elem_comp == c])
+        assert set(arrays["types"]) == {5.0}
+        stamps = [float(d.get("timestep")) for d in ET.parse(out / f"two_disks-{cname}.pvd").getroot().iter("DataSet")]
+        assert stamps == [0.0, 0.5]
+    grid.write_vtk(model, u, 1.0, out, append=False)      # restart of the sequence
+    assert len(list(ET.parse(out / "two_disks-inner.pvd").getroot().iter("DataSet"))) == 1
+
+
 def test_reduce_kernels_compile_without_a_gpu_and_errors_are_loud():
     import dune_copasi_b200 as D
     for name in ("gauss2d", "two_disks", "cell3d"):
