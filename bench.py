@@ -140,7 +140,8 @@ def cpu_baseline(args, steps, warmup, cells):
     available) with OpenMP over all host cores, on a bounded sample of the workload."""
     from oracle import core as ORC, ini as INI, mesh as OMESH
     cfg = INI.parse_ini(ini_for(args))
-    mesh = OMESH.structured(3, [cells] * 3)
+    dim = getattr(args, "dim", 3)
+    mesh = OMESH.structured(dim, [cells] * dim)
     om = ORC.Model(cfg, mesh)
     S = ORC.StepOperator(om, par=1)
     u = om.initial(0.0)
@@ -156,7 +157,7 @@ def cpu_baseline(args, steps, warmup, cells):
     wall = time.perf_counter() - t0
     cores = ORC.lib().orc_num_threads()
     return {"value": om.ndofs * steps / wall, "unit": "DOF-updates/s", "cores": int(cores), "kind": "port",
-            "sample": f"{steps} steps (after {warmup} warm-up) of the same model on a {cells}^3 lattice "
+            "sample": f"{steps} steps (after {warmup} warm-up) of the same model on a {cells}^{dim} lattice "
                       f"({om.ndofs} DOFs), matrix based, OpenMP over {cores} threads",
             "ms_per_step": 1e3 * wall / steps}, om.ndofs, wall
 
@@ -176,8 +177,9 @@ def run_reference(args):
 
 
 def config_dict(args, cells):
-    name = "cell3d_3comp_6species" if getattr(args, "workload", "grayscott") == "cell" else "grayscott3d"
-    return {"workload": f"{name}_p1_kuhn_{cells}^3", "cells": cells, "dt": args.dt, "rk": args.rk,
+    dim = getattr(args, "dim", 3)
+    name = "cell3d_3comp_6species" if getattr(args, "workload", "grayscott") == "cell" else f"grayscott{dim}d"
+    return {"workload": f"{name}_p1_kuhn_{cells}^{dim}", "cells": cells, "dt": args.dt, "rk": args.rk,
             "linear_solver": "BiCGSTAB", "preconditioner": args.prec, "matrix_free": bool(args.matrix_free),
             "linear_rel_tol": 1e-8, "newton_rel_tol": 1e-8, "assembly": args.scheme,
             "l2": "inputs larger than L2 (every vector and the mesh exceed 126 MB at the default size)"}
@@ -190,6 +192,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cells", type=int, default=256)
+    ap.add_argument("--dim", type=int, default=3, choices=[2, 3], help="3: the headline lattice; 2: SURVEY 8d S-2D squares")
     ap.add_argument("--cpu-cells", type=int, default=40)
     ap.add_argument("--dt", type=float, default=1.0)
     ap.add_argument("--rk", default="Alexander2")
@@ -222,9 +225,9 @@ def main():
 
     # ---- problem
     cfg = D.Config(ini_for(args))
-    model = D.Model(cfg, 3)
+    model = D.Model(cfg, args.dim)
     t_setup = time.perf_counter()
-    gglobal = D.Grid.structured(3, [args.cells] * 3)
+    gglobal = D.Grid.structured(args.dim, [args.cells] * args.dim)
     nv_global = gglobal.nv
     grid = gglobal.partition(rank, world) if world > 1 else gglobal
     grid.bind(model)
@@ -319,13 +322,14 @@ def main():
     value = ndofs_global * args.steps / (ms * 1e-3)
     # ---- roofline of the dominant kernel (by accumulated device time in the timed region)
     peak, peak_src = peaks()
-    nodes, tets = nv_global / world, 6 * args.cells ** 3 / world
+    dim = args.dim
+    nodes, tets = nv_global / world, (6 if dim == 3 else 2) * args.cells ** dim / world
     alg = {  # algorithmic bytes per launch, SURVEY.md 8(d) (per rank)
-        "patch_apply": nodes * (16 * 2 + 8 * 3 + 8 * 2) + tets * 16,
-        "patch_residual": nodes * (16 * 2 + 8 * 3) + tets * 16,
-        "patch_bdiag": nodes * (8 * 2 + 8 * 3 + 8 * 4) + tets * 16,
-        "elem_apply": nodes * (16 * 2 + 8 * 3 + 8 * 2) + tets * 16,
-        "elem_residual": nodes * (16 * 2 + 8 * 3) + tets * 16,
+        "patch_apply": nodes * (16 * 2 + 8 * dim + 8 * 2) + tets * 4 * (dim + 1),
+        "patch_residual": nodes * (16 * 2 + 8 * dim) + tets * 4 * (dim + 1),
+        "patch_bdiag": nodes * (8 * 2 + 8 * dim + 8 * 4) + tets * 4 * (dim + 1),
+        "elem_apply": nodes * (16 * 2 + 8 * dim + 8 * 2) + tets * 4 * (dim + 1),
+        "elem_residual": nodes * (16 * 2 + 8 * dim) + tets * 4 * (dim + 1),
         "spmv": op.ndofs * 30 * 12 + op.ndofs * 20,
         # structured-implicit variant: no connectivity, no coordinates (32 B/vertex)
         "struct_residual": nodes * (16 * 2),
@@ -346,8 +350,8 @@ def main():
         # report the live fp64 instruction rate against that peak next to the HBM fraction
         path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         per_cell = json.load(open(path)).get(f"{top}.fp64_instr_per_cell") if os.path.exists(path) else None
-        if per_cell and clocks and clocks.get("sm_mhz"):
-            cells_rank = args.cells ** 3 / world
+        if per_cell and dim == 3 and clocks and clocks.get("sm_mhz"):
+            cells_rank = args.cells ** dim / world
             rate = cells_rank * per_cell / (avg_ms * 1e-3)
             peak64 = 148 * 64 * clocks["sm_mhz"] * 1e6
             roof["fp64_pipe"] = {"instr_per_cell": per_cell, "achieved_ginstr_s": rate / 1e9,

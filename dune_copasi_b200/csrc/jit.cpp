@@ -55,14 +55,23 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
     }
   }
   if (all || group == JitGroup::Skeleton) {
+    // One launch covers the facet lists of every directional compartment pair: the lists are small
+    // (interfaces), so separate launches would be a chain of latency-bound kernels.  Blocks
+    // [first[p], first[p+1]) work on pair p.
     size_t np = model.outflow_pairs().size();
-    for (size_t p = 0; p < np; ++p) {
-      o << "extern \"C\" __global__ void __launch_bounds__(64) dc_k_skeleton_residual_" << p
-        << "(DcFacetArgs a) { dc_skeleton_residual<" << p << ">(a); }\n";
-      const char* names[3] = {"jacobian", "apply", "bdiag"};
-      for (int mode = 0; mode < 3; ++mode)
-        o << "extern \"C\" __global__ void __launch_bounds__(64) dc_k_skeleton_" << names[mode] << "_" << p
-          << "(DcFacetArgs a) { dc_skeleton_jacobian<" << p << ", " << mode << ">(a); }\n";
+    if (np) {
+      o << "struct DcFacetArgsAll { DcFacetArgs a[" << np << "]; int first[" << np + 1 << "]; };\n";
+      const char* names[4] = {"residual", "jacobian", "apply", "bdiag"};
+      for (int mode = 0; mode < 4; ++mode) {
+        o << "extern \"C\" __global__ void __launch_bounds__(64) dc_k_skeleton_" << names[mode] << "(DcFacetArgsAll A) {\n";
+        for (size_t p = 0; p < np; ++p) {
+          o << "  if ((int)blockIdx.x < A.first[" << p + 1 << "]) { ";
+          if (mode == 0) o << "dc_skeleton_residual<" << p << ">(A.a[" << p << "]);";
+          else o << "dc_skeleton_jacobian<" << p << ", " << mode - 1 << ">(A.a[" << p << "]);";
+          o << " return; }\n";
+        }
+        o << "}\n";
+      }
     }
   }
   return o.str();

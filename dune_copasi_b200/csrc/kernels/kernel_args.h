@@ -71,6 +71,7 @@ struct DcFacetArgs {
   long long ne_total;
   long long n;
   int dof_offset_s, dof_offset_t;
+  int block_offset;            // first block of this list inside a fused launch over all pairs
   double time, wA;
   const double* x;
   const double* z;

@@ -455,39 +455,53 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
 
 void DeviceOperator::launch_facets(const char* kind, double t, double wA, const double* x,
                                    const double* z, double* r, double* vals, double* bdiag) {
-  for (size_t p = 0; p < facets_.size(); ++p) {
+  // one fused launch over the facet lists of all directional pairs; the argument block mirrors the
+  // generated `struct DcFacetArgsAll { DcFacetArgs a[np]; int first[np + 1]; }` (jit.cpp)
+  const size_t np = facets_.size();
+  if (np == 0) return;
+  std::vector<char> blob(np * sizeof(DcFacetArgs) + (np + 1) * sizeof(int), 0);
+  auto* args = reinterpret_cast<DcFacetArgs*>(blob.data());
+  auto* first = reinterpret_cast<int*>(blob.data() + np * sizeof(DcFacetArgs));
+  int blocks = 0;
+  for (size_t p = 0; p < np; ++p) {
     const FacetList& F = facets_[p];
-    if (F.n == 0) continue;
     DcFacetArgs a{};
     a.coords = coords_.p; a.elems = elems_.p;
     a.f_self = F.f_self.p; a.f_other = F.f_other.p; a.f_lself = F.f_lself.p; a.f_lother = F.f_lother.p;
     a.vdof_s = comp_vdof_[F.cs].p; a.vdof_t = comp_vdof_[F.ct].p;
     a.cell = cell_.p; a.ne_total = grid->ne; a.n = F.n;
     a.dof_offset_s = (int)grid->comp_offset[F.cs]; a.dof_offset_t = (int)grid->comp_offset[F.ct];
+    a.block_offset = blocks;
     a.time = t; a.wA = wA; a.x = x; a.z = z; a.r = r;
     a.rowptr = (const long long*)rowptr.p; a.colidx = colidx.p; a.vals = vals;
     a.bdiag = bdiag ? bdiag + bdiag_shift(F.cs) : nullptr;
     a.cmask = cmask.p;
-    cudaKernel_t k = kernel(JitGroup::Skeleton, std::string(kind) + std::to_string(p));
-    ProfScope ps(this, "facets");
-    jit_launch(k, (unsigned)((F.n + 63) / 64), 64, 0, stream, a);
-    stats.launches++;
+    args[p] = a;
+    first[p] = blocks;
+    blocks += (int)((F.n + 63) / 64);
   }
+  first[np] = blocks;
+  if (blocks == 0) return;
+  cudaKernel_t k = kernel(JitGroup::Skeleton, kind);
+  ProfScope ps(this, "facets");
+  void* params[] = {(void*)blob.data()};
+  DCB_CUDA(cudaLaunchKernel((const void*)k, dim3((unsigned)blocks), dim3(64), params, 0, stream));
+  stats.launches++;
 }
 
 void DeviceOperator::residual(double t, double wM, double wA, const double* x, double* r) {
   launch_volume("dc_k_residual_volume_", 0, t, wM, wA, x, nullptr, r, nullptr, nullptr);
-  if (wA != 0.0) launch_facets("dc_k_skeleton_residual_", t, wA, x, nullptr, r, nullptr, nullptr);
+  if (wA != 0.0) launch_facets("dc_k_skeleton_residual", t, wA, x, nullptr, r, nullptr, nullptr);
 }
 
 void DeviceOperator::jacobian_apply(double t, double wM, double wA, const double* x, const double* z, double* y) {
   launch_volume("dc_k_jacobian_apply_volume_", 1, t, wM, wA, x, z, y, nullptr, nullptr);
-  if (wA != 0.0) launch_facets("dc_k_skeleton_apply_", t, wA, x, z, y, nullptr, nullptr);
+  if (wA != 0.0) launch_facets("dc_k_skeleton_apply", t, wA, x, z, y, nullptr, nullptr);
 }
 
 void DeviceOperator::block_diag(double t, double wM, double wA, const double* x, double* bdiag) {
   launch_volume("dc_k_bdiag_volume_", 2, t, wM, wA, x, nullptr, nullptr, nullptr, bdiag);
-  if (wA != 0.0) launch_facets("dc_k_skeleton_bdiag_", t, wA, x, nullptr, nullptr, nullptr, bdiag);
+  if (wA != 0.0) launch_facets("dc_k_skeleton_bdiag", t, wA, x, nullptr, nullptr, nullptr, bdiag);
 }
 
 bool DeviceOperator::scalar_diag(double t, double wM, double wA, const double* x, double* diag) {
@@ -499,7 +513,7 @@ bool DeviceOperator::scalar_diag(double t, double wM, double wA, const double* x
 void DeviceOperator::jacobian_csr(double t, double wM, double wA, const double* x, double* vals) {
   ensure_csr();
   launch_volume("dc_k_jacobian_volume_", 3, t, wM, wA, x, nullptr, nullptr, vals, nullptr);
-  if (wA != 0.0) launch_facets("dc_k_skeleton_jacobian_", t, wA, x, nullptr, nullptr, vals, nullptr);
+  if (wA != 0.0) launch_facets("dc_k_skeleton_jacobian", t, wA, x, nullptr, nullptr, vals, nullptr);
 }
 
 void DeviceOperator::ensure_csr() {
