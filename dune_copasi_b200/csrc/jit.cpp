@@ -33,7 +33,7 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
         << "(DcVolArgs a) { dc_jacobian_volume<" << c << ", 1>(a); }\n";
     }
     if (all || group == JitGroup::Csr)
-      o << "extern \"C\" __global__ void __launch_bounds__(128) dc_k_jacobian_volume_" << c
+      o << "extern \"C\" __global__ void __launch_bounds__(128, DC_CSR_MINB) dc_k_jacobian_volume_" << c
         << "(DcVolArgs a) { dc_jacobian_volume<" << c << ", 0>(a); }\n";
     if (all || group == JitGroup::Patch) {
       o << "extern \"C\" __global__ void __launch_bounds__(DC_PATCH_THREADS, DC_PATCH_MINB) dc_k_patch_residual_" << c
@@ -86,7 +86,11 @@ std::string jit_defines(const Model& model) {
   int sth = acfg.get("struct_threads", 64), sminb = acfg.get("struct_min_blocks", 6);
   if (sth < 32 || sth > 1024 || sth % 32) fail("model.assembly.b200.struct_threads must be a multiple of 32 in [32,1024]");
   if (sminb < 1 || sminb > 16) fail("model.assembly.b200.struct_min_blocks out of range");
-  return "#define DC_PATCH_THREADS " + std::to_string(th) + "\n#define DC_PATCH_MINB " + std::to_string(minb) +
+  // CSR fill is latency bound (binary searches + fp64 atomics): 8 resident CTAs of 128 threads
+  // measured 16 % faster than 4 on B200 despite the spills (profiles/r01_csr_fill_128_ncu.txt)
+  int cminb = acfg.get("csr_min_blocks", 8);
+  if (cminb < 1 || cminb > 16) fail("model.assembly.b200.csr_min_blocks out of range");
+  return "#define DC_CSR_MINB " + std::to_string(cminb) + "\n#define DC_PATCH_THREADS " + std::to_string(th) + "\n#define DC_PATCH_MINB " + std::to_string(minb) +
          "\n#define DC_STRUCT_THREADS " + std::to_string(sth) + "\n#define DC_STRUCT_MINB " + std::to_string(sminb) + "\n";
 }
 
