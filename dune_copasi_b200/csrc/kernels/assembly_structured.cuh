@@ -49,7 +49,7 @@ __device__ __forceinline__ void dc_structured_kernel(const DcStructArgs& a) {
   typedef DcComp<C> M;
   constexpr int NS = M::NS;
   constexpr int NV = MODE == 2 ? NS * NS : NS;
-  const long long cell = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long cell = a.cell_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (cell >= a.ncells) return;
   int idx[3];
   {

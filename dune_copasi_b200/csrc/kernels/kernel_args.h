@@ -48,6 +48,7 @@ struct DcPatchArgs {
 struct DcStructArgs {
   int n[3];                    // cells per axis of the (local) box
   double h[3], origin[3];
+  long long cell_begin;        // this launch covers the cells [cell_begin, ncells)
   long long ncells;
   int dof_offset;
   double time, wM, wA;

@@ -401,10 +401,22 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       static const char* sn[5] = {"dc_k_struct_residual_", "dc_k_struct_apply_", "dc_k_struct_bdiag_", "", "dc_k_struct_diag_"};
       static const char* sk[5] = {"struct_residual", "struct_apply", "struct_bdiag", "", "struct_diag"};
       cudaKernel_t k = kernel(JitGroup::Structured, std::string(sn[mode]) + std::to_string(c));
-      ProfScope ps(this, sk[mode]);
       const int sth = model->cfg.sub("model.assembly.b200").get("struct_threads", 64);
-      jit_launch(k, (unsigned)((a.ncells + sth - 1) / sth), sth, 0, stream, a);
-      stats.launches++;
+      // cell ranges of this launch: everything, or (multi-GPU overlap) the interior layers /
+      // the two layers along the slab axis that touch ghost planes
+      const long long total = a.ncells, layer = total / a.n[grid->dim - 1];
+      long long ranges[2][2] = {{0, total}, {0, 0}};
+      int nranges = 1;
+      if (struct_part_ == 1) { ranges[0][0] = layer; ranges[0][1] = total - layer; }
+      if (struct_part_ == 2) { ranges[0][1] = layer; ranges[1][0] = total - layer; ranges[1][1] = total; nranges = 2; }
+      for (int q = 0; q < nranges; ++q) {
+        a.cell_begin = ranges[q][0];
+        a.ncells = ranges[q][1];
+        if (a.ncells <= a.cell_begin) continue;
+        ProfScope ps(this, struct_part_ == 2 ? "struct_apply_halo_layers" : sk[mode]);
+        jit_launch(k, (unsigned)((a.ncells - a.cell_begin + sth - 1) / sth), sth, 0, stream, a);
+        stats.launches++;
+      }
       continue;
     }
     // the block-diagonal buffer grows with ns^2: fall back to the element kernel when it cannot be staged
@@ -494,8 +506,20 @@ void DeviceOperator::residual(double t, double wM, double wA, const double* x, d
   if (wA != 0.0) launch_facets("dc_k_skeleton_residual", t, wA, x, nullptr, r, nullptr, nullptr);
 }
 
-void DeviceOperator::jacobian_apply(double t, double wM, double wA, const double* x, const double* z, double* y) {
+bool DeviceOperator::can_split_apply() const {
+  int with_species = 0;
+  for (int c = 0; c < model->ncomp(); ++c) with_species += model->comp_nspec[c] > 0;
+  return scheme == "structured" && facets_.empty() && with_species == 1 && struct_comp_ >= 0 &&
+         !model->numerical_jacobian && grid->s_cells[grid->dim - 1] >= 3;
+}
+
+void DeviceOperator::jacobian_apply(double t, double wM, double wA, const double* x, const double* z, double* y,
+                                    int part) {
+  if (part != 0 && !can_split_apply()) fail("jacobian_apply: this operator cannot be split into interior / halo layers");
+  struct_part_ = part;
   launch_volume("dc_k_jacobian_apply_volume_", 1, t, wM, wA, x, z, y, nullptr, nullptr);
+  struct_part_ = 0;
+  if (part != 0) return;   // no facet terms on a splittable operator
   if (wA != 0.0) launch_facets("dc_k_skeleton_apply", t, wA, x, z, y, nullptr, nullptr);
 }
 

@@ -48,7 +48,11 @@ class DeviceOperator {
 
   // all pointers are device pointers; everything is ordered on `stream`
   void residual(double t, double wM, double wA, const double* x, double* r);
-  void jacobian_apply(double t, double wM, double wA, const double* x, const double* z, double* y);
+  // part 0: all cells; 1 / 2 (only if can_split_apply()): the cells whose vertices are all owned /
+  // the two cell layers along the slab axis that read ghost planes -- lets the caller overlap the
+  // halo exchange of z with the interior cells
+  void jacobian_apply(double t, double wM, double wA, const double* x, const double* z, double* y, int part = 0);
+  bool can_split_apply() const;
   void jacobian_csr(double t, double wM, double wA, const double* x, double* vals);
   void block_diag(double t, double wM, double wA, const double* x, double* bdiag);
   // scalar diagonal straight into a dof-indexed vector (structured scheme without facet terms);
@@ -122,6 +126,7 @@ class DeviceOperator {
   int64_t ne_patch_total_ = 0;
   size_t patch_smem(const PatchSet& P, int ns, int mode) const;
   int struct_comp_ = -1;   // compartment handled by the structured kernels
+  int struct_part_ = 0;    // cell range selector of the next structured launch (jacobian_apply)
   int patch_pn_ = 256, patch_pe_ = 512, patch_threads_ = 256, patch_smem_kb_ = 64;
 };
 

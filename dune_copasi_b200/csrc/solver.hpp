@@ -65,6 +65,10 @@ class LinearSolver {
   PinnedBuffer<double> hscal_;
   DeviceBuffer<double> dinv_, bdiag_, work_[6], basis_, sweep_[3], xalt_;
   cudaEvent_t ev_[2] = {nullptr, nullptr};   // first / second half step of BiCGSTAB reached the host buffers
+  // linear_solver.b200.overlap_halo: halo exchange on its own stream under the interior cells
+  bool overlap_halo_ = false;
+  cudaStream_t halo_stream_ = nullptr;
+  cudaEvent_t halo_ev_[2] = {nullptr, nullptr};
   // linearisation point
   double t_ = 0, wM_ = 0, wA_ = 0;
   const double* x_ = nullptr;

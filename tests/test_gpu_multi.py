@@ -15,14 +15,18 @@ def _ngpus():
     return D.lib().dcb_device_count()
 
 
-@pytest.mark.parametrize("name,mf", [("grayscott3d", "1"), ("grayscott3d", "0"), ("cell3d", "1"), ("two_disks", "0"),
-                                     ("gauss3d", "1"), ("advection3d", "0")])
-def test_two_rank_time_stepping_matches_serial_oracle(name, mf):
+OVERLAP = "model.time_step_operator.linear_solver.b200.overlap_halo=true"
+
+
+@pytest.mark.parametrize("name,mf,extra", [("grayscott3d", "1", ""), ("grayscott3d", "0", ""), ("cell3d", "1", ""),
+                                           ("two_disks", "0", ""), ("gauss3d", "1", ""), ("advection3d", "0", ""),
+                                           ("grayscott3d", "1", OVERLAP)])
+def test_two_rank_time_stepping_matches_serial_oracle(name, mf, extra):
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "mgpu_check.py"),
-           name, "2", mf]
+           name, "2", mf, extra]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "rel L2 err" in r.stdout

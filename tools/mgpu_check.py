@@ -32,6 +32,9 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     case = K.CASES[name]
     over = {"model.time_step_operator.linear_solver.matrix_free": "true" if mf else "false"}
+    for kv in filter(None, (sys.argv[4] if len(sys.argv) > 4 else "").split(",")):   # extra ini overrides
+        k, v = kv.split("=")
+        over[k] = v
     gmesh = case.mesh_fn()
     cfg = D.Config(case.ini_with(**over))
     model = D.Model(cfg, case.dim, gmesh.cell_keys)
