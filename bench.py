@@ -193,7 +193,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cells", type=int, default=256)
     ap.add_argument("--dim", type=int, default=3, choices=[2, 3], help="3: the headline lattice; 2: SURVEY 8d S-2D squares")
-    ap.add_argument("--cpu-cells", type=int, default=40)
+    ap.add_argument("--cpu-cells", type=int, default=56, help="lattice of the bounded CPU sample (10-30 s of CPU work)")
     ap.add_argument("--dt", type=float, default=1.0)
     ap.add_argument("--rk", default="Alexander2")
     ap.add_argument("--prec", default="Jacobi")
@@ -367,7 +367,7 @@ def main():
     shutdown()
     if not args.no_cpu_baseline:
         # the CPU arm runs after the GPUs are released (rank 0 only)
-        line["cpu_baseline"], _, _ = cpu_baseline(args, 1, 1, args.cpu_cells)
+        line["cpu_baseline"], _, _ = cpu_baseline(args, 2, 1, args.cpu_cells)
     print(json.dumps(line), flush=True)
 
 

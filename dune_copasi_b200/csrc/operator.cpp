@@ -75,7 +75,7 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
   kernel(scheme == "patch" ? JitGroup::Patch : scheme == "structured" ? JitGroup::Structured : JitGroup::Element, "");
 
   // ---- mesh on the device
-  const int nd = grid->nd(), ncomp = model->ncomp();
+  const int ncomp = model->ncomp();
   coords_.upload(grid->coords, stream);
   elems_.upload(grid->elems, stream);
   if (!grid->cell_data.empty()) cell_.upload(grid->cell_data, stream);

@@ -55,7 +55,6 @@ class LinearSolver {
  private:
   void precondition(const double* d, double* v);
   void precondition_sweep(const double* d, double* v);   // one sweep from v = 0
-  double reduce1(double* dev2);             // host value of scal_[0] after a reduction
   void fetch(int n);
   void fetch_slots(int first, int count, int total);
   std::shared_ptr<DeviceOperator> op_;
