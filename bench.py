@@ -37,6 +37,12 @@ import cases as K  # noqa: E402
 METRIC = "DOF-updates/s (3D Gray-Scott, CG-P1 Kuhn tets, implicit time stepping)"
 
 
+def metric_name(args):
+    if getattr(args, "element", "p1") == "q1":
+        return "DOF-updates/s (3D Gray-Scott, CG-Q1 cubes, implicit time stepping)"
+    return METRIC
+
+
 def ini_for(args):
     over = {
         "model.time_step_operator.type": args.rk,
@@ -125,14 +131,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def measured_traffic(kernel, cells, world):
+def measured_traffic(kernel, cells, world, elem=""):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel
     from the committed `ncu --set full` capture of this workload (profiles/ncu_traffic.json), or
     None when that configuration has not been captured."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(path):
         return None
-    return json.load(open(path)).get(f"{kernel}@{cells}^3/n{world}")
+    return json.load(open(path)).get(f"{kernel}@{cells}^3/n{world}" + elem)
 
 
 def cpu_baseline(args, steps, warmup, cells):
@@ -141,7 +147,7 @@ def cpu_baseline(args, steps, warmup, cells):
     from oracle import core as ORC, ini as INI, mesh as OMESH
     cfg = INI.parse_ini(ini_for(args))
     dim = getattr(args, "dim", 3)
-    mesh = OMESH.structured(dim, [cells] * dim)
+    mesh = OMESH.structured(dim, [cells] * dim, element="cube" if getattr(args, "element", "p1") == "q1" else "simplex")
     om = ORC.Model(cfg, mesh)
     S = ORC.StepOperator(om, par=1)
     u = om.initial(0.0)
@@ -167,7 +173,7 @@ def run_reference(args):
     if rank != 0:
         return
     cb, ndofs, wall = cpu_baseline(args, args.steps, args.warmup, args.cpu_cells)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "DOF-updates/s",
+    line = {"impl": "reference", "metric": metric_name(args), "value": cb["value"], "unit": "DOF-updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, args.cpu_cells), "cpu_baseline": cb,
@@ -179,7 +185,8 @@ def run_reference(args):
 def config_dict(args, cells):
     dim = getattr(args, "dim", 3)
     name = "cell3d_3comp_6species" if getattr(args, "workload", "grayscott") == "cell" else f"grayscott{dim}d"
-    return {"workload": f"{name}_p1_kuhn_{cells}^{dim}", "cells": cells, "dt": args.dt, "rk": args.rk,
+    elem = "q1_cubes" if getattr(args, "element", "p1") == "q1" else "p1_kuhn"
+    return {"workload": f"{name}_{elem}_{cells}^{dim}", "element": elem, "cells": cells, "dt": args.dt, "rk": args.rk,
             "linear_solver": "BiCGSTAB", "preconditioner": args.prec, "matrix_free": bool(args.matrix_free),
             "linear_rel_tol": 1e-8, "newton_rel_tol": 1e-8, "assembly": args.scheme,
             "l2": "inputs larger than L2 (every vector and the mesh exceed 126 MB at the default size)"}
@@ -193,6 +200,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cells", type=int, default=256)
     ap.add_argument("--dim", type=int, default=3, choices=[2, 3], help="3: the headline lattice; 2: SURVEY 8d S-2D squares")
+    ap.add_argument("--element", default="p1", choices=["p1", "q1"],
+                    help="p1: Kuhn simplices, the reference's element (headline); q1: the lattice cells as Q1 "
+                         "elements, BASELINE configs[3]'s wording (not a reference capability, own oracle)")
     ap.add_argument("--cpu-cells", type=int, default=56, help="lattice of the bounded CPU sample (10-30 s of CPU work)")
     ap.add_argument("--dt", type=float, default=1.0)
     ap.add_argument("--rk", default="Alexander2")
@@ -227,7 +237,7 @@ def main():
     cfg = D.Config(ini_for(args))
     model = D.Model(cfg, args.dim)
     t_setup = time.perf_counter()
-    gglobal = D.Grid.structured(args.dim, [args.cells] * args.dim)
+    gglobal = D.Grid.structured(args.dim, [args.cells] * args.dim, element="cube" if args.element == "q1" else "simplex")
     nv_global = gglobal.nv
     grid = gglobal.partition(rank, world) if world > 1 else gglobal
     grid.bind(model)
@@ -330,7 +340,7 @@ def main():
         "patch_bdiag": nodes * (8 * 2 + 8 * dim + 8 * 4) + tets * 4 * (dim + 1),
         "elem_apply": nodes * (16 * 2 + 8 * dim + 8 * 2) + tets * 4 * (dim + 1),
         "elem_residual": nodes * (16 * 2 + 8 * dim) + tets * 4 * (dim + 1),
-        "spmv": op.ndofs * 30 * 12 + op.ndofs * 20,
+        "spmv": op.ndofs * (54 if args.element == "q1" else 30) * 12 + op.ndofs * 20,
         # structured-implicit variant: no connectivity, no coordinates (32 B/vertex)
         "struct_residual": nodes * (16 * 2),
         "struct_apply": nodes * (16 * 2 + 8 * 2),
@@ -342,14 +352,15 @@ def main():
         avg_ms = prof[top]["ms"] / max(1, prof[top]["launches"])
         ach = alg.get(top, 0.0) / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": measured_traffic(top, args.cells, world), "algorithmic_bytes": alg.get(top, 0.0),
+                "traffic": measured_traffic(top, args.cells, world, "/q1" if args.element == "q1" else ""), "algorithmic_bytes": alg.get(top, 0.0),
                 "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches": prof[top]["launches"],
                 "share_of_step": prof[top]["ms"] / ms,
                 "breakdown_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}}
         # the assembly kernels are fp64-pipe bound on B200 (64 fp64 lanes/SM/clk), not HBM bound:
         # report the live fp64 instruction rate against that peak next to the HBM fraction
         path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        per_cell = json.load(open(path)).get(f"{top}.fp64_instr_per_cell") if os.path.exists(path) else None
+        key = f"{top}.fp64_instr_per_cell" + (".q1" if args.element == "q1" else "")
+        per_cell = json.load(open(path)).get(key) if os.path.exists(path) else None
         if per_cell and dim == 3 and clocks and clocks.get("sm_mhz"):
             cells_rank = args.cells ** dim / world
             rate = cells_rank * per_cell / (avg_ms * 1e-3)
@@ -358,7 +369,7 @@ def main():
                                  "peak_ginstr_s": peak64 / 1e9, "frac": rate / peak64,
                                  "note": "dominant kernel is bound by the fp64 pipe; HBM traffic is ~1.3x algorithmic"}
     cb = None
-    line = {"metric": METRIC, "value": value, "unit": "DOF-updates/s", "n_gpus": world, "steps": args.steps,
+    line = {"metric": metric_name(args), "value": value, "unit": "DOF-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, args.cells),
             "time_steps_per_s": args.steps / (ms * 1e-3), "dofs": int(ndofs_global), "e2e": e2e,

@@ -49,6 +49,8 @@ SYMBOLS = {
     "dcb_config_set": (C.c_int, [_P, C.c_char_p, C.c_char_p]),
     "dcb_config_dump": (C.c_size_t, [_P, C.c_char_p, C.c_size_t]),
     "dcb_grid_create_structured": (_P, [C.c_int, _I32, _D, _D]),
+    "dcb_grid_create_structured_cubes": (_P, [C.c_int, _I32, _D, _D]),
+    "dcb_grid_nodes_per_element": (C.c_int, [_P]),
     "dcb_grid_create": (_P, [C.c_int, C.c_int64, _D, C.c_int64, _I32, C.c_int, C.POINTER(C.c_char_p), _D]),
     "dcb_grid_destroy": (None, [_P]),
     "dcb_grid_dim": (C.c_int, [_P]),
@@ -196,11 +198,16 @@ class Grid:
         self.h = _ptr(handle, "grid")
 
     @staticmethod
-    def structured(dim, cells, origin=None, extent=None):
+    def structured(dim, cells, origin=None, extent=None, element="simplex"):
+        """element = "simplex": Kuhn split of the lattice (the reference's grid); "cube": the cells
+        as Q1 elements (BASELINE configs[3]; not a reference capability)."""
         cells = np.asarray(cells, dtype=np.int32)
         origin = _f64(np.zeros(dim) if origin is None else origin)
         extent = _f64(np.ones(dim) if extent is None else extent)
-        return Grid(lib().dcb_grid_create_structured(dim, cells.ctypes.data_as(_I32), _d(origin), _d(extent)))
+        if element not in ("simplex", "cube"):
+            raise ValueError("element must be 'simplex' or 'cube'")
+        make = lib().dcb_grid_create_structured_cubes if element == "cube" else lib().dcb_grid_create_structured
+        return Grid(make(dim, cells.ctypes.data_as(_I32), _d(origin), _d(extent)))
 
     @staticmethod
     def from_arrays(dim, coords, elems, cell_keys=(), cell_data=None):
@@ -215,6 +222,7 @@ class Grid:
     nv = property(lambda s: lib().dcb_grid_num_vertices(s.h))
     ne = property(lambda s: lib().dcb_grid_num_elements(s.h))
     ndofs = property(lambda s: lib().dcb_grid_num_dofs(s.h))
+    nodes_per_element = property(lambda s: lib().dcb_grid_nodes_per_element(s.h))
 
     def coords(self):
         out = np.empty((self.nv, self.dim))
@@ -222,7 +230,7 @@ class Grid:
         return out
 
     def elements(self):
-        out = np.empty((self.ne, self.dim + 1), dtype=np.int32)
+        out = np.empty((self.ne, self.nodes_per_element), dtype=np.int32)
         lib().dcb_grid_get_elements(self.h, out.ctypes.data_as(_I32))
         return out
 
@@ -236,7 +244,7 @@ class Grid:
         return out
 
     def elem_dof(self):
-        out = np.empty((self.ne, self.dim + 1), dtype=np.int64)
+        out = np.empty((self.ne, self.nodes_per_element), dtype=np.int64)
         lib().dcb_grid_get_elem_dof(self.h, out.ctypes.data_as(_I64))
         return out
 

@@ -107,6 +107,13 @@ dcb_grid* dcb_grid_create_structured(int dim, const int32_t* cells, const double
     return g;
   });
 }
+dcb_grid* dcb_grid_create_structured_cubes(int dim, const int32_t* cells, const double* origin, const double* extent) {
+  return guard_new<dcb_grid>([&] {
+    auto* g = new dcb_grid();
+    g->g = std::make_shared<Grid>(Grid::structured(dim, cells, origin, extent, 1));
+    return g;
+  });
+}
 dcb_grid* dcb_grid_create(int dim, int64_t nv, const double* coords, int64_t ne, const int32_t* elems,
                           int nkeys, const char* const* keys, const double* cell_data) {
   return guard_new<dcb_grid>([&] {
@@ -119,6 +126,7 @@ void dcb_grid_destroy(dcb_grid* g) { delete g; }
 int dcb_grid_dim(const dcb_grid* g) { return g->g->dim; }
 int64_t dcb_grid_num_vertices(const dcb_grid* g) { return g->g->nv; }
 int64_t dcb_grid_num_elements(const dcb_grid* g) { return g->g->ne; }
+int dcb_grid_nodes_per_element(const dcb_grid* g) { return g->g->nd(); }
 int dcb_grid_get_coords(const dcb_grid* g, double* c) {
   std::memcpy(c, g->g->coords.data(), g->g->coords.size() * sizeof(double));
   return 0;
@@ -159,7 +167,8 @@ int64_t dcb_model_compile(dcb_model* m, int kind, char* out, size_t cap) {
 int dcb_model_precompile(dcb_model* m) {
   return guard([&] {
     std::string defs = jit_defines(*m->m);
-    for (JitGroup g : {JitGroup::Patch, JitGroup::Element, JitGroup::Csr, JitGroup::Skeleton, JitGroup::Structured})
+    for (JitGroup g : {JitGroup::Patch, JitGroup::Element, JitGroup::Csr, JitGroup::Skeleton, JitGroup::Structured,
+                       JitGroup::StructuredQ1})
       jit_compile_cached(jit_source(*m->m, defs, g));
   });
 }

@@ -8,21 +8,25 @@
 
 namespace dcb {
 
-Grid Grid::structured(int dim, const int* cells, const double* origin, const double* extent) {
+Grid Grid::structured(int dim, const int* cells, const double* origin, const double* extent, int elem_kind) {
   if (dim < 2 || dim > 3) fail("structured grid: dim must be 2 or 3");
+  if (elem_kind != 0 && elem_kind != 1) fail("structured grid: element kind must be 0 (simplex) or 1 (cube)");
   for (int a = 0; a < dim; ++a)
     if (cells[a] < 1) fail("structured grid: cells must be >= 1");
-  Grid g = structured_box(dim, cells, origin, extent, 0, cells[dim - 1]);
+  Grid g = structured_box(dim, cells, origin, extent, 0, cells[dim - 1], elem_kind);
   for (int a = 0; a < dim; ++a) { g.s_origin_exact_[a] = origin[a]; g.s_extent_exact_[a] = extent[a]; }
   return g;
 }
 
 // cube layers [layer_lo, layer_hi) along the last axis of the global lattice `cells`
 Grid Grid::structured_box(int dim, const int* cells, const double* origin, const double* extent,
-                          int layer_lo, int layer_hi) {
+                          int layer_lo, int layer_hi, int elem_kind) {
   Grid g;
   g.dim = dim;
   g.is_structured = true;
+  g.elem_kind = elem_kind;
+  g.s_layer_lo = layer_lo;
+  g.s_layers_global = cells[dim - 1];
   int64_t ncg[3] = {1, 1, 1}, nc[3] = {1, 1, 1}, nvs[3] = {1, 1, 1}, off[3] = {0, 0, 0};
   for (int a = 0; a < dim; ++a) ncg[a] = nc[a] = cells[a];
   nc[dim - 1] = layer_hi - layer_lo;
@@ -34,7 +38,7 @@ Grid Grid::structured_box(int dim, const int* cells, const double* origin, const
     g.s_origin[a] = origin[a] + extent[a] * ((double)off[a] / (double)ncg[a]);
   }
   g.nv = nvs[0] * nvs[1] * nvs[2];
-  int nperm = dim == 2 ? 2 : 6;
+  int nperm = elem_kind == 1 ? 1 : dim == 2 ? 2 : 6;
   g.ne = nc[0] * nc[1] * nc[2] * nperm;
   if (g.nv > INT32_MAX || g.ne > (int64_t)INT32_MAX) fail("structured grid too large for one device");
   g.coords.resize(g.nv * dim);
@@ -53,7 +57,7 @@ Grid Grid::structured_box(int dim, const int* cells, const double* origin, const
   static const int perm2[2][2] = {{0, 1}, {1, 0}};
   static const int perm3[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
   int64_t stride[3] = {1, nvs[0], nvs[0] * nvs[1]};
-  int nd = dim + 1;
+  int nd = g.nd();
   g.elems.resize(g.ne * nd);
 #pragma omp parallel for schedule(static)
   for (int64_t k = 0; k < nc[2]; ++k)
@@ -61,6 +65,14 @@ Grid Grid::structured_box(int dim, const int* cells, const double* origin, const
       for (int64_t i = 0; i < nc[0]; ++i) {
         int64_t cube = i + nc[0] * (j + nc[1] * k);
         int64_t base = i * stride[0] + j * stride[1] + k * stride[2];
+        if (elem_kind == 1) {   // the cell itself, corners by bit pattern
+          for (int m = 0; m < nd; ++m) {
+            int64_t v = base;
+            for (int a = 0; a < dim; ++a) v += ((m >> a) & 1) * stride[a];
+            g.elems[cube * nd + m] = (int32_t)v;
+          }
+          continue;
+        }
         for (int p = 0; p < nperm; ++p) {
           int64_t cur = base;
           int32_t* el = &g.elems[(cube * nperm + p) * nd];
@@ -165,6 +177,24 @@ void Grid::bind(const Model& model) {
   for (auto& s : model.species) need_facets |= !expr_is_absent(s.constrain_boundary);
   f_in.clear(); f_out.clear(); f_lin.clear(); f_lout.clear(); boundary_vertices.clear();
   if (!need_facets) return;
+  if (elem_kind == 1) {
+    // Q1 lattices: no facet terms; Dirichlet data lives on the outer vertices of the global lattice
+    // (a slab's cut planes are not boundary)
+    if (model.has_outflow()) fail("outflow / transmission terms on Q1 cube grids are out of scope");
+    int64_t nvs[3] = {1, 1, 1};
+    for (int a = 0; a < dim; ++a) nvs[a] = s_cells[a] + 1;
+    const int L = dim - 1;
+    for (int64_t v = 0; v < nv; ++v) {
+      int64_t idx[3] = {v % nvs[0], (v / nvs[0]) % nvs[1], v / (nvs[0] * nvs[1])};
+      bool onb = false;
+      for (int a = 0; a < dim; ++a) {
+        int64_t gi = idx[a] + (a == L ? s_layer_lo : 0), gn = a == L ? s_layers_global : s_cells[a];
+        onb |= gi == 0 || gi == gn;
+      }
+      if (onb) boundary_vertices.push_back(v);
+    }
+    return;
+  }
   std::vector<FaceRec> recs((size_t)ne * ndl);
 #pragma omp parallel for schedule(static)
   for (int64_t e = 0; e < ne; ++e)
@@ -354,7 +384,7 @@ Grid Grid::partition(int rank, int size) const {
     double extent[3];
     for (int a = 0; a < dim; ++a) extent[a] = s_h[a] * s_cells[a];
     // s_origin/extent of a global grid are the creation arguments
-    Grid l = structured_box(dim, s_cells, s_origin_exact_, s_extent_exact_, lo, hi);
+    Grid l = structured_box(dim, s_cells, s_origin_exact_, s_extent_exact_, lo, hi, elem_kind);
     int64_t plane = 1;
     for (int a = 0; a < L; ++a) plane *= s_cells[a] + 1;
     int64_t cubes_per_layer = 1;
@@ -373,7 +403,7 @@ Grid Grid::partition(int rank, int size) const {
     l.owned_begin = (p0 - lo) * plane;
     l.n_owned = (p1 - p0) * plane;
     l.global_eid.resize(l.ne);
-    const int nperm = dim == 2 ? 2 : 6;
+    const int nperm = elem_kind == 1 ? 1 : dim == 2 ? 2 : 6;
     for (int64_t e = 0; e < l.ne; ++e) l.global_eid[e] = e + (int64_t)lo * cubes_per_layer * nperm;
     (void)extent;
     return l;
@@ -389,6 +419,7 @@ Grid Grid::partition(int rank, int size) const {
   const int64_t vb = vbeg(rank), ve = vbeg(rank + 1);
   Grid l;
   l.dim = dim;
+  l.elem_kind = elem_kind;
   l.cell_keys = cell_keys;
   // local elements: any vertex owned
   std::vector<int64_t> lel;

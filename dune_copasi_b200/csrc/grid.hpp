@@ -18,7 +18,12 @@ struct Grid {
   int dim = 0;
   int64_t nv = 0, ne = 0;
   std::vector<double> coords;            // [nv*dim]
-  std::vector<int32_t> elems;            // [ne*(dim+1)]
+  std::vector<int32_t> elems;            // [ne*nd()]
+  // 0: simplices (the reference's element type); 1: the cells of a structured lattice as Q1 cubes,
+  // corner m of a cell at the bit pattern of m (x = bit 0).  Q1 is BASELINE configs[3]'s element
+  // and NOT a reference capability (PkLocalFiniteElementMap is simplex-only): cube
+  // grids run on the implicit-geometry kernels only (kernels/assembly_q1.cuh).
+  int elem_kind = 0;
   std::vector<std::string> cell_keys;
   std::vector<double> cell_data;         // [nkeys*ne]
 
@@ -38,6 +43,7 @@ struct Grid {
   int s_cells[3] = {1, 1, 1};            // cells of this (local) box
   double s_origin[3] = {0, 0, 0}, s_h[3] = {1, 1, 1};
   double s_origin_exact_[3] = {0, 0, 0}, s_extent_exact_[3] = {1, 1, 1};   // creation arguments (global grid)
+  int s_layer_lo = 0, s_layers_global = 0;   // first cell layer of this box / cell layers of the global lattice (last axis)
 
   // ---- partition data (local grids produced by partition(); empty on a global grid)
   int64_t n_owned = -1;                  // number of owned vertices (-1: not a partitioned grid)
@@ -54,7 +60,7 @@ struct Grid {
   // local mesh is again a structured box (owned planes in the middle, one ghost plane per side).
   Grid partition(int rank, int size) const;
   static Grid structured_box(int dim, const int* cells, const double* origin, const double* extent,
-                             int layer_lo, int layer_hi);
+                             int layer_lo, int layer_hi, int elem_kind = 0);
   // owned local dof ranges per compartment (valid after bind)
   void owned_ranges(std::vector<int64_t>& begin, std::vector<int64_t>& end) const;
   // halo plan of a bound local grid: per peer the local dofs to send / receive, both ordered by
@@ -62,12 +68,12 @@ struct Grid {
   void halo_plan(int rank, std::vector<int>& peers, std::vector<std::vector<int32_t>>& send,
                  std::vector<std::vector<int32_t>>& recv) const;
 
-  static Grid structured(int dim, const int* cells, const double* origin, const double* extent);
+  static Grid structured(int dim, const int* cells, const double* origin, const double* extent, int elem_kind = 0);
   static Grid from_arrays(int dim, int64_t nv, const double* coords, int64_t ne, const int32_t* elems,
                           const std::vector<std::string>& keys, const double* cell_data);
 
   void bind(const Model& model);
-  int nd() const { return dim + 1; }
+  int nd() const { return elem_kind == 1 ? 1 << dim : dim + 1; }
   int64_t elem_dof(int64_t e, int a) const {   // dof of species 0 at local vertex a of element e
     int c = elem_comp[e];
     return c < 0 ? -1 : comp_vdof[c][elems[e * nd() + a]];

@@ -15,6 +15,7 @@ namespace dcb {
 extern const char* kKernelArgsSource;
 extern const char* kAssemblySource;
 extern const char* kStructuredSource;
+extern const char* kQ1Source;
 
 std::string jit_source(const Model& model, const std::string& defines, JitGroup group) {
   std::ostringstream o;
@@ -52,6 +53,17 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
       for (int mode = 0; mode < 4; ++mode)
         o << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, DC_STRUCT_MINB) dc_k_struct_" << names[mode] << "_" << c
           << "(DcStructArgs a) { dc_structured_kernel<" << c << ", " << mode << ">(a); }\n";
+    }
+  }
+  if (all || group == JitGroup::StructuredQ1) {
+    // Q1 cells of a structured lattice (BASELINE configs[3]; not a reference element type)
+    o << kQ1Source << "\n";
+    for (int c = 0; c < model.ncomp(); ++c) {
+      if (model.comp_nspec[c] == 0 || !model.diffusion_is_constant(c) || model.has_extended_terms(c)) continue;
+      const char* names[5] = {"residual", "apply", "bdiag", "diag", "csr"};
+      for (int mode = 0; mode < 5; ++mode)
+        o << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, " << (mode == 4 ? "2" : "DC_STRUCT_MINB") << ") dc_k_q1_"
+          << names[mode] << "_" << c << "(DcStructArgs a) { dc_q1_kernel<" << c << ", " << mode << ">(a); }\n";
     }
   }
   if (all || group == JitGroup::Skeleton) {

@@ -57,6 +57,9 @@ struct DcStructArgs {
   double* r;
   double* bdiag;
   const unsigned char* cmask;
+  const long long* rowptr;     // CSR of the Jacobian (Q1 fill only)
+  const int* colidx;
+  double* vals;
 };
 
 struct DcFacetArgs {

@@ -57,6 +57,14 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
          (int64_t)grid->comp_vertices[full].size() == grid->nv;
     if (scheme == "structured" && !ok)
       fail("model.assembly.b200.scheme = structured needs a structured single-compartment grid without cell data");
+    if (grid->elem_kind == 1) {
+      // Q1 cube grids exist on the implicit-geometry kernels only (kernels/assembly_q1.cuh)
+      if (!ok || (scheme != "auto" && scheme != "structured"))
+        fail("Q1 cube grids need one compartment over the whole lattice, no cell data, scalar point-independent "
+             "diffusion and model.assembly.b200.scheme = auto|structured");
+      if (model->numerical_jacobian) fail("model.jacobian.type = numerical is not built for Q1 cube grids");
+      if (model->has_outflow()) fail("outflow / transmission terms on Q1 cube grids are out of scope");
+    }
     // measured on B200 (profiles/): element-per-thread + fp64 RED atomics beats the patch kernels
     if (scheme == "auto") scheme = ok ? "structured" : "atomic";
     struct_comp_ = ok ? full : -1;
@@ -72,7 +80,9 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
   // ---- kernels for this model
   jit_defines_ = jit_defines(*model);
   // the hot group is compiled up front, the others on first use
-  kernel(scheme == "patch" ? JitGroup::Patch : scheme == "structured" ? JitGroup::Structured : JitGroup::Element, "");
+  kernel(scheme == "patch" ? JitGroup::Patch
+         : scheme == "structured" ? (grid->elem_kind == 1 ? JitGroup::StructuredQ1 : JitGroup::Structured)
+                                  : JitGroup::Element, "");
 
   // ---- mesh on the device
   const int ncomp = model->ncomp();
@@ -385,7 +395,8 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
     // finite-difference Jacobians (model.jacobian.type = numerical) live in the element kernels
     // ... and so do the general analytic Jacobians of advection / tensor / dD/du terms
     const bool fd = (model->numerical_jacobian || model->has_extended_terms(c)) && mode != 0;
-    if (scheme == "structured" && mode != 3 && c == struct_comp_ && !fd) {
+    const bool q1 = grid->elem_kind == 1;
+    if (scheme == "structured" && (mode != 3 || q1) && c == struct_comp_ && (!fd || q1)) {
       DcStructArgs a{};
       a.ncells = 1;
       for (int k = 0; k < 3; ++k) {
@@ -398,9 +409,12 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       a.time = t; a.wM = wM; a.wA = wA; a.x = x; a.z = z; a.r = r;
       a.bdiag = bdiag ? (mode == 4 ? bdiag : bdiag + bdiag_shift(c)) : nullptr;
       a.cmask = cmask.p;
+      a.rowptr = (const long long*)rowptr.p; a.colidx = colidx.p; a.vals = vals;
       static const char* sn[5] = {"dc_k_struct_residual_", "dc_k_struct_apply_", "dc_k_struct_bdiag_", "", "dc_k_struct_diag_"};
-      static const char* sk[5] = {"struct_residual", "struct_apply", "struct_bdiag", "", "struct_diag"};
-      cudaKernel_t k = kernel(JitGroup::Structured, std::string(sn[mode]) + std::to_string(c));
+      static const char* qn[5] = {"dc_k_q1_residual_", "dc_k_q1_apply_", "dc_k_q1_bdiag_", "dc_k_q1_csr_", "dc_k_q1_diag_"};
+      static const char* sk[5] = {"struct_residual", "struct_apply", "struct_bdiag", "struct_csr", "struct_diag"};
+      cudaKernel_t k = q1 ? kernel(JitGroup::StructuredQ1, std::string(qn[mode]) + std::to_string(c))
+                          : kernel(JitGroup::Structured, std::string(sn[mode]) + std::to_string(c));
       const int sth = model->cfg.sub("model.assembly.b200").get("struct_threads", 64);
       // cell ranges of this launch: everything, or (multi-GPU overlap) the interior layers /
       // the two layers along the slab axis that touch ghost planes

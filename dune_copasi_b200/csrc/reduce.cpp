@@ -65,6 +65,7 @@ Reducer::Reducer(std::shared_ptr<DeviceOperator> op, const PTree& cfg, Communica
   const Grid& g = *op_->grid;
   keys_ = parse_keys(m, cfg);
   if (keys_.empty()) return;
+  if (g.elem_kind == 1) fail("[model.reduce] functionals on Q1 cube grids are not built (simplex quadrature only)");
   require_device();
 
   // ---- elements per compartment; cells outside every compartment are visited too (their species

@@ -42,6 +42,8 @@ void write_vtk(const Grid& g, const Model& m, const double* u, double time, cons
   make_dirs(path);
   if (!append) timesteps.clear();
   const int nd = g.nd(), dim = g.dim;
+  // VTK_TRIANGLE / VTK_TETRA; Q1 cells as VTK_PIXEL / VTK_VOXEL, whose corner order is the bit pattern
+  const int cell_type = g.elem_kind == 1 ? (dim == 2 ? 8 : 11) : (dim == 2 ? 5 : 10);
   const std::string stem = stem_of(path);
   char num[16];
   snprintf(num, sizeof num, "%05zu", timesteps.size());
@@ -80,7 +82,7 @@ void write_vtk(const Grid& g, const Model& m, const double* u, double time, cons
     fprintf(f, "</DataArray>\n<DataArray type=\"Int32\" Name=\"offsets\" NumberOfComponents=\"1\" format=\"ascii\">\n");
     for (int64_t k = 1; k <= ncell; ++k) fprintf(f, "%lld%c", (long long)(k * nd), (k % 12 == 0 || k == ncell) ? '\n' : ' ');
     fprintf(f, "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" NumberOfComponents=\"1\" format=\"ascii\">\n");
-    for (int64_t k = 1; k <= ncell; ++k) fprintf(f, "%d%c", dim == 2 ? 5 : 10, (k % 24 == 0 || k == ncell) ? '\n' : ' ');
+    for (int64_t k = 1; k <= ncell; ++k) fprintf(f, "%d%c", cell_type, (k % 24 == 0 || k == ncell) ? '\n' : ' ');
     fprintf(f, "</DataArray>\n</Cells>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n");
     if (fclose(f) != 0) fail("error while writing '", file, "'");
     // time sequence file, rewritten with every stamp

@@ -80,6 +80,13 @@ size_t dcb_config_dump(const dcb_config*, char* out, size_t cap);
 /* ---- mesh (structure-of-arrays; simplices only, as the reference: grid/move_geometry.hh:48-49) */
 dcb_grid* dcb_grid_create_structured(int dim, const int32_t* cells, const double* origin,
                                      const double* extent);
+/* The lattice cells themselves as Q1 (multilinear) elements, 2-point Gauss rule per axis: BASELINE
+ * configs[3]'s element.  NOT a reference capability (PkLocalFiniteElementMap is simplex-only,
+ * model_single_compartment_traits.hh:23-24; grid/make_multi_domain_grid.hh:84-90 creates simplex
+ * grids) -- same weak form (local_operator.hh:417-707), checked against the oracle's own Q1 element.
+ * One compartment over the whole lattice, scalar point-independent diffusion, no facet terms. */
+dcb_grid* dcb_grid_create_structured_cubes(int dim, const int32_t* cells, const double* origin,
+                                           const double* extent);
 dcb_grid* dcb_grid_create(int dim, int64_t nv, const double* coords, int64_t ne,
                           const int32_t* elems, int nkeys, const char* const* keys,
                           const double* cell_data);
@@ -87,6 +94,7 @@ void dcb_grid_destroy(dcb_grid*);
 int dcb_grid_dim(const dcb_grid*);
 int64_t dcb_grid_num_vertices(const dcb_grid*);
 int64_t dcb_grid_num_elements(const dcb_grid*);
+int dcb_grid_nodes_per_element(const dcb_grid*);   /* dim+1 (simplices) or 2^dim (Q1 cubes) */
 int dcb_grid_get_coords(const dcb_grid*, double* coords);
 int dcb_grid_get_elements(const dcb_grid*, int32_t* elems);
 
@@ -110,7 +118,7 @@ int dcb_model_precompile(dcb_model*);
 int dcb_grid_bind(dcb_grid*, const dcb_model*);
 int64_t dcb_grid_num_dofs(const dcb_grid*);
 int dcb_grid_get_elem_compartment(const dcb_grid*, int32_t* elem_comp);
-int dcb_grid_get_elem_dof(const dcb_grid*, int64_t* elem_dof /* [ne*(dim+1)] */);
+int dcb_grid_get_elem_dof(const dcb_grid*, int64_t* elem_dof /* [ne*nodes_per_element] */);
 int64_t dcb_grid_num_facets(const dcb_grid*);
 int dcb_grid_get_facets(const dcb_grid*, int64_t* f_in, int64_t* f_out, int32_t* f_lin, int32_t* f_lout);
 /* pattern: first call with NULL arrays to get the sizes */

@@ -63,7 +63,7 @@ class CMesh(C.Structure):
                 ("nkeys", C.c_int32), ("cell_data", C.POINTER(C.c_double)),
                 ("elem_dof", C.POINTER(C.c_int64)), ("nf", C.c_int64),
                 ("f_in", C.POINTER(C.c_int64)), ("f_out", C.POINTER(C.c_int64)),
-                ("f_lin", C.POINTER(C.c_int32)), ("f_lout", C.POINTER(C.c_int32))]
+                ("f_lin", C.POINTER(C.c_int32)), ("f_lout", C.POINTER(C.c_int32)), ("etype", C.c_int32)]
 
 
 class CModel(C.Structure):
@@ -189,6 +189,8 @@ class Model:
         self.tptr = np.cumsum(tptr).astype(np.int32)
         self._pack()
         self.has_outflow = bool((self.terms[:, 0] == K_OUTFLOW).any()) if len(terms) else False
+        if mesh.etype == 1 and self.has_outflow:
+            raise NotImplementedError("outflow terms on Q1 cube grids are out of scope")
 
     # ------------------------------------------------------------------ compartments
     def _mark_compartments(self):
@@ -242,7 +244,7 @@ class Model:
         self.cmesh = CMesh(m.dim, m.nv, _p(m.coords, C.c_double), m.ne, _p(m.elems, C.c_int32),
                            _p(m.elem_comp, C.c_int32), len(m.cell_keys), _p(self._cell, C.c_double),
                            _p(self._ed, C.c_int64), len(m.f_in), _p(m.f_in, C.c_int64),
-                           _p(m.f_out, C.c_int64), _p(m.f_lin, C.c_int32), _p(m.f_lout, C.c_int32))
+                           _p(m.f_out, C.c_int64), _p(m.f_lin, C.c_int32), _p(m.f_lout, C.c_int32), m.etype)
 
     @property
     def ndofs(self):
@@ -339,7 +341,7 @@ class Model:
         """Sorted CSR pattern: volume links + skeleton/boundary links (local_operator.hh:340-399)."""
         import scipy.sparse as sp
         m = self.mesh
-        nd = m.dim + 1
+        nd = m.elems.shape[1]
         rows, cols = [], []
         for (i, j) in self.species_pairs():
             c = self.species[i].comp

@@ -44,6 +44,8 @@ class Mesh:
     comp_vertices: list | None = None         # per compartment sorted vertex ids
     elem_dof: np.ndarray | None = None        # [ne, dim+1] int64
     ndofs: int = 0
+    etype: int = 0                            # 0 simplices, 1 axis-aligned Q1 cubes (non-reference extension)
+    lattice: tuple | None = None              # vertices per axis of a structured grid
 
     @property
     def nv(self):
@@ -57,7 +59,10 @@ class Mesh:
         return self.coords[self.elems].mean(axis=1)
 
 
-def structured(dim: int, cells, origin=None, extent=None) -> Mesh:
+def structured(dim: int, cells, origin=None, extent=None, element: str = "simplex") -> Mesh:
+    """element = "simplex": Kuhn split (the reference's createSimplexGrid geometry);
+    element = "cube": the lattice cells themselves as Q1 elements, corner m of a cell at the bit
+    pattern of m (x = bit 0) -- BASELINE configs[3]'s "Q1", not a reference capability."""
     cells = [int(c) for c in cells][:dim]
     origin = np.zeros(dim) if origin is None else np.asarray(origin, float)[:dim]
     extent = np.ones(dim) if extent is None else np.asarray(extent, float)[:dim]
@@ -72,6 +77,12 @@ def structured(dim: int, cells, origin=None, extent=None) -> Mesh:
     g = np.meshgrid(*[np.arange(n) for n in reversed(cells)], indexing="ij")
     ci = [a.ravel().astype(np.int64) for a in reversed(g)]
     base = sum(ci[a] * stride[a] for a in range(dim))
+    if element == "cube":
+        el = np.stack([base + sum(((m >> a) & 1) * stride[a] for a in range(dim)) for m in range(1 << dim)], axis=1)
+        return Mesh(dim=dim, coords=np.ascontiguousarray(coords), elems=np.ascontiguousarray(el.astype(np.int32)),
+                    etype=1, lattice=tuple(nvs))
+    if element != "simplex":
+        raise ValueError("element must be 'simplex' or 'cube'")
     perms = list(itertools.permutations(range(dim)))
     el = np.empty((base.size, len(perms), dim + 1), dtype=np.int64)
     for p, perm in enumerate(perms):
@@ -81,7 +92,7 @@ def structured(dim: int, cells, origin=None, extent=None) -> Mesh:
             cur = cur + stride[ax]
             el[:, p, k + 1] = cur
     elems = el.reshape(-1, dim + 1).astype(np.int32)
-    return Mesh(dim=dim, coords=np.ascontiguousarray(coords), elems=np.ascontiguousarray(elems))
+    return Mesh(dim=dim, coords=np.ascontiguousarray(coords), elems=np.ascontiguousarray(elems), lattice=tuple(nvs))
 
 
 def two_disks(nr_inner: int, nr_outer: int, ntheta: int) -> Mesh:
@@ -117,6 +128,19 @@ def two_disks(nr_inner: int, nr_outer: int, ntheta: int) -> Mesh:
 
 def build_facets(m: Mesh):
     """Interface + boundary facets (see module docstring)."""
+    if m.etype == 1:
+        # Q1 cubes: single-compartment lattices only, no facet terms; the boundary vertices (for
+        # Dirichlet constraints) are the lattice's outer vertices
+        if np.any(m.elem_comp < 0) or np.unique(m.elem_comp).size != 1:
+            raise NotImplementedError("Q1 cube grids carry one compartment over the whole lattice")
+        idx = np.unravel_index(np.arange(m.nv), tuple(reversed(m.lattice)))
+        onb = np.zeros(m.nv, dtype=bool)
+        for a, n in zip(idx, reversed(m.lattice)):
+            onb |= (a == 0) | (a == n - 1)
+        m.boundary_vertices = np.nonzero(onb)[0]
+        m.f_in = np.zeros(0, dtype=np.int64); m.f_out = np.zeros(0, dtype=np.int64)
+        m.f_lin = np.zeros(0, dtype=np.int32); m.f_lout = np.zeros(0, dtype=np.int32)
+        return m
     dim, nd, ne = m.dim, m.dim + 1, m.ne
     # face opposite to local vertex a = all other vertices
     faces = np.empty((ne, nd, dim), dtype=np.int64)
@@ -161,7 +185,7 @@ def build_facets(m: Mesh):
 def build_dofmap(m: Mesh, comp_nspec):
     ncomp = len(comp_nspec)
     m.comp_vertices, offs = [], [0]
-    m.elem_dof = -np.ones((m.ne, m.dim + 1), dtype=np.int64)
+    m.elem_dof = -np.ones((m.ne, m.elems.shape[1]), dtype=np.int64)
     for c in range(ncomp):
         sel = m.elem_comp == c
         verts = np.unique(m.elems[sel])

@@ -53,6 +53,8 @@ typedef struct {
   const int64_t* f_out;      /* outside element or -1 */
   const int32_t* f_lin;      /* local index of the vertex opposite to the facet in f_in */
   const int32_t* f_lout;
+  int32_t etype;             /* 0: simplices (the reference's element type), 1: axis-aligned Q1 cubes
+                                (extension without a reference counterpart) */
 } OrcMesh;
 
 /* term kinds; (i, j, k) per kind:
@@ -170,7 +172,7 @@ static void p1(int dim, const double* xi, double* phi) {
 }
 
 /* geometry of a simplex: corners X[nd][dim]; returns det, fills grads[nd][dim] (global gradients) */
-static double simplex_geo(int dim, double X[4][3], double G[4][3]) {
+static double simplex_geo(int dim, double (*X)[3], double (*G)[3]) {
   double B[3][3], Bi[3][3], det;
   for (int k = 0; k < dim; ++k) for (int c = 0; c < dim; ++c) B[c][k] = X[k + 1][c] - X[0][c];
   /* x = x0 + B xi ;  grad phi_a = B^{-T} grad_ref phi_a */
@@ -195,6 +197,48 @@ static double simplex_geo(int dim, double X[4][3], double G[4][3]) {
   for (int c = 0; c < dim; ++c) G[0][c] = 0;
   for (int k = 0; k < dim; ++k)
     for (int c = 0; c < dim; ++c) { G[k + 1][c] = Bi[k][c]; G[0][c] -= Bi[k][c]; }
+  return det;
+}
+
+/* ---- element type dispatch.  etype 1 = multilinear Q1 basis on an axis-aligned box whose corner m
+ * sits at the bit pattern of m (x = bit 0), integrated with the 2-point Gauss rule per axis (what
+ * dune-geometry returns for a cube at order 2).  Not a reference capability (PkLocalFiniteElementMap
+ * is simplex-only, model_single_compartment_traits.hh:23-24): same weak form, different element. */
+#define MAXND 8
+static inline int mesh_nd(const OrcMesh* M) { return M->etype ? 1 << M->dim : M->dim + 1; }
+static inline double elem_fact(const OrcMesh* M) { return M->etype ? 1.0 : (M->dim == 2 ? 2.0 : 6.0); }
+
+static int elem_quad(const OrcMesh* M, double pts[][3], double* wts) {
+  if (!M->etype) return quad(M->dim, pts, wts);
+  const int nq = 1 << M->dim;
+  for (int q = 0; q < nq; ++q) {
+    for (int k = 0; k < 3; ++k) pts[q][k] = k < M->dim ? Q1[(q >> k) & 1] : 0.0;
+    wts[q] = 1.0 / nq;
+  }
+  return nq;
+}
+
+static void elem_basis(const OrcMesh* M, const double* xi, double* phi) {
+  if (!M->etype) { p1(M->dim, xi, phi); return; }
+  for (int m = 0; m < (1 << M->dim); ++m) {
+    double v = 1.0;
+    for (int k = 0; k < M->dim; ++k) v *= ((m >> k) & 1) ? xi[k] : 1.0 - xi[k];
+    phi[m] = v;
+  }
+}
+
+/* global gradients of the basis at reference point xi (constant on a simplex); returns det */
+static double elem_geo(const OrcMesh* M, double (*X)[3], const double* xi, double (*G)[3]) {
+  if (!M->etype) return simplex_geo(M->dim, X, G);
+  double det = 1.0, h[3] = {1, 1, 1};
+  for (int k = 0; k < M->dim; ++k) { h[k] = X[1 << k][k] - X[0][k]; det *= h[k]; }
+  for (int m = 0; m < (1 << M->dim); ++m)
+    for (int k = 0; k < M->dim; ++k) {
+      double v = (((m >> k) & 1) ? 1.0 : -1.0) / h[k];
+      for (int l = 0; l < M->dim; ++l)
+        if (l != k) v *= ((m >> l) & 1) ? xi[l] : 1.0 - xi[l];
+      G[m][k] = v;
+    }
   return det;
 }
 
@@ -229,8 +273,8 @@ static inline void sink_add(const Sink* S, int64_t row, int64_t col, double v) {
 #define TERMS(P, g, kind, t0, t1) \
   int t0 = (P)->tptr[(g) * K_NKIND + (kind)], t1 = (P)->tptr[(g) * K_NKIND + (kind) + 1]
 
-static void load_element(const OrcMesh* M, int64_t e, double X[4][3]) {
-  int nd = M->dim + 1;
+static void load_element(const OrcMesh* M, int64_t e, double (*X)[3]) {
+  int nd = mesh_nd(M);
   for (int a = 0; a < nd; ++a) {
     int64_t v = M->elems[e * nd + a];
     for (int c = 0; c < 3; ++c) X[a][c] = c < M->dim ? M->coords[v * M->dim + c] : 0.0;
@@ -243,8 +287,8 @@ static void set_cell(const OrcMesh* M, int64_t e, double* ctx) {
 
 /* values + gradients of all species of compartment c at a point with basis values phi */
 static void eval_fields(const OrcMesh* M, const OrcModel* P, int c, int64_t e, const double* x,
-                        const double* phi, double G[4][3], double* ctx) {
-  int nd = M->dim + 1;
+                        const double* phi, double (*G)[3], double* ctx) {
+  int nd = mesh_nd(M);
   for (int t = P->comp_ptr[c]; t < P->comp_ptr[c + 1]; ++t) {
     int g = P->comp_spec[t], s = P->spec_local[g];
     double val = 0, gr[3] = {0, 0, 0};
@@ -262,10 +306,10 @@ static void eval_fields(const OrcMesh* M, const OrcModel* P, int c, int64_t e, c
  * form 0 = stiffness (reaction, diffusion), 1 = mass (storage).  r += w * R_form(x)          */
 void orc_residual_volume(const OrcMesh* M, const OrcModel* P, int form, double time, double w,
                          const double* x, double* r, int par) {
-  const int dim = M->dim, nd = dim + 1;
-  double qp[4][3], qw[4];
-  const int nq = quad(dim, qp, qw);
-  double fact = dim == 2 ? 2.0 : 6.0;
+  const int dim = M->dim, nd = mesh_nd(M);
+  double qp[MAXND][3], qw[MAXND];
+  const int nq = elem_quad(M, qp, qw);
+  double fact = elem_fact(M);
 #pragma omp parallel if (par)
   {
     double* ctx = (double*)calloc(P->nslots, sizeof(double));
@@ -273,16 +317,17 @@ void orc_residual_volume(const OrcMesh* M, const OrcModel* P, int form, double t
     for (int64_t e = 0; e < M->ne; ++e) {
       int c = M->elem_comp[e];
       if (c < 0) continue;
-      double X[4][3], G[4][3], loc[16][4];
+      double X[MAXND][3], G[MAXND][3], loc[16][MAXND];
       load_element(M, e, X);
-      double det = simplex_geo(dim, X, G);
+      double det = elem_geo(M, X, qp[0], G);
       ctx[SLOT_TIME] = time; ctx[SLOT_ENTVOL] = fabs(det) / fact; ctx[SLOT_INVOL] = 1;
       set_cell(M, e, ctx);
       int ns = P->comp_ptr[c + 1] - P->comp_ptr[c];
       for (int s = 0; s < ns; ++s) for (int a = 0; a < nd; ++a) loc[s][a] = 0;
       for (int q = 0; q < nq; ++q) {
-        double phi[4];
-        p1(dim, qp[q], phi);
+        double phi[MAXND];
+        elem_basis(M, qp[q], phi);
+        if (M->etype) elem_geo(M, X, qp[q], G);   /* gradients vary inside a cube */
         for (int k = 0; k < 3; ++k) {
           double p = 0;
           for (int a = 0; a < nd; ++a) p += phi[a] * X[a][k];
@@ -337,10 +382,10 @@ void orc_residual_volume(const OrcMesh* M, const OrcModel* P, int form, double t
 /* ---------------------------------------------------------------- volume Jacobian (analytic)   */
 static void jacobian_volume(const OrcMesh* M, const OrcModel* P, int form, double time, double w,
                             const double* x, const Sink* S) {
-  const int dim = M->dim, nd = dim + 1;
-  double qp[4][3], qw[4];
-  const int nq = quad(dim, qp, qw);
-  double fact = dim == 2 ? 2.0 : 6.0;
+  const int dim = M->dim, nd = mesh_nd(M);
+  double qp[MAXND][3], qw[MAXND];
+  const int nq = elem_quad(M, qp, qw);
+  double fact = elem_fact(M);
 #pragma omp parallel if (S->par)
   {
     double* ctx = (double*)calloc(P->nslots, sizeof(double));
@@ -348,15 +393,16 @@ static void jacobian_volume(const OrcMesh* M, const OrcModel* P, int form, doubl
     for (int64_t e = 0; e < M->ne; ++e) {
       int c = M->elem_comp[e];
       if (c < 0) continue;
-      double X[4][3], G[4][3];
+      double X[MAXND][3], G[MAXND][3];
       load_element(M, e, X);
-      double det = simplex_geo(dim, X, G);
+      double det = elem_geo(M, X, qp[0], G);
       ctx[SLOT_TIME] = time; ctx[SLOT_ENTVOL] = fabs(det) / fact; ctx[SLOT_INVOL] = 1;
       set_cell(M, e, ctx);
       const int64_t* ed = M->elem_dof + e * nd;
       for (int q = 0; q < nq; ++q) {
-        double phi[4];
-        p1(dim, qp[q], phi);
+        double phi[MAXND];
+        elem_basis(M, qp[q], phi);
+        if (M->etype) elem_geo(M, X, qp[q], G);
         for (int k = 0; k < 3; ++k) {
           double p = 0;
           for (int a = 0; a < nd; ++a) p += phi[a] * X[a][k];
@@ -489,7 +535,7 @@ void orc_jacobian_apply_volume(const OrcMesh* M, const OrcModel* P, int form, do
 void orc_jacobian_volume_numerical(const OrcMesh* M, const OrcModel* P, int form, double time,
                                    double w, double eps, const double* x, const int64_t* rowptr,
                                    const int32_t* colidx, double* vals) {
-  const int dim = M->dim, nd = dim + 1;
+  const int nd = mesh_nd(M);
   Sink S = {0, rowptr, colidx, vals, 0, 0, 0};
   /* element-local evaluation through a one-element sub-mesh view */
   for (int64_t e = 0; e < M->ne; ++e) {
@@ -497,8 +543,8 @@ void orc_jacobian_volume_numerical(const OrcMesh* M, const OrcModel* P, int form
     if (c < 0) continue;
     int ns = P->comp_ptr[c + 1] - P->comp_ptr[c];
     OrcMesh one = *M;
-    int64_t ldof[4];
-    double xl[64], down[64], up[64];
+    int64_t ldof[MAXND];
+    double xl[128], down[128], up[128];
     for (int a = 0; a < nd; ++a) {
       ldof[a] = (int64_t)a * ns;
       for (int s = 0; s < ns; ++s) xl[a * ns + s] = x[M->elem_dof[e * nd + a] + s];

@@ -435,9 +435,10 @@ cells.evaluation.expression = integration_factor / entity_volume
 
 
 class Case:
-    def __init__(self, name, ini, dim, mesh_fn, t0=0.0, dt=0.1, structured=None):
+    def __init__(self, name, ini, dim, mesh_fn, t0=0.0, dt=0.1, structured=None, element="simplex"):
         self.name, self.ini, self.dim, self.mesh_fn, self.t0, self.dt = name, ini, dim, mesh_fn, t0, dt
         self.structured = structured   # (cells, origin, extent) when the mesh is a structured grid
+        self.element = element         # "cube": the lattice cells as Q1 elements (BASELINE configs[3])
 
     def oracle(self, **overrides):
         cfg = INI.parse_ini(self.ini)
@@ -453,9 +454,9 @@ class Case:
         return INI.to_text(cfg)
 
 
-def _s(dim, n, origin=None, extent=None):
-    cells = [n] * dim
-    return lambda: OMESH.structured(dim, cells, origin, extent)
+def _s(dim, n, origin=None, extent=None, element="simplex"):
+    cells = [n] * dim if np.isscalar(n) else list(n)
+    return lambda: OMESH.structured(dim, cells, origin, extent, element)
 
 
 CASES = {
@@ -473,6 +474,24 @@ CASES = {
 }
 
 
+def _q1(name, ini, dim, cells, origin, extent, **kw):
+    return Case(name, ini, dim, _s(dim, cells, origin, extent, "cube"), structured=(cells, origin, extent),
+                element="cube", **kw)
+
+
+# The same models on the lattice cells as Q1 elements (BASELINE configs[3] "Q1 on a structured grid").
+# Not a reference element type: parity is product vs the oracle's own Q1 element.
+Q1_CASES = {
+    "gauss2d_q1": _q1("gauss2d_q1", GAUSS, 2, [24, 20], [-1, -1], [2, 2], t0=1.0),
+    "gauss3d_q1": _q1("gauss3d_q1", GAUSS, 3, [8, 6, 7], [-1, -1, -1], [2, 2, 2], t0=1.0),
+    "poisson_q1": _q1("poisson_q1", POISSON, 2, [16, 16], [0, 0], [1, 1]),
+    "grayscott2d_q1": _q1("grayscott2d_q1", GRAY_SCOTT, 2, [32, 32], [0, 0], [1, 1], dt=1.0),
+    "grayscott3d_q1": _q1("grayscott3d_q1", GRAY_SCOTT, 3, [10, 9, 8], [0, 0, 0], [1, 0.9, 0.8], dt=1.0),
+    "mitchell_schaefer_q1": _q1("mitchell_schaefer_q1", MITCHELL_SCHAEFER, 2, [16, 16], [0, 0], [1, 1], dt=0.01),
+}
+ALL_CASES = {**CASES, **Q1_CASES}
+
+
 def product_objects(case: Case, **overrides):
     """-> (Config, Model, Grid bound) through the C ABI, fed with the oracle-side mesh arrays."""
     import dune_copasi_b200 as D
@@ -484,12 +503,22 @@ def product_objects(case: Case, **overrides):
     return cfg, model, grid
 
 
+def product_objects_structured(case: Case, **overrides):
+    """Like product_objects for a structured case, without building the oracle-side mesh (full-size runs)."""
+    import dune_copasi_b200 as D
+    cfg = D.Config(case.ini_with(**overrides))
+    model = D.Model(cfg, case.dim, [])
+    grid = D.Grid.structured(case.dim, *case.structured, element=case.element)
+    grid.bind(model)
+    return cfg, model, grid
+
+
 def product_grid(case: Case, mesh=None):
     """Structured cases go through the product's own generator (bit-identical arrays, see
     tests/test_host_parity.py) so that the implicit-geometry kernels are eligible."""
     import dune_copasi_b200 as D
     if case.structured:
-        return D.Grid.structured(case.dim, *case.structured)
+        return D.Grid.structured(case.dim, *case.structured, element=case.element)
     mesh = mesh or case.mesh_fn()
     return D.Grid.from_arrays(case.dim, mesh.coords, mesh.elems, mesh.cell_keys, mesh.cell_data)
 

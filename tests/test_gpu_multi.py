@@ -20,7 +20,8 @@ OVERLAP = "model.time_step_operator.linear_solver.b200.overlap_halo=true"
 
 @pytest.mark.parametrize("name,mf,extra", [("grayscott3d", "1", ""), ("grayscott3d", "0", ""), ("cell3d", "1", ""),
                                            ("two_disks", "0", ""), ("gauss3d", "1", ""), ("advection3d", "0", ""),
-                                           ("grayscott3d", "1", OVERLAP)])
+                                           ("grayscott3d", "1", OVERLAP), ("grayscott3d_q1", "1", ""),
+                                           ("grayscott3d_q1", "0", ""), ("gauss3d_q1", "1", OVERLAP)])
 def test_two_rank_time_stepping_matches_serial_oracle(name, mf, extra):
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")

@@ -10,18 +10,18 @@ import pytest
 
 import cases as K
 
-ALL = list(K.CASES)
+ALL = list(K.ALL_CASES)     # incl. the Q1 cube grids (non-reference element, own oracle)
 
 
 @pytest.mark.parametrize("name", ALL)
 def test_mesh_dofmap_pattern_bit_exact(name):
     import dune_copasi_b200 as D
-    case = K.CASES[name]
+    case = K.ALL_CASES[name]
     om = case.oracle()
     cfg, model, grid = K.product_objects(case)
     m = om.mesh
     if case.structured:
-        g2 = D.Grid.structured(case.dim, *case.structured)
+        g2 = D.Grid.structured(case.dim, *case.structured, element=case.element)
         assert np.array_equal(g2.coords(), m.coords)          # same doubles, same order
         assert np.array_equal(g2.elements(), m.elems)
     assert [s for s, _ in model.species()] == om.names

@@ -38,6 +38,9 @@ def _local_problem(case, rank, size, structured=False):
     # the oracle on the same local arrays (cell data restricted through the element ids is not
     # needed for the cases used here)
     lmesh = OMESH.Mesh(dim=case.dim, coords=gloc.coords(), elems=gloc.elements())
+    if case.element == "cube":      # a slab of a Q1 lattice is a Q1 lattice
+        lmesh.etype = 1
+        lmesh.lattice = tuple(int(np.unique(lmesh.coords[:, a]).size) for a in range(case.dim))
     if gmesh.cell_keys:
         lmesh.cell_keys = list(gmesh.cell_keys)
         lmesh.cell_data = np.ascontiguousarray(gmesh.cell_data[:, gloc.global_element_ids()])
@@ -71,7 +74,7 @@ def _worker(rank, size, port, name, structured, q):
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         dist.init_process_group("gloo", rank=rank, world_size=size)
         import torch
-        case = K.CASES[name]
+        case = K.ALL_CASES[name]
         om = case.oracle()                      # serial reference
         model, gloc, oml = _local_problem(case, rank, size, structured)
         gids = gloc.global_vertex_ids()
@@ -134,7 +137,8 @@ def _worker(rank, size, port, name, structured, q):
 
 
 @pytest.mark.parametrize("name,size,structured", [("grayscott3d", 2, False), ("cell3d", 2, False), ("grayscott2d", 3, False),
-                                                  ("two_disks", 2, False), ("grayscott3d", 3, True), ("cell3d", 2, True)])
+                                                  ("two_disks", 2, False), ("grayscott3d", 3, True), ("cell3d", 2, True),
+                                                  ("grayscott3d_q1", 2, True), ("grayscott2d_q1", 3, True)])
 def test_partition_halo_gloo(name, size, structured):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")

@@ -30,7 +30,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    case = K.CASES[name]
+    case = K.ALL_CASES[name]
     over = {"model.time_step_operator.linear_solver.matrix_free": "true" if mf else "false"}
     for kv in filter(None, (sys.argv[4] if len(sys.argv) > 4 else "").split(",")):   # extra ini overrides
         k, v = kv.split("=")
