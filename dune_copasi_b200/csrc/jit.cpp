@@ -53,10 +53,14 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
       for (int mode = 0; mode < 4; ++mode)
         o << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, DC_STRUCT_MINB) dc_k_struct_" << names[mode] << "_" << c
           << "(DcStructArgs a) { dc_structured_kernel<" << c << ", " << mode << ">(a); }\n";
+      for (int mode = 0; mode < 2; ++mode)
+        o << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, DC_STRUCT_MINB) dc_k_struct_march_" << names[mode] << "_" << c
+          << "(DcStructArgs a) { dc_structured_march_kernel<" << c << ", " << mode << ">(a); }\n";
     }
   }
   if (all || group == JitGroup::StructuredQ1) {
     // Q1 cells of a structured lattice (BASELINE configs[3]; not a reference element type)
+    if (!all) o << kStructuredSource << "\n";   // shared drivers (per cell / marching)
     o << kQ1Source << "\n";
     for (int c = 0; c < model.ncomp(); ++c) {
       if (model.comp_nspec[c] == 0 || !model.diffusion_is_constant(c) || model.has_extended_terms(c)) continue;
@@ -64,6 +68,9 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
       for (int mode = 0; mode < 5; ++mode)
         o << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, " << (mode == 4 ? "2" : "DC_STRUCT_MINB") << ") dc_k_q1_"
           << names[mode] << "_" << c << "(DcStructArgs a) { dc_q1_kernel<" << c << ", " << mode << ">(a); }\n";
+      for (int mode = 0; mode < 2; ++mode)
+        o << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, DC_STRUCT_MINB) dc_k_q1_march_"
+          << names[mode] << "_" << c << "(DcStructArgs a) { dc_q1_march_kernel<" << c << ", " << mode << ">(a); }\n";
     }
   }
   if (all || group == JitGroup::Skeleton) {

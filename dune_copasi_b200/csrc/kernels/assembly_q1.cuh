@@ -15,7 +15,7 @@
 // coefficients are point independent here (checked by the host), so the stiffness action is the
 // exact tensor form  sum_k |cell|/h_k^2  K1_k (x) M1 (x) M1  applied to the corner values.
 // MODE 0: residual, 1: Jacobian apply, 2: block diagonal, 3: scalar diagonal, 4: CSR values.
-#define DQ_NC (1 << DC_DIM)
+#define DQ_NC (1 << DC_DIM)   // == DC_NCORN of assembly_structured.cuh, whose drivers these kernels share
 #define DQ_A 0.78867513459481288225
 #define DQ_B 0.21132486540518711775
 
@@ -110,28 +110,142 @@ __device__ __forceinline__ constexpr double dq_kfactor(int k, int a, int b) {
   return v;
 }
 
+// per-cell constants and the evaluation context
+struct DqGeo {
+  double adet, f, rh[DC_DIM], wk[DC_DIM], x0[DC_DIM];
+};
+__device__ __forceinline__ void dq_setup(const DcStructArgs& a, const int* idx, DqGeo& g, DcCtx& c) {
+  g.adet = 1.0;
+#pragma unroll
+  for (int k = 0; k < DC_DIM; ++k) { g.adet *= a.h[k]; g.rh[k] = 1.0 / a.h[k]; }
+#pragma unroll
+  for (int k = 0; k < DC_DIM; ++k) g.wk[k] = g.adet * g.rh[k] * g.rh[k];
+  g.f = g.adet / DQ_NC;   // weight 2^-d per point times |det| = |cell|
+  c.time = a.time; c.entity_volume = g.adet; c.integration_factor = g.f;
+  c.in_volume = 1.0; c.in_boundary = 0.0; c.in_skeleton = 0.0;
+  c.nrm[0] = c.nrm[1] = c.nrm[2] = 0.0; c.pos[2] = 0.0;
+#pragma unroll
+  for (int k = 0; k < DC_DIM; ++k) g.x0[k] = a.origin[k] + idx[k] * a.h[k];
+}
+__device__ __forceinline__ void dq_set_pos(const DcStructArgs& a, const DqGeo& g, DcCtx& c, int q) {
+#pragma unroll
+  for (int k = 0; k < DC_DIM; ++k) c.pos[k] = g.x0[k] + (((q >> k) & 1) ? DQ_A : DQ_B) * a.h[k];
+}
+// point-independent diffusion coefficients, jd[i][j] = wA * D_ij
+template <int C>
+__device__ __forceinline__ void dq_diffusion(const DcStructArgs& a, const DqGeo& g, DcCtx& c,
+                                             double (*jd)[DcComp<C>::NS]) {
+  typedef DcComp<C> M;
+  constexpr int NS = M::NS;
+  double u0[NS], g0[NS][DC_DIM];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    u0[s] = 0.0;
+#pragma unroll
+    for (int k = 0; k < DC_DIM; ++k) g0[s][k] = 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < DC_DIM; ++k) c.pos[k] = g.x0[k] + 0.5 * a.h[k];
+  M::jac_diff(c, u0, g0, a.wA, jd);
+}
+
+// residual (MODE 0) / Jacobian apply (MODE 1) of one cell: Uc/Zc = corner values [corner][species],
+// acc = corner sums [corner][species] (overwritten)
 template <int C, int MODE>
-__device__ __forceinline__ void dc_q1_kernel(const DcStructArgs& a) {
+__device__ __forceinline__ void dc_q1_cell(const DcStructArgs& a, const int* idx, const double (*Uc)[DcComp<C>::NS],
+                                           const double (*Zc)[DcComp<C>::NS], double (*out)[DcComp<C>::NS]) {
+  typedef DcComp<C> M;
+  constexpr int NS = M::NS;
+  DqGeo g;
+  DcCtx c;
+  dq_setup(a, idx, g, c);
+  // species-major copies so that the tensor maps run over contiguous registers
+  double U[NS][DQ_NC], Z[MODE == 1 ? NS : 1][DQ_NC];
+#pragma unroll
+  for (int m = 0; m < DQ_NC; ++m)
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      U[s][m] = Uc[m][s];
+      if (MODE == 1) Z[s][m] = Zc[m][s];
+    }
+  double jd[NS][NS];
+  if (M::HAS_DIFF) dq_diffusion<C>(a, g, c, jd);
+  // gradients at the Gauss points (only models whose coefficients read grad_* keep this alive)
+  double G[DQ_NC][NS][DC_DIM];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int k = 0; k < DC_DIM; ++k) {
+      double gr[DQ_NC];
+      dq_gradient(U[s], k, g.rh[k], gr);
+#pragma unroll
+      for (int q = 0; q < DQ_NC; ++q) G[q][s][k] = gr[q];
+    }
+  // ---- diffusion first (needs the corner values), then the corner arrays turn into point arrays
+  double acc[NS][DQ_NC];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+#pragma unroll
+    for (int m = 0; m < DQ_NC; ++m) acc[i][m] = 0.0;
+    if (M::HAS_DIFF) {
+#pragma unroll
+      for (int j = 0; j < NS; ++j)
+        if (M::pair(i, j)) dq_stiffness(MODE == 0 ? U[j] : Z[j], g.wk, jd[i][j], acc[i]);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    dq_interp(U[s]);
+    if (MODE == 1) dq_interp(Z[s]);
+  }
+#pragma unroll
+  for (int q = 0; q < DQ_NC; ++q) {
+    double u[NS];
+    dq_set_pos(a, g, c, q);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) u[s] = U[s][q];
+    if (MODE == 0) {
+      double sc[NS];
+      M::scalar(c, u, G[q], a.wM, a.wA, sc);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) U[s][q] = sc[s];
+    } else {
+      double jm[NS][NS], w[NS];
+      M::jac_mass(c, u, G[q], a.wM, a.wA, jm);
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        w[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; ++j)
+          if (M::pair(i, j)) w[i] += jm[i][j] * Z[j][q];
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) Z[i][q] = w[i];
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    double* S = MODE == 0 ? U[s] : Z[s];
+    dq_interp(S);
+#pragma unroll
+    for (int m = 0; m < DQ_NC; ++m) out[m][s] = acc[s][m] + g.f * S[m];
+  }
+}
+
+// MODE 2: block diagonal, 3: scalar diagonal, 4: CSR values -- one thread per cell
+template <int C, int MODE>
+__device__ __forceinline__ void dc_q1_matrix_kernel(const DcStructArgs& a) {
   typedef DcComp<C> M;
   constexpr int NS = M::NS;
   const long long cell = a.cell_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (cell >= a.ncells) return;
   int idx[3];
-  {
-    long long rem = cell;
-    idx[0] = (int)(rem % a.n[0]); rem /= a.n[0];
-#if DC_DIM == 3
-    idx[1] = (int)(rem % a.n[1]); idx[2] = (int)(rem / a.n[1]);
-#else
-    idx[1] = (int)rem; idx[2] = 0;
-#endif
-  }
+  dc_cell_index(a, cell, idx);
   long long stride[3] = {1, a.n[0] + 1, (long long)(a.n[0] + 1) * (a.n[1] + 1)};
   long long base = 0;
 #pragma unroll
   for (int k = 0; k < DC_DIM; ++k) base += idx[k] * stride[k];
-  // ---- corner data, species-major so that the tensor maps run over contiguous registers
-  double U[NS][DQ_NC], Z[MODE == 1 ? NS : 1][DQ_NC];
+  double U[NS][DQ_NC];
   long long dof[DQ_NC];
 #pragma unroll
   for (int m = 0; m < DQ_NC; ++m) {
@@ -140,109 +254,25 @@ __device__ __forceinline__ void dc_q1_kernel(const DcStructArgs& a) {
     for (int k = 0; k < DC_DIM; ++k) v += ((m >> k) & 1) * stride[k];
     dof[m] = a.dof_offset + v * NS;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      U[s][m] = a.x[dof[m] + s];
-      if (MODE == 1) Z[s][m] = (a.cmask && a.cmask[dof[m] + s]) ? 0.0 : a.z[dof[m] + s];
-    }
+    for (int s = 0; s < NS; ++s) U[s][m] = a.x[dof[m] + s];
   }
-  double adet = 1.0, rh[DC_DIM], wk[DC_DIM];
-#pragma unroll
-  for (int k = 0; k < DC_DIM; ++k) { adet *= a.h[k]; rh[k] = 1.0 / a.h[k]; }
-#pragma unroll
-  for (int k = 0; k < DC_DIM; ++k) wk[k] = adet * rh[k] * rh[k];
-  const double f = adet / DQ_NC;   // weight 2^-d per point times |det| = |cell|
+  DqGeo g;
   DcCtx c;
-  c.time = a.time; c.entity_volume = adet; c.integration_factor = f;
-  c.in_volume = 1.0; c.in_boundary = 0.0; c.in_skeleton = 0.0;
-  c.nrm[0] = c.nrm[1] = c.nrm[2] = 0.0; c.pos[2] = 0.0;
-  double x0[DC_DIM];
-#pragma unroll
-  for (int k = 0; k < DC_DIM; ++k) x0[k] = a.origin[k] + idx[k] * a.h[k];
-  auto set_pos = [&](int q) {
-#pragma unroll
-    for (int k = 0; k < DC_DIM; ++k) c.pos[k] = x0[k] + (((q >> k) & 1) ? DQ_A : DQ_B) * a.h[k];
-  };
-
-  // point-independent diffusion coefficients, jd[i][j] = wA * D_ij
+  dq_setup(a, idx, g, c);
+  const double f = g.f;
+  const double* wk = g.wk;
   double jd[NS][NS];
-  if (M::HAS_DIFF) {
-    double u0[NS], g0[NS][DC_DIM];
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      u0[s] = 0.0;
-#pragma unroll
-      for (int k = 0; k < DC_DIM; ++k) g0[s][k] = 0.0;
-    }
-#pragma unroll
-    for (int k = 0; k < DC_DIM; ++k) c.pos[k] = x0[k] + 0.5 * a.h[k];
-    M::jac_diff(c, u0, g0, a.wA, jd);
-  }
-
-  // gradients at the Gauss points (only models whose coefficients read grad_* keep this alive)
+  if (M::HAS_DIFF) dq_diffusion<C>(a, g, c, jd);
   double G[DQ_NC][NS][DC_DIM];
 #pragma unroll
   for (int s = 0; s < NS; ++s)
 #pragma unroll
     for (int k = 0; k < DC_DIM; ++k) {
-      double g[DQ_NC];
-      dq_gradient(U[s], k, rh[k], g);
+      double gr[DQ_NC];
+      dq_gradient(U[s], k, g.rh[k], gr);
 #pragma unroll
-      for (int q = 0; q < DQ_NC; ++q) G[q][s][k] = g[q];
+      for (int q = 0; q < DQ_NC; ++q) G[q][s][k] = gr[q];
     }
-
-  if (MODE == 0 || MODE == 1) {
-    // ---- diffusion first (needs the corner values), then the corner arrays turn into point arrays
-    double acc[NS][DQ_NC];
-#pragma unroll
-    for (int i = 0; i < NS; ++i) {
-#pragma unroll
-      for (int m = 0; m < DQ_NC; ++m) acc[i][m] = 0.0;
-      if (M::HAS_DIFF) {
-#pragma unroll
-        for (int j = 0; j < NS; ++j)
-          if (M::pair(i, j)) dq_stiffness(MODE == 0 ? U[j] : Z[j], wk, jd[i][j], acc[i]);
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      dq_interp(U[s]);
-      if (MODE == 1) dq_interp(Z[s]);
-    }
-#pragma unroll
-    for (int q = 0; q < DQ_NC; ++q) {
-      double u[NS];
-      set_pos(q);
-#pragma unroll
-      for (int s = 0; s < NS; ++s) u[s] = U[s][q];
-      if (MODE == 0) {
-        double sc[NS];
-        M::scalar(c, u, G[q], a.wM, a.wA, sc);
-#pragma unroll
-        for (int s = 0; s < NS; ++s) U[s][q] = sc[s];
-      } else {
-        double jm[NS][NS], w[NS];
-        M::jac_mass(c, u, G[q], a.wM, a.wA, jm);
-#pragma unroll
-        for (int i = 0; i < NS; ++i) {
-          w[i] = 0.0;
-#pragma unroll
-          for (int j = 0; j < NS; ++j)
-            if (M::pair(i, j)) w[i] += jm[i][j] * Z[j][q];
-        }
-#pragma unroll
-        for (int i = 0; i < NS; ++i) Z[i][q] = w[i];
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      double* S = MODE == 0 ? U[s] : Z[s];
-      dq_interp(S);
-#pragma unroll
-      for (int m = 0; m < DQ_NC; ++m) dc_atomic_add(&a.r[dof[m] + s], acc[s][m] + f * S[m]);
-    }
-    return;
-  }
-
   // ---- Jacobian coefficients at the Gauss points
   double J[NS][NS][DQ_NC];
 #pragma unroll
@@ -250,7 +280,7 @@ __device__ __forceinline__ void dc_q1_kernel(const DcStructArgs& a) {
 #pragma unroll
   for (int q = 0; q < DQ_NC; ++q) {
     double u[NS], jm[NS][NS];
-    set_pos(q);
+    dq_set_pos(a, g, c, q);
 #pragma unroll
     for (int s = 0; s < NS; ++s) u[s] = U[s][q];
     M::jac_mass(c, u, G[q], a.wM, a.wA, jm);
@@ -312,4 +342,23 @@ __device__ __forceinline__ void dc_q1_kernel(const DcStructArgs& a) {
         }
       }
     }
+}
+
+template <int C, int MODE>
+__device__ __forceinline__ void dc_q1_kernel(const DcStructArgs& a) {
+  constexpr int NS = DcComp<C>::NS;
+  if constexpr (MODE >= 2) {
+    dc_q1_matrix_kernel<C, MODE>(a);
+  } else {
+    dc_struct_per_cell<C, MODE>(a, [&](const int* idx, const double (*U)[NS], const double (*Z)[NS], double (*acc)[NS]) {
+      dc_q1_cell<C, MODE>(a, idx, U, Z, acc);
+    });
+  }
+}
+template <int C, int MODE>
+__device__ __forceinline__ void dc_q1_march_kernel(const DcStructArgs& a) {
+  constexpr int NS = DcComp<C>::NS;
+  dc_struct_march<C, MODE>(a, [&](const int* idx, const double (*U)[NS], const double (*Z)[NS], double (*acc)[NS]) {
+    dc_q1_cell<C, MODE>(a, idx, U, Z, acc);
+  });
 }

@@ -44,44 +44,18 @@ __device__ __forceinline__ constexpr int dc_edge_paths(int m) {
   return a * b;
 }
 
+// contributions of one lattice cell: U/Z = corner values [corner][species], acc = corner sums (overwritten)
 template <int C, int MODE>
-__device__ __forceinline__ void dc_structured_kernel(const DcStructArgs& a) {
+__device__ __forceinline__ void dc_struct_cell(const DcStructArgs& a, const int* idx,
+                                               const double (*U)[DcComp<C>::NS], const double (*Z)[DcComp<C>::NS],
+                                               double (*acc)[MODE == 2 ? DcComp<C>::NS * DcComp<C>::NS : DcComp<C>::NS]) {
   typedef DcComp<C> M;
   constexpr int NS = M::NS;
   constexpr int NV = MODE == 2 ? NS * NS : NS;
-  const long long cell = a.cell_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (cell >= a.ncells) return;
-  int idx[3];
-  {
-    long long rem = cell;
-    idx[0] = (int)(rem % a.n[0]); rem /= a.n[0];
-#if DC_DIM == 3
-    idx[1] = (int)(rem % a.n[1]); idx[2] = (int)(rem / a.n[1]);
-#else
-    idx[1] = (int)rem; idx[2] = 0;
-#endif
-  }
-  long long stride[3] = {1, a.n[0] + 1, (long long)(a.n[0] + 1) * (a.n[1] + 1)};
-  long long base = 0;
 #pragma unroll
-  for (int k = 0; k < DC_DIM; ++k) base += idx[k] * stride[k];
-  // ---- corner data
-  double U[DC_NCORN][NS], Z[MODE == 1 ? DC_NCORN : 1][NS], acc[DC_NCORN][NV];
-  long long dof[DC_NCORN];
-#pragma unroll
-  for (int m = 0; m < DC_NCORN; ++m) {
-    long long v = base;
-#pragma unroll
-    for (int k = 0; k < DC_DIM; ++k) v += ((m >> k) & 1) * stride[k];
-    dof[m] = a.dof_offset + v * NS;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      U[m][s] = a.x[dof[m] + s];
-      if (MODE == 1) Z[m][s] = (a.cmask && a.cmask[dof[m] + s]) ? 0.0 : a.z[dof[m] + s];
-    }
+  for (int m = 0; m < DC_NCORN; ++m)
 #pragma unroll
     for (int s = 0; s < NV; ++s) acc[m][s] = 0.0;
-  }
   double adet = 1.0, rh[DC_DIM];
 #pragma unroll
   for (int k = 0; k < DC_DIM; ++k) { adet *= a.h[k]; rh[k] = 1.0 / a.h[k]; }
@@ -257,7 +231,48 @@ __device__ __forceinline__ void dc_structured_kernel(const DcStructArgs& a) {
       }
   }
 
-  // ---- one reduction per corner value
+}
+
+// decode a linear cell index
+__device__ __forceinline__ void dc_cell_index(const DcStructArgs& a, long long cell, int* idx) {
+  long long rem = cell;
+  idx[0] = (int)(rem % a.n[0]); rem /= a.n[0];
+#if DC_DIM == 3
+  idx[1] = (int)(rem % a.n[1]); idx[2] = (int)(rem / a.n[1]);
+#else
+  idx[1] = (int)rem; idx[2] = 0;
+#endif
+}
+
+// ---- driver 1: one thread per cell, one reduction per corner value (all modes)
+template <int C, int MODE, class CellFn>
+__device__ __forceinline__ void dc_struct_per_cell(const DcStructArgs& a, CellFn cell_fn) {
+  typedef DcComp<C> M;
+  constexpr int NS = M::NS;
+  constexpr int NV = MODE == 2 ? NS * NS : NS;
+  const long long cell = a.cell_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (cell >= a.ncells) return;
+  int idx[3];
+  dc_cell_index(a, cell, idx);
+  long long stride[3] = {1, a.n[0] + 1, (long long)(a.n[0] + 1) * (a.n[1] + 1)};
+  long long base = 0;
+#pragma unroll
+  for (int k = 0; k < DC_DIM; ++k) base += idx[k] * stride[k];
+  double U[DC_NCORN][NS], Z[MODE == 1 ? DC_NCORN : 1][NS], acc[DC_NCORN][NV];
+  long long dof[DC_NCORN];
+#pragma unroll
+  for (int m = 0; m < DC_NCORN; ++m) {
+    long long v = base;
+#pragma unroll
+    for (int k = 0; k < DC_DIM; ++k) v += ((m >> k) & 1) * stride[k];
+    dof[m] = a.dof_offset + v * NS;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      U[m][s] = a.x[dof[m] + s];
+      if (MODE == 1) Z[m][s] = (a.cmask && a.cmask[dof[m] + s]) ? 0.0 : a.z[dof[m] + s];
+    }
+  }
+  cell_fn(idx, U, Z, acc);
 #pragma unroll
   for (int m = 0; m < DC_NCORN; ++m) {
     if (MODE == 2) {
@@ -271,4 +286,153 @@ __device__ __forceinline__ void dc_structured_kernel(const DcStructArgs& a) {
       for (int s = 0; s < NS; ++s) dc_atomic_add(&a.r[dof[m] + s], acc[m][s]);
     }
   }
+}
+
+// ---- driver 2 (residual and apply): register marching along the last axis, lanes along x.
+// A thread walks a.march cells up the last axis: the top face of one cell is the bottom face of the
+// next, so per cell only the new face is loaded and only the finished bottom face is reduced; along
+// x the lanes of a warp hold neighbouring cells, so the x = 1 half of every face is exchanged by
+// warp shuffles instead of being loaded / reduced twice.  Per cell and species: 2 loads and 2
+// reductions (3-D) instead of 8 and 8 -- the per-cell driver kept the L2 at 75-90 % of its peak
+// throughput (profiles/r01_struct_apply_256_ncu.txt, r01_q1_apply_v1_256_ncu.txt).
+// The launch covers whole layers: cells [cell_begin, ncells) must be multiples of the layer size.
+#define DC_NFACE (DC_NCORN / 2)
+template <int C, int MODE, class CellFn>
+__device__ __forceinline__ void dc_struct_march(const DcStructArgs& a, CellFn cell_fn) {
+  typedef DcComp<C> M;
+  constexpr int NS = M::NS;
+  constexpr int L = DC_DIM - 1;
+  constexpr unsigned FULL = 0xffffffffu;
+  const long long layer = (long long)a.n[0] * (DC_DIM == 3 ? a.n[1] : 1);
+  const int k0 = (int)(a.cell_begin / layer), k1 = (int)(a.ncells / layer);
+  const int nchunk = (k1 - k0 + a.march - 1) / a.march;
+  const long long nthreads = layer * nchunk;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool valid = t < nthreads;
+  const long long tt = valid ? t : nthreads - 1;
+  int idx[3] = {0, 0, 0};
+  idx[0] = (int)(tt % a.n[0]);
+#if DC_DIM == 3
+  idx[1] = (int)((tt / a.n[0]) % a.n[1]);
+#endif
+  const int chunk = (int)(tt / layer);
+  const int kb = k0 + chunk * a.march, ke = min(kb + a.march, k1);
+  const unsigned lane = threadIdx.x & 31u;
+  // lane + 1 holds the cell at x + 1 of the same row and chunk (hence the same layer range)
+  const bool has_right = valid && lane < 31u && idx[0] + 1 < a.n[0];
+  const bool has_left = valid && lane > 0u && idx[0] > 0;
+  const long long stride[3] = {1, a.n[0] + 1, (long long)(a.n[0] + 1) * (a.n[1] + 1)};
+  long long vcol = idx[0];
+#if DC_DIM == 3
+  vcol += idx[1] * stride[1];
+#endif
+  long long foff[DC_NFACE];
+#pragma unroll
+  for (int f = 0; f < DC_NFACE; ++f) {
+    foff[f] = 0;
+#pragma unroll
+    for (int k = 0; k < L; ++k) foff[f] += ((f >> k) & 1) * stride[k];
+  }
+  auto load_face = [&](int plane, bool on, double (*Uf)[NS], double (*Zf)[NS]) {
+    const long long vb = vcol + plane * stride[L];
+#pragma unroll
+    for (int f = 0; f < DC_NFACE; ++f) {
+      if (f & 1) continue;
+      const long long d = a.dof_offset + (vb + foff[f]) * NS;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        Uf[f][s] = on ? a.x[d + s] : 0.0;
+        if (MODE == 1) Zf[f][s] = on ? ((a.cmask && a.cmask[d + s]) ? 0.0 : a.z[d + s]) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int f = 1; f < DC_NFACE; f += 2) {
+      const long long d = a.dof_offset + (vb + foff[f]) * NS;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const double ru = __shfl_down_sync(FULL, Uf[f - 1][s], 1);
+        Uf[f][s] = has_right ? ru : (on ? a.x[d + s] : 0.0);
+        if (MODE == 1) {
+          const double rz = __shfl_down_sync(FULL, Zf[f - 1][s], 1);
+          Zf[f][s] = has_right ? rz : (on ? ((a.cmask && a.cmask[d + s]) ? 0.0 : a.z[d + s]) : 0.0);
+        }
+      }
+    }
+  };
+  auto flush_face = [&](int plane, bool on, double (*af)[NS]) {
+    const long long vb = vcol + plane * stride[L];
+#pragma unroll
+    for (int f = 1; f < DC_NFACE; f += 2)
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const double recv = __shfl_up_sync(FULL, af[f][s], 1);
+        if (has_left) af[f - 1][s] += recv;
+      }
+    if (!on) return;
+#pragma unroll
+    for (int f = 0; f < DC_NFACE; ++f) {
+      if ((f & 1) && has_right) continue;   // the right neighbour reduces that corner
+      const long long d = a.dof_offset + (vb + foff[f]) * NS;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) dc_atomic_add(&a.r[d + s], af[f][s]);
+    }
+  };
+  double Ub[DC_NFACE][NS], Zb[MODE == 1 ? DC_NFACE : 1][NS], accb[DC_NFACE][NS];
+  load_face(kb, valid, Ub, Zb);
+#pragma unroll
+  for (int f = 0; f < DC_NFACE; ++f)
+#pragma unroll
+    for (int s = 0; s < NS; ++s) accb[f][s] = 0.0;
+  for (int kk = 0; kk < a.march; ++kk) {
+    const int k = kb + kk;
+    const bool act = valid && k < ke;
+    double Ut[DC_NFACE][NS], Zt[MODE == 1 ? DC_NFACE : 1][NS];
+    load_face(k + 1, act, Ut, Zt);
+    double acct[DC_NFACE][NS];
+    if (act) {
+      double U[DC_NCORN][NS], Z[MODE == 1 ? DC_NCORN : 1][NS], acc[DC_NCORN][NS];
+#pragma unroll
+      for (int f = 0; f < DC_NFACE; ++f)
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          U[f][s] = Ub[f][s];
+          U[f + DC_NFACE][s] = Ut[f][s];
+          if (MODE == 1) { Z[f][s] = Zb[f][s]; Z[f + DC_NFACE][s] = Zt[f][s]; }
+        }
+      idx[L] = k;
+      cell_fn(idx, U, Z, acc);
+#pragma unroll
+      for (int f = 0; f < DC_NFACE; ++f)
+#pragma unroll
+        for (int s = 0; s < NS; ++s) { accb[f][s] += acc[f][s]; acct[f][s] = acc[f + DC_NFACE][s]; }
+    }
+    flush_face(k, act, accb);
+    if (act) {
+#pragma unroll
+      for (int f = 0; f < DC_NFACE; ++f)
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          Ub[f][s] = Ut[f][s];
+          if (MODE == 1) Zb[f][s] = Zt[f][s];
+          accb[f][s] = acct[f][s];
+        }
+    }
+  }
+  flush_face(ke, valid && ke > kb, accb);
+}
+
+template <int C, int MODE>
+__device__ __forceinline__ void dc_structured_kernel(const DcStructArgs& a) {
+  constexpr int NS = DcComp<C>::NS;
+  constexpr int NV = MODE == 2 ? NS * NS : NS;
+  dc_struct_per_cell<C, MODE>(a, [&](const int* idx, const double (*U)[NS], const double (*Z)[NS], double (*acc)[NV]) {
+    dc_struct_cell<C, MODE>(a, idx, U, Z, acc);
+  });
+}
+template <int C, int MODE>
+__device__ __forceinline__ void dc_structured_march_kernel(const DcStructArgs& a) {
+  constexpr int NS = DcComp<C>::NS;
+  dc_struct_march<C, MODE>(a, [&](const int* idx, const double (*U)[NS], const double (*Z)[NS], double (*acc)[NS]) {
+    dc_struct_cell<C, MODE>(a, idx, U, Z, acc);
+  });
 }

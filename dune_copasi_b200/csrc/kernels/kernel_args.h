@@ -50,6 +50,7 @@ struct DcStructArgs {
   double h[3], origin[3];
   long long cell_begin;        // this launch covers the cells [cell_begin, ncells)
   long long ncells;
+  int march;                   // marching kernels: cells a thread walks along the last axis
   int dof_offset;
   double time, wM, wA;
   const double* x;

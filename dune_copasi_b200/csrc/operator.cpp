@@ -69,6 +69,10 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
     if (scheme == "auto") scheme = ok ? "structured" : "atomic";
     struct_comp_ = ok ? full : -1;
   }
+  struct_march_ = acfg.get("struct_march", 8);
+  if (struct_march_ < 0 || struct_march_ > 64) fail("model.assembly.b200.struct_march out of range");
+  // threads a launch should keep (4 waves of 148 SMs x 6 CTAs x 64 threads) before columns get shorter
+  struct_march_fill_ = acfg.get("struct_march_fill", 148 * 6 * 64 * 4);
   patch_pn_ = acfg.get("patch_vertices", 256);
   patch_pe_ = acfg.get("patch_elements", 512);
   patch_threads_ = acfg.get("patch_threads", 256);
@@ -413,12 +417,18 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       static const char* sn[5] = {"dc_k_struct_residual_", "dc_k_struct_apply_", "dc_k_struct_bdiag_", "", "dc_k_struct_diag_"};
       static const char* qn[5] = {"dc_k_q1_residual_", "dc_k_q1_apply_", "dc_k_q1_bdiag_", "dc_k_q1_csr_", "dc_k_q1_diag_"};
       static const char* sk[5] = {"struct_residual", "struct_apply", "struct_bdiag", "struct_csr", "struct_diag"};
-      cudaKernel_t k = q1 ? kernel(JitGroup::StructuredQ1, std::string(qn[mode]) + std::to_string(c))
-                          : kernel(JitGroup::Structured, std::string(sn[mode]) + std::to_string(c));
+      // residual / apply: register marching along the last axis (model.assembly.b200.struct_march
+      // cells per thread, 0 = one thread per cell); shortened when the box is too thin to fill the GPU
+      int march = (mode == 0 || mode == 1) ? struct_march_ : 0;
+      const long long total = a.ncells, layer = total / a.n[grid->dim - 1];
+      while (march > 1 && layer * ((a.n[grid->dim - 1] + march - 1) / march) < struct_march_fill_) march /= 2;
+      a.march = march;
+      const std::string kname = march > 0 ? std::string(q1 ? "dc_k_q1_march_" : "dc_k_struct_march_") + (mode == 0 ? "residual_" : "apply_")
+                                          : std::string(q1 ? qn[mode] : sn[mode]);
+      cudaKernel_t k = kernel(q1 ? JitGroup::StructuredQ1 : JitGroup::Structured, kname + std::to_string(c));
       const int sth = model->cfg.sub("model.assembly.b200").get("struct_threads", 64);
       // cell ranges of this launch: everything, or (multi-GPU overlap) the interior layers /
       // the two layers along the slab axis that touch ghost planes
-      const long long total = a.ncells, layer = total / a.n[grid->dim - 1];
       long long ranges[2][2] = {{0, total}, {0, 0}};
       int nranges = 1;
       if (struct_part_ == 1) { ranges[0][0] = layer; ranges[0][1] = total - layer; }
@@ -427,8 +437,13 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
         a.cell_begin = ranges[q][0];
         a.ncells = ranges[q][1];
         if (a.ncells <= a.cell_begin) continue;
+        long long nthreads = a.ncells - a.cell_begin;
+        if (march > 0) {
+          const long long layers = nthreads / layer;
+          nthreads = layer * ((layers + march - 1) / march);
+        }
         ProfScope ps(this, struct_part_ == 2 ? "struct_apply_halo_layers" : sk[mode]);
-        jit_launch(k, (unsigned)((a.ncells - a.cell_begin + sth - 1) / sth), sth, 0, stream, a);
+        jit_launch(k, (unsigned)((nthreads + sth - 1) / sth), sth, 0, stream, a);
         stats.launches++;
       }
       continue;

@@ -115,6 +115,8 @@ class DeviceOperator {
   std::vector<std::pair<uint64_t, int32_t>> morton_order(int c) const;
   cudaKernel_t kernel(JitGroup group, const std::string& name);
   std::map<int, std::unique_ptr<JitModule>> jit_;
+  int struct_march_ = 8;
+  long long struct_march_fill_ = 0;
   std::string jit_defines_;
   DeviceBuffer<double> coords_, cell_, cell_patch_;
   DeviceBuffer<int> elems_;
