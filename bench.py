@@ -186,7 +186,8 @@ def config_dict(args, cells):
     dim = getattr(args, "dim", 3)
     name = "cell3d_3comp_6species" if getattr(args, "workload", "grayscott") == "cell" else f"grayscott{dim}d"
     elem = "q1_cubes" if getattr(args, "element", "p1") == "q1" else "p1_kuhn"
-    return {"workload": f"{name}_{elem}_{cells}^{dim}", "element": elem, "cells": cells, "dt": args.dt, "rk": args.rk,
+    return {"workload": f"{name}_{elem}_{cells}^{dim}", "element": elem, "cells": cells,
+            "collectives": getattr(args, "collectives", "none (1 GPU)"), "dt": args.dt, "rk": args.rk,
             "linear_solver": "BiCGSTAB", "preconditioner": args.prec, "matrix_free": bool(args.matrix_free),
             "linear_rel_tol": 1e-8, "newton_rel_tol": 1e-8, "assembly": args.scheme,
             "l2": "inputs larger than L2 (every vector and the mesh exceed 126 MB at the default size)"}
@@ -249,6 +250,8 @@ def main():
             uid = torch.tensor(list(D.Comm.unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
         comm = D.Comm(bytes(uid.cpu().tolist()), rank, world, op)
+        args.collectives = ("NVLink peer memory (own kernels: all-reduce, slab halo) + NCCL for setup"
+                            if comm.uses_peer_memory else "NCCL")
         del gglobal
     owned = torch.tensor([sum(e - b for b, e in op.owned_ranges())], dtype=torch.int64, device="cuda")
     if dist is not None:

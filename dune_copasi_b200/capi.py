@@ -126,6 +126,7 @@ SYMBOLS = {
     "dcb_grid_halo_lists": (C.c_int, [_P, C.c_int, C.c_int, _I32, _I32]),
     "dcb_comm_create": (_P, [C.c_char_p, C.c_int, C.c_int, _P]),
     "dcb_comm_destroy": (None, [_P]),
+    "dcb_comm_uses_peer_memory": (C.c_int, [_P]),
     "dcb_operator_owned_ranges": (C.c_int, [_P, _I64, _I64, C.c_int]),
 }
 
@@ -431,6 +432,10 @@ class Operator:
 class Comm:
     def __init__(self, unique_id: bytes, rank: int, size: int, op: Operator):
         self.h = _ptr(lib().dcb_comm_create(unique_id, rank, size, op.h), "comm")
+
+    @property
+    def uses_peer_memory(self) -> bool:
+        return bool(lib().dcb_comm_uses_peer_memory(self.h))
 
     @staticmethod
     def unique_id() -> bytes:

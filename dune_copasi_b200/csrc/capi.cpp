@@ -509,6 +509,7 @@ dcb_comm* dcb_comm_create(const char id[128], int rank, int size, dcb_operator* 
   });
 }
 void dcb_comm_destroy(dcb_comm* c) { delete c; }
+int dcb_comm_uses_peer_memory(const dcb_comm* c) { return c && c->c && c->c->peer_active ? 1 : 0; }
 int dcb_operator_owned_ranges(const dcb_operator* o, int64_t* begin, int64_t* end, int cap) {
   std::vector<int64_t> b, e;
   o->op->grid->owned_ranges(b, e);

@@ -2,9 +2,13 @@
 
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "kernels/linalg.hpp"
+#include "kernels/peer.hpp"
 
 namespace dcb {
 
@@ -16,7 +20,8 @@ typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
 enum { ncclFloat64 = 8 };
-enum { ncclSum = 0 };
+enum { ncclSum = 0, ncclMin = 3 };
+enum { ncclInt8 = 0 };
 
 struct Nccl {
   void* h = nullptr;
@@ -24,6 +29,7 @@ struct Nccl {
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
@@ -47,6 +53,7 @@ Nccl& nccl() {
   n.CommInitRank = (decltype(n.CommInitRank))sym("ncclCommInitRank");
   n.CommDestroy = (decltype(n.CommDestroy))sym("ncclCommDestroy");
   n.AllReduce = (decltype(n.AllReduce))sym("ncclAllReduce");
+  n.AllGather = (decltype(n.AllGather))sym("ncclAllGather");
   n.Send = (decltype(n.Send))sym("ncclSend");
   n.Recv = (decltype(n.Recv))sym("ncclRecv");
   n.GroupStart = (decltype(n.GroupStart))sym("ncclGroupStart");
@@ -67,12 +74,100 @@ struct NcclCommunicator : Communicator {
   std::vector<DeviceBuffer<int32_t>> send_idx, recv_idx;
   std::vector<DeviceBuffer<double>> send_buf, recv_buf;
 
+  // ---- peer-memory path (kernels/peer.cu); NCCL stays the path for everything it does not cover
+  peer::Mailboxes boxes{};
+  peer::HaloArgs hargs{};
+  DeviceBuffer<unsigned> ticket;
+  bool peer_halo = false;
+  unsigned long long ar_seq = 0, halo_seq = 0;
+
   ~NcclCommunicator() override {
+    if (peer_active) {
+      cudaDeviceSynchronize();
+      for (int r = 0; r < size; ++r)
+        if (r != rank && boxes.box[r]) cudaIpcCloseMemHandle(boxes.box[r]);
+      if (boxes.box[rank]) cudaFree(boxes.box[rank]);
+    }
     if (comm) nccl().CommDestroy(comm);
   }
   void allreduce_sum(double* dev, int n, cudaStream_t s) override {
-    DCB_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclSum, comm, s));
+    if (peer_active && n <= peer::kMaxWords) {
+      peer::allreduce(boxes, dev, n, ++ar_seq, s);
+      DCB_CUDA(cudaGetLastError());
+    } else {
+      DCB_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclSum, comm, s));
+    }
     launches++;
+  }
+  // Map every rank's mailbox (CUDA IPC).  Collective; all ranks end up with the same answer.
+  void setup_peer_memory() {
+    const char* env = std::getenv("DCB_PEER_COLLECTIVES");
+    bool want = !(env && env[0] == '0') && size > 1 && size <= peer::kMaxRanks;
+    // halo slots: at most one lower and one higher neighbour, both with contiguous ranges
+    bool halo_ok = plan.peers.size() <= 2;
+    long long cap = 1;
+    for (size_t k = 0; k < plan.peers.size(); ++k) {
+      halo_ok = halo_ok && send_off[k] >= 0 && recv_off[k] >= 0;
+      cap = std::max<long long>(cap, (long long)plan.recv_idx[k].size());
+    }
+    if (plan.peers.size() == 2) halo_ok = halo_ok && ((plan.peers[0] < rank) != (plan.peers[1] < rank));
+    // agree on: everybody wants it, everybody's halo fits the slots, the largest slot
+    DeviceBuffer<double> d(3);
+    double h[3] = {want ? 1.0 : 0.0, halo_ok ? 1.0 : 0.0, -(double)cap};
+    DCB_CUDA(cudaMemcpy(d.p, h, sizeof h, cudaMemcpyHostToDevice));
+    DCB_NCCL(nccl().AllReduce(d.p, d.p, 3, ncclFloat64, ncclMin, comm, 0));
+    DCB_CUDA(cudaMemcpy(h, d.p, sizeof h, cudaMemcpyDeviceToHost));
+    if (h[0] < 0.5) return;
+    const bool halo_all = h[1] > 0.5;
+    cap = halo_all ? (long long)(-h[2]) : 1;
+    // own mailbox, zeroed, exported
+    const size_t bytes = peer::mailbox_bytes(size, cap);
+    char* mine = nullptr;
+    cudaIpcMemHandle_t handle;
+    std::memset(&handle, 0, sizeof handle);
+    bool ok = cudaMalloc(&mine, bytes) == cudaSuccess && cudaMemset(mine, 0, bytes) == cudaSuccess &&
+              cudaDeviceSynchronize() == cudaSuccess && cudaIpcGetMemHandle(&handle, mine) == cudaSuccess;
+    DeviceBuffer<char> hsend(sizeof handle), hall(sizeof handle * (size_t)size);
+    DCB_CUDA(cudaMemcpy(hsend.p, &handle, sizeof handle, cudaMemcpyHostToDevice));
+    DCB_NCCL(nccl().AllGather(hsend.p, hall.p, sizeof handle, ncclInt8, comm, 0));
+    std::vector<cudaIpcMemHandle_t> handles(size);
+    DCB_CUDA(cudaMemcpy(handles.data(), hall.p, sizeof handle * (size_t)size, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < peer::kMaxRanks; ++r) boxes.box[r] = nullptr;
+    for (int r = 0; r < size && ok; ++r) {
+      if (r == rank) { boxes.box[r] = mine; continue; }
+      void* ptr = nullptr;
+      ok = cudaIpcOpenMemHandle(&ptr, handles[r], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      boxes.box[r] = (char*)ptr;
+    }
+    cudaGetLastError();   // a failed mapping is not an error of the run: NCCL carries on
+    h[0] = ok ? 1.0 : 0.0;
+    DCB_CUDA(cudaMemcpy(d.p, h, sizeof(double), cudaMemcpyHostToDevice));
+    DCB_NCCL(nccl().AllReduce(d.p, d.p, 1, ncclFloat64, ncclMin, comm, 0));
+    DCB_CUDA(cudaMemcpy(h, d.p, sizeof(double), cudaMemcpyDeviceToHost));
+    if (h[0] < 0.5) {
+      for (int r = 0; r < size; ++r)
+        if (r != rank && boxes.box[r]) cudaIpcCloseMemHandle(boxes.box[r]);
+      if (mine) cudaFree(mine);
+      for (int r = 0; r < peer::kMaxRanks; ++r) boxes.box[r] = nullptr;
+      return;
+    }
+    boxes.rank = rank; boxes.size = size; boxes.cap = cap;
+    peer_active = true;
+    peer_halo = halo_all;
+    if (peer_halo) {
+      ticket.alloc(1);
+      ticket.zero();
+      hargs.npeers = (int)plan.peers.size();
+      hargs.counter = ticket.p;
+      for (size_t k = 0; k < plan.peers.size(); ++k) {
+        hargs.peer[k] = plan.peers[k];
+        hargs.local_slot[k] = plan.peers[k] < rank ? 0 : 1;    // where that peer's data lands here
+        hargs.remote_slot[k] = rank < plan.peers[k] ? 0 : 1;   // where ours lands there
+        hargs.send_off[k] = send_off[k]; hargs.send_n[k] = (long long)plan.send_idx[k].size();
+        hargs.recv_off[k] = recv_off[k]; hargs.recv_n[k] = (long long)plan.recv_idx[k].size();
+      }
+    }
+    DCB_CUDA(cudaDeviceSynchronize());
   }
   // contiguous index lists (slab partitions of structured grids: whole vertex planes) are sent
   // and received in place, without pack / unpack kernels
@@ -80,6 +175,12 @@ struct NcclCommunicator : Communicator {
 
   void halo_update(double* x, cudaStream_t s) override {
     const size_t np = plan.peers.size();
+    if (peer_halo) {   // every rank takes this branch or none does (setup_peer_memory agreed on it)
+      peer::halo(boxes, hargs, x, ++halo_seq, s);
+      DCB_CUDA(cudaGetLastError());
+      launches++;
+      return;
+    }
     if (np == 0) return;
     for (size_t k = 0; k < np; ++k)
       if (send_off[k] < 0 && send_idx[k].n) {
@@ -140,6 +241,7 @@ Communicator* nccl_communicator_create(const char unique_id[128], int rank, int 
     }
   }
   DCB_CUDA(cudaDeviceSynchronize());
+  c->setup_peer_memory();
   return c;
 }
 

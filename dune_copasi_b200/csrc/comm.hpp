@@ -25,6 +25,9 @@ struct Communicator {
   virtual void allreduce_sum(double* dev, int n, cudaStream_t s) = 0;   // in place
   virtual void halo_update(double* x, cudaStream_t s) = 0;              // owner -> ghost copies
   long long launches = 0;
+  // small all-reduces (and, on slab partitions, halo updates) run over NVLink peer memory
+  // (kernels/peer.cu) instead of NCCL; DCB_PEER_COLLECTIVES=0 turns that off
+  bool peer_active = false;
 };
 
 // NCCL-backed communicator; libnccl is resolved at run time (dlopen) so the library loads on

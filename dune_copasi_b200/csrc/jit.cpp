@@ -101,8 +101,9 @@ std::string jit_defines(const Model& model) {
   int th = acfg.get("patch_threads", 256), minb = acfg.get("patch_min_blocks", 3);
   if (th < 32 || th > 1024 || th % 32) fail("model.assembly.b200.patch_threads must be a multiple of 32 in [32,1024]");
   if (minb < 1 || minb > 8) fail("model.assembly.b200.patch_min_blocks out of range");
-  // 64 threads x 6 resident CTAs measured best on B200 (profiles/r01_struct_sweep.txt)
-  int sth = acfg.get("struct_threads", 64), sminb = acfg.get("struct_min_blocks", 6);
+  // 32 threads x 12 resident CTAs measured best on B200 (same 12 warps per SM as 64 x 6, finer
+  // grained: -4 % on the apply kernels; fewer registers spill, more registers starve the fp64 pipe)
+  int sth = acfg.get("struct_threads", 32), sminb = acfg.get("struct_min_blocks", 12);
   if (sth < 32 || sth > 1024 || sth % 32) fail("model.assembly.b200.struct_threads must be a multiple of 32 in [32,1024]");
   if (sminb < 1 || sminb > 16) fail("model.assembly.b200.struct_min_blocks out of range");
   // CSR fill is latency bound (binary searches + fp64 atomics): 8 resident CTAs of 128 threads

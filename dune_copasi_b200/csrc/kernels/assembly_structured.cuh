@@ -366,7 +366,7 @@ __device__ __forceinline__ void dc_struct_march(const DcStructArgs& a, CellFn ce
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         const double recv = __shfl_up_sync(FULL, af[f][s], 1);
-        if (has_left) af[f - 1][s] += recv;
+        if (has_left && on) af[f - 1][s] += recv;   // (idle iterations of a short last chunk still shuffle)
       }
     if (!on) return;
 #pragma unroll

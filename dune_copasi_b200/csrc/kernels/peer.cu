@@ -1,0 +1,109 @@
+// Collectives over NVLink peer memory (sm_100a), written for the two exchanges that sit on the
+// critical path of every Krylov half step on a slab-partitioned lattice:
+//   * all-reduce of 1..8 doubles (dot products, norms) across all ranks,
+//   * halo update of contiguous vertex planes with the two slab neighbours.
+// NCCL needs ~20-30 us for each of them at these sizes; a half step of the 256^3 problem on 8 GPUs
+// is ~0.25 ms of kernels, so three NCCL calls were a third of the step.  Here every rank owns a
+// "mailbox" in device memory that its peers have mapped through CUDA IPC: a rank *stores* its
+// contribution straight into the peers' mailboxes (P2P writes over NVSwitch), publishes it with a
+// sequence flag after a system-scope fence, and spins on its own flags for the peers' data.
+// Two parities of every slot make the protocol safe without a barrier: a rank can be at most one
+// exchange ahead of a peer, because finishing exchange s needs the peer's flag s, which the peer
+// writes only after it has finished reading exchange s-1.
+// Sums are formed in rank order on every rank: deterministic and identical everywhere.
+#include "peer.hpp"
+
+namespace dcb {
+namespace peer {
+
+namespace {
+
+__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_flag(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_data(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// one block, one thread per peer
+__global__ void __launch_bounds__(64) k_allreduce(Mailboxes m, double* data, int n, unsigned long long seq) {
+  const int p = threadIdx.x, par = (int)(seq & 1ull);
+  __shared__ double mine[kMaxWords];
+  if (p < n) mine[p] = data[p];
+  __syncthreads();
+  if (p < m.size) {
+    char* box = m.box[p];
+    double* dst = (double*)(box + ar_val_offset(m.size, par, m.rank));
+    for (int i = 0; i < n; ++i) dst[i] = mine[i];
+    __threadfence_system();
+    st_flag((unsigned long long*)(box + ar_flag_offset(m.size, par, m.rank)), seq);
+    // wait for peer p's contribution in the local mailbox
+    const unsigned long long* f = (const unsigned long long*)(m.box[m.rank] + ar_flag_offset(m.size, par, p));
+    while (ld_flag(f) != seq) {}
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (p < n) {
+    double sum = 0.0;
+    for (int q = 0; q < m.size; ++q)
+      sum += ld_data((const double*)(m.box[m.rank] + ar_val_offset(m.size, par, q)) + p);
+    data[p] = sum;
+  }
+}
+
+// grid of G blocks: push the send ranges into the neighbours' mailboxes, publish, wait, pull
+__global__ void __launch_bounds__(256) k_halo(Mailboxes m, HaloArgs h, double* x, unsigned long long seq) {
+  const int par = (int)(seq & 1ull);
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (int k = 0; k < h.npeers; ++k) {
+    // slot of the receiver that is reserved for data arriving from this side
+    double* dst = (double*)(m.box[h.peer[k]] + halo_data_offset(m.size, m.cap, h.remote_slot[k], par));
+    const double* src = x + h.send_off[k];
+    for (long long i = tid; i < h.send_n[k]; i += nth) dst[i] = src[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(h.counter, 1u);
+    last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    *h.counter = 0;
+    __threadfence_system();
+    for (int k = 0; k < h.npeers; ++k)
+      st_flag((unsigned long long*)(m.box[h.peer[k]] + halo_flag_offset(m.size, h.remote_slot[k], par)), seq);
+  }
+  for (int k = 0; k < h.npeers; ++k) {
+    if (threadIdx.x == 0) {
+      const unsigned long long* f = (const unsigned long long*)(m.box[m.rank] + halo_flag_offset(m.size, h.local_slot[k], par));
+      while (ld_flag(f) != seq) {}
+    }
+    __syncthreads();
+    __threadfence_system();
+    const double* src = (const double*)(m.box[m.rank] + halo_data_offset(m.size, m.cap, h.local_slot[k], par));
+    double* dst = x + h.recv_off[k];
+    for (long long i = tid; i < h.recv_n[k]; i += nth) dst[i] = ld_data(src + i);
+  }
+}
+
+}  // namespace
+
+void allreduce(const Mailboxes& m, double* data, int n, unsigned long long seq, cudaStream_t s) {
+  k_allreduce<<<1, 64, 0, s>>>(m, data, n, seq);
+}
+
+void halo(const Mailboxes& m, const HaloArgs& h, double* x, unsigned long long seq, cudaStream_t s) {
+  k_halo<<<kHaloBlocks, 256, 0, s>>>(m, h, x, seq);
+}
+
+}  // namespace peer
+}  // namespace dcb

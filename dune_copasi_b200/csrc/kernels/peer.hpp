@@ -1,0 +1,50 @@
+// Peer-memory collectives (peer.cu): mailbox layout shared by host and device, launchers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+
+namespace dcb {
+namespace peer {
+
+constexpr int kMaxRanks = 16;     // one NVSwitch domain
+constexpr int kMaxWords = 8;      // doubles per all-reduce
+constexpr int kHaloBlocks = 64;
+
+struct Mailboxes {
+  char* box[kMaxRanks];           // box[rank] is local, the others are IPC mappings of the peers'
+  int rank, size;
+  long long cap;                  // doubles per halo slot (the largest receive list of any rank)
+};
+
+// byte offsets inside a mailbox
+__host__ __device__ inline size_t ar_val_offset(int size, int par, int src) {
+  return ((size_t)(par * size + src) * kMaxWords) * sizeof(double);
+}
+__host__ __device__ inline size_t ar_flag_offset(int size, int par, int src) {
+  return (size_t)2 * size * kMaxWords * sizeof(double) + (size_t)(par * size + src) * 8;
+}
+// slot 0: data from the lower neighbour, slot 1: from the higher one
+__host__ __device__ inline size_t halo_flag_offset(int size, int slot, int par) {
+  return (size_t)2 * size * kMaxWords * sizeof(double) + (size_t)2 * size * 8 + (size_t)(slot * 2 + par) * 8;
+}
+__host__ __device__ inline size_t halo_data_offset(int size, long long cap, int slot, int par) {
+  size_t head = (size_t)2 * size * kMaxWords * sizeof(double) + (size_t)2 * size * 8 + 4 * 8;
+  head = (head + 255) / 256 * 256;
+  return head + (size_t)(slot * 2 + par) * (size_t)cap * sizeof(double);
+}
+inline size_t mailbox_bytes(int size, long long cap) { return halo_data_offset(size, cap, 2, 0); }
+
+struct HaloArgs {
+  int npeers;                     // <= 2
+  int peer[2];
+  int local_slot[2], remote_slot[2];
+  long long send_off[2], send_n[2], recv_off[2], recv_n[2];
+  unsigned* counter;              // self-resetting ticket of the push phase
+};
+
+void allreduce(const Mailboxes& m, double* data, int n, unsigned long long seq, cudaStream_t s);
+void halo(const Mailboxes& m, const HaloArgs& h, double* x, unsigned long long seq, cudaStream_t s);
+
+}  // namespace peer
+}  // namespace dcb

@@ -69,8 +69,12 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
     if (scheme == "auto") scheme = ok ? "structured" : "atomic";
     struct_comp_ = ok ? full : -1;
   }
+  // measured on B200 (256^3, profiles/README.md): marching pays for the residual (-7 % P1, -20 % Q1)
+  // but not for the apply, whose second field doubles the carried state (+5 %): off there by default
   struct_march_ = acfg.get("struct_march", 8);
-  if (struct_march_ < 0 || struct_march_ > 64) fail("model.assembly.b200.struct_march out of range");
+  struct_march_apply_ = acfg.get("struct_march_apply", 0);
+  if (struct_march_ < 0 || struct_march_ > 64 || struct_march_apply_ < 0 || struct_march_apply_ > 64)
+    fail("model.assembly.b200.struct_march / struct_march_apply out of range");
   // threads a launch should keep (4 waves of 148 SMs x 6 CTAs x 64 threads) before columns get shorter
   struct_march_fill_ = acfg.get("struct_march_fill", 148 * 6 * 64 * 4);
   patch_pn_ = acfg.get("patch_vertices", 256);
@@ -419,14 +423,14 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       static const char* sk[5] = {"struct_residual", "struct_apply", "struct_bdiag", "struct_csr", "struct_diag"};
       // residual / apply: register marching along the last axis (model.assembly.b200.struct_march
       // cells per thread, 0 = one thread per cell); shortened when the box is too thin to fill the GPU
-      int march = (mode == 0 || mode == 1) ? struct_march_ : 0;
+      int march = mode == 0 ? struct_march_ : mode == 1 ? struct_march_apply_ : 0;
       const long long total = a.ncells, layer = total / a.n[grid->dim - 1];
       while (march > 1 && layer * ((a.n[grid->dim - 1] + march - 1) / march) < struct_march_fill_) march /= 2;
       a.march = march;
       const std::string kname = march > 0 ? std::string(q1 ? "dc_k_q1_march_" : "dc_k_struct_march_") + (mode == 0 ? "residual_" : "apply_")
                                           : std::string(q1 ? qn[mode] : sn[mode]);
       cudaKernel_t k = kernel(q1 ? JitGroup::StructuredQ1 : JitGroup::Structured, kname + std::to_string(c));
-      const int sth = model->cfg.sub("model.assembly.b200").get("struct_threads", 64);
+      const int sth = model->cfg.sub("model.assembly.b200").get("struct_threads", 32);
       // cell ranges of this launch: everything, or (multi-GPU overlap) the interior layers /
       // the two layers along the slab axis that touch ghost planes
       long long ranges[2][2] = {{0, total}, {0, 0}};

@@ -115,7 +115,7 @@ class DeviceOperator {
   std::vector<std::pair<uint64_t, int32_t>> morton_order(int c) const;
   cudaKernel_t kernel(JitGroup group, const std::string& name);
   std::map<int, std::unique_ptr<JitModule>> jit_;
-  int struct_march_ = 8;
+  int struct_march_ = 8, struct_march_apply_ = 0;
   long long struct_march_fill_ = 0;
   std::string jit_defines_;
   DeviceBuffer<double> coords_, cell_, cell_patch_;

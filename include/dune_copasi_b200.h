@@ -211,6 +211,9 @@ int dcb_grid_halo_lists(const dcb_grid* local, int rank, int k, int32_t* send, i
 /* communicator for a bound local grid (halo plan derived from the partition) */
 dcb_comm* dcb_comm_create(const char id[128], int rank, int size, dcb_operator* op);
 void dcb_comm_destroy(dcb_comm*);
+/* 1 when the small all-reduces (and slab halo updates) run over NVLink peer memory mapped with CUDA IPC
+ * instead of NCCL (environment DCB_PEER_COLLECTIVES=0 forces NCCL) */
+int dcb_comm_uses_peer_memory(const dcb_comm*);
 /* owned local dof ranges [begin,end) per compartment */
 int dcb_operator_owned_ranges(const dcb_operator*, int64_t* begin, int64_t* end, int cap);
 

@@ -31,3 +31,16 @@ def test_two_rank_time_stepping_matches_serial_oracle(name, mf, extra):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "rel L2 err" in r.stdout
+
+
+def test_two_ranks_over_nccl_only():
+    """DCB_PEER_COLLECTIVES=0: the same run with every collective on NCCL."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29518", os.path.join(ROOT, "tools", "mgpu_check.py"),
+           "grayscott3d", "2", "1", ""]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT,
+                       env=dict(os.environ, DCB_PEER_COLLECTIVES="0"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "peer_memory=False" in r.stdout and "rel L2 err" in r.stdout

@@ -234,3 +234,35 @@ def test_fullsize_properties(n):
     Mu = op.jacobian_apply(t, 1.0, 0.0, x0, ones)
     coef = np.tile([0.042, 0.042 + 0.061], nd // 2)
     assert rel(K1, coef * Mu) <= 1e-10
+
+
+MARCH_CASES = ["gauss2d", "gauss3d", "poisson", "grayscott2d", "grayscott3d", "mitchell_schaefer"] + ALL
+
+
+@pytest.mark.parametrize("march", [0, 1, 3, 8])
+@pytest.mark.parametrize("name", MARCH_CASES)
+def test_marching_kernels(name, march):
+    """Residual / apply through the marching drivers (threads walk `march` cells up the last axis,
+    warp shuffles along x) on lattices whose rows do not align with warps; march = 0 is the
+    one-thread-per-cell driver.  struct_march_fill = 0 keeps the columns long on these small grids."""
+    import dune_copasi_b200 as D
+    case = K.ALL_CASES[name]
+    over = {"model.assembly.b200.struct_march": march, "model.assembly.b200.struct_march_apply": march,
+            "model.assembly.b200.struct_march_fill": 0}
+    om = case.oracle(**over)
+    cfg, model, grid = K.product_objects(case, **over)
+    op = D.Operator(model, grid)
+    x = K.rand_state(om.ndofs, 21)
+    z = K.rand_state(om.ndofs, 22, -1.0, 1.0)
+    t, wM, wA = case.t0 + 0.2, 0.9, 0.4 * case.dt
+    ref = np.zeros(om.ndofs)
+    om.residual(1, t, wM, x, ref)
+    om.residual(0, t, wA, x, ref)
+    assert rel(op.residual(t, wM, wA, x), ref) <= OP_TOL, (name, march)
+    cd, _ = om.constraints()
+    z2 = z.copy()
+    z2[cd] = 0.0
+    ref = np.zeros(om.ndofs)
+    om.jacobian_apply(1, t, wM, x, z2, ref)
+    om.jacobian_apply(0, t, wA, x, z2, ref)
+    assert rel(op.jacobian_apply(t, wM, wA, x, z), ref) <= OP_TOL, (name, march)

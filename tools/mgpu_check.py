@@ -88,7 +88,7 @@ def main():
                     got[mg.comp_offset[c] + pos * ns + s] = vals[c][s::ns]
         assert not np.isnan(got).any(), "some dofs were not owned by any rank"
         err = np.linalg.norm(got - uref) / np.linalg.norm(uref)
-        print(f"mgpu_check {name} world={world} steps={nsteps} matrix_free={mf}: rel L2 err {err:.3e}")
+        print(f"mgpu_check {name} world={world} steps={nsteps} matrix_free={mf} peer_memory={comm.uses_peer_memory}: rel L2 err {err:.3e}")
         ok = err <= 1e-10
         if red_vals:
             ref_vals, _ = K.ORC.reduce(om, uref, tt)
