@@ -217,6 +217,7 @@ def main():
     ap.add_argument("--set", default="", help="any ini key overrides, e.g. model.time_step_operator.linear_solver.b200.speculation=false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-q1", action="store_true", help="skip the Q1 variant that rides along with the P1 headline")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -234,151 +235,177 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    # ---- problem
-    cfg = D.Config(ini_for(args))
-    model = D.Model(cfg, args.dim)
-    t_setup = time.perf_counter()
-    gglobal = D.Grid.structured(args.dim, [args.cells] * args.dim, element="cube" if args.element == "q1" else "simplex")
-    nv_global = gglobal.nv
-    grid = gglobal.partition(rank, world) if world > 1 else gglobal
-    grid.bind(model)
-    op = D.Operator(model, grid)
-    comm = None
-    if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid = torch.tensor(list(D.Comm.unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(uid, 0)
-        comm = D.Comm(bytes(uid.cpu().tolist()), rank, world, op)
-        args.collectives = ("NVLink peer memory (own kernels: all-reduce, slab halo) + NCCL for setup"
-                            if comm.uses_peer_memory else "NCCL")
-        del gglobal
-    owned = torch.tensor([sum(e - b for b, e in op.owned_ranges())], dtype=torch.int64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(owned)
-    ndofs_global = int(owned.item())
-    st = D.Stepper(op, cfg, comm)
-    u0 = grid.interpolate(model, 0.0)
-    st.set_state(u0, 0.0)
-    t_setup = time.perf_counter() - t_setup
-    stream = torch.cuda.ExternalStream(op.stream)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(nsteps, e2e):
-        """-> device ms for nsteps (max over ranks)"""
-        u_host = None
-        if e2e:
-            # host buffers of the step's input/result live in pinned memory
-            u_host = torch.empty(op.ndofs, dtype=torch.float64).pin_memory().numpy()
-            st.get_state(u_host)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(nsteps):
-            if e2e:
-                st.set_state(u_host, st.time)        # H2D of the step's input through the C ABI
-            ok = st.step(args.dt)
-            if not ok:
-                raise SystemExit("time step failed")
-            if e2e:
-                st.get_state(u_host)                 # D2H of the step's result
-        e1.record(stream)
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    for _ in range(args.warmup):
-        assert st.step(args.dt)
-    s0 = st.stats()
-    D.lib().dcb_operator_profile(op.h, 1)
-    sampler.begin()
-    ms = timed(args.steps, False)
-    sampler.end()
-    prof = op.profile()
-    D.lib().dcb_operator_profile(op.h, 0)
-    s1 = st.stats()
-    clocks = sampler.stop() if rank == 0 else None
-    e2e = None
-    if not args.no_e2e:
-        ms_e2e = timed(args.steps, True)
-        nbytes = op.ndofs * 8
-        e2e = {"value": ndofs_global * args.steps / (ms_e2e * 1e-3), "unit": "DOF-updates/s",
-               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / args.steps}
-
-    def shutdown():
-        # every rank tears down in the same order: library objects (their NCCL communicator)
-        # first, then torch's process group
-        nonlocal st, comm, op
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        st = None
+    def measure(args):
+        # ---- problem
+        cfg = D.Config(ini_for(args))
+        model = D.Model(cfg, args.dim)
+        t_setup = time.perf_counter()
+        gglobal = D.Grid.structured(args.dim, [args.cells] * args.dim, element="cube" if args.element == "q1" else "simplex")
+        nv_global = gglobal.nv
+        grid = gglobal.partition(rank, world) if world > 1 else gglobal
+        grid.bind(model)
+        op = D.Operator(model, grid)
         comm = None
-        op = None
+        if world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid = torch.tensor(list(D.Comm.unique_id()), dtype=torch.uint8, device="cuda")
+            dist.broadcast(uid, 0)
+            comm = D.Comm(bytes(uid.cpu().tolist()), rank, world, op)
+            args.collectives = ("NVLink peer memory (own kernels: all-reduce, slab halo) + NCCL for setup"
+                                if comm.uses_peer_memory else "NCCL")
+            del gglobal
+        owned = torch.tensor([sum(e - b for b, e in op.owned_ranges())], dtype=torch.int64, device="cuda")
         if dist is not None:
-            dist.destroy_process_group()
+            dist.all_reduce(owned)
+        ndofs_global = int(owned.item())
+        st = D.Stepper(op, cfg, comm)
+        u0 = grid.interpolate(model, 0.0)
+        st.set_state(u0, 0.0)
+        t_setup = time.perf_counter() - t_setup
+        stream = torch.cuda.ExternalStream(op.stream)
 
-    if rank != 0:
+        def barrier():
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def timed(nsteps, e2e):
+            """-> device ms for nsteps (max over ranks)"""
+            u_host = None
+            if e2e:
+                # host buffers of the step's input/result live in pinned memory
+                u_host = torch.empty(op.ndofs, dtype=torch.float64).pin_memory().numpy()
+                st.get_state(u_host)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(nsteps):
+                if e2e:
+                    st.set_state(u_host, st.time)        # H2D of the step's input through the C ABI
+                ok = st.step(args.dt)
+                if not ok:
+                    raise SystemExit("time step failed")
+                if e2e:
+                    st.get_state(u_host)                 # D2H of the step's result
+            e1.record(stream)
+            barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms.item())
+
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        for _ in range(args.warmup):
+            assert st.step(args.dt)
+        s0 = st.stats()
+        D.lib().dcb_operator_profile(op.h, 1)
+        sampler.begin()
+        ms = timed(args.steps, False)
+        sampler.end()
+        prof = op.profile()
+        host = {k: v for k, v in prof.items() if k.startswith("host_")}     # host-side timers (ms)
+        prof = {k: v for k, v in prof.items() if not k.startswith("host_")}
+        D.lib().dcb_operator_profile(op.h, 0)
+        s1 = st.stats()
+        clocks = sampler.stop() if rank == 0 else None
+        e2e = None
+        if not args.no_e2e:
+            ms_e2e = timed(args.steps, True)
+            nbytes = op.ndofs * 8
+            e2e = {"value": ndofs_global * args.steps / (ms_e2e * 1e-3), "unit": "DOF-updates/s",
+                   "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / args.steps}
+
+        def shutdown():
+            # every rank tears down in the same order: library objects (their NCCL communicator)
+            # first; torch's process group goes last, in main()
+            nonlocal st, comm, op
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            st = None
+            comm = None
+            op = None
+
+        if rank != 0:
+            shutdown()
+            return None
+        d = {k: s1[k] - s0[k] for k in s1}
+        value = ndofs_global * args.steps / (ms * 1e-3)
+        # ---- roofline of the dominant kernel (by accumulated device time in the timed region)
+        peak, peak_src = peaks()
+        dim = args.dim
+        nodes, tets = nv_global / world, (6 if dim == 3 else 2) * args.cells ** dim / world
+        alg = {  # algorithmic bytes per launch, SURVEY.md 8(d) (per rank)
+            "patch_apply": nodes * (16 * 2 + 8 * dim + 8 * 2) + tets * 4 * (dim + 1),
+            "patch_residual": nodes * (16 * 2 + 8 * dim) + tets * 4 * (dim + 1),
+            "patch_bdiag": nodes * (8 * 2 + 8 * dim + 8 * 4) + tets * 4 * (dim + 1),
+            "elem_apply": nodes * (16 * 2 + 8 * dim + 8 * 2) + tets * 4 * (dim + 1),
+            "elem_residual": nodes * (16 * 2 + 8 * dim) + tets * 4 * (dim + 1),
+            "spmv": op.ndofs * (54 if args.element == "q1" else 30) * 12 + op.ndofs * 20,
+            # structured-implicit variant: no connectivity, no coordinates (SURVEY 8d: 32 B/vertex)
+            "struct_residual": nodes * (16 * 2),
+            "struct_apply": nodes * (16 * 2 + 8 * 2),
+            "struct_bdiag": nodes * (8 * 2 + 8 * 4),
+        }
+        top = max(prof, key=lambda k: prof[k]["ms"]) if prof else None
+        roof = None
+        if top:
+            avg_ms = prof[top]["ms"] / max(1, prof[top]["launches"])
+            ach = alg.get(top, 0.0) / (avg_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": measured_traffic(top, args.cells, world, "/q1" if args.element == "q1" else ""), "algorithmic_bytes": alg.get(top, 0.0),
+                    "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches": prof[top]["launches"],
+                    "share_of_step": prof[top]["ms"] / ms,
+                    "breakdown_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
+                    "host_ms_per_step": {k: v["ms"] / args.steps for k, v in host.items()}}
+            # the assembly kernels are fp64-pipe bound on B200 (64 fp64 lanes/SM/clk), not HBM bound:
+            # report the live fp64 instruction rate against that peak next to the HBM fraction
+            path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            key = f"{top}.fp64_instr_per_cell" + (".q1" if args.element == "q1" else "")
+            per_cell = json.load(open(path)).get(key) if os.path.exists(path) else None
+            if per_cell and dim == 3 and clocks and clocks.get("sm_mhz"):
+                cells_rank = args.cells ** dim / world
+                rate = cells_rank * per_cell / (avg_ms * 1e-3)
+                peak64 = 148 * 64 * clocks["sm_mhz"] * 1e6
+                roof["fp64_pipe"] = {"instr_per_cell": per_cell, "achieved_ginstr_s": rate / 1e9,
+                                     "peak_ginstr_s": peak64 / 1e9, "frac": rate / peak64,
+                                     "note": "dominant kernel is bound by the fp64 pipe; HBM traffic is ~1.3x algorithmic"}
+        cb = None
+        line = {"metric": metric_name(args), "value": value, "unit": "DOF-updates/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, args.cells),
+                "time_steps_per_s": args.steps / (ms * 1e-3), "dofs": int(ndofs_global), "e2e": e2e,
+                "gpu_launches": int(d["kernel_launches"]), "clocks": clocks, "roofline": roof, "cpu_baseline": cb,
+                "solver_stats": d, "setup_s": t_setup}
         shutdown()
+        return line
+
+    line = measure(args)
+    # BASELINE configs[3] words the lattice as "Q1": the same run on the cells as Q1 elements rides along
+    # (the headline stays on the reference's own element, P1 on the Kuhn split -- SURVEY.md F3)
+    q1 = None
+    if args.element == "p1" and args.dim == 3 and args.workload == "grayscott" and not args.no_q1:
+        qargs = argparse.Namespace(**vars(args))
+        qargs.element = "q1"
+        q1 = measure(qargs)
+    if dist is not None:
+        dist.destroy_process_group()
+    if rank != 0:
         return
-    d = {k: s1[k] - s0[k] for k in s1}
-    value = ndofs_global * args.steps / (ms * 1e-3)
-    # ---- roofline of the dominant kernel (by accumulated device time in the timed region)
-    peak, peak_src = peaks()
-    dim = args.dim
-    nodes, tets = nv_global / world, (6 if dim == 3 else 2) * args.cells ** dim / world
-    alg = {  # algorithmic bytes per launch, SURVEY.md 8(d) (per rank)
-        "patch_apply": nodes * (16 * 2 + 8 * dim + 8 * 2) + tets * 4 * (dim + 1),
-        "patch_residual": nodes * (16 * 2 + 8 * dim) + tets * 4 * (dim + 1),
-        "patch_bdiag": nodes * (8 * 2 + 8 * dim + 8 * 4) + tets * 4 * (dim + 1),
-        "elem_apply": nodes * (16 * 2 + 8 * dim + 8 * 2) + tets * 4 * (dim + 1),
-        "elem_residual": nodes * (16 * 2 + 8 * dim) + tets * 4 * (dim + 1),
-        "spmv": op.ndofs * (54 if args.element == "q1" else 30) * 12 + op.ndofs * 20,
-        # structured-implicit variant: no connectivity, no coordinates (SURVEY 8d: 32 B/vertex)
-        "struct_residual": nodes * (16 * 2),
-        "struct_apply": nodes * (16 * 2 + 8 * 2),
-        "struct_bdiag": nodes * (8 * 2 + 8 * 4),
-    }
-    top = max(prof, key=lambda k: prof[k]["ms"]) if prof else None
-    roof = None
-    if top:
-        avg_ms = prof[top]["ms"] / max(1, prof[top]["launches"])
-        ach = alg.get(top, 0.0) / (avg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": measured_traffic(top, args.cells, world, "/q1" if args.element == "q1" else ""), "algorithmic_bytes": alg.get(top, 0.0),
-                "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches": prof[top]["launches"],
-                "share_of_step": prof[top]["ms"] / ms,
-                "breakdown_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}}
-        # the assembly kernels are fp64-pipe bound on B200 (64 fp64 lanes/SM/clk), not HBM bound:
-        # report the live fp64 instruction rate against that peak next to the HBM fraction
-        path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        key = f"{top}.fp64_instr_per_cell" + (".q1" if args.element == "q1" else "")
-        per_cell = json.load(open(path)).get(key) if os.path.exists(path) else None
-        if per_cell and dim == 3 and clocks and clocks.get("sm_mhz"):
-            cells_rank = args.cells ** dim / world
-            rate = cells_rank * per_cell / (avg_ms * 1e-3)
-            peak64 = 148 * 64 * clocks["sm_mhz"] * 1e6
-            roof["fp64_pipe"] = {"instr_per_cell": per_cell, "achieved_ginstr_s": rate / 1e9,
-                                 "peak_ginstr_s": peak64 / 1e9, "frac": rate / peak64,
-                                 "note": "dominant kernel is bound by the fp64 pipe; HBM traffic is ~1.3x algorithmic"}
-    cb = None
-    line = {"metric": metric_name(args), "value": value, "unit": "DOF-updates/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, args.cells),
-            "time_steps_per_s": args.steps / (ms * 1e-3), "dofs": int(ndofs_global), "e2e": e2e,
-            "gpu_launches": int(d["kernel_launches"]), "clocks": clocks, "roofline": roof, "cpu_baseline": cb,
-            "solver_stats": d, "setup_s": t_setup}
-    shutdown()
+    if q1 is not None:
+        keep = ("metric", "value", "unit", "ms_per_step", "time_steps_per_s", "dofs", "e2e", "gpu_launches", "clocks",
+                "solver_stats")
+        line["q1_variant"] = {k: q1[k] for k in keep}
+        line["q1_variant"]["config"] = q1["config"]
+        line["q1_variant"]["roofline"] = {k: q1["roofline"][k] for k in
+                                          ("kernel", "achieved", "peak", "frac", "avg_launch_ms", "share_of_step",
+                                           "breakdown_ms_per_step") if q1["roofline"] and k in q1["roofline"]}
+        if q1["roofline"] and "fp64_pipe" in q1["roofline"]:
+            line["q1_variant"]["roofline"]["fp64_pipe"] = q1["roofline"]["fp64_pipe"]
     if not args.no_cpu_baseline:
         # the CPU arm runs after the GPUs are released (rank 0 only)
         line["cpu_baseline"], _, _ = cpu_baseline(args, 2, 1, args.cpu_cells)

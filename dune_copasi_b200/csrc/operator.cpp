@@ -200,7 +200,8 @@ void DeviceOperator::prof_end() {
   DCB_CUDA(cudaEventRecord(prof_.back().b, stream));
 }
 std::map<std::string, std::pair<double, long long>> DeviceOperator::profile_collect() {
-  std::map<std::string, std::pair<double, long long>> out;
+  std::map<std::string, std::pair<double, long long>> out = host_prof_;
+  host_prof_.clear();
   if (prof_.empty()) return out;
   DCB_CUDA(cudaStreamSynchronize(stream));
   for (auto& r : prof_) {

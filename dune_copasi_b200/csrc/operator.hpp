@@ -6,6 +6,7 @@
 // 403-405): apply(x, r) is additive (cf. :223), derivative(x) yields either the "container"
 // (CSR) or a matrix-free apply.
 #pragma once
+#include <chrono>
 #include <map>
 #include <memory>
 #include <vector>
@@ -94,6 +95,22 @@ class DeviceOperator {
   void prof_end();
   // synchronises; kind -> (accumulated ms, launches); clears the record
   std::map<std::string, std::pair<double, long long>> profile_collect();
+  // host-side time (ms) next to the device events: how long the host waited in synchronisations
+  // ("host_wait") against the whole step ("host_step") tells whether the device ever starves
+  void host_add(const char* kind, double ms) {
+    if (!profiling_) return;
+    host_prof_[kind].first += ms;
+    host_prof_[kind].second += 1;
+  }
+  struct HostTimer {
+    DeviceOperator* op;
+    const char* kind;
+    std::chrono::steady_clock::time_point t0;
+    HostTimer(DeviceOperator* o, const char* k) : op(o), kind(k), t0(std::chrono::steady_clock::now()) {}
+    ~HostTimer() {
+      op->host_add(kind, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+  };
   struct ProfScope {
     DeviceOperator* op;
     ProfScope(DeviceOperator* o, const char* kind) : op(o) { op->prof_begin(kind); }
@@ -105,6 +122,7 @@ class DeviceOperator {
   struct ProfRec { std::string kind; cudaEvent_t a = nullptr, b = nullptr; };
   bool profiling_ = false;
   std::vector<ProfRec> prof_;
+  std::map<std::string, std::pair<double, long long>> host_prof_;
   void launch_volume(const char* kind, int mode, double t, double wM, double wA, const double* x,
                      const double* z, double* r, double* vals, double* bdiag);
   void launch_facets(const char* kind, double t, double wA, const double* x, const double* z,

@@ -229,7 +229,7 @@ SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
     { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, r, r, pair(-1) + 1, ws_, s); L++; }
     if (comm_) comm_->allreduce_sum(pair(-1) + 1, 1, s);
     DCB_CUDA(cudaMemcpyAsync(hscal_.p, pair(-1) + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
-    DCB_CUDA(cudaStreamSynchronize(s));
+    { DeviceOperator::HostTimer ht(op_.get(), "host_wait"); DCB_CUDA(cudaStreamSynchronize(s)); }
     double norm0 = std::sqrt(hscal_.p[0]), norm = norm0;
     res.defect0 = norm0;
     if (!(norm0 == norm0)) { res.converged = false; return res; }
@@ -273,7 +273,7 @@ SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
       queued = false;
       const bool ahead = speculate(norm);
       if (ahead) second_half(i, x_cur, x_alt);            // speculative
-      DCB_CUDA(cudaEventSynchronize(ev_[0]));
+      { DeviceOperator::HostTimer ht(op_.get(), "host_wait"); DCB_CUDA(cudaEventSynchronize(ev_[0])); }
       pending = true;
       double h = hscal_.p[2];
       alpha = rho_new / h;
@@ -284,7 +284,7 @@ SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
       it += 0.5;
       if (!ahead) second_half(i, x_cur, x_alt);
       if (it + 0.5 < max_iterations && speculate(norm)) { first_half(i + 1); queued = true; }   // speculative
-      DCB_CUDA(cudaEventSynchronize(ev_[1]));
+      { DeviceOperator::HostTimer ht(op_.get(), "host_wait"); DCB_CUDA(cudaEventSynchronize(ev_[1])); }
       pending = false;
       std::swap(x_cur, x_alt);                            // the iterate of this iteration
       const double* pr = hscal_.p + 8 + 2 * (i & 1);

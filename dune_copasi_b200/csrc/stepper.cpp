@@ -83,7 +83,7 @@ double StepOperator::norm2(const double* r) {
   op->stats.launches++;
   if (comm_) comm_->allreduce_sum(scal_.p, 1, s);
   DCB_CUDA(cudaMemcpyAsync(hscal_.p, scal_.p, sizeof(double), cudaMemcpyDeviceToHost, s));
-  DCB_CUDA(cudaStreamSynchronize(s));
+  { DeviceOperator::HostTimer ht(op.get(), "host_wait"); DCB_CUDA(cudaStreamSynchronize(s)); }
   return hscal_.p[0];
 }
 
@@ -139,6 +139,7 @@ bool StepOperator::solve_stage(double* x, double ts, double wM, double wA, const
 }
 
 bool StepOperator::step(double* u, double t, double dt) {
+  DeviceOperator::HostTimer whole(op.get(), "host_step");
   cudaStream_t s = op->stream;
   const int64_t n = op->ndofs;
   const size_t nst = a_.size();

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Measurement variants next to the headline: python bench.py with other schemes / solvers /
 # workloads, one summary line each.  Usage: bash tools/bench_variants.sh [name ...]
-run() { name=$1; shift; timeout 300 python bench.py --no-cpu-baseline "$@" > gpurun_out/var_$name.log 2>&1; tail -1 gpurun_out/var_$name.log | python -c "
+run() { name=$1; shift; timeout 300 python bench.py --no-cpu-baseline --no-q1 "$@" > gpurun_out/var_$name.log 2>&1; tail -1 gpurun_out/var_$name.log | python -c "
 import sys,json
 try:
     d=json.loads(sys.stdin.read()); r=d.get('roofline') or {}

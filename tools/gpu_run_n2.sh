@@ -10,7 +10,7 @@ tail -5 gpurun_out/multi_tests.log
 fi
 for el in ${2:-p1 q1}; do
 for peer in 1 0; do
-DCB_PEER_COLLECTIVES=$peer timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --element $el --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_${el}_n${N}_peer${peer}.json 2> gpurun_out/bench_${el}_n${N}_peer${peer}.err; echo "bench $el n$N peer=$peer rc=$?"
+DCB_PEER_COLLECTIVES=$peer timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --element $el --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-q1 > gpurun_out/bench_${el}_n${N}_peer${peer}.json 2> gpurun_out/bench_${el}_n${N}_peer${peer}.err; echo "bench $el n$N peer=$peer rc=$?"
 tail -1 gpurun_out/bench_${el}_n${N}_peer${peer}.json | python -c "
 import sys, json
 d=json.loads(sys.stdin.read()); r=d['roofline']

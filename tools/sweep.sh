@@ -3,7 +3,7 @@
 cells=$1; shift
 for v in "$@"; do
   echo "== $v"
-  timeout 300 python bench.py --cells $cells --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --b200 "$v" 2>&1 | tail -1 | python -c "
+  timeout 300 python bench.py --cells $cells --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-q1 --b200 "$v" 2>&1 | tail -1 | python -c "
 import sys, json
 l=sys.stdin.read().strip()
 try:
