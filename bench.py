@@ -60,7 +60,7 @@ def ini_for(args):
     for kv in filter(None, getattr(args, "set", "").split(",")):
         k, v = kv.split("=")
         over[k] = v
-    case = "cell3d" if getattr(args, "workload", "grayscott") == "cell" else "grayscott3d"
+    case = {"cell": "cell3d", "cell10": "cell3d_10"}.get(getattr(args, "workload", "grayscott"), "grayscott3d")
     return K.CASES[case].ini_with(**over)
 
 
@@ -184,7 +184,8 @@ def run_reference(args):
 
 def config_dict(args, cells):
     dim = getattr(args, "dim", 3)
-    name = "cell3d_3comp_6species" if getattr(args, "workload", "grayscott") == "cell" else f"grayscott{dim}d"
+    name = {"cell": "cell3d_3comp_6species", "cell10": "cell3d_3comp_10species"}.get(getattr(args, "workload", "grayscott"),
+                                                                                       f"grayscott{dim}d")
     elem = "q1_cubes" if getattr(args, "element", "p1") == "q1" else "p1_kuhn"
     return {"workload": f"{name}_{elem}_{cells}^{dim}", "element": elem, "cells": cells,
             "collectives": getattr(args, "collectives", "none (1 GPU)"), "dt": args.dt, "rk": args.rk,
@@ -210,9 +211,9 @@ def main():
     ap.add_argument("--prec", default="Jacobi")
     ap.add_argument("--scheme", default="auto")
     ap.add_argument("--matrix-free", type=int, default=1)
-    ap.add_argument("--workload", default="grayscott", choices=["grayscott", "cell"],
-                    help="grayscott: BASELINE configs[3] (headline); cell: 3-compartment / 6-species cell model "
-                         "(configs[4] in miniature, general unstructured kernels)")
+    ap.add_argument("--workload", default="grayscott", choices=["grayscott", "cell", "cell10"],
+                    help="grayscott: BASELINE configs[3] (headline); cell / cell10: 3-compartment cell model with "
+                         "6 / 10 species (configs[4] in miniature, general unstructured kernels)")
     ap.add_argument("--b200", default="", help="model.assembly.b200.* overrides, e.g. patch_elements=768,patch_min_blocks=4")
     ap.add_argument("--set", default="", help="any ini key overrides, e.g. model.time_step_operator.linear_solver.b200.speculation=false")
     ap.add_argument("--no-cpu-baseline", action="store_true")

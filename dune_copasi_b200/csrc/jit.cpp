@@ -33,9 +33,13 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
       o << "extern \"C\" __global__ void __launch_bounds__(128) dc_k_bdiag_volume_" << c
         << "(DcVolArgs a) { dc_jacobian_volume<" << c << ", 1>(a); }\n";
     }
-    if (all || group == JitGroup::Csr)
+    if (all || group == JitGroup::Csr) {
       o << "extern \"C\" __global__ void __launch_bounds__(128, DC_CSR_MINB) dc_k_jacobian_volume_" << c
         << "(DcVolArgs a) { dc_jacobian_volume<" << c << ", 0>(a); }\n";
+      if (!model.numerical_jacobian && !model.has_extended_terms(c))
+        o << "extern \"C\" __global__ void __launch_bounds__(64) dc_k_jacobian_gather_" << c
+          << "(DcVolArgs a) { dc_jacobian_gather<" << c << ">(a); }\n";
+    }
     if (all || group == JitGroup::Patch) {
       o << "extern \"C\" __global__ void __launch_bounds__(DC_PATCH_THREADS, DC_PATCH_MINB) dc_k_patch_residual_" << c
         << "(DcPatchArgs a) { dc_patch_kernel<" << c << ", 0>(a); }\n";

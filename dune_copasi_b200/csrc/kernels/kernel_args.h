@@ -21,6 +21,11 @@ struct DcVolArgs {
   double* vals;
   double* bdiag;               // block diagonal, NS x NS per vertex: bdiag[dof0*NS + i*NS + j]
   const unsigned char* cmask;  // per-dof Dirichlet mask (null: none); masked z entries act as 0
+  // gather form of the CSR fill: vertices of this compartment and the elements around them
+  const int* verts;            // vertex ids (null: 0..n-1)
+  const int* vptr;             // [n+1]
+  const int* vel;              // (element << 2 | local vertex index)
+  int gather_maxlen;           // longest row of the compartment (shared-memory slots per species row)
 };
 
 struct DcPatchArgs {

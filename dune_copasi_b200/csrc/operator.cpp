@@ -77,6 +77,12 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
     fail("model.assembly.b200.struct_march / struct_march_apply out of range");
   // threads a launch should keep (4 waves of 148 SMs x 6 CTAs x 64 threads) before columns get shorter
   struct_march_fill_ = acfg.get("struct_march_fill", 148 * 6 * 64 * 4);
+  // CSR fill: scatter = element per thread + fp64 atomics (default); gather = one thread per vertex
+  // re-integrating the elements around it, rows accumulated in shared memory, no atomics.  Measured on
+  // B200 (128^3 Gray-Scott): scatter 4.7 ms, gather 13.8 ms per fill -- the (d+1)-fold redundant
+  // element loads and the long serial loop per thread cost more than the atomics (profiles/README.md)
+  csr_fill_ = acfg.get("csr_fill", std::string("scatter"));
+  if (csr_fill_ != "gather" && csr_fill_ != "scatter") fail("model.assembly.b200.csr_fill must be 'gather' or 'scatter'");
   patch_pn_ = acfg.get("patch_vertices", 256);
   patch_pe_ = acfg.get("patch_elements", 512);
   patch_threads_ = acfg.get("patch_threads", 256);
@@ -490,6 +496,22 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       a.rowptr = (const long long*)rowptr.p; a.colidx = colidx.p; a.vals = vals;
       a.bdiag = bdiag ? bdiag + bdiag_shift(c) : nullptr;
       a.cmask = cmask.p;
+      if (mode == 3 && csr_fill_ == "gather" && !fd) {
+        ensure_gather();
+        const GatherSet& G = gather_[c];
+        if (G.usable) {
+          a.verts = G.verts.p; a.vptr = G.vptr.p; a.vel = G.vel.p; a.gather_maxlen = G.maxlen;
+          a.n = G.nverts;
+          const int th = 64;
+          const size_t smem = (size_t)G.maxlen * ns * sizeof(double) * th;
+          cudaKernel_t k = kernel(JitGroup::Csr, "dc_k_jacobian_gather_" + std::to_string(c));
+          DCB_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          ProfScope ps(this, "csr_fill");
+          jit_launch(k, (unsigned)((a.n + th - 1) / th), th, smem, stream, a);
+          stats.launches++;
+          continue;
+        }
+      }
       cudaKernel_t k = kernel(mode == 3 ? JitGroup::Csr : JitGroup::Element, std::string(kind) + std::to_string(c));
       static const char* ek[4] = {"elem_residual", "elem_apply", "elem_bdiag", "csr_fill"};
       ProfScope ps(this, ek[mode]);
@@ -572,6 +594,47 @@ void DeviceOperator::jacobian_csr(double t, double wM, double wA, const double* 
   ensure_csr();
   launch_volume("dc_k_jacobian_volume_", 3, t, wM, wA, x, nullptr, nullptr, vals, nullptr);
   if (wA != 0.0) launch_facets("dc_k_skeleton_jacobian", t, wA, x, nullptr, nullptr, vals, nullptr);
+}
+
+void DeviceOperator::ensure_gather() {
+  if (!gather_.empty()) return;
+  ensure_csr();
+  const int ncomp = model->ncomp(), nd = grid->nd();
+  gather_.resize(ncomp);
+  for (int c = 0; c < ncomp; ++c) {
+    GatherSet& G = gather_[c];
+    const int ns = model->comp_nspec[c];
+    if (ns == 0 || comp_nelem_[c] == 0 || grid->elem_kind != 0) continue;
+    if (grid->ne * 4 > (int64_t)INT32_MAX) continue;   // (element << 2 | local index) in 32 bits
+    const auto& verts = grid->comp_vertices[c];
+    const int64_t n = (int64_t)verts.size();
+    // longest row of the compartment -> shared-memory slots per thread
+    int maxlen = 0;
+    for (int64_t lv = 0; lv < n; ++lv)
+      for (int i = 0; i < ns; ++i) {
+        const int64_t row = grid->comp_vdof[c][verts[lv]] + i;
+        maxlen = std::max(maxlen, (int)(h_rowptr[row + 1] - h_rowptr[row]));
+      }
+    if ((size_t)maxlen * ns * sizeof(double) * 64 > 200 * 1024) continue;
+    std::vector<int> local(grid->nv, -1);
+    for (int64_t lv = 0; lv < n; ++lv) local[verts[lv]] = (int)lv;
+    std::vector<int> vptr(n + 1, 0);
+    for (int64_t e = 0; e < grid->ne; ++e)
+      if (grid->elem_comp[e] == c)
+        for (int a = 0; a < nd; ++a) vptr[local[grid->elems[e * nd + a]] + 1]++;
+    for (int64_t lv = 0; lv < n; ++lv) vptr[lv + 1] += vptr[lv];
+    std::vector<int> vel(vptr[n]), cur(vptr.begin(), vptr.end() - 1);
+    for (int64_t e = 0; e < grid->ne; ++e)
+      if (grid->elem_comp[e] == c)
+        for (int a = 0; a < nd; ++a) vel[cur[local[grid->elems[e * nd + a]]]++] = (int)(e << 2 | a);
+    if (n != grid->nv) G.verts.upload(std::vector<int>(verts.begin(), verts.end()), stream);
+    G.vptr.upload(vptr, stream);
+    G.vel.upload(vel, stream);
+    G.nverts = n;
+    G.maxlen = maxlen;
+    G.usable = true;
+    DCB_CUDA(cudaStreamSynchronize(stream));
+  }
 }
 
 void DeviceOperator::ensure_csr() {

@@ -145,6 +145,17 @@ class DeviceOperator {
   int64_t nnz_ = 0;
   int64_t ne_patch_total_ = 0;
   size_t patch_smem(const PatchSet& P, int ns, int mode) const;
+  // gather form of the CSR fill (kernels/assembly_element.cuh): vertices of a compartment and the
+  // elements around them, built with the pattern on first use
+  struct GatherSet {
+    DeviceBuffer<int> verts, vptr, vel;
+    int64_t nverts = 0;
+    int maxlen = 0;        // longest CSR row of the compartment
+    bool usable = false;
+  };
+  std::vector<GatherSet> gather_;
+  std::string csr_fill_ = "scatter";
+  void ensure_gather();
   int struct_comp_ = -1;   // compartment handled by the structured kernels
   int struct_part_ = 0;    // cell range selector of the next structured launch (jacobian_apply)
   int patch_pn_ = 256, patch_pe_ = 512, patch_threads_ = 256, patch_smem_kb_ = 64;

@@ -19,6 +19,12 @@
  *   orc_jacobian_skeleton    local_operator.hh:973-1199, :1354-1396, :1417-1452
  *   quadrature / basis       dune-geometry simplex rules of order 2, dune-localfunctions P1
  *                            (third party, values as listed in SURVEY.md App. A.3)
+ *   etype 1 (Q1 cubes)       NOT a reference element (PkLocalFiniteElementMap is simplex-only,
+ *                            model_single_compartment_traits.hh:23-24): the same loops with the
+ *                            multilinear basis and the 2-point Gauss rule per axis, for BASELINE
+ *                            configs[3]'s "Q1"; pinned by closed-form element matrices and the
+ *                            gauss / poisson KATs (tests/test_q1_oracle.py), parity unpinned by
+ *                            construction (nothing in the reference to compare with)
  *   orc_bicgstab / orc_cg    dune-istl BiCGSTABSolver / CGSolver operation order (third party,
  *                            SURVEY.md App. C.1), built by dune/copasi/solver/istl/factory/iterative.hh:36-73
  *   preconditioners          dune-istl SeqJac; dune/copasi/solver/istl/block_jacobi.hh:46-128

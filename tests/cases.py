@@ -303,6 +303,58 @@ time_end = 1
 """ + SOLVER
 
 
+# BASELINE config 5 names 10 species: the cell model above with four more (a second extracellular
+# messenger, a fourth cytosolic species, two more nuclear ones), cross-diffusion between them and a
+# second transmission condition cytosol <-> nucleus.  2 + 4 + 4 species in the three compartments.
+CELL10 = CELL.replace("[model.time_step_operator]\ntime_end = 1\n", """
+[model.scalar_field.e2]
+compartment = ecs
+storage.expression = 1
+cross_diffusion.e2.expression = 0.015
+cross_diffusion.e1.expression = 0.001
+reaction.expression = k2*e1 - 0.1*e2
+reaction.jacobian.e1.expression = k2
+reaction.jacobian.e2.expression = -0.1
+initial.expression = 0.2
+[model.scalar_field.c4]
+compartment = cytosol
+storage.expression = 1
+cross_diffusion.c4.expression = 0.008
+cross_diffusion.c1.expression = 0.001
+reaction.expression = 0.2*c3 - 0.3*c4*c1
+reaction.jacobian.c3.expression = 0.2
+reaction.jacobian.c4.expression = -0.3*c1
+reaction.jacobian.c1.expression = -0.3*c4
+initial.expression = 0.05 + 0.05*position_x
+outflow.nucleus.expression = 0.1*(c4 - n3)
+outflow.nucleus.jacobian.c4.expression = 0.1
+outflow.nucleus.jacobian.n3.expression = -0.1
+[model.scalar_field.n3]
+compartment = nucleus
+storage.expression = 1
+cross_diffusion.n3.expression = 0.01
+reaction.expression = -0.02*n3 + 0.01*n1
+reaction.jacobian.n3.expression = -0.02
+reaction.jacobian.n1.expression = 0.01
+initial.expression = 0.02
+outflow.cytosol.expression = 0.1*(n3 - c4)
+outflow.cytosol.jacobian.n3.expression = 0.1
+outflow.cytosol.jacobian.c4.expression = -0.1
+[model.scalar_field.n4]
+compartment = nucleus
+storage.expression = 1
+cross_diffusion.n4.expression = 0.005
+cross_diffusion.n3.expression = 0.002
+reaction.expression = 0.02*n3*n4 - 0.01*n4
+reaction.jacobian.n3.expression = 0.02*n4
+reaction.jacobian.n4.expression = 0.02*n3 - 0.01
+initial.expression = 0.1
+[model.time_step_operator]
+time_end = 1
+""")
+assert CELL10 != CELL
+
+
 # Synthetic: every volume term of local_operator.hh:417-707 the inis above do not reach -- advection
 # (velocity.{x,y,z} with a jacobian), tensor diffusion, solution dependent diffusion with its
 # jacobian entries (scalar and tensor), a storage coefficient with a jacobian.
@@ -469,6 +521,7 @@ CASES = {
     "mitchell_schaefer": Case("mitchell_schaefer", MITCHELL_SCHAEFER + REDUCE["mitchell_schaefer"], 2, _s(2, 16), dt=0.01, structured=([16, 16], [0, 0], [1, 1])),
     "two_disks": Case("two_disks", TWO_DISKS + REDUCE["two_disks"], 2, lambda: OMESH.two_disks(6, 6, 32), dt=1.0),
     "cell3d": Case("cell3d", CELL + REDUCE["cell3d"], 3, _s(3, 8), dt=0.05, structured=([8, 8, 8], [0, 0, 0], [1, 1, 1])),
+    "cell3d_10": Case("cell3d_10", CELL10, 3, _s(3, 6), dt=0.05, structured=([6, 6, 6], [0, 0, 0], [1, 1, 1])),
     "advection2d": Case("advection2d", ADVECTION, 2, _s(2, 12), dt=0.05, structured=([12, 12], [0, 0], [1, 1])),
     "advection3d": Case("advection3d", ADVECTION, 3, _s(3, 5), dt=0.05, structured=([5, 5, 5], [0, 0, 0], [1, 1, 1])),
 }

@@ -54,9 +54,12 @@ def test_residual(name, scheme):
     assert rel(got, ref) <= OP_TOL
 
 
+@pytest.mark.parametrize("fill", ["gather", "scatter"])
 @pytest.mark.parametrize("name", ALL)
-def test_jacobian_csr(name):
-    case, om, cfg, model, grid, op = make(name)
+def test_jacobian_csr(name, fill):
+    """CSR values by the gather form (one thread per vertex, rows accumulated in shared memory, no
+    atomics; falls back to scatter for FD / extended Jacobians) and by the element scatter form."""
+    case, om, cfg, model, grid, op = make(name, **{"model.assembly.b200.csr_fill": fill})
     x = K.rand_state(om.ndofs, 3)
     t = case.t0 + 0.1
     rp, ci = om.pattern()
