@@ -190,7 +190,7 @@ __device__ __forceinline__ void dc_q1_cell(const DcStructArgs& a, const int* idx
     if (M::HAS_DIFF) {
 #pragma unroll
       for (int j = 0; j < NS; ++j)
-        if (M::pair(i, j)) dq_stiffness(MODE == 0 ? U[j] : Z[j], g.wk, jd[i][j], acc[i]);
+        if (M::dpair(i, j)) dq_stiffness(MODE == 0 ? U[j] : Z[j], g.wk, jd[i][j], acc[i]);
     }
   }
 #pragma unroll

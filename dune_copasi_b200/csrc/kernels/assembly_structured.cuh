@@ -70,14 +70,21 @@ __device__ __forceinline__ void dc_struct_cell(const DcStructArgs& a, const int*
   for (int k = 0; k < DC_DIM; ++k) x0[k] = a.origin[k] + idx[k] * a.h[k];
 
   // ---- mass / reaction part, simplex by simplex
+  double TT[MODE <= 1 ? DC_NPERM : 1][NS];   // sum over the points of simplex p (residual / apply)
 #pragma unroll
   for (int p = 0; p < DC_NPERM; ++p) {
     double xl[NS][DC_ND], BS[NS], gu[NS][DC_DIM];
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-      double t = 0.0;
 #pragma unroll
-      for (int k = 0; k < DC_ND; ++k) { xl[s][k] = U[dc_corner(p, k)][s]; t += xl[s][k]; }
+      for (int k = 0; k < DC_ND; ++k) xl[s][k] = U[dc_corner(p, k)][s];
+      // every Kuhn simplex runs from corner 0 to corner 2^d - 1: that pair is summed once per cell
+      double t = U[0][s] + U[DC_NCORN - 1][s];
+#if DC_DIM == 3
+      t += xl[s][1] + xl[s][2];
+#else
+      t += xl[s][1];
+#endif
       BS[s] = DC_PB * t;
 #pragma unroll
       for (int k = 0; k < DC_DIM; ++k) gu[s][dc_perm(p, k)] = (xl[s][k + 1] - xl[s][k]) * rh[dc_perm(p, k)];
@@ -114,18 +121,19 @@ __device__ __forceinline__ void dc_struct_cell(const DcStructArgs& a, const int*
         }
       }
 #pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        const double bt = Bf * T[s];
-#pragma unroll
-        for (int k = 0; k < DC_ND; ++k) acc[dc_corner(p, k)][s] += bt;
-      }
+      for (int s = 0; s < NS; ++s) TT[p][s] = T[s];
     } else if (MODE == 1) {
       double zl[NS][DC_ND], BZ[NS], T[NS];
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
-        double t = 0.0;
 #pragma unroll
-        for (int k = 0; k < DC_ND; ++k) { zl[s][k] = Z[dc_corner(p, k)][s]; t += zl[s][k]; }
+        for (int k = 0; k < DC_ND; ++k) zl[s][k] = Z[dc_corner(p, k)][s];
+        double t = Z[0][s] + Z[DC_NCORN - 1][s];
+#if DC_DIM == 3
+        t += zl[s][1] + zl[s][2];
+#else
+        t += zl[s][1];
+#endif
         BZ[s] = DC_PB * t;
         T[s] = 0.0;
       }
@@ -150,11 +158,7 @@ __device__ __forceinline__ void dc_struct_cell(const DcStructArgs& a, const int*
         }
       }
 #pragma unroll
-      for (int i = 0; i < NS; ++i) {
-        const double bt = Bf * T[i];
-#pragma unroll
-        for (int k = 0; k < DC_ND; ++k) acc[dc_corner(p, k)][i] += bt;
-      }
+      for (int i = 0; i < NS; ++i) TT[p][i] = T[i];
     } else {
       double JS[NS][NS], JV[DC_ND][NS][NS];
 #pragma unroll
@@ -185,6 +189,25 @@ __device__ __forceinline__ void dc_struct_cell(const DcStructArgs& a, const int*
     }
   }
 
+  // the B * (sum over the points) part of every simplex goes to its d+1 corners: summed per corner
+  // first (corner 0 and the last corner see all simplices -- the same sum --, the others d!/ (d+1 choose ..) of them)
+  if (MODE <= 1) {
+#pragma unroll
+    for (int m = 0; m < DC_NCORN; ++m)
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        double t = 0.0;
+#pragma unroll
+        for (int p = 0; p < DC_NPERM; ++p) {
+          bool has = false;
+#pragma unroll
+          for (int k = 0; k < DC_ND; ++k) has |= dc_corner(p, k) == m;
+          if (has) t += TT[p][s];
+        }
+        acc[m][s] += Bf * t;
+      }
+  }
+
   // ---- diffusion part, lattice edge by lattice edge
   if (M::HAS_DIFF) {
     double u0[NS], g0[NS][DC_DIM], jd[NS][NS];
@@ -197,35 +220,50 @@ __device__ __forceinline__ void dc_struct_cell(const DcStructArgs& a, const int*
 #pragma unroll
     for (int k = 0; k < DC_DIM; ++k) c.pos[k] = x0[k] + 0.5 * a.h[k];
     M::jac_diff(c, u0, g0, a.wA, jd);   // jd[i][j] = wA * D_ij (point independent)
+    double cw[DC_DIM], jdw[NS][NS][DC_DIM];   // |simplex| / h_k^2 and the coefficients times it
+#pragma unroll
+    for (int k = 0; k < DC_DIM; ++k) {
+      cw[k] = vol * rh[k] * rh[k];
+#pragma unroll
+      for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int j = 0; j < NS; ++j) jdw[i][j][k] = jd[i][j] * cw[k];
+    }
 #pragma unroll
     for (int m = 0; m < DC_NCORN; ++m)
 #pragma unroll
       for (int k = 0; k < DC_DIM; ++k) {
         if ((m >> k) & 1) continue;
         const int m2 = m | (1 << k);
-        const double wgt = dc_edge_paths(m) * vol * rh[k] * rh[k];
+        const double wgt = dc_edge_paths(m) * cw[k];
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
           if (MODE == 2) {
 #pragma unroll
             for (int j = 0; j < NS; ++j)
-              if (M::pair(i, j)) {
+              if (M::dpair(i, j)) {
                 acc[m][i * NS + j] += wgt * jd[i][j];
                 acc[m2][i * NS + j] += wgt * jd[i][j];
               }
           } else if (MODE == 3) {
-            if (M::pair(i, i)) {
+            if (M::dpair(i, i)) {
               acc[m][i] += wgt * jd[i][i];
               acc[m2][i] += wgt * jd[i][i];
             }
           } else {
+            // only the couplings the model writes (dpair); the edge weight is folded into the coefficient
             double d = 0.0;
+            bool any = false;
 #pragma unroll
             for (int j = 0; j < NS; ++j)
-              if (M::pair(i, j)) d += jd[i][j] * (MODE == 0 ? (U[m2][j] - U[m][j]) : (Z[m2][j] - Z[m][j]));
-            d *= wgt;
-            acc[m2][i] += d;
-            acc[m][i] -= d;
+              if (M::dpair(i, j)) {
+                d += (dc_edge_paths(m) * jdw[i][j][k]) * (MODE == 0 ? (U[m2][j] - U[m][j]) : (Z[m2][j] - Z[m][j]));
+                any = true;
+              }
+            if (any) {
+              acc[m2][i] += d;
+              acc[m][i] -= d;
+            }
           }
         }
       }

@@ -323,6 +323,19 @@ std::string Model::cuda_source() const {
       for (size_t w = 0; w < words.size(); ++w) o << words[w] << "ull" << (w + 1 < words.size() ? "," : "");
       o << "};\n    return (m[(i * NS + j) >> 6] >> ((i * NS + j) & 63)) & 1ull;\n  }\n";
     }
+    // diffusion mask (which D_ij are written in the ini): lets the kernels skip the zero couplings
+    {
+      int n = std::max(ns, 1);
+      std::vector<unsigned long long> words((n * n + 63) / 64, 0ull);
+      for (auto& t : terms)
+        if ((t.kind == Term::Diff || t.kind == Term::DiffT) && species[t.i].comp == c && species[t.j].comp == c) {
+          int i = species[t.i].local, j = species[t.j].local;
+          words[(i * n + j) >> 6] |= 1ull << ((i * n + j) & 63);
+        }
+      o << "  __host__ __device__ static constexpr bool dpair(int i, int j) {\n    const unsigned long long m[" << words.size() << "] = {";
+      for (size_t w = 0; w < words.size(); ++w) o << words[w] << "ull" << (w + 1 < words.size() ? "," : "");
+      o << "};\n    return (m[(i * NS + j) >> 6] >> ((i * NS + j) & 63)) & 1ull;\n  }\n";
+    }
     // ---- scalar part of the residual at a point
     o << "  // sc[i] = wA*(-R_i) + wM*(u_i*storage_i)   (local_operator.hh:479-480)\n";
     o << "  __device__ __forceinline__ static void scalar(const DcCtx& c, const double* u, const double (*g)[DC_DIM], double wM, double wA, double* sc) {\n";
