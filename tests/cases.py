@@ -216,6 +216,65 @@ time_step_max = 1
 time_end = 1
 """ + SOLVER
 
+# test/two_disks_cell_data.ini: the two-disks problem twice -- (u_in, u_out) with a diffusion coefficient
+# read from per-cell grid data (`sigma`, "sigma := position_x" in the reference's comment; its data
+# file is a git-LFS pointer, so sigma is generated here as the cell centre's x), (v_in, v_out) with the
+# analytic 1 + position_x^2 -- and a reduce functional comparing the two.
+TWO_DISKS_CELL_DATA = """
+[parser_context]
+phi.type = constant
+phi.value = 1
+[compartments]
+outer.expression = (gmsh_id == 1)
+inner.expression = (gmsh_id == 2)
+[model.scalar_field.u_in]
+compartment = inner
+cross_diffusion.u_in.expression = (gmsh_id == 2) ? 1 : 0
+outflow.outer.expression = phi*(u_in - u_out)
+outflow.outer.jacobian.u_in.expression = phi
+outflow.outer.jacobian.u_out.expression = -phi
+[model.scalar_field.u_out]
+compartment = outer
+cross_diffusion.u_out.expression = 1 + sigma^2
+storage.expression = 0
+constrain.boundary.expression = position_x
+outflow.inner.expression = phi*(u_out - u_in)
+outflow.inner.jacobian.u_out.expression = phi
+outflow.inner.jacobian.u_in.expression = -phi
+[model.scalar_field.v_in]
+compartment = inner
+cross_diffusion.v_in.expression = 1
+outflow.outer.expression = phi*(v_in - v_out)
+outflow.outer.jacobian.v_in.expression = phi
+outflow.outer.jacobian.v_out.expression = -phi
+[model.scalar_field.v_out]
+compartment = outer
+cross_diffusion.v_out.expression = 1 + position_x^2
+storage.expression = 0
+constrain.boundary.expression = position_x
+outflow.inner.expression = phi*(v_out - v_in)
+outflow.inner.jacobian.v_out.expression = phi
+outflow.inner.jacobian.v_in.expression = -phi
+[model]
+is_linear = true
+parser_type = ExprTk
+[model.time_step_operator]
+time_step_max = 1
+time_end = 1
+[model.reduce]
+u_error.evaluation.expression = ((u_in - v_in)^2 + (u_out - v_out)^2) * integration_factor
+u_error.transformation.expression = arg: sqrt(arg)
+""" + SOLVER
+
+
+def two_disks_with_sigma():
+    m = OMESH.two_disks(6, 6, 32)
+    sigma = m.coords[m.elems][:, :, 0].mean(axis=1)
+    m.cell_keys = ["gmsh_id", "sigma"]
+    m.cell_data = np.ascontiguousarray(np.stack([m.cell_data[0], sigma]))
+    return m
+
+
 # BASELINE config 5 in miniature: cytosol / nucleus / extracellular space as nested regions of a
 # structured tet mesh, several species per compartment, constant cross-diffusion, non-linear
 # reactions, membrane fluxes between touching compartments and an outflow boundary condition.
@@ -520,6 +579,7 @@ CASES = {
     "grayscott3d": Case("grayscott3d", GRAY_SCOTT, 3, _s(3, 10), dt=1.0, structured=([10, 10, 10], [0, 0, 0], [1, 1, 1])),
     "mitchell_schaefer": Case("mitchell_schaefer", MITCHELL_SCHAEFER + REDUCE["mitchell_schaefer"], 2, _s(2, 16), dt=0.01, structured=([16, 16], [0, 0], [1, 1])),
     "two_disks": Case("two_disks", TWO_DISKS + REDUCE["two_disks"], 2, lambda: OMESH.two_disks(6, 6, 32), dt=1.0),
+    "two_disks_cell_data": Case("two_disks_cell_data", TWO_DISKS_CELL_DATA, 2, two_disks_with_sigma, dt=1.0),
     "cell3d": Case("cell3d", CELL + REDUCE["cell3d"], 3, _s(3, 8), dt=0.05, structured=([8, 8, 8], [0, 0, 0], [1, 1, 1])),
     "cell3d_10": Case("cell3d_10", CELL10, 3, _s(3, 6), dt=0.05, structured=([6, 6, 6], [0, 0, 0], [1, 1, 1])),
     "advection2d": Case("advection2d", ADVECTION, 2, _s(2, 12), dt=0.05, structured=([12, 12], [0, 0], [1, 1])),

@@ -66,3 +66,32 @@ def test_library_does_not_link_the_oracle():
             if f.endswith((".py", ".cpp", ".hpp", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dp, f), errors="ignore").read()
                 assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
+
+
+def _build_c_host(tmp_path):
+    """tests/c_host/host_check.c: a plain C99 program on the C ABI (no Python, no torch)."""
+    exe = str(tmp_path / "host_check")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_host", "host_check.c"), "-o", exe,
+                           "-L", os.path.dirname(LIB), "-ldune_copasi_b200", "-Wl,-rpath," + os.path.dirname(LIB)])
+    return exe
+
+
+def test_header_is_c99_and_a_c_host_runs(tmp_path):
+    import dune_copasi_b200 as D
+    exe = _build_c_host(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    f = out.stdout.split()
+    # 5 x 4 x 3 vertices, 2 species: 120 rows; 15-point (Kuhn P1) and 27-point (Q1) stencils
+    assert f[0] == "ok" and f[1] == "120" and f[3] == "120" and int(f[2]) < int(f[4])
+    if D.lib().dcb_device_count() < 1:
+        assert f[5] == "nodevice"         # no silent CPU fallback behind the C ABI either
+
+
+@pytest.mark.gpu
+def test_c_host_computes_on_the_device(tmp_path):
+    exe = _build_c_host(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.split()[0] == "ok" and float(out.stdout.split()[5]) > 0

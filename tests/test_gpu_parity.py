@@ -263,7 +263,8 @@ STEP_CASES = [("gauss2d", "Alexander2", 2), ("gauss3d", "ImplicitEuler", 2), ("e
               ("grayscott2d", "ExplicitEuler", 2), ("grayscott2d", "Heun", 2), ("grayscott2d", "Shu3", 2),
               ("grayscott2d", "RungeKutta4", 2), ("mitchell_schaefer", "Alexander3", 2),
               ("grayscott2d", "FractionalStepTheta", 2), ("advection2d", "Alexander2", 2),
-              ("advection3d", "ImplicitEuler", 2)]
+              ("advection3d", "ImplicitEuler", 2), ("two_disks_cell_data", "Alexander2", 1),
+              ("cell3d_10", "ImplicitEuler", 1)]
 
 
 @pytest.mark.parametrize("matrix_free", [False, True])
@@ -330,7 +331,8 @@ def test_numerical_jacobian(name):
         assert rel(st.get_state()[0], u) <= 1e-8
 
 
-@pytest.mark.parametrize("name", ["gauss2d", "gauss3d", "exp", "poisson", "two_disks", "mitchell_schaefer", "cell3d"])
+@pytest.mark.parametrize("name", ["gauss2d", "gauss3d", "exp", "poisson", "two_disks", "mitchell_schaefer", "cell3d",
+                                  "two_disks_cell_data"])
 def test_reduce_matches_oracle(name):
     """[model.reduce] functionals (reduce.hh:38-285) on the device: sums to rounding, max / min
     exactly (same quadrature points), warn / error statuses as the oracle."""

@@ -332,3 +332,25 @@ f.expression = s, t: a*s + t^2
     c = np.zeros((1, sym.nslots))
     c[0, sym.table["u"]] = 4.0
     assert ORC.eval_program(code, consts, c)[0] == 2.5 * 4 + 9 + 2.5
+
+
+def test_two_disks_cell_data_kat():
+    """test/two_disks_cell_data.ini:70-74: the solution with the diffusion coefficient read from
+    per-cell grid data (sigma = x of the cell centre) agrees with the one using the analytic
+    1 + position_x^2, and the difference shrinks under refinement (the reference warns above 1e-7 with
+    its own data file, a git-LFS pointer here)."""
+    errs = []
+    for nr, nt in ((6, 32), (12, 64)):
+        def mesh(nr=nr, nt=nt):
+            m = OMESH.two_disks(nr, nr, nt)
+            sigma = m.coords[m.elems][:, :, 0].mean(axis=1)
+            m.cell_keys = ["gmsh_id", "sigma"]
+            m.cell_data = np.ascontiguousarray(np.stack([m.cell_data[0], sigma]))
+            return m
+        om = K.Case("tdc", K.TWO_DISKS_CELL_DATA, 2, mesh, dt=1.0).oracle()
+        S = ORC.StepOperator(om)
+        u, ok = S.apply(om.initial(0.0), 0.0, 1.0)
+        assert ok
+        vals, status = ORC.reduce(om, u, 1.0)
+        errs.append(vals["u_error"])
+    assert errs[0] < 2e-3 and errs[1] < 0.4 * errs[0]
