@@ -387,9 +387,10 @@ def main():
 
     line = measure(args)
     # BASELINE configs[3] words the lattice as "Q1": the same run on the cells as Q1 elements rides along
-    # (the headline stays on the reference's own element, P1 on the Kuhn split -- SURVEY.md F3)
+    # (the headline stays on the reference's own element, P1 on the Kuhn split -- SURVEY.md F3); single-GPU
+    # runs only: under torchrun use --element q1 for the Q1 numbers
     q1 = None
-    if args.element == "p1" and args.dim == 3 and args.workload == "grayscott" and not args.no_q1:
+    if args.element == "p1" and args.dim == 3 and args.workload == "grayscott" and not args.no_q1 and world == 1:
         qargs = argparse.Namespace(**vars(args))
         qargs.element = "q1"
         q1 = measure(qargs)

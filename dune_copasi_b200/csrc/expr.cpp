@@ -498,4 +498,138 @@ static std::string cond_text(const NodeP& a, const std::function<std::string(con
   (void)is_cmp;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// symbolic differentiation
+namespace {
+NodeP mk_call(const std::string& name, std::vector<NodeP> kids) {
+  auto n = std::make_shared<Node>();
+  n->op = Op::Call;
+  n->name = name;
+  n->kids = std::move(kids);
+  return fold(n);
+}
+bool is_num(const NodeP& a, double v) { return a->op == Op::Num && a->num == v; }
+// constructors with the algebraic identities that keep derived trees small
+NodeP s_neg(const NodeP& a) {
+  if (a->op == Op::Num) return mk_num(-a->num);
+  if (a->op == Op::Neg) return a->kids[0];
+  return mk(Op::Neg, {a});
+}
+NodeP s_add(const NodeP& a, const NodeP& b) {
+  if (is_num(a, 0.0)) return b;
+  if (is_num(b, 0.0)) return a;
+  return fold(mk(Op::Add, {a, b}));
+}
+NodeP s_sub(const NodeP& a, const NodeP& b) {
+  if (is_num(b, 0.0)) return a;
+  if (is_num(a, 0.0)) return s_neg(b);
+  return fold(mk(Op::Sub, {a, b}));
+}
+NodeP s_mul(const NodeP& a, const NodeP& b) {
+  if (is_num(a, 0.0) || is_num(b, 0.0)) return mk_num(0.0);
+  if (is_num(a, 1.0)) return b;
+  if (is_num(b, 1.0)) return a;
+  if (is_num(a, -1.0)) return s_neg(b);
+  if (is_num(b, -1.0)) return s_neg(a);
+  return fold(mk(Op::Mul, {a, b}));
+}
+NodeP s_div(const NodeP& a, const NodeP& b) {
+  if (is_num(a, 0.0)) return mk_num(0.0);
+  if (is_num(b, 1.0)) return a;
+  return fold(mk(Op::Div, {a, b}));
+}
+NodeP s_pow(const NodeP& a, const NodeP& b) {
+  if (is_num(b, 0.0)) return mk_num(1.0);
+  if (is_num(b, 1.0)) return a;
+  return fold(mk(Op::Pow, {a, b}));
+}
+NodeP s_sel(const NodeP& c, const NodeP& a, const NodeP& b) {
+  if (is_num(a, 0.0) && is_num(b, 0.0)) return mk_num(0.0);
+  return fold(mk(Op::Sel, {c, a, b}));
+}
+
+NodeP diff(const NodeP& a, const std::string& var) {
+  switch (a->op) {
+    case Op::Num: return mk_num(0.0);
+    case Op::Var: return mk_num(a->name == var ? 1.0 : 0.0);
+    case Op::Neg: return s_neg(diff(a->kids[0], var));
+    case Op::Add: return s_add(diff(a->kids[0], var), diff(a->kids[1], var));
+    case Op::Sub: return s_sub(diff(a->kids[0], var), diff(a->kids[1], var));
+    case Op::Mul:
+      return s_add(s_mul(diff(a->kids[0], var), a->kids[1]), s_mul(a->kids[0], diff(a->kids[1], var)));
+    case Op::Div: {
+      const NodeP &f = a->kids[0], &g = a->kids[1];
+      NodeP df = diff(f, var), dg = diff(g, var);
+      // f'/g - f g'/g^2
+      return s_sub(s_div(df, g), s_div(s_mul(f, dg), s_mul(g, g)));
+    }
+    case Op::Pow: {
+      const NodeP &f = a->kids[0], &g = a->kids[1];
+      NodeP df = diff(f, var), dg = diff(g, var);
+      double c;
+      if (is_constant(g, &c)) return s_mul(s_mul(mk_num(c), s_pow(f, mk_num(c - 1.0))), df);
+      // f^g (g' log f + g f'/f)
+      return s_mul(a, s_add(s_mul(dg, mk_call("log", {f})), s_div(s_mul(g, df), f)));
+    }
+    case Op::Mod: return diff(a->kids[0], var);   // almost everywhere, for a constant modulus
+    case Op::Not: case Op::Lt: case Op::Gt: case Op::Le: case Op::Ge: case Op::Eq: case Op::Ne:
+    case Op::And: case Op::Or:
+      return mk_num(0.0);
+    case Op::Sel: return s_sel(a->kids[0], diff(a->kids[1], var), diff(a->kids[2], var));
+    case Op::Call: {
+      const std::string& f = a->name;
+      if (a->kids.size() == 1) {
+        const NodeP& x = a->kids[0];
+        NodeP dx = diff(x, var);
+        if (is_num(dx, 0.0)) return dx;
+        if (f == "sqrt") return s_div(dx, s_mul(mk_num(2.0), a));
+        if (f == "exp") return s_mul(a, dx);
+        if (f == "log" || f == "ln") return s_div(dx, x);
+        if (f == "log10") return s_div(dx, s_mul(x, mk_num(std::log(10.0))));
+        if (f == "log2") return s_div(dx, s_mul(x, mk_num(std::log(2.0))));
+        if (f == "exp2") return s_mul(s_mul(a, mk_num(std::log(2.0))), dx);
+        if (f == "sin") return s_mul(mk_call("cos", {x}), dx);
+        if (f == "cos") return s_neg(s_mul(mk_call("sin", {x}), dx));
+        if (f == "tan") { NodeP c = mk_call("cos", {x}); return s_div(dx, s_mul(c, c)); }
+        if (f == "tanh") return s_mul(s_sub(mk_num(1.0), s_mul(a, a)), dx);
+        if (f == "sinh") return s_mul(mk_call("cosh", {x}), dx);
+        if (f == "cosh") return s_mul(mk_call("sinh", {x}), dx);
+        if (f == "asin") return s_div(dx, mk_call("sqrt", {s_sub(mk_num(1.0), s_mul(x, x))}));
+        if (f == "acos") return s_neg(s_div(dx, mk_call("sqrt", {s_sub(mk_num(1.0), s_mul(x, x))})));
+        if (f == "atan") return s_div(dx, s_add(mk_num(1.0), s_mul(x, x)));
+        if (f == "abs") return s_mul(mk_call("sgn", {x}), dx);
+        if (f == "floor" || f == "ceil" || f == "round" || f == "sgn" || f == "sign") return mk_num(0.0);
+      } else if (a->kids.size() == 2) {
+        const NodeP &x = a->kids[0], &y = a->kids[1];
+        if (f == "pow") return diff(mk(Op::Pow, {x, y}), var);
+        if (f == "min") return s_sel(mk(Op::Lt, {x, y}), diff(x, var), diff(y, var));
+        if (f == "max") return s_sel(mk(Op::Gt, {x, y}), diff(x, var), diff(y, var));
+        if (f == "atan2") {   // d atan2(x, y) = (y x' - x y') / (x^2 + y^2)
+          NodeP den = s_add(s_mul(x, x), s_mul(y, y));
+          return s_div(s_sub(s_mul(y, diff(x, var)), s_mul(x, diff(y, var))), den);
+        }
+      } else if (f == "min" || f == "max") {   // n-ary: fold pairwise like the evaluator does
+        NodeP acc = a->kids[0];
+        for (size_t i = 1; i < a->kids.size(); ++i) {
+          auto n = std::make_shared<Node>();
+          n->op = Op::Call; n->name = f; n->kids = {acc, a->kids[i]};
+          acc = n;
+        }
+        return diff(acc, var);
+      }
+      fail("cannot differentiate function '", f, "' with ", a->kids.size(), " argument(s)");
+    }
+  }
+  fail("internal: differentiate");
+}
+}  // namespace
+
+NodeP differentiate(const NodeP& ast, const std::string& var) { return diff(ast, var); }
+bool is_zero(const NodeP& ast) { return ast->op == Op::Num && ast->num == 0.0; }
+
+std::string to_text(const NodeP& ast) {
+  return to_cuda(ast, [](const std::string& name) { return name; });
+}
+
 }  // namespace dcb

@@ -51,6 +51,16 @@ NodeP resolve_expr(const NodeP& ast, const ParserContext& ctx);
 bool is_constant(const NodeP& ast, double* value = nullptr);
 void collect_vars(const NodeP& ast, std::vector<std::string>& out);
 
+// d(ast)/d(var) of a resolved expression, simplified (0 + x, 1 * x, constant folding ...).  Comparisons,
+// logical operators, floor/ceil/round/sgn are piecewise constant: their derivative is 0 and the
+// condition of a selection is kept as it is (derivative of the taken branch).  This is what north_star
+// calls "analytic Jacobians from SymEngine": the reference itself takes its Jacobian entries from the
+// ini (local_equations.hh:553-579); model.jacobian.type = symbolic derives them instead.
+NodeP differentiate(const NodeP& ast, const std::string& var);
+bool is_zero(const NodeP& ast);
+// infix text of a tree (diagnostics, generated-source comments)
+std::string to_text(const NodeP& ast);
+
 // host evaluation; `lookup` maps a variable name to its value (throws for unknown names)
 double eval_expr(const NodeP& ast, const std::function<double(const std::string&)>& lookup);
 

@@ -1,5 +1,7 @@
 #include "model.hpp"
 
+#include <functional>
+
 #include <algorithm>
 #include <cmath>
 #include <set>
@@ -19,9 +21,10 @@ Model::Model(const PTree& cfg_, int dim_, const std::vector<std::string>& keys)
   if (mcfg.get("order", 1) != 1) fail("model.order = ", mcfg.get("order", 1), ": only P1 is built");
   {
     std::string jt = mcfg.get("jacobian.type", std::string("analytical"));
-    if (jt != "analytical" && jt != "numerical")
-      fail("The option 'model.jacobian.type' must be either 'analytical' or 'numerical'");
+    if (jt != "analytical" && jt != "numerical" && jt != "symbolic")
+      fail("The option 'model.jacobian.type' must be either 'analytical' or 'numerical' (or the extension 'symbolic')");
     numerical_jacobian = jt == "numerical" && !is_linear;
+    symbolic_jacobian = jt == "symbolic";
     fd_epsilon = mcfg.get("jacobian.epsilon", 1e-7);
   }
   const PTree& comps = cfg.sub("compartments");
@@ -69,14 +72,38 @@ Model::Model(const PTree& cfg_, int dim_, const std::vector<std::string>& keys)
     terms.push_back(t);
     return true;
   };
+  // symbolic mode: d(term)/d(species k) for every species k of the given compartments, kept when it
+  // is not identically zero
+  auto derive = [&](Term::Kind jkind, const Term& fn, std::vector<int> comps,
+                    const std::function<void(Term&, int)>& place) {
+    std::sort(comps.begin(), comps.end());
+    comps.erase(std::unique(comps.begin(), comps.end()), comps.end());
+    for (int c : comps)
+      for (int k = comp_first[c]; k < comp_first[c] + comp_nspec[c]; ++k) {
+        NodeP d = differentiate(fn.ast, species[k].name);
+        if (is_zero(d)) continue;
+        Term t;
+        t.kind = jkind; t.i = fn.i; t.ast = d;
+        t.text = to_text(d);
+        place(t, k);
+        terms.push_back(t);
+      }
+  };
   for (int g = 0; g < nspec(); ++g) {
     const PTree& f = *scfg[g];
+    const int cg = species[g].comp;
     {
       // velocity.<axis>.expression, velocity.jacobian.<wrt>.<axis>.expression (local_equations.hh:663-669)
       const PTree& v = f.sub("velocity");
       bool active = false;
       for (int a = 0; a < dim; ++a) active |= add(Term::Vel, g, a, -1, v.sub(kAxis[a]).get("expression", std::string()));
-      if (active)
+      if (active && symbolic_jacobian) {
+        std::vector<Term> fns;
+        for (auto& t : terms)
+          if (t.kind == Term::Vel && t.i == g) fns.push_back(t);
+        for (auto& fn : fns)
+          derive(Term::VelJac, fn, {cg}, [&](Term& t, int k) { t.j = k; t.k = fn.j; });
+      } else if (active)
         for (auto& wrt : v.sub("jacobian").sub_keys()) {
           int k = species_index(wrt);
           if (k < 0) continue;
@@ -88,7 +115,11 @@ Model::Model(const PTree& cfg_, int dim_, const std::vector<std::string>& keys)
         {Term::Reaction, Term::ReactionJac, "reaction"}, {Term::Storage, Term::StorageJac, "storage"}};
     for (auto& tk : two) {
       const PTree& t = f.sub(tk.key);
-      if (add(tk.k, g, -1, -1, t.get("expression", std::string())))
+      if (!add(tk.k, g, -1, -1, t.get("expression", std::string()))) continue;
+      if (symbolic_jacobian) {
+        const Term fn = terms.back();
+        derive(tk.jk, fn, {cg}, [&](Term& d, int k) { d.j = k; d.k = -1; });
+      } else
         for (auto& wrt : t.sub("jacobian").sub_keys()) {
           int j = species_index(wrt);
           if (j >= 0) add(tk.jk, g, j, -1, t.sub("jacobian").sub(wrt).get("expression", std::string()));
@@ -113,7 +144,16 @@ Model::Model(const PTree& cfg_, int dim_, const std::vector<std::string>& keys)
           }
         return active;
       };
-      if (diffusion(d, Term::Diff, Term::DiffT, -1))
+      const size_t first_new = terms.size();
+      const bool have = diffusion(d, Term::Diff, Term::DiffT, -1);
+      if (have && symbolic_jacobian) {
+        std::vector<Term> fns(terms.begin() + first_new, terms.end());
+        for (auto& fn : fns)
+          derive(fn.kind == Term::Diff ? Term::DiffJac : Term::DiffTJac, fn, {cg}, [&](Term& t, int k) {
+            t.j = fn.j;
+            t.k = fn.kind == Term::Diff ? k : fn.k + 9 * k;
+          });
+      } else if (have)
         for (auto& kk : d.sub("jacobian").sub_keys()) {
           int k = species_index(kk);
           if (k >= 0) diffusion(d.sub("jacobian").sub(kk), Term::DiffJac, Term::DiffTJac, k);
@@ -125,7 +165,11 @@ Model::Model(const PTree& cfg_, int dim_, const std::vector<std::string>& keys)
       if (it == comp_names.end()) continue;
       int l = (int)(it - comp_names.begin());
       const PTree& o = of.sub(cname);
-      if (add(Term::Outflow, g, l, -1, o.get("expression", std::string())))
+      if (!add(Term::Outflow, g, l, -1, o.get("expression", std::string()))) continue;
+      if (symbolic_jacobian) {
+        const Term fn = terms.back();
+        derive(Term::OutflowJac, fn, {cg, l}, [&](Term& t, int k) { t.j = l; t.k = k; });
+      } else
         for (auto& kk : o.sub("jacobian").sub_keys()) {
           int k = species_index(kk);
           if (k >= 0) add(Term::OutflowJac, g, l, k, o.sub("jacobian").sub(kk).get("expression", std::string()));

@@ -42,6 +42,11 @@ class Model {
   // (local_operator.hh:193-202, 713-765); linear operators always use the analytic path (:234-235)
   bool numerical_jacobian = false;
   double fd_epsilon = 1e-7;
+  // model.jacobian.type = symbolic (extension; north_star: "analytic Jacobians from SymEngine"): every
+  // jacobian entry is derived from its function by expr.cpp's differentiator, the ini's own
+  // `jacobian.*` sub-sections are not read.  The reference only knows user-supplied entries
+  // (local_equations.hh:553-579).
+  bool symbolic_jacobian = false;
   std::vector<std::string> cell_keys;
   std::vector<std::string> comp_names;
   std::vector<NodeP> comp_expr;

@@ -442,3 +442,30 @@ storage.expression = 1
     S = K.ORC.StepOperator(om)
     u, ok = S.apply(x, 0.0, 0.1)
     assert ok and rel(st.get_state()[0], u) <= FIELD_TOL
+
+
+@pytest.mark.parametrize("name,rk,nsteps", [("grayscott3d", "Alexander2", 2), ("cell3d", "ImplicitEuler", 1),
+                                            ("mitchell_schaefer", "Alexander2", 2), ("advection2d", "ImplicitEuler", 1)])
+def test_symbolic_jacobian_steps_match_oracle(name, rk, nsteps):
+    """model.jacobian.type = symbolic (entries derived by csrc/expr.cpp's differentiator instead of read
+    from the ini): same Jacobian values and same fields as the oracle, which keeps the ini's entries."""
+    import dune_copasi_b200 as D
+    over = {"model.time_step_operator.type": rk, "model.jacobian.type": "symbolic"}
+    case, om, cfg, model, grid, op = make(name, **over)
+    assert not om.numerical
+    x = K.rand_state(om.ndofs, 50)
+    rp, ci = om.pattern()
+    ref = np.zeros(ci.size)
+    om.jacobian(1, case.t0, 1.0, x, rp, ci, ref)
+    om.jacobian(0, case.t0, 0.3 * case.dt, x, rp, ci, ref)
+    assert rel(op.jacobian(case.t0, 1.0, 0.3 * case.dt, x), ref) <= OP_TOL
+    S = K.ORC.StepOperator(om)
+    u = om.initial(case.t0)
+    st = D.Stepper(op, cfg)
+    st.set_state(grid.interpolate(model, case.t0), case.t0)
+    t = case.t0
+    for _ in range(nsteps):
+        u, ok = S.apply(u, t, case.dt)
+        assert ok and st.step(case.dt)
+        t += case.dt
+    assert rel(st.get_state()[0], u) <= FIELD_TOL
