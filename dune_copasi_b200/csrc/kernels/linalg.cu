@@ -492,6 +492,33 @@ void fill(int64_t n, double v, double* y, cudaStream_t s) {
   k_fill<<<grid_for(n, 2), kThreads, 0, s>>>(n, v, y);
   check_launch();
 }
+namespace {
+__global__ void __launch_bounds__(128) k_sor_level(const int32_t* __restrict__ rows, int64_t count,
+                                                   const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                   const double* __restrict__ vals, const double* __restrict__ d,
+                                                   double* v, double relax, bool skip_diag) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const int i = rows[t];
+  double rhs = d[i], diag = 1.0;
+  for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+    const int j = colidx[k];
+    const double a = vals[k];
+    if (j == i) {
+      diag = a;
+      if (skip_diag) continue;
+    }
+    rhs -= a * v[j];
+  }
+  v[i] += relax * (rhs / diag);
+}
+}  // namespace
+void sor_level(const int32_t* rows, int64_t count, const int64_t* rowptr, const int32_t* colidx, const double* vals,
+               const double* d, double* v, double relax, bool skip_diag, cudaStream_t s) {
+  if (count <= 0) return;
+  k_sor_level<<<(unsigned)((count + 127) / 128), 128, 0, s>>>(rows, count, rowptr, colidx, vals, d, v, relax, skip_diag);
+  check_launch();
+}
 void jacobi_apply(int64_t n, const double* dinv, double relax, const double* d, double* v, cudaStream_t s) {
   k_jacobi<<<grid_for(n, 2), kThreads, 0, s>>>(n, dinv, relax, d, v);
   check_launch();

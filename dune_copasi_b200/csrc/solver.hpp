@@ -9,6 +9,7 @@
 // factory/preconditioner.hh:96-113; only the data-parallel subset is built (BiCGSTAB, CG,
 // RestartedGMRes; Richardson, Jacobi, BlockJacobi), anything else fails loudly.
 #pragma once
+#include <vector>
 #include <memory>
 #include <string>
 
@@ -68,6 +69,15 @@ class LinearSolver {
   bool overlap_halo_ = false;
   cudaStream_t halo_stream_ = nullptr;
   cudaEvent_t halo_ev_[2] = {nullptr, nullptr};
+  // SSOR / SOR / GaussSeidel (dune-istl SeqSSOR / SeqSOR / SeqGS; SSOR is the reference's default
+  // preconditioner, solver/istl/factory/preconditioner.hh:17,101-104): level-scheduled sweeps over the
+  // assembled CSR.  level_ptr_[l] .. level_ptr_[l+1] index level_rows_, the rows whose lower
+  // neighbours all sit in earlier levels.
+  bool sor_family() const { return prec_type == "SSOR" || prec_type == "SOR" || prec_type == "GaussSeidel"; }
+  void build_levels();
+  void sor_apply(const double* d, double* v);
+  std::vector<int64_t> level_ptr_;
+  DeviceBuffer<int32_t> level_rows_;
   // linearisation point
   double t_ = 0, wM_ = 0, wA_ = 0;
   const double* x_ = nullptr;

@@ -448,7 +448,7 @@ def linear_solve(rowptr, colidx, vals, b, cfg: dict, rel_tol: float, par=0):
     rhs = b.copy()
     pc = INI.sub(cfg, "preconditioner")
     ptype = pc.get("type", "Jacobi")
-    kind = {"Richardson": 0, "Jacobi": 1, "BlockJacobi": 2}[ptype]
+    kind = {"Richardson": 0, "Jacobi": 1, "BlockJacobi": 2, "SSOR": 3, "SOR": 4, "GaussSeidel": 5}[ptype]
     bs = int(pc.get("block_size", 1))
     relax = float(pc.get("relaxation", 1.0))
     maxit = int(str(INI.get(cfg, "convergence_condition.iteration_range", "1 500")).split()[-1])

@@ -834,7 +834,14 @@ static double dot(int64_t n, const double* a, const double* b, int par) {
 }
 
 /* preconditioner: kind 0 none (Richardson w=1), 1 Jacobi (SeqJac, 1 sweep from v=0: v = w D^-1 d),
- * 2 BlockJacobi with node blocks of size bs (block_jacobi.hh:46-128 with iterations=1: v = w Dblk^-1 d) */
+ * 2 BlockJacobi with node blocks of size bs (block_jacobi.hh:46-128 with iterations=1: v = w Dblk^-1 d),
+ * 3 SSOR, 4 SOR, 5 GaussSeidel = dune-istl SeqSSOR / SeqSOR / SeqGS on scalar entries in the dof order
+ * (registry: solver/istl/factory/preconditioner.hh:101-104; SSOR is DUNE_COPASI_DEFAULT_PRECONDITIONER,
+ * :17).  Third party, restated from dune-istl's gsetc.hh as published:
+ *   bsorf: for rows i ascending   x_i += w (d_i - sum_j a_ij x_j) / a_ii   (current x, diagonal included)
+ *   bsorb: the same for rows descending
+ *   dbgs:  for rows i ascending   x_i += w (d_i - sum_{j != i} a_ij x_j) / a_ii
+ *   SeqSSOR::apply = n x (bsorf; bsorb), SeqSOR::apply = n x bsorf, SeqGS::apply = n x dbgs, v = 0 on entry */
 typedef struct {
   int kind, bs; double relax; double* dinv; int64_t n;
   int iters; const int64_t* rowptr; const int32_t* colidx; const double* vals;   /* sweeps > 1 */
@@ -896,7 +903,29 @@ static void prec_sweep(const Prec* Pc, const double* d, double* v);
  * Jacobi = dune-istl SeqJac: v += w D^-1 (d - A v) with the old iterate in every row.
  * BlockJacobi = block_jacobi.hh:102-127 as written: the right-hand side copy is modified
  * cumulatively, b_k = b_{k-1} - A v_{k-1}, which is the true defect only for the first two sweeps. */
+static void sor_sweep(const Prec* Pc, const double* d, double* v, int backward, int skip_diag) {
+  const int64_t n = Pc->n;
+  for (int64_t q = 0; q < n; ++q) {
+    const int64_t i = backward ? n - 1 - q : q;
+    double rhs = d[i], diag = 1.0;
+    for (int64_t k = Pc->rowptr[i]; k < Pc->rowptr[i + 1]; ++k) {
+      const int64_t j = Pc->colidx[k];
+      if (j == i) { diag = Pc->vals[k]; if (skip_diag) continue; }
+      rhs -= Pc->vals[k] * v[j];
+    }
+    v[i] += Pc->relax * (rhs / diag);
+  }
+}
+
 static void prec_apply(const Prec* Pc, const double* d, double* v) {
+  if (Pc->kind >= 3) {
+    memset(v, 0, sizeof(double) * Pc->n);
+    for (int it = 0; it < Pc->iters; ++it) {
+      sor_sweep(Pc, d, v, 0, Pc->kind == 5);
+      if (Pc->kind == 3) sor_sweep(Pc, d, v, 1, 0);
+    }
+    return;
+  }
   prec_sweep(Pc, d, v);
   if (Pc->iters <= 1 || Pc->kind == 0) return;
   int64_t n = Pc->n;

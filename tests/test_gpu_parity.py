@@ -469,3 +469,69 @@ def test_symbolic_jacobian_steps_match_oracle(name, rk, nsteps):
         assert ok and st.step(case.dt)
         t += case.dt
     assert rel(st.get_state()[0], u) <= FIELD_TOL
+
+
+@pytest.mark.parametrize("solver,prec,sweeps,relax", [("BiCGSTAB", "SSOR", 1, 1.0), ("BiCGSTAB", "SOR", 1, 1.0),
+                                                     ("BiCGSTAB", "GaussSeidel", 2, 1.0), ("CG", "SSOR", 1, 1.0),
+                                                     ("RestartedGMRes", "SSOR", 1, 1.0), ("BiCGSTAB", "SSOR", 2, 0.8),
+                                                     ("RestartedGMRes", "SOR", 1, 1.2)])
+@pytest.mark.parametrize("name", ["grayscott3d", "mitchell_schaefer", "gauss3d", "two_disks"])
+def test_sor_family_matches_oracle(name, solver, prec, sweeps, relax):
+    """SSOR (the reference's default preconditioner, solver/istl/factory/preconditioner.hh:17) / SOR /
+    GaussSeidel as level-scheduled sweeps over the assembled CSR: the same iterates as the oracle's
+    sequential dune-istl sweeps -- identical Krylov iteration counts, solutions to rounding."""
+    import dune_copasi_b200 as D
+    if solver == "CG" and name != "gauss3d":
+        pytest.skip("CG needs the symmetric problem")
+    case, om, cfg, model, grid, op = make(name)
+    x = K.rand_state(om.ndofs, 60)
+    t, wM, wA = case.t0, (0.0 if name == "two_disks" else 1.0), 0.5 * case.dt
+    if name == "two_disks":
+        wA = 1.0
+    lcfg = D.Config(f"type = {solver}\npreconditioner.type = {prec}\npreconditioner.iterations = {sweeps}\n"
+                    f"preconditioner.relaxation = {relax}\nmatrix_free = false\n")
+    sol = D.Solver(op, lcfg)
+    sol.linearize(t, wM, wA, x)
+    b = K.rand_state(om.ndofs, 61, -1.0, 1.0)
+    cd, _ = om.constraints()
+    b[cd] = 0.0
+    z, res = sol.solve(b, 1e-10)
+    S = K.ORC.StepOperator(om)
+    vals = S._stage_jacobian(x, t, wM, wA)
+    zo, ro = K.ORC.linear_solve(S.rowptr, S.colidx, vals, b,
+                                {"type": solver, "preconditioner": {"type": prec, "iterations": sweeps, "relaxation": relax}},
+                                1e-10)
+    assert bool(res.converged) == bool(ro.converged)
+    # long erratic runs may stop an iteration apart by rounding (order of the sums in SpMV / dots)
+    slack = 0 if ro.iterations_x2 < 40 else max(2, ro.iterations_x2 // 8)
+    assert abs(res.half_iterations - ro.iterations_x2) <= slack, (res.half_iterations, ro.iterations_x2)
+    assert rel(z, zo) <= 1e-7
+
+
+def test_reference_mitchell_schaefer_solver_configuration():
+    """test/mitchell_schaefer.ini:76-80 as written: RestartedGMRes with the SSOR preconditioner."""
+    import dune_copasi_b200 as D
+    over = {"model.time_step_operator.type": "Alexander2",
+            "model.time_step_operator.linear_solver.type": "RestartedGMRes",
+            "model.time_step_operator.linear_solver.preconditioner.type": "SSOR",
+            "model.time_step_operator.linear_solver.matrix_free": "false"}
+    case, om, cfg, model, grid, op = make("mitchell_schaefer", **over)
+    S = K.ORC.StepOperator(om)
+    u = om.initial(case.t0)
+    st = D.Stepper(op, cfg)
+    st.set_state(grid.interpolate(model, case.t0), case.t0)
+    t = case.t0
+    for _ in range(2):
+        u, ok = S.apply(u, t, case.dt)
+        assert ok and st.step(case.dt)
+        t += case.dt
+    assert rel(st.get_state()[0], u) <= FIELD_TOL
+
+
+def test_sor_family_needs_the_assembled_matrix():
+    import dune_copasi_b200 as D
+    case, om, cfg, model, grid, op = make("grayscott2d")
+    with pytest.raises(D.DcbError, match="matrix_free = false"):
+        D.Solver(op, D.Config("type = BiCGSTAB\npreconditioner.type = SSOR\nmatrix_free = true\n"))
+    with pytest.raises(D.DcbError, match="not built"):
+        D.Solver(op, D.Config("type = BiCGSTAB\npreconditioner.type = ILU\n"))
