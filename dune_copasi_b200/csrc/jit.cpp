@@ -49,10 +49,15 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
         << "(DcPatchArgs a) { dc_patch_kernel<" << c << ", 2>(a); }\n";
     }
   }
+  // the implicit-geometry kernels serve grids that one compartment covers entirely: models with
+  // species in several compartments never launch them, so they are not generated (compile time)
+  int with_species = 0;
+  for (int c = 0; c < model.ncomp(); ++c) with_species += model.comp_nspec[c] > 0;
+  const bool structured_possible = with_species == 1;
   if (all || group == JitGroup::Structured) {
     o << kStructuredSource << "\n";
     for (int c = 0; c < model.ncomp(); ++c) {
-      if (model.comp_nspec[c] == 0 || !model.diffusion_is_constant(c)) continue;
+      if (!structured_possible || model.comp_nspec[c] == 0 || !model.diffusion_is_constant(c)) continue;
       const char* names[4] = {"residual", "apply", "bdiag", "diag"};
       for (int mode = 0; mode < 4; ++mode)
         o << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, DC_STRUCT_MINB) dc_k_struct_" << names[mode] << "_" << c
@@ -67,7 +72,7 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
     if (!all) o << kStructuredSource << "\n";   // shared drivers (per cell / marching)
     o << kQ1Source << "\n";
     for (int c = 0; c < model.ncomp(); ++c) {
-      if (model.comp_nspec[c] == 0 || !model.diffusion_is_constant(c) || model.has_extended_terms(c)) continue;
+      if (!structured_possible || model.comp_nspec[c] == 0 || !model.diffusion_is_constant(c) || model.has_extended_terms(c)) continue;
       const char* names[5] = {"residual", "apply", "bdiag", "diag", "csr"};
       for (int mode = 0; mode < 5; ++mode)
         o << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, " << (mode == 4 ? "2" : "DC_STRUCT_MINB") << ") dc_k_q1_"

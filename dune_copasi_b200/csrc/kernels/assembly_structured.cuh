@@ -29,10 +29,34 @@ __device__ __forceinline__ constexpr int dc_perm(int p, int t) {
 }
 #endif
 // corner mask of local vertex k of simplex p: axes p_0..p_{k-1} stepped
-__device__ __forceinline__ constexpr int dc_corner(int p, int k) {
+__device__ __forceinline__ constexpr int dc_corner_ref(int p, int k) {
   int m = 0;
   for (int t = 0; t < k; ++t) m |= 1 << dc_perm(p, t);
   return m;
+}
+// the same as a packed table (DC_DIM bits per vertex): the kernels call this several hundred times in
+// fully unrolled loops, and folding the loop form above cost NVRTC minutes per model
+__device__ __forceinline__ constexpr int dc_corner(int p, int k) {
+#if DC_DIM == 2
+  return ((p == 0 ? 0x34 : 0x38) >> (2 * k)) & 3;
+#else
+  return ((p == 0 ? 0xEC8 : p == 1 ? 0xF48 : p == 2 ? 0xED0 : p == 3 ? 0xF90 : p == 4 ? 0xF60 : 0xFA0) >> (3 * k)) & 7;
+#endif
+}
+constexpr bool dc_corner_table_ok() {
+  for (int p = 0; p < DC_NPERM; ++p)
+    for (int k = 0; k <= DC_DIM; ++k)
+      if (dc_corner(p, k) != dc_corner_ref(p, k)) return false;
+  return true;
+}
+static_assert(dc_corner_table_ok(), "packed corner table disagrees with the permutation walk");
+// simplices p that contain corner m, as a bit mask
+__device__ __forceinline__ constexpr int dc_simplices_of(int m) {
+  int mask = 0;
+  for (int p = 0; p < DC_NPERM; ++p)
+    for (int k = 0; k <= DC_DIM; ++k)
+      if (dc_corner(p, k) == m) mask |= 1 << p;
+  return mask;
 }
 // number of Kuhn paths through the lattice edge that leaves corner m: |m|! (d-1-|m|)!
 __device__ __forceinline__ constexpr int dc_edge_paths(int m) {
@@ -43,6 +67,21 @@ __device__ __forceinline__ constexpr int dc_edge_paths(int m) {
   for (int i = 2; i <= DC_DIM - 1 - bits; ++i) b *= i;
   return a * b;
 }
+
+// dc_simplices_of as literals (checked at compile time)
+__device__ __forceinline__ constexpr int dc_simplices_table(int m) {
+#if DC_DIM == 2
+  return m == 0 || m == 3 ? 3 : m == 1 ? 1 : 2;
+#else
+  return m == 0 || m == 7 ? 63 : m == 1 ? 3 : m == 2 ? 12 : m == 4 ? 48 : m == 3 ? 5 : m == 5 ? 18 : 40;
+#endif
+}
+constexpr bool dc_simplices_table_ok() {
+  for (int m = 0; m < DC_NCORN; ++m)
+    if (dc_simplices_table(m) != dc_simplices_of(m)) return false;
+  return true;
+}
+static_assert(dc_simplices_table_ok(), "simplex-of-corner table disagrees with the corner table");
 
 // contributions of one lattice cell: U/Z = corner values [corner][species], acc = corner sums (overwritten)
 template <int C, int MODE>
@@ -198,12 +237,8 @@ __device__ __forceinline__ void dc_struct_cell(const DcStructArgs& a, const int*
       for (int s = 0; s < NS; ++s) {
         double t = 0.0;
 #pragma unroll
-        for (int p = 0; p < DC_NPERM; ++p) {
-          bool has = false;
-#pragma unroll
-          for (int k = 0; k < DC_ND; ++k) has |= dc_corner(p, k) == m;
-          if (has) t += TT[p][s];
-        }
+        for (int p = 0; p < DC_NPERM; ++p)
+          if ((dc_simplices_table(m) >> p) & 1) t += TT[p][s];
         acc[m][s] += Bf * t;
       }
   }

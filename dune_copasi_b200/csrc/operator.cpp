@@ -53,7 +53,9 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
       if (n == grid->ne && model->comp_nspec[c] > 0) full = c;
       else if (n != 0 && model->comp_nspec[c] > 0) ok = false;
     }
-    ok = ok && full >= 0 && model->diffusion_is_constant(full) &&
+    int species_comps = 0;   // the structured kernels are generated for single-compartment models only (jit.cpp)
+    for (int c = 0; c < model->ncomp(); ++c) species_comps += model->comp_nspec[c] > 0;
+    ok = ok && species_comps == 1 && full >= 0 && model->diffusion_is_constant(full) &&
          (int64_t)grid->comp_vertices[full].size() == grid->nv;
     if (scheme == "structured" && !ok)
       fail("model.assembly.b200.scheme = structured needs a structured single-compartment grid without cell data");
