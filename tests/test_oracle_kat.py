@@ -354,3 +354,65 @@ def test_two_disks_cell_data_kat():
         vals, status = ORC.reduce(om, u, 1.0)
         errs.append(vals["u_error"])
     assert errs[0] < 2e-3 and errs[1] < 0.4 * errs[0]
+
+
+# test/time_snap.ini: three species, A + B -> C, "exact time-step to finish in two steps"
+# (dune-copasi issue 67: a third, tiny step appeared when 0.1 + 0.1 did not compare equal to 0.2).
+# The TIFF initial data and the disk mesh are git-LFS pointers: smooth synthetic data on a square.
+TIME_SNAP = """
+[compartments.domain]
+type = expression
+expression = 1
+[model.scalar_field.A]
+compartment = domain
+cross_diffusion.A.expression = 0.4
+reaction.expression = A*B*1e-06*-100.0
+reaction.jacobian.A.expression = B*1e-06*-100.0
+reaction.jacobian.B.expression = A*1e-06*-100.0
+storage.expression = 1
+initial.expression = 1000*(0.5 + 0.5*sin(3*position_x)*cos(2*position_y))
+[model.scalar_field.B]
+compartment = domain
+cross_diffusion.B.expression = 0.4
+reaction.expression = A*B*1e-06*-100.0
+reaction.jacobian.A.expression = B*1e-06*-100.0
+reaction.jacobian.B.expression = A*1e-06*-100.0
+storage.expression = 1
+initial.expression = 1000*(0.5 + 0.4*cos(position_x + position_y))
+[model.scalar_field.C]
+compartment = domain
+cross_diffusion.C.expression = 25
+reaction.expression = A*B*1e-06*100.0
+reaction.jacobian.A.expression = B*1e-06*100.0
+reaction.jacobian.B.expression = A*1e-06*100.0
+storage.expression = 1
+initial.expression = 0
+[model.time_step_operator]
+type = ImplicitEuler
+time_step_initial = 0.1
+time_end = 0.2
+""" + K.SOLVER
+
+
+def test_time_snap_kat():
+    """test/time_snap.ini:46-49: with time_step_initial = 0.1 and time_end = 0.2 the stepper takes exactly
+    two steps and lands on 0.2 (no third sliver step); A + B + 2 C is conserved by the scheme."""
+    om = K.Case("time_snap", TIME_SNAP, 2, lambda: OMESH.structured(2, [12, 12]), dt=0.1).oracle()
+    S = ORC.StepOperator(om)
+    u0 = om.initial(0.0)
+    u, t, n = ORC.evolve(S, u0, 0.0, 0.2, 0.1)
+    assert n == 2 and t == pytest.approx(0.2, abs=1e-14)
+    # the same through sloppy arithmetic on the end time (0.1 + 0.1 != 0.2 patterns)
+    u2, t2, n2 = ORC.evolve(S, u0, 0.0, 0.1 + 0.1 + 1e-17, 0.1)
+    assert n2 == 2 and np.array_equal(u, u2)
+    # mass matrix weighted totals: d/dt (A + C) = 0 and d/dt (B + C) = 0 for no-flux boundaries
+    rp, ci = om.pattern()
+    vals = np.zeros(ci.size)
+    om.jacobian(1, 0.0, 1.0, u0, rp, ci, vals)
+    import scipy.sparse as sp
+    M = sp.csr_matrix((vals, ci, rp), shape=(om.ndofs, om.ndofs))
+    m0, m1 = M @ u0, M @ u
+    for s in (0, 1):
+        tot0 = m0[s::3].sum() + m0[2::3].sum()
+        tot1 = m1[s::3].sum() + m1[2::3].sum()
+        assert abs(tot1 - tot0) <= 1e-9 * abs(tot0)
