@@ -170,3 +170,33 @@ def test_owned_ranges_are_contiguous_per_compartment(structured):
                 assert idx[-1] - idx[0] + 1 == idx.size
             total += int(owned.sum()) * oml.comp_nspec[c]
     assert total == case.oracle().ndofs
+
+
+@pytest.mark.parametrize("name", ["poisson_q1", "poisson"])
+def test_dirichlet_constraints_on_slabs(name):
+    """Slab partitions of a structured lattice: the cut planes are not boundary.  Every rank's constraint
+    set equals the serial one restricted to its local vertices (owned and ghost), values included --
+    for the Kuhn split (facet search) and for Q1 cells (lattice indices of the global box)."""
+    import dune_copasi_b200 as D
+    case = K.ALL_CASES[name]
+    cfg = D.Config(case.ini)
+    model = D.Model(cfg, case.dim, [])
+    gglob = K.product_grid(case)
+    gser = K.product_grid(case)
+    gser.bind(model)
+    d, v = gser.constraints(model)
+    serial = dict(zip(d.tolist(), v.tolist()))           # single species: dof == global vertex id
+    assert len(serial) > 0
+    size = 3
+    seen = set()
+    for rank in range(size):
+        gloc = gglob.partition(rank, size)
+        gloc.bind(model)
+        gids = gloc.global_vertex_ids()
+        dl, vl = gloc.constraints(model)
+        local = dict(zip(gids[dl].tolist(), vl.tolist()))
+        expect = {g: serial[g] for g in gids.tolist() if g in serial}
+        assert local == expect, (name, rank, len(local), len(expect))
+        ob, oe = gloc.owned_vertex_range()
+        seen.update(g for g in gids[ob:oe].tolist() if g in serial)
+    assert seen == set(serial)
