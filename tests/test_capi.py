@@ -95,3 +95,14 @@ def test_c_host_computes_on_the_device(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.split()[0] == "ok" and float(out.stdout.split()[5]) > 0
+
+
+def test_peer_mailbox_layout(tmp_path):
+    """csrc/kernels/peer.hpp: the slots of the CUDA-IPC mailboxes never overlap (host-side check)."""
+    exe = str(tmp_path / "peer_layout")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "dune_copasi_b200", "csrc"),
+                           "-I", os.path.join(cuda, "include"), os.path.join(ROOT, "tests", "c_host", "peer_layout_check.cpp"),
+                           "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
