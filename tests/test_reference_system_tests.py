@@ -17,8 +17,9 @@ REF = "/root/reference/test"
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
 
 
-def run_reference_ini(name, dim, overrides=()):
-    cfg = INI.parse_ini(open(os.path.join(REF, name)).read())
+def run_reference_ini(name, dim, overrides=(), pin_solver=True):
+    path = name if os.path.isabs(name) else os.path.join(REF, name)
+    cfg = INI.parse_ini(open(path).read())
     for k, v in overrides:
         INI.set_key(cfg, k, v)
     g = INI.sub(cfg, "grid")
@@ -29,8 +30,9 @@ def run_reference_ini(name, dim, overrides=()):
         return [float(x) for x in raw][:dim] if raw else [default] * dim
     cells = [int(c) * 2 ** int(g.get("refinement_level", 0)) for c in vec("cells", 1)]
     mesh = OMESH.structured(dim, cells, vec("origin", 0.0), vec("extensions", 1.0))
-    INI.set_key(cfg, "model.time_step_operator.linear_solver.type", "BiCGSTAB")
-    INI.set_key(cfg, "model.time_step_operator.linear_solver.preconditioner.type", "SSOR")
+    if pin_solver:
+        INI.set_key(cfg, "model.time_step_operator.linear_solver.type", "BiCGSTAB")
+        INI.set_key(cfg, "model.time_step_operator.linear_solver.preconditioner.type", "SSOR")
     om = ORC.Model(cfg, mesh)
     S = ORC.StepOperator(om)
     ts = INI.sub(INI.sub(cfg, "model"), "time_step_operator")
@@ -71,3 +73,32 @@ def test_poisson_from_the_reference_file(dim):
     om, u, n, values, status = run_reference_ini("poisson.ini", dim, over)
     assert max(status.values()) < 2, (values, status)
     assert values["u_error"] <= 2.0
+
+
+DOCS = "/root/reference/doc/docusaurus/static/ini/next"
+
+
+def test_documented_gray_scott_with_its_own_solver_settings():
+    """doc/docusaurus/static/ini/next/grey_scott.ini as written -- RestartedGMRes + Jacobi, Newton at 1e-8,
+    128^2 lattice (refinement_level 7) -- for the first steps of its adaptive run: every setting of the
+    file is inside the data-parallel path, nothing is pinned."""
+    om, u, n, values, status = run_reference_ini(os.path.join(DOCS, "grey_scott.ini"), 2,
+                                                 [("model.time_step_operator.time_end", "0.6")], pin_solver=False)
+    assert n == 5 and om.ndofs == 2 * 129 * 129       # dt = 0.1, 0.11, 0.121, 0.1331, then the snap to 0.6
+    U, V = u[0::2], u[1::2]
+    assert np.isfinite(u).all() and V.min() > -1e-6 and 0.3 < V.max() < 0.7 and 0.5 < U.min() < 0.7
+    # away from the bumps V ~ 0 and U follows U' = F (1 - U): U = 1 - 0.3 exp(-F t), F = 0.042
+    assert U.max() == pytest.approx(1.0 - 0.3 * np.exp(-0.042 * 0.6), abs=2e-5)
+
+
+def test_documented_lotka_volterra_and_heat_files_run():
+    """volka_terra.ini (two triangles: an ODE system through the PDE machinery) and heat.ini, a few steps."""
+    om, u, n, values, status = run_reference_ini(os.path.join(DOCS, "volka_terra.ini"), 2,
+                                                 [("model.time_step_operator.time_end", "1.0")])
+    assert n >= 4 and np.isfinite(u).all() and u.min() > 0
+    # identical states at the four vertices and no diffusion: the fields stay spatially constant up to the
+    # file's (default) solver tolerances -- Newton stops at 1e-8 on the *squared* defect norm
+    assert np.ptp(u[0::2]) <= 1e-3 * abs(u[0]) and np.ptp(u[1::2]) <= 1e-3 * abs(u[1])
+    om, u, n, values, status = run_reference_ini(os.path.join(DOCS, "heat.ini"), 2,
+                                                 [("model.time_step_operator.time_end", "0.3"), ("grid.refinement_level", "2")])
+    assert n >= 1 and np.isfinite(u).all()
