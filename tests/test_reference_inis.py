@@ -45,3 +45,39 @@ def test_reference_ini(path):
     assert a.size == s.size and a.size > 0
     tol = 1e-12 * np.maximum(np.abs(a), np.abs(a).max() * 1e-3)
     assert np.all(np.abs(a - s) <= tol), (name, np.abs(a - s).max())
+
+
+def test_restated_cases_equal_the_reference_files():
+    """tests/cases.py restates the reference's test inis as text (the GPU box has no /root/reference): the
+    physics sections -- [compartments], [model.scalar_field.*] and the [parser_context] entries they use --
+    are the files', entry for entry.  Differences that are allowed, and why:
+    rng (replaced by a function exactly as test/CMakeLists.txt:78-79 does), Heaviside / parser_type (unused
+    by the equations), u_*_analytic (helpers of the [model.reduce] section, kept with the restated reduce)."""
+    import cases as K
+    INI = K.INI
+    pairs = {"gauss.ini": K.GAUSS, "exp.ini": K.EXP, "poisson.ini": K.POISSON, "two_disks.ini": K.TWO_DISKS,
+             "mitchell_schaefer.ini": K.MITCHELL_SCHAEFER, "two_disks_cell_data.ini": K.TWO_DISKS_CELL_DATA}
+    allowed = {"rng", "Heaviside", "parser_type", "u_in_analytic", "u_out_analytic"}
+
+    def norm(d):
+        return {k: norm(v) for k, v in d.items()} if isinstance(d, dict) else " ".join(str(d).split())
+    for name, text in pairs.items():
+        ref = INI.parse_ini(open(f"{REF}/test/{name}").read())
+        mine = INI.parse_ini(text)
+        assert norm(INI.sub(ref, "compartments")) == norm(INI.sub(mine, "compartments")), name
+        assert norm(INI.sub(INI.sub(ref, "model"), "scalar_field")) == norm(INI.sub(INI.sub(mine, "model"), "scalar_field")), name
+        a, b = norm(INI.sub(ref, "parser_context")), norm(INI.sub(mine, "parser_context"))
+        for key in set(a) | set(b):
+            if key not in allowed:
+                assert a.get(key) == b.get(key), (name, key)
+        for key in ("is_linear",):
+            assert str(INI.sub(ref, "model").get(key, "false")) == str(INI.sub(mine, "model").get(key, "false")), (name, key)
+    # the Gray-Scott case is the documented example's model (bumps in 3-D added for the 3-D lattice)
+    ref = INI.parse_ini(open(f"{REF}/doc/docusaurus/static/ini/next/grey_scott.ini").read())
+    mine = INI.parse_ini(K.GRAY_SCOTT)
+    fr, fm = norm(INI.sub(INI.sub(ref, "model"), "scalar_field")), norm(INI.sub(INI.sub(mine, "model"), "scalar_field"))
+    for sp in ("U", "V"):
+        for key in ("storage", "reaction", "cross_diffusion", "compartment"):
+            assert fr[sp][key] == fm[sp][key], (sp, key)
+    for key in ("F", "k", "D"):
+        assert norm(INI.sub(ref, "parser_context"))[key] == norm(INI.sub(mine, "parser_context"))[key]
