@@ -216,3 +216,24 @@ def test_nvrtc_compiles_every_case_without_gpu():
         cubin = model.compile()
         assert cubin[:4] == b"\x7fELF" and len(cubin) > 10000
         assert b"dc_k_patch_residual_0" in cubin and b"dc_k_jacobian_volume_0" in cubin
+
+
+@pytest.mark.parametrize("name,vtk_type", [("grayscott2d_q1", 8.0), ("grayscott3d_q1", 11.0)])
+def test_vtk_output_of_q1_lattices(tmp_path, name, vtk_type):
+    """Q1 cells are written as VTK_PIXEL / VTK_VOXEL, whose corner order is the bit pattern used here."""
+    import xml.etree.ElementTree as ET
+    case = K.Q1_CASES[name]
+    om = case.oracle()
+    cfg, model, grid = K.product_objects(case)
+    u = K.rand_state(om.ndofs, 4)
+    out = tmp_path / "q1"
+    grid.write_vtk(model, u, 0.0, out, append=False)
+    piece = ET.parse(out / "q1-compartment-00000.vtu").getroot().find(".//Piece")
+    assert int(piece.get("NumberOfPoints")) == om.mesh.nv and int(piece.get("NumberOfCells")) == om.mesh.ne
+    arrays = {a.get("Name"): np.array(a.text.split(), dtype=float) for a in piece.iter("DataArray")}
+    nd = om.mesh.elems.shape[1]
+    assert set(arrays["types"]) == {vtk_type}
+    assert np.array_equal(arrays["connectivity"].astype(int).reshape(-1, nd), om.mesh.elems)
+    assert np.array_equal(arrays["offsets"].astype(int), nd * np.arange(1, om.mesh.ne + 1))
+    assert np.array_equal(arrays["U"], u[0::2]) and np.array_equal(arrays["V"], u[1::2])
+    assert np.array_equal(arrays["Coordinates"].reshape(-1, 3)[:, :case.dim], om.mesh.coords)
