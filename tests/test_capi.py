@@ -106,3 +106,30 @@ def test_peer_mailbox_layout(tmp_path):
                            "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
+
+
+def _build_cxx_example(tmp_path):
+    exe = str(tmp_path / "gray_scott")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "gray_scott.cpp"), "-o", exe,
+                           "-L", os.path.dirname(LIB), "-ldune_copasi_b200", "-Wl,-rpath," + os.path.dirname(LIB)])
+    return exe
+
+
+def test_cxx_example_builds_and_refuses_to_run_without_a_device(tmp_path):
+    """examples/gray_scott.cpp: the documented Gray-Scott model end to end from C++ (no Python)."""
+    import dune_copasi_b200 as D
+    exe = _build_cxx_example(tmp_path)
+    out = subprocess.run([exe, "16", "1.0"], capture_output=True, text=True, timeout=300)
+    if D.lib().dcb_device_count() < 1:
+        assert out.returncode == 2 and "no CUDA device" in out.stderr
+    else:
+        assert out.returncode == 0, out.stderr
+
+
+@pytest.mark.gpu
+def test_cxx_example_runs_on_the_device(tmp_path):
+    exe = _build_cxx_example(tmp_path)
+    out = subprocess.run([exe, "64", "5.0", str(tmp_path / "vtk")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("t = 5 after") and (tmp_path / "vtk" / "vtk-compartment-00000.vtu").exists()
