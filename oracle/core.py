@@ -739,19 +739,41 @@ def reduce(model: Model, u, time: float, cfg: dict | None = None):
     rc = INI.sub(INI.sub(cfg if cfg is not None else model.cfg, "model"), "reduce")
     keys = [(k, v) for k, v in rc.items() if isinstance(v, dict)]
     m = model.mesh
-    dim, nd = m.dim, m.dim + 1
-    lam, w = _reduce_rule(dim)
-    nq = w.size
+    dim = m.dim
     X = m.coords[m.elems]                                        # [ne, nd, dim]
-    Bm = np.transpose(X[:, 1:, :] - X[:, :1, :], (0, 2, 1))      # columns = edges
-    det = np.abs(np.linalg.det(Bm))
-    Binv = np.linalg.inv(Bm)                                     # rows = grad of xi_k
-    G = np.concatenate([-Binv.sum(axis=1, keepdims=True), Binv], axis=1)   # [ne, nd, dim]
     sym = model.sym
+    if m.etype == 1:
+        # Q1 cells (not a reference element): the order-4 rule of a cube is the 3-point Gauss rule per
+        # axis; lam[q, a] = multilinear shape function a at point q, dlam its reference gradient
+        g1 = np.array([0.5 - math.sqrt(0.15), 0.5, 0.5 + math.sqrt(0.15)])
+        w1 = np.array([5.0, 8.0, 5.0]) / 18.0
+        pts = np.stack([a.ravel() for a in np.meshgrid(*[g1] * dim, indexing="ij")], axis=1)[:, ::-1]   # x fastest
+        w = np.prod(np.stack([a.ravel() for a in np.meshgrid(*[w1] * dim, indexing="ij")], axis=1), axis=1)
+        nd, nq = 1 << dim, w.size
+        lam = np.ones((nq, nd))
+        dlam = np.ones((nq, nd, dim))
+        for a in range(nd):
+            for k in range(dim):
+                f = pts[:, k] if (a >> k) & 1 else 1.0 - pts[:, k]
+                lam[:, a] *= f
+                for r in range(dim):
+                    dlam[:, a, r] *= (1.0 if (a >> k) & 1 else -1.0) if r == k else f
+        h = np.stack([X[:, 1 << k, k] - X[:, 0, k] for k in range(dim)], axis=1)       # [ne, dim]
+        det = np.prod(h, axis=1)
+        entvol = det
+    else:
+        nd = dim + 1
+        lam, w = _reduce_rule(dim)
+        nq = w.size
+        Bm = np.transpose(X[:, 1:, :] - X[:, :1, :], (0, 2, 1))      # columns = edges
+        det = np.abs(np.linalg.det(Bm))
+        Binv = np.linalg.inv(Bm)                                     # rows = grad of xi_k
+        G = np.concatenate([-Binv.sum(axis=1, keepdims=True), Binv], axis=1)   # [ne, nd, dim]
+        entvol = det / (2.0 if dim == 2 else 6.0)
     ctx = np.zeros((m.ne, nq, sym.nslots))
     ctx[..., E.SLOT_TIME] = time
     ctx[..., E.SLOT_INTFAC] = w[None, :] * det[:, None]
-    ctx[..., E.SLOT_ENTVOL] = (det / (2.0 if dim == 2 else 6.0))[:, None]
+    ctx[..., E.SLOT_ENTVOL] = entvol[:, None]
     ctx[..., E.SLOT_INVOL] = 1.0
     ctx[..., E.SLOT_POS:E.SLOT_POS + dim] = np.einsum("qa,ead->eqd", lam, X)
     for k in range(len(m.cell_keys)):
@@ -761,7 +783,10 @@ def reduce(model: Model, u, time: float, cfg: dict | None = None):
         xl = u[m.elem_dof[sel] + sp.local]                       # [nsel, nd]
         base = sym.spec_base + 4 * g
         ctx[sel, :, base] = xl @ lam.T
-        ctx[sel, :, base + 1:base + 1 + dim] = np.einsum("ea,ead->ed", xl, G[sel])[:, None, :]
+        if m.etype == 1:
+            ctx[sel, :, base + 1:base + 1 + dim] = np.einsum("ea,qad->eqd", xl, dlam) / h[sel][:, None, :]
+        else:
+            ctx[sel, :, base + 1:base + 1 + dim] = np.einsum("ea,ead->ed", xl, G[sel])[:, None, :]
     rows = ctx.reshape(-1, sym.nslots)
     values, status = {}, {}
     for key, sub in keys:

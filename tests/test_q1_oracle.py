@@ -102,3 +102,38 @@ def test_poisson_kat_on_cubes():
     X = om.mesh.coords
     e = u - (X ** 2).sum(axis=1)
     assert np.sqrt((1 / 16) ** 2 * (e ** 2).sum()) <= 1e-2
+
+
+def test_reduce_functionals_on_cubes():
+    """[model.reduce] on Q1 cells in the oracle (3-point Gauss rule per axis, exact to degree 5): volume,
+    a polynomial of degree (4, 5), a gradient functional of a bilinear field, the points-per-cell count.
+    (The product does not build reduce on cubes yet and says so: DESIGN.md section 7.)"""
+    cfg = INI.parse_ini(K.GAUSS + \"\"\"
+[model.reduce]
+vol.evaluation.expression = integration_factor
+poly.evaluation.expression = position_x^4 * position_y^5 * integration_factor
+ugrad.evaluation.expression = (grad_u_x + 2*grad_u_y) * integration_factor
+cells.evaluation.expression = integration_factor / entity_volume
+\"\"\")
+    mesh = OMESH.structured(2, [3, 5], [0, 0], [1.5, 2.0], element="cube")
+    om = ORC.Model(cfg, mesh)
+    X = mesh.coords
+    u = 3 * X[:, 0] + 0.5 * X[:, 1] + X[:, 0] * X[:, 1]
+    vals, status = ORC.reduce(om, u, 0.0)
+    assert vals["vol"] == pytest.approx(3.0, rel=1e-14)
+    assert vals["poly"] == pytest.approx(1.5 ** 5 / 5 * 2.0 ** 6 / 6, rel=1e-13)
+    # d/dx = 3 + y, d/dy = 0.5 + x integrated over [0,1.5] x [0,2]
+    assert vals["ugrad"] == pytest.approx((3 * 3.0 + 1.5 * 2.0) + 2 * (0.5 * 3.0 + 2.0 * 1.125), rel=1e-13)
+    assert vals["cells"] == pytest.approx(15.0, rel=1e-13)
+
+
+@pytest.mark.parametrize("dim,n", [(2, 32), (3, 16)])
+def test_gauss_assertions_on_cubes_through_reduce(dim, n):
+    \"\"\"test/gauss.ini:38-55 in the reference's own reduce vocabulary, Q1 discretisation: no error fires.\"\"\"
+    cfg = INI.parse_ini(K.GAUSS + K.REDUCE["gauss"])
+    INI.set_key(cfg, "model.time_step_operator.type", "Alexander2")
+    om = ORC.Model(cfg, OMESH.structured(dim, [n] * dim, [-1] * dim, [2] * dim, element="cube"))
+    S = ORC.StepOperator(om)
+    u, t, _ = ORC.evolve(S, om.initial(1.0), 1.0, 1.2, 0.1)
+    vals, status = ORC.reduce(om, u, t)
+    assert max(status.values()) < 2 and vals["u_error"] <= 0.5
