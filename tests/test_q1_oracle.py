@@ -108,13 +108,13 @@ def test_reduce_functionals_on_cubes():
     """[model.reduce] on Q1 cells in the oracle (3-point Gauss rule per axis, exact to degree 5): volume,
     a polynomial of degree (4, 5), a gradient functional of a bilinear field, the points-per-cell count.
     (The product does not build reduce on cubes yet and says so: DESIGN.md section 7.)"""
-    cfg = INI.parse_ini(K.GAUSS + \"\"\"
+    cfg = INI.parse_ini(K.GAUSS + """
 [model.reduce]
 vol.evaluation.expression = integration_factor
 poly.evaluation.expression = position_x^4 * position_y^5 * integration_factor
 ugrad.evaluation.expression = (grad_u_x + 2*grad_u_y) * integration_factor
 cells.evaluation.expression = integration_factor / entity_volume
-\"\"\")
+""")
     mesh = OMESH.structured(2, [3, 5], [0, 0], [1.5, 2.0], element="cube")
     om = ORC.Model(cfg, mesh)
     X = mesh.coords
@@ -129,7 +129,7 @@ cells.evaluation.expression = integration_factor / entity_volume
 
 @pytest.mark.parametrize("dim,n", [(2, 32), (3, 16)])
 def test_gauss_assertions_on_cubes_through_reduce(dim, n):
-    \"\"\"test/gauss.ini:38-55 in the reference's own reduce vocabulary, Q1 discretisation: no error fires.\"\"\"
+    """test/gauss.ini:38-55 in the reference's own reduce vocabulary, Q1 discretisation: no error fires."""
     cfg = INI.parse_ini(K.GAUSS + K.REDUCE["gauss"])
     INI.set_key(cfg, "model.time_step_operator.type", "Alexander2")
     om = ORC.Model(cfg, OMESH.structured(dim, [n] * dim, [-1] * dim, [2] * dim, element="cube"))
