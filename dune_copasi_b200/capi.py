@@ -65,8 +65,12 @@ SYMBOLS = {
     "dcb_model_species_name": (C.c_char_p, [_P, C.c_int]),
     "dcb_model_species_compartment": (C.c_int, [_P, C.c_int]),
     "dcb_model_cuda_source": (C.c_char_p, [_P]),
+    "dcb_model_cuda_source_group": (C.c_char_p, [_P, C.c_int]),
+    "dcb_operator_uses_tiles": (C.c_int, [_P]),
+    "dcb_solver_is_fused": (C.c_int, [_P]),
     "dcb_model_compile": (C.c_int64, [_P, C.c_int, C.c_char_p, C.c_size_t]),
     "dcb_model_precompile": (C.c_int, [_P]),
+    "dcb_model_precompile_group": (C.c_int, [_P, C.c_int]),
     "dcb_grid_bind": (C.c_int, [_P, _P]),
     "dcb_grid_num_dofs": (C.c_int64, [_P]),
     "dcb_grid_get_elem_compartment": (C.c_int, [_P, _I32]),
@@ -343,6 +347,15 @@ class Model:
             raise DcbError(lib().dcb_last_error().decode())
         return s.decode()
 
+    def precompile_group(self, group: int):
+        _check(lib().dcb_model_precompile_group(self.h, group))
+
+    def cuda_source_group(self, group: int) -> str:
+        s = lib().dcb_model_cuda_source_group(self.h, group)
+        if s is None:
+            _check(-1)
+        return s.decode()
+
     def precompile(self, reduce_config: "Config | None" = None):
         _check(lib().dcb_model_precompile(self.h))
         if reduce_config is not None:
@@ -372,6 +385,10 @@ class Operator:
     nnz = property(lambda s: lib().dcb_operator_nnz(s.h))
     launches = property(lambda s: lib().dcb_operator_launches(s.h))
     stream = property(lambda s: lib().dcb_operator_stream(s.h))
+
+    @property
+    def uses_tiles(self) -> bool:
+        return bool(lib().dcb_operator_uses_tiles(self.h))
 
     def sync(self):
         _check(lib().dcb_operator_sync(self.h))
@@ -452,6 +469,10 @@ class Solver:
     def __init__(self, op: Operator, linear_solver_cfg: Config, comm: Comm | None = None):
         self.op = op
         self.h = _ptr(lib().dcb_solver_create(op.h, linear_solver_cfg.h, comm.h if comm else None), "solver")
+
+    @property
+    def fused(self) -> bool:
+        return bool(lib().dcb_solver_is_fused(self.h))
 
     def linearize(self, time, wM, wA, x):
         x = _f64(x)

@@ -153,6 +153,13 @@ const char* dcb_model_cuda_source(dcb_model* m) {
   if (guard([&] { m->source = jit_source(*m->m, jit_defines(*m->m)); })) return nullptr;
   return m->source.c_str();
 }
+const char* dcb_model_cuda_source_group(dcb_model* m, int group) {
+  if (guard([&] {
+        if (group < 0 || group > (int)JitGroup::TileQ1) fail("kernel group ", group, " does not exist");
+        m->source = jit_source(*m->m, jit_defines(*m->m), (JitGroup)group);
+      })) return nullptr;
+  return m->source.c_str();
+}
 int64_t dcb_model_compile(dcb_model* m, int kind, char* out, size_t cap) {
   int64_t n = -1;
   guard([&] {
@@ -168,8 +175,15 @@ int dcb_model_precompile(dcb_model* m) {
   return guard([&] {
     std::string defs = jit_defines(*m->m);
     for (JitGroup g : {JitGroup::Patch, JitGroup::Element, JitGroup::Csr, JitGroup::Skeleton, JitGroup::Structured,
-                       JitGroup::StructuredQ1})
+                       JitGroup::StructuredQ1, JitGroup::Tile, JitGroup::TileQ1})
       jit_compile_cached(jit_source(*m->m, defs, g));
+  });
+}
+
+int dcb_model_precompile_group(dcb_model* m, int group) {
+  return guard([&] {
+    if (group < 0 || group > (int)JitGroup::TileQ1) fail("kernel group ", group, " does not exist");
+    jit_compile_cached(jit_source(*m->m, jit_defines(*m->m), (JitGroup)group));
   });
 }
 
@@ -300,6 +314,7 @@ int dcb_block_diagonal(dcb_operator* o, double t, double wM, double wA, const do
     b.download(bdiag, s);
   });
 }
+int dcb_operator_uses_tiles(const dcb_operator* o) { return o->op->tile_ready() ? 1 : 0; }
 int dcb_residual_dev(dcb_operator* o, double t, double wM, double wA, const double* x, double* r) {
   return guard([&] { o->op->residual(t, wM, wA, x, r); });
 }
@@ -339,6 +354,7 @@ int dcb_solver_solve(dcb_solver* s, const double* b, double* z, double rel_tol, 
     }
   });
 }
+int dcb_solver_is_fused(const dcb_solver* s) { return s->s->is_fused() ? 1 : 0; }
 int dcb_solver_apply_operator(dcb_solver* s, const double* v, double* y) {
   return guard([&] {
     cudaStream_t st = s->op->op->stream;

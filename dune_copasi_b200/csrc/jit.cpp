@@ -4,6 +4,7 @@
 #include <nvrtc.h>
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -16,6 +17,7 @@ extern const char* kKernelArgsSource;
 extern const char* kAssemblySource;
 extern const char* kStructuredSource;
 extern const char* kQ1Source;
+extern const char* kTileSource;
 
 std::string jit_source(const Model& model, const std::string& defines, JitGroup group) {
   std::ostringstream o;
@@ -82,6 +84,22 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
           << names[mode] << "_" << c << "(DcStructArgs a) { dc_q1_march_kernel<" << c << ", " << mode << ">(a); }\n";
     }
   }
+  if (group == JitGroup::Tile || group == JitGroup::TileQ1) {
+    // tile-marching drivers (kernels/assembly_tile.cuh) around the same cell functions; compiled on first use
+    const bool q1 = group == JitGroup::TileQ1;
+    if (q1) o << "#define DC_TILE_Q1 1\n";
+    o << kStructuredSource << "\n";
+    if (q1) o << kQ1Source << "\n";
+    o << kTileSource << "\n";
+    for (int c = 0; c < model.ncomp(); ++c) {
+      if (!structured_possible || model.comp_nspec[c] == 0 || !model.diffusion_is_constant(c)) continue;
+      if (q1 && model.has_extended_terms(c)) continue;
+      const char* names[2] = {"residual", "apply"};
+      for (int mode = 0; mode < 2; ++mode)
+        o << "extern \"C\" __global__ void __launch_bounds__(DC_TILE_THREADS, DC_TILE_MINB) dc_k_tile_" << (q1 ? "q1_" : "")
+          << names[mode] << "_" << c << "(DcTileArgs A) { dc_tile_" << (q1 ? "q1_" : "") << "kernel<" << c << ", " << mode << ">(A); }\n";
+    }
+  }
   if (all || group == JitGroup::Skeleton) {
     // One launch covers the facet lists of every directional compartment pair: the lists are small
     // (interfaces), so separate launches would be a chain of latency-bound kernels.  Blocks
@@ -119,7 +137,15 @@ std::string jit_defines(const Model& model) {
   // measured 16 % faster than 4 on B200 despite the spills (profiles/r01_csr_fill_128_ncu.txt)
   int cminb = acfg.get("csr_min_blocks", 8);
   if (cminb < 1 || cminb > 16) fail("model.assembly.b200.csr_min_blocks out of range");
-  return "#define DC_CSR_MINB " + std::to_string(cminb) + "\n#define DC_PATCH_THREADS " + std::to_string(th) + "\n#define DC_PATCH_MINB " + std::to_string(minb) +
+  // tile-marching drivers: 32 x tile_y cells per CTA in 3-D (one warp per row), tile_x2 cells in 2-D
+  int ns_max = 1;
+  for (int c = 0; c < model.ncomp(); ++c) ns_max = std::max(ns_max, model.comp_nspec[c]);
+  int ty = acfg.get("tile_y", ns_max <= 4 ? 4 : 2), tx2 = acfg.get("tile_x2", 128);
+  int tminb = acfg.get("tile_min_blocks", ns_max <= 2 ? 3 : ns_max <= 4 ? 2 : 1);
+  if (ty < 1 || ty > 32 || tx2 < 32 || tx2 > 1024 || tx2 % 32) fail("model.assembly.b200.tile_y / tile_x2 out of range");
+  if (tminb < 1 || tminb > 8) fail("model.assembly.b200.tile_min_blocks out of range");
+  return "#define DC_TILE_X (DC_DIM == 3 ? 32 : " + std::to_string(tx2) + ")\n#define DC_TILE_Y " + std::to_string(ty) +
+         "\n#define DC_TILE_MINB " + std::to_string(tminb) + "\n#define DC_CSR_MINB " + std::to_string(cminb) + "\n#define DC_PATCH_THREADS " + std::to_string(th) + "\n#define DC_PATCH_MINB " + std::to_string(minb) +
          "\n#define DC_STRUCT_THREADS " + std::to_string(sth) + "\n#define DC_STRUCT_MINB " + std::to_string(sminb) + "\n";
 }
 

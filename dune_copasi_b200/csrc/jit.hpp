@@ -16,7 +16,7 @@ namespace dcb {
 
 // Kernels are compiled in groups so that a run only pays for what it launches: the patch kernels
 // (hot path) eagerly, the element-per-thread kernels, the CSR fill and the facet kernels on first use.
-enum class JitGroup { All, Patch, Element, Csr, Skeleton, Structured, StructuredQ1 };
+enum class JitGroup { All, Patch, Element, Csr, Skeleton, Structured, StructuredQ1, Tile, TileQ1 };
 // full translation unit (defines + model source + kernel_args.h + assembly.cuh + entry points)
 std::string jit_source(const Model& model, const std::string& defines = "", JitGroup group = JitGroup::All);
 // #defines derived from model.assembly.b200.* (patch geometry)

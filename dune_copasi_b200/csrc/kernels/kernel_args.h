@@ -68,6 +68,39 @@ struct DcStructArgs {
   double* vals;
 };
 
+// Tile-marching drivers (kernels/assembly_tile.cuh): the structured kernels as an owner-computes
+// sweep.  A CTA owns a tile of the lattice's first DIM-1 axes and walks `lz` cell layers up the last
+// axis; vertex data of a plane is staged in shared memory, every result entry is written once with
+// a plain store.  Vertices shared with a neighbouring tile / chunk ("cut" vertices) get their partial
+// sums in `slots` and are finished by la::tile_fixup.
+struct DcTileArgs {
+  DcStructArgs s;              // lattice, weights; s.x = linearisation point, s.z = direction, s.r = result
+  int lz;                      // cell layers per chunk along the marching (last) axis
+  int ntx, nty;                // tiles along x and y (nty = 1 in 2-D)
+  int own_lo, own_hi;          // vertex planes [own_lo, own_hi) of the marching axis enter the reductions
+  int pro;                     // 0: direction = s.z;  1: p_out = r_in + beta (p_in - omega v_in), direction = relax dinv p_out
+                               // 2: r_out = r_in - alpha v_in, direction = relax dinv r_out, partial 0 = |r_out|^2
+  int epi;                     // 0: none;  1: partial 1 = <w, result>;  2: partial 1 = <result, r_out>, partial 2 = |result|^2
+  int first;                   // pro 1: p_out = r_in (first BiCGSTAB iteration)
+  int accumulate;              // result += instead of result =
+  int identity;                // apply: rows of Dirichlet-constrained dofs are identity rows (result = s.z there)
+  double relax;
+  const double* r_in;
+  const double* p_in;
+  const double* v_in;
+  const double* dinv;
+  const double* w;
+  double* r_out;
+  double* p_out;
+  const double* rho_new;       // device scalars of the BiCGSTAB recurrences (kernels/linalg.cu)
+  const double* rho;
+  const double* hptr;
+  const double* trtt;
+  double* slots;               // slots[(k - 1) * slot_stride + dof], k = 1..7: partial sums of cut vertices
+  long long slot_stride;
+  double* partials;            // [gridDim.x][4] reduction partials of this launch
+};
+
 struct DcFacetArgs {
   const double* coords;
   const int* elems;

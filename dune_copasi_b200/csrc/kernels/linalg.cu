@@ -411,6 +411,141 @@ __global__ void k_scatter(int64_t n, const int32_t* idx, const double* buf, doub
   if (i < n) x[idx[i]] = buf[i];
 }
 
+// ---------------------------------------------------------------- tile fix-up
+// One thread per cut vertex, three families: x-cut planes, y-cut planes (vertices that are not
+// x-cut), chunk boundary planes (vertices that are neither).
+__global__ void __launch_bounds__(kThreads) k_tile_fixup(TileFixup f, double* partials, unsigned* counter) {
+  const long long P0 = f.n[0] + 1, P1 = f.n[1] + 1, P2 = f.n[2] + 1;
+  const long long ncx = f.n[0] > 0 ? (f.n[0] - 1) / f.tile[0] : 0;
+  const long long ncy = f.n[1] > 0 ? (f.n[1] - 1) / f.tile[1] : 0;
+  const long long ncz = f.n[2] > 0 ? (f.n[2] - 1) / f.tile[2] : 0;
+  const long long famx = ncx * P1 * P2, famy = ncy * P0 * P2, famz = ncz * P0 * P1;
+  const long long total = famx + famy + famz;
+  double red[3] = {0.0, 0.0, 0.0};
+  for (long long t = blockIdx.x * (long long)kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
+    long long vx, vy, vz;
+    if (t < famx) {
+      vx = (t % ncx + 1) * f.tile[0];
+      vy = (t / ncx) % P1;
+      vz = t / (ncx * P1);
+    } else if (t < famx + famy) {
+      const long long u = t - famx;
+      vx = u % P0;
+      vy = ((u / P0) % ncy + 1) * f.tile[1];
+      vz = u / (P0 * ncy);
+    } else {
+      const long long u = t - famx - famy;
+      vx = u % P0;
+      vy = (u / P0) % P1;
+      vz = (u / (P0 * P1) + 1) * f.tile[2];
+    }
+    const bool xc = vx > 0 && vx < f.n[0] && vx % f.tile[0] == 0;
+    const bool yc = vy > 0 && vy < f.n[1] && vy % f.tile[1] == 0;
+    const bool zc = vz > 0 && vz < f.n[2] && vz % f.tile[2] == 0;
+    if (t >= famx && xc) continue;               // counted in the x family
+    if (t >= famx + famy && yc) continue;        // counted in the y family
+    const int m = (xc ? 1 : 0) | (yc ? 2 : 0) | (zc ? 4 : 0);
+    const long long d = f.dof_offset + (vx + vy * P0 + vz * P0 * P1) * f.ns;
+    const bool counts = vz >= f.own_lo && vz < f.own_hi;
+    for (int s = 0; s < f.ns; ++s) {
+      double val = f.y[d + s];
+      for (int k = 1; k < 8; ++k)
+        if ((k & ~m) == 0) val += f.slots[(k - 1) * f.slot_stride + d + s];
+      if (f.cmask && f.cmask[d + s]) val = f.zraw[d + s];
+      f.y[d + s] = val;
+      if (counts) {
+        if (f.epi == 1) red[1] += f.w[d + s] * val;
+        if (f.epi == 2) { red[1] += val * f.aux[d + s]; red[2] += val * val; }
+      }
+    }
+  }
+  // block sums, then the last block adds everything up in a fixed order
+  __shared__ double sm[3][kThreads / 32];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    double x = red[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) sm[q][warp] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      double x = 0.0;
+      for (int w = 0; w < kThreads / 32; ++w) x += sm[q][w];
+      partials[(size_t)blockIdx.x * 4 + q] = x;
+    }
+    __threadfence();
+    const unsigned ticket = atomicInc(counter, gridDim.x - 1);
+    last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    if (!((f.out_mask >> q) & 1)) continue;
+    // fixed order: strided partial sums per thread, lanes, warps -- the same for every run
+    double x = 0.0;
+    for (int b = threadIdx.x; b < f.nmain; b += kThreads) x += f.main_partials[(size_t)b * 4 + q];
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads) x += partials[(size_t)b * 4 + q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) sm[q][warp] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      if (!((f.out_mask >> q) & 1)) continue;
+      double x = 0.0;
+      for (int w = 0; w < kThreads / 32; ++w) x += sm[q][w];
+      f.out[q] = x;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_bicg_x_half(int64_t n, const double* __restrict__ rho_p,
+                                                          const double* __restrict__ hptr,
+                                                          const double* __restrict__ dinv, double relax,
+                                                          const double* __restrict__ p, double* __restrict__ x) {
+  const double alpha = *rho_p / *hptr;
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    x[i] += alpha * (relax * dinv[i] * p[i]);
+}
+
+// the closing sweep of a BiCGSTAB iteration with the Jacobi applications recomputed from their
+// arguments (y1 = relax dinv p, y2 = relax dinv r: the same products k_bicg_p_prec / k_bicg_r_prec store)
+__global__ void __launch_bounds__(kThreads) k_bicg_final_fold(int64_t n, Ranges own, const double* __restrict__ rho_p,
+                                                              const double* __restrict__ hptr,
+                                                              const double* __restrict__ trtt,
+                                                              const double* __restrict__ dinv, double relax,
+                                                              const double* __restrict__ p,
+                                                              const double* __restrict__ r,
+                                                              const double* __restrict__ xin, double* __restrict__ xout,
+                                                              const double* __restrict__ t, double* __restrict__ rout,
+                                                              const double* __restrict__ rt, double* partials,
+                                                              unsigned* counter, double* out) {
+  double acc[2] = {0.0, 0.0};
+  const bool single = own.n == 1 && own.b[0] == 0 && own.e[0] == n;
+  const double alpha = *rho_p / *hptr, omega = trtt[0] / trtt[1];
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    const double di = relax * dinv[i], rh = r[i];
+    const double y1 = di * p[i], y2 = di * rh;
+    xout[i] = (xin[i] + alpha * y1) + omega * y2;
+    const double ri = rh - omega * t[i];
+    rout[i] = ri;
+    if (single || in_ranges(own, i)) {
+      acc[0] += ri * ri;
+      acc[1] += rt[i] * ri;
+    }
+  }
+  grid_reduce<2>(acc, partials, counter, out);
+}
+
 inline void check_launch() { DCB_CUDA(cudaGetLastError()); }
 
 }  // namespace
@@ -590,6 +725,26 @@ void csr_constrain(int64_t nrows, const int64_t* rowptr, const int32_t* colidx, 
 void bdiag_constrain(int64_t dof0, int64_t nblocks, int bs, double* bdiag, const unsigned char* mask, cudaStream_t s) {
   if (nblocks == 0) return;
   k_bdiag_constrain<<<grid_for(nblocks * bs), kThreads, 0, s>>>(dof0, nblocks * bs, bs, bdiag, mask);
+  check_launch();
+}
+void tile_fixup(const TileFixup& f, const ReduceWorkspace& w, cudaStream_t s) {
+  const long long P0 = f.n[0] + 1, P1 = f.n[1] + 1, P2 = f.n[2] + 1;
+  const long long ncx = f.n[0] > 0 ? (f.n[0] - 1) / f.tile[0] : 0, ncy = f.n[1] > 0 ? (f.n[1] - 1) / f.tile[1] : 0,
+                  ncz = f.n[2] > 0 ? (f.n[2] - 1) / f.tile[2] : 0;
+  const long long total = ncx * P1 * P2 + ncy * P0 * P2 + ncz * P0 * P1;
+  k_tile_fixup<<<grid_for(total), kThreads, 0, s>>>(f, w.partials, w.counter);
+  check_launch();
+}
+void bicg_x_half(int64_t n, const double* rho, const double* hptr, const double* dinv, double relax, const double* p,
+                 double* x, cudaStream_t s) {
+  k_bicg_x_half<<<grid_for(n, 2), kThreads, 0, s>>>(n, rho, hptr, dinv, relax, p, x);
+  check_launch();
+}
+void bicg_final_fold(int64_t n, const Ranges& own, const double* rho, const double* hptr, const double* trtt,
+                     const double* dinv, double relax, const double* p, const double* r, const double* xin, double* xout,
+                     const double* t, double* rout, const double* rt, double* out, const ReduceWorkspace& w, cudaStream_t s) {
+  k_bicg_final_fold<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, rho, hptr, trtt, dinv, relax, p, r, xin, xout, t, rout, rt,
+                                                        w.partials, w.counter, out);
   check_launch();
 }
 void gather(int64_t n, const int32_t* idx, const double* x, double* buf, cudaStream_t s) {

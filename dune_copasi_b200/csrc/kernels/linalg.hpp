@@ -108,6 +108,38 @@ void csr_constrain(int64_t nrows, const int64_t* rowptr, const int32_t* colidx, 
 // block diagonal rows/cols of constrained dofs -> identity
 void bdiag_constrain(int64_t dof0, int64_t nblocks, int bs, double* bdiag, const unsigned char* mask, cudaStream_t s);
 
+// Second pass of the tile-marching assembly drivers (kernels/assembly_tile.cuh): every vertex that
+// lies on a tile edge or a chunk boundary plane ("cut") gets its partial sums added in slot order
+// (slot 0 = y itself), its share of the reductions is added, and the last block forms the final sums:
+// the partials of the main launch in block order, then those of this launch in block order.
+struct TileFixup {
+  int n[3];                 // cells per axis; 2-D lattices are passed as (nx, 0, ny)
+  int tile[3];              // tile extents along x, y and the chunk length along the marching axis
+  int ns;
+  long long dof_offset;
+  int own_lo, own_hi;       // vertex planes of the marching axis that enter the reductions
+  int epi;                  // as DcTileArgs::epi
+  int accumulate_unused;
+  double* y;
+  const double* slots;
+  long long slot_stride;
+  const double* w;          // epi 1: <w, y>
+  const double* aux;        // epi 2: <y, aux>, |y|^2
+  const unsigned char* cmask;   // identity rows: y = zraw there
+  const double* zraw;
+  const double* main_partials;  // [nmain][4]
+  int nmain;
+  double* out;              // out[q] = sum of partial q for every q with (out_mask >> q) & 1
+  int out_mask;
+};
+void tile_fixup(const TileFixup& f, const ReduceWorkspace& w, cudaStream_t s);
+// x += (rho / h) * relax * dinv * p     (BiCGSTAB stops after its first half step)
+void bicg_x_half(int64_t n, const double* rho, const double* hptr, const double* dinv, double relax, const double* p,
+                 double* x, cudaStream_t s);
+// xout = (xin + alpha relax dinv p) + omega relax dinv r ; rout = r - omega t ; out[0] = <rout,rout> ; out[1] = <rt,rout>
+void bicg_final_fold(int64_t n, const Ranges& own, const double* rho, const double* hptr, const double* trtt,
+                     const double* dinv, double relax, const double* p, const double* r, const double* xin, double* xout,
+                     const double* t, double* rout, const double* rt, double* out, const ReduceWorkspace& w, cudaStream_t s);
 // halo exchange helpers
 void gather(int64_t n, const int32_t* idx, const double* x, double* buf, cudaStream_t s);   // buf[i] = x[idx[i]]
 void scatter(int64_t n, const int32_t* idx, const double* buf, double* x, cudaStream_t s);  // x[idx[i]] = buf[i]

@@ -92,6 +92,23 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
   if (patch_pn_ < 16 || patch_pn_ > 16384) fail("model.assembly.b200.patch_vertices out of range");
   if (patch_pe_ < 16 || patch_pe_ > 16383) fail("model.assembly.b200.patch_elements out of range");
   DCB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  // tile-marching drivers: same eligibility as the structured kernels, no facet terms, analytic
+  // Jacobian of the standard terms, staged planes within the shared-memory budget
+  {
+    const int ns = struct_comp_ >= 0 ? model->comp_nspec[struct_comp_] : 0;
+    int ns_max = 1;
+    for (int c = 0; c < model->ncomp(); ++c) ns_max = std::max(ns_max, model->comp_nspec[c]);
+    tile_x_ = grid->dim == 3 ? 32 : acfg.get("tile_x2", 128);
+    tile_y_ = grid->dim == 3 ? acfg.get("tile_y", ns_max <= 4 ? 4 : 2) : 1;
+    tile_minb_ = acfg.get("tile_min_blocks", ns_max <= 2 ? 3 : ns_max <= 4 ? 2 : 1);
+    tile_lz_ = acfg.get("tile_lz", 0);
+    tile_residual_ = acfg.get("tile_residual", true);
+    const bool want = acfg.get("tile", true);
+    tile_ok_ = want && scheme == "structured" && struct_comp_ >= 0 && !model->has_outflow() &&
+               !(model->numerical_jacobian || model->has_extended_terms(struct_comp_)) &&
+               tile_smem_bytes(ns, tile_x_, tile_y_, grid->dim) <= 200 * 1024;
+    if (tile_ok_) la::reduce_workspace_create(&tile_ws_);
+  }
 
   // ---- kernels for this model
   jit_defines_ = jit_defines(*model);
@@ -187,6 +204,7 @@ cudaKernel_t DeviceOperator::kernel(JitGroup group, const std::string& name) {
 }
 
 DeviceOperator::~DeviceOperator() {
+  la::reduce_workspace_destroy(&tile_ws_);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -559,7 +577,98 @@ void DeviceOperator::launch_facets(const char* kind, double t, double wA, const 
   stats.launches++;
 }
 
+// ---------------------------------------------------------------------------------- tile marching
+size_t tile_smem_bytes(int ns, int tile_x, int tile_y, int dim) {
+  const size_t plane = (size_t)(tile_x + 1) * (dim == 3 ? tile_y + 1 : 1);
+  return (size_t)(3 * 3 + 1 + 2 * 4) * ns * plane * sizeof(double);   // ring, result plane, raw operand planes
+}
+
+void DeviceOperator::launch_tile(int mode, double t, double wM, double wA, const double* x, const double* z, double* y,
+                                 const TileFused* f, bool accumulate) {
+  if (!tile_ok_) fail("tile-marching kernels are not available for this operator");
+  const int c = struct_comp_, dim = grid->dim, L = dim - 1;
+  const int ns = model->comp_nspec[c];
+  const bool q1 = grid->elem_kind == 1;
+  DcTileArgs A{};
+  DcStructArgs& a = A.s;
+  a.ncells = 1;
+  for (int k = 0; k < 3; ++k) {
+    a.n[k] = k < dim ? grid->s_cells[k] : 1;
+    a.h[k] = grid->s_h[k];
+    a.origin[k] = grid->s_origin[k];
+    a.ncells *= a.n[k];
+  }
+  a.dof_offset = (int)grid->comp_offset[c];
+  a.time = t; a.wM = wM; a.wA = wA; a.x = x; a.z = z; a.r = y;
+  a.cmask = cmask.p;
+  A.ntx = (a.n[0] + tile_x_ - 1) / tile_x_;
+  A.nty = dim == 3 ? (a.n[1] + tile_y_ - 1) / tile_y_ : 1;
+  // chunks along the marching axis: enough CTAs for ~8 waves of 148 SMs x resident CTAs, but chunks
+  // of at least 8 layers (every chunk stages one extra plane and leaves one more cut plane)
+  const int nL = a.n[L];
+  int lz = tile_lz_;
+  if (lz <= 0) {
+    const long long tiles = (long long)A.ntx * A.nty;
+    const long long want = (148LL * tile_minb_ * 8 + tiles - 1) / tiles;
+    lz = (int)std::max<long long>(8, (nL + want - 1) / want);
+  }
+  lz = std::min(lz, nL);
+  A.lz = lz;
+  const int nchunk = (nL + lz - 1) / lz;
+  const long long plane = (long long)(a.n[0] + 1) * (dim == 3 ? a.n[1] + 1 : 1);
+  A.own_lo = 0; A.own_hi = nL + 1;
+  if (grid->n_owned >= 0) {
+    A.own_lo = (int)(grid->owned_begin / plane);
+    A.own_hi = A.own_lo + (int)(grid->n_owned / plane);
+  }
+  if (f) {
+    A.pro = f->pro; A.epi = f->epi; A.first = f->first; A.relax = f->relax;
+    A.r_in = f->r_in; A.p_in = f->p_in; A.v_in = f->v_in; A.dinv = f->dinv; A.w = f->w;
+    A.r_out = f->r_out; A.p_out = f->p_out;
+    A.rho_new = f->rho_new; A.rho = f->rho; A.hptr = f->hptr; A.trtt = f->trtt;
+  }
+  A.accumulate = accumulate;
+  A.identity = mode == 1 && !accumulate && A.pro == 0 && ncons > 0;
+  const unsigned nblocks = (unsigned)((long long)A.ntx * A.nty * nchunk);
+  if (tile_slots_.n < 7 * ndofs) tile_slots_.alloc(7 * ndofs);
+  if (tile_partials_.n < (int64_t)nblocks * 4) tile_partials_.alloc((int64_t)nblocks * 4);
+  A.slots = tile_slots_.p; A.slot_stride = ndofs; A.partials = tile_partials_.p;
+  const size_t smem = tile_smem_bytes(ns, tile_x_, tile_y_, dim);
+  const std::string kname = std::string("dc_k_tile_") + (q1 ? "q1_" : "") + (mode == 0 ? "residual_" : "apply_") + std::to_string(c);
+  cudaKernel_t k = kernel(q1 ? JitGroup::TileQ1 : JitGroup::Tile, kname);
+  DCB_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    ProfScope ps(this, mode == 0 ? "tile_residual" : "tile_apply");
+    jit_launch(k, nblocks, (unsigned)(tile_x_ * (dim == 3 ? tile_y_ : 1)), smem, stream, A);
+    stats.launches++;
+  }
+  la::TileFixup F{};
+  F.n[0] = a.n[0]; F.n[1] = dim == 3 ? a.n[1] : 0; F.n[2] = nL;
+  F.tile[0] = tile_x_; F.tile[1] = dim == 3 ? tile_y_ : 1; F.tile[2] = lz;
+  F.ns = ns; F.dof_offset = a.dof_offset; F.own_lo = A.own_lo; F.own_hi = A.own_hi;
+  F.epi = A.epi; F.y = y; F.slots = tile_slots_.p; F.slot_stride = ndofs;
+  F.w = A.w; F.aux = A.r_out;
+  F.cmask = A.identity ? cmask.p : nullptr; F.zraw = z;
+  F.main_partials = tile_partials_.p; F.nmain = (int)nblocks;
+  F.out = f ? f->out : nullptr; F.out_mask = f && f->out ? f->out_mask : 0;
+  {
+    ProfScope ps(this, "tile_fixup");
+    la::tile_fixup(F, tile_ws_, stream);
+    stats.launches++;
+  }
+}
+
+void DeviceOperator::tile_apply(double t, double wM, double wA, const double* x, const double* z, double* y,
+                                const TileFused* f) {
+  launch_tile(1, t, wM, wA, x, z, y, f, false);
+}
+
+void DeviceOperator::tile_residual(double t, double wM, double wA, const double* x, double* r) {
+  launch_tile(0, t, wM, wA, x, nullptr, r, nullptr, true);
+}
+
 void DeviceOperator::residual(double t, double wM, double wA, const double* x, double* r) {
+  if (tile_ok_ && tile_residual_) { tile_residual(t, wM, wA, x, r); return; }
   launch_volume("dc_k_residual_volume_", 0, t, wM, wA, x, nullptr, r, nullptr, nullptr);
   if (wA != 0.0) launch_facets("dc_k_skeleton_residual", t, wA, x, nullptr, r, nullptr, nullptr);
 }
@@ -574,6 +683,7 @@ bool DeviceOperator::can_split_apply() const {
 void DeviceOperator::jacobian_apply(double t, double wM, double wA, const double* x, const double* z, double* y,
                                     int part) {
   if (part != 0 && !can_split_apply()) fail("jacobian_apply: this operator cannot be split into interior / halo layers");
+  if (part == 0 && tile_ok_) { launch_tile(1, t, wM, wA, x, z, y, nullptr, true); return; }   // y += J z
   struct_part_ = part;
   launch_volume("dc_k_jacobian_apply_volume_", 1, t, wM, wA, x, z, y, nullptr, nullptr);
   struct_part_ = 0;

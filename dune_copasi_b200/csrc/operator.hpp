@@ -19,6 +19,9 @@
 
 namespace dcb {
 
+// dynamic shared memory of the tile-marching kernels (kernels/assembly_tile.cuh)
+size_t tile_smem_bytes(int ns, int tile_x, int tile_y, int dim);
+
 struct PatchSet {
   int comp = 0;
   int npatch = 0;
@@ -59,6 +62,24 @@ class DeviceOperator {
   // scalar diagonal straight into a dof-indexed vector (structured scheme without facet terms);
   // returns false when unsupported -- callers then derive it from block_diag
   bool scalar_diag(double t, double wM, double wA, const double* x, double* diag);
+
+  // ---- tile-marching drivers (kernels/assembly_tile.cuh): owner computes, plain stores, the result is
+  // written (not accumulated), optional fused BiCGSTAB update in front and reductions behind.
+  struct TileFused {
+    int pro = 0, epi = 0, first = 0;
+    double relax = 1.0;
+    const double *r_in = nullptr, *p_in = nullptr, *v_in = nullptr, *dinv = nullptr, *w = nullptr;
+    double *r_out = nullptr, *p_out = nullptr;
+    const double *rho_new = nullptr, *rho = nullptr, *hptr = nullptr, *trtt = nullptr;
+    double* out = nullptr;   // device scalars: out[q] = reduction q for every bit q of out_mask
+    int out_mask = 0;
+  };
+  // structured single-compartment lattices without facet terms whose staged planes fit shared memory
+  bool tile_ready() const { return tile_ok_; }
+  // y = J(x) z  (fused: see TileFused; the direction is then formed from r_in / p_in / v_in / dinv)
+  void tile_apply(double t, double wM, double wA, const double* x, const double* z, double* y, const TileFused* f = nullptr);
+  // r += wM M(x) + wA A(t, x) without atomics
+  void tile_residual(double t, double wM, double wA, const double* x, double* r);
 
   // sparsity pattern on the device (built on first use)
   void ensure_csr();
@@ -156,6 +177,12 @@ class DeviceOperator {
   std::vector<GatherSet> gather_;
   std::string csr_fill_ = "scatter";
   void ensure_gather();
+  bool tile_ok_ = false, tile_residual_ = true;
+  int tile_x_ = 32, tile_y_ = 8, tile_lz_ = 0, tile_minb_ = 2;
+  DeviceBuffer<double> tile_slots_, tile_partials_;
+  la::ReduceWorkspace tile_ws_;
+  void launch_tile(int mode, double t, double wM, double wA, const double* x, const double* z, double* y, const TileFused* f,
+                   bool accumulate);
   int struct_comp_ = -1;   // compartment handled by the structured kernels
   int struct_part_ = 0;    // cell range selector of the next structured launch (jacobian_apply)
   int patch_pn_ = 256, patch_pe_ = 512, patch_threads_ = 256, patch_smem_kb_ = 64;

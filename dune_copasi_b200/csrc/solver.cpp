@@ -31,8 +31,8 @@ LinearSolver::LinearSolver(std::shared_ptr<DeviceOperator> op, const PTree& cfg,
   max_iterations = (int)range.back();
   la::reduce_workspace_create(&ws_);
   const bool gmres = type == "RestartedGMRes";
-  scal_.alloc(gmres ? std::max(16, restart + 2) : 16);
-  hscal_.alloc(gmres ? std::max(16, restart + 2) : 16);
+  scal_.alloc(gmres ? std::max(32, restart + 2) : 32);
+  hscal_.alloc(gmres ? std::max(32, restart + 2) : 32);
   const int nwork = type == "BiCGSTAB" ? 6 : 2;
   for (int k = 0; k < nwork; ++k) work_[k].alloc(op_->ndofs);
   if (type == "BiCGSTAB") {
@@ -61,6 +61,11 @@ LinearSolver::LinearSolver(std::shared_ptr<DeviceOperator> op, const PTree& cfg,
     for (auto& e : halo_ev_) DCB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   if (prec_type == "Jacobi") dinv_.alloc(op_->ndofs);
+  // BiCGSTAB with the vector updates and dot products fused into the tile-marching apply kernels
+  // (kernels/assembly_tile.cuh): matrix free, Jacobi folded, no Dirichlet rows
+  fused_ = type == "BiCGSTAB" && matrix_free && prec_type == "Jacobi" && prec_iterations == 1 && op_->tile_ready() &&
+           op_->ncons == 0 && !overlap_halo_ && cfg.get("b200.fused", true);
+  if (fused_) valt_.alloc(op_->ndofs);
   if (prec_type == "BlockJacobi" || (matrix_free && prec_type == "Jacobi")) bdiag_.alloc(op_->bdiag_size());
 }
 
@@ -106,6 +111,8 @@ void LinearSolver::linearize(double t, double wM, double wA, const double* x) {
       if (prec_type == "Jacobi") { la::block_diag_to_dinv(g.comp_offset[c], nb, bs, bdiag_.p + op_->bdiag_shift(c), dinv_.p, s); op_->stats.launches++; }
     }
   }
+  // the fused sweeps form D^-1 p at ghost vertices themselves: the owners' diagonal entries are needed there
+  if (fused_ && comm_) comm_->halo_update(dinv_.p, s);
   if (prec_type == "BlockJacobi")
     for (int c = 0; c < ncomp; ++c) {
       int bs = op_->model->comp_nspec[c];
@@ -141,6 +148,9 @@ void LinearSolver::apply_operator(const double* v, double* y) {
     DeviceOperator::ProfScope ps(op_.get(), "spmv");
     la::spmv_csr(op_->ndofs, op_->rowptr.p, op_->rowptr32.p, op_->colidx.p, vals.p, v, y, avg, s);
     op_->stats.launches++;
+  } else if (op_->tile_ready()) {
+    // owner-computes sweep: y is written, not accumulated; identity rows included
+    op_->tile_apply(t_, wM_, wA_, x_, v, y);
   } else {
     la::fill(op_->ndofs, 0.0, y, s);   // MatrixFreeAdapter::apply zeroes y first (make_step_operator.hh:70-75)
     op_->stats.launches++;
@@ -260,7 +270,118 @@ void LinearSolver::fetch(int n) {
   DCB_CUDA(cudaStreamSynchronize(s));
 }
 
+// dune-istl BiCGSTABSolver::apply with everything between two operator applications fused into the
+// apply kernels (kernels/assembly_tile.cuh), same operation order as the unfused loop in apply():
+//   A: K1  p' = r + beta (p - omega v); v' = A (w D^-1 p');          <rt, v'>
+//      K2  r~ = r - alpha v';           t  = A (w D^-1 r~);          |r~|^2, <t, r~>, <t, t>
+//   B: K3  x' = x + alpha w D^-1 p' + omega w D^-1 r~;  r = r~ - omega t;   |r|^2, <rt, r>
+// p, v and r are double buffered (a neighbouring tile may still read the old value of a vertex whose
+// owner has already written the new one).  The defect norm of the first half step reaches the host
+// one apply later than in the unfused loop, i.e. K2 of the last iteration may run in vain.
+// Device scalars: s[2] = <rt,v>, s[3] = |r~|^2, s[4..5] = (<t,r~>, <t,t>), pair k at s[8+2k] as in apply().
+SolveResult LinearSolver::apply_bicgstab_fused(double* b, double* x, double rel_tol) {
+  cudaStream_t s = op_->stream;
+  const int64_t n = op_->ndofs;
+  const la::Ranges& own = op_->owned;
+  SolveResult res;
+  auto& L = op_->stats.launches;
+  double *r = b, *rt = work_[0].p, *t = work_[3].p, *ralt = work_[4].p;
+  double* pbuf[2] = {work_[1].p, work_[5].p};
+  double* vbuf[2] = {work_[2].p, valt_.p};
+  int pb = 0, vb = 0;
+  double* sc = scal_.p;
+  auto pair = [&](int it_index) { return sc + 8 + 2 * (it_index & 1); };
+  { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::fill(n, 0.0, x, s); L++; }
+  if (comm_) comm_->halo_update(r, s);   // the sweeps update ghost entries locally from here on
+  { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::copy(n, r, rt, s); L++; }
+  { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, r, r, pair(-1) + 1, ws_, s); L++; }
+  if (comm_) comm_->allreduce_sum(pair(-1) + 1, 1, s);
+  DCB_CUDA(cudaMemcpyAsync(hscal_.p, pair(-1) + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+  { DeviceOperator::HostTimer ht(op_.get(), "host_wait"); DCB_CUDA(cudaStreamSynchronize(s)); }
+  double norm0 = std::sqrt(hscal_.p[0]), norm = norm0;
+  res.defect0 = norm0;
+  if (!(norm0 == norm0)) { res.converged = false; return res; }
+  if (norm0 < 1e-30) { res.converged = true; res.reduction = 0; return res; }
+  double rho = 1, alpha = 1, omega = 1, rho_new = hscal_.p[0];
+  double *x_cur = x, *x_alt = xalt_.p;
+  double* hA = hscal_.p + 16;   // [4 * parity]: <rt,v>, |r~|^2, <t,r~>, <t,t>
+  double* hB = hscal_.p + 24;   // [2 * parity]: |r|^2, <rt,r>
+  auto stage_a = [&](int i) {
+    DeviceOperator::TileFused f;
+    f.pro = 1; f.epi = 1; f.first = i == 0; f.relax = relaxation;
+    f.r_in = r; f.p_in = pbuf[pb]; f.v_in = vbuf[vb]; f.dinv = dinv_.p; f.w = rt; f.p_out = pbuf[pb ^ 1];
+    f.rho_new = pair(i - 1) + 1; f.rho = pair(i - 2) + 1; f.hptr = sc + 2; f.trtt = sc + 4;
+    f.out = sc + 1; f.out_mask = 2;
+    op_->tile_apply(t_, wM_, wA_, x_, nullptr, vbuf[vb ^ 1], &f);
+    pb ^= 1; vb ^= 1;
+    if (comm_) { comm_->allreduce_sum(sc + 2, 1, s); comm_->halo_update(vbuf[vb], s); }
+    DeviceOperator::TileFused g;
+    g.pro = 2; g.epi = 2; g.relax = relaxation;
+    g.r_in = r; g.v_in = vbuf[vb]; g.dinv = dinv_.p; g.r_out = ralt;
+    g.rho = pair(i - 1) + 1; g.hptr = sc + 2;
+    g.out = sc + 3; g.out_mask = 7;
+    op_->tile_apply(t_, wM_, wA_, x_, nullptr, t, &g);
+    if (comm_) { comm_->allreduce_sum(sc + 3, 3, s); comm_->halo_update(t, s); }
+    DCB_CUDA(cudaMemcpyAsync(hA + 4 * (i & 1), sc + 2, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
+    DCB_CUDA(cudaEventRecord(ev_[0], s));
+  };
+  auto stage_b = [&](int i, const double* xin, double* xout) {
+    { DeviceOperator::ProfScope ps(op_.get(), "blas1");
+      la::bicg_final_fold(n, own, pair(i - 1) + 1, sc + 2, sc + 4, dinv_.p, relaxation, pbuf[pb], ralt, xin, xout, t, r, rt,
+                          pair(i), ws_, s); L++; }
+    if (comm_) comm_->allreduce_sum(pair(i), 2, s);
+    DCB_CUDA(cudaMemcpyAsync(hB + 2 * (i & 1), pair(i), sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
+    DCB_CUDA(cudaEventRecord(ev_[1], s));
+  };
+  auto speculate = [&](double known_norm) { return speculation && known_norm >= 100.0 * rel_tol * norm0; };
+  double it = 0.5;
+  bool pending = false;
+  int i = 0;
+  bool queued = false;
+  for (; it < max_iterations; it += 0.5, ++i) {
+    if (std::fabs(rho) <= 1e-80 || std::fabs(omega) <= 1e-80) break;   // breakdown (SolverAbort)
+    if (!queued) stage_a(i);
+    queued = false;
+    const bool ahead = speculate(norm);
+    if (ahead) stage_b(i, x_cur, x_alt);                  // speculative
+    { DeviceOperator::HostTimer ht(op_.get(), "host_wait"); DCB_CUDA(cudaEventSynchronize(ev_[0])); }
+    pending = true;
+    const double* a4 = hA + 4 * (i & 1);
+    const double h = a4[0];
+    alpha = rho_new / h;
+    norm = std::sqrt(a4[1]);
+    res.half_iterations++;
+    if (std::fabs(h) < 1e-80 || !(norm == norm)) break;
+    if (norm < rel_tol * norm0 || norm < 1e-30) { res.converged = true; break; }
+    it += 0.5;
+    if (!ahead) stage_b(i, x_cur, x_alt);
+    if (it + 0.5 < max_iterations && speculate(norm)) { stage_a(i + 1); queued = true; }   // speculative
+    { DeviceOperator::HostTimer ht(op_.get(), "host_wait"); DCB_CUDA(cudaEventSynchronize(ev_[1])); }
+    pending = false;
+    std::swap(x_cur, x_alt);
+    const double* b2 = hB + 2 * (i & 1);
+    omega = a4[2] / a4[3];
+    rho = rho_new;
+    rho_new = b2[1];
+    norm = std::sqrt(b2[0]);
+    res.half_iterations++;
+    if (!(norm == norm)) break;
+    if (norm < rel_tol * norm0 || norm < 1e-30) { res.converged = true; break; }
+  }
+  if (pending) {
+    // x += alpha w D^-1 p of the first half step (the speculative second half, if any, wrote x_alt only)
+    DeviceOperator::ProfScope ps(op_.get(), "blas1");
+    la::bicg_x_half(n, pair(i - 1) + 1, sc + 2, dinv_.p, relaxation, pbuf[pb], x_cur, s); L++;
+  }
+  if (x_cur != x) { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::copy(n, x_cur, x, s); L++; }
+  res.iterations = (int)std::ceil(std::min<double>(it, max_iterations));
+  res.reduction = norm / norm0;
+  if (comm_) comm_->halo_update(x, s);
+  return res;
+}
+
 SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
+  if (fused_) return apply_bicgstab_fused(b, x, rel_tol);
   cudaStream_t s = op_->stream;
   const int64_t n = op_->ndofs;
   const la::Ranges& own = op_->owned;

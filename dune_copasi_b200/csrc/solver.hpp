@@ -40,6 +40,8 @@ class LinearSolver {
   SolveResult apply(double* b, double* z, double rel_tol);
   // y = J v with the current linearisation
   void apply_operator(const double* v, double* y);
+  // BiCGSTAB with its vector updates and dot products fused into the tile-marching apply kernels
+  bool is_fused() const { return fused_; }
 
   bool matrix_free = false;
   std::string type, prec_type;
@@ -57,6 +59,9 @@ class LinearSolver {
   void precondition(const double* d, double* v);
   void precondition_sweep(const double* d, double* v);   // one sweep from v = 0
   void fetch(int n);
+  SolveResult apply_bicgstab_fused(double* b, double* z, double rel_tol);
+  bool fused_ = false;
+  DeviceBuffer<double> valt_;
   void fetch_slots(int first, int count, int total);
   std::shared_ptr<DeviceOperator> op_;
   Communicator* comm_;

@@ -107,12 +107,16 @@ const char* dcb_model_species_name(const dcb_model*, int species);
 int dcb_model_species_compartment(const dcb_model*, int species);
 /* generated CUDA translation unit (model functions + kernels); owned by the model */
 const char* dcb_model_cuda_source(dcb_model*);
+/* the translation unit of one kernel group as the run-time compiler sees it (csrc/jit.hpp JitGroup:
+ * 0 all, 1 patch, 2 element, 3 CSR fill, 4 facets, 5 structured, 6 structured Q1, 7 tile, 8 tile Q1) */
+const char* dcb_model_cuda_source_group(dcb_model*, int group);
 /* NVRTC-compile the model kernels for sm_100a (no GPU needed). kind 0: cubin, 1: PTX.
  * Returns the byte count and copies at most cap bytes; <0 on error. */
 int64_t dcb_model_compile(dcb_model*, int kind, char* out, size_t cap);
 
 /* compile every kernel group of the model into the on-disk JIT cache (no GPU needed) */
 int dcb_model_precompile(dcb_model*);
+int dcb_model_precompile_group(dcb_model*, int group);   /* one kernel group, numbered as above */
 
 /* ---- binding a model to a mesh: compartments, facets, DOF map, sparsity pattern (host) ---- */
 int dcb_grid_bind(dcb_grid*, const dcb_model*);
@@ -151,6 +155,8 @@ int dcb_jacobian_apply(dcb_operator*, double time, double wM, double wA, const d
 int dcb_block_diagonal(dcb_operator*, double time, double wM, double wA, const double* x, double* bdiag,
                        int64_t cap);
 /* device-pointer entry points (accumulate into r / y / vals) */
+/* 1 when residual / Jacobian apply run on the tile-marching (owner computes, atomic free) kernels (diagnostic) */
+int dcb_operator_uses_tiles(const dcb_operator*);
 int dcb_residual_dev(dcb_operator*, double time, double wM, double wA, const double* x, double* r);
 int dcb_jacobian_dev(dcb_operator*, double time, double wM, double wA, const double* x, double* vals);
 int dcb_jacobian_apply_dev(dcb_operator*, double time, double wM, double wA, const double* x,
@@ -162,6 +168,8 @@ void dcb_solver_destroy(dcb_solver*);
 int dcb_solver_linearize(dcb_solver*, double time, double wM, double wA, const double* x_host);
 int dcb_solver_solve(dcb_solver*, const double* b_host, double* z_host, double rel_tol, dcb_solve_result*);
 int dcb_solver_apply_operator(dcb_solver*, const double* v_host, double* y_host);
+/* 1 when the solve runs as BiCGSTAB fused into the tile-marching apply kernels (diagnostic) */
+int dcb_solver_is_fused(const dcb_solver*);
 
 /* ---- time stepping (config = the whole ini; uses model.time_step_operator.*) ---- */
 dcb_stepper* dcb_stepper_create(dcb_operator*, const dcb_config*, dcb_comm*);

@@ -587,6 +587,25 @@ CASES = {
 }
 
 
+def _p1(name, ini, dim, cells, origin, extent, **kw):
+    return Case(name, ini, dim, _s(dim, cells, origin, extent), structured=(cells, origin, extent), **kw)
+
+
+# P1 lattices that a transposed index decode or swapped per-axis weights cannot survive: different
+# cell counts and different mesh widths per axis; the "wide" ones span several tiles of the
+# tile-marching kernels along x
+ANISO_CASES = {
+    "grayscott3d_aniso": _p1("grayscott3d_aniso", GRAY_SCOTT, 3, [10, 9, 8], [0, 0, 0], [1, 0.9, 0.8], dt=1.0),
+    "gauss3d_aniso": _p1("gauss3d_aniso", GAUSS + REDUCE["gauss"], 3, [8, 6, 7], [-1, -1, -1], [2, 1.8, 2.2], t0=1.0),
+    "grayscott2d_aniso": _p1("grayscott2d_aniso", GRAY_SCOTT, 2, [24, 20], [0, 0], [1, 0.8], dt=1.0),
+    "poisson_aniso": _p1("poisson_aniso", POISSON + REDUCE["poisson"], 2, [14, 18], [0, 0], [1, 1.2]),
+    "grayscott3d_wide": _p1("grayscott3d_wide", GRAY_SCOTT, 3, [40, 5, 7], [0, 0, 0], [2, 0.3, 0.4], dt=1.0),
+    "grayscott2d_wide": _p1("grayscott2d_wide", GRAY_SCOTT, 2, [70, 9], [0, 0], [2, 0.3], dt=1.0),
+    "advection3d_aniso": _p1("advection3d_aniso", ADVECTION, 3, [5, 4, 6], [0, 0, 0], [1, 0.7, 1.3], dt=0.05),
+}
+CASES.update(ANISO_CASES)
+
+
 def _q1(name, ini, dim, cells, origin, extent, **kw):
     return Case(name, ini, dim, _s(dim, cells, origin, extent, "cube"), structured=(cells, origin, extent),
                 element="cube", **kw)
