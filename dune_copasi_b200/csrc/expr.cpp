@@ -1,5 +1,7 @@
 #include "expr.hpp"
 
+#include <algorithm>
+
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -388,6 +390,14 @@ NodeP parse_expr(const std::string& text) {
 
 NodeP resolve_expr(const NodeP& ast, const ParserContext& ctx) { return resolve_rec(ast, ctx, 0); }
 
+NodeP make_node(Op op, std::vector<NodeP> kids) { return mk(op, std::move(kids)); }
+NodeP make_var(const std::string& name) {
+  auto n = std::make_shared<Node>();
+  n->op = Op::Var;
+  n->name = name;
+  return n;
+}
+
 bool is_constant(const NodeP& ast, double* value) {
   if (ast->op != Op::Num) return false;
   if (value) *value = ast->num;
@@ -498,6 +508,105 @@ static std::string cond_text(const NodeP& a, const std::function<std::string(con
   (void)is_cmp;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// polynomial normal form
+namespace {
+using Mono = std::vector<int>;
+using Poly = std::map<Mono, double>;
+
+struct PolyBuilder {
+  std::vector<NodeP>& atoms;
+  std::map<std::string, int> index;   // text of the sub-expression -> atom id
+  size_t max_terms, max_degree;
+
+  int atom(const NodeP& a) {
+    const std::string key = to_text(a);
+    auto it = index.find(key);
+    if (it != index.end()) return it->second;
+    atoms.push_back(a);
+    return index[key] = (int)atoms.size() - 1;
+  }
+  static void add(Poly& p, const Mono& m, double c) {
+    if (c == 0.0) return;
+    double& v = p[m];
+    v += c;
+    if (v == 0.0) p.erase(m);
+  }
+  bool mul(const Poly& a, const Poly& b, Poly& out) {
+    out.clear();
+    for (auto& ta : a)
+      for (auto& tb : b) {
+        Mono m(ta.first);
+        m.insert(m.end(), tb.first.begin(), tb.first.end());
+        std::sort(m.begin(), m.end());
+        if (m.size() > max_degree) return false;
+        add(out, m, ta.second * tb.second);
+        if (out.size() > max_terms) return false;
+      }
+    return true;
+  }
+  bool build(const NodeP& a, Poly& out) {
+    out.clear();
+    switch (a->op) {
+      case Op::Num: add(out, {}, a->num); return true;
+      case Op::Neg: {
+        Poly p;
+        if (!build(a->kids[0], p)) return false;
+        for (auto& t : p) add(out, t.first, -t.second);
+        return true;
+      }
+      case Op::Add: case Op::Sub: {
+        Poly p, q;
+        if (!build(a->kids[0], p) || !build(a->kids[1], q)) return false;
+        out = p;
+        for (auto& t : q) add(out, t.first, a->op == Op::Add ? t.second : -t.second);
+        return out.size() <= max_terms;
+      }
+      case Op::Mul: {
+        Poly p, q;
+        return build(a->kids[0], p) && build(a->kids[1], q) && mul(p, q, out);
+      }
+      case Op::Div: {
+        double d;
+        if (!is_constant(a->kids[1], &d) || d == 0.0) break;
+        Poly p;
+        if (!build(a->kids[0], p)) return false;
+        for (auto& t : p) add(out, t.first, t.second / d);
+        return true;
+      }
+      case Op::Pow: {
+        double e;
+        if (!is_constant(a->kids[1], &e) || e != std::floor(e) || e < 0 || e > (double)max_degree) break;
+        Poly base, acc, tmp;
+        if (!build(a->kids[0], base)) return false;
+        add(acc, {}, 1.0);
+        for (int i = 0; i < (int)e; ++i) {
+          if (!mul(acc, base, tmp)) return false;
+          acc = tmp;
+        }
+        out = acc;
+        return true;
+      }
+      default: break;
+    }
+    add(out, {atom(a)}, 1.0);   // anything else is one opaque factor
+    return true;
+  }
+};
+}  // namespace
+
+bool expand_polynomials(const std::vector<NodeP>& exprs, PolyForm& out, size_t max_terms, size_t max_degree) {
+  out.atoms.clear();
+  out.polys.clear();
+  PolyBuilder b{out.atoms, {}, max_terms, max_degree};
+  for (auto& e : exprs) {
+    Poly p;
+    if (!b.build(e, p)) return false;
+    out.polys.push_back(std::move(p));
+  }
+  return true;
+}
 
 // ------------------------------------------------------------------------------------------------
 // symbolic differentiation

@@ -46,6 +46,9 @@ ParserContext::Fn parse_function_expression(const std::string& text, const std::
 bool expr_is_absent(const std::string& text);
 
 NodeP parse_expr(const std::string& text);
+// tree construction for callers that combine parsed expressions
+NodeP make_node(Op op, std::vector<NodeP> kids);
+NodeP make_var(const std::string& name);
 // inline context constants/functions, fold constants
 NodeP resolve_expr(const NodeP& ast, const ParserContext& ctx);
 bool is_constant(const NodeP& ast, double* value = nullptr);
@@ -63,6 +66,19 @@ std::string to_text(const NodeP& ast);
 
 // host evaluation; `lookup` maps a variable name to its value (throws for unknown names)
 double eval_expr(const NodeP& ast, const std::function<double(const std::string&)>& lookup);
+
+// Polynomial normal form of a set of expressions over common atoms (variables and every
+// sub-expression that is not a sum / product / small integer power / division by a constant).  The
+// generated kernels evaluate the reaction terms at every quadrature point of every element and the
+// fp64 pipe is what bounds them: in this form an entry costs one product per distinct monomial
+// (shared by all entries of a function) and one fused multiply-add per term, with the Runge-Kutta
+// weights folded into the coefficients.  Same value up to the rounding of the reassociated products.
+struct PolyForm {
+  std::vector<NodeP> atoms;                                    // atom id -> sub-expression
+  std::vector<std::map<std::vector<int>, double>> polys;       // per expression: monomial (sorted atom ids) -> coefficient
+};
+// false when an expansion exceeds max_terms terms or max_degree factors (callers then emit the tree as it is)
+bool expand_polynomials(const std::vector<NodeP>& exprs, PolyForm& out, size_t max_terms = 24, size_t max_degree = 6);
 
 // CUDA C text; `symbol` maps a variable name to a C expression (returns "" for unknown -> error)
 std::string to_cuda(const NodeP& ast, const std::function<std::string(const std::string&)>& symbol);

@@ -137,14 +137,14 @@ std::string jit_defines(const Model& model) {
   // measured 16 % faster than 4 on B200 despite the spills (profiles/r01_csr_fill_128_ncu.txt)
   int cminb = acfg.get("csr_min_blocks", 8);
   if (cminb < 1 || cminb > 16) fail("model.assembly.b200.csr_min_blocks out of range");
-  // tile-marching drivers: 32 x tile_y cells per CTA in 3-D (one warp per row), tile_x2 cells in 2-D
+  // tile-marching drivers: 32 x (tile_w * tile_r) cells per CTA in 3-D (tile_w warps, tile_r cell rows each)
   int ns_max = 1;
   for (int c = 0; c < model.ncomp(); ++c) ns_max = std::max(ns_max, model.comp_nspec[c]);
-  int ty = acfg.get("tile_y", ns_max <= 4 ? 4 : 2), tx2 = acfg.get("tile_x2", 128);
+  int tw = acfg.get("tile_w", 4), tr = acfg.get("tile_r", 1);
   int tminb = acfg.get("tile_min_blocks", ns_max <= 2 ? 3 : ns_max <= 4 ? 2 : 1);
-  if (ty < 1 || ty > 32 || tx2 < 32 || tx2 > 1024 || tx2 % 32) fail("model.assembly.b200.tile_y / tile_x2 out of range");
-  if (tminb < 1 || tminb > 8) fail("model.assembly.b200.tile_min_blocks out of range");
-  return "#define DC_TILE_X (DC_DIM == 3 ? 32 : " + std::to_string(tx2) + ")\n#define DC_TILE_Y " + std::to_string(ty) +
+  if (tw < 1 || tw > 32 || tr < 1 || tr > 16) fail("model.assembly.b200.tile_w / tile_r out of range");
+  if (tminb < 1 || tminb > 16) fail("model.assembly.b200.tile_min_blocks out of range");
+  return "#define DC_TILE_W " + std::to_string(tw) + "\n#define DC_TILE_R " + std::to_string(tr) +
          "\n#define DC_TILE_MINB " + std::to_string(tminb) + "\n#define DC_CSR_MINB " + std::to_string(cminb) + "\n#define DC_PATCH_THREADS " + std::to_string(th) + "\n#define DC_PATCH_MINB " + std::to_string(minb) +
          "\n#define DC_STRUCT_THREADS " + std::to_string(sth) + "\n#define DC_STRUCT_MINB " + std::to_string(sminb) + "\n";
 }

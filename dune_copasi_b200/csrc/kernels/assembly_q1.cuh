@@ -117,7 +117,7 @@ struct DqGeo {
 __device__ __forceinline__ void dq_setup(const DcStructArgs& a, const int* idx, DqGeo& g, DcCtx& c) {
   g.adet = 1.0;
 #pragma unroll
-  for (int k = 0; k < DC_DIM; ++k) { g.adet *= a.h[k]; g.rh[k] = 1.0 / a.h[k]; }
+  for (int k = 0; k < DC_DIM; ++k) { g.adet *= a.h[k]; g.rh[k] = a.rh[k]; }
 #pragma unroll
   for (int k = 0; k < DC_DIM; ++k) g.wk[k] = g.adet * g.rh[k] * g.rh[k];
   g.f = g.adet / DQ_NC;   // weight 2^-d per point times |det| = |cell|

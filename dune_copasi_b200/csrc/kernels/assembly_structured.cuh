@@ -97,7 +97,7 @@ __device__ __forceinline__ void dc_struct_cell(const DcStructArgs& a, const int*
     for (int s = 0; s < NV; ++s) acc[m][s] = 0.0;
   double adet = 1.0, rh[DC_DIM];
 #pragma unroll
-  for (int k = 0; k < DC_DIM; ++k) { adet *= a.h[k]; rh[k] = 1.0 / a.h[k]; }
+  for (int k = 0; k < DC_DIM; ++k) { adet *= a.h[k]; rh[k] = a.rh[k]; }
   const double f = DC_QW * adet, vol = adet / DC_FACT;
   const double ABf = DC_PAB * f, Bf = DC_PB * f;
   DcCtx c;

@@ -53,6 +53,7 @@ struct DcPatchArgs {
 struct DcStructArgs {
   int n[3];                    // cells per axis of the (local) box
   double h[3], origin[3];
+  double rh[3];                // 1 / h (the host divides once)
   long long cell_begin;        // this launch covers the cells [cell_begin, ncells)
   long long ncells;
   int march;                   // marching kernels: cells a thread walks along the last axis

@@ -550,8 +550,9 @@ inline void check_launch() { DCB_CUDA(cudaGetLastError()); }
 
 }  // namespace
 
-void reduce_workspace_create(ReduceWorkspace* w) {
-  DCB_CUDA(cudaMalloc(&w->partials, sizeof(double) * kMaxBlocks * 4));
+void reduce_workspace_create(ReduceWorkspace* w, int max_blocks) {
+  w->max_blocks = max_blocks;
+  DCB_CUDA(cudaMalloc(&w->partials, sizeof(double) * max_blocks * 4));
   DCB_CUDA(cudaMalloc(&w->counter, sizeof(unsigned)));
   DCB_CUDA(cudaMemset(w->counter, 0, sizeof(unsigned)));
 }
@@ -732,7 +733,9 @@ void tile_fixup(const TileFixup& f, const ReduceWorkspace& w, cudaStream_t s) {
   const long long ncx = f.n[0] > 0 ? (f.n[0] - 1) / f.tile[0] : 0, ncy = f.n[1] > 0 ? (f.n[1] - 1) / f.tile[1] : 0,
                   ncz = f.n[2] > 0 ? (f.n[2] - 1) / f.tile[2] : 0;
   const long long total = ncx * P1 * P2 + ncy * P0 * P2 + ncz * P0 * P1;
-  k_tile_fixup<<<grid_for(total), kThreads, 0, s>>>(f, w.partials, w.counter);
+  // latency bound gathers: one vertex per thread as long as the partials buffer allows
+  const long long blocks = std::max<long long>(1, std::min<long long>((total + kThreads - 1) / kThreads, w.max_blocks));
+  k_tile_fixup<<<(unsigned)blocks, kThreads, 0, s>>>(f, w.partials, w.counter);
   check_launch();
 }
 void bicg_x_half(int64_t n, const double* rho, const double* hptr, const double* dinv, double relax, const double* p,

@@ -13,8 +13,9 @@ namespace la {
 // Deterministic grid reductions: every reducing kernel runs on a fixed grid and writes its result
 // through a "last block sums the partials in order" epilogue.
 struct ReduceWorkspace {
-  double* partials = nullptr;   // [kMaxBlocks * 4]
+  double* partials = nullptr;   // [max_blocks * 4]
   unsigned* counter = nullptr;  // self-resetting ticket
+  int max_blocks = 0;
 };
 constexpr int kMaxBlocks = 148 * 8;
 // dofs that enter global reductions (multi-GPU: the owned dofs; one range per compartment)
@@ -23,7 +24,7 @@ struct Ranges {
   long long b[8], e[8];
   static Ranges all(long long len) { Ranges r; r.n = 1; r.b[0] = 0; r.e[0] = len; return r; }
 };
-void reduce_workspace_create(ReduceWorkspace* w);
+void reduce_workspace_create(ReduceWorkspace* w, int max_blocks = kMaxBlocks);
 void reduce_workspace_destroy(ReduceWorkspace* w);
 
 // y = A x (CSR, sorted columns); rowptr32 != null selects 32-bit row pointers

@@ -312,6 +312,68 @@ static bool depends_on_point(const NodeP& ast) {
 
 
 
+namespace {
+// One point function of the generated kernels: lhs = wA * a + wM * m for every entry, in polynomial
+// normal form over common atoms (see expand_polynomials).  Returns false when an expression does
+// not expand within the limits; nothing has been written then.
+struct WeightedEntry { std::string lhs; NodeP a, m; };
+
+bool emit_polynomial_entries(std::ostream& o, const std::vector<WeightedEntry>& entries,
+                             const std::function<std::string(const std::string&)>& sym) {
+  std::vector<NodeP> exprs;
+  for (auto& e : entries) {
+    if (e.a) exprs.push_back(e.a);
+    if (e.m) exprs.push_back(e.m);
+  }
+  PolyForm pf;
+  if (!expand_polynomials(exprs, pf)) return false;
+  std::ostringstream out;
+  char buf[64];
+  auto lit = [&](double v) { snprintf(buf, sizeof buf, "%.17g", v); std::string t = buf;
+                             if (t.find_first_of(".eEn") == std::string::npos) t += ".0"; return t; };
+  for (size_t k = 0; k < pf.atoms.size(); ++k) out << "    const double q" << k << " = " << to_cuda(pf.atoms[k], sym) << ";\n";
+  // products: every monomial of degree >= 2 and its prefixes, shortest first
+  std::map<std::vector<int>, std::string> name;
+  std::vector<std::vector<int>> order;
+  std::function<void(const std::vector<int>&)> need = [&](const std::vector<int>& m) {
+    if (m.size() < 2 || name.count(m)) return;
+    std::vector<int> prefix(m.begin(), m.end() - 1);
+    need(prefix);
+    name[m] = "m" + std::to_string(order.size());
+    order.push_back(m);
+  };
+  for (auto& p : pf.polys)
+    for (auto& t : p) need(t.first);
+  auto mono_name = [&](const std::vector<int>& m) { return m.size() == 1 ? "q" + std::to_string(m[0]) : name.at(m); };
+  for (auto& m : order) {
+    std::vector<int> prefix(m.begin(), m.end() - 1);
+    out << "    const double " << name[m] << " = " << mono_name(prefix) << " * q" << m.back() << ";\n";
+  }
+  size_t at = 0;
+  for (auto& e : entries) {
+    // coefficient of a monomial: the weighted sum over the two forms, e.g. (wA * 0.042 + wM)
+    std::map<std::vector<int>, std::string> coef;
+    auto take = [&](const std::map<std::vector<int>, double>& p, const char* wname) {
+      for (auto& t : p) {
+        const std::string c = t.second == 1.0 ? std::string(wname) : t.second == -1.0 ? "-" + std::string(wname)
+                                                                                      : std::string(wname) + " * " + lit(t.second);
+        std::string& dst = coef[t.first];
+        dst += (dst.empty() ? "" : " + ") + c;
+      }
+    };
+    if (e.a) take(pf.polys[at++], "wA");
+    if (e.m) take(pf.polys[at++], "wM");
+    if (coef.empty()) { out << "    " << e.lhs << " = 0.0;\n"; continue; }
+    std::string text;
+    for (auto& kv : coef)
+      text += (text.empty() ? "" : " + ") + ("(" + kv.second + ")") + (kv.first.empty() ? "" : " * " + mono_name(kv.first));
+    out << "    " << e.lhs << " = " << text << ";\n";
+  }
+  o << out.str();
+  return true;
+}
+}  // namespace
+
 std::string Model::cuda_source() const {
   std::ostringstream o;
   o << "// generated by dune_copasi_b200 Model::cuda_source()\n";
@@ -383,14 +445,28 @@ std::string Model::cuda_source() const {
     // ---- scalar part of the residual at a point
     o << "  // sc[i] = wA*(-R_i) + wM*(u_i*storage_i)   (local_operator.hh:479-480)\n";
     o << "  __device__ __forceinline__ static void scalar(const DcCtx& c, const double* u, const double (*g)[DC_DIM], double wM, double wA, double* sc) {\n";
-    for (int i = 0; i < ns; ++i) {
-      const Term* r = find(Term::Reaction, g0 + i);
-      const Term* s = find(Term::Storage, g0 + i);
-      o << "    sc[" << i << "] = ";
-      if (!r && !s) o << "0.0";
-      if (r) o << "wA * (-(" << code(*r) << "))";
-      if (s) o << (r ? " + " : "") << "wM * (u[" << i << "] * (" << code(*s) << "))";
-      o << ";\n";
+    const bool poly = cfg.sub("model.assembly.b200").get("polynomial_terms", true);
+    {
+      std::vector<WeightedEntry> entries;
+      for (int i = 0; i < ns; ++i) {
+        const Term* r = find(Term::Reaction, g0 + i);
+        const Term* s = find(Term::Storage, g0 + i);
+        WeightedEntry e;
+        e.lhs = "sc[" + std::to_string(i) + "]";
+        if (r) e.a = make_node(Op::Neg, {r->ast});
+        if (s) e.m = make_node(Op::Mul, {make_var(species[g0 + i].name), s->ast});
+        entries.push_back(e);
+      }
+      if (!(poly && emit_polynomial_entries(o, entries, sym)))
+        for (int i = 0; i < ns; ++i) {
+          const Term* r = find(Term::Reaction, g0 + i);
+          const Term* s = find(Term::Storage, g0 + i);
+          o << "    sc[" << i << "] = ";
+          if (!r && !s) o << "0.0";
+          if (r) o << "wA * (-(" << code(*r) << "))";
+          if (s) o << (r ? " + " : "") << "wM * (u[" << i << "] * (" << code(*s) << "))";
+          o << ";\n";
+        }
     }
     o << "    (void)c; (void)u; (void)g; (void)wM; (void)wA; (void)sc;\n  }\n";
     // ---- diffusive flux
@@ -422,15 +498,41 @@ std::string Model::cuda_source() const {
          "  //   (local_operator.hh:605-641)\n";
     o << "  __device__ __forceinline__ static void jac_mass(const DcCtx& c, const double* u, const double (*g)[DC_DIM], double wM, double wA, double (*jm)[NS]) {\n";
     o << "    for (int i = 0; i < NS; ++i) for (int j = 0; j < NS; ++j) jm[i][j] = 0.0;\n";
-    for (auto& t : terms) {
-      if (species[t.i].comp != c) continue;
-      int i = species[t.i].local;
-      if (t.kind == Term::ReactionJac && species[t.j].comp == c)
-        o << "    jm[" << i << "][" << species[t.j].local << "] += wA * (-(" << code(t) << "));\n";
-      if (t.kind == Term::Storage)
-        o << "    jm[" << i << "][" << i << "] += wM * (" << code(t) << ");\n";
-      if (t.kind == Term::StorageJac && species[t.j].comp == c)
-        o << "    jm[" << i << "][" << species[t.j].local << "] += wM * ((" << code(t) << ") * u[" << i << "]);\n";
+    {
+      std::map<std::pair<int, int>, WeightedEntry> by_entry;
+      auto sum = [](const NodeP& acc, const NodeP& x) { return acc ? make_node(Op::Add, {acc, x}) : x; };
+      for (auto& t : terms) {
+        if (species[t.i].comp != c) continue;
+        int i = species[t.i].local;
+        if (t.kind == Term::ReactionJac && species[t.j].comp == c) {
+          auto& e = by_entry[{i, species[t.j].local}];
+          e.a = sum(e.a, make_node(Op::Neg, {t.ast}));
+        }
+        if (t.kind == Term::Storage) {
+          auto& e = by_entry[{i, i}];
+          e.m = sum(e.m, t.ast);
+        }
+        if (t.kind == Term::StorageJac && species[t.j].comp == c) {
+          auto& e = by_entry[{i, species[t.j].local}];
+          e.m = sum(e.m, make_node(Op::Mul, {t.ast, make_var(species[t.i].name)}));
+        }
+      }
+      std::vector<WeightedEntry> entries;
+      for (auto& kv : by_entry) {
+        kv.second.lhs = "jm[" + std::to_string(kv.first.first) + "][" + std::to_string(kv.first.second) + "]";
+        entries.push_back(kv.second);
+      }
+      if (!(poly && emit_polynomial_entries(o, entries, sym)))
+        for (auto& t : terms) {
+          if (species[t.i].comp != c) continue;
+          int i = species[t.i].local;
+          if (t.kind == Term::ReactionJac && species[t.j].comp == c)
+            o << "    jm[" << i << "][" << species[t.j].local << "] += wA * (-(" << code(t) << "));\n";
+          if (t.kind == Term::Storage)
+            o << "    jm[" << i << "][" << i << "] += wM * (" << code(t) << ");\n";
+          if (t.kind == Term::StorageJac && species[t.j].comp == c)
+            o << "    jm[" << i << "][" << species[t.j].local << "] += wM * ((" << code(t) << ") * u[" << i << "]);\n";
+        }
     }
     o << "    (void)c; (void)u; (void)g; (void)wM; (void)wA;\n  }\n";
     o << "  // jd[i][j]: coefficient of grad(phi_a).grad(phi_b) = wA*D_ij   (local_operator.hh:674-685)\n";

@@ -98,16 +98,21 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
     const int ns = struct_comp_ >= 0 ? model->comp_nspec[struct_comp_] : 0;
     int ns_max = 1;
     for (int c = 0; c < model->ncomp(); ++c) ns_max = std::max(ns_max, model->comp_nspec[c]);
-    tile_x_ = grid->dim == 3 ? 32 : acfg.get("tile_x2", 128);
-    tile_y_ = grid->dim == 3 ? acfg.get("tile_y", ns_max <= 4 ? 4 : 2) : 1;
+    tile_w_ = grid->dim == 3 ? acfg.get("tile_w", 4) : 1;
+    tile_r_ = grid->dim == 3 ? acfg.get("tile_r", 1) : 1;
     tile_minb_ = acfg.get("tile_min_blocks", ns_max <= 2 ? 3 : ns_max <= 4 ? 2 : 1);
     tile_lz_ = acfg.get("tile_lz", 0);
     tile_residual_ = acfg.get("tile_residual", true);
-    const bool want = acfg.get("tile", true);
+    // off by default: measured on B200 (256^3 Gray-Scott, profiles/README.md) the tile kernels run the apply at
+    // 56-59 % of the fp64 pipe (two barriers per layer, 12 warps per SM of which a third stage / finish) against
+    // 82 % for the per-cell kernels -- 1.17 ms against 0.84 ms per launch --, which the saved BLAS-1 sweeps
+    // (31 -> 11 ms per step) do not win back: 109 against 98.5 ms per time step
+    const bool want = acfg.get("tile", false);
     tile_ok_ = want && scheme == "structured" && struct_comp_ >= 0 && !model->has_outflow() &&
                !(model->numerical_jacobian || model->has_extended_terms(struct_comp_)) &&
-               tile_smem_bytes(ns, tile_x_, tile_y_, grid->dim) <= 200 * 1024;
-    if (tile_ok_) la::reduce_workspace_create(&tile_ws_);
+               (ns % 2 != 0 || grid->comp_offset[struct_comp_] % 2 == 0) &&
+               tile_smem_bytes(ns, tile_w_, tile_r_, grid->dim) <= 200 * 1024;
+    if (tile_ok_) la::reduce_workspace_create(&tile_ws_, 148 * 256);
   }
 
   // ---- kernels for this model
@@ -437,6 +442,7 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       for (int k = 0; k < 3; ++k) {
         a.n[k] = k < grid->dim ? grid->s_cells[k] : 1;
         a.h[k] = grid->s_h[k];
+        a.rh[k] = 1.0 / grid->s_h[k];
         a.origin[k] = grid->s_origin[k];
         a.ncells *= a.n[k];
       }
@@ -578,9 +584,19 @@ void DeviceOperator::launch_facets(const char* kind, double t, double wA, const 
 }
 
 // ---------------------------------------------------------------------------------- tile marching
-size_t tile_smem_bytes(int ns, int tile_x, int tile_y, int dim) {
-  const size_t plane = (size_t)(tile_x + 1) * (dim == 3 ? tile_y + 1 : 1);
-  return (size_t)(3 * 3 + 1 + 2 * 4) * ns * plane * sizeof(double);   // ring, result plane, raw operand planes
+size_t tile_smem_bytes(int ns, int tile_w, int tile_r, int dim) {
+  // 14 planes of 33 x (rows + 1) vertices (3 u, 3 direction, 2 epilogue operand, 4 raw, 2 accumulators) + spill rows
+  const size_t rows = dim == 3 ? (size_t)tile_w * tile_r + 1 : 1, w = dim == 3 ? tile_w : 1;
+  return (14 * 33 * rows + 2 * w * 33) * ns * sizeof(double);
+}
+
+// vectors of the tile kernels move as 16-byte accesses when the species count is even
+bool DeviceOperator::tile_aligned(std::initializer_list<const void*> ptrs) const {
+  if (!tile_ok_) return false;
+  if (model->comp_nspec[struct_comp_] % 2 != 0) return true;
+  for (const void* p : ptrs)
+    if (reinterpret_cast<uintptr_t>(p) & 15u) return false;
+  return true;
 }
 
 void DeviceOperator::launch_tile(int mode, double t, double wM, double wA, const double* x, const double* z, double* y,
@@ -595,12 +611,14 @@ void DeviceOperator::launch_tile(int mode, double t, double wM, double wA, const
   for (int k = 0; k < 3; ++k) {
     a.n[k] = k < dim ? grid->s_cells[k] : 1;
     a.h[k] = grid->s_h[k];
+    a.rh[k] = 1.0 / grid->s_h[k];
     a.origin[k] = grid->s_origin[k];
     a.ncells *= a.n[k];
   }
   a.dof_offset = (int)grid->comp_offset[c];
   a.time = t; a.wM = wM; a.wA = wA; a.x = x; a.z = z; a.r = y;
   a.cmask = cmask.p;
+  const int tile_x_ = 32, tile_y_ = tile_w_ * tile_r_;
   A.ntx = (a.n[0] + tile_x_ - 1) / tile_x_;
   A.nty = dim == 3 ? (a.n[1] + tile_y_ - 1) / tile_y_ : 1;
   // chunks along the marching axis: enough CTAs for ~8 waves of 148 SMs x resident CTAs, but chunks
@@ -633,13 +651,15 @@ void DeviceOperator::launch_tile(int mode, double t, double wM, double wA, const
   if (tile_slots_.n < 7 * ndofs) tile_slots_.alloc(7 * ndofs);
   if (tile_partials_.n < (int64_t)nblocks * 4) tile_partials_.alloc((int64_t)nblocks * 4);
   A.slots = tile_slots_.p; A.slot_stride = ndofs; A.partials = tile_partials_.p;
-  const size_t smem = tile_smem_bytes(ns, tile_x_, tile_y_, dim);
+  const size_t smem = tile_smem_bytes(ns, tile_w_, tile_r_, dim);
+  if (!tile_aligned({x, z, y, A.r_in, A.p_in, A.v_in, A.dinv, A.w, A.r_out, A.p_out}))
+    fail("tile-marching kernels: vectors of an even number of species must be 16-byte aligned");
   const std::string kname = std::string("dc_k_tile_") + (q1 ? "q1_" : "") + (mode == 0 ? "residual_" : "apply_") + std::to_string(c);
   cudaKernel_t k = kernel(q1 ? JitGroup::TileQ1 : JitGroup::Tile, kname);
   DCB_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     ProfScope ps(this, mode == 0 ? "tile_residual" : "tile_apply");
-    jit_launch(k, nblocks, (unsigned)(tile_x_ * (dim == 3 ? tile_y_ : 1)), smem, stream, A);
+    jit_launch(k, nblocks, (unsigned)(32 * (dim == 3 ? tile_w_ : 1)), smem, stream, A);
     stats.launches++;
   }
   la::TileFixup F{};
@@ -668,7 +688,7 @@ void DeviceOperator::tile_residual(double t, double wM, double wA, const double*
 }
 
 void DeviceOperator::residual(double t, double wM, double wA, const double* x, double* r) {
-  if (tile_ok_ && tile_residual_) { tile_residual(t, wM, wA, x, r); return; }
+  if (tile_residual_ && tile_aligned({x, r})) { tile_residual(t, wM, wA, x, r); return; }
   launch_volume("dc_k_residual_volume_", 0, t, wM, wA, x, nullptr, r, nullptr, nullptr);
   if (wA != 0.0) launch_facets("dc_k_skeleton_residual", t, wA, x, nullptr, r, nullptr, nullptr);
 }
@@ -683,7 +703,7 @@ bool DeviceOperator::can_split_apply() const {
 void DeviceOperator::jacobian_apply(double t, double wM, double wA, const double* x, const double* z, double* y,
                                     int part) {
   if (part != 0 && !can_split_apply()) fail("jacobian_apply: this operator cannot be split into interior / halo layers");
-  if (part == 0 && tile_ok_) { launch_tile(1, t, wM, wA, x, z, y, nullptr, true); return; }   // y += J z
+  if (part == 0 && tile_aligned({x, z, y})) { launch_tile(1, t, wM, wA, x, z, y, nullptr, true); return; }   // y += J z
   struct_part_ = part;
   launch_volume("dc_k_jacobian_apply_volume_", 1, t, wM, wA, x, z, y, nullptr, nullptr);
   struct_part_ = 0;

@@ -7,6 +7,7 @@
 // (CSR) or a matrix-free apply.
 #pragma once
 #include <chrono>
+#include <initializer_list>
 #include <map>
 #include <memory>
 #include <vector>
@@ -20,7 +21,7 @@
 namespace dcb {
 
 // dynamic shared memory of the tile-marching kernels (kernels/assembly_tile.cuh)
-size_t tile_smem_bytes(int ns, int tile_x, int tile_y, int dim);
+size_t tile_smem_bytes(int ns, int tile_w, int tile_r, int dim);
 
 struct PatchSet {
   int comp = 0;
@@ -76,6 +77,8 @@ class DeviceOperator {
   };
   // structured single-compartment lattices without facet terms whose staged planes fit shared memory
   bool tile_ready() const { return tile_ok_; }
+  // ... and whose vectors the kernels can move with 16-byte accesses (even species counts)
+  bool tile_aligned(std::initializer_list<const void*> ptrs) const;
   // y = J(x) z  (fused: see TileFused; the direction is then formed from r_in / p_in / v_in / dinv)
   void tile_apply(double t, double wM, double wA, const double* x, const double* z, double* y, const TileFused* f = nullptr);
   // r += wM M(x) + wA A(t, x) without atomics
@@ -178,7 +181,7 @@ class DeviceOperator {
   std::string csr_fill_ = "scatter";
   void ensure_gather();
   bool tile_ok_ = false, tile_residual_ = true;
-  int tile_x_ = 32, tile_y_ = 8, tile_lz_ = 0, tile_minb_ = 2;
+  int tile_w_ = 4, tile_r_ = 2, tile_lz_ = 0, tile_minb_ = 3;
   DeviceBuffer<double> tile_slots_, tile_partials_;
   la::ReduceWorkspace tile_ws_;
   void launch_tile(int mode, double t, double wM, double wA, const double* x, const double* z, double* y, const TileFused* f,

@@ -148,7 +148,7 @@ void LinearSolver::apply_operator(const double* v, double* y) {
     DeviceOperator::ProfScope ps(op_.get(), "spmv");
     la::spmv_csr(op_->ndofs, op_->rowptr.p, op_->rowptr32.p, op_->colidx.p, vals.p, v, y, avg, s);
     op_->stats.launches++;
-  } else if (op_->tile_ready()) {
+  } else if (op_->tile_aligned({x_, v, y})) {
     // owner-computes sweep: y is written, not accumulated; identity rows included
     op_->tile_apply(t_, wM_, wA_, x_, v, y);
   } else {

@@ -2,8 +2,8 @@
 Jacobian apply with plain stores, slots + fix-up pass for the vertices on tile edges / chunk boundary
 planes, and the BiCGSTAB whose vector updates and dot products are fused into the apply sweeps.
 
-Every case runs with the production tile shape and with deliberately small tiles (2 cell rows, chunks
-of 3 layers, 32 cells along x) so that the small lattices of the suite have cut vertices along every
+Every case runs with the production tile shape and with deliberately small tiles (2 warps of one
+cell row / one warp of 3 rows, chunks of 3 / 2 layers) so that the small lattices of the suite have cut vertices along every
 axis, corners shared by 8 contributors included.  Reference for the numbers: the CPU oracle;
 reference for "nothing changed": the per-cell kernels (model.assembly.b200.tile = false) and the
 unfused BiCGSTAB (linear_solver.b200.fused = false).
@@ -17,9 +17,11 @@ pytestmark = pytest.mark.gpu
 
 OP_TOL = 1e-12
 FIELD_TOL = 1e-10
-SMALL = {"model.assembly.b200.tile_y": 2, "model.assembly.b200.tile_lz": 3, "model.assembly.b200.tile_x2": 32}
-ODD = {"model.assembly.b200.tile_y": 3, "model.assembly.b200.tile_lz": 2, "model.assembly.b200.tile_x2": 64}
+SMALL = {"model.assembly.b200.tile_w": 2, "model.assembly.b200.tile_r": 1, "model.assembly.b200.tile_lz": 3}
+ODD = {"model.assembly.b200.tile_w": 1, "model.assembly.b200.tile_r": 3, "model.assembly.b200.tile_lz": 2}
 SHAPES = {"default": {}, "small": SMALL, "odd": ODD}
+for _s in SHAPES.values():
+    _s["model.assembly.b200.tile"] = "true"     # the tile drivers are an option (off by default, see operator.cpp)
 P1 = ["gauss2d", "gauss3d", "exp", "poisson", "grayscott2d", "grayscott3d", "mitchell_schaefer", "grayscott3d_aniso",
       "gauss3d_aniso", "grayscott2d_aniso", "poisson_aniso", "grayscott3d_wide", "grayscott2d_wide"]
 Q1 = ["gauss2d_q1", "gauss3d_q1", "poisson_q1", "grayscott2d_q1", "grayscott3d_q1", "mitchell_schaefer_q1"]
@@ -75,7 +77,7 @@ def test_tile_residual_and_apply(name, shape):
 def test_tile_equals_per_cell_kernels(name):
     """Same cell integrals behind both drivers: the results differ by the summation order only."""
     case, om, cfg, model, grid, op = make(name, **SMALL)
-    _, _, _, _, _, old = make(name, **{"model.assembly.b200.tile": "false"})
+    _, _, _, _, _, old = make(name)
     assert op.uses_tiles and not old.uses_tiles
     x = K.rand_state(om.ndofs, 44)
     z = K.rand_state(om.ndofs, 45, -1.0, 1.0)

@@ -1,7 +1,4 @@
-# tile kernel: parity tests, launch-shape variants and one ncu --set full capture of the fused apply
 mkdir -p gpurun_out
-( time timeout 1500 python -m pytest tests/test_gpu_tile.py -q -m gpu --tb=short -x ) > gpurun_out/tile_tests.log 2>&1; echo "tile tests rc=$?"
-tail -15 gpurun_out/tile_tests.log
 run() {
   name=$1; shift
   timeout 600 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e --no-q1 "$@" > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err
@@ -14,6 +11,4 @@ except Exception as e:
     print('$name failed', e); print(open('gpurun_out/bench_$name.err').read()[-1500:])
 "
 }
-run default
 for v in "$@"; do run "$(echo $v | tr ',=' '__')" --b200 $v; done
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:dc_k_tile_apply -s 20 -c 1 -o gpurun_out/tile_apply_v3 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-q1 > gpurun_out/ncu_tile.log 2>&1; echo "ncu rc=$?"
