@@ -26,13 +26,10 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "tests")):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
-
-import cases as K  # noqa: E402
 
 METRIC = "DOF-updates/s (3D Gray-Scott, CG-P1 Kuhn tets, implicit time stepping)"
 
@@ -60,8 +57,8 @@ def ini_for(args):
     for kv in filter(None, getattr(args, "set", "").split(",")):
         k, v = kv.split("=")
         over[k] = v
-    case = {"cell": "cell3d", "cell10": "cell3d_10"}.get(getattr(args, "workload", "grayscott"), "grayscott3d")
-    return K.CASES[case].ini_with(**over)
+    from dune_copasi_b200 import workloads as W
+    return W.ini_text(getattr(args, "workload", "grayscott"), **over)
 
 
 def precompile():
@@ -145,6 +142,9 @@ def cpu_baseline(args, steps, warmup, cells):
     """The oracle restatement (kind "port": the reference itself needs a DUNE stack that is not
     available) with OpenMP over all host cores, on a bounded sample of the workload."""
     from oracle import core as ORC, ini as INI, mesh as OMESH
+    # all host cores, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1)
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ORC.lib().orc_set_num_threads(int(ncores))
     cfg = INI.parse_ini(ini_for(args))
     dim = getattr(args, "dim", 3)
     mesh = OMESH.structured(dim, [cells] * dim, element="cube" if getattr(args, "element", "p1") == "q1" else "simplex")
@@ -164,7 +164,8 @@ def cpu_baseline(args, steps, warmup, cells):
     cores = ORC.lib().orc_num_threads()
     return {"value": om.ndofs * steps / wall, "unit": "DOF-updates/s", "cores": int(cores), "kind": "port",
             "sample": f"{steps} steps (after {warmup} warm-up) of the same model on a {cells}^{dim} lattice "
-                      f"({om.ndofs} DOFs), matrix based, OpenMP over {cores} threads",
+                      f"({om.ndofs} DOFs), matrix based (the reference's Jacobi needs the assembled matrix), "
+                      f"OpenMP over {cores} threads (assembly, SpMV, dot products, vector sweeps)",
             "ms_per_step": 1e3 * wall / steps}, om.ndofs, wall
 
 
@@ -176,7 +177,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": metric_name(args), "value": cb["value"], "unit": "DOF-updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args, args.cpu_cells), "cpu_baseline": cb,
+            "config": dict(config_dict(args, args.cpu_cells), matrix_free=False), "dofs": int(ndofs), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "DOF-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -191,7 +192,11 @@ def config_dict(args, cells):
             "collectives": getattr(args, "collectives", "none (1 GPU)"), "dt": args.dt, "rk": args.rk,
             "linear_solver": "BiCGSTAB", "preconditioner": args.prec, "matrix_free": bool(args.matrix_free),
             "linear_rel_tol": 1e-8, "newton_rel_tol": 1e-8, "assembly": args.scheme,
-            "l2": "inputs larger than L2 (every vector and the mesh exceed 126 MB at the default size)"}
+            "l2": "inputs larger than L2 (every vector and the mesh exceed 126 MB at the default size)",
+            "reference_reachability": ("matrix-free + Jacobi is the same operator the reference assembles: its registry "
+                                       "offers Jacobi for the assembled matrix only (solver/istl/factory/preconditioner.hh:"
+                                       "98-104); the matrix-based run of the same model is `assembled_variant`")
+            if args.matrix_free and args.prec == "Jacobi" else "as the reference's registry offers it"}
 
 
 def main():
@@ -205,7 +210,9 @@ def main():
     ap.add_argument("--element", default="p1", choices=["p1", "q1"],
                     help="p1: Kuhn simplices, the reference's element (headline); q1: the lattice cells as Q1 "
                          "elements, BASELINE configs[3]'s wording (not a reference capability, own oracle)")
-    ap.add_argument("--cpu-cells", type=int, default=56, help="lattice of the bounded CPU sample (10-30 s of CPU work)")
+    ap.add_argument("--cpu-cells", type=int, default=72, help="lattice of the bounded CPU sample (10-30 s of CPU work)")
+    ap.add_argument("--no-assembled", action="store_true", help="skip the matrix-based variant that rides along")
+    ap.add_argument("--assembled-cells", type=int, default=160, help="lattice of the matrix-based variant")
     ap.add_argument("--dt", type=float, default=1.0)
     ap.add_argument("--rk", default="Alexander2")
     ap.add_argument("--prec", default="Jacobi")
@@ -302,6 +309,11 @@ def main():
             sampler.start()
         for _ in range(args.warmup):
             assert st.step(args.dt)
+        # the state the timed steps start from: the end-to-end pass below is rewound to it, so that both
+        # passes integrate the same K steps (same Newton / Krylov iteration counts)
+        u_start = torch.empty(op.ndofs, dtype=torch.float64).pin_memory().numpy()
+        st.get_state(u_start)
+        t_start = st.time
         s0 = st.stats()
         D.lib().dcb_operator_profile(op.h, 1)
         sampler.begin()
@@ -315,10 +327,15 @@ def main():
         clocks = sampler.stop() if rank == 0 else None
         e2e = None
         if not args.no_e2e:
+            st.set_state(u_start, t_start)
             ms_e2e = timed(args.steps, True)
+            s2 = st.stats()
             nbytes = op.ndofs * 8
             e2e = {"value": ndofs_global * args.steps / (ms_e2e * 1e-3), "unit": "DOF-updates/s",
-                   "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / args.steps}
+                   "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / args.steps,
+                   "solver_stats": {k: s2[k] - s1[k] for k in s2},
+                   "note": "same K steps as `value` (state rewound), host buffers in pinned memory, "
+                           "H2D of the state before and D2H after every step inside the timed region"}
 
         def shutdown():
             # every rank tears down in the same order: library objects (their NCCL communicator)
@@ -351,6 +368,10 @@ def main():
             "struct_residual": nodes * (16 * 2),
             "struct_apply": nodes * (16 * 2 + 8 * 2),
             "struct_bdiag": nodes * (8 * 2 + 8 * 4),
+            # tile-marching sweeps with the BiCGSTAB updates fused in (mean of the two sweeps of an iteration:
+            # read u, r, p, v, dinv, rt / write p, v = 128 B per vertex; read u, r, v, dinv / write r, t = 96)
+            "tile_apply": nodes * 112,
+            "tile_residual": nodes * (16 * 2 + 8 * 2),
         }
         top = max(prof, key=lambda k: prof[k]["ms"]) if prof else None
         roof = None
@@ -394,10 +415,27 @@ def main():
         qargs = argparse.Namespace(**vars(args))
         qargs.element = "q1"
         q1 = measure(qargs)
+    # the reference-reachable Jacobi configuration: the assembled matrix (CSR fill + SpMV), on the largest
+    # lattice whose matrix set-up fits the bench's time budget; single-GPU runs only
+    asm = None
+    if (args.matrix_free and args.element == "p1" and args.dim == 3 and args.workload == "grayscott" and world == 1
+            and not args.no_assembled):
+        aargs = argparse.Namespace(**vars(args))
+        aargs.matrix_free, aargs.cells = 0, min(args.cells, args.assembled_cells)
+        aargs.steps, aargs.warmup, aargs.no_e2e = min(args.steps, 3), min(args.warmup, 2), True
+        asm = measure(aargs)
     if dist is not None:
         dist.destroy_process_group()
     if rank != 0:
         return
+    if asm is not None:
+        line["assembled_variant"] = {k: asm[k] for k in ("value", "unit", "ms_per_step", "dofs", "steps", "warmup", "gpu_launches",
+                                                         "solver_stats", "setup_s")}
+        line["assembled_variant"]["config"] = asm["config"]
+        if asm["roofline"]:
+            line["assembled_variant"]["roofline"] = {k: asm["roofline"][k] for k in
+                                                     ("kernel", "achieved", "peak", "frac", "avg_launch_ms", "share_of_step",
+                                                      "breakdown_ms_per_step") if k in asm["roofline"]}
     if q1 is not None:
         keep = ("metric", "value", "unit", "ms_per_step", "time_steps_per_s", "dofs", "e2e", "gpu_launches", "clocks",
                 "solver_stats")

@@ -198,6 +198,14 @@ std::string cache_dir() {
 }
 }  // namespace
 
+void jit_cache_evict(const std::string& source) {
+  int major = 0, minor = 0;
+  nvrtcVersion(&major, &minor);
+  char name[64];
+  snprintf(name, sizeof name, "%016llx_%d_%d.cubin", (unsigned long long)fnv1a(source), major, minor);
+  std::remove((cache_dir() + "/" + name).c_str());
+}
+
 std::vector<char> jit_compile_cached(const std::string& source) {
   int major = 0, minor = 0;
   nvrtcVersion(&major, &minor);
@@ -216,11 +224,17 @@ std::vector<char> jit_compile_cached(const std::string& source) {
   std::vector<char> bin = jit_compile(source, &log, false);
   mkdir(dir.c_str(), 0755);
   const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+  bool written = false;
   {
     std::ofstream f(tmp, std::ios::binary);
-    if (f) f.write(bin.data(), (std::streamsize)bin.size());
+    if (f) {
+      f.write(bin.data(), (std::streamsize)bin.size());
+      f.close();
+      written = f.good();
+    }
   }
-  std::rename(tmp.c_str(), path.c_str());   // atomic publish; failures only cost a recompile
+  // atomic publish of a complete file only (a short write -- disk full, quota -- must not become a cache entry)
+  if (!written || std::rename(tmp.c_str(), path.c_str()) != 0) std::remove(tmp.c_str());
   return bin;
 }
 

@@ -23,6 +23,8 @@ std::string jit_source(const Model& model, const std::string& defines = "", JitG
 std::string jit_defines(const Model& model);
 // compile with an on-disk cache next to the library (or $DCB_JIT_CACHE), keyed by source + NVRTC version
 std::vector<char> jit_compile_cached(const std::string& source);
+// drop the cache entry of a source (a cached blob the driver refuses to load is recompiled once)
+void jit_cache_evict(const std::string& source);
 // compile for sm_100a; works without a GPU.  `log` receives the NVRTC log.
 std::vector<char> jit_compile(const std::string& source, std::string* log, bool ptx = false);
 

@@ -646,9 +646,19 @@ __global__ void __launch_bounds__(128) k_sor_level(const int32_t* __restrict__ r
     }
     rhs -= a * v[j];
   }
-  v[i] += relax * (rhs / diag);
+  if (skip_diag) v[i] = rhs / diag;   // dbgs assigns the unrelaxed value; the caller blends with the old iterate
+  else v[i] += relax * (rhs / diag);
+}
+__global__ void __launch_bounds__(kThreads) k_relax_blend(int64_t n, double w, const double* __restrict__ xold,
+                                                          double* __restrict__ x) {
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    x[i] = w * x[i] + (1.0 - w) * xold[i];
 }
 }  // namespace
+void relax_blend(int64_t n, double w, const double* xold, double* x, cudaStream_t s) {
+  k_relax_blend<<<grid_for(n, 2), kThreads, 0, s>>>(n, w, xold, x);
+  check_launch();
+}
 void sor_level(const int32_t* rows, int64_t count, const int64_t* rowptr, const int32_t* colidx, const double* vals,
                const double* d, double* v, double relax, bool skip_diag, cudaStream_t s) {
   if (count <= 0) return;

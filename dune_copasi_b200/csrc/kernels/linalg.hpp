@@ -78,11 +78,14 @@ void fill(int64_t n, double v, double* y, cudaStream_t s);
 // preconditioners
 void jacobi_apply(int64_t n, const double* dinv, double relax, const double* d, double* v, cudaStream_t s);
 // One level of a level-scheduled SOR / Gauss-Seidel sweep (dune-istl bsorf / bsorb / dbgs on scalar
-// entries): for every row i of the level  v_i += relax (d_i - sum_j a_ij v_j) / a_ii, the diagonal
-// term included in the sum unless skip_diag.  Rows of one level are not coupled (structurally
+// entries): for every row i of the level  v_i += relax (d_i - sum_j a_ij v_j) / a_ii with the diagonal term
+// in the sum (bsorf / bsorb), or, with skip_diag (dbgs), v_i = (d_i - sum_{j != i} a_ij v_j) / a_ii -- dbgs
+// relaxes after the sweep: relax_blend.  Rows of one level are not coupled (structurally
 // symmetric pattern), so the result is the sequential sweep's, whatever the order inside the level.
 void sor_level(const int32_t* rows, int64_t count, const int64_t* rowptr, const int32_t* colidx, const double* vals,
                const double* d, double* v, double relax, bool skip_diag, cudaStream_t s);
+// x = w x + (1 - w) xold   (the relaxation step that closes a dbgs sweep)
+void relax_blend(int64_t n, double w, const double* xold, double* x, cudaStream_t s);
 void csr_extract_diag_inv(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* vals,
                           double* dinv, cudaStream_t s);
 // block diagonal of node blocks of size bs over dofs [dof0, dof0 + nblocks*bs): bdiag[dof*bs + j]

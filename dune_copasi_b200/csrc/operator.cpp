@@ -203,7 +203,14 @@ cudaKernel_t DeviceOperator::kernel(JitGroup group, const std::string& name) {
   auto& mod = jit_[(int)group];
   if (!mod) {
     mod = std::make_unique<JitModule>();
-    mod->load(jit_compile_cached(jit_source(*model, jit_defines_, group)));
+    const std::string src = jit_source(*model, jit_defines_, group);
+    try {
+      mod->load(jit_compile_cached(src));
+    } catch (const std::exception&) {
+      // a damaged cache entry: evict, compile again, and let a second failure surface
+      jit_cache_evict(src);
+      mod->load(jit_compile_cached(src));
+    }
   }
   return name.empty() ? nullptr : mod->kernel(name);
 }

@@ -17,7 +17,10 @@ LinearSolver::LinearSolver(std::shared_ptr<DeviceOperator> op, const PTree& cfg,
     fail("linear_solver.type = '", type, "' is not built for the B200 path (available: BiCGSTAB, CG, RestartedGMRes)");
   restart = cfg.get("restart", 40);   // iterative.hh:64
   if (type == "RestartedGMRes" && (restart < 1 || restart > 500)) fail("linear_solver.restart = ", restart, " is out of range [1, 500]");
-  prec_type = cfg.get("preconditioner.type", std::string("Jacobi"));
+  // DUNE_COPASI_DEFAULT_PRECONDITIONER is SSOR (solver/istl/factory/preconditioner.hh:17): an ini without
+  // preconditioner.type gets the reference's choice; where SSOR cannot run here (matrix free, partitioned
+  // grids: checked below) the call fails loudly instead of solving with something else
+  prec_type = cfg.get("preconditioner.type", std::string("SSOR"));
   if (prec_type != "Jacobi" && prec_type != "BlockJacobi" && prec_type != "Richardson" && !sor_family())
     fail("linear_solver.preconditioner.type = '", prec_type,
          "' is not built for the B200 path (available: Richardson, Jacobi, BlockJacobi, SSOR, SOR, GaussSeidel)");
@@ -47,8 +50,9 @@ LinearSolver::LinearSolver(std::shared_ptr<DeviceOperator> op, const PTree& cfg,
     vals.alloc(op_->nnz());
   }
   if (sor_family()) {
-    if (matrix_free) fail("linear_solver.preconditioner.type = ", prec_type, " sweeps over the assembled matrix: set linear_solver.matrix_free = false");
-    if (comm_ && comm_->size > 1) fail("linear_solver.preconditioner.type = ", prec_type, " is a sequential sweep in dof order and is not built for partitioned (multi-GPU) runs");
+    const char* how = cfg.has_key("preconditioner.type") ? "" : " (the reference's default when preconditioner.type is not set)";
+    if (matrix_free) fail("linear_solver.preconditioner.type = ", prec_type, how, " sweeps over the assembled matrix: set linear_solver.matrix_free = false or choose Jacobi / BlockJacobi");
+    if (comm_ && comm_->size > 1) fail("linear_solver.preconditioner.type = ", prec_type, how, " is a sequential sweep in dof order and is not built for partitioned (multi-GPU) runs: choose Jacobi / BlockJacobi");
     build_levels();
   }
   // off by default: measured on 2 x B200 (256^3) the two extra launches for the halo layers cost
@@ -203,11 +207,14 @@ void LinearSolver::sor_apply(const double* d, double* v) {
   const bool skip_diag = prec_type == "GaussSeidel";
   la::fill(op_->ndofs, 0.0, v, s);
   op_->stats.launches++;
+  if (skip_diag && sweep_[0].n < (size_t)op_->ndofs) sweep_[0].alloc(op_->ndofs);
   for (int it = 0; it < prec_iterations; ++it) {
+    if (skip_diag) { la::copy(op_->ndofs, v, sweep_[0].p, s); op_->stats.launches++; }   // dbgs: xold
     for (int l = 0; l < nlev; ++l)
       la::sor_level(level_rows_.p + level_ptr_[l], level_ptr_[l + 1] - level_ptr_[l], rp, op_->colidx.p, vals.p, d, v,
                     relaxation, skip_diag, s);
     op_->stats.launches += nlev;
+    if (skip_diag) { la::relax_blend(op_->ndofs, relaxation, sweep_[0].p, v, s); op_->stats.launches++; }
     if (prec_type != "SSOR") continue;
     for (int l = nlev - 1; l >= 0; --l)
       la::sor_level(level_rows_.p + level_ptr_[l], level_ptr_[l + 1] - level_ptr_[l], rp, op_->colidx.p, vals.p, d, v,
@@ -551,8 +558,8 @@ SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
         yv[a] = acc / Hh(a, a);
       }
       for (int a = 0; a < i; ++a) { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::axpy(n, yv[a], V(a), x, s); L++; }
-      if (!res.converged && j < max_iterations) {
-        // restart from the true preconditioned defect
+      if (!res.converged && j <= max_iterations) {
+        // restart from the true preconditioned defect (dune-istl: the same condition as the outer loop)
         apply_operator(x, tmp);
         { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::sub(n, b, tmp, w, s); L++; }
         precondition(w, V(0));

@@ -64,7 +64,8 @@ StepOperator::StepOperator(std::shared_ptr<DeviceOperator> o, const PTree& cfg, 
   dx_min_rel_tol = nl.get("dx_inverse_min_relative_tolerance", 0.1);
   std::string norm = nl.get("norm", std::string("l_2"));
   if (norm != "l_2") fail("nonlinear_solver.norm = '", norm, "' is not built (only l_2, i.e. the squared 2-norm)");
-  dt_min = cfg.get("time_step_min", 1e-12);
+  has_dt_min = cfg.has_key("time_step_min");   // optional in the reference (src/dune_copasi.cc:389-396)
+  dt_min = cfg.get("time_step_min", 0.0);
   dt_max = cfg.get("time_step_max", 0.0);
   inc_factor = cfg.get("time_step_increase_factor", 1.1);
   dec_factor = cfg.get("time_step_decrease_factor", 0.5);
@@ -169,20 +170,61 @@ bool StepOperator::step(double* u, double t, double dt) {
   return true;
 }
 
+// dune-common FloatCmp with its defaults (relativeWeak, epsilon = 8 ulp): what stepper.hh compares times with
+static bool fc_eq(double a, double b) {
+  return std::fabs(a - b) <= 8.0 * 2.220446049250313e-16 * std::max(std::fabs(a), std::fabs(b));
+}
+static bool fc_le(double a, double b) { return a < b || fc_eq(a, b); }
+static bool fc_lt(double a, double b) { return a < b && !fc_eq(a, b); }
+
+// SimpleAdaptiveStepper::check_dt (stepper.hh:375-386): a step outside [time_step_min, time_step_max] is an error
+bool StepOperator::check_dt(double dt) const {
+  if (has_dt_min && fc_lt(std::fabs(dt), std::fabs(dt_min))) return false;
+  if (dt_max > 0 && !fc_le(std::fabs(dt), std::fabs(dt_max))) return false;
+  return true;
+}
+
+// SimpleAdaptiveStepper::do_step (stepper.hh:337-368): retry with dt * decrease_factor until the step
+// succeeds or the lower limit is reached; after a success dt grows by increase_factor (clamped to the maximum)
+bool StepOperator::do_step(double* u, double* t, double* dt) {
+  if (!check_dt(*dt)) return false;
+  bool ok = step(u, *t, *dt);
+  while (!ok) {
+    *dt *= dec_factor;
+    if (!check_dt(*dt)) return false;
+    ok = step(u, *t, *dt);
+  }
+  *t += *dt;
+  double next = *dt * inc_factor;
+  if (dt_max > 0) next = std::min(std::max(next, -std::fabs(dt_max)), std::fabs(dt_max));
+  *dt = next;
+  return true;
+}
+
+// TimeStepper::evolve with snap_to_end_time (stepper.hh:145-176) and snap_to_time (:192-239): full steps
+// while two of them still fit, then the remainder in ceil(remainder / dt) equal steps (recomputed after
+// every step, since dt keeps growing), halving dt after a failure, at most 100 times.
+// max_steps bounds the number of accepted steps of this call (an extension for callers that interleave output).
 int StepOperator::evolve(double* u, double* t, double t_end, double* dt, int max_steps) {
   int accepted = 0;
-  while (t_end - *t > 1e-12 * std::max(1.0, std::fabs(t_end)) && accepted < max_steps) {
-    double dt_try = std::min(*dt, t_end - *t);   // snap to the end time (stepper.hh:192-239)
-    for (;;) {
-      if (step(u, *t, dt_try)) break;
-      dt_try *= dec_factor;   // stepper.hh:350-357
-      if (dt_try < dt_min) fail("time step underflow at t = ", *t);
-    }
-    *t += dt_try;
+  if (snap_target_ != t_end) { snapping_ = false; snap_target_ = t_end; snap_count_ = 0; }
+  while (!snapping_ && accepted < max_steps) {
+    if (!fc_le(*t + 2.0 * *dt, t_end)) { snapping_ = true; break; }
+    if (!do_step(u, t, dt)) fail("Evolving system could not approach final time (t = ", *t, ", dt = ", *dt, ")");
     ++accepted;
-    double next = dt_try * inc_factor;   // stepper.hh:360-366
-    if (dt_max > 0) next = std::min(next, dt_max);
-    *dt = next;
+  }
+  while (snapping_ && accepted < max_steps && fc_lt(*t, t_end)) {
+    const int n = (int)std::ceil((t_end - *t) / *dt);
+    if (n <= 0) fail("Timestep doesn't make advances towards snap step");
+    *dt = (t_end - *t) / n;
+    const double t_before = *t, dt_try = *dt;
+    if (do_step(u, t, dt)) {
+      ++accepted;
+    } else {
+      *t = t_before;
+      if (snap_count_++ == 100) fail("Snapping time exceeded maximum iteration count");
+      *dt = dt_try * 0.5;
+    }
   }
   return accepted;
 }

@@ -24,8 +24,12 @@ class StepOperator {
   // u (device, ndofs) is advanced from t by dt in place; returns false if the step failed
   // (Newton / linear solver did not converge) in which case u is unchanged.
   bool step(double* u, double t, double dt);
-  // adaptive evolution (SimpleAdaptiveStepper): returns the number of accepted steps
+  // adaptive evolution to t_end (TimeStepper::evolve + snap_to_time over SimpleAdaptiveStepper::do_step,
+  // common/stepper.hh:145-239, 337-386): returns the number of accepted steps
   int evolve(double* u, double* t, double t_end, double* dt, int max_steps);
+  // one adaptive step: u, t advanced by the dt that succeeded, dt replaced by the next suggestion
+  bool do_step(double* u, double* t, double* dt);
+  bool check_dt(double dt) const;
 
   std::string rk_type;
   bool is_linear = false;
@@ -33,7 +37,8 @@ class StepOperator {
   int newton_max_it = 40;
   bool dx_fixed_tol = false;
   double dx_min_rel_tol = 0.1;
-  double dt_min = 1e-12, dt_max = 0.0, inc_factor = 1.1, dec_factor = 0.5;
+  double dt_min = 0.0, dt_max = 0.0, inc_factor = 1.1, dec_factor = 0.5;
+  bool has_dt_min = false;
   StepStats stats;
   std::shared_ptr<DeviceOperator> op;
   std::unique_ptr<LinearSolver> linear;
@@ -43,6 +48,9 @@ class StepOperator {
   void stage_residual(const double* x, double ts, double wM, double wA, const double* constant, double* r);
   double norm2(const double* r);
   Communicator* comm_;
+  bool snapping_ = false;       // evolve() has entered snap_to_time for snap_target_
+  double snap_target_ = -1e300;
+  int snap_count_ = 0;
   std::vector<std::vector<double>> a_, b_;
   std::vector<double> d_;
   std::vector<DeviceBuffer<double>> stage_;   // stage solutions u_1..u_s

@@ -447,7 +447,7 @@ def linear_solve(rowptr, colidx, vals, b, cfg: dict, rel_tol: float, par=0):
     z = np.zeros(n)
     rhs = b.copy()
     pc = INI.sub(cfg, "preconditioner")
-    ptype = pc.get("type", "Jacobi")
+    ptype = pc.get("type", "SSOR")     # DUNE_COPASI_DEFAULT_PRECONDITIONER (factory/preconditioner.hh:17)
     kind = {"Richardson": 0, "Jacobi": 1, "BlockJacobi": 2, "SSOR": 3, "SOR": 4, "GaussSeidel": 5}[ptype]
     bs = int(pc.get("block_size", 1))
     relax = float(pc.get("relaxation", 1.0))
@@ -630,27 +630,72 @@ class StepOperator:
         return True
 
 
-def evolve(step: StepOperator, u, t0, t_end, dt0, dt_max=None, dt_min=1e-12, inc=1.1, dec=0.5,
-           on_step=None):
-    """SimpleAdaptiveStepper::evolve (stepper.hh:145-176, 337-368) with snap-to-end."""
-    t, dt, nsteps = t0, dt0, 0
-    while t_end - t > 1e-12 * max(1.0, abs(t_end)):
-        dt_try = min(dt, t_end - t)
-        while True:
-            un, ok = step.apply(u, t, dt_try)
-            if ok:
-                break
-            dt_try *= dec
-            if dt_try < dt_min:
-                raise RuntimeError("time step underflow")
-        u, t = un, t + dt_try
-        nsteps += 1
-        dt = dt_try * inc
+def _fc_eq(a, b):
+    """dune-common FloatCmp::eq with its defaults (relativeWeak, 8 ulp)"""
+    return abs(a - b) <= 8.0 * 2.220446049250313e-16 * max(abs(a), abs(b))
+
+
+def _fc_le(a, b):
+    return a < b or _fc_eq(a, b)
+
+
+def _fc_lt(a, b):
+    return a < b and not _fc_eq(a, b)
+
+
+def evolve(step: StepOperator, u, t0, t_end, dt0, dt_max=None, dt_min=None, inc=1.1, dec=0.5,
+           on_step=None, steps_taken=None):
+    """TimeStepper::evolve with snap_to_end_time (stepper.hh:145-176), snap_to_time (:192-239) and
+    SimpleAdaptiveStepper::do_step / check_dt (:337-386), literally: full steps while two of them still
+    fit before t_end, then the remainder in ceil(remainder / dt) equal steps, recomputed after every step
+    (dt keeps growing by `inc`), halved after a failure (at most 100 times)."""
+    state = {"u": u, "t": t0, "dt": dt0, "n": 0}
+
+    def check_dt(dt):
+        if dt_min is not None and _fc_lt(abs(dt), abs(dt_min)):
+            return False
+        if dt_max is not None and not _fc_le(abs(dt), abs(dt_max)):
+            return False
+        return True
+
+    def do_step():
+        if not check_dt(state["dt"]):
+            return False
+        un, ok = step.apply(state["u"], state["t"], state["dt"])
+        while not ok:
+            state["dt"] *= dec
+            if not check_dt(state["dt"]):
+                return False
+            un, ok = step.apply(state["u"], state["t"], state["dt"])
+        state["u"], state["t"] = un, state["t"] + state["dt"]
+        if steps_taken is not None:
+            steps_taken.append(state["dt"])
+        nxt = state["dt"] * inc
         if dt_max is not None:
-            dt = min(dt, dt_max)
+            nxt = min(max(nxt, -abs(dt_max)), abs(dt_max))
+        state["dt"] = nxt
+        state["n"] += 1
         if on_step:
-            on_step(t, u)
-    return u, t, nsteps
+            on_step(state["t"], state["u"])
+        return True
+
+    while _fc_le(state["t"] + 2.0 * state["dt"], t_end):
+        if not do_step():
+            raise RuntimeError("Evolving system could not approach final time")
+    snap_count = 0
+    while _fc_lt(state["t"], t_end):
+        n = int(np.ceil((t_end - state["t"]) / state["dt"]))
+        if n <= 0:
+            raise ArithmeticError("Timestep doesn't make advances towards snap step")
+        state["dt"] = (t_end - state["t"]) / n
+        t_before, dt_try = state["t"], state["dt"]
+        if not do_step():
+            state["t"] = t_before
+            if snap_count == 100:
+                raise RuntimeError("Snapping time exceeded maximum iteration count")
+            snap_count += 1
+            state["dt"] = dt_try * 0.5
+    return state["u"], state["t"], state["n"]
 
 
 # ---------------------------------------------------------------------- reduce (L2 functional)

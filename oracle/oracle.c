@@ -826,6 +826,12 @@ void orc_spmv(int64_t n, const int64_t* rowptr, const int32_t* colidx, const dou
   }
 }
 
+/* elementwise vector sweeps: identical results for any thread count (dune-istl's are sequential; the
+ * bench's CPU arm turns the threads on so that the baseline is not held back by them) */
+#define PAR_PRAGMA(x) _Pragma(#x)
+#define PAR_FOR(par) PAR_PRAGMA(omp parallel for schedule(static) if (par))
+static int g_par_blas = 0;
+
 static double dot(int64_t n, const double* a, const double* b, int par) {
   double s = 0;
 #pragma omp parallel for reduction(+ : s) schedule(static) if (par)
@@ -840,7 +846,7 @@ static double dot(int64_t n, const double* a, const double* b, int par) {
  * :17).  Third party, restated from dune-istl's gsetc.hh as published:
  *   bsorf: for rows i ascending   x_i += w (d_i - sum_j a_ij x_j) / a_ii   (current x, diagonal included)
  *   bsorb: the same for rows descending
- *   dbgs:  for rows i ascending   x_i += w (d_i - sum_{j != i} a_ij x_j) / a_ii
+ *   dbgs:  xold = x; for rows i ascending   x_i = (d_i - sum_{j != i} a_ij x_j) / a_ii;  then x = w x + (1 - w) xold
  *   SeqSSOR::apply = n x (bsorf; bsorb), SeqSOR::apply = n x bsorf, SeqGS::apply = n x dbgs, v = 0 on entry */
 typedef struct {
   int kind, bs; double relax; double* dinv; int64_t n;
@@ -913,17 +919,23 @@ static void sor_sweep(const Prec* Pc, const double* d, double* v, int backward, 
       if (j == i) { diag = Pc->vals[k]; if (skip_diag) continue; }
       rhs -= Pc->vals[k] * v[j];
     }
-    v[i] += Pc->relax * (rhs / diag);
+    if (skip_diag) v[i] = rhs / diag;   /* dbgs: the unrelaxed value inside the sweep ... */
+    else v[i] += Pc->relax * (rhs / diag);
   }
 }
 
 static void prec_apply(const Prec* Pc, const double* d, double* v) {
   if (Pc->kind >= 3) {
     memset(v, 0, sizeof(double) * Pc->n);
+    double* xold = Pc->kind == 5 ? malloc(sizeof(double) * Pc->n) : 0;
     for (int it = 0; it < Pc->iters; ++it) {
+      if (xold) memcpy(xold, v, sizeof(double) * Pc->n);
       sor_sweep(Pc, d, v, 0, Pc->kind == 5);
+      /* ... and x = w x + (1 - w) xold once the sweep is through (dune-istl gsetc.hh, dbgs) */
+      if (xold) for (int64_t i = 0; i < Pc->n; ++i) v[i] = Pc->relax * v[i] + (1.0 - Pc->relax) * xold[i];
       if (Pc->kind == 3) sor_sweep(Pc, d, v, 1, 0);
     }
+    free(xold);
     return;
   }
   prec_sweep(Pc, d, v);
@@ -944,7 +956,7 @@ static void prec_apply(const Prec* Pc, const double* d, double* v) {
 static void prec_sweep(const Prec* Pc, const double* d, double* v) {
   int64_t n = Pc->n;
   if (Pc->kind == 0) { for (int64_t i = 0; i < n; ++i) v[i] = d[i]; }
-  else if (Pc->kind == 1) { for (int64_t i = 0; i < n; ++i) v[i] = Pc->relax * Pc->dinv[i] * d[i]; }
+  else if (Pc->kind == 1) { PAR_FOR(g_par_blas) for (int64_t i = 0; i < n; ++i) v[i] = Pc->relax * Pc->dinv[i] * d[i]; }
   else {
     int bs = Pc->bs;
     for (int64_t I = 0; I < n / bs; ++I)
@@ -963,11 +975,12 @@ void orc_bicgstab(int64_t n, const int64_t* rowptr, const int32_t* colidx, const
                   double* x, double* b, double reduction, int maxit, int prec_kind, int bs,
                   double relax, int par, OrcResult* res) {
   Prec Pc = {prec_kind, bs, relax, 0, 0, 1, 0, 0, 0};
+  g_par_blas = par;   /* elementwise sweeps over all host threads when the caller asks for it (bench CPU arm) */
   prec_setup(&Pc, n, rowptr, colidx, vals);
   double *r = b, *rt = malloc(8 * n), *p = calloc(n, 8), *v = calloc(n, 8), *t = malloc(8 * n),
          *y = malloc(8 * n);
   orc_spmv(n, rowptr, colidx, vals, x, t, par);
-  for (int64_t i = 0; i < n; ++i) { r[i] -= t[i]; rt[i] = r[i]; }
+  PAR_FOR(par) for (int64_t i = 0; i < n; ++i) { r[i] -= t[i]; rt[i] = r[i]; }
   double norm0 = sqrt(dot(n, r, r, par)), norm = norm0;
   double rho = 1, alpha = 1, omega = 1, rho_new, h;
   double it = 0;
@@ -976,24 +989,24 @@ void orc_bicgstab(int64_t n, const int64_t* rowptr, const int32_t* colidx, const
   for (it = 0.5; it < maxit; it += 0.5) {
     rho_new = dot(n, rt, r, par);
     if (fabs(rho) <= 1e-80 || fabs(omega) <= 1e-80) break;
-    if (it < 1) { for (int64_t i = 0; i < n; ++i) p[i] = r[i]; }
+    if (it < 1) { PAR_FOR(par) for (int64_t i = 0; i < n; ++i) p[i] = r[i]; }
     else {
       double beta = (rho_new / rho) * (alpha / omega);
-      for (int64_t i = 0; i < n; ++i) p[i] = r[i] + beta * (p[i] - omega * v[i]);
+      PAR_FOR(par) for (int64_t i = 0; i < n; ++i) p[i] = r[i] + beta * (p[i] - omega * v[i]);
     }
     prec_apply(&Pc, p, y);
     orc_spmv(n, rowptr, colidx, vals, y, v, par);
     h = dot(n, rt, v, par);
     if (fabs(h) < 1e-80) break;
     alpha = rho_new / h;
-    for (int64_t i = 0; i < n; ++i) { x[i] += alpha * y[i]; r[i] -= alpha * v[i]; }
+    PAR_FOR(par) for (int64_t i = 0; i < n; ++i) { x[i] += alpha * y[i]; r[i] -= alpha * v[i]; }
     norm = sqrt(dot(n, r, r, par));
     if (norm < reduction * norm0 || norm < 1e-30) { res->converged = 1; break; }
     it += 0.5;
     prec_apply(&Pc, r, y);
     orc_spmv(n, rowptr, colidx, vals, y, t, par);
     omega = dot(n, t, r, par) / dot(n, t, t, par);
-    for (int64_t i = 0; i < n; ++i) { x[i] += omega * y[i]; r[i] -= omega * t[i]; }
+    PAR_FOR(par) for (int64_t i = 0; i < n; ++i) { x[i] += omega * y[i]; r[i] -= omega * t[i]; }
     rho = rho_new;
     norm = sqrt(dot(n, r, r, par));
     if (norm < reduction * norm0 || norm < 1e-30) { res->converged = 1; break; }
@@ -1109,7 +1122,7 @@ void orc_gmres(int64_t n, const int64_t* rowptr, const int32_t* colidx, const do
       const double* va = V + (size_t)a * n;
       for (int64_t q = 0; q < n; ++q) x[q] += yv[a] * va[q];
     }
-    if (!res->converged && j < maxit) {
+    if (!res->converged && j <= maxit) {   /* dune-istl: the outer loop's condition */
       memcpy(b, b2, 8 * n);
       orc_spmv(n, rowptr, colidx, vals, x, tmp, par);
       for (int64_t q = 0; q < n; ++q) b[q] -= tmp[q];
@@ -1122,6 +1135,14 @@ void orc_gmres(int64_t n, const int64_t* rowptr, const int32_t* colidx, const do
 done:
 #undef Hh
   free(V); free(w); free(b2); free(tmp); free(H); free(s); free(cs); free(sn); free(yv); free(Pc.dinv);
+}
+
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
 }
 
 int orc_num_threads(void) {

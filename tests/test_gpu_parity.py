@@ -410,6 +410,33 @@ def test_adaptive_evolve_matches_oracle_and_kat():
     assert got.max() <= 1 / (4 * 3.14159265359 * Dc) and got.min() >= -1e-2
 
 
+def test_snap_to_time_matches_oracle_step_for_step():
+    """dt that does not divide the interval (t_end = 1, dt0 = 0.3): the product takes the oracle's literal
+    evolve / snap_to_time sequence 0.3, 0.33, 0.185, 0.185 (common/stepper.hh:145-239), also when the caller
+    asks for one accepted step per call; a dt above time_step_max fails as check_dt does (:375-386)."""
+    import dune_copasi_b200 as D
+    case, om, cfg, model, grid, op = make("exp", **{"model.time_step_operator.time_step_max": "10"})
+    S = K.ORC.StepOperator(om)
+    taken = []
+    uo, to, no = K.ORC.evolve(S, om.initial(0.0), 0.0, 1.0, 0.3, dt_max=10.0, steps_taken=taken)
+    st = D.Stepper(op, cfg)
+    st.set_state(grid.interpolate(model, 0.0), 0.0)
+    n, _ = st.evolve(1.0, 0.3)
+    got, tg = st.get_state()
+    assert n == no == 4 and abs(tg - 1.0) < 1e-13 and rel(got, uo) <= FIELD_TOL
+    st.set_state(grid.interpolate(model, 0.0), 0.0)
+    dt, times = 0.3, [0.0]
+    for _ in range(4):
+        k, dt = st.evolve(1.0, dt, max_steps=1)
+        assert k == 1
+        times.append(st.time)
+    assert np.diff(times) == pytest.approx(taken, abs=1e-12)
+    st2 = D.Stepper(op, D.Config(case.ini_with(**{"model.time_step_operator.time_step_max": "0.2"})))
+    st2.set_state(grid.interpolate(model, 0.0), 0.0)
+    with pytest.raises(D.DcbError):
+        st2.evolve(1.0, 0.3)
+
+
 def test_empty_and_ragged_inputs():
     """Compartments without cells / cells without compartment / single element meshes."""
     import dune_copasi_b200 as D
@@ -474,7 +501,8 @@ def test_symbolic_jacobian_steps_match_oracle(name, rk, nsteps):
 @pytest.mark.parametrize("solver,prec,sweeps,relax", [("BiCGSTAB", "SSOR", 1, 1.0), ("BiCGSTAB", "SOR", 1, 1.0),
                                                      ("BiCGSTAB", "GaussSeidel", 2, 1.0), ("CG", "SSOR", 1, 1.0),
                                                      ("RestartedGMRes", "SSOR", 1, 1.0), ("BiCGSTAB", "SSOR", 2, 0.8),
-                                                     ("RestartedGMRes", "SOR", 1, 1.2)])
+                                                     ("RestartedGMRes", "SOR", 1, 1.2), ("BiCGSTAB", "GaussSeidel", 2, 0.8),
+                                                     ("BiCGSTAB", "GaussSeidel", 3, 1.3)])
 @pytest.mark.parametrize("name", ["grayscott3d", "mitchell_schaefer", "gauss3d", "two_disks"])
 def test_sor_family_matches_oracle(name, solver, prec, sweeps, relax):
     """SSOR (the reference's default preconditioner, solver/istl/factory/preconditioner.hh:17) / SOR /

@@ -32,7 +32,9 @@ def test_exp_kat():
     om = K.CASES["exp"].oracle()
     S = ORC.StepOperator(om)
     u, t, n = ORC.evolve(S, om.initial(0.0), 0.0, 10.0, 0.1, dt_max=0.1)
-    assert n == 100
+    # 99 full steps, then snap_to_time (stepper.hh:213-218): the accumulated time is a few ulp short of 9.9, so
+    # ceil(remainder / dt) = 2 and the remainder goes in two equal steps -- as the reference's arithmetic does
+    assert n in (100, 101) and t == pytest.approx(10.0, abs=1e-12)
     err = ORC.reduce_l2(om, u, "u", lambda pos, t: np.exp(-2 * t) + 0 * pos[..., 0], t)
     assert err <= 5e-3
     assert S.stats["newton_its"] >= n          # the non-linear path was exercised
@@ -392,6 +394,20 @@ type = ImplicitEuler
 time_step_initial = 0.1
 time_end = 0.2
 """ + K.SOLVER
+
+
+def test_snap_to_time_step_sequence():
+    """TimeStepper::evolve + snap_to_time (common/stepper.hh:145-239) with a dt that does not divide the
+    interval: t_end = 1, dt0 = 0.3, increase factor 1.1 -> 0.3, 0.33, then the remainder 0.37 in two equal steps
+    0.185, 0.185 (not 0.363 + a 0.007 sliver); a dt above time_step_max is an error (check_dt, :375-386)."""
+    om = K.CASES["exp"].oracle()
+    S = ORC.StepOperator(om)
+    taken = []
+    u, t, n = ORC.evolve(S, om.initial(0.0), 0.0, 1.0, 0.3, steps_taken=taken)
+    assert n == 4 and t == pytest.approx(1.0, abs=1e-14)
+    assert taken == pytest.approx([0.3, 0.33, 0.185, 0.185], abs=1e-12)
+    with pytest.raises(RuntimeError):
+        ORC.evolve(S, om.initial(0.0), 0.0, 1.0, 0.3, dt_max=0.2)
 
 
 def test_time_snap_kat():

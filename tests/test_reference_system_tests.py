@@ -37,8 +37,8 @@ def run_reference_ini(name, dim, overrides=(), pin_solver=True):
     S = ORC.StepOperator(om)
     ts = INI.sub(INI.sub(cfg, "model"), "time_step_operator")
     t0, t_end = float(ts.get("time_begin", 0.0)), float(ts["time_end"])
-    dt0 = float(ts.get("time_step_initial", 0.1))          # config_opts.json: default 0.1
     dt_max = float(ts["time_step_max"]) if "time_step_max" in ts else None
+    dt0 = float(ts.get("time_step_initial", dt_max if dt_max is not None else 0.1))   # src/dune_copasi.cc:397
     u, t, n = ORC.evolve(S, om.initial(t0), t0, t_end, dt0, dt_max=dt_max)
     assert abs(t - t_end) <= 1e-12 * max(1.0, abs(t_end))
     values, status = ORC.reduce(om, u, t)
@@ -61,7 +61,8 @@ def test_gauss_from_the_reference_file(dim):
 @pytest.mark.parametrize("dim", [2, 3])
 def test_exp_from_the_reference_file(dim):
     om, u, n, values, status = run_reference_ini("exp.ini", dim, [("grid.dimension", str(dim))])
-    assert n == 100 and max(status.values()) < 2, (values, status)
+    # 99 full steps + snap_to_time, which splits a remainder a few ulp above dt in two (stepper.hh:213-218)
+    assert n in (100, 101) and max(status.values()) < 2, (values, status)
     assert values["u_error"] <= 5e-3
     # u_mass_analytic has no integration_factor in the file: a plain sum over the quadrature points
     assert values["u_mass_analytic"] == pytest.approx(np.exp(-20.0) * (values["u_mass_analytic"] / np.exp(-20.0)).round())
