@@ -58,7 +58,10 @@ def ini_for(args):
         k, v = kv.split("=")
         over[k] = v
     from dune_copasi_b200 import workloads as W
-    return W.ini_text(getattr(args, "workload", "grayscott"), **over)
+    name = getattr(args, "workload", "grayscott")
+    if getattr(args, "mesh", "lattice") == "spheres":
+        name += "_spheres"
+    return W.ini_text(name, **over)
 
 
 def precompile():
@@ -147,7 +150,13 @@ def cpu_baseline(args, steps, warmup, cells):
     ORC.lib().orc_set_num_threads(int(ncores))
     cfg = INI.parse_ini(ini_for(args))
     dim = getattr(args, "dim", 3)
-    mesh = OMESH.structured(dim, [cells] * dim, element="cube" if getattr(args, "element", "p1") == "q1" else "simplex")
+    if getattr(args, "mesh", "lattice") == "spheres":
+        from dune_copasi_b200 import meshgen
+        coords, elems, keys, data = meshgen.nested_spheres(cells)
+        mesh = OMESH.Mesh(dim=3, coords=coords, elems=elems)
+        mesh.cell_keys, mesh.cell_data = keys, data
+    else:
+        mesh = OMESH.structured(dim, [cells] * dim, element="cube" if getattr(args, "element", "p1") == "q1" else "simplex")
     om = ORC.Model(cfg, mesh)
     S = ORC.StepOperator(om, par=1)
     u = om.initial(0.0)
@@ -188,6 +197,8 @@ def config_dict(args, cells):
     name = {"cell": "cell3d_3comp_6species", "cell10": "cell3d_3comp_10species"}.get(getattr(args, "workload", "grayscott"),
                                                                                        f"grayscott{dim}d")
     elem = "q1_cubes" if getattr(args, "element", "p1") == "q1" else "p1_kuhn"
+    if getattr(args, "mesh", "lattice") == "spheres":
+        elem = "p1_tets_nested_spheres"      # unstructured tetrahedral mesh of dune_copasi_b200/meshgen.py, 6 n^3 tets
     return {"workload": f"{name}_{elem}_{cells}^{dim}", "element": elem, "cells": cells,
             "collectives": getattr(args, "collectives", "none (1 GPU)"), "dt": args.dt, "rk": args.rk,
             "linear_solver": "BiCGSTAB", "preconditioner": args.prec, "matrix_free": bool(args.matrix_free),
@@ -221,6 +232,9 @@ def main():
     ap.add_argument("--workload", default="grayscott", choices=["grayscott", "cell", "cell10"],
                     help="grayscott: BASELINE configs[3] (headline); cell / cell10: 3-compartment cell model with "
                          "6 / 10 species (configs[4] in miniature, general unstructured kernels)")
+    ap.add_argument("--mesh", default="lattice", choices=["lattice", "spheres"],
+                    help="spheres: the cell workloads on the unstructured tetrahedral mesh of three nested spherical "
+                         "compartments (BASELINE configs[4]; dune_copasi_b200/meshgen.py, 6 cells^3 tets, RCB partition)")
     ap.add_argument("--b200", default="", help="model.assembly.b200.* overrides, e.g. patch_elements=768,patch_min_blocks=4")
     ap.add_argument("--set", default="", help="any ini key overrides, e.g. model.time_step_operator.linear_solver.b200.speculation=false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -246,9 +260,17 @@ def main():
     def measure(args):
         # ---- problem
         cfg = D.Config(ini_for(args))
-        model = D.Model(cfg, args.dim)
         t_setup = time.perf_counter()
-        gglobal = D.Grid.structured(args.dim, [args.cells] * args.dim, element="cube" if args.element == "q1" else "simplex")
+        if args.mesh == "spheres":
+            from dune_copasi_b200 import meshgen
+            coords, elems, keys, data = meshgen.nested_spheres(args.cells)
+            model = D.Model(cfg, 3, keys)
+            gglobal = D.Grid.from_arrays(3, coords, elems, keys, data)
+            del coords, elems, data
+        else:
+            model = D.Model(cfg, args.dim)
+            gglobal = D.Grid.structured(args.dim, [args.cells] * args.dim, element="cube" if args.element == "q1" else "simplex")
+        ne_global = gglobal.ne
         nv_global = gglobal.nv
         grid = gglobal.partition(rank, world) if world > 1 else gglobal
         grid.bind(model)
@@ -373,6 +395,19 @@ def main():
             "tile_apply": nodes * 112,
             "tile_residual": nodes * (16 * 2 + 8 * 2),
         }
+        if args.workload != "grayscott":
+            # general meshes, several compartments (one launch per compartment and application): per
+            # application read x, z and write y (24 B per dof), read the coordinates once per vertex and
+            # compartment (8 d) and the connectivity (4 (d + 1) per element) -- SURVEY.md 8(d)
+            ranges = op.owned_ranges()
+            nsp = {}
+            for _, c in model.species():
+                nsp[c] = nsp.get(c, 0) + 1
+            comps = [c for c in sorted(nsp)]
+            verts = sum((e - b) / nsp[c] for (b, e), c in zip(ranges, comps))
+            per_apply = op.ndofs * 24 + verts * 8 * dim + grid.ne * 4 * (dim + 1)
+            alg["elem_apply"] = per_apply / max(1, len(comps))
+            alg["elem_residual"] = (op.ndofs * 16 + verts * 8 * dim + grid.ne * 4 * (dim + 1)) / max(1, len(comps))
         top = max(prof, key=lambda k: prof[k]["ms"]) if prof else None
         roof = None
         if top:
@@ -400,7 +435,7 @@ def main():
         line = {"metric": metric_name(args), "value": value, "unit": "DOF-updates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, args.cells),
-                "time_steps_per_s": args.steps / (ms * 1e-3), "dofs": int(ndofs_global), "e2e": e2e,
+                "time_steps_per_s": args.steps / (ms * 1e-3), "dofs": int(ndofs_global), "elements": int(ne_global), "e2e": e2e,
                 "gpu_launches": int(d["kernel_launches"]), "clocks": clocks, "roofline": roof, "cpu_baseline": cb,
                 "solver_stats": d, "setup_s": t_setup}
         shutdown()

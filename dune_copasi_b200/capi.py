@@ -120,6 +120,7 @@ SYMBOLS = {
     "dcb_model_precompile_reduce": (C.c_int, [_P, _P]),
     "dcb_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "dcb_grid_partition": (_P, [_P, C.c_int, C.c_int]),
+    "dcb_grid_partition_method": (_P, [_P, C.c_int, C.c_int, C.c_char_p]),
     "dcb_grid_num_owned_vertices": (C.c_int64, [_P]),
     "dcb_grid_owned_vertex_range": (C.c_int, [_P, _I64, _I64]),
     "dcb_grid_get_global_vertex_ids": (C.c_int, [_P, _I64]),
@@ -288,8 +289,9 @@ class Grid:
             lib().dcb_grid_constraints(self.h, model.h, d.ctypes.data_as(_I32), _d(v), n)
         return d, v
 
-    def partition(self, rank, size):
-        return Grid(lib().dcb_grid_partition(self.h, rank, size))
+    def partition(self, rank, size, method="auto"):
+        """slab (structured lattices) | rcb | range | auto (slab for lattices, rcb otherwise)"""
+        return Grid(lib().dcb_grid_partition_method(self.h, rank, size, method.encode()))
 
     def global_element_ids(self):
         out = np.empty(self.ne, dtype=np.int64)

@@ -465,9 +465,12 @@ int dcb_model_precompile_reduce(dcb_model* m, const dcb_config* cfg) {
 // ---- multi GPU
 int dcb_nccl_unique_id(char id[128]) { return guard([&] { nccl_unique_id(id); }); }
 dcb_grid* dcb_grid_partition(const dcb_grid* global, int rank, int size) {
+  return dcb_grid_partition_method(global, rank, size, "auto");
+}
+dcb_grid* dcb_grid_partition_method(const dcb_grid* global, int rank, int size, const char* method) {
   return guard_new<dcb_grid>([&] {
     auto* g = new dcb_grid();
-    g->g = std::make_shared<Grid>(global->g->partition(rank, size));
+    g->g = std::make_shared<Grid>(global->g->partition(rank, size, method ? method : "auto"));
     return g;
   });
 }

@@ -262,7 +262,9 @@ void Grid::pattern(const Model& model, std::vector<int64_t>& rowptr, std::vector
           int64_t row = elem_dof(e, a) + model.species[t.i].local;
           for (int b = 0; b < ndl; ++b) {
             if (b == opp) continue;
-            int32_t gv = elems[e * ndl + b];
+            // the other element's vertex that carries phi_b of this element: the same vertex, or
+            // (reference_compat, local_operator.hh:1133-1143) the one with the same local index
+            int32_t gv = (model.reference_compat && ew != e) ? elems[ew * ndl + b] : elems[e * ndl + b];
             int32_t col = comp_vdof[ck][gv] + model.species[t.k].local;
             extra.push_back({row, col});
           }
@@ -370,10 +372,45 @@ void Grid::constraints(const Model& model, std::vector<int32_t>& dofs, std::vect
 
 // ------------------------------------------------------------------------------------------------
 // multi-GPU partition
-Grid Grid::partition(int rank, int size) const {
+// Recursive coordinate bisection of the vertices into `size` parts: split the longest
+// axis of the bounding box at the weighted median, parts in proportion to the ranks on either side (any
+// rank count), ties broken by the vertex id -- every rank computes the same map from the global mesh.
+static void rcb_split(const std::vector<double>& coords, int dim, std::vector<int64_t>& ids, size_t b, size_t e,
+                      int r0, int nparts, std::vector<int32_t>& owner) {
+  if (nparts == 1) {
+    for (size_t i = b; i < e; ++i) owner[ids[i]] = r0;
+    return;
+  }
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (size_t i = b; i < e; ++i)
+    for (int k = 0; k < dim; ++k) {
+      const double x = coords[ids[i] * dim + k];
+      lo[k] = std::min(lo[k], x);
+      hi[k] = std::max(hi[k], x);
+    }
+  int axis = 0;
+  for (int k = 1; k < dim; ++k)
+    if (hi[k] - lo[k] > hi[axis] - lo[axis]) axis = k;
+  const int nl = nparts / 2;
+  const size_t mid = b + (size_t)((__int128)(e - b) * nl / nparts);
+  std::nth_element(ids.begin() + b, ids.begin() + mid, ids.begin() + e, [&](int64_t p, int64_t q) {
+    const double xp = coords[p * dim + axis], xq = coords[q * dim + axis];
+    return xp != xq ? xp < xq : p < q;
+  });
+  rcb_split(coords, dim, ids, b, mid, r0, nl, owner);
+  rcb_split(coords, dim, ids, mid, e, r0 + nl, nparts - nl, owner);
+}
+
+Grid Grid::partition(int rank, int size, const std::string& method_in) const {
   if (size < 1 || rank < 0 || rank >= size) fail("partition: bad rank/size");
   const int ndl = nd();
-  if (is_structured && global_vid.empty()) {
+  std::string method = method_in.empty() ? "auto" : method_in;
+  if (method != "auto" && method != "slab" && method != "range" && method != "rcb")
+    fail("partition: method must be auto, slab (structured lattices), range or rcb");
+  const bool lattice = is_structured && global_vid.empty();
+  if (method == "slab" && !lattice) fail("partition: slabs need a structured lattice");
+  if (method == "auto") method = lattice ? "slab" : "rcb";
+  if (method == "slab") {
     // slabs of vertex planes along the last axis
     const int L = dim - 1;
     const int64_t nplanes = s_cells[L] + 1;
@@ -408,15 +445,18 @@ Grid Grid::partition(int rank, int size) const {
     (void)extent;
     return l;
   }
-  auto vbeg = [&](int r) { return (int64_t)((__int128)nv * r / size); };
-  auto owner_of = [&](int64_t v) {
-    int r = (int)((__int128)(v + 1) * size / nv);
-    if (r > size - 1) r = size - 1;
-    while (r > 0 && v < vbeg(r)) --r;
-    while (r < size - 1 && v >= vbeg(r + 1)) ++r;
-    return r;
-  };
-  const int64_t vb = vbeg(rank), ve = vbeg(rank + 1);
+  // vertex -> owning rank: contiguous ranges of the global numbering, or recursive coordinate bisection
+  std::vector<int32_t> owner(nv, 0);
+  if (method == "range") {
+    auto vbeg = [&](int r) { return (int64_t)((__int128)nv * r / size); };
+    for (int r = 0; r < size; ++r)
+      for (int64_t v = vbeg(r); v < vbeg(r + 1); ++v) owner[v] = r;
+  } else {
+    if (coords.size() != (size_t)nv * dim) fail("partition: rcb needs vertex coordinates");
+    std::vector<int64_t> ids(nv);
+    std::iota(ids.begin(), ids.end(), (int64_t)0);
+    rcb_split(coords, dim, ids, 0, (size_t)nv, 0, size, owner);
+  }
   Grid l;
   l.dim = dim;
   l.elem_kind = elem_kind;
@@ -425,10 +465,7 @@ Grid Grid::partition(int rank, int size) const {
   std::vector<int64_t> lel;
   for (int64_t e = 0; e < ne; ++e) {
     bool mine = false;
-    for (int a = 0; a < ndl; ++a) {
-      int64_t v = elems[e * ndl + a];
-      mine |= (v >= vb && v < ve);
-    }
+    for (int a = 0; a < ndl; ++a) mine |= owner[elems[e * ndl + a]] == rank;
     if (mine) lel.push_back(e);
   }
   // local vertices: owned range first, ghosts ascending
@@ -437,18 +474,19 @@ Grid Grid::partition(int rank, int size) const {
     for (int a = 0; a < ndl; ++a) used[elems[e * ndl + a]] = 1;
   std::vector<int32_t> g2l(nv, -1);
   int64_t nl = 0;
-  for (int64_t v = vb; v < ve; ++v) { g2l[v] = (int32_t)nl++; l.global_vid.push_back(v); }
+  for (int64_t v = 0; v < nv; ++v)
+    if (owner[v] == rank) { g2l[v] = (int32_t)nl++; l.global_vid.push_back(v); }   // owned first, ascending global id
   l.n_owned = nl;
   l.owned_begin = 0;
   for (int64_t v = 0; v < nv; ++v)
-    if (used[v] && (v < vb || v >= ve)) { g2l[v] = (int32_t)nl++; l.global_vid.push_back(v); }
+    if (used[v] && owner[v] != rank) { g2l[v] = (int32_t)nl++; l.global_vid.push_back(v); }   // ghosts last
   l.nv = nl;
   l.ne = (int64_t)lel.size();
   l.coords.resize(nl * dim);
   l.vowner.resize(nl);
   for (int64_t i = 0; i < nl; ++i) {
     for (int k = 0; k < dim; ++k) l.coords[i * dim + k] = coords[l.global_vid[i] * dim + k];
-    l.vowner[i] = owner_of(l.global_vid[i]);
+    l.vowner[i] = owner[l.global_vid[i]];
   }
   l.elems.resize(l.ne * ndl);
   l.global_eid = lel;

@@ -53,12 +53,15 @@ struct Grid {
   std::vector<int32_t> vowner;           // [nv] owning rank
   std::vector<int64_t> global_eid;       // [ne] global element id
 
-  // Vertex-range partition: rank r owns a contiguous range of global vertex
-  // ids; its local mesh holds every element touching an owned vertex (owner computes, one layer of
-  // ghosts), vertices renumbered owned-first (each group ascending in global id).
-  // Structured grids are cut into slabs of vertex planes along the last axis instead, so that every
-  // local mesh is again a structured box (owned planes in the middle, one ghost plane per side).
-  Grid partition(int rank, int size) const;
+  // Vertex partition: every vertex has one owning rank; a rank's local mesh holds every
+  // element touching an owned vertex (owner computes, one layer of ghosts), vertices renumbered owned
+  // first, ghosts last (each group ascending in global id).  Methods:
+  //   slab   structured lattices: slabs of vertex planes along the last axis, so that every local mesh is
+  //          again a structured box (owned planes in the middle, one ghost plane per side)
+  //   rcb    recursive coordinate bisection of the vertex coordinates (any rank count)
+  //   range  contiguous ranges of the global vertex numbering
+  //   auto   slab for structured lattices, rcb otherwise
+  Grid partition(int rank, int size, const std::string& method = "auto") const;
   static Grid structured_box(int dim, const int* cells, const double* origin, const double* extent,
                              int layer_lo, int layer_hi, int elem_kind = 0);
   // owned local dof ranges per compartment (valid after bind)

@@ -13,6 +13,7 @@ struct DcFacet {
   double xs[NSS][DC_DIM], xt[NST][DC_DIM];    // coefficients at the facet vertices
   double gs[NSS][DC_DIM], gt[NST][DC_DIM];    // gradients (element-wise constants)
   double area, ie;
+  bool self_inside;                           // this side is the facet's inside element (the lower element id)
   DcCtx c;
 
   __device__ __forceinline__ bool load(const DcFacetArgs& a, long long* fout) {
@@ -21,6 +22,7 @@ struct DcFacet {
     *fout = f;
     const long long es = a.f_self[f], et = a.f_other[f];
     const int ms = a.f_lself[f];
+    self_inside = et < 0 || es < et;
     int vs[DC_ND], ds[DC_ND], gvf[DC_DIM];
     double Xs[DC_ND][DC_DIM], Gs[DC_ND][DC_DIM], xall[NSS][DC_ND];
 #pragma unroll
@@ -79,16 +81,39 @@ struct DcFacet {
     }
     if (!O::BOUNDARY && et >= 0) {
       double Xt[DC_ND][DC_DIM], Gt[DC_ND][DC_DIM], xtall[NST][DC_ND];
-      int vt[DC_ND];
+      int vt[DC_ND], dt[DC_ND];
 #pragma unroll
       for (int k = 0; k < DC_ND; ++k) {
         vt[k] = a.elems[et * DC_ND + k];
 #pragma unroll
         for (int cc = 0; cc < DC_DIM; ++cc) Xt[k][cc] = a.coords[(long long)vt[k] * DC_DIM + cc];
-        const int d = a.vdof_t ? a.vdof_t[vt[k]] : a.dof_offset_t + vt[k] * O::NST_REAL;
+        dt[k] = a.vdof_t ? a.vdof_t[vt[k]] : a.dof_offset_t + vt[k] * O::NST_REAL;
 #pragma unroll
-        for (int s = 0; s < O::NST_REAL; ++s) xtall[s][k] = a.x[d + s];
+        for (int s = 0; s < O::NST_REAL; ++s) xtall[s][k] = a.x[dt[k] + s];
       }
+#if DC_REF_COMPAT
+      // local_operator.hh:903-916 / :939-941 as written: the coefficients of the element across the facet are
+      // paired, local index by local index, with this element's shape functions and gradients
+      (void)Xt; (void)Gt;
+#pragma unroll
+      for (int s = 0; s < O::NST_REAL; ++s)
+#pragma unroll
+        for (int k = 0; k < DC_DIM; ++k) {
+          double acc = 0.0;
+#pragma unroll
+          for (int b = 0; b < DC_ND; ++b) acc += xtall[s][b] * Gs[b][k];
+          gt[s][k] = acc;
+        }
+#pragma unroll
+      for (int n = 0; n < DC_DIM; ++n) {
+        const bool lo = n < ms;
+        doft[n] = lo ? dt[n] : dt[n + 1];
+#pragma unroll
+        for (int s = 0; s < O::NST_REAL; ++s) xt[s][n] = lo ? xtall[s][n] : xtall[s][n + 1];
+#pragma unroll
+        for (int cc = 0; cc < DC_DIM; ++cc) Gtf[n][cc] = Gsf[n][cc];
+      }
+#else
       dc_geometry(Xt, Gt);
 #pragma unroll
       for (int s = 0; s < O::NST_REAL; ++s)
@@ -112,6 +137,7 @@ struct DcFacet {
             for (int cc = 0; cc < DC_DIM; ++cc) Gtf[n][cc] = Gt[k][cc];
           }
       }
+#endif
     }
     // facet measure and unit outer normal of the own side: -grad(phi_m)/|grad(phi_m)|
     double nn = 0.0;
@@ -239,7 +265,18 @@ __device__ __noinline__ void dc_fd_skeleton(DcFacet<P>& F, double wA, Sink sink)
         const double* shape = side == 0 ? F.Gsf[mb] : F.Gtf[mb];
         const double keep = *coef;
         double gkeep[DC_DIM];
-        const double delta = DC_FD_EPS * (1.0 + fabs(keep));
+#if DC_REF_COMPAT
+        // :1298 sizes delta of an out-side column with coeff_in read at the out-side node: the own-side
+        // container at the same (species slot, local vertex), 0 where it has no such entry
+        // (inside = this side when self_inside; slots pair the two elements by local index here)
+        const bool out_column = (side == 0) != F.self_inside;
+        const double partner = side == 0 ? (j < O::NST_REAL ? F.xt[j < O::NST_REAL ? j : 0][mb] : 0.0)
+                                         : (j < O::NSS ? F.xs[j < O::NSS ? j : 0][mb] : 0.0);
+        const double sized = out_column ? partner : keep;
+#else
+        const double sized = keep;
+#endif
+        const double delta = DC_FD_EPS * (1.0 + fabs(sized));
         *coef = keep + delta;
 #pragma unroll
         for (int k = 0; k < DC_DIM; ++k) { gkeep[k] = grad[k]; grad[k] += delta * shape[k]; }

@@ -26,6 +26,7 @@ Model::Model(const PTree& cfg_, int dim_, const std::vector<std::string>& keys)
     numerical_jacobian = jt == "numerical" && !is_linear;
     symbolic_jacobian = jt == "symbolic";
     fd_epsilon = mcfg.get("jacobian.epsilon", 1e-7);
+    reference_compat = mcfg.get("b200.reference_compat", true);
   }
   const PTree& comps = cfg.sub("compartments");
   for (auto& name : comps.sub_keys()) {
@@ -382,6 +383,7 @@ std::string Model::cuda_source() const {
     char eps[64];
     snprintf(eps, sizeof eps, "%.17g", fd_epsilon);
     o << "#define DC_NUMJAC " << (numerical_jacobian ? 1 : 0) << "\n#define DC_FD_EPS " << eps << "\n";
+    o << "#define DC_REF_COMPAT " << (reference_compat ? 1 : 0) << "\n";
   }
   o << "struct DcCtx { double time, entity_volume, integration_factor, in_volume, in_boundary, in_skeleton;"
        " double pos[3]; double nrm[3]; double cell[" << std::max<size_t>(1, cell_keys.size()) << "]; };\n";

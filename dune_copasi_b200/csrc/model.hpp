@@ -41,6 +41,9 @@ class Model {
   // model.jacobian.type = numerical: finite differences with model.jacobian.epsilon
   // (local_operator.hh:193-202, 713-765); linear operators always use the analytic path (:234-235)
   bool numerical_jacobian = false;
+  // model.b200.reference_compat (default true): facet terms exactly as local_operator.hh:903-916 / :1298 compute
+  // them (cross-side coefficients paired with this side's shape functions by local index)
+  bool reference_compat = true;
   double fd_epsilon = 1e-7;
   // model.jacobian.type = symbolic (extension; north_star: "analytic Jacobians from SymEngine"): every
   // jacobian entry is derived from its function by expr.cpp's differentiator, the ini's own

@@ -226,6 +226,7 @@ int StepOperator::evolve(double* u, double* t, double t_end, double* dt, int max
       *dt = dt_try * 0.5;
     }
   }
+  if (!fc_lt(*t, t_end)) { snapping_ = false; snap_target_ = -1e300; snap_count_ = 0; }   // arrived: the next call starts afresh
   return accepted;
 }
 

@@ -198,7 +198,22 @@ time_end = 1
 """)
 
 
-WORKLOADS = {"grayscott": GRAY_SCOTT, "cell": CELL, "cell10": CELL10}
+
+
+def _on_gmsh_ids(text: str) -> str:
+    """the same model with the compartments marked by the mesh's cell datum, as the reference's Gmsh
+    workflows do (`compartments.<name>.expression = (gmsh_id == k)`, e.g. test/two_disks.ini)"""
+    head, tail = text.split("[parser_context]", 1)
+    return ("\n[compartments]\necs.expression = (gmsh_id == 3)\ncytosol.expression = (gmsh_id == 2)\n"
+            "nucleus.expression = (gmsh_id == 1)\n[parser_context]" + tail)
+
+
+# BASELINE configs[4]: the 10-species model on the nested-spheres tetrahedral mesh of meshgen.nested_spheres
+CELL10_SPHERES = _on_gmsh_ids(CELL10)
+CELL_SPHERES = _on_gmsh_ids(CELL)
+
+WORKLOADS = {"grayscott": GRAY_SCOTT, "cell": CELL, "cell10": CELL10, "cell_spheres": CELL_SPHERES,
+             "cell10_spheres": CELL10_SPHERES}
 
 
 def config(name: str, **overrides) -> Config:

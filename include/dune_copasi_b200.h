@@ -201,9 +201,13 @@ int dcb_model_precompile_reduce(dcb_model*, const dcb_config*);
 
 /* ---- multi-GPU: one process per GPU, NCCL ---- */
 int dcb_nccl_unique_id(char id[128]);
-/* Vertex-range partition of a global mesh for `rank` of `size`: returns the local mesh (owned
- * vertices first, then one layer of ghosts).  Maps are retrievable below. */
+/* Vertex partition of a global mesh for `rank` of `size`: returns the local mesh (owned vertices first,
+ * then one layer of ghosts, each group ascending in global id).  Maps are retrievable below.
+ * method: "slab" (structured lattices: planes along the last axis), "rcb" (recursive coordinate bisection
+ * of the vertices, any rank count), "range" (contiguous ranges of the vertex numbering), "auto" / NULL
+ * (slab for structured lattices, rcb otherwise -- what dcb_grid_partition does). */
 dcb_grid* dcb_grid_partition(const dcb_grid* global, int rank, int size);
+dcb_grid* dcb_grid_partition_method(const dcb_grid* global, int rank, int size, const char* method);
 int64_t dcb_grid_num_owned_vertices(const dcb_grid* local);
 /* owned vertices are the local ids [begin, end): a prefix for the general partition, the middle
  * planes of the slab for structured grids */

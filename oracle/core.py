@@ -369,7 +369,10 @@ class Model:
                         continue
                     fv = [a for a in range(nd) if a != (m.f_lin[f] if e == ei else m.f_lout[f])]
                     gv = m.elems[e, fv]
-                    fw = [int(np.nonzero(m.elems[ew] == g)[0][0]) for g in gv]
+                    if ew != e and self.reference_compat:
+                        fw = fv      # column dof_j of the other element carries phi_j of this one (:1133-1143)
+                    else:
+                        fw = [int(np.nonzero(m.elems[ew] == g)[0][0]) for g in gv]
                     r = m.elem_dof[e, fv] + self.species[i].local
                     cc = m.elem_dof[ew, fw] + self.species[k].local
                     rows.append(np.repeat(r, len(fv)))
@@ -385,8 +388,15 @@ class Model:
         return A.indptr.astype(np.int64), A.indices.astype(np.int32)
 
     # ------------------------------------------------------------------ operators
+    @property
+    def reference_compat(self):
+        """model.b200.reference_compat (default true): facet terms exactly as local_operator.hh:903-916, :1298"""
+        v = str(INI.get(self.cfg, "model.b200.reference_compat", "true")).strip().lower()
+        return v not in ("false", "0", "no", "off")
+
     def residual(self, form, time, w, x, r, par=0):
         L = lib()
+        L.orc_set_reference_compat(C.c_int(int(self.reference_compat)))
         L.orc_residual_volume(C.byref(self.cmesh), C.byref(self.cmodel), C.c_int(form), C.c_double(time),
                               C.c_double(w), _p(x, C.c_double), _p(r, C.c_double), C.c_int(par))
         if form == 0 and self.has_outflow:
@@ -395,6 +405,7 @@ class Model:
 
     def jacobian(self, form, time, w, x, rowptr, colidx, vals, par=0, numerical=False, eps=1e-7):
         L = lib()
+        L.orc_set_reference_compat(C.c_int(int(self.reference_compat)))
         if numerical:
             L.orc_jacobian_volume_numerical(C.byref(self.cmesh), C.byref(self.cmodel), C.c_int(form),
                                             C.c_double(time), C.c_double(w), C.c_double(eps),
@@ -416,6 +427,7 @@ class Model:
 
     def jacobian_apply(self, form, time, w, x, z, y, par=0):
         L = lib()
+        L.orc_set_reference_compat(C.c_int(int(self.reference_compat)))
         L.orc_jacobian_apply_volume(C.byref(self.cmesh), C.byref(self.cmodel), C.c_int(form),
                                     C.c_double(time), C.c_double(w), _p(x, C.c_double),
                                     _p(z, C.c_double), _p(y, C.c_double), C.c_int(par))

@@ -641,19 +641,30 @@ static void facet_geo(const OrcMesh* M, int64_t f, FacetGeo* F) {
   }
 }
 
-/* fill ctx with every species of both sides at the facet point with facet barycentrics lam */
+/* model.b200.reference_compat: cross-side values as local_operator.hh:903-916 / :939-941 compute them -- the
+ * coefficients of the element across the facet are paired, local index by local index, with the shape
+ * functions (and their gradients) of the element whose residual rows are being assembled (bound through
+ * quad_proj_i / quad_proj_o).  0: the P1 trace at the physical point (what the formula means when both
+ * elements number the shared vertices alike).  Set per call by oracle/core.py. */
+static int g_ref_compat = 1;
+void orc_set_reference_compat(int on) { g_ref_compat = on; }
+
+/* fill ctx with every species of both sides at the facet point with facet barycentrics lam, as seen from
+ * `self_side` (the side whose rows are assembled) */
 static void facet_fields(const OrcMesh* M, const OrcModel* P, int64_t f, const FacetGeo* F,
-                         const double* lam, const double* x, double* ctx) {
+                         const double* lam, const double* x, double* ctx, int self_side) {
   const int dim = M->dim, nd = dim + 1;
   for (int side = 0; side < 2; ++side) {
     int64_t e = side == 0 ? M->f_in[f] : M->f_out[f];
     if (e < 0) continue;
     int c = M->elem_comp[e];
     if (c < 0) continue;
+    /* whose shape functions: its own, or (compat, other side) those of the assembling element */
+    const int basis = (g_ref_compat && M->f_out[f] >= 0) ? self_side : side;
     double phi[4] = {0, 0, 0, 0};
-    const int* fv = side == 0 ? F->fv_i : F->fv_o;
+    const int* fv = basis == 0 ? F->fv_i : F->fv_o;
     for (int k = 0; k < dim; ++k) phi[fv[k]] = lam[k];
-    double(*G)[3] = side == 0 ? (double(*)[3])F->Gi : (double(*)[3])F->Go;
+    double(*G)[3] = basis == 0 ? (double(*)[3])F->Gi : (double(*)[3])F->Go;
     eval_fields(M, P, c, e, x, phi, G, ctx);
     (void)nd;
   }
@@ -705,7 +716,7 @@ static void skeleton_range(const OrcMesh* M, const OrcModel* P, double time, dou
         }
         double factor = qw[q] * ie;
         ctx[SLOT_INTFAC] = factor;
-        facet_fields(M, P, f, &F, lam[q], x, ctx);
+        facet_fields(M, P, f, &F, lam[q], x, ctx, side);
         for (int t = P->comp_ptr[cs]; t < P->comp_ptr[cs + 1]; ++t) {
           int g = P->comp_spec[t], si = P->spec_local[g];
           TERMS(P, g, K_OUTFLOW, o0, o1);
@@ -724,7 +735,11 @@ static void skeleton_range(const OrcMesh* M, const OrcModel* P, double time, dou
                 /* block choice: the side where the wrt species lives (local_operator.hh:1129-1131) */
                 int64_t ew; const int* fw;
                 if (cw == cs) { ew = e; fw = fv; }
-                else if (eo >= 0 && cw == (side == 0 ? co : ci)) { ew = side == 0 ? eo : ei; fw = side == 0 ? F.fv_o : F.fv_i; }
+                else if (eo >= 0 && cw == (side == 0 ? co : ci)) {
+                  ew = side == 0 ? eo : ei;
+                  /* compat: column dof_j of the other element's basis carries phi_j of this element (:1133-1143) */
+                  fw = g_ref_compat ? fv : (side == 0 ? F.fv_o : F.fv_i);
+                }
                 else continue;
                 for (int a = 0; a < dim; ++a)
                   for (int b = 0; b < dim; ++b)
@@ -763,9 +778,9 @@ void orc_jacobian_apply_skeleton(const OrcMesh* M, const OrcModel* P, double tim
 /* numerical skeleton / boundary Jacobian, local_operator.hh:1205-1343: one-sided differences of the
  * facet residual, column by column over the coefficients of both sides, delta = eps (1 + |x_col|).
  * Columns are the dofs at the facet's vertices (the links of the skeleton pattern); entries
- * outside the pattern are dropped.  Deviation: for out-side columns the reference sizes delta
- * with `coeff_in` read at the out-side node (:1298), an index mix-up; the out-side coefficient
- * itself is used here.  `n` = number of dofs. */
+ * outside the pattern are dropped.  For out-side columns the reference sizes delta with `coeff_in` read at
+ * the out-side node (:1298): reproduced under reference_compat (see `partner` below), otherwise the out-side
+ * coefficient itself is used.  `n` = number of dofs. */
 void orc_jacobian_skeleton_numerical(const OrcMesh* M, const OrcModel* P, double time, double w, double eps,
                                      int64_t n, const double* x, const int64_t* rowptr,
                                      const int32_t* colidx, double* vals) {
@@ -778,7 +793,7 @@ void orc_jacobian_skeleton_numerical(const OrcMesh* M, const OrcModel* P, double
     int64_t ei = M->f_in[f], eo = M->f_out[f];
     int ci = M->elem_comp[ei], co = eo >= 0 ? M->elem_comp[eo] : -1;
     if (eo >= 0 && ci == co) continue;
-    int64_t dofs[2 * 3 * 32];
+    int64_t dofs[2 * 4 * 32], partner[2 * 4 * 32];
     int nd_f = 0;
     for (int side = 0; side < 2; ++side) {
       int64_t e = side == 0 ? ei : eo;
@@ -787,14 +802,26 @@ void orc_jacobian_skeleton_numerical(const OrcMesh* M, const OrcModel* P, double
       int m = side == 0 ? M->f_lin[f] : M->f_lout[f];
       int ns = P->comp_ptr[c + 1] - P->comp_ptr[c];
       for (int a = 0; a < nd; ++a)
-        if (a != m)
-          for (int s = 0; s < ns; ++s) dofs[nd_f++] = M->elem_dof[e * nd + a] + s;
+        if (a != m || (g_ref_compat && eo >= 0))   /* compat: the local index pairing reaches every vertex */
+          for (int s = 0; s < ns; ++s) {
+            dofs[nd_f] = M->elem_dof[e * nd + a] + s;
+            /* compat (:1298): delta of an out-side column is sized with coeff_in read at the out-side node --
+             * the inside container at the same (species slot, local vertex), 0 where it has no such entry */
+            partner[nd_f] = -1;
+            if (side == 1 && g_ref_compat) {
+              int nsi = P->comp_ptr[ci + 1] - P->comp_ptr[ci];
+              partner[nd_f] = s < nsi ? M->elem_dof[ei * nd + a] + s : -2;
+            }
+            ++nd_f;
+          }
     }
     for (int k = 0; k < nd_f; ++k) down[dofs[k]] = 0.0;
     skeleton_range(M, P, time, 1.0, xw, down, 0, 0, f, f + 1);
     for (int cidx = 0; cidx < nd_f; ++cidx) {
       int64_t col = dofs[cidx];
-      double keep = xw[col], delta = eps * (1.0 + fabs(keep));
+      double keep = xw[col];
+      double sized = partner[cidx] == -1 ? keep : partner[cidx] == -2 ? 0.0 : xw[partner[cidx]];
+      double delta = eps * (1.0 + fabs(sized));
       xw[col] = keep + delta;
       for (int k = 0; k < nd_f; ++k) up[dofs[k]] = 0.0;
       skeleton_range(M, P, time, 1.0, xw, up, 0, 0, f, f + 1);

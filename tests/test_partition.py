@@ -23,7 +23,7 @@ def _free_port():
     return p
 
 
-def _local_problem(case, rank, size, structured=False):
+def _local_problem(case, rank, size, structured=False, method="auto"):
     import dune_copasi_b200 as D
     from oracle import core as ORC, ini as INI, mesh as OMESH
     gmesh = case.mesh_fn()
@@ -33,7 +33,7 @@ def _local_problem(case, rank, size, structured=False):
         gglob = K.product_grid(case, gmesh)      # slab partition of the structured box
     else:
         gglob = D.Grid.from_arrays(case.dim, gmesh.coords, gmesh.elems, gmesh.cell_keys, gmesh.cell_data)
-    gloc = gglob.partition(rank, size)
+    gloc = gglob.partition(rank, size, method)
     gloc.bind(model)
     # the oracle on the same local arrays (cell data restricted through the element ids is not
     # needed for the cases used here)
@@ -68,7 +68,7 @@ def _global_dofs(om_glob, om_loc, gids):
     return out
 
 
-def _worker(rank, size, port, name, structured, q):
+def _worker(rank, size, port, name, structured, q, method="auto"):
     import torch.distributed as dist
     try:
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -76,7 +76,7 @@ def _worker(rank, size, port, name, structured, q):
         import torch
         case = K.ALL_CASES[name]
         om = case.oracle()                      # serial reference
-        model, gloc, oml = _local_problem(case, rank, size, structured)
+        model, gloc, oml = _local_problem(case, rank, size, structured, method)
         gids = gloc.global_vertex_ids()
         owner = gloc.vertex_owner()
         ob, oe = gloc.owned_vertex_range()
@@ -84,7 +84,11 @@ def _worker(rank, size, port, name, structured, q):
         is_owned = np.zeros(gloc.nv, dtype=bool)
         is_owned[ob:oe] = True
         assert (owner[is_owned] == rank).all() and (owner[~is_owned] != rank).all()
-        assert np.all(np.diff(gids[ob:oe]) == 1) and len(np.unique(gids)) == gids.size
+        # owned first then ghosts, each group ascending in global id; contiguous ranges for slab / range
+        assert np.all(np.diff(gids[ob:oe]) >= 1) and len(np.unique(gids)) == gids.size
+        assert np.all(np.diff(gids[:ob]) >= 1) and np.all(np.diff(gids[oe:]) >= 1)
+        if structured or method == "range":
+            assert np.all(np.diff(gids[ob:oe]) == 1)
         assert gloc.ndofs == oml.ndofs and np.array_equal(gloc.elem_dof(), oml.mesh.elem_dof)
         l2g = _global_dofs(om, oml, gids)
         # owned dof ranges: contiguous per compartment, and exactly the dofs on owned vertices
@@ -140,11 +144,48 @@ def _worker(rank, size, port, name, structured, q):
                                                   ("two_disks", 2, False), ("grayscott3d", 3, True), ("cell3d", 2, True),
                                                   ("grayscott3d_q1", 2, True), ("grayscott2d_q1", 3, True)])
 def test_partition_halo_gloo(name, size, structured):
+    _spawn(name, size, structured, "auto")
+
+
+@pytest.mark.parametrize("name,size,method", [("cell3d", 3, "rcb"), ("two_disks", 4, "rcb"), ("grayscott3d", 2, "range"),
+                                              ("cell3d", 3, "range"), ("two_disks_cell_data", 2, "rcb")])
+def test_partition_methods_gloo(name, size, method):
+    """Recursive coordinate bisection (any rank count) and contiguous vertex ranges on general meshes: the
+    same owner-computes checks as above (bit-exact maps against the serial numbering, halo plan complete,
+    owned rows equal the serial residual)."""
+    _spawn(name, size, False, method)
+
+
+def test_rcb_is_balanced_and_compact():
+    """RCB: parts differ by at most one vertex per bisection level and every part is a box-shaped cloud (its
+    bounding boxes overlap only at the cuts)."""
+    import dune_copasi_b200 as D
+    case = K.CASES["cell3d"]
+    gmesh = case.mesh_fn()
+    g = D.Grid.from_arrays(case.dim, gmesh.coords, gmesh.elems, gmesh.cell_keys, gmesh.cell_data)
+    size = 5
+    counts, boxes, seen = [], [], np.zeros(gmesh.coords.shape[0], dtype=int)
+    for r in range(size):
+        loc = g.partition(r, size, "rcb")
+        ob, oe = loc.owned_vertex_range()
+        gids = loc.global_vertex_ids()[ob:oe]
+        seen[gids] += 1
+        counts.append(gids.size)
+        pts = gmesh.coords[gids]
+        boxes.append((pts.min(0), pts.max(0)))
+    assert (seen == 1).all()
+    assert max(counts) - min(counts) <= 3
+    vol = sum(np.prod(hi - lo) for lo, hi in boxes)
+    allv = np.prod(gmesh.coords.max(0) - gmesh.coords.min(0))
+    assert vol <= 1.0 * allv + 1e-12        # the boxes tile the domain (they do not overlap beyond the cut planes)
+
+
+def _spawn(name, size, structured, method):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, size, port, name, structured, q)) for r in range(size)]
+    procs = [ctx.Process(target=_worker, args=(r, size, port, name, structured, q, method)) for r in range(size)]
     for p in procs:
         p.start()
     results = [q.get(timeout=240) for _ in procs]
