@@ -59,8 +59,8 @@ def ini_for(args):
         over[k] = v
     from dune_copasi_b200 import workloads as W
     name = getattr(args, "workload", "grayscott")
-    if getattr(args, "mesh", "lattice") == "spheres":
-        name += "_spheres"
+    if getattr(args, "mesh", "lattice") == "nested":
+        name += "_nested"
     return W.ini_text(name, **over)
 
 
@@ -150,9 +150,9 @@ def cpu_baseline(args, steps, warmup, cells):
     ORC.lib().orc_set_num_threads(int(ncores))
     cfg = INI.parse_ini(ini_for(args))
     dim = getattr(args, "dim", 3)
-    if getattr(args, "mesh", "lattice") == "spheres":
+    if getattr(args, "mesh", "lattice") == "nested":
         from dune_copasi_b200 import meshgen
-        coords, elems, keys, data = meshgen.nested_spheres(cells)
+        coords, elems, keys, data = meshgen.nested_compartments(cells)
         mesh = OMESH.Mesh(dim=3, coords=coords, elems=elems)
         mesh.cell_keys, mesh.cell_data = keys, data
     else:
@@ -197,8 +197,8 @@ def config_dict(args, cells):
     name = {"cell": "cell3d_3comp_6species", "cell10": "cell3d_3comp_10species"}.get(getattr(args, "workload", "grayscott"),
                                                                                        f"grayscott{dim}d")
     elem = "q1_cubes" if getattr(args, "element", "p1") == "q1" else "p1_kuhn"
-    if getattr(args, "mesh", "lattice") == "spheres":
-        elem = "p1_tets_nested_spheres"      # unstructured tetrahedral mesh of dune_copasi_b200/meshgen.py, 6 n^3 tets
+    if getattr(args, "mesh", "lattice") == "nested":
+        elem = "p1_tets_nested_compartments"      # unstructured tetrahedral mesh of dune_copasi_b200/meshgen.py, 6 n^3 tets
     return {"workload": f"{name}_{elem}_{cells}^{dim}", "element": elem, "cells": cells,
             "collectives": getattr(args, "collectives", "none (1 GPU)"), "dt": args.dt, "rk": args.rk,
             "linear_solver": "BiCGSTAB", "preconditioner": args.prec, "matrix_free": bool(args.matrix_free),
@@ -232,8 +232,8 @@ def main():
     ap.add_argument("--workload", default="grayscott", choices=["grayscott", "cell", "cell10"],
                     help="grayscott: BASELINE configs[3] (headline); cell / cell10: 3-compartment cell model with "
                          "6 / 10 species (configs[4] in miniature, general unstructured kernels)")
-    ap.add_argument("--mesh", default="lattice", choices=["lattice", "spheres"],
-                    help="spheres: the cell workloads on the unstructured tetrahedral mesh of three nested spherical "
+    ap.add_argument("--mesh", default="lattice", choices=["lattice", "nested"],
+                    help="nested: the cell workloads on the unstructured tetrahedral mesh of three nested "
                          "compartments (BASELINE configs[4]; dune_copasi_b200/meshgen.py, 6 cells^3 tets, RCB partition)")
     ap.add_argument("--b200", default="", help="model.assembly.b200.* overrides, e.g. patch_elements=768,patch_min_blocks=4")
     ap.add_argument("--set", default="", help="any ini key overrides, e.g. model.time_step_operator.linear_solver.b200.speculation=false")
@@ -261,9 +261,9 @@ def main():
         # ---- problem
         cfg = D.Config(ini_for(args))
         t_setup = time.perf_counter()
-        if args.mesh == "spheres":
+        if args.mesh == "nested":
             from dune_copasi_b200 import meshgen
-            coords, elems, keys, data = meshgen.nested_spheres(args.cells)
+            coords, elems, keys, data = meshgen.nested_compartments(args.cells)
             model = D.Model(cfg, 3, keys)
             gglobal = D.Grid.from_arrays(3, coords, elems, keys, data)
             del coords, elems, data

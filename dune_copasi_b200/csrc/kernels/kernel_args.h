@@ -26,6 +26,9 @@ struct DcVolArgs {
   const int* vptr;             // [n+1]
   const int* vel;              // (element << 2 | local vertex index)
   int gather_maxlen;           // longest row of the compartment (shared-memory slots per species row)
+  // 16-byte gathers: the element kernels are bound by the L1 gather wavefronts, not by DRAM or the fp64 pipe
+  const double* coords4;       // 3-D: [nv][4] coordinates padded to 32 bytes per vertex (null: use coords)
+  int vec;                     // 1: x, z are 16-byte aligned and every dof block starts at an even offset (NS even)
 };
 
 struct DcPatchArgs {

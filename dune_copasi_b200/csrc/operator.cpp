@@ -125,6 +125,17 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
   // ---- mesh on the device
   const int ncomp = model->ncomp();
   coords_.upload(grid->coords, stream);
+  vector_gather_ = acfg.get("vector_gather", false);
+  if (vector_gather_ && grid->dim == 3 && !grid->coords.empty()) {
+    // padded copy for 16-byte gathers (kernels/assembly_element.cuh)
+    std::vector<double> c4((size_t)grid->nv * 4, 0.0);
+    for (int64_t v = 0; v < grid->nv; ++v)
+      for (int k = 0; k < 3; ++k) c4[v * 4 + k] = grid->coords[v * 3 + k];
+    coords4_.upload(c4, stream);
+  }
+  dofs_even_ = true;
+  for (int c = 0; c < model->ncomp(); ++c)
+    if (model->comp_nspec[c] > 0 && grid->comp_offset[c] % 2 != 0) dofs_even_ = false;
   elems_.upload(grid->elems, stream);
   if (!grid->cell_data.empty()) cell_.upload(grid->cell_data, stream);
   comp_elem_ids_.resize(ncomp);
@@ -216,6 +227,8 @@ cudaKernel_t DeviceOperator::kernel(JitGroup group, const std::string& name) {
 }
 
 DeviceOperator::~DeviceOperator() {
+  for (auto& r : prof_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : prof_pool_) cudaEventDestroy(e);
   la::reduce_workspace_destroy(&tile_ws_);
   if (stream) cudaStreamDestroy(stream);
 }
@@ -228,8 +241,11 @@ void DeviceOperator::prof_begin(const char* kind) {
   if (!profiling_) return;
   ProfRec r;
   r.kind = kind;
-  DCB_CUDA(cudaEventCreate(&r.a));
-  DCB_CUDA(cudaEventCreate(&r.b));
+  // events are pooled: creating two per kernel would show up as host-side gaps on launch-bound workloads
+  for (cudaEvent_t* e : {&r.a, &r.b}) {
+    if (!prof_pool_.empty()) { *e = prof_pool_.back(); prof_pool_.pop_back(); }
+    else DCB_CUDA(cudaEventCreate(e));
+  }
   DCB_CUDA(cudaEventRecord(r.a, stream));
   prof_.push_back(r);
 }
@@ -248,8 +264,8 @@ std::map<std::string, std::pair<double, long long>> DeviceOperator::profile_coll
       out[r.kind].first += ms;
       out[r.kind].second += 1;
     }
-    cudaEventDestroy(r.a);
-    cudaEventDestroy(r.b);
+    prof_pool_.push_back(r.a);
+    prof_pool_.push_back(r.b);
   }
   prof_.clear();
   return out;
@@ -529,6 +545,12 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       a.rowptr = (const long long*)rowptr.p; a.colidx = colidx.p; a.vals = vals;
       a.bdiag = bdiag ? bdiag + bdiag_shift(c) : nullptr;
       a.cmask = cmask.p;
+      // 16-byte gathers (padded coordinates, double2 dof loads): measured neutral on B200 (cell model on the
+      // nested mesh, 96^3: 0.170 against 0.159 ms per launch) -- the kernel is bound by the fp64 atomics of
+      // its scatter (~130 G RED/s), not by the gather wavefronts; kept as an option
+      a.coords4 = vector_gather_ ? coords4_.p : nullptr;
+      a.vec = vector_gather_ && ns % 2 == 0 && dofs_even_ &&
+              !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(z)) & 15u);
       if (mode == 3 && csr_fill_ == "gather" && !fd) {
         ensure_gather();
         const GatherSet& G = gather_[c];

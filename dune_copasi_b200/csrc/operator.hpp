@@ -146,6 +146,7 @@ class DeviceOperator {
   struct ProfRec { std::string kind; cudaEvent_t a = nullptr, b = nullptr; };
   bool profiling_ = false;
   std::vector<ProfRec> prof_;
+  std::vector<cudaEvent_t> prof_pool_;
   std::map<std::string, std::pair<double, long long>> host_prof_;
   void launch_volume(const char* kind, int mode, double t, double wM, double wA, const double* x,
                      const double* z, double* r, double* vals, double* bdiag);
@@ -160,7 +161,9 @@ class DeviceOperator {
   int struct_march_ = 8, struct_march_apply_ = 0;
   long long struct_march_fill_ = 0;
   std::string jit_defines_;
-  DeviceBuffer<double> coords_, cell_, cell_patch_;
+  DeviceBuffer<double> coords_, coords4_, cell_, cell_patch_;
+  bool vector_gather_ = false;
+  bool dofs_even_ = false;   // every compartment's dof block starts at an even offset (16-byte gathers)
   DeviceBuffer<int> elems_;
   std::vector<DeviceBuffer<int>> comp_elem_ids_, comp_vdof_;
   std::vector<int64_t> comp_nelem_;

@@ -1,5 +1,6 @@
 """Synthetic unstructured tetrahedral meshes for the multi-compartment workload (BASELINE.json configs[4],
-SURVEY.md 8d "S-MC": three nested compartments -- a sphere in a sphere and a shell around them).
+SURVEY.md 8d "S-MC": three nested compartments -- nucleus inside cytosol inside an outer shell -- with
+curved, conforming interfaces).
 
 The reference reads such meshes from Gmsh files (`grid.path`, dune/copasi/grid/make_multi_domain_grid.hh:
 40-75) and marks the compartments through the cell datum `gmsh_id`
@@ -8,11 +9,15 @@ tree and gmsh is not in the image, so the mesh comes from this generator, in the
 (coordinates, connectivity, one cell datum) the C ABI takes (`dcb_grid_create`).
 
 Construction: the cube [-1, 1]^3 as an n^3 lattice of Kuhn-split cells, vertices jittered by a seeded
-random offset (tangentially only on the interfaces and on the outer boundary), then mapped to the unit
-ball by x -> x |x|_inf / |x|_2: the cube shells |x|_inf = const become concentric spheres, so the
-compartment interfaces are exact spheres and the mesh is conforming across them.  Vertices and elements
-are then renumbered (Morton order of their positions by default, or a seeded random permutation), so that
-nothing of the lattice survives in memory: the kernels see coordinates, connectivity and cell data only.
+random offset (tangentially only on the interfaces and on the outer boundary), then bent by the smooth map
+p -> p * ((1 - a) + a g(p)), g_x = sqrt(1 - y^2/2 - z^2/2 + y^2 z^2/3) (cyclic; a = 1 would send the cube
+onto the unit ball, a = 0.7 keeps the elements well shaped along the cube's edges): the nested cube shells
+|p|_inf = const become nested closed curved surfaces, the compartment interfaces, and the mesh is conforming
+across them.  (Projecting the shells onto exact spheres was tried first: every cell on a cube edge then
+owns a simplex with all four vertices on one sphere, volume O(h^4) -- slivers that wreck the conditioning.)
+Vertices and elements are then renumbered (Morton order of their positions by default, or a seeded random
+permutation), so that nothing of the lattice survives in memory: the kernels see coordinates, connectivity
+and cell data only.
 """
 from __future__ import annotations
 
@@ -34,12 +39,13 @@ def _morton3(q):
     return spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)) | (spread(q[:, 2]) << np.uint64(2))
 
 
-def nested_spheres(n: int, radii=(0.4, 0.8), seed: int = 12345, jitter: float = 0.2, order: str = "morton"):
+def nested_compartments(n: int, radii=(0.4, 0.8), seed: int = 12345, jitter: float = 0.2, order: str = "morton",
+                        roundness: float = 0.7):
     """-> coords [nv, 3] float64, elems [ne, 4] int32, cell_keys ["gmsh_id"], cell_data [1, ne] float64.
 
     n      cells per axis of the underlying lattice (even); ne = 6 n^3, nv = (n + 1)^3
-    radii  radii of the two interfaces inside the unit ball (rounded to lattice shells): gmsh_id = 1 inside
-           the first (nucleus), 2 between them (cytosol), 3 outside the second (shell / extracellular space)
+    radii  parametric size of the two interfaces (rounded to lattice shells): gmsh_id = 1 inside the first
+           (nucleus), 2 between them (cytosol), 3 outside the second (shell / extracellular space)
     order  "morton" | "random" | "lattice": numbering of vertices and elements
     """
     if n < 4 or n % 2:
@@ -61,10 +67,10 @@ def nested_spheres(n: int, radii=(0.4, 0.8), seed: int = 12345, jitter: float = 
     dp[on_surface[:, None] & at_max] = 0.0                          # interfaces / boundary: tangential jitter only
     dp[shell == 0] = 0.0
     p = p + dp
-    ninf = np.abs(p).max(1)
-    n2 = np.sqrt((p * p).sum(1))
-    scale = np.divide(ninf, n2, out=np.ones_like(ninf), where=n2 > 0)
-    coords = p * scale[:, None]
+    x2, y2, z2 = p[:, 0] ** 2, p[:, 1] ** 2, p[:, 2] ** 2
+    g = np.stack([np.sqrt(1 - y2 / 2 - z2 / 2 + y2 * z2 / 3), np.sqrt(1 - z2 / 2 - x2 / 2 + z2 * x2 / 3),
+                  np.sqrt(1 - x2 / 2 - y2 / 2 + x2 * y2 / 3)], 1)
+    coords = p * ((1.0 - roundness) + roundness * g)
     # Kuhn split: from the lowest corner of a cell step the axes in the order of the permutation
     ci = np.arange(n, dtype=np.int64)
     CI, CJ, CK = np.meshgrid(ci, ci, ci, indexing="ij")
@@ -84,7 +90,7 @@ def nested_spheres(n: int, radii=(0.4, 0.8), seed: int = 12345, jitter: float = 
     # orientation / validity
     X = coords[elems]
     vol = np.einsum("ij,ij->i", np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]), X[:, 3] - X[:, 0]) / 6.0
-    if not (np.abs(vol) > 1e-6 * h ** 3).all():      # (the Kuhn simplices alternate in orientation; |det| is what counts)
+    if not (np.abs(vol) > 1e-3 * h ** 3).all():      # (the Kuhn simplices alternate in orientation; |det| is what counts)
         raise RuntimeError("degenerate tetrahedra: reduce the jitter")
     # renumber
     nv, ne = coords.shape[0], elems.shape[0]
@@ -108,7 +114,7 @@ def nested_spheres(n: int, radii=(0.4, 0.8), seed: int = 12345, jitter: float = 
     return coords, elems, ["gmsh_id"], cell_data
 
 
-def nested_spheres_stats(coords, elems, cell_data):
+def mesh_stats(coords, elems, cell_data):
     X = coords[elems]
     vol = np.abs(np.einsum("ij,ij->i", np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]), X[:, 3] - X[:, 0])) / 6.0
     ids = cell_data[0]

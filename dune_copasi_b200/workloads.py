@@ -208,12 +208,12 @@ def _on_gmsh_ids(text: str) -> str:
             "nucleus.expression = (gmsh_id == 1)\n[parser_context]" + tail)
 
 
-# BASELINE configs[4]: the 10-species model on the nested-spheres tetrahedral mesh of meshgen.nested_spheres
-CELL10_SPHERES = _on_gmsh_ids(CELL10)
-CELL_SPHERES = _on_gmsh_ids(CELL)
+# BASELINE configs[4]: the 10-species model on the nested-compartment tetrahedral mesh of meshgen.nested_compartments
+CELL10_NESTED = _on_gmsh_ids(CELL10)
+CELL_NESTED = _on_gmsh_ids(CELL)
 
-WORKLOADS = {"grayscott": GRAY_SCOTT, "cell": CELL, "cell10": CELL10, "cell_spheres": CELL_SPHERES,
-             "cell10_spheres": CELL10_SPHERES}
+WORKLOADS = {"grayscott": GRAY_SCOTT, "cell": CELL, "cell10": CELL10, "cell_nested": CELL_NESTED,
+             "cell10_nested": CELL10_NESTED}
 
 
 def config(name: str, **overrides) -> Config:

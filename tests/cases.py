@@ -18,7 +18,8 @@ if ROOT not in sys.path:
 from oracle import core as ORC  # noqa: E402
 from oracle import ini as INI  # noqa: E402
 from oracle import mesh as OMESH  # noqa: E402
-from dune_copasi_b200.workloads import CELL, CELL10, GRAY_SCOTT, SOLVER  # noqa: E402  (the bench workloads live with the package)
+from dune_copasi_b200.workloads import CELL, CELL10, CELL10_NESTED, GRAY_SCOTT, SOLVER  # noqa: E402  (the bench workloads live with the package)
+from dune_copasi_b200 import meshgen as MESHGEN  # noqa: E402
 
 
 # test/gauss.ini: single compartment, linear diffusion of a Gaussian, D = 0.005, t in [1, 1.2]
@@ -402,6 +403,17 @@ CASES = {
     "advection2d": Case("advection2d", ADVECTION, 2, _s(2, 12), dt=0.05, structured=([12, 12], [0, 0], [1, 1])),
     "advection3d": Case("advection3d", ADVECTION, 3, _s(3, 5), dt=0.05, structured=([5, 5, 5], [0, 0, 0], [1, 1, 1])),
 }
+
+
+def nested_mesh(n=8, order="morton"):
+    """BASELINE configs[4] in miniature: the unstructured tetrahedral mesh of three nested compartments"""
+    coords, elems, keys, data = MESHGEN.nested_compartments(n, order=order)
+    m = OMESH.Mesh(dim=3, coords=coords, elems=elems)
+    m.cell_keys, m.cell_data = keys, data
+    return m
+
+
+CASES["cell10_nested"] = Case("cell10_nested", CELL10_NESTED, 3, nested_mesh, dt=0.05)
 
 
 def _p1(name, ini, dim, cells, origin, extent, **kw):

@@ -96,7 +96,7 @@ def test_jacobian_apply(name, scheme):
 
 
 @pytest.mark.parametrize("scheme", ["auto", "patch", "atomic"])
-@pytest.mark.parametrize("name", ["grayscott3d", "cell3d", "two_disks", "gauss2d"])
+@pytest.mark.parametrize("name", ["grayscott3d", "cell3d", "two_disks", "gauss2d", "grayscott3d_aniso", "cell10_nested"])
 def test_block_diagonal(name, scheme):
     case, om, cfg, model, grid, op = make(name, **{"model.assembly.b200.scheme": scheme})
     x = K.rand_state(om.ndofs, 6)
@@ -265,7 +265,9 @@ STEP_CASES = [("gauss2d", "Alexander2", 2), ("gauss3d", "ImplicitEuler", 2), ("e
               ("grayscott2d", "RungeKutta4", 2), ("mitchell_schaefer", "Alexander3", 2),
               ("grayscott2d", "FractionalStepTheta", 2), ("advection2d", "Alexander2", 2),
               ("advection3d", "ImplicitEuler", 2), ("two_disks_cell_data", "Alexander2", 1),
-              ("cell3d_10", "ImplicitEuler", 1)]
+              ("cell3d_10", "ImplicitEuler", 1), ("cell10_nested", "ImplicitEuler", 1),
+              ("grayscott3d_aniso", "Alexander2", 2), ("grayscott2d_aniso", "ImplicitEuler", 2),
+              ("poisson_aniso", "ImplicitEuler", 1), ("gauss3d_aniso", "Alexander2", 2), ("advection3d_aniso", "ImplicitEuler", 1)]
 
 
 @pytest.mark.parametrize("matrix_free", [False, True])

@@ -148,7 +148,7 @@ def test_partition_halo_gloo(name, size, structured):
 
 
 @pytest.mark.parametrize("name,size,method", [("cell3d", 3, "rcb"), ("two_disks", 4, "rcb"), ("grayscott3d", 2, "range"),
-                                              ("cell3d", 3, "range"), ("two_disks_cell_data", 2, "rcb")])
+                                              ("cell3d", 3, "range"), ("two_disks_cell_data", 2, "rcb"), ("cell10_nested", 4, "rcb")])
 def test_partition_methods_gloo(name, size, method):
     """Recursive coordinate bisection (any rank count) and contiguous vertex ranges on general meshes: the
     same owner-computes checks as above (bit-exact maps against the serial numbering, halo plan complete,
