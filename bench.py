@@ -141,6 +141,43 @@ def measured_traffic(kernel, cells, world, elem=""):
     return json.load(open(path)).get(f"{kernel}@{cells}^3/n{world}" + elem)
 
 
+def timeline(torch, run, rank, path):
+    """Device timeline of `run()` from CUPTI activity records (torch.profiler): per kernel name the launches, the
+    busy time and the idle time on the device right before it; what nsys would show (not installed here)."""
+    import tempfile
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as p:
+        run()
+    if rank != 0:
+        return None
+    with tempfile.NamedTemporaryFile(suffix=".json") as f:
+        p.export_chrome_trace(f.name)
+        ev = json.load(open(f.name))["traceEvents"]
+    dev = sorted((e for e in ev if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "dur" in e),
+                 key=lambda e: e["ts"])
+    if not dev:
+        return {"error": "no device records"}
+    per, end = {}, None
+    for e in dev:
+        name = e["name"].split("(")[0].split("<")[0]
+        if e["cat"] != "kernel":
+            name = e["cat"] + ":" + name
+        r = per.setdefault(name, {"n": 0, "busy_us": 0.0, "gap_before_us": 0.0})
+        r["n"] += 1
+        r["busy_us"] += e["dur"]
+        if end is not None:
+            r["gap_before_us"] += max(0.0, e["ts"] - end)
+        end = max(end or 0.0, e["ts"] + e["dur"])
+    span = dev[-1]["ts"] + dev[-1]["dur"] - dev[0]["ts"]
+    busy = sum(r["busy_us"] for r in per.values())
+    out = {"span_ms": span / 1e3, "busy_ms": busy / 1e3, "idle_ms": (span - busy) / 1e3, "records": len(dev),
+           "kernels": {k: {"n": v["n"], "busy_ms": round(v["busy_us"] / 1e3, 4), "gap_before_ms": round(v["gap_before_us"] / 1e3, 4)}
+                       for k, v in sorted(per.items(), key=lambda kv: -kv[1]["busy_us"] - kv[1]["gap_before_us"])}}
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    json.dump(out, open(path, "w"), indent=1)
+    return {k: out[k] for k in ("span_ms", "busy_ms", "idle_ms", "records")}
+
+
 def cpu_baseline(args, steps, warmup, cells):
     """The oracle restatement (kind "port": the reference itself needs a DUNE stack that is not
     available) with OpenMP over all host cores, on a bounded sample of the workload."""
@@ -237,6 +274,8 @@ def main():
                          "compartments (BASELINE configs[4]; dune_copasi_b200/meshgen.py, 6 cells^3 tets, RCB partition)")
     ap.add_argument("--b200", default="", help="model.assembly.b200.* overrides, e.g. patch_elements=768,patch_min_blocks=4")
     ap.add_argument("--set", default="", help="any ini key overrides, e.g. model.time_step_operator.linear_solver.b200.speculation=false")
+    ap.add_argument("--timeline", default="", help="also run 2 steps under torch.profiler (CUPTI kernel records) and "
+                    "write the per-kernel busy time and the idle gaps on the stream to this JSON file (rank 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-q1", action="store_true", help="skip the Q1 variant that rides along with the P1 headline")
@@ -337,25 +376,36 @@ def main():
         st.get_state(u_start)
         t_start = st.time
         s0 = st.stats()
-        D.lib().dcb_operator_profile(op.h, 1)
         sampler.begin()
         ms = timed(args.steps, False)
         sampler.end()
+        s_timed = st.stats()
+        clocks = sampler.stop() if rank == 0 else None
+        # per-kernel durations: the same K steps replayed (state rewound) with a CUDA event pair around every
+        # launch on the operator's stream -- kept out of the timed pass, where the event records would sit
+        # between the kernels (measured: 2-7 % of the step at N = 8)
+        st.set_state(u_start, t_start)
+        D.lib().dcb_operator_profile(op.h, 1)
+        ms_prof = timed(args.steps, False)
         prof = op.profile()
         host = {k: v for k, v in prof.items() if k.startswith("host_")}     # host-side timers (ms)
         prof = {k: v for k, v in prof.items() if not k.startswith("host_")}
         D.lib().dcb_operator_profile(op.h, 0)
         s1 = st.stats()
-        clocks = sampler.stop() if rank == 0 else None
+        tl = None
+        if args.timeline:
+            st.set_state(u_start, t_start)
+            tl = timeline(torch, lambda: timed(min(args.steps, 2), False), rank, args.timeline)
         e2e = None
         if not args.no_e2e:
             st.set_state(u_start, t_start)
+            s1e = st.stats()
             ms_e2e = timed(args.steps, True)
             s2 = st.stats()
             nbytes = op.ndofs * 8
             e2e = {"value": ndofs_global * args.steps / (ms_e2e * 1e-3), "unit": "DOF-updates/s",
                    "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / args.steps,
-                   "solver_stats": {k: s2[k] - s1[k] for k in s2},
+                   "solver_stats": {k: s2[k] - s1e[k] for k in s2},
                    "note": "same K steps as `value` (state rewound), host buffers in pinned memory, "
                            "H2D of the state before and D2H after every step inside the timed region"}
 
@@ -373,7 +423,7 @@ def main():
         if rank != 0:
             shutdown()
             return None
-        d = {k: s1[k] - s0[k] for k in s1}
+        d = {k: s_timed[k] - s0[k] for k in s_timed}
         value = ndofs_global * args.steps / (ms * 1e-3)
         # ---- roofline of the dominant kernel (by accumulated device time in the timed region)
         peak, peak_src = peaks()
@@ -416,7 +466,7 @@ def main():
             roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": measured_traffic(top, args.cells, world, "/q1" if args.element == "q1" else ""), "algorithmic_bytes": alg.get(top, 0.0),
                     "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches": prof[top]["launches"],
-                    "share_of_step": prof[top]["ms"] / ms,
+                    "share_of_step": prof[top]["ms"] / ms_prof, "profiled_ms_per_step": ms_prof / args.steps,
                     "breakdown_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
                     "host_ms_per_step": {k: v["ms"] / args.steps for k, v in host.items()}}
             # the assembly kernels are fp64-pipe bound on B200 (64 fp64 lanes/SM/clk), not HBM bound:
@@ -438,6 +488,8 @@ def main():
                 "time_steps_per_s": args.steps / (ms * 1e-3), "dofs": int(ndofs_global), "elements": int(ne_global), "e2e": e2e,
                 "gpu_launches": int(d["kernel_launches"]), "clocks": clocks, "roofline": roof, "cpu_baseline": cb,
                 "solver_stats": d, "setup_s": t_setup}
+        if tl is not None:
+            line["timeline"] = tl
         shutdown()
         return line
 

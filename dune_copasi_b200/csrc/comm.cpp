@@ -90,9 +90,30 @@ struct NcclCommunicator : Communicator {
     }
     if (comm) nccl().CommDestroy(comm);
   }
+  DeviceBuffer<int> error_flag;   // raised by a bounded spin that gave up
+
+  bool reduce_links_ready() const override { return peer_active; }
+  bool push_links_ready() const override { return peer_active && peer_halo; }
+  void link_reduce(peer::Link* l) override {
+    l->m = boxes; l->h = hargs; l->reduce = 1; l->ar_seq = ++ar_seq;
+  }
+  void link_push(peer::Link* l) override {
+    l->m = boxes; l->h = hargs; l->push = 1; l->halo_seq = ++halo_seq;
+  }
+  void halo_pull(double* x, cudaStream_t s) override {
+    peer::halo_pull(boxes, hargs, x, halo_seq, s);
+    DCB_CUDA(cudaGetLastError());
+    launches++;
+  }
+  bool peer_error() override {
+    if (!peer_active) return false;
+    int e = 0;
+    DCB_CUDA(cudaMemcpy(&e, error_flag.p, sizeof e, cudaMemcpyDeviceToHost));
+    return e != 0;
+  }
   void allreduce_sum(double* dev, int n, cudaStream_t s) override {
     if (peer_active && n <= peer::kMaxWords) {
-      peer::allreduce(boxes, dev, n, ++ar_seq, s);
+      peer::allreduce(boxes, dev, n, ++ar_seq, error_flag.p, s);
       DCB_CUDA(cudaGetLastError());
     } else {
       DCB_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclSum, comm, s));
@@ -153,6 +174,9 @@ struct NcclCommunicator : Communicator {
     }
     boxes.rank = rank; boxes.size = size; boxes.cap = cap;
     peer_active = true;
+    error_flag.alloc(1);
+    error_flag.zero();
+    hargs.error = error_flag.p;
     peer_halo = halo_all;
     if (peer_halo) {
       ticket.alloc(1);

@@ -1,5 +1,7 @@
 #include "expr.hpp"
 
+#include <mutex>
+
 #include <algorithm>
 
 #include <cfloat>
@@ -196,8 +198,27 @@ NodeP subst(const NodeP& a, const std::map<std::string, NodeP>& env) {
   return n;
 }
 
+// tables by their unique key: trees carry only the key (Op::Call), evaluation and lowering look the data up here
+std::map<std::string, std::shared_ptr<const Table>>& table_registry() {
+  static std::map<std::string, std::shared_ptr<const Table>> r;
+  return r;
+}
+std::mutex& table_mutex() { static std::mutex m; return m; }
+std::shared_ptr<const Table> find_table(const std::string& key) {
+  if (key.rfind("dc_tab_", 0) != 0) return nullptr;
+  std::lock_guard<std::mutex> lock(table_mutex());
+  auto it = table_registry().find(key);
+  return it == table_registry().end() ? nullptr : it->second;
+}
+
 double apply1(const std::string& f, double a, bool* ok) {
   *ok = true;
+  if (auto t = find_table(f)) {
+    bool oob = false;
+    double v = t->eval(a, &oob);
+    if (oob) fail("interpolation of function '", t->name, "' is out of bounds: ", a, " not in [", t->domain[0], ", ", t->domain[1], "]");
+    return v;
+  }
   if (f == "sqrt") return std::sqrt(a);
   if (f == "exp") return std::exp(a);
   if (f == "log" || f == "ln") return std::log(a);
@@ -264,6 +285,7 @@ NodeP fold(const NodeP& a) {
     case Op::Call: {
       bool ok = false;
       double v = 0;
+      if (a->name.rfind("dc_tab_", 0) == 0) return a;   // tabulated functions are folded in resolve_rec
       if (a->kids.size() == 1) v = apply1(a->name, a->kids[0]->num, &ok);
       else if (a->kids.size() >= 2) {
         v = a->kids[0]->num;
@@ -291,13 +313,24 @@ NodeP resolve_rec(const NodeP& a, const ParserContext& ctx, int depth) {
   for (auto& k : n->kids) k = resolve_rec(k, ctx, depth);
   if (n->op == Op::Call) {
     auto it = ctx.functions.find(n->name);
-    if (it != ctx.functions.end()) {
+    if (it != ctx.functions.end() && !ctx.tables.count(n->name)) {
       const auto& fn = it->second;
       if (fn.args.size() != n->kids.size())
         fail("function '", n->name, "' expects ", fn.args.size(), " arguments, got ", n->kids.size());
       std::map<std::string, NodeP> env;
       for (size_t i = 0; i < fn.args.size(); ++i) env[fn.args[i]] = n->kids[i];
       return resolve_rec(subst(parse_expr(fn.body), env), ctx, depth + 1);
+    }
+    auto tb = ctx.tables.find(n->name);
+    if (tb != ctx.tables.end()) {
+      if (n->kids.size() != 1) fail("function '", n->name, "' expects 1 argument, got ", n->kids.size());
+      n->name = tb->second->key;
+      if (n->kids[0]->op == Op::Num) {   // constant argument: fold unless it is out of bounds (left to run time)
+        bool oob = false;
+        double v = tb->second->eval(n->kids[0]->num, &oob);
+        if (!oob) return mk_num(v);
+      }
+      return n;
     }
     if (n->name == "if" && n->kids.size() == 3) return fold(mk(Op::Sel, n->kids));
   }
@@ -339,8 +372,39 @@ ParserContext::Fn parse_function_expression(const std::string& e, const std::str
   return fn;
 }
 
+// std::lerp as libstdc++ implements it (the reference calls std::lerp): exact at the ends, monotonic
+static double lerp_std(double a, double b, double t) {
+  if ((a <= 0 && b >= 0) || (a >= 0 && b <= 0)) return t * b + (1 - t) * a;
+  if (t == 1) return b;
+  const double x = a + t * (b - a);
+  return (t > 1) == (b > a) ? (b < x ? x : b) : (x < b ? x : b);
+}
+
+double Table::eval(double x, bool* out_of_bounds) const {
+  if (kind == 0) {   // context.cc:83-95
+    const size_t d = std::lower_bound(domain.begin(), domain.end(), x) - domain.begin();
+    if (d == 0) return range.front();
+    if (d == domain.size()) return range.back();
+    return lerp_std(range[d - 1], range[d], (x - domain[d - 1]) / (domain[d] - domain[d - 1]));
+  }
+  // context.cc:256-277
+  const double d0 = domain[0], d1 = domain[1];
+  const size_t n = range.size() - 1;   // intervals
+  if (clamp) x = d0 < x ? x : d0;
+  else if (x < d0 || x > d1 || !(x == x)) {
+    if (out_of_bounds) *out_of_bounds = true;
+    return std::nan("");
+  }
+  double interval = (x - d0) * ((double)n / (d1 - d0));
+  double whole;
+  std::modf(interval, &whole);
+  size_t k = whole <= 0.0 ? 0 : (whole >= (double)n ? n : (size_t)whole);
+  return range[k];
+}
+
 ParserContext ParserContext::from_config(const PTree& pc) {
   ParserContext ctx;
+  std::vector<std::string> sampled;   // functions with interpolate = true: tabulated once the context is complete
   for (auto& name : pc.sub_keys()) {
     const PTree& s = pc.sub(name);
     std::string type = s.get("type", std::string());
@@ -348,12 +412,115 @@ ParserContext ParserContext::from_config(const PTree& pc) {
       ctx.constants[name] = s.get("value", 0.0);
     } else if (type == "function") {
       ctx.functions[name] = parse_function_expression(s.get("expression", std::string()), "parser_context." + name);
+      if (s.get("interpolate", false)) sampled.push_back(name);
+    } else if (type == "interpolation") {
+      auto t = std::make_shared<Table>();
+      t->kind = 0;
+      t->name = name;
+      t->domain = s.get_vec("domain", {});
+      t->range = s.get_vec("range", {});
+      if (!std::is_sorted(t->domain.begin(), t->domain.end())) fail("parser_context.", name, ": the interpolation domain must be sorted");
+      if (t->domain.size() < 2 || t->domain.size() != t->range.size())
+        fail("parser_context.", name, ": interpolation range and domain must have at least two points and be the same size");
+      ctx.tables[name] = t;
     } else if (!type.empty()) {
-      // interpolation / tiff / random_field context entries are outside the hot path
+      // tiff needs libtiff and image files (the reference's test images are git-LFS pointers), random_field
+      // needs parafields: both only feed initial conditions, outside the hot path
       fail("parser_context.", name, ": type '", type, "' is not supported by this build");
     }
   }
+  for (auto& name : sampled) {
+    const PTree& s = pc.sub(name);
+    const Fn fn = ctx.functions.at(name);
+    if (fn.args.size() != 1) fail("parser_context.", name, ": cannot interpolate a function with ", fn.args.size(), " arguments");
+    const long long intervals = s.get("interpolation.intervals", 1000);
+    if (intervals > 100000) fail("parser_context.", name, ": number of interpolation intervals is too big");
+    if (intervals < 1) fail("parser_context.", name, ": at least one interval is required");
+    auto t = std::make_shared<Table>();
+    t->kind = 1;
+    t->name = name;
+    t->domain = s.get_vec("interpolation.domain." + fn.args[0], {0.0, 1.0});
+    if (t->domain.size() != 2 || t->domain[0] >= t->domain[1]) fail("parser_context.", name, ": domain arguments are not ordered");
+    const std::string ooo = s.get("interpolation.out_of_bounds", std::string("error"));
+    if (ooo != "clamp" && ooo != "error") fail("parser_context.", name, ": not known interpolation.out_of_bounds = ", ooo);
+    t->clamp = ooo == "clamp";
+    // sample the function itself (it may use the context's constants and its other, untabulated functions)
+    ParserContext plain = ctx;
+    plain.tables.clear();
+    NodeP body = resolve_expr(parse_expr(fn.body), plain);
+    const double width = (t->domain[1] - t->domain[0]) / (double)intervals;
+    t->range.resize((size_t)intervals + 1);
+    for (size_t i = 0; i < t->range.size(); ++i) {
+      const double x = t->domain[0] + (double)i * width;
+      t->range[i] = eval_expr(body, [&](const std::string& v) -> double {
+        if (v != fn.args[0]) fail("parser_context.", name, ": unknown symbol '", v, "' while sampling the function");
+        return x;
+      });
+    }
+    ctx.tables[name] = t;
+  }
+  // unique keys: the data decides, so equal tables of different models share a symbol and different ones never clash
+  for (auto& kv : ctx.tables) {
+    auto t = std::const_pointer_cast<Table>(kv.second);
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) {
+      for (size_t i = 0; i < n; ++i) { h ^= ((const unsigned char*)p)[i]; h *= 1099511628211ull; }
+    };
+    mix(&t->kind, sizeof t->kind); mix(&t->clamp, sizeof t->clamp);
+    mix(t->domain.data(), t->domain.size() * sizeof(double));
+    mix(t->range.data(), t->range.size() * sizeof(double));
+    char buf[32];
+    snprintf(buf, sizeof buf, "%016llx", h);
+    std::string id;
+    for (char ch : kv.first) id += (isalnum((unsigned char)ch) ? ch : '_');
+    t->key = "dc_tab_" + id + "_" + buf;
+    std::lock_guard<std::mutex> lock(table_mutex());
+    table_registry()[t->key] = t;
+  }
   return ctx;
+}
+
+std::string ParserContext::cuda_tables() const {
+  std::ostringstream o;
+  if (!tables.empty())
+    o << "__device__ __forceinline__ double dc_lerp(double a, double b, double t) {\n"
+         "  if ((a <= 0 && b >= 0) || (a >= 0 && b <= 0)) return t * b + (1 - t) * a;\n"
+         "  if (t == 1) return b;\n"
+         "  const double x = a + t * (b - a);\n"
+         "  return (t > 1) == (b > a) ? (b < x ? x : b) : (x < b ? x : b);\n}\n";
+  std::set<std::string> done;
+  for (auto& kv : tables) {
+    const Table& t = *kv.second;
+    if (!done.insert(t.key).second) continue;
+    auto array = [&](const char* what, const std::vector<double>& v) {
+      o << "__device__ const double " << t.key << "_" << what << "[" << v.size() << "] = {";
+      for (size_t i = 0; i < v.size(); ++i) o << (i ? ", " : "") << num_lit(v[i]);
+      o << "};\n";
+    };
+    array("r", t.range);
+    if (t.kind == 0) {
+      array("d", t.domain);
+      const size_t n = t.domain.size();
+      // std::lower_bound: first index with domain[index] >= x
+      o << "__device__ __noinline__ double " << t.key << "(double x) {\n"
+        << "  int lo = 0, hi = " << n << ";\n"
+        << "  while (lo < hi) { const int mid = (lo + hi) >> 1; if (" << t.key << "_d[mid] < x) lo = mid + 1; else hi = mid; }\n"
+        << "  if (lo == 0) return " << t.key << "_r[0];\n"
+        << "  if (lo == " << n << ") return " << t.key << "_r[" << n - 1 << "];\n"
+        << "  return dc_lerp(" << t.key << "_r[lo - 1], " << t.key << "_r[lo], (x - " << t.key << "_d[lo - 1]) / (" << t.key
+        << "_d[lo] - " << t.key << "_d[lo - 1]));\n}\n";
+    } else {
+      const size_t n = t.range.size() - 1;
+      o << "__device__ __noinline__ double " << t.key << "(double x) {\n"
+        << "  const double d0 = " << num_lit(t.domain[0]) << ", d1 = " << num_lit(t.domain[1]) << ";\n";
+      if (t.clamp) o << "  x = d0 < x ? x : d0;\n";
+      else o << "  if (x < d0 || x > d1 || !(x == x)) return 0.0 / 0.0;\n";
+      o << "  double whole;\n  modf((x - d0) * (" << num_lit((double)n) << " / (d1 - d0)), &whole);\n"
+        << "  const int k = whole <= 0.0 ? 0 : (whole >= " << num_lit((double)n) << " ? " << n << " : (int)whole);\n"
+        << "  return " << t.key << "_r[k];\n}\n";
+    }
+  }
+  return o.str();
 }
 
 bool expr_is_absent(const std::string& text) {
@@ -477,6 +644,7 @@ std::string to_cuda(const NodeP& a, const std::function<std::string(const std::s
       static const std::map<std::string, std::string> two = {
           {"min", "dc_min"}, {"max", "dc_max"}, {"atan2", "atan2"}, {"pow", "pow"}};
       if (a->kids.size() == 1 && one.count(f)) return one.at(f) + "(" + rec(a->kids[0]) + ")";
+      if (a->kids.size() == 1 && f.rfind("dc_tab_", 0) == 0) return f + "(" + rec(a->kids[0]) + ")";
       if (a->kids.size() >= 2 && two.count(f)) {
         std::string r = rec(a->kids[0]);
         for (size_t i = 1; i < a->kids.size(); ++i) r = two.at(f) + "(" + r + ", " + rec(a->kids[i]) + ")";
@@ -727,6 +895,8 @@ NodeP diff(const NodeP& a, const std::string& var) {
         }
         return diff(acc, var);
       }
+      if (f.rfind("dc_tab_", 0) == 0)
+        fail("cannot differentiate a tabulated context function symbolically: give the jacobian entries in the ini");
       fail("cannot differentiate function '", f, "' with ", a->kids.size(), " argument(s)");
     }
   }

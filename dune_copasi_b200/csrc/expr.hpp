@@ -31,11 +31,31 @@ struct Node {
   std::vector<NodeP> kids;
 };
 
+// Tabulated one-argument context functions (src/dune/copasi/parser/context.cc):
+//   kind 0  `type = interpolation` (:72-97): sorted `domain`, `range`; lower_bound, constant outside, std::lerp inside;
+//   kind 1  `type = function` with `interpolate = true` (:237-283): the function sampled on `intervals` equal
+//           intervals of `interpolation.domain.<arg>`, `interpolation.out_of_bounds = error | clamp`.  Restated
+//           literally: the reference forms i = max(0, k) and j = min(k, intervals + 1) from the same interval
+//           number k, i.e. it returns sample k (piecewise constant, lerp(g[k], g[k], t)); `clamp` is
+//           std::clamp(domain[0], pos, domain[1]) = max(domain[0], pos) (arguments in that order).  Where the
+//           reference would read past the table (pos > domain[1] under `clamp`) the last sample is used;
+//           `error` yields NaN on the device (the reference throws) and throws on the host.
+struct Table {
+  int kind = 0;
+  std::vector<double> domain, range;   // kind 1: domain = {d0, d1}, range = the intervals + 1 samples
+  bool clamp = false;
+  std::string name, key;               // context name; unique symbol used in trees and generated code
+  double eval(double x, bool* out_of_bounds = nullptr) const;
+};
+
 struct ParserContext {
   std::map<std::string, double> constants;
   struct Fn { std::vector<std::string> args; std::string body; };
   std::map<std::string, Fn> functions;
+  std::map<std::string, std::shared_ptr<const Table>> tables;   // context name -> table
   static ParserContext from_config(const PTree& parser_context);
+  // CUDA C definitions of the tables (constant arrays + evaluation functions named after Table::key)
+  std::string cuda_tables() const;
 };
 
 // "a, b: body" (ParserContext::parse_function_expression, src/dune/copasi/parser/context.cc)

@@ -317,46 +317,70 @@ __device__ __forceinline__ void dc_cell_index(const DcStructArgs& a, long long c
 #endif
 }
 
-// ---- driver 1: one thread per cell, one reduction per corner value (all modes)
+// ---- driver 1: one thread per cell (all modes).  The lanes of a warp hold consecutive cells of a lattice row, so
+// the x = 1 corners of lane l are the x = 0 corners of lane l + 1: those halves are summed through a warp shuffle
+// first, and only one reduction per *vertex* value leaves the warp (plus the last lane's x = 1 half).  ncu on the
+// 256^3 apply had the L2's atomic unit at 90 % of its peak (`lts__d_atomic_input_cycles_active`,
+// profiles/r02_struct_apply_256_ncu.txt) next to the fp64 pipe at 77 %: this halves the `RED` sectors.
 template <int C, int MODE, class CellFn>
 __device__ __forceinline__ void dc_struct_per_cell(const DcStructArgs& a, CellFn cell_fn) {
   typedef DcComp<C> M;
   constexpr int NS = M::NS;
   constexpr int NV = MODE == 2 ? NS * NS : NS;
   const long long cell = a.cell_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (cell >= a.ncells) return;
-  int idx[3];
-  dc_cell_index(a, cell, idx);
-  long long stride[3] = {1, a.n[0] + 1, (long long)(a.n[0] + 1) * (a.n[1] + 1)};
-  long long base = 0;
+  const bool active = cell < a.ncells;     // idle lanes stay for the shuffles
+  int idx[3] = {0, 0, 0};
+  double acc[DC_NCORN][NV];
+  // dof of corner m = d0 + off(m): one 64-bit base and two 32-bit plane strides instead of 2^d 64-bit indices
+  long long d0 = 0;
+  const int o1 = (a.n[0] + 1) * NS, o2 = DC_DIM == 3 ? o1 * (a.n[1] + 1) : 0;
+  auto off = [&](int m) { return ((m & 1) ? NS : 0) + ((m & 2) ? o1 : 0) + ((m & 4) ? o2 : 0); };
+  if (active) {
+    dc_cell_index(a, cell, idx);
+    d0 = a.dof_offset + (idx[0] * (long long)NS + idx[1] * (long long)o1 + idx[2] * (long long)o2);
+    double U[DC_NCORN][NS], Z[MODE == 1 ? DC_NCORN : 1][NS];
+    const double* xb = a.x + d0;
+    const double* zb = MODE == 1 ? a.z + d0 : nullptr;
+    const unsigned char* mb = a.cmask ? a.cmask + d0 : nullptr;
 #pragma unroll
-  for (int k = 0; k < DC_DIM; ++k) base += idx[k] * stride[k];
-  double U[DC_NCORN][NS], Z[MODE == 1 ? DC_NCORN : 1][NS], acc[DC_NCORN][NV];
-  long long dof[DC_NCORN];
+    for (int m = 0; m < DC_NCORN; ++m) {
 #pragma unroll
-  for (int m = 0; m < DC_NCORN; ++m) {
-    long long v = base;
-#pragma unroll
-    for (int k = 0; k < DC_DIM; ++k) v += ((m >> k) & 1) * stride[k];
-    dof[m] = a.dof_offset + v * NS;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      U[m][s] = a.x[dof[m] + s];
-      if (MODE == 1) Z[m][s] = (a.cmask && a.cmask[dof[m] + s]) ? 0.0 : a.z[dof[m] + s];
+      for (int s = 0; s < NS; ++s) {
+        U[m][s] = xb[off(m) + s];
+        if (MODE == 1) Z[m][s] = (mb && mb[off(m) + s]) ? 0.0 : zb[off(m) + s];
+      }
     }
+    cell_fn(idx, U, Z, acc);
+  } else {
+#pragma unroll
+    for (int m = 0; m < DC_NCORN; ++m)
+#pragma unroll
+      for (int s = 0; s < NV; ++s) acc[m][s] = 0.0;
   }
-  cell_fn(idx, U, Z, acc);
+  // lane l - 1 holds the cell to the left iff this cell is not the first of its row; it keeps its x = 1 half iff
+  // it is the last lane, the last cell of its row or the last cell of the launch
+  const int lane = threadIdx.x & 31;
+  const bool take = active && lane > 0 && idx[0] > 0;
+  const bool keep = lane == 31 || idx[0] + 1 == a.n[0] || cell + 1 >= a.ncells;
+#pragma unroll
+  for (int m = 1; m < DC_NCORN; m += 2)
+#pragma unroll
+    for (int s = 0; s < NV; ++s) {
+      const double t = __shfl_up_sync(0xffffffffu, acc[m][s], 1);
+      if (take) acc[m - 1][s] += t;
+    }
+  if (!active) return;
 #pragma unroll
   for (int m = 0; m < DC_NCORN; ++m) {
+    if ((m & 1) && !keep) continue;
     if (MODE == 2) {
+      double* out = a.bdiag + (d0 + off(m)) * NS;
 #pragma unroll
-      for (int s = 0; s < NV; ++s) dc_atomic_add(&a.bdiag[dof[m] * NS + s], acc[m][s]);
-    } else if (MODE == 3) {   // scalar diagonal, vector layout
+      for (int s = 0; s < NV; ++s) dc_atomic_add(out + s, acc[m][s]);
+    } else {   // residual / apply into r; scalar diagonal into a vector laid out like r
+      double* out = (MODE == 3 ? a.bdiag : a.r) + d0 + off(m);
 #pragma unroll
-      for (int s = 0; s < NS; ++s) dc_atomic_add(&a.bdiag[dof[m] + s], acc[m][s]);
-    } else {
-#pragma unroll
-      for (int s = 0; s < NS; ++s) dc_atomic_add(&a.r[dof[m] + s], acc[m][s]);
+      for (int s = 0; s < NS; ++s) dc_atomic_add(out + s, acc[m][s]);
     }
   }
 }

@@ -4,6 +4,8 @@
 // SMs, reductions deterministic (fixed grid, ordered final sum).
 #include "linalg.hpp"
 
+#include "peer_device.cuh"
+
 #include "../util.hpp"
 
 namespace dcb {
@@ -28,10 +30,14 @@ __device__ __forceinline__ bool in_ranges(const Ranges& r, long long i) {
   return hit;
 }
 
-// block reduce NOUT values, then "last block sums the partials in order"
+// block reduce NOUT values, then "last block sums the partials in order".  With a link the last block goes on:
+// it publishes the halo planes the blocks have pushed while streaming, all-reduces the sums over the peer
+// mailboxes (peer_device.cuh) and mirrors them into mapped host memory -- no k_halo / k_allreduce launch and no
+// device-to-host copy between two sweeps.
 template <int NOUT>
-__device__ void grid_reduce(double (&v)[NOUT], double* partials, unsigned* counter, double* out) {
+__device__ void grid_reduce(double (&v)[NOUT], double* partials, unsigned* counter, double* out, const Link& L = Link()) {
   __shared__ double sm[NOUT][kThreads / 32];
+  __shared__ double fin[peer::kMaxWords];
   __shared__ bool last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -56,6 +62,7 @@ __device__ void grid_reduce(double (&v)[NOUT], double* partials, unsigned* count
   __syncthreads();
   if (!last) return;
   __threadfence();
+  if (L.peer.push && threadIdx.x == 0) peer::publish_halo(L.peer.m, L.peer.h, L.peer.halo_seq);
 #pragma unroll
   for (int k = 0; k < NOUT; ++k) {
     double x = 0.0;
@@ -70,8 +77,25 @@ __device__ void grid_reduce(double (&v)[NOUT], double* partials, unsigned* count
     for (int k = 0; k < NOUT; ++k) {
       double x = 0.0;
       for (int w = 0; w < kThreads / 32; ++w) x += sm[k][w];
-      out[k] = x;
+      fin[k] = x;
     }
+  }
+  if (L.peer.reduce) peer::block_allreduce(L.peer.m, fin, NOUT, L.peer.ar_seq, L.peer.h.error);
+  else __syncthreads();
+  if (threadIdx.x < NOUT) {
+    out[threadIdx.x] = fin[threadIdx.x];
+    if (L.host_out) L.host_out[threadIdx.x] = fin[threadIdx.x];
+  }
+}
+
+// sweeps without a reduction: count the blocks, the last one publishes the pushed planes
+__device__ __forceinline__ void finish_push(unsigned* counter, const Link& L) {
+  if (!L.peer.push) return;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicInc(counter, gridDim.x - 1);
+    if (ticket == gridDim.x - 1) peer::publish_halo(L.peer.m, L.peer.h, L.peer.halo_seq);
   }
 }
 
@@ -114,20 +138,20 @@ void spmv_launch(int64_t nrows, const RP* rp, const int32_t* ci, const double* v
 // ---------------------------------------------------------------- BLAS-1
 __global__ void __launch_bounds__(kThreads) k_dot(Ranges own, const double* __restrict__ a,
                                                   const double* __restrict__ b, double* partials,
-                                                  unsigned* counter, double* out) {
+                                                  unsigned* counter, double* out, Link L) {
   double v[1] = {0.0};
   for (int k = 0; k < own.n; ++k)
     for (long long i = own.b[k] + blockIdx.x * (long long)kThreads + threadIdx.x; i < own.e[k];
          i += (long long)gridDim.x * kThreads)
       v[0] += a[i] * b[i];
-  grid_reduce<1>(v, partials, counter, out);
+  grid_reduce<1>(v, partials, counter, out, L);
 }
 
 __global__ void __launch_bounds__(kThreads) k_dot2(Ranges own, const double* __restrict__ a,
                                                    const double* __restrict__ b,
                                                    const double* __restrict__ c,
                                                    const double* __restrict__ d, double* partials,
-                                                   unsigned* counter, double* out) {
+                                                   unsigned* counter, double* out, Link L) {
   double v[2] = {0.0, 0.0};
   for (int k = 0; k < own.n; ++k)
     for (long long i = own.b[k] + blockIdx.x * (long long)kThreads + threadIdx.x; i < own.e[k];
@@ -135,7 +159,7 @@ __global__ void __launch_bounds__(kThreads) k_dot2(Ranges own, const double* __r
       v[0] += a[i] * b[i];
       v[1] += c[i] * d[i];
     }
-  grid_reduce<2>(v, partials, counter, out);
+  grid_reduce<2>(v, partials, counter, out, L);
 }
 
 __global__ void __launch_bounds__(kThreads) k_bicg_p(int64_t n, double* __restrict__ p,
@@ -177,24 +201,31 @@ __global__ void __launch_bounds__(kThreads) k_axpy_pair_norm(int64_t n, Ranges o
 // p = r + beta (p - omega v) ; y = relax * dinv * p
 __global__ void __launch_bounds__(kThreads) k_bicg_p_prec(int64_t n, double* __restrict__ p,
                                                           const double* __restrict__ r,
-                                                          const double* __restrict__ v,
+                                                          double* v,
                                                           const double* __restrict__ rho_new_p,
                                                           const double* __restrict__ rho_p,
                                                           const double* __restrict__ hptr,
                                                           const double* __restrict__ trtt, bool first,
                                                           const double* __restrict__ dinv, double relax,
-                                                          double* __restrict__ y) {
+                                                          double* __restrict__ y, unsigned* counter, Link L) {
   double beta = 0.0, omega = 0.0;
   if (!first) {
     const double rho = *rho_p, alpha = rho / *hptr;
     omega = trtt[0] / trtt[1];
     beta = (*rho_new_p / rho) * (alpha / omega);
   }
+  const int par = (int)(L.peer.halo_seq & 1ull);
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
     const double pi = first ? r[i] : r[i] + beta * (p[i] - omega * v[i]);
     p[i] = pi;
-    if (dinv) y[i] = relax * dinv[i] * pi;
+    if (L.zero_input) v[i] = 0.0;   // v is done: the operator application that follows accumulates into it
+    if (dinv) {
+      const double yi = relax * dinv[i] * pi;
+      y[i] = yi;
+      if (L.peer.push) peer::push_entry(L.peer.m, L.peer.h, par, i, yi);
+    }
   }
+  finish_push(counter, L);
 }
 // r -= alpha v ; out[0] = <r,r> ; y2 = relax * dinv * r
 __global__ void __launch_bounds__(kThreads) k_bicg_r_prec(int64_t n, Ranges own,
@@ -204,17 +235,23 @@ __global__ void __launch_bounds__(kThreads) k_bicg_r_prec(int64_t n, Ranges own,
                                                           double* __restrict__ r,
                                                           const double* __restrict__ dinv, double relax,
                                                           double* __restrict__ y2, double* partials,
-                                                          unsigned* counter, double* out) {
+                                                          unsigned* counter, double* out, Link L) {
   double acc[1] = {0.0};
   const bool single = own.n == 1 && own.b[0] == 0 && own.e[0] == n;
   const double alpha = *rho_p / *hptr;   // alpha = rho'/<rt,v> from the device-resident reductions
+  const int par = (int)(L.peer.halo_seq & 1ull);
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
     const double ri = r[i] - alpha * v[i];
     r[i] = ri;
-    if (dinv) y2[i] = relax * dinv[i] * ri;
+    if (dinv) {
+      const double yi = relax * dinv[i] * ri;
+      y2[i] = yi;
+      if (L.peer.push) peer::push_entry(L.peer.m, L.peer.h, par, i, yi);
+    }
     if (single || in_ranges(own, i)) acc[0] += ri * ri;
   }
-  grid_reduce<1>(acc, partials, counter, out);
+  if (L.peer.push) __threadfence_system();
+  grid_reduce<1>(acc, partials, counter, out, L);
 }
 // xout = xin + alpha y1 + omega y2 ; r -= omega t ; out[0] = <r,r> ; out[1] = <rt,r>
 __global__ void __launch_bounds__(kThreads) k_bicg_final(int64_t n, Ranges own,
@@ -225,10 +262,10 @@ __global__ void __launch_bounds__(kThreads) k_bicg_final(int64_t n, Ranges own,
                                                          const double* __restrict__ y2,
                                                          const double* __restrict__ xin,
                                                          double* __restrict__ xout,
-                                                         const double* __restrict__ t,
+                                                         double* t,
                                                          double* __restrict__ r,
                                                          const double* __restrict__ rt, double* partials,
-                                                         unsigned* counter, double* out) {
+                                                         unsigned* counter, double* out, Link L) {
   double acc[2] = {0.0, 0.0};
   const bool single = own.n == 1 && own.b[0] == 0 && own.e[0] == n;
   const double alpha = *rho_p / *hptr, omega = trtt[0] / trtt[1];
@@ -236,12 +273,13 @@ __global__ void __launch_bounds__(kThreads) k_bicg_final(int64_t n, Ranges own,
     xout[i] = (xin[i] + alpha * y1[i]) + omega * y2[i];
     const double ri = r[i] - omega * t[i];
     r[i] = ri;
+    if (L.zero_input) t[i] = 0.0;   // t is done: the next operator application accumulates into it
     if (single || in_ranges(own, i)) {
       acc[0] += ri * ri;
       acc[1] += rt[i] * ri;
     }
   }
-  grid_reduce<2>(acc, partials, counter, out);
+  grid_reduce<2>(acc, partials, counter, out, L);
 }
 
 __global__ void __launch_bounds__(kThreads) k_xpby(int64_t n, double* __restrict__ p,
@@ -576,13 +614,14 @@ static int64_t ranges_len(const Ranges& r) {
   return n;
 }
 
-void dot(const Ranges& own, const double* a, const double* b, double* out, const ReduceWorkspace& w, cudaStream_t s) {
-  k_dot<<<grid_for(ranges_len(own), 4), kThreads, 0, s>>>(own, a, b, w.partials, w.counter, out);
+void dot(const Ranges& own, const double* a, const double* b, double* out, const ReduceWorkspace& w, cudaStream_t s,
+         const Link& L) {
+  k_dot<<<grid_for(ranges_len(own), 4), kThreads, 0, s>>>(own, a, b, w.partials, w.counter, out, L);
   check_launch();
 }
 void dot2(const Ranges& own, const double* a, const double* b, const double* c, const double* d, double* out,
-          const ReduceWorkspace& w, cudaStream_t s) {
-  k_dot2<<<grid_for(ranges_len(own), 4), kThreads, 0, s>>>(own, a, b, c, d, w.partials, w.counter, out);
+          const ReduceWorkspace& w, cudaStream_t s, const Link& L) {
+  k_dot2<<<grid_for(ranges_len(own), 4), kThreads, 0, s>>>(own, a, b, c, d, w.partials, w.counter, out, L);
   check_launch();
 }
 void bicg_update_p(int64_t n, double* p, const double* r, const double* v, double beta, double omega,
@@ -595,21 +634,22 @@ void axpy_pair_norm(int64_t n, const Ranges& own, double alpha, const double* y,
   k_axpy_pair_norm<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, alpha, y, x, v, r, rt, w.partials, w.counter, out);
   check_launch();
 }
-void bicg_p_prec(int64_t n, double* p, const double* r, const double* v, const double* rho_new, const double* rho,
+void bicg_p_prec(int64_t n, double* p, const double* r, double* v, const double* rho_new, const double* rho,
                  const double* hptr, const double* trtt, bool first, const double* dinv, double relax, double* y,
-                 cudaStream_t s) {
-  k_bicg_p_prec<<<grid_for(n, 2), kThreads, 0, s>>>(n, p, r, v, rho_new, rho, hptr, trtt, first, dinv, relax, y);
+                 const ReduceWorkspace& w, cudaStream_t s, const Link& L) {
+  k_bicg_p_prec<<<grid_for(n, 2), kThreads, 0, s>>>(n, p, r, v, rho_new, rho, hptr, trtt, first, dinv, relax, y, w.counter, L);
   check_launch();
 }
 void bicg_r_prec(int64_t n, const Ranges& own, const double* rho, const double* hptr, const double* v, double* r,
-                 const double* dinv, double relax, double* y2, double* out, const ReduceWorkspace& w, cudaStream_t s) {
-  k_bicg_r_prec<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, rho, hptr, v, r, dinv, relax, y2, w.partials, w.counter, out);
+                 const double* dinv, double relax, double* y2, double* out, const ReduceWorkspace& w, cudaStream_t s,
+                 const Link& L) {
+  k_bicg_r_prec<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, rho, hptr, v, r, dinv, relax, y2, w.partials, w.counter, out, L);
   check_launch();
 }
 void bicg_final(int64_t n, const Ranges& own, const double* rho, const double* hptr, const double* trtt, const double* y1,
-                const double* y2, const double* xin, double* xout, const double* t, double* r, const double* rt,
-                double* out, const ReduceWorkspace& w, cudaStream_t s) {
-  k_bicg_final<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, rho, hptr, trtt, y1, y2, xin, xout, t, r, rt, w.partials, w.counter, out);
+                const double* y2, const double* xin, double* xout, double* t, double* r, const double* rt,
+                double* out, const ReduceWorkspace& w, cudaStream_t s, const Link& L) {
+  k_bicg_final<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, rho, hptr, trtt, y1, y2, xin, xout, t, r, rt, w.partials, w.counter, out, L);
   check_launch();
 }
 void xpby(int64_t n, double* p, const double* q, double beta, cudaStream_t s) {

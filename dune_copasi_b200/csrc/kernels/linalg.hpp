@@ -7,6 +7,8 @@
 
 #include <cstdint>
 
+#include "peer.hpp"
+
 namespace dcb {
 namespace la {
 
@@ -24,6 +26,16 @@ struct Ranges {
   long long b[8], e[8];
   static Ranges all(long long len) { Ranges r; r.n = 1; r.b[0] = 0; r.e[0] = len; return r; }
 };
+// What a sweep does beyond its own arithmetic (all off by default):
+//   peer       the collectives that follow it in the algorithm, fused into the kernel (peer.hpp);
+//   host_out   reducing kernels: the final sums also go to this mapped pinned host address (no D2H copy);
+//   zero_input the sweep clears the operator-result vector it has just consumed (v in bicg_p_prec, t in
+//              bicg_final), so the next matrix-free application can accumulate without a fill launch.
+struct Link {
+  peer::Link peer;
+  double* host_out = nullptr;
+  int zero_input = 0;
+};
 void reduce_workspace_create(ReduceWorkspace* w, int max_blocks = kMaxBlocks);
 void reduce_workspace_destroy(ReduceWorkspace* w);
 
@@ -32,10 +44,11 @@ void spmv_csr(int64_t nrows, const int64_t* rowptr, const int32_t* rowptr32, con
               const double* vals, const double* x, double* y, int avg_nnz, cudaStream_t s);
 
 // out[0] = <a,b>            (out is a device pointer)
-void dot(const Ranges& own, const double* a, const double* b, double* out, const ReduceWorkspace& w, cudaStream_t s);
+void dot(const Ranges& own, const double* a, const double* b, double* out, const ReduceWorkspace& w, cudaStream_t s,
+         const Link& L = Link());
 // out[0] = <a,b>, out[1] = <c,d>
 void dot2(const Ranges& own, const double* a, const double* b, const double* c, const double* d, double* out,
-          const ReduceWorkspace& w, cudaStream_t s);
+          const ReduceWorkspace& w, cudaStream_t s, const Link& L = Link());
 
 // BiCGSTAB: p = r + beta (p - omega v)      (first = true: p = r)
 void bicg_update_p(int64_t n, double* p, const double* r, const double* v, double beta, double omega,
@@ -49,16 +62,17 @@ void axpy_pair_norm(int64_t n, const Ranges& own, double alpha, const double* y,
 //   rho = <rt,r> at the start of the iteration, hptr = <rt,v>, trtt = (<t,r>, <t,t>):
 //   alpha = rho / h, omega = tr / tt, beta = (rho_new / rho) * (alpha / omega)  (dune-istl's order)
 // p = r + beta (p - omega v) ; y = relax dinv p      (rho, hptr, trtt: those of the previous iteration)
-void bicg_p_prec(int64_t n, double* p, const double* r, const double* v, const double* rho_new, const double* rho,
+void bicg_p_prec(int64_t n, double* p, const double* r, double* v, const double* rho_new, const double* rho,
                  const double* hptr, const double* trtt, bool first, const double* dinv, double relax, double* y,
-                 cudaStream_t s);
+                 const ReduceWorkspace& w, cudaStream_t s, const Link& L = Link());
 // r -= alpha v ; out[0] = <r,r> ; y2 = relax dinv r
 void bicg_r_prec(int64_t n, const Ranges& own, const double* rho, const double* hptr, const double* v, double* r,
-                 const double* dinv, double relax, double* y2, double* out, const ReduceWorkspace& w, cudaStream_t s);
+                 const double* dinv, double relax, double* y2, double* out, const ReduceWorkspace& w, cudaStream_t s,
+                 const Link& L = Link());
 // xout = xin + alpha y1 + omega y2 ; r -= omega t ; out[0] = <r,r> ; out[1] = <rt,r>
 void bicg_final(int64_t n, const Ranges& own, const double* rho, const double* hptr, const double* trtt, const double* y1,
-                const double* y2, const double* xin, double* xout, const double* t, double* r, const double* rt,
-                double* out, const ReduceWorkspace& w, cudaStream_t s);
+                const double* y2, const double* xin, double* xout, double* t, double* r, const double* rt,
+                double* out, const ReduceWorkspace& w, cudaStream_t s, const Link& L = Link());
 // GMRES (modified Gram-Schmidt) with device-resident coefficients:
 // y += sign * (*coef) * x
 void axpy_dev(int64_t n, const double* coef, double sign, const double* x, double* y, cudaStream_t s);

@@ -12,50 +12,19 @@
 // writes only after it has finished reading exchange s-1.
 // Sums are formed in rank order on every rank: deterministic and identical everywhere.
 #include "peer.hpp"
+#include "peer_device.cuh"
 
 namespace dcb {
 namespace peer {
 
 namespace {
 
-__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_flag(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ double ld_data(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
-
 // one block, one thread per peer
-__global__ void __launch_bounds__(64) k_allreduce(Mailboxes m, double* data, int n, unsigned long long seq) {
-  const int p = threadIdx.x, par = (int)(seq & 1ull);
+__global__ void __launch_bounds__(64) k_allreduce(Mailboxes m, double* data, int n, unsigned long long seq, int* error) {
   __shared__ double mine[kMaxWords];
-  if (p < n) mine[p] = data[p];
-  __syncthreads();
-  if (p < m.size) {
-    char* box = m.box[p];
-    double* dst = (double*)(box + ar_val_offset(m.size, par, m.rank));
-    for (int i = 0; i < n; ++i) dst[i] = mine[i];
-    __threadfence_system();
-    st_flag((unsigned long long*)(box + ar_flag_offset(m.size, par, m.rank)), seq);
-    // wait for peer p's contribution in the local mailbox
-    const unsigned long long* f = (const unsigned long long*)(m.box[m.rank] + ar_flag_offset(m.size, par, p));
-    while (ld_flag(f) != seq) {}
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (p < n) {
-    double sum = 0.0;
-    for (int q = 0; q < m.size; ++q)
-      sum += ld_data((const double*)(m.box[m.rank] + ar_val_offset(m.size, par, q)) + p);
-    data[p] = sum;
-  }
+  if (threadIdx.x < n) mine[threadIdx.x] = data[threadIdx.x];
+  block_allreduce(m, mine, n, seq, error);
+  if (threadIdx.x < n) data[threadIdx.x] = mine[threadIdx.x];
 }
 
 // grid of G blocks: push the send ranges into the neighbours' mailboxes, publish, wait, pull
@@ -83,10 +52,23 @@ __global__ void __launch_bounds__(256) k_halo(Mailboxes m, HaloArgs h, double* x
       st_flag((unsigned long long*)(m.box[h.peer[k]] + halo_flag_offset(m.size, h.remote_slot[k], par)), seq);
   }
   for (int k = 0; k < h.npeers; ++k) {
-    if (threadIdx.x == 0) {
-      const unsigned long long* f = (const unsigned long long*)(m.box[m.rank] + halo_flag_offset(m.size, h.local_slot[k], par));
-      while (ld_flag(f) != seq) {}
-    }
+    if (threadIdx.x == 0)
+      wait_flag((const unsigned long long*)(m.box[m.rank] + halo_flag_offset(m.size, h.local_slot[k], par)), seq, h.error);
+    __syncthreads();
+    __threadfence_system();
+    const double* src = (const double*)(m.box[m.rank] + halo_data_offset(m.size, m.cap, h.local_slot[k], par));
+    double* dst = x + h.recv_off[k];
+    for (long long i = tid; i < h.recv_n[k]; i += nth) dst[i] = ld_data(src + i);
+  }
+}
+
+// second half of k_halo on its own: the planes of exchange `seq` were pushed by the neighbours' sweeps (push_entry)
+__global__ void __launch_bounds__(256) k_halo_pull(Mailboxes m, HaloArgs h, double* x, unsigned long long seq) {
+  const int par = (int)(seq & 1ull);
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (int k = 0; k < h.npeers; ++k) {
+    if (threadIdx.x == 0)
+      wait_flag((const unsigned long long*)(m.box[m.rank] + halo_flag_offset(m.size, h.local_slot[k], par)), seq, h.error);
     __syncthreads();
     __threadfence_system();
     const double* src = (const double*)(m.box[m.rank] + halo_data_offset(m.size, m.cap, h.local_slot[k], par));
@@ -97,8 +79,11 @@ __global__ void __launch_bounds__(256) k_halo(Mailboxes m, HaloArgs h, double* x
 
 }  // namespace
 
-void allreduce(const Mailboxes& m, double* data, int n, unsigned long long seq, cudaStream_t s) {
-  k_allreduce<<<1, 64, 0, s>>>(m, data, n, seq);
+void allreduce(const Mailboxes& m, double* data, int n, unsigned long long seq, int* error, cudaStream_t s) {
+  k_allreduce<<<1, 64, 0, s>>>(m, data, n, seq, error);
+}
+void halo_pull(const Mailboxes& m, const HaloArgs& h, double* x, unsigned long long seq, cudaStream_t s) {
+  k_halo_pull<<<kHaloBlocks, 256, 0, s>>>(m, h, x, seq);
 }
 
 void halo(const Mailboxes& m, const HaloArgs& h, double* x, unsigned long long seq, cudaStream_t s) {

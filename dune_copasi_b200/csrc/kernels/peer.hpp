@@ -41,10 +41,30 @@ struct HaloArgs {
   int local_slot[2], remote_slot[2];
   long long send_off[2], send_n[2], recv_off[2], recv_n[2];
   unsigned* counter;              // self-resetting ticket of the push phase
+  // spins are bounded: a peer that never publishes (died, diverged) raises *error instead of hanging the device
+  int* error;
 };
+constexpr long long kSpinLimit = 1ll << 26;   // polls of a flag before giving up (about a minute of wall time)
 
-void allreduce(const Mailboxes& m, double* data, int n, unsigned long long seq, cudaStream_t s);
+void allreduce(const Mailboxes& m, double* data, int n, unsigned long long seq, int* error, cudaStream_t s);
 void halo(const Mailboxes& m, const HaloArgs& h, double* x, unsigned long long seq, cudaStream_t s);
+
+// ---- exchanges fused into the kernels of the Krylov sweeps (kernels/linalg.cu, peer_device.cuh) ------------
+// Link of one kernel launch to the collectives that follow it in the algorithm.  The producing kernel does the
+// communication itself instead of handing over to k_allreduce / k_halo:
+//   * reduce: the last block of a reducing kernel all-reduces the sums it has just formed over the mailboxes
+//     (exchange number ar_seq) before it writes them;
+//   * push:   a sweep that writes a vector also stores the entries of the send ranges into the neighbours' halo
+//     slots (exchange number halo_seq) while it streams; its last block publishes the flags.  The receiver
+//     copies the planes into its ghost range with halo_pull right before the operator application.
+// A link with reduce = push = 0 leaves the kernel local (single GPU, NCCL fallback).
+struct Link {
+  Mailboxes m;
+  int reduce = 0, push = 0;
+  unsigned long long ar_seq = 0, halo_seq = 0;
+  HaloArgs h;
+};
+void halo_pull(const Mailboxes& m, const HaloArgs& h, double* x, unsigned long long seq, cudaStream_t s);
 
 }  // namespace peer
 }  // namespace dcb

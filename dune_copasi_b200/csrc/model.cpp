@@ -392,6 +392,7 @@ std::string Model::cuda_source() const {
   o << "__device__ __forceinline__ double dc_sgn(double x) { return (double)((x > 0.0) - (x < 0.0)); }\n";
   o << "__device__ __forceinline__ double dc_min(double a, double b) { return a < b ? a : b; }\n";
   o << "__device__ __forceinline__ double dc_max(double a, double b) { return a > b ? a : b; }\n";
+  o << ctx.cuda_tables();   // tabulated parser_context functions (expr.hpp)
   o << "template <int C> struct DcComp;\ntemplate <int P> struct DcOutflow;\n";
   auto pairs = species_pairs();
   for (int c = 0; c < ncomp(); ++c) {

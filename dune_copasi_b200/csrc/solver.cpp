@@ -128,7 +128,9 @@ void LinearSolver::linearize(double t, double wM, double wA, const double* x) {
     }
 }
 
-void LinearSolver::apply_operator(const double* v, double* y) {
+// pushed: the ghost planes of v are already on their way (the sweep that wrote v pushed them, link_push):
+// only the pull is left.  zeroed: y is zero on entry (cleared by the sweep that consumed it last).
+void LinearSolver::apply_operator(const double* v, double* y, bool pushed, bool zeroed) {
   cudaStream_t s = op_->stream;
   if (comm_ && overlap_halo_) {
     // structured slabs, matrix free: the ghost planes of v travel on a second (high priority)
@@ -146,7 +148,8 @@ void LinearSolver::apply_operator(const double* v, double* y) {
     if (op_->ncons) { la::copy_values(op_->ncons, op_->cdofs.p, v, y, s); op_->stats.launches++; }
     return;
   }
-  if (comm_) comm_->halo_update(const_cast<double*>(v), s);
+  if (comm_ && pushed) comm_->halo_pull(const_cast<double*>(v), s);
+  else if (comm_) comm_->halo_update(const_cast<double*>(v), s);
   if (!matrix_free) {
     int avg = (int)(op_->nnz() / std::max<int64_t>(1, op_->ndofs));
     DeviceOperator::ProfScope ps(op_.get(), "spmv");
@@ -156,8 +159,10 @@ void LinearSolver::apply_operator(const double* v, double* y) {
     // owner-computes sweep: y is written, not accumulated; identity rows included
     op_->tile_apply(t_, wM_, wA_, x_, v, y);
   } else {
-    la::fill(op_->ndofs, 0.0, y, s);   // MatrixFreeAdapter::apply zeroes y first (make_step_operator.hh:70-75)
-    op_->stats.launches++;
+    if (!zeroed) {
+      la::fill(op_->ndofs, 0.0, y, s);   // MatrixFreeAdapter::apply zeroes y first (make_step_operator.hh:70-75)
+      op_->stats.launches++;
+    }
     op_->jacobian_apply(t_, wM_, wA_, x_, v, y);
     if (op_->ncons) { la::copy_values(op_->ncons, op_->cdofs.p, v, y, s); op_->stats.launches++; }   // identity rows
   }
@@ -388,7 +393,15 @@ SolveResult LinearSolver::apply_bicgstab_fused(double* b, double* x, double rel_
 }
 
 SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
-  if (fused_) return apply_bicgstab_fused(b, x, rel_tol);
+  SolveResult res = fused_ ? apply_bicgstab_fused(b, x, rel_tol) : apply_krylov(b, x, rel_tol);
+  // the flag spins of the peer-memory collectives are bounded: a solve that did not converge because a peer
+  // never answered is reported as what it is
+  if (!res.converged && comm_ && comm_->peer_error())
+    fail("a peer-memory collective gave up waiting for another rank (rank ", comm_->rank, " of ", comm_->size, ")");
+  return res;
+}
+
+SolveResult LinearSolver::apply_krylov(double* b, double* x, double rel_tol) {
   cudaStream_t s = op_->stream;
   const int64_t n = op_->ndofs;
   const la::Ranges& own = op_->owned;
@@ -412,10 +425,30 @@ SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
     // Jacobi is folded into the sweeps that produce its argument; other preconditioners run on their own
     const double* fold = prec_type == "Jacobi" && prec_iterations == 1 ? dinv_.p : nullptr;
     { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::copy(n, r, rt, s); L++; }
+    // Collectives and host traffic fused into the sweeps (kernels/linalg.cu, peer_device.cuh):
+    //   * the last block of every reducing kernel all-reduces its sums over the peer mailboxes and mirrors them
+    //     into mapped host memory (no k_allreduce launch, no device-to-host copy between two sweeps);
+    //   * the sweeps that write the operator's input (y, y2; Jacobi folded) push the halo planes to the
+    //     neighbours while they stream, the operator application only pulls them into the ghost range;
+    //   * the sweeps that consume the operator's result clear it for the next application (no fill launch).
+    const bool rlink = !comm_ || comm_->reduce_links_ready();              // sums reach hscal_ straight from the kernels
+    const bool plink = comm_ && fold && comm_->push_links_ready() && !overlap_halo_;
+    const bool zfuse = matrix_free && fold && !overlap_halo_ && !op_->tile_aligned({x_, y, v});
+    auto link = [&](bool reduce, double* host_out, bool push, bool zero) {
+      la::Link k;
+      if (comm_ && reduce && rlink) comm_->link_reduce(&k.peer);
+      if (push && plink) comm_->link_push(&k.peer);
+      k.host_out = rlink ? host_out : nullptr;
+      k.zero_input = zero && zfuse;
+      return k;
+    };
+    auto reduce_after = [&](double* dev, int count) { if (comm_ && !rlink) comm_->allreduce_sum(dev, count, s); };
     // <rt,r> = <r,r> at the start: stored where iteration 0 looks for its rho
-    { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, r, r, pair(-1) + 1, ws_, s); L++; }
-    if (comm_) comm_->allreduce_sum(pair(-1) + 1, 1, s);
-    DCB_CUDA(cudaMemcpyAsync(hscal_.p, pair(-1) + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+    { DeviceOperator::ProfScope ps(op_.get(), "blas1");
+      la::dot(own, r, r, pair(-1) + 1, ws_, s, link(true, hscal_.p, false, false)); L++; }
+    reduce_after(pair(-1) + 1, 1);
+    if (!rlink) DCB_CUDA(cudaMemcpyAsync(hscal_.p, pair(-1) + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (zfuse) { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::fill(n, 0.0, v, s); la::fill(n, 0.0, t, s); L += 2; }
     { DeviceOperator::HostTimer ht(op_.get(), "host_wait"); DCB_CUDA(cudaStreamSynchronize(s)); }
     double norm0 = std::sqrt(hscal_.p[0]), norm = norm0;
     res.defect0 = norm0;
@@ -425,26 +458,31 @@ SolveResult LinearSolver::apply(double* b, double* x, double rel_tol) {
     double *x_cur = x, *x_alt = xalt_.p;
     auto first_half = [&](int i) {
       { DeviceOperator::ProfScope ps(op_.get(), "blas1");
-        la::bicg_p_prec(n, p, r, v, pair(i - 1) + 1, pair(i - 2) + 1, sc + 2, sc + 4, i == 0, fold, relaxation, y, s); L++; }
+        la::bicg_p_prec(n, p, r, v, pair(i - 1) + 1, pair(i - 2) + 1, sc + 2, sc + 4, i == 0, fold, relaxation, y, ws_, s,
+                        link(false, nullptr, true, true)); L++; }
       if (!fold) precondition(p, y);
-      apply_operator(y, v);
-      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot(own, rt, v, sc + 2, ws_, s); L++; }
-      if (comm_) comm_->allreduce_sum(sc + 2, 1, s);
+      apply_operator(y, v, plink, zfuse);
       { DeviceOperator::ProfScope ps(op_.get(), "blas1");
-        la::bicg_r_prec(n, own, pair(i - 1) + 1, sc + 2, v, r, fold, relaxation, y2, sc, ws_, s); L++; }
-      if (comm_) comm_->allreduce_sum(sc, 1, s);
-      DCB_CUDA(cudaMemcpyAsync(hscal_.p, sc, sizeof(double) * 3, cudaMemcpyDeviceToHost, s));
+        la::dot(own, rt, v, sc + 2, ws_, s, link(true, hscal_.p + 2, false, false)); L++; }
+      reduce_after(sc + 2, 1);
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1");
+        la::bicg_r_prec(n, own, pair(i - 1) + 1, sc + 2, v, r, fold, relaxation, y2, sc, ws_, s,
+                        link(true, hscal_.p, true, false)); L++; }
+      reduce_after(sc, 1);
+      if (!rlink) DCB_CUDA(cudaMemcpyAsync(hscal_.p, sc, sizeof(double) * 3, cudaMemcpyDeviceToHost, s));
       DCB_CUDA(cudaEventRecord(ev_[0], s));
     };
     auto second_half = [&](int i, const double* xin, double* xout) {
       if (!fold) precondition(r, y2);
-      apply_operator(y2, t);
-      { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::dot2(own, t, r, t, t, sc + 4, ws_, s); L++; }
-      if (comm_) comm_->allreduce_sum(sc + 4, 2, s);
+      apply_operator(y2, t, plink, zfuse);
       { DeviceOperator::ProfScope ps(op_.get(), "blas1");
-        la::bicg_final(n, own, pair(i - 1) + 1, sc + 2, sc + 4, y, y2, xin, xout, t, r, rt, pair(i), ws_, s); L++; }
-      if (comm_) comm_->allreduce_sum(pair(i), 2, s);
-      DCB_CUDA(cudaMemcpyAsync(hscal_.p + 4, sc + 4, sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
+        la::dot2(own, t, r, t, t, sc + 4, ws_, s, link(true, hscal_.p + 4, false, false)); L++; }
+      reduce_after(sc + 4, 2);
+      { DeviceOperator::ProfScope ps(op_.get(), "blas1");
+        la::bicg_final(n, own, pair(i - 1) + 1, sc + 2, sc + 4, y, y2, xin, xout, t, r, rt, pair(i), ws_, s,
+                       link(true, hscal_.p + 8 + 2 * (i & 1), false, true)); L++; }
+      reduce_after(pair(i), 2);
+      if (!rlink) DCB_CUDA(cudaMemcpyAsync(hscal_.p + 4, sc + 4, sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
       DCB_CUDA(cudaEventRecord(ev_[1], s));
     };
     // work ahead only while the last known defect is two orders above the target: the half steps

@@ -39,7 +39,7 @@ class LinearSolver {
   // solve J z = b to the relative defect reduction `rel_tol`; b is consumed (holds the final defect)
   SolveResult apply(double* b, double* z, double rel_tol);
   // y = J v with the current linearisation
-  void apply_operator(const double* v, double* y);
+  void apply_operator(const double* v, double* y, bool pushed = false, bool zeroed = false);
   // BiCGSTAB with its vector updates and dot products fused into the tile-marching apply kernels
   bool is_fused() const { return fused_; }
 
@@ -60,6 +60,7 @@ class LinearSolver {
   void precondition_sweep(const double* d, double* v);   // one sweep from v = 0
   void fetch(int n);
   SolveResult apply_bicgstab_fused(double* b, double* z, double rel_tol);
+  SolveResult apply_krylov(double* b, double* z, double rel_tol);
   bool fused_ = false;
   DeviceBuffer<double> valt_;
   void fetch_slots(int first, int count, int total);
