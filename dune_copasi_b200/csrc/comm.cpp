@@ -124,7 +124,8 @@ struct NcclCommunicator : Communicator {
   void setup_peer_memory() {
     const char* env = std::getenv("DCB_PEER_COLLECTIVES");
     bool want = !(env && env[0] == '0') && size > 1 && size <= peer::kMaxRanks;
-    // halo slots: at most one lower and one higher neighbour, both with contiguous ranges
+    // slab halo: at most one lower and one higher neighbour, both with contiguous ranges; anything else goes
+    // through the general (index list) exchange with one slot per source rank
     bool halo_ok = plan.peers.size() <= 2;
     long long cap = 1;
     for (size_t k = 0; k < plan.peers.size(); ++k) {
@@ -132,6 +133,8 @@ struct NcclCommunicator : Communicator {
       cap = std::max<long long>(cap, (long long)plan.recv_idx[k].size());
     }
     if (plan.peers.size() == 2) halo_ok = halo_ok && ((plan.peers[0] < rank) != (plan.peers[1] < rank));
+    const char* genv = std::getenv("DCB_PEER_GENERAL_HALO");
+    const bool want_general = !(genv && genv[0] == '0');
     // agree on: everybody wants it, everybody's halo fits the slots, the largest slot
     DeviceBuffer<double> d(3);
     double h[3] = {want ? 1.0 : 0.0, halo_ok ? 1.0 : 0.0, -(double)cap};
@@ -140,9 +143,10 @@ struct NcclCommunicator : Communicator {
     DCB_CUDA(cudaMemcpy(h, d.p, sizeof h, cudaMemcpyDeviceToHost));
     if (h[0] < 0.5) return;
     const bool halo_all = h[1] > 0.5;
-    cap = halo_all ? (long long)(-h[2]) : 1;
+    const bool general = !halo_all && want_general;   // the same on every rank: h[1] is the global minimum
+    cap = (halo_all || general) ? (long long)(-h[2]) : 1;
     // own mailbox, zeroed, exported
-    const size_t bytes = peer::mailbox_bytes(size, cap);
+    const size_t bytes = peer::mailbox_bytes(size, cap, general ? size : 2);
     char* mine = nullptr;
     cudaIpcMemHandle_t handle;
     std::memset(&handle, 0, sizeof handle);
@@ -191,8 +195,32 @@ struct NcclCommunicator : Communicator {
         hargs.recv_off[k] = recv_off[k]; hargs.recv_n[k] = (long long)plan.recv_idx[k].size();
       }
     }
+    if (general) {
+      peer_general = true;
+      ticket.alloc(1);
+      ticket.zero();
+      gargs.npeers = (int)plan.peers.size();
+      gargs.counter = ticket.p;
+      gargs.error = error_flag.p;
+      std::vector<int32_t> sidx, ridx;
+      gargs.send_ptr[0] = gargs.recv_ptr[0] = 0;
+      for (size_t k = 0; k < plan.peers.size(); ++k) {
+        gargs.peer[k] = plan.peers[k];
+        sidx.insert(sidx.end(), plan.send_idx[k].begin(), plan.send_idx[k].end());
+        ridx.insert(ridx.end(), plan.recv_idx[k].begin(), plan.recv_idx[k].end());
+        gargs.send_ptr[k + 1] = (long long)sidx.size();
+        gargs.recv_ptr[k + 1] = (long long)ridx.size();
+      }
+      if (!sidx.empty()) gsend.upload(sidx);
+      if (!ridx.empty()) grecv.upload(ridx);
+      gargs.send_idx = gsend.p;
+      gargs.recv_idx = grecv.p;
+    }
     DCB_CUDA(cudaDeviceSynchronize());
   }
+  peer::GeneralHaloArgs gargs{};
+  DeviceBuffer<int32_t> gsend, grecv;
+  bool peer_general = false;
   // contiguous index lists (slab partitions of structured grids: whole vertex planes) are sent
   // and received in place, without pack / unpack kernels
   std::vector<long long> send_off, recv_off;   // >= 0: contiguous range starting there
@@ -201,6 +229,12 @@ struct NcclCommunicator : Communicator {
     const size_t np = plan.peers.size();
     if (peer_halo) {   // every rank takes this branch or none does (setup_peer_memory agreed on it)
       peer::halo(boxes, hargs, x, ++halo_seq, s);
+      DCB_CUDA(cudaGetLastError());
+      launches++;
+      return;
+    }
+    if (peer_general) {
+      peer::halo_general(boxes, gargs, x, ++halo_seq, s);
       DCB_CUDA(cudaGetLastError());
       launches++;
       return;

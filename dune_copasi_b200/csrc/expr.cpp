@@ -1,6 +1,8 @@
 #include "expr.hpp"
 
 #include <mutex>
+#include <set>
+#include <sstream>
 
 #include <algorithm>
 

@@ -347,6 +347,12 @@ void Grid::interpolate(const Model& model, double time, std::vector<double>& u) 
   }
 }
 
+// Dirichlet translation constraints (constraints.hh:114-195).  The reference walks the intersections and, per
+// vertex of a face, keeps the value when the vertex is a boundary vertex exactly if the face is a boundary face
+// (`in_boundary == isBoundary(vertex)`, :182): `constrain.boundary` therefore binds the boundary vertices,
+// `constrain.skeleton` the vertices that are not on the boundary (each of them lies on a face with a neighbour).
+// Restated per vertex: the expression sees the vertex position and in_boundary / in_skeleton; the face-dependent
+// symbols (normal_*, entity_volume) read 0 -- with them the reference's value depends on which face is visited last.
 void Grid::constraints(const Model& model, std::vector<int32_t>& dofs, std::vector<double>& vals) const {
   dofs.clear();
   vals.clear();
@@ -354,14 +360,19 @@ void Grid::constraints(const Model& model, std::vector<int32_t>& dofs, std::vect
   for (auto v : boundary_vertices) isb[v] = 1;
   for (int g = 0; g < model.nspec(); ++g) {
     const auto& s = model.species[g];
-    if (expr_is_absent(s.constrain_boundary)) continue;
-    NodeP ast = model.compile(s.constrain_boundary);
+    const bool hb = !expr_is_absent(s.constrain_boundary), hs = !expr_is_absent(s.constrain_skeleton);
+    if (!hb && !hs) continue;
+    NodeP ab = hb ? model.compile(s.constrain_boundary) : nullptr;
+    NodeP as = hs ? model.compile(s.constrain_skeleton) : nullptr;
     const auto& verts = comp_vertices[s.comp];
     int ns = comp_nspec[s.comp];
     for (int64_t lv = 0; lv < (int64_t)verts.size(); ++lv) {
-      if (!isb[verts[lv]]) continue;
+      const bool onb = isb[verts[lv]];
+      const NodeP& ast = onb ? ab : as;
+      if (!ast) continue;
       // time is NaN for constraints (constraints.hh:63-66); no_value == DBL_MAX => unconstrained
-      double val = model.eval_host(ast, &coords[(int64_t)verts[lv] * dim], std::nan(""), nullptr, 0.0, 1.0);
+      double val = model.eval_host(ast, &coords[(int64_t)verts[lv] * dim], std::nan(""), nullptr, 0.0, onb ? 1.0 : 0.0,
+                                   onb ? 0.0 : 1.0);
       if (val == DBL_MAX) continue;
       dofs.push_back((int32_t)(comp_offset[s.comp] + lv * ns + s.local));
       vals.push_back(val);

@@ -689,6 +689,48 @@ __global__ void __launch_bounds__(128) k_sor_level(const int32_t* __restrict__ r
   if (skip_diag) v[i] = rhs / diag;   // dbgs assigns the unrelaxed value; the caller blends with the old iterate
   else v[i] += relax * (rhs / diag);
 }
+// Self-scheduled sweep: the whole forward (or backward) sweep in ONE launch.  Slot p of `slots` holds a row (or -1:
+// padding, so that the 32 rows of a warp belong to one level and never wait for each other); slots are in level order.
+// A row spins until every coupled row that the sequential sweep visits earlier carries this sweep's epoch, then
+// computes exactly what k_sor_level computes and publishes itself.  Every wait is for a row in an earlier slot and
+// blocks start in index order, so the sweep cannot deadlock; coupled rows are symmetrised on the host (dep_ptr /
+// dep_idx = pattern of A + A^T), which also keeps a row from overwriting a value a smaller row still has to read.
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__global__ void __launch_bounds__(128) k_sor_sweep(const int32_t* __restrict__ slots, int64_t nslots, bool backward,
+                                                   const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                   const double* __restrict__ vals, const int64_t* __restrict__ dep_ptr,
+                                                   const int32_t* __restrict__ dep_idx, const double* __restrict__ d,
+                                                   double* v, double relax, bool skip_diag, int* done, int epoch) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= nslots) return;
+  const int i = slots[backward ? nslots - 1 - t : t];
+  if (i < 0) return;
+  for (int64_t k = dep_ptr[i]; k < dep_ptr[i + 1]; ++k) {
+    const int j = dep_idx[k];
+    if (backward ? j > i : j < i)
+      while (ld_acquire(done + j) != epoch) {}
+  }
+  double rhs = d[i], diag = 1.0;
+  for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+    const int j = colidx[k];
+    const double a = vals[k];
+    if (j == i) {
+      diag = a;
+      if (skip_diag) continue;
+    }
+    rhs -= a * __ldcg(v + j);   // L2: other SMs write v during the sweep
+  }
+  if (skip_diag) v[i] = rhs / diag;
+  else v[i] = __ldcg(v + i) + relax * (rhs / diag);
+  st_release(done + i, epoch);
+}
 __global__ void __launch_bounds__(kThreads) k_relax_blend(int64_t n, double w, const double* __restrict__ xold,
                                                           double* __restrict__ x) {
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
@@ -703,6 +745,14 @@ void sor_level(const int32_t* rows, int64_t count, const int64_t* rowptr, const 
                const double* d, double* v, double relax, bool skip_diag, cudaStream_t s) {
   if (count <= 0) return;
   k_sor_level<<<(unsigned)((count + 127) / 128), 128, 0, s>>>(rows, count, rowptr, colidx, vals, d, v, relax, skip_diag);
+  check_launch();
+}
+void sor_sweep(const int32_t* slots, int64_t nslots, bool backward, const int64_t* rowptr, const int32_t* colidx,
+               const double* vals, const int64_t* dep_ptr, const int32_t* dep_idx, const double* d, double* v, double relax,
+               bool skip_diag, int* done, int epoch, cudaStream_t s) {
+  if (nslots <= 0) return;
+  k_sor_sweep<<<(unsigned)((nslots + 127) / 128), 128, 0, s>>>(slots, nslots, backward, rowptr, colidx, vals, dep_ptr, dep_idx, d,
+                                                               v, relax, skip_diag, done, epoch);
   check_launch();
 }
 void jacobi_apply(int64_t n, const double* dinv, double relax, const double* d, double* v, cudaStream_t s) {

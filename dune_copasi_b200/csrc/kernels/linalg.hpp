@@ -98,6 +98,12 @@ void jacobi_apply(int64_t n, const double* dinv, double relax, const double* d, 
 // symmetric pattern), so the result is the sequential sweep's, whatever the order inside the level.
 void sor_level(const int32_t* rows, int64_t count, const int64_t* rowptr, const int32_t* colidx, const double* vals,
                const double* d, double* v, double relax, bool skip_diag, cudaStream_t s);
+// The same sweep as nlev calls of sor_level, self-scheduled in one launch: slots = the rows in level order, every
+// level padded with -1 to a multiple of 32; dep_ptr / dep_idx = pattern of A + A^T; done[row] = epoch once a row is
+// finished (epochs increase from sweep to sweep; `done` starts at 0, epochs at 1).  Bit-identical to the level loop.
+void sor_sweep(const int32_t* slots, int64_t nslots, bool backward, const int64_t* rowptr, const int32_t* colidx,
+               const double* vals, const int64_t* dep_ptr, const int32_t* dep_idx, const double* d, double* v, double relax,
+               bool skip_diag, int* done, int epoch, cudaStream_t s);
 // x = w x + (1 - w) xold   (the relaxation step that closes a dbgs sweep)
 void relax_blend(int64_t n, double w, const double* xold, double* x, cudaStream_t s);
 void csr_extract_diag_inv(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* vals,

@@ -77,7 +77,47 @@ __global__ void __launch_bounds__(256) k_halo_pull(Mailboxes m, HaloArgs h, doub
   }
 }
 
+// general halo plan in one launch: gather the send lists straight into the neighbours' slots, publish, wait for the
+// neighbours' flags, scatter the slots into the ghost entries (replaces gather kernels + ncclSend/Recv + scatter
+// kernels: 15 launches per exchange with 7 neighbours)
+__global__ void __launch_bounds__(256) k_halo_general(Mailboxes m, GeneralHaloArgs h, double* x, unsigned long long seq) {
+  const int par = (int)(seq & 1ull);
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (int k = 0; k < h.npeers; ++k) {
+    double* dst = (double*)(m.box[h.peer[k]] + halo_data_offset(m.size, m.cap, m.rank, par));
+    const long long b = h.send_ptr[k], n = h.send_ptr[k + 1] - b;
+    for (long long i = tid; i < n; i += nth) dst[i] = x[h.send_idx[b + i]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(h.counter, 1u);
+    last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    *h.counter = 0;
+    __threadfence_system();
+    for (int k = 0; k < h.npeers; ++k)
+      st_flag((unsigned long long*)(m.box[h.peer[k]] + halo_flag_offset(m.size, m.rank, par)), seq);
+  }
+  for (int k = 0; k < h.npeers; ++k) {
+    if (threadIdx.x == 0)
+      wait_flag((const unsigned long long*)(m.box[m.rank] + halo_flag_offset(m.size, h.peer[k], par)), seq, h.error);
+    __syncthreads();
+    __threadfence_system();
+    const double* src = (const double*)(m.box[m.rank] + halo_data_offset(m.size, m.cap, h.peer[k], par));
+    const long long b = h.recv_ptr[k], n = h.recv_ptr[k + 1] - b;
+    for (long long i = tid; i < n; i += nth) x[h.recv_idx[b + i]] = ld_data(src + i);
+  }
+}
+
 }  // namespace
+
+void halo_general(const Mailboxes& m, const GeneralHaloArgs& h, double* x, unsigned long long seq, cudaStream_t s) {
+  k_halo_general<<<kHaloBlocks, 256, 0, s>>>(m, h, x, seq);
+}
 
 void allreduce(const Mailboxes& m, double* data, int n, unsigned long long seq, int* error, cudaStream_t s) {
   k_allreduce<<<1, 64, 0, s>>>(m, data, n, seq, error);

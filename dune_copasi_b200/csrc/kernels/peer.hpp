@@ -24,16 +24,17 @@ __host__ __device__ inline size_t ar_val_offset(int size, int par, int src) {
 __host__ __device__ inline size_t ar_flag_offset(int size, int par, int src) {
   return (size_t)2 * size * kMaxWords * sizeof(double) + (size_t)(par * size + src) * 8;
 }
-// slot 0: data from the lower neighbour, slot 1: from the higher one
+// Halo slots.  Slab partitions use two (slot 0: data from the lower neighbour, slot 1: from the higher one);
+// general partitions (RCB over unstructured meshes: several neighbours, index lists) use one slot per source rank.
 __host__ __device__ inline size_t halo_flag_offset(int size, int slot, int par) {
   return (size_t)2 * size * kMaxWords * sizeof(double) + (size_t)2 * size * 8 + (size_t)(slot * 2 + par) * 8;
 }
 __host__ __device__ inline size_t halo_data_offset(int size, long long cap, int slot, int par) {
-  size_t head = (size_t)2 * size * kMaxWords * sizeof(double) + (size_t)2 * size * 8 + 4 * 8;
+  size_t head = (size_t)2 * size * kMaxWords * sizeof(double) + (size_t)2 * size * 8 + (size_t)kMaxRanks * 2 * 8;
   head = (head + 255) / 256 * 256;
   return head + (size_t)(slot * 2 + par) * (size_t)cap * sizeof(double);
 }
-inline size_t mailbox_bytes(int size, long long cap) { return halo_data_offset(size, cap, 2, 0); }
+inline size_t mailbox_bytes(int size, long long cap, int nslots = 2) { return halo_data_offset(size, cap, nslots, 0); }
 
 struct HaloArgs {
   int npeers;                     // <= 2
@@ -46,7 +47,21 @@ struct HaloArgs {
 };
 constexpr long long kSpinLimit = 1ll << 26;   // polls of a flag before giving up (about a minute of wall time)
 
+// general partitions: peer k sends the entries send_idx[send_ptr[k] .. send_ptr[k+1]) of the vector (both sides
+// list them in the same canonical order) and fills recv_idx[recv_ptr[k] .. recv_ptr[k+1]); slot = source rank
+struct GeneralHaloArgs {
+  int npeers;
+  int peer[kMaxRanks];
+  long long send_ptr[kMaxRanks + 1], recv_ptr[kMaxRanks + 1];
+  const int* send_idx;
+  const int* recv_idx;
+  unsigned* counter;
+  int* error;
+};
+
 void allreduce(const Mailboxes& m, double* data, int n, unsigned long long seq, int* error, cudaStream_t s);
+// one launch per exchange whatever the number of neighbours: pack + push, publish, wait, pull + unpack
+void halo_general(const Mailboxes& m, const GeneralHaloArgs& h, double* x, unsigned long long seq, cudaStream_t s);
 void halo(const Mailboxes& m, const HaloArgs& h, double* x, unsigned long long seq, cudaStream_t s);
 
 // ---- exchanges fused into the kernels of the Krylov sweeps (kernels/linalg.cu, peer_device.cuh) ------------

@@ -135,3 +135,114 @@ __device__ __forceinline__ void dc_reduce_kernel(const DcReduceArgs& a) {
     for (int k = 0; k < DC_NRED; ++k) a.partials[(long long)blockIdx.x * DC_NRED + k] = sh[k];
   }
 }
+
+// ---- Q1 cells (lattice cubes as multilinear elements, kernels/assembly_q1.cuh): the order-4 rule of a cube is the
+// 3-point Gauss rule per axis (dune-geometry's cube rules are Gauss-Legendre tensor products); corner a sits at the
+// bit pattern of a (x = bit 0), points run x fastest.  The gradient of a field varies inside the cell and is formed
+// per point.  Restated in oracle/core.py (reduce, etype 1).
+#define DC_Q1_ND (1 << DC_DIM)
+#if DC_DIM == 2
+#define DC_Q1_NQ 9
+#else
+#define DC_Q1_NQ 27
+#endif
+template <int C>
+__device__ __forceinline__ void dc_reduce_q1_kernel(const DcReduceArgs& a) {
+  typedef DcReduce<C> R;
+  constexpr int NS = R::NS;
+  double acc[DC_NRED];
+#pragma unroll
+  for (int k = 0; k < DC_NRED; ++k) acc[k] = a.init[k];
+  DcCtx c;
+  c.time = a.time;
+  c.in_volume = 1.0; c.in_boundary = 0.0; c.in_skeleton = 0.0;
+  c.nrm[0] = c.nrm[1] = c.nrm[2] = 0.0;
+  c.pos[2] = 0.0;
+  const double g1[3] = {0.5 - 0.3872983346207417, 0.5, 0.5 + 0.3872983346207417};   // 1/2 -+ sqrt(0.15)
+  const double w1[3] = {5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0};
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < a.n; t += (long long)gridDim.x * blockDim.x) {
+    const long long e = a.elem_ids ? (long long)a.elem_ids[t] : t;
+    double X[DC_Q1_ND][DC_DIM], xl[NS][DC_Q1_ND], h[DC_DIM];
+#pragma unroll
+    for (int k = 0; k < DC_Q1_ND; ++k) {
+      const int v = a.elems[e * DC_Q1_ND + k];
+#pragma unroll
+      for (int d = 0; d < DC_DIM; ++d) X[k][d] = a.coords[(long long)v * DC_DIM + d];
+      if (R::NS_REAL > 0) {
+        const int dof = a.vdof ? a.vdof[v] : a.dof_offset + v * NS;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) xl[s][k] = a.x[dof + s];
+      } else {
+        xl[0][k] = 0.0;
+      }
+    }
+    double det = 1.0;
+#pragma unroll
+    for (int d = 0; d < DC_DIM; ++d) { h[d] = X[1 << d][d] - X[0][d]; det *= h[d]; }
+    c.entity_volume = det;
+#pragma unroll
+    for (int k = 0; k < DC_NKEYS; ++k) c.cell[k] = a.cell[(long long)k * a.ne_total + e];
+#pragma unroll 1
+    for (int q = 0; q < DC_Q1_NQ; ++q) {
+      int qi[3] = {q % 3, (q / 3) % 3, q / 9};
+      double w = 1.0, p[DC_DIM];
+#pragma unroll
+      for (int d = 0; d < DC_DIM; ++d) { p[d] = g1[qi[d]]; w *= w1[qi[d]]; }
+      double lam[DC_Q1_ND], u[NS], gu[NS][DC_DIM], val[DC_NRED];
+#pragma unroll
+      for (int m = 0; m < DC_Q1_ND; ++m) {
+        double f = 1.0;
+#pragma unroll
+        for (int d = 0; d < DC_DIM; ++d) f *= ((m >> d) & 1) ? p[d] : 1.0 - p[d];
+        lam[m] = f;
+      }
+#pragma unroll
+      for (int d = 0; d < DC_DIM; ++d) {
+        double x = 0.0;
+#pragma unroll
+        for (int m = 0; m < DC_Q1_ND; ++m) x += lam[m] * X[m][d];
+        c.pos[d] = x;
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        double v = 0.0;
+#pragma unroll
+        for (int m = 0; m < DC_Q1_ND; ++m) v += lam[m] * xl[s][m];
+        u[s] = v;
+#pragma unroll
+        for (int r = 0; r < DC_DIM; ++r) {
+          double g = 0.0;
+#pragma unroll
+          for (int m = 0; m < DC_Q1_ND; ++m) {
+            double f = ((m >> r) & 1) ? 1.0 : -1.0;
+#pragma unroll
+            for (int d = 0; d < DC_DIM; ++d)
+              if (d != r) f *= ((m >> d) & 1) ? p[d] : 1.0 - p[d];
+            g += xl[s][m] * f;
+          }
+          gu[s][r] = g / h[r];
+        }
+      }
+      c.integration_factor = w * det;
+      R::eval(c, u, gu, val);
+#pragma unroll
+      for (int k = 0; k < DC_NRED; ++k) acc[k] = dc_reduce_op(k, val[k], acc[k]);
+    }
+  }
+  __shared__ double sh[DC_RED_THREADS * DC_NRED];
+#pragma unroll
+  for (int k = 0; k < DC_NRED; ++k) sh[threadIdx.x * DC_NRED + k] = acc[k];
+  __syncthreads();
+  for (int stride = DC_RED_THREADS / 2; stride > 0; stride >>= 1) {
+    if ((int)threadIdx.x < stride) {
+#pragma unroll
+      for (int k = 0; k < DC_NRED; ++k)
+        sh[threadIdx.x * DC_NRED + k] = dc_reduce_op(k, sh[(threadIdx.x + stride) * DC_NRED + k], sh[threadIdx.x * DC_NRED + k]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < DC_NRED; ++k) a.partials[(long long)blockIdx.x * DC_NRED + k] = sh[k];
+  }
+}

@@ -52,8 +52,9 @@ Model::Model(const PTree& cfg_, int dim_, const std::vector<std::string>& keys)
       s.local = comp_nspec[c]++;
       s.initial = f.get("initial.expression", std::string());
       s.constrain_boundary = f.get("constrain.boundary.expression", std::string());
-      if (f.has_sub("constrain.skeleton") || f.has_sub("constrain.volume"))
-        fail("scalar_field.", name, ": only constrain.boundary is built");
+      s.constrain_skeleton = f.get("constrain.skeleton.expression", std::string());
+      // constrain.volume binds the dofs attached to the cell itself (codim 0, constraints.hh:93-112): P1 / Q1
+      // elements have none, so the section is read and has no effect -- as in the reference
       species.push_back(s);
       scfg.push_back(&f);
     }
@@ -234,12 +235,13 @@ std::vector<std::pair<int, int>> Model::outflow_pairs() const {
 NodeP Model::compile(const std::string& text) const { return resolve_expr(parse_expr(text), ctx); }
 
 double Model::eval_host(const NodeP& ast, const double* pos, double time, const double* cell,
-                        double in_volume, double in_boundary) const {
+                        double in_volume, double in_boundary, double in_skeleton) const {
   return eval_expr(ast, [&](const std::string& n) -> double {
     if (n == "time") return time;
     if (n == "in_volume") return in_volume;
     if (n == "in_boundary") return in_boundary;
-    if (n == "in_skeleton" || n == "integration_factor" || n == "entity_volume") return 0.0;
+    if (n == "in_skeleton") return in_skeleton;
+    if (n == "integration_factor" || n == "entity_volume") return 0.0;
     for (int a = 0; a < 3; ++a) {
       if (n == std::string("position_") + kAxis[a]) return a < dim ? pos[a] : 0.0;
       if (n == std::string("normal_") + kAxis[a]) return 0.0;

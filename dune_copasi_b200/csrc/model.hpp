@@ -28,7 +28,7 @@ struct Term {
 struct SpeciesInfo {
   std::string name;
   int comp = -1, local = -1;
-  std::string initial, constrain_boundary;   // raw expressions ("" if absent)
+  std::string initial, constrain_boundary, constrain_skeleton;   // raw expressions ("" if absent)
 };
 
 class Model {
@@ -75,7 +75,7 @@ class Model {
 
   // host evaluation of a resolved expression with position/time/cell data bound (setup work only)
   double eval_host(const NodeP& ast, const double* pos, double time, const double* cell,
-                   double in_volume, double in_boundary) const;
+                   double in_volume, double in_boundary, double in_skeleton = 0.0) const;
   NodeP compile(const std::string& text) const;   // parse + resolve against the context
 
   // CUDA source of the per-model device functions (see kernels/assembly.cuh for the consumers)

@@ -65,7 +65,6 @@ Reducer::Reducer(std::shared_ptr<DeviceOperator> op, const PTree& cfg, Communica
   const Grid& g = *op_->grid;
   keys_ = parse_keys(m, cfg);
   if (keys_.empty()) return;
-  if (g.elem_kind == 1) fail("[model.reduce] functionals on Q1 cube grids are not built (simplex quadrature only)");
   require_device();
 
   // ---- elements per compartment; cells outside every compartment are visited too (their species
@@ -134,7 +133,9 @@ std::string Reducer::source(const Model& m, const std::vector<Key>& keys_) {
   o << kReduceSource << "\n";
   for (int c = 0; c <= m.ncomp(); ++c)
     o << "extern \"C\" __global__ void __launch_bounds__(DC_RED_THREADS) dc_k_reduce_" << c
-      << "(DcReduceArgs a) { dc_reduce_kernel<" << c << ">(a); }\n";
+      << "(DcReduceArgs a) { dc_reduce_kernel<" << c << ">(a); }\n"
+      << "extern \"C\" __global__ void __launch_bounds__(DC_RED_THREADS) dc_k_reduce_q1_" << c
+      << "(DcReduceArgs a) { dc_reduce_q1_kernel<" << c << ">(a); }\n";
   return o.str();
 }
 
@@ -167,7 +168,7 @@ std::vector<ReduceEntry> Reducer::apply(double time, const double* x, bool throw
     const int blocks = (int)std::min<int64_t>(max_blocks_, (nelem_[c] + 127) / 128);
     {
       DeviceOperator::ProfScope ps(op_.get(), "reduce");
-      jit_launch(jit_.kernel("dc_k_reduce_" + std::to_string(c)), blocks, 128, 0, s, a);
+      jit_launch(jit_.kernel((g.elem_kind == 1 ? "dc_k_reduce_q1_" : "dc_k_reduce_") + std::to_string(c)), blocks, 128, 0, s, a);
       op_->stats.launches++;
     }
     host.resize((size_t)blocks * nk);

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <vector>
 
 #include "comm.hpp"
@@ -30,6 +31,7 @@ LinearSolver::LinearSolver(std::shared_ptr<DeviceOperator> op, const PTree& cfg,
   matrix_free = cfg.get("matrix_free", false);
   verbosity = cfg.get("verbosity", 0);
   speculation = cfg.get("b200.speculation", true);
+  sor_sweep_ = cfg.get("b200.sor_sweep", true);
   auto range = cfg.get_vec("convergence_condition.iteration_range", {1, 500});   // iterative.hh:53-54
   max_iterations = (int)range.back();
   la::reduce_workspace_create(&ws_);
@@ -200,6 +202,46 @@ void LinearSolver::build_levels() {
   std::vector<int64_t> cur(level_ptr_.begin(), level_ptr_.end() - 1);
   for (int64_t i = 0; i < n; ++i) rows[cur[level[i]]++] = (int32_t)i;
   level_rows_.upload(rows, op_->stream);
+  if (sor_sweep_) {
+    // slots of the self-scheduled sweeps: levels padded to whole warps
+    std::vector<int32_t> slots;
+    slots.reserve((size_t)n + 32 * (size_t)nlev);
+    for (int32_t l = 0; l < nlev; ++l) {
+      for (int64_t p = level_ptr_[l]; p < level_ptr_[l + 1]; ++p) slots.push_back(rows[p]);
+      while (slots.size() % 32) slots.push_back(-1);
+    }
+    sweep_nslots_ = (int64_t)slots.size();
+    sweep_slots_.upload(slots, op_->stream);
+    // rows to wait for: the pattern of A + A^T.  Structurally symmetric patterns (the usual case) reuse A's.
+    bool symmetric = true;
+#pragma omp parallel for schedule(static) reduction(&& : symmetric)
+    for (int64_t i = 0; i < n; ++i)
+      for (int64_t k = rp[i]; k < rp[i + 1] && symmetric; ++k) {
+        const int32_t j = ci[k];
+        symmetric = symmetric && std::binary_search(ci.begin() + rp[j], ci.begin() + rp[j + 1], (int32_t)i);
+      }
+    dep_is_pattern_ = symmetric;
+    if (!symmetric) {
+      std::vector<std::vector<int32_t>> extra(n);   // transposed entries missing from the row
+      for (int64_t i = 0; i < n; ++i)
+        for (int64_t k = rp[i]; k < rp[i + 1]; ++k) {
+          const int32_t j = ci[k];
+          if (!std::binary_search(ci.begin() + rp[j], ci.begin() + rp[j + 1], (int32_t)i)) extra[j].push_back((int32_t)i);
+        }
+      std::vector<int64_t> dp(n + 1, 0);
+      std::vector<int32_t> di;
+      for (int64_t i = 0; i < n; ++i) {
+        di.insert(di.end(), ci.begin() + rp[i], ci.begin() + rp[i + 1]);
+        di.insert(di.end(), extra[i].begin(), extra[i].end());
+        dp[i + 1] = (int64_t)di.size();
+      }
+      dep_ptr_.upload(dp, op_->stream);
+      dep_idx_.upload(di, op_->stream);
+    }
+    sweep_done_.alloc(n);
+    sweep_done_.zero(op_->stream);
+    sweep_epoch_ = 0;
+  }
   DCB_CUDA(cudaStreamSynchronize(op_->stream));
 }
 
@@ -213,18 +255,26 @@ void LinearSolver::sor_apply(const double* d, double* v) {
   la::fill(op_->ndofs, 0.0, v, s);
   op_->stats.launches++;
   if (skip_diag && sweep_[0].n < (size_t)op_->ndofs) sweep_[0].alloc(op_->ndofs);
+  auto sweep = [&](bool backward, bool skip) {
+    if (sor_sweep_) {
+      if (sweep_epoch_ == INT32_MAX) { sweep_done_.zero(s); sweep_epoch_ = 0; }
+      la::sor_sweep(sweep_slots_.p, sweep_nslots_, backward, rp, op_->colidx.p, vals.p, dep_is_pattern_ ? rp : dep_ptr_.p,
+                    dep_is_pattern_ ? op_->colidx.p : dep_idx_.p, d, v, relaxation, skip, sweep_done_.p, ++sweep_epoch_, s);
+      op_->stats.launches++;
+      return;
+    }
+    for (int k = 0; k < nlev; ++k) {
+      const int l = backward ? nlev - 1 - k : k;
+      la::sor_level(level_rows_.p + level_ptr_[l], level_ptr_[l + 1] - level_ptr_[l], rp, op_->colidx.p, vals.p, d, v,
+                    relaxation, skip, s);
+    }
+    op_->stats.launches += nlev;
+  };
   for (int it = 0; it < prec_iterations; ++it) {
     if (skip_diag) { la::copy(op_->ndofs, v, sweep_[0].p, s); op_->stats.launches++; }   // dbgs: xold
-    for (int l = 0; l < nlev; ++l)
-      la::sor_level(level_rows_.p + level_ptr_[l], level_ptr_[l + 1] - level_ptr_[l], rp, op_->colidx.p, vals.p, d, v,
-                    relaxation, skip_diag, s);
-    op_->stats.launches += nlev;
+    sweep(false, skip_diag);
     if (skip_diag) { la::relax_blend(op_->ndofs, relaxation, sweep_[0].p, v, s); op_->stats.launches++; }
-    if (prec_type != "SSOR") continue;
-    for (int l = nlev - 1; l >= 0; --l)
-      la::sor_level(level_rows_.p + level_ptr_[l], level_ptr_[l + 1] - level_ptr_[l], rp, op_->colidx.p, vals.p, d, v,
-                    relaxation, false, s);
-    op_->stats.launches += nlev;
+    if (prec_type == "SSOR") sweep(true, false);
   }
 }
 

@@ -84,6 +84,14 @@ class LinearSolver {
   void sor_apply(const double* d, double* v);
   std::vector<int64_t> level_ptr_;
   DeviceBuffer<int32_t> level_rows_;
+  // self-scheduled sweeps (la::sor_sweep, linear_solver.b200.sor_sweep = true): one launch per sweep instead of one per level
+  bool sor_sweep_ = true;
+  DeviceBuffer<int32_t> sweep_slots_, dep_idx_;
+  DeviceBuffer<int64_t> dep_ptr_;
+  DeviceBuffer<int> sweep_done_;
+  int64_t sweep_nslots_ = 0;
+  int sweep_epoch_ = 0;
+  bool dep_is_pattern_ = true;
   // linearisation point
   double t_ = 0, wM_ = 0, wA_ = 0;
   const double* x_ = nullptr;

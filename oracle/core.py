@@ -289,29 +289,39 @@ class Model:
         return self.eval_at_dofs("initial", time)
 
     def constraints(self):
-        """-> (dof indices, values) of Dirichlet translation constraints (constraints.hh:158-195).
-        `time` is NaN there; a value of no_value (DBL_MAX) means unconstrained."""
+        """-> (dof indices, values) of Dirichlet translation constraints (constraints.hh:114-195).
+        `time` is NaN there; a value of no_value (DBL_MAX) means unconstrained.  A vertex of a face keeps its
+        value when it is a boundary vertex exactly if the face is a boundary face (:182): constrain.boundary
+        binds the boundary vertices, constrain.skeleton the others (every one of them lies on a face with a
+        neighbour); constrain.volume binds codim-0 dofs, which P1 / Q1 do not have (:93-112).  The
+        face-dependent symbols (normal_*, entity_volume) read 0."""
         m = self.mesh
-        pos, spec = self.dof_positions()
         isb = np.zeros(m.nv, dtype=bool)
         isb[m.boundary_vertices] = True
         dofs, vals = [], []
         for g, sp in enumerate(self.species):
-            text = INI.get(sp.cfg, "constrain.boundary.expression")
-            if text is None or E.is_absent(text):
-                continue
             v = m.comp_vertices[sp.comp]
             d = m.comp_offset[sp.comp] + np.arange(v.size) * self.comp_nspec[sp.comp] + sp.local
-            sel = isb[v]
-            code, consts = E.compile_expr(text, self.sym, self.ctx)
-            ctx = np.zeros((int(sel.sum()), self.sym.nslots))
-            ctx[:, E.SLOT_TIME] = np.nan
-            ctx[:, E.SLOT_INBND] = 1.0
-            ctx[:, E.SLOT_POS:E.SLOT_POS + m.dim] = m.coords[v[sel]]
-            val = eval_program(code, consts, ctx)
-            ok = val != E.DBL_MAX
-            dofs.append(d[sel][ok])
-            vals.append(val[ok])
+            dd, vv = [], []
+            for key, slot, sel in (("constrain.boundary.expression", E.SLOT_INBND, isb[v]),
+                                   ("constrain.skeleton.expression", E.SLOT_INSKEL, ~isb[v])):
+                text = INI.get(sp.cfg, key)
+                if text is None or E.is_absent(text):
+                    continue
+                code, consts = E.compile_expr(text, self.sym, self.ctx)
+                ctx = np.zeros((int(sel.sum()), self.sym.nslots))
+                ctx[:, E.SLOT_TIME] = np.nan
+                ctx[:, slot] = 1.0
+                ctx[:, E.SLOT_POS:E.SLOT_POS + m.dim] = m.coords[v[sel]]
+                val = eval_program(code, consts, ctx)
+                ok = val != E.DBL_MAX
+                dd.append(d[sel][ok])
+                vv.append(val[ok])
+            if dd:
+                dd, vv = np.concatenate(dd), np.concatenate(vv)
+                order = np.argsort(dd, kind="stable")       # ascending dofs within a species, as the product walks them
+                dofs.append(dd[order])
+                vals.append(vv[order])
         if not dofs:
             return np.zeros(0, dtype=np.int64), np.zeros(0)
         return np.concatenate(dofs), np.concatenate(vals)

@@ -39,6 +39,7 @@ OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_NEG = 2, 3, 4, 5, 6, 7
 OP_LT, OP_GT, OP_LE, OP_GE, OP_EQ, OP_NE = 8, 9, 10, 11, 12, 13
 OP_AND, OP_OR, OP_NOT, OP_SEL = 14, 15, 16, 17
 OP_F1, OP_F2, OP_MOD = 18, 19, 20
+OP_TAB = 21          # tabulated context function: arg = offset of its record in the constants
 
 F1 = {"sqrt": 0, "exp": 1, "log": 2, "sin": 3, "cos": 4, "tan": 5, "abs": 6, "floor": 7,
       "ceil": 8, "tanh": 9, "sinh": 10, "cosh": 11, "asin": 12, "acos": 13, "atan": 14,
@@ -83,11 +84,62 @@ def tokenize(s: str):
     return out
 
 
+def lerp_std(a: float, b: float, t: float) -> float:
+    """std::lerp as libstdc++ implements it (the reference calls std::lerp, context.cc:93, :262)."""
+    if (a <= 0 and b >= 0) or (a >= 0 and b <= 0):
+        return t * b + (1 - t) * a
+    if t == 1:
+        return b
+    x = a + t * (b - a)
+    return max(b, x) if (t > 1) == (b > a) else min(b, x)
+
+
+@dataclass
+class Table:
+    """Tabulated one-argument context function.
+    kind 0: `type = interpolation` (context.cc:72-97): lower_bound on the sorted domain, the end
+            values outside, std::lerp inside.
+    kind 1: `type = function` with `interpolate = true` (context.cc:237-283), restated literally:
+            the sample index i = max(0, k) and j = min(k, intervals + 1) come from the same interval
+            number k, so lerp(g[i], g[j], t) = g[k]; `clamp` is std::clamp(domain[0], pos, domain[1])
+            with the arguments in that order, i.e. max(domain[0], pos); `error` raises (NaN in the C VM)."""
+    kind: int
+    domain: list
+    range: list
+    clamp: bool = False
+    name: str = ""
+
+    def __call__(self, x: float) -> float:
+        import bisect
+        if self.kind == 0:
+            d = bisect.bisect_left(self.domain, x)
+            if d == 0:
+                return self.range[0]
+            if d == len(self.domain):
+                return self.range[-1]
+            return lerp_std(self.range[d - 1], self.range[d],
+                            (x - self.domain[d - 1]) / (self.domain[d] - self.domain[d - 1]))
+        d0, d1 = self.domain
+        n = len(self.range) - 1
+        if self.clamp:
+            x = x if d0 < x else d0
+        elif x < d0 or x > d1 or x != x:
+            raise ExprError(f"interpolation of function {self.name} is out of bounds: {x} not in [{d0}, {d1}]")
+        whole = math.modf((x - d0) * (n / (d1 - d0)))[1]
+        k = 0 if whole <= 0 else (n if whole >= n else int(whole))
+        return self.range[k]
+
+    def record(self) -> list:
+        """what the C VM reads at the OP_TAB offset: kind, samples, clamp, domain, range"""
+        return [float(self.kind), float(len(self.range)), float(self.clamp)] + list(self.domain) + list(self.range)
+
+
 @dataclass
 class Context:
-    """parser_context: constants and inline functions (context.cc:56-97)."""
+    """parser_context: constants, inline functions and tabulated functions (context.cc:56-97, 237-283)."""
     constants: dict = field(default_factory=dict)          # name -> float
     functions: dict = field(default_factory=dict)          # name -> (argnames, body string)
+    tables: dict = field(default_factory=dict)             # name -> Table
 
     @staticmethod
     def from_config(cfg: dict) -> "Context":
@@ -103,6 +155,41 @@ class Context:
                 head, body = sub["expression"].split(":", 1)
                 args = [a.strip() for a in head.split(",") if a.strip()]
                 ctx.functions[name] = (args, body.strip())
+            elif typ == "interpolation":
+                dom = [float(v) for v in str(sub["domain"]).split()]
+                rng = [float(v) for v in str(sub["range"]).split()]
+                if dom != sorted(dom):
+                    raise ExprError("The interpolation domain must be sorted")
+                if len(dom) < 2 or len(dom) != len(rng):
+                    raise ExprError("Interpolation range and domain must have at least two points and be the same size")
+                ctx.tables[name] = Table(0, dom, rng, name=name)
+        truthy = ("1", "true", "yes", "on")
+        for name, sub in cfg.items():
+            if not isinstance(sub, dict) or sub.get("type") != "function":
+                continue
+            if str(sub.get("interpolate", "false")).strip().lower() not in truthy:
+                continue
+            args, body = ctx.functions[name]
+            if len(args) != 1:
+                raise ExprError(f"Cannot interpolate '{name}' function with {len(args)} arguments")
+            isub = sub.get("interpolation", {}) if isinstance(sub.get("interpolation", {}), dict) else {}
+            n = int(isub.get("intervals", 1000))
+            if n > 1e5:
+                raise ExprError("Number of interpolation intervals is too big!")
+            if n < 1:
+                raise ExprError(f"At least one interval is required in function {name}")
+            dsub = isub.get("domain", {})
+            dom = [float(v) for v in str(dsub.get(args[0], "0 1")).split()] if isinstance(dsub, dict) else [0.0, 1.0]
+            if len(dom) != 2 or dom[0] >= dom[1]:
+                raise ExprError(f"Domain arguments of function {name} are not ordered")
+            ooo = str(isub.get("out_of_bounds", "error"))
+            if ooo not in ("clamp", "error"):
+                raise ExprError(f"Not known '{name}.interpolation.out_of_bounds = {ooo}'")
+            plain = Context(ctx.constants, {k: v for k, v in ctx.functions.items()}, {})
+            ast = resolve(Parser(body).parse(), plain)
+            width = (dom[1] - dom[0]) / float(n)
+            rng = [py_eval(ast, {args[0]: dom[0] + float(i) * width}) for i in range(n + 1)]
+            ctx.tables[name] = Table(1, dom, rng, clamp=(ooo == "clamp"), name=name)
         return ctx
 
 
@@ -228,6 +315,8 @@ def _subst(ast, env):
         return ("sel", _subst(ast[1], env), _subst(ast[2], env), _subst(ast[3], env))
     if k == "call":
         return ("call", ast[1], [_subst(a, env) for a in ast[2]])
+    if k == "tab":
+        return ("tab", ast[1], _subst(ast[2], env))
     raise AssertionError(k)
 
 
@@ -255,6 +344,10 @@ def resolve(ast, ctx: Context, depth=0):
         return ("sel",) + tuple(resolve(a, ctx, depth) for a in ast[1:])
     if k == "call":
         name, args = ast[1], [resolve(a, ctx, depth) for a in ast[2]]
+        if name in ctx.tables:
+            if len(args) != 1:
+                raise ExprError(f"function {name} expects 1 argument, got {len(args)}")
+            return ("tab", ctx.tables[name], args[0])
         if name in ctx.functions:
             argn, body = ctx.functions[name]
             if len(argn) != len(args):
@@ -265,6 +358,8 @@ def resolve(ast, ctx: Context, depth=0):
         if name == "if" and len(args) == 3:
             return ("sel", args[0], args[1], args[2])
         return ("call", name, args)
+    if k == "tab":
+        return ("tab", ast[1], resolve(ast[2], ctx, depth))
     raise AssertionError(k)
 
 
@@ -330,6 +425,10 @@ def emit(ast, sym: Symbols, code: list, consts: list):
                 code += [OP_F2, F2[name]]
         else:
             raise ExprError(f"unknown function {name!r}/{len(args)}")
+    elif k == "tab":
+        emit(ast[2], sym, code, consts)
+        code += [OP_TAB, len(consts)]
+        consts.extend(ast[1].record())
     else:
         raise AssertionError(k)
 
@@ -384,4 +483,6 @@ def py_eval(ast, env: dict):
         if n == "abs": return abs(args[0])
         if n in ("sgn", "sign"): return float((args[0] > 0) - (args[0] < 0))
         return getattr(math, n)(args[0])
+    if k == "tab":
+        return ast[1](py_eval(ast[2], env))
     raise AssertionError(k)

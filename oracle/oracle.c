@@ -109,6 +109,35 @@ static double f2(int id, double a, double b) {
   return NAN;
 }
 
+/* std::lerp as libstdc++ implements it (context.cc:93 calls std::lerp) */
+static double lerp_std(double a, double b, double t) {
+  if ((a <= 0 && b >= 0) || (a >= 0 && b <= 0)) return t * b + (1 - t) * a;
+  if (t == 1) return b;
+  const double x = a + t * (b - a);
+  return (t > 1) == (b > a) ? (b < x ? x : b) : (x < b ? x : b);
+}
+/* tabulated context function; rec = kind, samples, clamp, domain..., range... (expr.py Table.record)
+   kind 0: context.cc:83-95 (lower_bound + lerp); kind 1: context.cc:256-277, literally (returns sample k) */
+static double tab_eval(const double* rec, double x) {
+  const int kind = (int)rec[0], n = (int)rec[1], clamp = (int)rec[2];
+  if (kind == 0) {
+    const double *dom = rec + 3, *rng = rec + 3 + n;
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (dom[mid] < x) lo = mid + 1; else hi = mid; }
+    if (lo == 0) return rng[0];
+    if (lo == n) return rng[n - 1];
+    return lerp_std(rng[lo - 1], rng[lo], (x - dom[lo - 1]) / (dom[lo] - dom[lo - 1]));
+  }
+  const double d0 = rec[3], d1 = rec[4], *rng = rec + 5;
+  const int m = n - 1;   /* intervals */
+  if (clamp) x = d0 < x ? x : d0;
+  else if (x < d0 || x > d1 || x != x) return NAN;   /* the reference throws */
+  double whole;
+  modf((x - d0) * ((double)m / (d1 - d0)), &whole);
+  const int k = whole <= 0.0 ? 0 : (whole >= (double)m ? m : (int)whole);
+  return rng[k];
+}
+
 double orc_eval(const int32_t* code, int n, const double* consts, const double* ctx) {
   double st[64];
   int sp = 0;
@@ -136,6 +165,7 @@ double orc_eval(const int32_t* code, int n, const double* consts, const double* 
       case 18: st[sp - 1] = f1(arg, st[sp - 1]); break;
       case 19: sp--; st[sp - 1] = f2(arg, st[sp - 1], st[sp]); break;
       case 20: sp--; st[sp - 1] = fmod(st[sp - 1], st[sp]); break;
+      case 21: st[sp - 1] = tab_eval(consts + arg, st[sp - 1]); break;
     }
   }
   return st[0];

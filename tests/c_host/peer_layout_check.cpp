@@ -19,13 +19,13 @@ int main() {
           spans.push_back({ar_val_offset(size, par, src), ar_val_offset(size, par, src) + kMaxWords * sizeof(double)});
           spans.push_back({ar_flag_offset(size, par, src), ar_flag_offset(size, par, src) + 8});
         }
-      for (int slot = 0; slot < 2; ++slot)
+      for (int slot = 0; slot < size; ++slot)
         for (int par = 0; par < 2; ++par) {
           spans.push_back({halo_flag_offset(size, slot, par), halo_flag_offset(size, slot, par) + 8});
           spans.push_back({halo_data_offset(size, cap, slot, par),
                            halo_data_offset(size, cap, slot, par) + (size_t)cap * sizeof(double)});
         }
-      const size_t total = mailbox_bytes(size, cap);
+      const size_t total = mailbox_bytes(size, cap, size);
       std::sort(spans.begin(), spans.end());
       for (size_t i = 0; i < spans.size(); ++i) {
         if (spans[i].first % 8 != 0 || spans[i].second > total) { printf("bad span size=%d cap=%lld\n", size, cap); return 1; }

@@ -67,6 +67,45 @@ time_step_max = 0.1
 time_end = 10
 """ + SOLVER
 
+# tabulated parser_context functions (src/dune/copasi/parser/context.cc:72-97 `type = interpolation`,
+# :237-283 `interpolate = true`): a saturating uptake whose rate and slope are tables, a tabulated source profile
+TABLES = """
+[compartments.domain]
+type = expression
+expression = 1
+[parser_context.rate]
+type = interpolation
+domain = 0 0.25 0.5 1 2
+range = 0 0.4 0.65 0.9 1
+[parser_context.slope]
+type = interpolation
+domain = 0 0.25 0.2500001 0.5 0.5000001 1 1.0000001 2
+range = 1.6 1.6 1 1 0.5 0.5 0.1 0.1
+[parser_context.profile]
+type = function
+expression = x: exp(-8*(x-0.5)^2)
+interpolate = true
+interpolation.intervals = 64
+interpolation.domain.x = 0 1
+interpolation.out_of_bounds = clamp
+[parser_context.bump]
+type = function
+expression = s: 0.5 + 0.25*sin(6*s)
+interpolate = true
+interpolation.intervals = 20
+interpolation.domain.s = -1 3
+[model.scalar_field.u]
+compartment = domain
+initial.expression = 0.2 + 0.6*position_x
+storage.expression = 1
+cross_diffusion.u.expression = 0.01*bump(1)
+reaction.expression = profile(position_x) - rate(u)*bump(u)
+reaction.jacobian.u.expression = -slope(u)*bump(u)
+[model.time_step_operator]
+time_step_max = 0.1
+time_end = 10
+""" + SOLVER
+
 # test/poisson.ini: -lap u = -2 dim with Dirichlet data |x|^2 (constraints)
 POISSON = """
 [parser_context]
@@ -392,6 +431,12 @@ CASES = {
     "gauss2d": Case("gauss2d", GAUSS + REDUCE["gauss"], 2, _s(2, 32, [-1, -1], [2, 2]), t0=1.0, structured=([32, 32], [-1, -1], [2, 2])),
     "gauss3d": Case("gauss3d", GAUSS + REDUCE["gauss"], 3, _s(3, 8, [-1, -1, -1], [2, 2, 2]), t0=1.0, structured=([8, 8, 8], [-1, -1, -1], [2, 2, 2])),
     "exp": Case("exp", EXP + REDUCE["exp"], 2, _s(2, 2), structured=([2, 2], [0, 0], [1, 1])),
+    "tables": Case("tables", TABLES, 2, _s(2, 6), dt=0.05, structured=([6, 6], [0, 0], [1, 1])),
+    # constrain.skeleton binds vertices off the boundary (constraints.hh:128-156), constrain.volume no P1 dof at all (:93-112)
+    "poisson_pinned": Case("poisson_pinned", POISSON.replace(
+        "initial.expression = 0", "initial.expression = 0\nconstrain.skeleton.expression = "
+        "(abs(position_x - 0.5) < 1e-9 and in_skeleton) ? 0.1 + position_y : no_value\nconstrain.volume.expression = 7"),
+        2, _s(2, 16), structured=([16, 16], [0, 0], [1, 1])),
     "poisson": Case("poisson", POISSON + REDUCE["poisson"], 2, _s(2, 16), structured=([16, 16], [0, 0], [1, 1])),
     "grayscott2d": Case("grayscott2d", GRAY_SCOTT, 2, _s(2, 32), dt=1.0, structured=([32, 32], [0, 0], [1, 1])),
     "grayscott3d": Case("grayscott3d", GRAY_SCOTT, 3, _s(3, 10), dt=1.0, structured=([10, 10, 10], [0, 0, 0], [1, 1, 1])),
@@ -443,12 +488,12 @@ def _q1(name, ini, dim, cells, origin, extent, **kw):
 # The same models on the lattice cells as Q1 elements (BASELINE configs[3] "Q1 on a structured grid").
 # Not a reference element type: parity is product vs the oracle's own Q1 element.
 Q1_CASES = {
-    "gauss2d_q1": _q1("gauss2d_q1", GAUSS, 2, [24, 20], [-1, -1], [2, 2], t0=1.0),
-    "gauss3d_q1": _q1("gauss3d_q1", GAUSS, 3, [8, 6, 7], [-1, -1, -1], [2, 2, 2], t0=1.0),
-    "poisson_q1": _q1("poisson_q1", POISSON, 2, [16, 16], [0, 0], [1, 1]),
+    "gauss2d_q1": _q1("gauss2d_q1", GAUSS + REDUCE["gauss"], 2, [24, 20], [-1, -1], [2, 2], t0=1.0),
+    "gauss3d_q1": _q1("gauss3d_q1", GAUSS + REDUCE["gauss"], 3, [8, 6, 7], [-1, -1, -1], [2, 2, 2], t0=1.0),
+    "poisson_q1": _q1("poisson_q1", POISSON + REDUCE["poisson"], 2, [16, 16], [0, 0], [1, 1]),
     "grayscott2d_q1": _q1("grayscott2d_q1", GRAY_SCOTT, 2, [32, 32], [0, 0], [1, 1], dt=1.0),
     "grayscott3d_q1": _q1("grayscott3d_q1", GRAY_SCOTT, 3, [10, 9, 8], [0, 0, 0], [1, 0.9, 0.8], dt=1.0),
-    "mitchell_schaefer_q1": _q1("mitchell_schaefer_q1", MITCHELL_SCHAEFER, 2, [16, 16], [0, 0], [1, 1], dt=0.01),
+    "mitchell_schaefer_q1": _q1("mitchell_schaefer_q1", MITCHELL_SCHAEFER + REDUCE["mitchell_schaefer"], 2, [16, 16], [0, 0], [1, 1], dt=0.01),
 }
 ALL_CASES = {**CASES, **Q1_CASES}
 

@@ -1,0 +1,136 @@
+"""Tabulated parser_context functions: `type = interpolation` (src/dune/copasi/parser/context.cc:72-97) and
+`type = function` with `interpolate = true` (:237-283), restated literally in the oracle (Python evaluator and C
+byte-code VM) and in the product's front-end (host evaluation, generated CUDA source compiled as host C++)."""
+import math
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import cases as K
+from oracle import core as ORC, expr as E, ini as INI
+
+CTX = """
+[parser_context.tab]
+type = interpolation
+domain = -1 0 0.5 2
+range = 3 1 -2 4
+[parser_context.sq]
+type = function
+expression = x: c*x^2
+interpolate = true
+interpolation.intervals = 8
+interpolation.domain.x = 0 2
+interpolation.out_of_bounds = clamp
+[parser_context.strict]
+type = function
+expression = t: 1 + t
+interpolate = true
+interpolation.intervals = 4
+interpolation.domain.t = 0 1
+[parser_context.c]
+type = constant
+value = 3
+"""
+
+
+def _ctx():
+    return E.Context.from_config(INI.sub(INI.parse_ini(CTX), "parser_context"))
+
+
+def test_interpolation_table_is_lower_bound_plus_lerp():
+    t = _ctx().tables["tab"]
+    assert t(-5) == 3 and t(-1) == 3          # lower_bound == begin: front
+    assert t(2.5) == 4                        # lower_bound == end: back
+    assert t(0) == 1 and t(0.5) == -2 and t(2) == 4   # nodes are hit exactly
+    assert t(-0.5) == pytest.approx(2.0) and t(0.25) == pytest.approx(-0.5) and t(1.25) == pytest.approx(1.0)
+    assert E.lerp_std(1.0, 5.0, 1.0) == 5.0 and E.lerp_std(-1.0, 1.0, 0.5) == 0.0
+
+
+def test_sampled_function_is_the_references_literal_piecewise_constant():
+    ctx = _ctx()
+    sq = ctx.tables["sq"]
+    assert len(sq.range) == 9 and sq.range[4] == 3.0      # c x^2 at x = 1
+    # context.cc:262-264: i and j are the same interval number -> the left sample of the interval
+    assert sq(1.0) == 3.0 and sq(1.2) == 3.0 and sq(1.249) == 3.0 and sq(1.25) == pytest.approx(3 * 1.25 ** 2)
+    assert sq(2.0) == 12.0
+    assert sq(-4.0) == 0.0                                # clamp = max(domain[0], pos)
+    assert sq(7.0) == 12.0                                # past the table: last sample (the reference reads out of bounds)
+    strict = ctx.tables["strict"]
+    assert strict(0.5) == 1.5
+    with pytest.raises(E.ExprError, match="out of bounds"):
+        strict(1.5)
+
+
+def test_c_vm_and_python_evaluator_agree():
+    ctx = _ctx()
+    sym = E.Symbols(2, ["u"])
+    text = "tab(u) + 2*sq(u + position_x) - strict(0.25*abs(u))"
+    code, consts = E.compile_expr(text, sym, ctx)
+    ast = E.resolve(E.Parser(text).parse(), ctx)
+    rows = np.zeros((50, sym.nslots))
+    rng = np.random.default_rng(5)
+    rows[:, sym.value_slot(0)] = rng.uniform(-1.5, 2.5, 50)
+    rows[:, E.SLOT_POS] = rng.uniform(0, 1, 50)
+    got = ORC.eval_program(code, consts, rows)
+    for k in range(50):
+        want = E.py_eval(ast, {"u": rows[k, sym.value_slot(0)], "position_x": rows[k, E.SLOT_POS]})
+        assert got[k] == want
+    # out of bounds under `error`: NaN in the VM
+    code, consts = E.compile_expr("strict(u)", sym, ctx)
+    rows[0, sym.value_slot(0)] = 2.0
+    assert math.isnan(ORC.eval_program(code, consts, rows[:1])[0])
+
+
+def test_generated_source_matches_the_oracle():
+    """Model::cuda_source with the tables as constant arrays, compiled as host C++"""
+    case = K.CASES["tables"]
+    om = case.oracle()
+    cfg, model, grid = K.product_objects(case)
+    src = model.cuda_source().split("// Argument blocks shared")[0]
+    assert "dc_tab_rate_" in src and "dc_tab_profile_" in src
+    rng = np.random.default_rng(2)
+    pts = [(float(rng.uniform(0.0, 2.2)), float(rng.uniform(-0.2, 1.2))) for _ in range(40)]
+    body = ["#include <cmath>\n#include <cstdio>\nusing namespace std;\n#define __device__\n#define __host__\n"
+            "#define __forceinline__ inline\n#define __noinline__\n", src,
+            "int main(){ DcCtx c{}; double u[4], g[4][DC_DIM] = {}, sc[4], jm[1][1]; c.in_volume = 1;\n"]
+    for u, x in pts:
+        body.append(f"u[0]={u!r}; c.pos[0]={x!r}; DcComp<0>::scalar(c,u,g,0.0,1.0,sc); printf(\"%.17g\\n\", sc[0]);"
+                    f" DcComp<0>::jac_mass(c,u,g,0.0,1.0,jm); printf(\"%.17g\\n\", jm[0][0]);\n")
+    body.append("return 0; }\n")
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "m.cpp"), "w").write("".join(body))
+        subprocess.check_call(["g++", "-std=c++17", "-O0", "-o", os.path.join(td, "m"), os.path.join(td, "m.cpp")])
+        out = [float(v) for v in subprocess.check_output([os.path.join(td, "m")], text=True).split()]
+    progs = {k: om.progs[prog] for k, ti, tj, tk, prog in om.terms if k in (ORC.K_REACTION, ORC.K_REACTION_JAC)}
+    for n, (u, x) in enumerate(pts):
+        ctx = np.zeros((1, om.sym.nslots))
+        ctx[0, E.SLOT_INVOL] = 1
+        ctx[0, E.SLOT_POS] = x
+        ctx[0, om.sym.value_slot(0)] = u
+        r = ORC.eval_program(*progs[ORC.K_REACTION], ctx)[0]
+        j = ORC.eval_program(*progs[ORC.K_REACTION_JAC], ctx)[0]
+        assert out[2 * n] == pytest.approx(-r, rel=1e-14, abs=1e-300)
+        assert out[2 * n + 1] == pytest.approx(-j, rel=1e-14, abs=1e-300)
+
+
+def test_product_host_evaluation_and_errors():
+    import dune_copasi_b200 as D
+    case = K.CASES["tables"]
+    om = case.oracle()
+    cfg, model, grid = K.product_objects(case)
+    # initial values and the constant-folded diffusion coefficient go through the host evaluator
+    u0 = grid.interpolate(model, 0.0)
+    assert np.allclose(u0, om.initial(0.0), rtol=0, atol=1e-15)
+    model.precompile()                        # NVRTC accepts the generated tables (sm_100a, no GPU needed)
+    bad = case.ini_with(**{"parser_context.rate.domain": "0 1 0.5 2 3"})
+    with pytest.raises(D.DcbError, match="must be sorted"):
+        D.Model(D.Config(bad), 2)
+    bad = case.ini_with(**{"parser_context.bump.interpolation.intervals": "0"})
+    with pytest.raises(D.DcbError, match="at least one interval"):
+        D.Model(D.Config(bad), 2)
+    bad = case.ini_with(**{"parser_context.img.type": "tiff", "parser_context.img.path": "x.tif"})
+    with pytest.raises(D.DcbError, match="not supported"):
+        D.Model(D.Config(bad), 2)

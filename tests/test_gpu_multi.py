@@ -21,7 +21,9 @@ OVERLAP = "model.time_step_operator.linear_solver.b200.overlap_halo=true"
 @pytest.mark.parametrize("name,mf,extra", [("grayscott3d", "1", ""), ("grayscott3d", "0", ""), ("cell3d", "1", ""),
                                            ("two_disks", "0", ""), ("gauss3d", "1", ""), ("advection3d", "0", ""),
                                            ("grayscott3d", "1", OVERLAP), ("grayscott3d_q1", "1", ""),
-                                           ("grayscott3d_q1", "0", ""), ("gauss3d_q1", "1", OVERLAP)])
+                                           ("grayscott3d_q1", "0", ""), ("gauss3d_q1", "1", OVERLAP),
+                                           ("cell10_nested", "1", ""),   # unstructured tets, RCB partition, general halo plan
+                                           ("tables", "1", "")])
 def test_two_rank_time_stepping_matches_serial_oracle(name, mf, extra):
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
@@ -65,6 +67,7 @@ def _run(world, name, mf, extra, port, env=None):
                                            ("grayscott3d_aniso", "0", ""),      # assembled (CSR + SpMV)
                                            ("cell3d", "1", ""),                 # three compartments, general halo plan
                                            ("grayscott3d_q1", "1", ""),
+                                           ("cell10_nested", "1", ""),          # BASELINE configs[4] in miniature: RCB over unstructured tets
                                            ("grayscott3d_wide", "1", TILE)])    # tile drivers + fused BiCGSTAB
 def test_many_rank_time_stepping_matches_serial_oracle(world, name, mf, extra):
     """3 and 4 ranks cut the lattices of the suite into slabs of unequal thickness (down to one owned plane

@@ -182,6 +182,26 @@ def test_gauss_kat_on_cubes():
     assert u.max() <= 1.0 / (4 * np.pi * Dc) and u.min() >= -1e-2
 
 
+@pytest.mark.parametrize("name", ["gauss2d_q1", "gauss3d_q1", "poisson_q1", "mitchell_schaefer_q1"])
+def test_reduce_matches_oracle(name):
+    """[model.reduce] functionals on cube cells (3-point Gauss rule per axis, kernels/reduce.cuh
+    dc_reduce_q1_kernel) against the oracle's Q1 branch of reduce (oracle/core.py)."""
+    import dune_copasi_b200 as D
+    case, om, cfg, model, grid, op = make(name)
+    red = D.Reducer(op, cfg)
+    assert red.keys
+    for seed, t in ((None, case.t0), (41, case.t0 + 0.37)):
+        x = om.initial(t) if seed is None else K.rand_state(om.ndofs, seed, -0.5, 1.5)
+        ref, ref_status = K.ORC.reduce(om, x, t)
+        got = red.apply(t, x, raise_on_error=False)
+        assert list(got) == list(ref)
+        for key in ref:
+            scale = max(abs(ref[key]), 1e-300)
+            # (+ 1e-25: the gradient energy of a constant field is rounding noise on cubes, exactly 0 on simplices)
+            assert abs(got[key] - ref[key]) <= 1e-11 * scale + 1e-25, (key, got[key], ref[key])
+            assert red.status[key] == ref_status[key], (key, red.status[key], ref_status[key])
+
+
 def test_unsupported_configurations_fail_loudly():
     import dune_copasi_b200 as D
     case = K.Q1_CASES["grayscott2d_q1"]
