@@ -216,6 +216,7 @@ std::shared_ptr<const Table> find_table(const std::string& key) {
 double apply1(const std::string& f, double a, bool* ok) {
   *ok = true;
   if (auto t = find_table(f)) {
+    if (t->kind == 2) fail("function '", t->name, "' expects 2 arguments");
     bool oob = false;
     double v = t->eval(a, &oob);
     if (oob) fail("interpolation of function '", t->name, "' is out of bounds: ", a, " not in [", t->domain[0], ", ", t->domain[1], "]");
@@ -247,6 +248,9 @@ double apply1(const std::string& f, double a, bool* ok) {
 
 double apply2(const std::string& f, double a, double b, bool* ok) {
   *ok = true;
+  if (auto t = find_table(f)) {
+    if (t->kind == 2) return t->img(a, b);
+  }
   if (f == "min") return a < b ? a : b;
   if (f == "max") return a > b ? a : b;
   if (f == "atan2") return std::atan2(a, b);
@@ -324,6 +328,12 @@ NodeP resolve_rec(const NodeP& a, const ParserContext& ctx, int depth) {
       return resolve_rec(subst(parse_expr(fn.body), env), ctx, depth + 1);
     }
     auto tb = ctx.tables.find(n->name);
+    if (tb != ctx.tables.end() && tb->second->kind == 2) {
+      if (n->kids.size() != 2) fail("function '", n->name, "' expects 2 arguments, got ", n->kids.size());
+      n->name = tb->second->key;
+      if (n->kids[0]->op == Op::Num && n->kids[1]->op == Op::Num) return mk_num(tb->second->img(n->kids[0]->num, n->kids[1]->num));
+      return n;
+    }
     if (tb != ctx.tables.end()) {
       if (n->kids.size() != 1) fail("function '", n->name, "' expects 1 argument, got ", n->kids.size());
       n->name = tb->second->key;
@@ -425,9 +435,14 @@ ParserContext ParserContext::from_config(const PTree& pc) {
       if (t->domain.size() < 2 || t->domain.size() != t->range.size())
         fail("parser_context.", name, ": interpolation range and domain must have at least two points and be the same size");
       ctx.tables[name] = t;
+    } else if (type == "tiff") {
+      auto t = std::make_shared<Table>();
+      t->kind = 2;
+      t->name = name;
+      t->img = read_tiff(s.get("path", std::string()));
+      ctx.tables[name] = t;
     } else if (!type.empty()) {
-      // tiff needs libtiff and image files (the reference's test images are git-LFS pointers), random_field
-      // needs parafields: both only feed initial conditions, outside the hot path
+      // random_field needs parafields (absent from the image); it only feeds initial conditions
       fail("parser_context.", name, ": type '", type, "' is not supported by this build");
     }
   }
@@ -471,6 +486,11 @@ ParserContext ParserContext::from_config(const PTree& pc) {
     mix(&t->kind, sizeof t->kind); mix(&t->clamp, sizeof t->clamp);
     mix(t->domain.data(), t->domain.size() * sizeof(double));
     mix(t->range.data(), t->range.size() * sizeof(double));
+    if (t->kind == 2) {
+      const float geo[4] = {t->img.x_res, t->img.y_res, t->img.x_off, t->img.y_off};
+      mix(&t->img.rows, sizeof t->img.rows); mix(&t->img.cols, sizeof t->img.cols); mix(geo, sizeof geo);
+      mix(t->img.values.data(), t->img.values.size() * sizeof(double));
+    }
     char buf[32];
     snprintf(buf, sizeof buf, "%016llx", h);
     std::string id;
@@ -499,6 +519,21 @@ std::string ParserContext::cuda_tables() const {
       for (size_t i = 0; i < v.size(); ++i) o << (i ? ", " : "") << num_lit(v[i]);
       o << "};\n";
     };
+    if (t.kind == 2) {
+      if (t.img.values.size() > Table::kMaxDevicePixels) continue;   // host-only (to_cuda refuses to reference it)
+      array("r", t.img.values);
+      auto flit = [](float v) { char b[48]; snprintf(b, sizeof b, "%.9gf", (double)v); std::string s = b; if (s.find_first_of(".e") == std::string::npos) s.insert(s.size() - 1, ".0"); return s; };
+      o << "__device__ __noinline__ double " << t.key << "(double x, double y) {\n"
+        << "  const float fx = " << flit(t.img.x_res) << " * ((float)x - " << flit(t.img.x_off) << "), fy = " << flit(t.img.y_res)
+        << " * ((float)y - " << flit(t.img.y_off) << ");\n"
+        << "  unsigned px = fx <= 0.0f ? 0u : (fx >= 4294967040.0f ? 4294967295u : (unsigned)fx);\n"
+        << "  const unsigned py = fy <= 0.0f ? 0u : (fy >= 4294967040.0f ? 4294967295u : (unsigned)fy);\n"
+        << "  unsigned line = " << t.img.rows << "u - py - 1u;\n"
+        << "  if (px > " << t.img.cols - 1 << "u) px = " << t.img.cols - 1 << "u;\n"
+        << "  if (line > " << t.img.rows - 1 << "u) line = " << t.img.rows - 1 << "u;\n"
+        << "  return " << t.key << "_r[(size_t)line * " << t.img.cols << " + px];\n}\n";
+      continue;
+    }
     array("r", t.range);
     if (t.kind == 0) {
       array("d", t.domain);
@@ -647,6 +682,13 @@ std::string to_cuda(const NodeP& a, const std::function<std::string(const std::s
           {"min", "dc_min"}, {"max", "dc_max"}, {"atan2", "atan2"}, {"pow", "pow"}};
       if (a->kids.size() == 1 && one.count(f)) return one.at(f) + "(" + rec(a->kids[0]) + ")";
       if (a->kids.size() == 1 && f.rfind("dc_tab_", 0) == 0) return f + "(" + rec(a->kids[0]) + ")";
+      if (a->kids.size() == 2 && f.rfind("dc_tab_", 0) == 0) {
+        auto t = find_table(f);
+        if (t && t->img.values.size() > Table::kMaxDevicePixels)
+          fail("image function '", t->name, "' (", t->img.rows, " x ", t->img.cols, " pixels) is too large for device code: "
+               "use it in initial / constrain / compartment expressions, or an image of at most ", Table::kMaxDevicePixels, " pixels");
+        return f + "(" + rec(a->kids[0]) + ", " + rec(a->kids[1]) + ")";
+      }
       if (a->kids.size() >= 2 && two.count(f)) {
         std::string r = rec(a->kids[0]);
         for (size_t i = 1; i < a->kids.size(); ++i) r = two.at(f) + "(" + r + ", " + rec(a->kids[i]) + ")";

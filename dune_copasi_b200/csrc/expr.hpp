@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "ptree.hpp"
+#include "tiff.hpp"
 
 namespace dcb {
 
@@ -40,7 +41,12 @@ struct Node {
 //           std::clamp(domain[0], pos, domain[1]) = max(domain[0], pos) (arguments in that order).  Where the
 //           reference would read past the table (pos > domain[1] under `clamp`) the last sample is used;
 //           `error` yields NaN on the device (the reference throws) and throws on the host.
+//   kind 2  `type = tiff` (:66-71): a grayscale image as a function of (x, y), nearest pixel (tiff.hpp).  Available to
+//           every host-evaluated expression (initial values, constraints, compartments); device code embeds images
+//           of up to kMaxDevicePixels pixels as constant arrays, larger ones fail loudly when a kernel needs them.
 struct Table {
+  static constexpr size_t kMaxDevicePixels = 1u << 18;
+  TiffImage img;                       // kind 2
   int kind = 0;
   std::vector<double> domain, range;   // kind 1: domain = {d0, d1}, range = the intervals + 1 samples
   bool clamp = false;

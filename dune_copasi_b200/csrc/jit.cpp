@@ -28,9 +28,9 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
   for (int c = 0; c < model.ncomp(); ++c) {
     if (model.comp_nspec[c] == 0) continue;
     if (all || group == JitGroup::Element) {
-      o << "extern \"C\" __global__ void __launch_bounds__(128) dc_k_residual_volume_" << c
+      o << "extern \"C\" __global__ void __launch_bounds__(128, DC_ELEM_MINB) dc_k_residual_volume_" << c
         << "(DcVolArgs a) { dc_residual_volume<" << c << ">(a); }\n";
-      o << "extern \"C\" __global__ void __launch_bounds__(128) dc_k_jacobian_apply_volume_" << c
+      o << "extern \"C\" __global__ void __launch_bounds__(128, DC_ELEM_MINB) dc_k_jacobian_apply_volume_" << c
         << "(DcVolArgs a) { dc_jacobian_apply_volume<" << c << ">(a); }\n";
       o << "extern \"C\" __global__ void __launch_bounds__(128) dc_k_bdiag_volume_" << c
         << "(DcVolArgs a) { dc_jacobian_volume<" << c << ", 1>(a); }\n";
@@ -137,6 +137,9 @@ std::string jit_defines(const Model& model) {
   // measured 16 % faster than 4 on B200 despite the spills (profiles/r01_csr_fill_128_ncu.txt)
   int cminb = acfg.get("csr_min_blocks", 8);
   if (cminb < 1 || cminb > 16) fail("model.assembly.b200.csr_min_blocks out of range");
+  // element-per-thread residual / apply (128 threads): resident CTAs per SM the compiler has to leave room for
+  int eminb = acfg.get("elem_min_blocks", 4);   // 4 x 128 threads: 128 registers, measured -2 % on the cell model against 164 registers x 3
+  if (eminb < 1 || eminb > 16) fail("model.assembly.b200.elem_min_blocks out of range");
   // tile-marching drivers: 32 x (tile_w * tile_r) cells per CTA in 3-D (tile_w warps, tile_r cell rows each)
   int ns_max = 1;
   for (int c = 0; c < model.ncomp(); ++c) ns_max = std::max(ns_max, model.comp_nspec[c]);
@@ -145,7 +148,7 @@ std::string jit_defines(const Model& model) {
   if (tw < 1 || tw > 32 || tr < 1 || tr > 16) fail("model.assembly.b200.tile_w / tile_r out of range");
   if (tminb < 1 || tminb > 16) fail("model.assembly.b200.tile_min_blocks out of range");
   return "#define DC_TILE_W " + std::to_string(tw) + "\n#define DC_TILE_R " + std::to_string(tr) +
-         "\n#define DC_TILE_MINB " + std::to_string(tminb) + "\n#define DC_CSR_MINB " + std::to_string(cminb) + "\n#define DC_PATCH_THREADS " + std::to_string(th) + "\n#define DC_PATCH_MINB " + std::to_string(minb) +
+         "\n#define DC_TILE_MINB " + std::to_string(tminb) + "\n#define DC_CSR_MINB " + std::to_string(cminb) + "\n#define DC_ELEM_MINB " + std::to_string(eminb) + "\n#define DC_PATCH_THREADS " + std::to_string(th) + "\n#define DC_PATCH_MINB " + std::to_string(minb) +
          "\n#define DC_STRUCT_THREADS " + std::to_string(sth) + "\n#define DC_STRUCT_MINB " + std::to_string(sminb) + "\n";
 }
 

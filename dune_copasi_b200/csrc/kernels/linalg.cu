@@ -282,6 +282,23 @@ __global__ void __launch_bounds__(kThreads) k_bicg_final(int64_t n, Ranges own,
   grid_reduce<2>(acc, partials, counter, out, L);
 }
 
+// One step of modified Gram-Schmidt in a single pass: w -= (*coef) vprev (skipped when coef is null), then
+// out[0] = <vnext, w> over the owned entries (vnext null: <w, w>).  The unfused pair (k_axpy_dev, k_dot) reads w twice.
+__global__ void __launch_bounds__(kThreads) k_mgs_step(int64_t n, Ranges own, const double* __restrict__ coef,
+                                                       const double* __restrict__ vprev, double* __restrict__ w,
+                                                       const double* __restrict__ vnext, double* partials,
+                                                       unsigned* counter, double* out, Link L) {
+  double acc[1] = {0.0};
+  const bool single = own.n == 1 && own.b[0] == 0 && own.e[0] == n;
+  const double a = coef ? *coef : 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    double wi = w[i];
+    if (coef) { wi -= a * vprev[i]; w[i] = wi; }
+    if (single || in_ranges(own, i)) acc[0] += (vnext ? vnext[i] : wi) * wi;
+  }
+  grid_reduce<1>(acc, partials, counter, out, L);
+}
+
 __global__ void __launch_bounds__(kThreads) k_xpby(int64_t n, double* __restrict__ p,
                                                    const double* __restrict__ q, double beta) {
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
@@ -650,6 +667,11 @@ void bicg_final(int64_t n, const Ranges& own, const double* rho, const double* h
                 const double* y2, const double* xin, double* xout, double* t, double* r, const double* rt,
                 double* out, const ReduceWorkspace& w, cudaStream_t s, const Link& L) {
   k_bicg_final<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, rho, hptr, trtt, y1, y2, xin, xout, t, r, rt, w.partials, w.counter, out, L);
+  check_launch();
+}
+void mgs_step(int64_t n, const Ranges& own, const double* coef, const double* vprev, double* w, const double* vnext,
+              double* out, const ReduceWorkspace& ws, cudaStream_t s, const Link& L) {
+  k_mgs_step<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, coef, vprev, w, vnext, ws.partials, ws.counter, out, L);
   check_launch();
 }
 void xpby(int64_t n, double* p, const double* q, double beta, cudaStream_t s) {

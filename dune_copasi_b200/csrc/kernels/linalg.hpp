@@ -73,6 +73,10 @@ void bicg_r_prec(int64_t n, const Ranges& own, const double* rho, const double* 
 void bicg_final(int64_t n, const Ranges& own, const double* rho, const double* hptr, const double* trtt, const double* y1,
                 const double* y2, const double* xin, double* xout, double* t, double* r, const double* rt,
                 double* out, const ReduceWorkspace& w, cudaStream_t s, const Link& L = Link());
+// GMRES, one modified Gram-Schmidt step per pass: w -= (*coef) vprev (coef null: skipped), out[0] = <vnext, w>
+// over `own` (vnext null: <w, w>); coef is the device-resident result of the previous step
+void mgs_step(int64_t n, const Ranges& own, const double* coef, const double* vprev, double* w, const double* vnext,
+              double* out, const ReduceWorkspace& ws, cudaStream_t s, const Link& L = Link());
 // GMRES (modified Gram-Schmidt) with device-resident coefficients:
 // y += sign * (*coef) * x
 void axpy_dev(int64_t n, const double* coef, double sign, const double* x, double* y, cudaStream_t s);

@@ -606,21 +606,22 @@ SolveResult LinearSolver::apply_krylov(double* b, double* x, double rel_tol) {
       for (i = 0; i < m && j <= max_iterations && !res.converged; ++i, ++j) {
         apply_operator(V(i), V(i + 1));
         precondition(V(i + 1), w);
-        for (int k = 0; k < i + 1; ++k) {
+        // modified Gram-Schmidt, dune-istl's order (h_k = <v_k, w>; w -= h_k v_k), one pass per basis vector:
+        // step k subtracts the projection found by step k - 1 and forms the next product on the updated w;
+        // the last step closes with <w, w>.  Sums are all-reduced by the kernels' last block (peer links) and
+        // mirrored into hscal_.
+        const bool rlink = !comm_ || comm_->reduce_links_ready();
+        for (int k = 0; k <= i + 1; ++k) {
           DeviceOperator::ProfScope ps(op_.get(), "blas1");
-          la::dot(own, V(k), w, scal_.p + k, ws_, s);
-          if (comm_) comm_->allreduce_sum(scal_.p + k, 1, s);
-          la::axpy_dev(n, scal_.p + k, -1.0, V(k), w, s);
-          L += 2;
+          la::Link lk;
+          if (comm_ && rlink) comm_->link_reduce(&lk.peer);
+          if (rlink) lk.host_out = hscal_.p + k;
+          la::mgs_step(n, own, k ? scal_.p + k - 1 : nullptr, k ? V(k - 1) : nullptr, w, k <= i ? V(k) : nullptr, scal_.p + k, ws_, s, lk);
+          if (comm_ && !rlink) comm_->allreduce_sum(scal_.p + k, 1, s);
+          L++;
         }
-        {
-          DeviceOperator::ProfScope ps(op_.get(), "blas1");
-          la::dot(own, w, w, scal_.p + i + 1, ws_, s);
-          if (comm_) comm_->allreduce_sum(scal_.p + i + 1, 1, s);
-          la::normalize_dev(n, w, scal_.p + i + 1, V(i + 1), s);
-          L += 2;
-        }
-        DCB_CUDA(cudaMemcpyAsync(hscal_.p, scal_.p, sizeof(double) * (i + 2), cudaMemcpyDeviceToHost, s));
+        { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::normalize_dev(n, w, scal_.p + i + 1, V(i + 1), s); L++; }
+        if (!rlink) DCB_CUDA(cudaMemcpyAsync(hscal_.p, scal_.p, sizeof(double) * (i + 2), cudaMemcpyDeviceToHost, s));
         DCB_CUDA(cudaStreamSynchronize(s));
         for (int k = 0; k < i + 1; ++k) Hh(k, i) = hscal_.p[k];
         double hn = std::sqrt(hscal_.p[i + 1]);

@@ -40,6 +40,7 @@ OP_LT, OP_GT, OP_LE, OP_GE, OP_EQ, OP_NE = 8, 9, 10, 11, 12, 13
 OP_AND, OP_OR, OP_NOT, OP_SEL = 14, 15, 16, 17
 OP_F1, OP_F2, OP_MOD = 18, 19, 20
 OP_TAB = 21          # tabulated context function: arg = offset of its record in the constants
+OP_TAB2 = 22         # image function of two arguments (tiff): arg = offset of its record
 
 F1 = {"sqrt": 0, "exp": 1, "log": 2, "sin": 3, "cos": 4, "tan": 5, "abs": 6, "floor": 7,
       "ceil": 8, "tanh": 9, "sinh": 10, "cosh": 11, "asin": 12, "acos": 13, "atan": 14,
@@ -155,6 +156,9 @@ class Context:
                 head, body = sub["expression"].split(":", 1)
                 args = [a.strip() for a in head.split(",") if a.strip()]
                 ctx.functions[name] = (args, body.strip())
+            elif typ == "tiff":
+                from . import tiff as TIFF
+                ctx.tables[name] = TIFF.read(str(sub["path"]))
             elif typ == "interpolation":
                 dom = [float(v) for v in str(sub["domain"]).split()]
                 rng = [float(v) for v in str(sub["range"]).split()]
@@ -317,6 +321,8 @@ def _subst(ast, env):
         return ("call", ast[1], [_subst(a, env) for a in ast[2]])
     if k == "tab":
         return ("tab", ast[1], _subst(ast[2], env))
+    if k == "tab2":
+        return ("tab2", ast[1], _subst(ast[2], env), _subst(ast[3], env))
     raise AssertionError(k)
 
 
@@ -344,6 +350,10 @@ def resolve(ast, ctx: Context, depth=0):
         return ("sel",) + tuple(resolve(a, ctx, depth) for a in ast[1:])
     if k == "call":
         name, args = ast[1], [resolve(a, ctx, depth) for a in ast[2]]
+        if name in ctx.tables and not isinstance(ctx.tables[name], Table):      # image: two arguments
+            if len(args) != 2:
+                raise ExprError(f"function {name} expects 2 arguments, got {len(args)}")
+            return ("tab2", ctx.tables[name], args[0], args[1])
         if name in ctx.tables:
             if len(args) != 1:
                 raise ExprError(f"function {name} expects 1 argument, got {len(args)}")
@@ -360,6 +370,8 @@ def resolve(ast, ctx: Context, depth=0):
         return ("call", name, args)
     if k == "tab":
         return ("tab", ast[1], resolve(ast[2], ctx, depth))
+    if k == "tab2":
+        return ("tab2", ast[1], resolve(ast[2], ctx, depth), resolve(ast[3], ctx, depth))
     raise AssertionError(k)
 
 
@@ -429,6 +441,11 @@ def emit(ast, sym: Symbols, code: list, consts: list):
         emit(ast[2], sym, code, consts)
         code += [OP_TAB, len(consts)]
         consts.extend(ast[1].record())
+    elif k == "tab2":
+        emit(ast[2], sym, code, consts)
+        emit(ast[3], sym, code, consts)
+        code += [OP_TAB2, len(consts)]
+        consts.extend(ast[1].record())
     else:
         raise AssertionError(k)
 
@@ -485,4 +502,6 @@ def py_eval(ast, env: dict):
         return getattr(math, n)(args[0])
     if k == "tab":
         return ast[1](py_eval(ast[2], env))
+    if k == "tab2":
+        return ast[1](py_eval(ast[2], env), py_eval(ast[3], env))
     raise AssertionError(k)

@@ -138,6 +138,20 @@ static double tab_eval(const double* rec, double x) {
   return rng[k];
 }
 
+/* image function (type = tiff); rec = 2, rows, cols, x_res, y_res, x_off, y_off, values[rows][cols] (oracle/tiff.py).
+   TIFFGrayscale::operator(), src/dune/copasi/common/tiff_grayscale.cc:91-105: float arithmetic, uint32 truncation
+   (the row index wraps as in the reference), clamped to the image; negative offsets (undefined in the reference) -> 0 */
+static uint32_t tiff_pixel(float v) { return v <= 0.0f ? 0u : (v >= 4294967040.0f ? 4294967295u : (uint32_t)v); }
+static double tab2_eval(const double* rec, double x, double y) {
+  const uint32_t rows = (uint32_t)rec[1], cols = (uint32_t)rec[2];
+  const float x_res = (float)rec[3], y_res = (float)rec[4], x_off = (float)rec[5], y_off = (float)rec[6];
+  uint32_t px = tiff_pixel(x_res * ((float)x - x_off));
+  uint32_t line = rows - tiff_pixel(y_res * ((float)y - y_off)) - 1u;
+  if (px > cols - 1) px = cols - 1;
+  if (line > rows - 1) line = rows - 1;
+  return rec[7 + (size_t)line * cols + px];
+}
+
 double orc_eval(const int32_t* code, int n, const double* consts, const double* ctx) {
   double st[64];
   int sp = 0;
@@ -166,6 +180,7 @@ double orc_eval(const int32_t* code, int n, const double* consts, const double* 
       case 19: sp--; st[sp - 1] = f2(arg, st[sp - 1], st[sp]); break;
       case 20: sp--; st[sp - 1] = fmod(st[sp - 1], st[sp]); break;
       case 21: st[sp - 1] = tab_eval(consts + arg, st[sp - 1]); break;
+      case 22: sp--; st[sp - 1] = tab2_eval(consts + arg, st[sp - 1], st[sp]); break;
     }
   }
   return st[0];

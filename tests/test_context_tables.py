@@ -131,6 +131,88 @@ def test_product_host_evaluation_and_errors():
     bad = case.ini_with(**{"parser_context.bump.interpolation.intervals": "0"})
     with pytest.raises(D.DcbError, match="at least one interval"):
         D.Model(D.Config(bad), 2)
-    bad = case.ini_with(**{"parser_context.img.type": "tiff", "parser_context.img.path": "x.tif"})
+    bad = case.ini_with(**{"parser_context.img.type": "tiff", "parser_context.img.path": "no_such_file.tif"})
+    with pytest.raises(D.DcbError, match="does not exists"):
+        D.Model(D.Config(bad), 2)
+    bad = case.ini_with(**{"parser_context.f.type": "random_field"})
     with pytest.raises(D.DcbError, match="not supported"):
         D.Model(D.Config(bad), 2)
+
+
+TIFF_INI = """
+[compartments.domain]
+type = expression
+expression = 1
+[parser_context.img]
+type = tiff
+path = {a}
+[parser_context.mask]
+type = tiff
+path = {b}
+[model.scalar_field.u]
+compartment = domain
+initial.expression = img(position_x, position_y) + 0.5*mask(position_x + 0.25, position_y)
+storage.expression = 1
+cross_diffusion.u.expression = 0.01
+reaction.expression = -u*mask(position_x, position_y)
+reaction.jacobian.u.expression = -mask(position_x, position_y)
+[model.time_step_operator]
+time_step_max = 0.1
+time_end = 10
+""" + K.SOLVER
+
+
+def test_tiff_images_as_context_functions(tmp_path):
+    """`type = tiff` (context.cc:66-71, tiff_grayscale.cc:91-105): the product's reader (csrc/tiff.cpp) and the oracle's
+    (oracle/tiff.py) agree on every layout they read, host evaluation and the generated device code reproduce the
+    oracle's pixel lookup -- inside the image, on its edges and outside (clamped / wrapped as in the reference)."""
+    import dune_copasi_b200 as D
+    from oracle import tiff as TIFF
+    rng = np.random.default_rng(9)
+    a, b = str(tmp_path / "a.tif"), str(tmp_path / "b.tif")
+    pa = rng.integers(0, 256, (12, 20))
+    pb = rng.integers(0, 65536, (33, 17))
+    TIFF.write(a, pa, bits=8, x_res=(20, 1), y_res=(12, 1))                                   # unit square, MinIsBlack
+    TIFF.write(b, pb, bits=16, x_res=(34, 3), y_res=(33, 2), x_off=(1, 4), y_off=(1, 8), photometric=0, packbits=True,
+               big_endian=True, rows_per_strip=5)                                             # offsets, MinIsWhite, strips
+    ia, ib = TIFF.read(a), TIFF.read(b)
+    assert np.array_equal(ia.values, pa / 256.0) and np.array_equal(ib.values, (65536.0 - pb) / 65536.0)
+    assert ia(0.0, 0.0) == pa[11, 0] / 256.0 and ia(0.999, 0.999) == pa[0, 19] / 256.0       # y runs upwards from the last line
+    assert ia(5.0, 0.5) == pa[5, 19] / 256.0 and ia(0.5, 7.0) == pa[11, 10] / 256.0            # right of / above: clamp, wrap
+    text = TIFF_INI.format(a=a, b=b)
+    case = K.Case("tiff", text, 2, lambda: K.OMESH.structured(2, [9, 7]), dt=0.05, structured=([9, 7], [0, 0], [1, 1]))
+    om = case.oracle()
+    cfg, model, grid = K.product_objects(case)
+    assert np.array_equal(grid.interpolate(model, 0.0), om.initial(0.0))                      # both readers, both evaluators
+    src = model.cuda_source().split("// Argument blocks shared")[0]
+    pts = [(float(rng.uniform(0.1, 1.0)), float(rng.uniform(-0.3, 1.4)), float(rng.uniform(-0.3, 1.4))) for _ in range(60)]
+    body = ["#include <cmath>\n#include <cstdio>\nusing namespace std;\n#define __device__\n#define __host__\n"
+            "#define __forceinline__ inline\n#define __noinline__\n", src,
+            "int main(){ DcCtx c{}; double u[4], g[4][DC_DIM] = {}, sc[4]; c.in_volume = 1;\n"]
+    for u, x, y in pts:
+        body.append(f"u[0]={u!r}; c.pos[0]={x!r}; c.pos[1]={y!r}; DcComp<0>::scalar(c,u,g,0.0,1.0,sc); printf(\"%.17g\\n\", sc[0]);\n")
+    body.append("return 0; }\n")
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "m.cpp"), "w").write("".join(body))
+        subprocess.check_call(["g++", "-std=c++17", "-O0", "-o", os.path.join(td, "m"), os.path.join(td, "m.cpp")])
+        out = [float(v) for v in subprocess.check_output([os.path.join(td, "m")], text=True).split()]
+    prog = {k: om.progs[p] for k, ti, tj, tk, p in om.terms if k == ORC.K_REACTION}[ORC.K_REACTION]
+    for n, (u, x, y) in enumerate(pts):
+        ctx = np.zeros((1, om.sym.nslots))
+        ctx[0, E.SLOT_INVOL] = 1
+        ctx[0, E.SLOT_POS], ctx[0, E.SLOT_POS + 1] = x, y
+        ctx[0, om.sym.value_slot(0)] = u
+        assert out[n] == pytest.approx(-ORC.eval_program(*prog, ctx)[0], rel=1e-15, abs=1e-300)
+    model.precompile()
+    # formats the own reader does not cover fail loudly, as do images too large for device code
+    bad = str(tmp_path / "rgb.tif")
+    raw = bytearray(open(a, "rb").read())
+    raw[raw.index(b"\x06\x01\x03\x00") + 8] = 2            # PhotometricInterpretation = RGB
+    open(bad, "wb").write(bytes(raw))
+    with pytest.raises(D.DcbError, match="must be in grayscale"):
+        D.Model(D.Config(TIFF_INI.format(a=bad, b=b)), 2)
+    big = str(tmp_path / "big.tif")
+    TIFF.write(big, rng.integers(0, 256, (600, 600)), bits=8, x_res=(600, 1), y_res=(600, 1))
+    big_model = D.Model(D.Config(TIFF_INI.format(a=a, b=big)), 2)      # fine on the host ...
+    with pytest.raises(D.DcbError, match="too large for device code"):
+        big_model.cuda_source()                                        # ... refused where a kernel would need it

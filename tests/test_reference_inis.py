@@ -15,16 +15,25 @@ REF = "/root/reference"
 FILES = sorted(glob.glob(f"{REF}/test/*.ini") + glob.glob(f"{REF}/doc/docusaurus/static/ini/next/*.ini"))
 # test/CMakeLists.txt:70-80: the mitchell-schaefer system test replaces the random field by a function
 OVERRIDES = {"mitchell_schaefer.ini": {"parser_context.rng.type": "function", "parser_context.rng.expression": "x,y:0"}}
-# parser_context types outside the hot path (TIFF images): not built, must fail loudly
-UNSUPPORTED = {"time_snap.ini": "tiff"}
+# time_snap.ini reads two TIFF images whose files are git-LFS pointers in the reference tree: synthetic images of
+# the same names are written next to the test (the file's relative paths resolve against the working directory)
+TIFFS = {"time_snap.ini": ("data/tiff/A_initialConcentration.tif", "data/tiff/B_initialConcentration.tif")}
+UNSUPPORTED = {}
 
 pytestmark = pytest.mark.skipif(not FILES, reason="reference tree not mounted")
 
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
-def test_reference_ini(path):
+def test_reference_ini(path, tmp_path, monkeypatch):
     import dune_copasi_b200 as D
+    from oracle import tiff as TIFF
     name = os.path.basename(path)
+    if name in TIFFS:
+        monkeypatch.chdir(tmp_path)
+        rng = np.random.default_rng(3)
+        for k, rel in enumerate(TIFFS[name]):
+            os.makedirs(os.path.dirname(rel), exist_ok=True)
+            TIFF.write(rel, rng.integers(0, 65536, (40, 50)), bits=16, x_res=(50, 1), y_res=(40, 1), packbits=bool(k))
     text = open(path).read()
     keys = [k for k in ("gmsh_id", "sigma") if k in text]
     dim = 2
