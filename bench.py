@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import re
 import os
 import subprocess
 import sys
@@ -159,7 +160,9 @@ def timeline(torch, run, rank, path):
         return {"error": "no device records"}
     per, end = {}, None
     for e in dev:
-        name = e["name"].split("(")[0].split("<")[0]
+        name = e["name"]
+        m = re.search(r"\b(k_\w+|dc_k_\w+)", name)       # our kernels: the function name without namespaces / arguments
+        name = m.group(1) if m else name.split("(")[0].split("<")[0]
         if e["cat"] != "kernel":
             name = e["cat"] + ":" + name
         r = per.setdefault(name, {"n": 0, "busy_us": 0.0, "gap_before_us": 0.0})

@@ -341,13 +341,18 @@ __device__ __forceinline__ void dc_struct_per_cell(const DcStructArgs& a, CellFn
     double U[DC_NCORN][NS], Z[MODE == 1 ? DC_NCORN : 1][NS];
     const double* xb = a.x + d0;
     const double* zb = MODE == 1 ? a.z + d0 : nullptr;
+    const double* sb = (MODE == 1 && a.zscale) ? a.zscale + d0 : nullptr;
     const unsigned char* mb = a.cmask ? a.cmask + d0 : nullptr;
 #pragma unroll
     for (int m = 0; m < DC_NCORN; ++m) {
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         U[m][s] = xb[off(m) + s];
-        if (MODE == 1) Z[m][s] = (mb && mb[off(m) + s]) ? 0.0 : zb[off(m) + s];
+        if (MODE == 1) {
+          double z = zb[off(m) + s];
+          if (sb) z = (a.zrelax * sb[off(m) + s]) * z;   // the product k_bicg_p_prec / k_bicg_r_prec would have stored
+          Z[m][s] = (mb && mb[off(m) + s]) ? 0.0 : z;
+        }
       }
     }
     cell_fn(idx, U, Z, acc);

@@ -26,6 +26,11 @@ struct DcVolArgs {
   const int* vptr;             // [n+1]
   const int* vel;              // (element << 2 | local vertex index)
   int gather_maxlen;           // longest row of the compartment (shared-memory slots per species row)
+  // Packed connectivity of the compartment (3-D, model.assembly.b200.packed_conn): thread position t reads its four
+  // vertex ids and its four dof bases with two 16-byte loads instead of walking elem_ids[t] -> elems[e] -> vdof[v]
+  // -> x[dof] (four dependent loads; the kernels wait on `long_scoreboard` at 4 warps per scheduler)
+  const int* pverts;           // [n][4] vertex ids (null: walk the mesh arrays)
+  const int* pdofs;            // [n][4] dof of species 0 at those vertices
   // 16-byte gathers: the element kernels are bound by the L1 gather wavefronts, not by DRAM or the fp64 pipe
   const double* coords4;       // 3-D: [nv][4] coordinates padded to 32 bytes per vertex (null: use coords)
   int vec;                     // 1: x, z are 16-byte aligned and every dof block starts at an even offset (NS even)
@@ -67,6 +72,10 @@ struct DcStructArgs {
   double* r;
   double* bdiag;
   const unsigned char* cmask;
+  // Jacobian apply of the per-cell driver: direction = zrelax * zscale .* z when zscale != null (the Jacobi
+  // application of the Krylov solve formed while the corners are loaded, instead of a vector written and re-read)
+  const double* zscale;
+  double zrelax;
   const long long* rowptr;     // CSR of the Jacobian (Q1 fill only)
   const int* colidx;
   double* vals;

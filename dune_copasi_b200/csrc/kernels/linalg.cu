@@ -219,11 +219,12 @@ __global__ void __launch_bounds__(kThreads) k_bicg_p_prec(int64_t n, double* __r
     const double pi = first ? r[i] : r[i] + beta * (p[i] - omega * v[i]);
     p[i] = pi;
     if (L.zero_input) v[i] = 0.0;   // v is done: the operator application that follows accumulates into it
+    double out = pi;                // what the operator application reads: y, or p itself (it applies D^-1 on the fly)
     if (dinv) {
-      const double yi = relax * dinv[i] * pi;
-      y[i] = yi;
-      if (L.peer.push) peer::push_entry(L.peer.m, L.peer.h, par, i, yi);
+      out = relax * dinv[i] * pi;
+      y[i] = out;
     }
+    if (L.peer.push) peer::push_entry(L.peer.m, L.peer.h, par, i, out);
   }
   finish_push(counter, L);
 }
@@ -243,11 +244,12 @@ __global__ void __launch_bounds__(kThreads) k_bicg_r_prec(int64_t n, Ranges own,
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
     const double ri = r[i] - alpha * v[i];
     r[i] = ri;
+    double out = ri;
     if (dinv) {
-      const double yi = relax * dinv[i] * ri;
-      y2[i] = yi;
-      if (L.peer.push) peer::push_entry(L.peer.m, L.peer.h, par, i, yi);
+      out = relax * dinv[i] * ri;
+      y2[i] = out;
     }
+    if (L.peer.push) peer::push_entry(L.peer.m, L.peer.h, par, i, out);
     if (single || in_ranges(own, i)) acc[0] += ri * ri;
   }
   if (L.peer.push) __threadfence_system();
@@ -579,11 +581,11 @@ __global__ void __launch_bounds__(kThreads) k_bicg_final_fold(int64_t n, Ranges 
                                                               const double* __restrict__ trtt,
                                                               const double* __restrict__ dinv, double relax,
                                                               const double* __restrict__ p,
-                                                              const double* __restrict__ r,
+                                                              const double* r,
                                                               const double* __restrict__ xin, double* __restrict__ xout,
-                                                              const double* __restrict__ t, double* __restrict__ rout,
+                                                              double* t, double* rout,
                                                               const double* __restrict__ rt, double* partials,
-                                                              unsigned* counter, double* out) {
+                                                              unsigned* counter, double* out, Link L) {
   double acc[2] = {0.0, 0.0};
   const bool single = own.n == 1 && own.b[0] == 0 && own.e[0] == n;
   const double alpha = *rho_p / *hptr, omega = trtt[0] / trtt[1];
@@ -592,13 +594,14 @@ __global__ void __launch_bounds__(kThreads) k_bicg_final_fold(int64_t n, Ranges 
     const double y1 = di * p[i], y2 = di * rh;
     xout[i] = (xin[i] + alpha * y1) + omega * y2;
     const double ri = rh - omega * t[i];
-    rout[i] = ri;
+    rout[i] = ri;          // rout may be r itself
+    if (L.zero_input) t[i] = 0.0;
     if (single || in_ranges(own, i)) {
       acc[0] += ri * ri;
       acc[1] += rt[i] * ri;
     }
   }
-  grid_reduce<2>(acc, partials, counter, out);
+  grid_reduce<2>(acc, partials, counter, out, L);
 }
 
 inline void check_launch() { DCB_CUDA(cudaGetLastError()); }
@@ -737,7 +740,7 @@ __global__ void __launch_bounds__(128) k_sor_sweep(const int32_t* __restrict__ s
   for (int64_t k = dep_ptr[i]; k < dep_ptr[i + 1]; ++k) {
     const int j = dep_idx[k];
     if (backward ? j > i : j < i)
-      while (ld_acquire(done + j) != epoch) {}
+      while (ld_acquire(done + j) != epoch) __nanosleep(40);   // back off: spinning warps would crowd the L2 the chain runs through
   }
   double rhs = d[i], diag = 1.0;
   for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
@@ -867,9 +870,10 @@ void bicg_x_half(int64_t n, const double* rho, const double* hptr, const double*
 }
 void bicg_final_fold(int64_t n, const Ranges& own, const double* rho, const double* hptr, const double* trtt,
                      const double* dinv, double relax, const double* p, const double* r, const double* xin, double* xout,
-                     const double* t, double* rout, const double* rt, double* out, const ReduceWorkspace& w, cudaStream_t s) {
+                     double* t, double* rout, const double* rt, double* out, const ReduceWorkspace& w, cudaStream_t s,
+                     const Link& L) {
   k_bicg_final_fold<<<grid_for(n, 2), kThreads, 0, s>>>(n, own, rho, hptr, trtt, dinv, relax, p, r, xin, xout, t, rout, rt,
-                                                        w.partials, w.counter, out);
+                                                        w.partials, w.counter, out, L);
   check_launch();
 }
 void gather(int64_t n, const int32_t* idx, const double* x, double* buf, cudaStream_t s) {

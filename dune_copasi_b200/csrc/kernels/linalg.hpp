@@ -167,7 +167,8 @@ void bicg_x_half(int64_t n, const double* rho, const double* hptr, const double*
 // xout = (xin + alpha relax dinv p) + omega relax dinv r ; rout = r - omega t ; out[0] = <rout,rout> ; out[1] = <rt,rout>
 void bicg_final_fold(int64_t n, const Ranges& own, const double* rho, const double* hptr, const double* trtt,
                      const double* dinv, double relax, const double* p, const double* r, const double* xin, double* xout,
-                     const double* t, double* rout, const double* rt, double* out, const ReduceWorkspace& w, cudaStream_t s);
+                     double* t, double* rout, const double* rt, double* out, const ReduceWorkspace& w, cudaStream_t s,
+                     const Link& L = Link());
 // halo exchange helpers
 void gather(int64_t n, const int32_t* idx, const double* x, double* buf, cudaStream_t s);   // buf[i] = x[idx[i]]
 void scatter(int64_t n, const int32_t* idx, const double* buf, double* x, cudaStream_t s);  // x[idx[i]] = buf[i]

@@ -27,6 +27,15 @@ Model::Model(const PTree& cfg_, int dim_, const std::vector<std::string>& keys)
     symbolic_jacobian = jt == "symbolic";
     fd_epsilon = mcfg.get("jacobian.epsilon", 1e-7);
     reference_compat = mcfg.get("b200.reference_compat", true);
+    // model.blocked_layout.{scalar_fields, compartments} (factory.hh:74-75, 96-131) select the *nesting* of the dune-istl
+    // containers -- PDELab::EntityGrouping<ES, Blocked> per vertex, PDELab::Lexicographic<Blocked> over the
+    // compartments (model_single_compartment_traits.hh:26-27, model_multi_compartment_traits.hh:22) -- not the order of
+    // the scalars: compartment-major, vertex, species in all four combinations.  The C ABI takes flat arrays in that
+    // order, so the flags are read and change nothing here (the DUNE-side shim copies between the nested container
+    // and the flat array either way).
+    blocked_scalar_fields = mcfg.get("blocked_layout.scalar_fields", false);
+    blocked_compartments = mcfg.get("blocked_layout.compartments", false);
+
   }
   const PTree& comps = cfg.sub("compartments");
   for (auto& name : comps.sub_keys()) {

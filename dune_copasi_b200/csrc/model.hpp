@@ -44,6 +44,7 @@ class Model {
   // model.b200.reference_compat (default true): facet terms exactly as local_operator.hh:903-916 / :1298 compute
   // them (cross-side coefficients paired with this side's shape functions by local index)
   bool reference_compat = true;
+  bool blocked_scalar_fields = false, blocked_compartments = false;   // container nesting only (model.cpp)
   double fd_epsilon = 1e-7;
   // model.jacobian.type = symbolic (extension; north_star: "analytic Jacobians from SymEngine"): every
   // jacobian entry is derived from its function by expr.cpp's differentiator, the ini's own

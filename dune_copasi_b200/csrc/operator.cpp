@@ -126,6 +126,7 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
   const int ncomp = model->ncomp();
   coords_.upload(grid->coords, stream);
   vector_gather_ = acfg.get("vector_gather", false);
+  packed_conn_ = acfg.get("packed_conn", true);
   if (vector_gather_ && grid->dim == 3 && !grid->coords.empty()) {
     // padded copy for 16-byte gathers (kernels/assembly_element.cuh)
     std::vector<double> c4((size_t)grid->nv * 4, 0.0);
@@ -206,6 +207,24 @@ void DeviceOperator::ensure_element_order() {
         if (grid->elem_comp[e] == c) ids.push_back((int)e);
     }
     if (!ids.empty()) comp_elem_ids_[c].upload(ids, stream);
+    // packed connectivity in thread order (kernel_args.h): vertex ids and dof bases of the four corners
+    if (packed_conn_ && grid->dim == 3 && grid->elem_kind == 0) {
+      const int64_t n = comp_nelem_[c];
+      const int ns = model->comp_nspec[c];
+      std::vector<int> pv((size_t)n * 4), pd((size_t)n * 4);
+      const bool identity = comp_vdof_[c].p == nullptr;
+      for (int64_t t = 0; t < n; ++t) {
+        const int64_t e = ids.empty() ? t : ids[t];
+        for (int k = 0; k < 4; ++k) {
+          const int v = grid->elems[e * 4 + k];
+          pv[t * 4 + k] = v;
+          pd[t * 4 + k] = identity ? (int)grid->comp_offset[c] + v * ns : grid->comp_vdof[c][v];
+        }
+      }
+      if (comp_pverts_.size() < (size_t)model->ncomp()) { comp_pverts_.resize(model->ncomp()); comp_pdofs_.resize(model->ncomp()); }
+      comp_pverts_[c].upload(pv, stream);
+      comp_pdofs_[c].upload(pd, stream);
+    }
   }
   DCB_CUDA(cudaStreamSynchronize(stream));
 }
@@ -473,6 +492,7 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       a.time = t; a.wM = wM; a.wA = wA; a.x = x; a.z = z; a.r = r;
       a.bdiag = bdiag ? (mode == 4 ? bdiag : bdiag + bdiag_shift(c)) : nullptr;
       a.cmask = cmask.p;
+      a.zscale = nullptr; a.zrelax = 1.0;
       a.rowptr = (const long long*)rowptr.p; a.colidx = colidx.p; a.vals = vals;
       static const char* sn[5] = {"dc_k_struct_residual_", "dc_k_struct_apply_", "dc_k_struct_bdiag_", "", "dc_k_struct_diag_"};
       static const char* qn[5] = {"dc_k_q1_residual_", "dc_k_q1_apply_", "dc_k_q1_bdiag_", "dc_k_q1_csr_", "dc_k_q1_diag_"};
@@ -483,6 +503,10 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       const long long total = a.ncells, layer = total / a.n[grid->dim - 1];
       while (march > 1 && layer * ((a.n[grid->dim - 1] + march - 1) / march) < struct_march_fill_) march /= 2;
       a.march = march;
+      if (mode == 1 && zscale_) {
+        if (march > 0) fail("internal: scaled Jacobian apply with a marching driver");
+        a.zscale = zscale_; a.zrelax = zrelax_;
+      }
       const std::string kname = march > 0 ? std::string(q1 ? "dc_k_q1_march_" : "dc_k_struct_march_") + (mode == 0 ? "residual_" : "apply_")
                                           : std::string(q1 ? qn[mode] : sn[mode]);
       cudaKernel_t k = kernel(q1 ? JitGroup::StructuredQ1 : JitGroup::Structured, kname + std::to_string(c));
@@ -537,6 +561,7 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       jit_launch(k, gridsz, patch_threads_, smem, stream, a);
     } else {
       ensure_element_order();
+      if (mode == 1 && zscale_) fail("internal: scaled Jacobian apply reached the element kernels");
       DcVolArgs a{};
       a.coords = coords_.p; a.elems = elems_.p; a.elem_ids = comp_elem_ids_[c].p; a.vdof = comp_vdof_[c].p;
       a.cell = cell_.p; a.ne_total = grid->ne; a.n = comp_nelem_[c];
@@ -548,6 +573,7 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       // 16-byte gathers (padded coordinates, double2 dof loads): measured neutral on B200 (cell model on the
       // nested mesh, 96^3: 0.170 against 0.159 ms per launch) -- the kernel is bound by the fp64 atomics of
       // its scatter (~130 G RED/s), not by the gather wavefronts; kept as an option
+      if (c < (int)comp_pverts_.size() && comp_pverts_[c].p) { a.pverts = comp_pverts_[c].p; a.pdofs = comp_pdofs_[c].p; }
       a.coords4 = vector_gather_ ? coords4_.p : nullptr;
       a.vec = vector_gather_ && ns % 2 == 0 && dofs_even_ &&
               !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(z)) & 15u);
@@ -727,6 +753,13 @@ bool DeviceOperator::can_split_apply() const {
   for (int c = 0; c < model->ncomp(); ++c) with_species += model->comp_nspec[c] > 0;
   return scheme == "structured" && facets_.empty() && with_species == 1 && struct_comp_ >= 0 &&
          !model->numerical_jacobian && grid->s_cells[grid->dim - 1] >= 3;
+}
+
+// the per-cell structured apply can form its direction as relax * dinv .* z while it loads the corners
+bool DeviceOperator::apply_scale_ready() const {
+  // (finite-difference and extended-term Jacobians are applied by the element kernels even on structured grids)
+  return scheme == "structured" && struct_comp_ >= 0 && struct_march_apply_ == 0 && !tile_ready() && facets_.empty() &&
+         ncons == 0 && model->ncomp() == 1 && !model->numerical_jacobian && !model->has_extended_terms(struct_comp_);
 }
 
 void DeviceOperator::jacobian_apply(double t, double wM, double wA, const double* x, const double* z, double* y,

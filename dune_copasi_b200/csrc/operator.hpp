@@ -58,6 +58,10 @@ class DeviceOperator {
   // halo exchange of z with the interior cells
   void jacobian_apply(double t, double wM, double wA, const double* x, const double* z, double* y, int part = 0);
   bool can_split_apply() const;
+  // Jacobi folded into the apply: the next jacobian_apply reads its direction as relax * dinv .* z (structured
+  // per-cell driver only: apply_scale_ready()); null switches it off again
+  bool apply_scale_ready() const;
+  void set_apply_scale(const double* dinv, double relax) { zscale_ = dinv; zrelax_ = relax; }
   void jacobian_csr(double t, double wM, double wA, const double* x, double* vals);
   void block_diag(double t, double wM, double wA, const double* x, double* bdiag);
   // scalar diagonal straight into a dof-indexed vector (structured scheme without facet terms);
@@ -162,10 +166,14 @@ class DeviceOperator {
   long long struct_march_fill_ = 0;
   std::string jit_defines_;
   DeviceBuffer<double> coords_, coords4_, cell_, cell_patch_;
+  const double* zscale_ = nullptr;   // set_apply_scale: consumed by the structured per-cell apply
+  double zrelax_ = 1.0;
   bool vector_gather_ = false;
   bool dofs_even_ = false;   // every compartment's dof block starts at an even offset (16-byte gathers)
   DeviceBuffer<int> elems_;
   std::vector<DeviceBuffer<int>> comp_elem_ids_, comp_vdof_;
+  std::vector<DeviceBuffer<int>> comp_pverts_, comp_pdofs_;   // packed connectivity in thread order (kernel_args.h)
+  bool packed_conn_ = true;
   std::vector<int64_t> comp_nelem_;
   std::vector<PatchSet> patches_;
   std::vector<FacetList> facets_;

@@ -31,7 +31,11 @@ LinearSolver::LinearSolver(std::shared_ptr<DeviceOperator> op, const PTree& cfg,
   matrix_free = cfg.get("matrix_free", false);
   verbosity = cfg.get("verbosity", 0);
   speculation = cfg.get("b200.speculation", true);
-  sor_sweep_ = cfg.get("b200.sor_sweep", true);
+  // measured on B200 (tools/bench_ms.py, tools/bench_ssor3d.py): the self-scheduled sweep loses to the level loop
+  // (mitchell_schaefer 128^2: 706 vs 380 ms per step, Gray-Scott 64^3: 2888 vs 502) -- a few hundred thousand
+  // spinning threads polling the L2 starve the chain of rows that can run; off by default, the level loop runs as a graph
+  sor_sweep_ = cfg.get("b200.sor_sweep", false);
+  sor_graph_ = cfg.get("b200.sor_graph", true);
   auto range = cfg.get_vec("convergence_condition.iteration_range", {1, 500});   // iterative.hh:53-54
   max_iterations = (int)range.back();
   la::reduce_workspace_create(&ws_);
@@ -72,10 +76,16 @@ LinearSolver::LinearSolver(std::shared_ptr<DeviceOperator> op, const PTree& cfg,
   fused_ = type == "BiCGSTAB" && matrix_free && prec_type == "Jacobi" && prec_iterations == 1 && op_->tile_ready() &&
            op_->ncons == 0 && !overlap_halo_ && cfg.get("b200.fused", true);
   if (fused_) valt_.alloc(op_->ndofs);
+  // BiCGSTAB without the preconditioned vectors y = w D^-1 p, y2 = w D^-1 r: the structured apply forms them while it
+  // loads its corners (fp64-bound kernel, the extra loads hit L1) and the closing sweep recomputes them from p, r and
+  // D^-1 -- 21 instead of 25 vector passes per iteration, the same products in the same order (identical iterates)
+  yfree_ = type == "BiCGSTAB" && matrix_free && prec_type == "Jacobi" && prec_iterations == 1 && !fused_ && !overlap_halo_ &&
+           op_->apply_scale_ready() && cfg.get("b200.yfree", true);
   if (prec_type == "BlockJacobi" || (matrix_free && prec_type == "Jacobi")) bdiag_.alloc(op_->bdiag_size());
 }
 
 LinearSolver::~LinearSolver() {
+  for (auto& g : sor_graphs_) cudaGraphExecDestroy(g.second.exec);
   la::reduce_workspace_destroy(&ws_);
   for (auto& e : ev_)
     if (e) cudaEventDestroy(e);
@@ -118,7 +128,7 @@ void LinearSolver::linearize(double t, double wM, double wA, const double* x) {
     }
   }
   // the fused sweeps form D^-1 p at ghost vertices themselves: the owners' diagonal entries are needed there
-  if (fused_ && comm_) comm_->halo_update(dinv_.p, s);
+  if ((fused_ || yfree_) && comm_) comm_->halo_update(dinv_.p, s);
   if (prec_type == "BlockJacobi")
     for (int c = 0; c < ncomp; ++c) {
       int bs = op_->model->comp_nspec[c];
@@ -132,8 +142,13 @@ void LinearSolver::linearize(double t, double wM, double wA, const double* x) {
 
 // pushed: the ghost planes of v are already on their way (the sweep that wrote v pushed them, link_push):
 // only the pull is left.  zeroed: y is zero on entry (cleared by the sweep that consumed it last).
-void LinearSolver::apply_operator(const double* v, double* y, bool pushed, bool zeroed) {
+void LinearSolver::apply_operator(const double* v, double* y, bool pushed, bool zeroed, bool scaled) {
   cudaStream_t s = op_->stream;
+  struct ScaleGuard {   // scaled: the operator reads w D^-1 v instead of v (yfree_)
+    DeviceOperator* op;
+    ~ScaleGuard() { if (op) op->set_apply_scale(nullptr, 1.0); }
+  } guard{scaled ? op_.get() : nullptr};
+  if (scaled) op_->set_apply_scale(dinv_.p, relaxation);
   if (comm_ && overlap_halo_) {
     // structured slabs, matrix free: the ghost planes of v travel on a second (high priority)
     // stream while the cells that only read owned vertices are integrated; the two cell layers next
@@ -252,9 +267,28 @@ void LinearSolver::sor_apply(const double* d, double* v) {
   const int64_t* rp = (const int64_t*)op_->rowptr.p;
   const int nlev = (int)level_ptr_.size() - 1;
   const bool skip_diag = prec_type == "GaussSeidel";
-  la::fill(op_->ndofs, 0.0, v, s);
-  op_->stats.launches++;
   if (skip_diag && sweep_[0].n < (size_t)op_->ndofs) sweep_[0].alloc(op_->ndofs);
+  // The application is a chain of 2 nlev + 1 dependent launches with fixed arguments per (d, v) pair: captured once
+  // into a CUDA graph and replayed (linear_solver.b200.sor_graph, default on) -- the launches of a level loop are
+  // issue-bound (2-5 us each on the stream, ~1 us as graph nodes).
+  const auto key = std::make_pair((const void*)d, (void*)v);
+  long long& L = op_->stats.launches;
+  if (sor_graph_ && !sor_sweep_) {
+    auto it = sor_graphs_.find(key);
+    if (it != sor_graphs_.end()) {
+      DCB_CUDA(cudaGraphLaunch(it->second.exec, s));
+      L += it->second.launches;
+      return;
+    }
+    if (sor_graphs_.size() >= 128) {   // GMRES basis vectors come back after a restart; anything beyond that is a leak
+      for (auto& g : sor_graphs_) cudaGraphExecDestroy(g.second.exec);
+      sor_graphs_.clear();
+    }
+    DCB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+  }
+  const long long L0 = L;
+  la::fill(op_->ndofs, 0.0, v, s);
+  L++;
   auto sweep = [&](bool backward, bool skip) {
     if (sor_sweep_) {
       if (sweep_epoch_ == INT32_MAX) { sweep_done_.zero(s); sweep_epoch_ = 0; }
@@ -275,6 +309,16 @@ void LinearSolver::sor_apply(const double* d, double* v) {
     sweep(false, skip_diag);
     if (skip_diag) { la::relax_blend(op_->ndofs, relaxation, sweep_[0].p, v, s); op_->stats.launches++; }
     if (prec_type == "SSOR") sweep(true, false);
+  }
+  if (sor_graph_ && !sor_sweep_) {
+    cudaGraph_t graph = nullptr;
+    DCB_CUDA(cudaStreamEndCapture(s, &graph));
+    SorGraph g;
+    g.launches = L - L0;
+    DCB_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    sor_graphs_[key] = g;
+    DCB_CUDA(cudaGraphLaunch(g.exec, s));   // the capture recorded the work, this runs it
   }
 }
 
@@ -484,6 +528,8 @@ SolveResult LinearSolver::apply_krylov(double* b, double* x, double rel_tol) {
     const bool rlink = !comm_ || comm_->reduce_links_ready();              // sums reach hscal_ straight from the kernels
     const bool plink = comm_ && fold && comm_->push_links_ready() && !overlap_halo_;
     const bool zfuse = matrix_free && fold && !overlap_halo_ && !op_->tile_aligned({x_, y, v});
+    const bool yfree = yfree_ && zfuse;
+    const double* fold_store = yfree ? nullptr : fold;   // sweeps store w D^-1 (.) only when somebody reads it
     auto link = [&](bool reduce, double* host_out, bool push, bool zero) {
       la::Link k;
       if (comm_ && reduce && rlink) comm_->link_reduce(&k.peer);
@@ -508,15 +554,15 @@ SolveResult LinearSolver::apply_krylov(double* b, double* x, double rel_tol) {
     double *x_cur = x, *x_alt = xalt_.p;
     auto first_half = [&](int i) {
       { DeviceOperator::ProfScope ps(op_.get(), "blas1");
-        la::bicg_p_prec(n, p, r, v, pair(i - 1) + 1, pair(i - 2) + 1, sc + 2, sc + 4, i == 0, fold, relaxation, y, ws_, s,
+        la::bicg_p_prec(n, p, r, v, pair(i - 1) + 1, pair(i - 2) + 1, sc + 2, sc + 4, i == 0, fold_store, relaxation, y, ws_, s,
                         link(false, nullptr, true, true)); L++; }
       if (!fold) precondition(p, y);
-      apply_operator(y, v, plink, zfuse);
+      apply_operator(yfree ? p : y, v, plink, zfuse, yfree);
       { DeviceOperator::ProfScope ps(op_.get(), "blas1");
         la::dot(own, rt, v, sc + 2, ws_, s, link(true, hscal_.p + 2, false, false)); L++; }
       reduce_after(sc + 2, 1);
       { DeviceOperator::ProfScope ps(op_.get(), "blas1");
-        la::bicg_r_prec(n, own, pair(i - 1) + 1, sc + 2, v, r, fold, relaxation, y2, sc, ws_, s,
+        la::bicg_r_prec(n, own, pair(i - 1) + 1, sc + 2, v, r, fold_store, relaxation, y2, sc, ws_, s,
                         link(true, hscal_.p, true, false)); L++; }
       reduce_after(sc, 1);
       if (!rlink) DCB_CUDA(cudaMemcpyAsync(hscal_.p, sc, sizeof(double) * 3, cudaMemcpyDeviceToHost, s));
@@ -524,13 +570,18 @@ SolveResult LinearSolver::apply_krylov(double* b, double* x, double rel_tol) {
     };
     auto second_half = [&](int i, const double* xin, double* xout) {
       if (!fold) precondition(r, y2);
-      apply_operator(y2, t, plink, zfuse);
+      apply_operator(yfree ? r : y2, t, plink, zfuse, yfree);
       { DeviceOperator::ProfScope ps(op_.get(), "blas1");
         la::dot2(own, t, r, t, t, sc + 4, ws_, s, link(true, hscal_.p + 4, false, false)); L++; }
       reduce_after(sc + 4, 2);
       { DeviceOperator::ProfScope ps(op_.get(), "blas1");
-        la::bicg_final(n, own, pair(i - 1) + 1, sc + 2, sc + 4, y, y2, xin, xout, t, r, rt, pair(i), ws_, s,
-                       link(true, hscal_.p + 8 + 2 * (i & 1), false, true)); L++; }
+        if (yfree)
+          la::bicg_final_fold(n, own, pair(i - 1) + 1, sc + 2, sc + 4, dinv_.p, relaxation, p, r, xin, xout, t, r, rt, pair(i),
+                              ws_, s, link(true, hscal_.p + 8 + 2 * (i & 1), false, true));
+        else
+          la::bicg_final(n, own, pair(i - 1) + 1, sc + 2, sc + 4, y, y2, xin, xout, t, r, rt, pair(i), ws_, s,
+                         link(true, hscal_.p + 8 + 2 * (i & 1), false, true));
+        L++; }
       reduce_after(pair(i), 2);
       if (!rlink) DCB_CUDA(cudaMemcpyAsync(hscal_.p + 4, sc + 4, sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
       DCB_CUDA(cudaEventRecord(ev_[1], s));
@@ -571,7 +622,12 @@ SolveResult LinearSolver::apply_krylov(double* b, double* x, double rel_tol) {
       if (!(norm == norm)) break;
       if (norm < rel_tol * norm0 || norm < 1e-30) { res.converged = true; break; }
     }
-    if (pending) { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::axpy(n, alpha, y, x_cur, s); L++; }
+    if (pending) {
+      DeviceOperator::ProfScope ps(op_.get(), "blas1");
+      if (yfree) la::bicg_x_half(n, pair(i - 1) + 1, sc + 2, dinv_.p, relaxation, p, x_cur, s);   // alpha = rho / h as on the host
+      else la::axpy(n, alpha, y, x_cur, s);
+      L++;
+    }
     if (x_cur != x) { DeviceOperator::ProfScope ps(op_.get(), "blas1"); la::copy(n, x_cur, x, s); L++; }
     res.iterations = (int)std::ceil(std::min<double>(it, max_iterations));
     res.reduction = norm / norm0;

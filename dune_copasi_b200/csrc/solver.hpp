@@ -10,6 +10,7 @@
 // RestartedGMRes; Richardson, Jacobi, BlockJacobi), anything else fails loudly.
 #pragma once
 #include <vector>
+#include <map>
 #include <memory>
 #include <string>
 
@@ -39,7 +40,7 @@ class LinearSolver {
   // solve J z = b to the relative defect reduction `rel_tol`; b is consumed (holds the final defect)
   SolveResult apply(double* b, double* z, double rel_tol);
   // y = J v with the current linearisation
-  void apply_operator(const double* v, double* y, bool pushed = false, bool zeroed = false);
+  void apply_operator(const double* v, double* y, bool pushed = false, bool zeroed = false, bool scaled = false);
   // BiCGSTAB with its vector updates and dot products fused into the tile-marching apply kernels
   bool is_fused() const { return fused_; }
 
@@ -62,6 +63,7 @@ class LinearSolver {
   SolveResult apply_bicgstab_fused(double* b, double* z, double rel_tol);
   SolveResult apply_krylov(double* b, double* z, double rel_tol);
   bool fused_ = false;
+  bool yfree_ = false;   // BiCGSTAB without the stored preconditioned vectors (solver.cpp)
   DeviceBuffer<double> valt_;
   void fetch_slots(int first, int count, int total);
   std::shared_ptr<DeviceOperator> op_;
@@ -85,7 +87,9 @@ class LinearSolver {
   std::vector<int64_t> level_ptr_;
   DeviceBuffer<int32_t> level_rows_;
   // self-scheduled sweeps (la::sor_sweep, linear_solver.b200.sor_sweep = true): one launch per sweep instead of one per level
-  bool sor_sweep_ = true;
+  bool sor_sweep_ = false, sor_graph_ = true;
+  struct SorGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; };
+  std::map<std::pair<const void*, void*>, SorGraph> sor_graphs_;   // one captured application per (d, v) pair
   DeviceBuffer<int32_t> sweep_slots_, dep_idx_;
   DeviceBuffer<int64_t> dep_ptr_;
   DeviceBuffer<int> sweep_done_;

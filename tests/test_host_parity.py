@@ -237,3 +237,17 @@ def test_vtk_output_of_q1_lattices(tmp_path, name, vtk_type):
     assert np.array_equal(arrays["offsets"].astype(int), nd * np.arange(1, om.mesh.ne + 1))
     assert np.array_equal(arrays["U"], u[0::2]) and np.array_equal(arrays["V"], u[1::2])
     assert np.array_equal(arrays["Coordinates"].reshape(-1, 3)[:, :case.dim], om.mesh.coords)
+
+
+def test_blocked_layout_flags_change_the_container_nesting_only():
+    """model.blocked_layout.{scalar_fields, compartments} (factory.hh:74-75): EntityGrouping<.., Blocked> /
+    Lexicographic<Blocked> nest the dune-istl containers; the flat scalar order the C ABI uses is the same."""
+    base = K.CASES["cell3d"]
+    ref = None
+    for sf in ("false", "true"):
+        for cb in ("false", "true"):
+            cfg, model, grid = K.product_objects(base, **{"model.blocked_layout.scalar_fields": sf,
+                                                          "model.blocked_layout.compartments": cb})
+            got = (grid.ndofs, grid.elem_dof().tobytes(), grid.pattern(model)[0].tobytes(), grid.pattern(model)[1].tobytes())
+            ref = ref or got
+            assert got == ref

@@ -24,6 +24,9 @@ def run(level, steps, sweep):
             "model.time_step_operator.linear_solver.preconditioner.type": "SSOR",
             "model.time_step_operator.linear_solver.matrix_free": "false",
             "model.time_step_operator.linear_solver.b200.sor_sweep": "true" if sweep else "false"}
+    for kv in filter(None, os.environ.get("MS_SET", "").split(",")):
+        k, v = kv.split("=")
+        over[k] = v
     case = K.CASES["mitchell_schaefer"]
     cfg = D.Config(case.ini_with(**over))
     model = D.Model(cfg, 2)
@@ -60,4 +63,4 @@ if __name__ == "__main__":
     a = run(level, steps, True)
     import numpy as np
     if a is not None and b is not None:
-        print("identical fields:", bool(np.array_equal(a, b)))
+        print("identical fields:", bool(np.array_equal(a, b)), "max abs difference", float(np.abs(a - b).max()))
