@@ -2,6 +2,7 @@
 
 #include <dlfcn.h>
 #include <nvrtc.h>
+#include <fcntl.h>
 #include <sys/stat.h>
 
 #include <algorithm>
@@ -220,7 +221,10 @@ std::vector<char> jit_compile_cached(const std::string& source) {
     std::ifstream f(path, std::ios::binary);
     if (f) {
       std::vector<char> bin((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-      if (!bin.empty()) return bin;
+      if (!bin.empty()) {
+        utimensat(AT_FDCWD, path.c_str(), nullptr, 0);   // mark as in use: build() prunes entries no build has touched
+        return bin;
+      }
     }
   }
   std::string log;

@@ -62,6 +62,8 @@ struct DcStructArgs {
   int n[3];                    // cells per axis of the (local) box
   double h[3], origin[3];
   double rh[3];                // 1 / h (the host divides once)
+  double vol;                  // volume of one Kuhn simplex, prod(h) / dim! (an fp64 division: ~6 % of the apply kernel's
+                               // issue slots when every thread redid it, profiles/r02_struct_apply_256_xpair_ncu.txt)
   long long cell_begin;        // this launch covers the cells [cell_begin, ncells)
   long long ncells;
   int march;                   // marching kernels: cells a thread walks along the last axis

@@ -488,6 +488,7 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
         a.origin[k] = grid->s_origin[k];
         a.ncells *= a.n[k];
       }
+      a.vol = struct_simplex_volume();
       a.dof_offset = (int)grid->comp_offset[c];
       a.time = t; a.wM = wM; a.wA = wA; a.x = x; a.z = z; a.r = r;
       a.bdiag = bdiag ? (mode == 4 ? bdiag : bdiag + bdiag_shift(c)) : nullptr;
@@ -670,6 +671,7 @@ void DeviceOperator::launch_tile(int mode, double t, double wM, double wA, const
     a.origin[k] = grid->s_origin[k];
     a.ncells *= a.n[k];
   }
+  a.vol = struct_simplex_volume();
   a.dof_offset = (int)grid->comp_offset[c];
   a.time = t; a.wM = wM; a.wA = wA; a.x = x; a.z = z; a.r = y;
   a.cmask = cmask.p;
@@ -753,6 +755,13 @@ bool DeviceOperator::can_split_apply() const {
   for (int c = 0; c < model->ncomp(); ++c) with_species += model->comp_nspec[c] > 0;
   return scheme == "structured" && facets_.empty() && with_species == 1 && struct_comp_ >= 0 &&
          !model->numerical_jacobian && grid->s_cells[grid->dim - 1] >= 3;
+}
+
+// prod(h) / dim!, in the kernels' operation order (h[0] * h[1] * h[2], then one division)
+double DeviceOperator::struct_simplex_volume() const {
+  double adet = 1.0;
+  for (int k = 0; k < grid->dim; ++k) adet *= grid->s_h[k];
+  return adet / (grid->dim == 3 ? 6.0 : 2.0);
 }
 
 // the per-cell structured apply can form its direction as relax * dinv .* z while it loads the corners

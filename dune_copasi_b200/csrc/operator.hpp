@@ -61,6 +61,7 @@ class DeviceOperator {
   // Jacobi folded into the apply: the next jacobian_apply reads its direction as relax * dinv .* z (structured
   // per-cell driver only: apply_scale_ready()); null switches it off again
   bool apply_scale_ready() const;
+  double struct_simplex_volume() const;
   void set_apply_scale(const double* dinv, double relax) { zscale_ = dinv; zrelax_ = relax; }
   void jacobian_csr(double t, double wM, double wA, const double* x, double* vals);
   void block_diag(double t, double wM, double wA, const double* x, double* bdiag);
