@@ -65,6 +65,10 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
       for (int mode = 0; mode < 4; ++mode)
         o << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, DC_STRUCT_MINB) dc_k_struct_" << names[mode] << "_" << c
           << "(DcStructArgs a) { dc_structured_kernel<" << c << ", " << mode << ">(a); }\n";
+      o << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, DC_STRUCT_MINB) dc_k_struct_apply_scaled_" << c
+        << "(DcStructArgs a) { dc_structured_kernel<" << c << ", 1, true>(a); }\n"
+        << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, DC_STRUCT_MINB) dc_k_struct_apply_nomask_" << c
+        << "(DcStructArgs a) { dc_structured_kernel<" << c << ", 1, false, true>(a); }\n";
       for (int mode = 0; mode < 2; ++mode)
         o << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, DC_STRUCT_MINB) dc_k_struct_march_" << names[mode] << "_" << c
           << "(DcStructArgs a) { dc_structured_march_kernel<" << c << ", " << mode << ">(a); }\n";
@@ -80,6 +84,10 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
       for (int mode = 0; mode < 5; ++mode)
         o << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, " << (mode == 4 ? "2" : "DC_STRUCT_MINB") << ") dc_k_q1_"
           << names[mode] << "_" << c << "(DcStructArgs a) { dc_q1_kernel<" << c << ", " << mode << ">(a); }\n";
+      o << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, DC_STRUCT_MINB) dc_k_q1_apply_scaled_" << c
+        << "(DcStructArgs a) { dc_q1_kernel<" << c << ", 1, true>(a); }\n"
+        << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, DC_STRUCT_MINB) dc_k_q1_apply_nomask_" << c
+        << "(DcStructArgs a) { dc_q1_kernel<" << c << ", 1, false, true>(a); }\n";
       for (int mode = 0; mode < 2; ++mode)
         o << "extern \"C\" __global__ void __launch_bounds__(DC_STRUCT_THREADS, DC_STRUCT_MINB) dc_k_q1_march_"
           << names[mode] << "_" << c << "(DcStructArgs a) { dc_q1_march_kernel<" << c << ", " << mode << ">(a); }\n";
@@ -139,6 +147,9 @@ std::string jit_defines(const Model& model) {
   int cminb = acfg.get("csr_min_blocks", 8);
   if (cminb < 1 || cminb > 16) fail("model.assembly.b200.csr_min_blocks out of range");
   // element-per-thread residual / apply (128 threads): resident CTAs per SM the compiler has to leave room for
+  // structured per-cell driver: L2 prefetch of the first-touch vertex row one plane ahead (assembly_structured.cuh)
+  const int host_vol = acfg.get("host_vol", false) ? 1 : 0;   // simplex volume from the host instead of one fp64 division per thread
+  const int sprefetch = acfg.get("struct_prefetch", false) ? 1 : 0;   // measured neutral on B200: off
   int eminb = acfg.get("elem_min_blocks", 4);   // 4 x 128 threads: 128 registers, measured -2 % on the cell model against 164 registers x 3
   if (eminb < 1 || eminb > 16) fail("model.assembly.b200.elem_min_blocks out of range");
   // tile-marching drivers: 32 x (tile_w * tile_r) cells per CTA in 3-D (tile_w warps, tile_r cell rows each)
@@ -149,7 +160,7 @@ std::string jit_defines(const Model& model) {
   if (tw < 1 || tw > 32 || tr < 1 || tr > 16) fail("model.assembly.b200.tile_w / tile_r out of range");
   if (tminb < 1 || tminb > 16) fail("model.assembly.b200.tile_min_blocks out of range");
   return "#define DC_TILE_W " + std::to_string(tw) + "\n#define DC_TILE_R " + std::to_string(tr) +
-         "\n#define DC_TILE_MINB " + std::to_string(tminb) + "\n#define DC_CSR_MINB " + std::to_string(cminb) + "\n#define DC_ELEM_MINB " + std::to_string(eminb) + "\n#define DC_PATCH_THREADS " + std::to_string(th) + "\n#define DC_PATCH_MINB " + std::to_string(minb) +
+         "\n#define DC_TILE_MINB " + std::to_string(tminb) + "\n#define DC_CSR_MINB " + std::to_string(cminb) + "\n#define DC_ELEM_MINB " + std::to_string(eminb) + "\n#define DC_STRUCT_PREFETCH " + std::to_string(sprefetch) + "\n#define DC_HOST_VOL " + std::to_string(host_vol) + "\n#define DC_PATCH_THREADS " + std::to_string(th) + "\n#define DC_PATCH_MINB " + std::to_string(minb) +
          "\n#define DC_STRUCT_THREADS " + std::to_string(sth) + "\n#define DC_STRUCT_MINB " + std::to_string(sminb) + "\n";
 }
 

@@ -344,15 +344,16 @@ __device__ __forceinline__ void dc_q1_matrix_kernel(const DcStructArgs& a) {
     }
 }
 
-template <int C, int MODE>
+template <int C, int MODE, bool SCALED = false, bool NOMASK = false>
 __device__ __forceinline__ void dc_q1_kernel(const DcStructArgs& a) {
   constexpr int NS = DcComp<C>::NS;
   if constexpr (MODE >= 2) {
     dc_q1_matrix_kernel<C, MODE>(a);
   } else {
-    dc_struct_per_cell<C, MODE>(a, [&](const int* idx, const double (*U)[NS], const double (*Z)[NS], double (*acc)[NS]) {
+    auto cell = [&](const int* idx, const double (*U)[NS], const double (*Z)[NS], double (*acc)[NS]) {
       dc_q1_cell<C, MODE>(a, idx, U, Z, acc);
-    });
+    };
+    dc_struct_per_cell<C, MODE, decltype(cell), SCALED, NOMASK>(a, cell);
   }
 }
 template <int C, int MODE>

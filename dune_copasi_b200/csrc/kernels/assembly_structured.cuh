@@ -98,7 +98,11 @@ __device__ __forceinline__ void dc_struct_cell(const DcStructArgs& a, const int*
   double adet = 1.0, rh[DC_DIM];
 #pragma unroll
   for (int k = 0; k < DC_DIM; ++k) { adet *= a.h[k]; rh[k] = a.rh[k]; }
+#if DC_HOST_VOL
   const double f = DC_QW * adet, vol = a.vol;   // = adet / DC_FACT, divided once on the host
+#else
+  const double f = DC_QW * adet, vol = adet / DC_FACT;
+#endif
   const double ABf = DC_PAB * f, Bf = DC_PB * f;
   DcCtx c;
   c.time = a.time; c.entity_volume = vol; c.integration_factor = f;
@@ -322,7 +326,11 @@ __device__ __forceinline__ void dc_cell_index(const DcStructArgs& a, long long c
 // first, and only one reduction per *vertex* value leaves the warp (plus the last lane's x = 1 half).  ncu on the
 // 256^3 apply had the L2's atomic unit at 90 % of its peak (`lts__d_atomic_input_cycles_active`,
 // profiles/r02_struct_apply_256_ncu.txt) next to the fp64 pipe at 77 %: this halves the `RED` sectors.
-template <int C, int MODE, class CellFn>
+// SCALED (apply only): the direction is (zrelax * zscale) .* z, formed while the corners are loaded -- a separate
+// instantiation, because a run-time switch in the load phase (16 conditional loads) cost the plain apply 10 %
+// (same box: 0.838 -> 0.922 ms; the loads no longer issued as one batch)
+// NOMASK (apply only): the operator has no Dirichlet rows (the host checks), the mask is not looked at
+template <int C, int MODE, class CellFn, bool SCALED = false, bool NOMASK = false>
 __device__ __forceinline__ void dc_struct_per_cell(const DcStructArgs& a, CellFn cell_fn) {
   typedef DcComp<C> M;
   constexpr int NS = M::NS;
@@ -341,18 +349,18 @@ __device__ __forceinline__ void dc_struct_per_cell(const DcStructArgs& a, CellFn
     double U[DC_NCORN][NS], Z[MODE == 1 ? DC_NCORN : 1][NS];
     const double* xb = a.x + d0;
     const double* zb = MODE == 1 ? a.z + d0 : nullptr;
-    const double* sb = (MODE == 1 && a.zscale) ? a.zscale + d0 : nullptr;
+    const double* sb = (MODE == 1 && SCALED) ? a.zscale + d0 : nullptr;
     const unsigned char* mb = a.cmask ? a.cmask + d0 : nullptr;
 #if DC_DIM == 3
     // The only vertex row a warp is the first to touch is (y + 1, z + 1); everything else was loaded by the row or
     // the plane before and hits L1 / L2.  ncu had 16 % of the apply kernel's samples on the first use of the loaded
     // corners (`long_scoreboard`, DRAM latency at 3 warps per scheduler): the same row one plane ahead -- the first
     // touch of the cell n0 * n1 positions later -- is pulled into L2 now.  No extra DRAM traffic: it is demanded later.
-    if ((MODE == 0 || MODE == 1) && idx[2] + 2 <= a.n[2]) {
+    if (DC_STRUCT_PREFETCH && (MODE == 0 || MODE == 1) && idx[2] + 2 <= a.n[2]) {
       const long long ahead = (long long)o1 + 2ll * o2;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + ahead));
       if (MODE == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(zb + ahead));
-      if (MODE == 1 && sb) asm volatile("prefetch.global.L2 [%0];" ::"l"(sb + ahead));
+      if (MODE == 1 && SCALED) asm volatile("prefetch.global.L2 [%0];" ::"l"(sb + ahead));
     }
 #endif
 #pragma unroll
@@ -360,11 +368,13 @@ __device__ __forceinline__ void dc_struct_per_cell(const DcStructArgs& a, CellFn
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         U[m][s] = xb[off(m) + s];
-        if (MODE == 1) {
-          double z = zb[off(m) + s];
-          if (sb) z = (a.zrelax * sb[off(m) + s]) * z;   // the product k_bicg_p_prec / k_bicg_r_prec would have stored
-          Z[m][s] = (mb && mb[off(m) + s]) ? 0.0 : z;
-        }
+        // (the unscaled form is kept exactly as it was: written as "load, then select" the same statement compiled to
+        // a kernel 11 % slower -- 131 predicated instructions instead of 22 short branches, same-box A/B)
+        if (MODE == 1 && !SCALED && !NOMASK) Z[m][s] = (mb && mb[off(m) + s]) ? 0.0 : zb[off(m) + s];
+        if (MODE == 1 && !SCALED && NOMASK) Z[m][s] = zb[off(m) + s];
+        // zscale = relax * dinv, rounded once: the product k_bicg_p_prec / k_bicg_r_prec would have stored
+        // (only operators without Dirichlet rows take this path: apply_scale_ready)
+        if (MODE == 1 && SCALED) Z[m][s] = sb[off(m) + s] * zb[off(m) + s];
       }
     }
     cell_fn(idx, U, Z, acc);
@@ -535,13 +545,14 @@ __device__ __forceinline__ void dc_struct_march(const DcStructArgs& a, CellFn ce
   flush_face(ke, valid && ke > kb, accb);
 }
 
-template <int C, int MODE>
+template <int C, int MODE, bool SCALED = false, bool NOMASK = false>
 __device__ __forceinline__ void dc_structured_kernel(const DcStructArgs& a) {
   constexpr int NS = DcComp<C>::NS;
   constexpr int NV = MODE == 2 ? NS * NS : NS;
-  dc_struct_per_cell<C, MODE>(a, [&](const int* idx, const double (*U)[NS], const double (*Z)[NS], double (*acc)[NV]) {
+  auto cell = [&](const int* idx, const double (*U)[NS], const double (*Z)[NS], double (*acc)[NV]) {
     dc_struct_cell<C, MODE>(a, idx, U, Z, acc);
-  });
+  };
+  dc_struct_per_cell<C, MODE, decltype(cell), SCALED, NOMASK>(a, cell);
 }
 template <int C, int MODE>
 __device__ __forceinline__ void dc_structured_march_kernel(const DcStructArgs& a) {

@@ -105,7 +105,7 @@ __device__ __forceinline__ void dc_struct_cell_stream(const DcStructArgs& a, con
   double adet = 1.0, rh[DC_DIM];
 #pragma unroll
   for (int k = 0; k < DC_DIM; ++k) { adet *= a.h[k]; rh[k] = a.rh[k]; }
-  const double f = DC_QW * adet, vol = a.vol;   // = adet / DC_FACT, divided once on the host
+  const double f = DC_QW * adet, vol = adet / DC_FACT;
   const double ABf = DC_PAB * f, Bf = DC_PB * f;
   DcCtx c;
   c.time = a.time; c.entity_volume = vol; c.integration_factor = f;

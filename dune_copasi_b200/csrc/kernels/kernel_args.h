@@ -74,10 +74,11 @@ struct DcStructArgs {
   double* r;
   double* bdiag;
   const unsigned char* cmask;
-  // Jacobian apply of the per-cell driver: direction = zrelax * zscale .* z when zscale != null (the Jacobi
-  // application of the Krylov solve formed while the corners are loaded, instead of a vector written and re-read)
+  // Jacobian apply of the per-cell driver, scaled instantiation: direction = zscale .* z with zscale = relax * D^-1
+  // (the Jacobi application of the Krylov solve formed while the corners are loaded, instead of a vector written
+  // and re-read)
   const double* zscale;
-  double zrelax;
+  double zrelax;               // unused (the relaxation factor is folded into zscale by the host)
   const long long* rowptr;     // CSR of the Jacobian (Q1 fill only)
   const int* colidx;
   double* vals;

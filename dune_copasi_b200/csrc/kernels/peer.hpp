@@ -45,7 +45,7 @@ struct HaloArgs {
   // spins are bounded: a peer that never publishes (died, diverged) raises *error instead of hanging the device
   int* error;
 };
-constexpr long long kSpinLimit = 1ll << 26;   // polls of a flag before giving up (about a minute of wall time)
+constexpr long long kSpinLimit = 1ll << 29;   // polls of a flag before giving up: minutes of wall time (a rank may sit in NVRTC for a while)
 
 // general partitions: peer k sends the entries send_idx[send_ptr[k] .. send_ptr[k+1]) of the vector (both sides
 // list them in the same canonical order) and fills recv_idx[recv_ptr[k] .. recv_ptr[k+1]); slot = source rank

@@ -127,6 +127,8 @@ DeviceOperator::DeviceOperator(std::shared_ptr<const Model> m, std::shared_ptr<c
   coords_.upload(grid->coords, stream);
   vector_gather_ = acfg.get("vector_gather", false);
   packed_conn_ = acfg.get("packed_conn", true);
+  // same-box A/B (tools/gpu_run_r02n.sh): P1 apply 0.830 -> 0.805 ms, Q1 apply 0.735 -> 0.652 ms
+  struct_nomask_ = acfg.get("struct_nomask", true);
   if (vector_gather_ && grid->dim == 3 && !grid->coords.empty()) {
     // padded copy for 16-byte gathers (kernels/assembly_element.cuh)
     std::vector<double> c4((size_t)grid->nv * 4, 0.0);
@@ -509,6 +511,8 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
         a.zscale = zscale_; a.zrelax = zrelax_;
       }
       const std::string kname = march > 0 ? std::string(q1 ? "dc_k_q1_march_" : "dc_k_struct_march_") + (mode == 0 ? "residual_" : "apply_")
+                                : a.zscale ? std::string(q1 ? "dc_k_q1_apply_scaled_" : "dc_k_struct_apply_scaled_")
+                                : (mode == 1 && ncons == 0 && struct_nomask_) ? std::string(q1 ? "dc_k_q1_apply_nomask_" : "dc_k_struct_apply_nomask_")
                                           : std::string(q1 ? qn[mode] : sn[mode]);
       cudaKernel_t k = kernel(q1 ? JitGroup::StructuredQ1 : JitGroup::Structured, kname + std::to_string(c));
       const int sth = model->cfg.sub("model.assembly.b200").get("struct_threads", 32);

@@ -175,6 +175,7 @@ class DeviceOperator {
   std::vector<DeviceBuffer<int>> comp_elem_ids_, comp_vdof_;
   std::vector<DeviceBuffer<int>> comp_pverts_, comp_pdofs_;   // packed connectivity in thread order (kernel_args.h)
   bool packed_conn_ = true;
+  bool struct_nomask_ = true;   // apply instantiation without the Dirichlet mask when the operator has no constrained dofs
   std::vector<int64_t> comp_nelem_;
   std::vector<PatchSet> patches_;
   std::vector<FacetList> facets_;

@@ -80,7 +80,9 @@ LinearSolver::LinearSolver(std::shared_ptr<DeviceOperator> op, const PTree& cfg,
   // loads its corners (fp64-bound kernel, the extra loads hit L1) and the closing sweep recomputes them from p, r and
   // D^-1 -- 21 instead of 25 vector passes per iteration, the same products in the same order (identical iterates)
   yfree_ = type == "BiCGSTAB" && matrix_free && prec_type == "Jacobi" && prec_iterations == 1 && !fused_ && !overlap_halo_ &&
-           op_->apply_scale_ready() && cfg.get("b200.yfree", true);
+           op_->apply_scale_ready() && cfg.get("b200.yfree", op_->grid->elem_kind == 0);
+  // (on by default for P1 only: same box, 256^3: P1 94.8 -> 93.7 ms per step; Q1 55.9 -> 58.2 -- the Q1 apply is bound by
+  // its loads, not by the fp64 pipe, and pays more for the extra corner loads than the sweeps save)
   if (prec_type == "BlockJacobi" || (matrix_free && prec_type == "Jacobi")) bdiag_.alloc(op_->bdiag_size());
 }
 
@@ -129,6 +131,12 @@ void LinearSolver::linearize(double t, double wM, double wA, const double* x) {
   }
   // the fused sweeps form D^-1 p at ghost vertices themselves: the owners' diagonal entries are needed there
   if ((fused_ || yfree_) && comm_) comm_->halo_update(dinv_.p, s);
+  if (yfree_ && relaxation != 1.0) {   // relax * dinv, rounded once: what the sweeps multiply p and r with
+    if (wdinv_.n < (size_t)op_->ndofs) wdinv_.alloc(op_->ndofs);
+    la::copy(op_->ndofs, dinv_.p, wdinv_.p, s);
+    la::scale(op_->ndofs, relaxation, wdinv_.p, s);
+    op_->stats.launches += 2;
+  }
   if (prec_type == "BlockJacobi")
     for (int c = 0; c < ncomp; ++c) {
       int bs = op_->model->comp_nspec[c];
@@ -148,7 +156,7 @@ void LinearSolver::apply_operator(const double* v, double* y, bool pushed, bool 
     DeviceOperator* op;
     ~ScaleGuard() { if (op) op->set_apply_scale(nullptr, 1.0); }
   } guard{scaled ? op_.get() : nullptr};
-  if (scaled) op_->set_apply_scale(dinv_.p, relaxation);
+  if (scaled) op_->set_apply_scale(relaxation == 1.0 ? dinv_.p : wdinv_.p, 1.0);
   if (comm_ && overlap_halo_) {
     // structured slabs, matrix free: the ghost planes of v travel on a second (high priority)
     // stream while the cells that only read owned vertices are integrated; the two cell layers next

@@ -64,6 +64,7 @@ class LinearSolver {
   SolveResult apply_krylov(double* b, double* z, double rel_tol);
   bool fused_ = false;
   bool yfree_ = false;   // BiCGSTAB without the stored preconditioned vectors (solver.cpp)
+  DeviceBuffer<double> wdinv_;   // relaxation * dinv_ (yfree_ with relaxation != 1)
   DeviceBuffer<double> valt_;
   void fetch_slots(int first, int count, int total);
   std::shared_ptr<DeviceOperator> op_;
