@@ -437,6 +437,8 @@ def main():
         peak, peak_src = peaks()
         dim = args.dim
         nodes, tets = nv_global / world, (6 if dim == 3 else 2) * args.cells ** dim / world
+        yfree_apply = (args.element == "p1" and args.workload == "grayscott" and args.matrix_free and args.prec == "Jacobi"
+                       and "yfree=false" not in args.set and "tile=true" not in args.b200)
         alg = {  # algorithmic bytes per launch, SURVEY.md 8(d) (per rank)
             "patch_apply": nodes * (16 * 2 + 8 * dim + 8 * 2) + tets * 4 * (dim + 1),
             "patch_residual": nodes * (16 * 2 + 8 * dim) + tets * 4 * (dim + 1),
@@ -446,7 +448,9 @@ def main():
             "spmv": op.ndofs * (54 if args.element == "q1" else 30) * 12 + op.ndofs * 20,
             # structured-implicit variant: no connectivity, no coordinates (32 B/vertex)
             "struct_residual": nodes * (16 * 2),
-            "struct_apply": nodes * (16 * 2 + 8 * 2),
+            # P1 default (linear_solver.b200.yfree): the apply also reads D^-1 and forms the Jacobi application itself:
+            # read u, z, dinv / write y = 64 B per vertex at two species; otherwise read u, z / write y = 48
+            "struct_apply": nodes * (16 * 2 + 8 * 2 + (8 * 2 if yfree_apply else 0)),
             "struct_bdiag": nodes * (8 * 2 + 8 * 4),
             # tile-marching sweeps with the BiCGSTAB updates fused in (mean of the two sweeps of an iteration:
             # read u, r, p, v, dinv, rt / write p, v = 128 B per vertex; read u, r, v, dinv / write r, t = 96)

@@ -33,6 +33,8 @@ std::string jit_source(const Model& model, const std::string& defines, JitGroup 
         << "(DcVolArgs a) { dc_residual_volume<" << c << ">(a); }\n";
       o << "extern \"C\" __global__ void __launch_bounds__(128, DC_ELEM_MINB) dc_k_jacobian_apply_volume_" << c
         << "(DcVolArgs a) { dc_jacobian_apply_volume<" << c << ">(a); }\n";
+      o << "extern \"C\" __global__ void __launch_bounds__(128, DC_ELEM_MINB) dc_k_jacobian_apply_volume_nomask_" << c
+        << "(DcVolArgs a) { dc_jacobian_apply_volume<" << c << ", true>(a); }\n";
       o << "extern \"C\" __global__ void __launch_bounds__(128) dc_k_bdiag_volume_" << c
         << "(DcVolArgs a) { dc_jacobian_volume<" << c << ", 1>(a); }\n";
     }

@@ -598,7 +598,9 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
           continue;
         }
       }
-      cudaKernel_t k = kernel(mode == 3 ? JitGroup::Csr : JitGroup::Element, std::string(kind) + std::to_string(c));
+      const bool nomask = mode == 1 && ncons == 0 && struct_nomask_;   // direction used as loaded (no Dirichlet rows)
+      cudaKernel_t k = kernel(mode == 3 ? JitGroup::Csr : JitGroup::Element,
+                              std::string(kind) + (nomask ? "nomask_" : "") + std::to_string(c));
       static const char* ek[4] = {"elem_residual", "elem_apply", "elem_bdiag", "csr_fill"};
       ProfScope ps(this, ek[mode]);
       jit_launch(k, (unsigned)((a.n + 127) / 128), 128, 0, stream, a);
