@@ -545,8 +545,8 @@ def main():
                                            "breakdown_ms_per_step") if q1["roofline"] and k in q1["roofline"]}
         if q1["roofline"] and "fp64_pipe" in q1["roofline"]:
             line["q1_variant"]["roofline"]["fp64_pipe"] = q1["roofline"]["fp64_pipe"]
-    if not args.no_cpu_baseline:
-        # the CPU arm runs after the GPUs are released (rank 0 only)
+    if not args.no_cpu_baseline and world == 1:
+        # the CPU arm runs after the GPU is released (single-GPU runs only: the scaling runs carry no CPU leg)
         line["cpu_baseline"], _, _ = cpu_baseline(args, 2, 1, args.cpu_cells)
     print(json.dumps(line), flush=True)
 

@@ -133,3 +133,30 @@ def test_cxx_example_runs_on_the_device(tmp_path):
     out = subprocess.run([exe, "64", "5.0", str(tmp_path / "vtk")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.startswith("t = 5 after") and (tmp_path / "vtk" / "vtk-compartment-00000.vtu").exists()
+
+
+def _build_dune_shim(tmp_path):
+    """examples/dune_shim: the reference-side binding of INTEGRATION.md section 2 (B200StageOperator, B200LinearSolver)
+    compiled against stand-in PDELab names and linked with the C ABI"""
+    exe = str(tmp_path / "shim_check")
+    shim = os.path.join(ROOT, "examples", "dune_shim")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(shim, "stub"), "-I", shim, os.path.join(shim, "check.cpp"), "-o", exe,
+                           "-L", os.path.dirname(LIB), "-ldune_copasi_b200", "-Wl,-rpath," + os.path.dirname(LIB)])
+    return exe
+
+
+def test_dune_side_shim_compiles_and_fails_loudly_without_a_device(tmp_path):
+    import dune_copasi_b200 as D
+    out = subprocess.run([_build_dune_shim(tmp_path)], capture_output=True, text=True, timeout=300)
+    if D.lib().dcb_device_count() < 1:
+        assert out.returncode == 2 and "no CUDA device" in out.stderr
+    else:
+        assert out.returncode == 0, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_dune_side_shim_runs_on_the_device(tmp_path):
+    """residual through the shim == residual through the ABI, and J z = b solved back to z through B200LinearSolver"""
+    out = subprocess.run([_build_dune_shim(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.startswith("shim ok"), out.stdout + out.stderr
