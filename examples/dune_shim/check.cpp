@@ -74,7 +74,8 @@ int main() {
   for (size_t i = 0; i < n; ++i) { de += (sol[i] - z[i]) * (sol[i] - z[i]); ne += z[i] * z[i]; }
   printf("shim ok: dofs %zu, residual via shim vs ABI %.1e, solve error %.1e after %d iterations\n", n,
          std::sqrt(dr / nr), std::sqrt(de / ne), (int)lin.last.iterations);
-  const bool good = dr == 0.0 && std::sqrt(de / ne) < 1e-7;
+  // (two runs of the same residual differ by the order of the fp64 atomics: rounding, not zero)
+  const bool good = std::sqrt(dr / nr) < 1e-13 && std::sqrt(de / ne) < 1e-7;
   dcb_solver_destroy(solver); dcb_config_destroy(lcfg); dcb_operator_destroy(op); dcb_model_destroy(model);
   dcb_grid_destroy(grid); dcb_config_destroy(cfg);
   return good ? 0 : 3;
