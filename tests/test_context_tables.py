@@ -216,3 +216,41 @@ def test_tiff_images_as_context_functions(tmp_path):
     big_model = D.Model(D.Config(TIFF_INI.format(a=a, b=big)), 2)      # fine on the host ...
     with pytest.raises(D.DcbError, match="too large for device code"):
         big_model.cuda_source()                                        # ... refused where a kernel would need it
+
+
+def test_reference_tiff_unit_test_restated(tmp_path):
+    """test/dune/copasi/common/tiff_grayscale.cc (the reference's own unit test; its flower-minisblack-{04,08,16}.tif
+    are git-LFS pointers here, so the same picture is synthesised at 72 dpi): a 4-bit image is refused
+    (UnsupportedEncoding), the 8-bit and the 16-bit version of one picture agree within 2 / 255 pixel by pixel and
+    position by position (Compare16vs8Bits) -- through the oracle's reader and the product's."""
+    import dune_copasi_b200 as D
+    from oracle import tiff as TIFF
+    rng = np.random.default_rng(4)
+    rows, cols = 43, 73
+    yy, xx = np.mgrid[0:rows, 0:cols]
+    pic8 = np.clip(128 + 100 * np.sin(xx / 9.0) * np.cos(yy / 7.0) + rng.integers(-5, 6, (rows, cols)), 0, 255).astype(np.int64)
+    p8, p16, p4 = (str(tmp_path / n) for n in ("f08.tif", "f16.tif", "f04.tif"))
+    TIFF.write(p8, pic8, bits=8, x_res=(72, 1), y_res=(72, 1))
+    TIFF.write(p16, pic8 * 257, bits=16, x_res=(72, 1), y_res=(72, 1))
+    raw = bytearray(open(p8, "rb").read())
+    raw[raw.index(b"\x02\x01\x03\x00") + 8] = 4          # BitsPerSample = 4
+    open(p4, "wb").write(bytes(raw))
+    with pytest.raises(TIFF.TiffError, match="4 bits not implemented"):
+        TIFF.read(p4)
+    i8, i16 = TIFF.read(p8), TIFF.read(p16)
+    assert (i8.rows, i8.cols) == (i16.rows, i16.cols) == (rows, cols)
+    thr = 2.0 / 255
+    assert np.abs(i8.values - i16.values).max() <= thr
+    res_unit = 72
+    for i in range(0, rows, 3):
+        for j in range(0, cols, 5):
+            assert abs(i8(j / res_unit, i / res_unit) - i16(j / res_unit, i / res_unit)) <= thr
+    # the product's reader: the same three files behind parser_context functions
+    ini = K.EXP.replace("initial.expression = 1", "initial.expression = a(position_x, position_y) - b(position_x, position_y)")
+    ini += "\n[parser_context.a]\ntype = tiff\npath = {}\n[parser_context.b]\ntype = tiff\npath = {}\n"
+    case = K.Case("tiff_unit", ini.format(p8, p16), 2, lambda: K.OMESH.structured(2, [8, 8]), structured=([8, 8], [0, 0], [1, 1]))
+    cfg, model, grid = K.product_objects(case)
+    u0 = grid.interpolate(model, 0.0)
+    assert np.abs(u0).max() <= thr and np.array_equal(u0, case.oracle().initial(0.0))
+    with pytest.raises(D.DcbError, match="4 bits not implemented"):
+        D.Model(D.Config(ini.format(p4, p16)), 2)
