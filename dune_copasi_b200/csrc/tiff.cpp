@@ -1,5 +1,8 @@
 #include "tiff.hpp"
 
+#include <dlfcn.h>
+
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -31,6 +34,57 @@ struct Reader {
   }
 };
 
+// TIFF LZW (compression 5): MSB-first codes of 9..12 bits, ClearCode 256, EndOfInformation 257, code width grows one
+// code early ("early change", what every TIFF writer since 5.0 does)
+void lzw_decode(const unsigned char* in, size_t n, std::vector<unsigned char>& out) {
+  std::vector<std::vector<unsigned char>> table;
+  auto reset = [&] {
+    table.assign(258, {});
+    for (int i = 0; i < 256; ++i) table[i] = {(unsigned char)i};
+  };
+  reset();
+  int width = 9;
+  long prev = -1;
+  uint32_t acc = 0;
+  int bits = 0;
+  size_t pos = 0;
+  for (;;) {
+    while (bits < width && pos < n) { acc = (acc << 8) | in[pos++]; bits += 8; }
+    if (bits < width) break;
+    const uint32_t code = (acc >> (bits - width)) & ((1u << width) - 1);
+    bits -= width;
+    if (code == 257) break;
+    if (code == 256) { reset(); width = 9; prev = -1; continue; }
+    std::vector<unsigned char> entry;
+    if (code < table.size()) entry = table[code];
+    else if (prev >= 0 && code == table.size()) { entry = table[prev]; entry.push_back(table[prev][0]); }
+    else fail("TIFF file: corrupt LZW stream");
+    out.insert(out.end(), entry.begin(), entry.end());
+    if (prev >= 0) {
+      std::vector<unsigned char> add = table[prev];
+      add.push_back(entry[0]);
+      table.push_back(std::move(add));
+    }
+    prev = code;
+    if (table.size() + 1 >= (1u << width) && width < 12) ++width;
+  }
+}
+
+// Deflate (compression 8 / 32946) through the system's zlib, resolved at run time like NCCL: no link-time dependency
+void inflate_strip(const unsigned char* in, size_t n, size_t expect, std::vector<unsigned char>& out) {
+  typedef int (*uncompress_t)(unsigned char*, unsigned long*, const unsigned char*, unsigned long);
+  static uncompress_t fn = [] {
+    void* h = dlopen("libz.so.1", RTLD_NOW);
+    if (!h) h = dlopen("libz.so", RTLD_NOW);
+    return h ? (uncompress_t)dlsym(h, "uncompress") : (uncompress_t) nullptr;
+  }();
+  if (!fn) fail("TIFF file: Deflate-compressed strips need libz.so.1, which could not be loaded");
+  std::vector<unsigned char> buf(expect);
+  unsigned long len = (unsigned long)expect;
+  if (fn(buf.data(), &len, in, (unsigned long)n) != 0) fail("TIFF file: corrupt Deflate stream");
+  out.insert(out.end(), buf.begin(), buf.begin() + len);
+}
+
 }  // namespace
 
 TiffImage read_tiff(const std::string& path) {
@@ -44,7 +98,7 @@ TiffImage read_tiff(const std::string& path) {
   size_t ifd = (size_t)r.get(4, 4);
   const int nent = (int)r.get(ifd, 2);
   TiffImage im;
-  uint32_t compression = 1, photometric = 99, samples = 1, rows_per_strip = 0xffffffffu, planar = 1;
+  uint32_t compression = 1, photometric = 99, samples = 1, rows_per_strip = 0xffffffffu, planar = 1, predictor = 1;
   std::vector<uint64_t> offsets, counts;
   static const int tsize[13] = {0, 1, 1, 2, 4, 8, 1, 1, 2, 4, 8, 4, 8};
   for (int e = 0; e < nent; ++e) {
@@ -73,6 +127,7 @@ TiffImage read_tiff(const std::string& path) {
       case 283: im.y_res = rational(); break;
       case 284: planar = (uint32_t)val(0); break;
       case 286: im.x_off = rational(); break;
+      case 317: predictor = (uint32_t)val(0); break;
       case 287: im.y_off = rational(); break;
       default: break;
     }
@@ -83,8 +138,9 @@ TiffImage read_tiff(const std::string& path) {
   if (im.bits != 8 && im.bits != 16 && im.bits != 32 && im.bits != 64)
     fail("Encoding with ", im.bits, " bits not implemented");   // tiff_grayscale.cc:79
   if (samples != 1 || planar != 1) fail("TIFF file '", path, "': only one sample per pixel is read by this build");
-  if (compression != 1 && compression != 32773)
-    fail("TIFF file '", path, "': compression ", compression, " needs libtiff (this build reads uncompressed and PackBits strips)");
+  if (compression != 1 && compression != 32773 && compression != 5 && compression != 8 && compression != 32946)
+    fail("TIFF file '", path, "': compression ", compression, " needs libtiff (this build reads uncompressed, PackBits, LZW and Deflate strips)");
+  if (predictor != 1 && predictor != 2) fail("TIFF file '", path, "': predictor ", predictor, " needs libtiff");
   if (im.rows == 0 || im.cols == 0 || offsets.empty() || offsets.size() != counts.size()) fail("TIFF file '", path, "' has no image data");
   if (rows_per_strip > im.rows) rows_per_strip = im.rows;
   const size_t bpp = im.bits / 8, line = (size_t)im.cols * bpp;
@@ -93,8 +149,13 @@ TiffImage read_tiff(const std::string& path) {
   for (size_t s = 0; s < offsets.size(); ++s) {
     const size_t b = (size_t)offsets[s], n = (size_t)counts[s];
     if (b + n > d.size()) fail("TIFF file '", path, "' is truncated");
+    const size_t strip_rows = std::min<size_t>(rows_per_strip, im.rows - s * (size_t)rows_per_strip);
     if (compression == 1) {
       raw.insert(raw.end(), d.begin() + b, d.begin() + b + n);
+    } else if (compression == 5) {
+      lzw_decode(d.data() + b, n, raw);
+    } else if (compression == 8 || compression == 32946) {
+      inflate_strip(d.data() + b, n, strip_rows * line, raw);
     } else {   // PackBits
       size_t i = b;
       while (i < b + n) {
@@ -105,6 +166,15 @@ TiffImage read_tiff(const std::string& path) {
     }
   }
   if (raw.size() < (size_t)im.rows * line) fail("TIFF file '", path, "' holds fewer pixels than its header says");
+  if (predictor == 2) {   // horizontal differencing: every sample is stored as the difference to its left neighbour
+    Reader in{raw, r.big};
+    for (size_t row = 0; row < im.rows; ++row)
+      for (size_t col = 1; col < im.cols; ++col) {
+        const size_t at = (row * im.cols + col) * bpp;
+        const uint64_t v = in.get(at, (int)bpp) + in.get(at - bpp, (int)bpp);
+        for (size_t k = 0; k < bpp; ++k) raw[at + (r.big ? bpp - 1 - k : k)] = (unsigned char)(v >> (8 * k));
+      }
+  }
   const double maxv = std::ldexp(1.0, im.bits);   // std::size_t{1} << bits in the reference (2^64 wraps there)
   im.values.resize((size_t)im.rows * im.cols);
   Reader px{raw, r.big};

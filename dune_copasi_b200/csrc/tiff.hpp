@@ -1,7 +1,8 @@
 // Grayscale TIFF images as two-argument parser_context functions (`type = tiff`, src/dune/copasi/parser/context.cc:66-71,
 // dune/copasi/common/tiff_grayscale.hh, src/dune/copasi/common/tiff_{file,grayscale}.cc).  The reference reads the files
 // through libtiff (not in this image): this is an own reader for the baseline layouts its images use -- one sample per
-// pixel, 8 / 16 / 32 / 64 bits, strips, uncompressed or PackBits; anything else fails loudly.
+// pixel, 8 / 16 / 32 / 64 bits, strips, uncompressed / PackBits / LZW / Deflate (zlib resolved at run time), optional
+// horizontal predictor; anything else (tiles, JPEG, several samples) fails loudly.
 #pragma once
 #include <cstdint>
 #include <string>

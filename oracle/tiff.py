@@ -3,7 +3,8 @@
 The reference reads images through libtiff (src/dune/copasi/common/tiff_file.cc:16-47) and evaluates them with
 TIFFGrayscale::operator() (src/dune/copasi/common/tiff_grayscale.cc:35-105).  libtiff is not in this image: this is an
 independent reader (struct-based, written apart from the product's csrc/tiff.cpp) for the baseline layouts -- one sample
-per pixel, 8 / 16 / 32 / 64 bits, strips, uncompressed or PackBits -- plus a writer for the tests."""
+per pixel, 8 / 16 / 32 / 64 bits, strips, uncompressed / PackBits / LZW / Deflate, optional horizontal predictor -- plus a
+writer for the tests."""
 from __future__ import annotations
 
 import struct
@@ -15,6 +16,85 @@ _TSIZE = {1: 1, 2: 1, 3: 2, 4: 4, 5: 8, 6: 1, 7: 1, 8: 2, 9: 4, 10: 8, 11: 4, 12
 
 class TiffError(Exception):
     pass
+
+
+def lzw_decode(data: bytes) -> bytes:
+    """TIFF LZW (compression 5): MSB-first 9..12 bit codes, Clear = 256, EndOfInformation = 257, early change."""
+    out = bytearray()
+    table = [bytes([i]) for i in range(256)] + [b"", b""]
+    width, prev, acc, bits, pos = 9, None, 0, 0, 0
+    while True:
+        while bits < width and pos < len(data):
+            acc = (acc << 8) | data[pos]
+            pos += 1
+            bits += 8
+        if bits < width:
+            break
+        code = (acc >> (bits - width)) & ((1 << width) - 1)
+        bits -= width
+        acc &= (1 << bits) - 1
+        if code == 257:
+            break
+        if code == 256:
+            table = table[:258]
+            width, prev = 9, None
+            continue
+        if code < len(table):
+            entry = table[code]
+        elif prev is not None and code == len(table):
+            entry = table[prev] + table[prev][:1]
+        else:
+            raise TiffError("corrupt LZW stream")
+        out += entry
+        if prev is not None:
+            table.append(table[prev] + entry[:1])
+        prev = code
+        if len(table) + 1 >= (1 << width) and width < 12:
+            width += 1
+    return bytes(out)
+
+
+def lzw_encode(data: bytes) -> bytes:
+    """the matching encoder (tests only)"""
+    out, acc, bits = bytearray(), 0, 0
+
+    def put(code, width):
+        nonlocal acc, bits
+        acc = (acc << width) | code
+        bits += width
+        while bits >= 8:
+            out.append((acc >> (bits - 8)) & 0xFF)
+            bits -= 8
+            acc &= (1 << bits) - 1
+
+    table = {bytes([i]): i for i in range(256)}
+    nxt, width = 258, 9
+    put(256, width)
+    w = b""
+    for byte in data:
+        wc = w + bytes([byte])
+        if wc in table:
+            w = wc
+            continue
+        put(table[w], width)
+        table[wc] = nxt
+        nxt += 1
+        if nxt + 1 >= (1 << width) + 1 and width < 12:      # the decoder has one entry fewer at this point
+            width += 1
+        if nxt >= 4094:
+            put(256, width)
+            table = {bytes([i]): i for i in range(256)}
+            nxt, width = 258, 9
+        w = bytes([byte])
+    if w:
+        put(table[w], width)
+        nxt += 1
+        if nxt + 1 >= (1 << width) + 1 and width < 12:
+            width += 1
+    put(257, width)
+    if bits:
+        out.append((acc << (8 - bits)) & 0xFF)
+    return bytes(out)
 
 
 class Image:
@@ -88,13 +168,21 @@ def read(path: str) -> Image:
     if tags.get(277, [1])[0] != 1:
         raise TiffError("only one sample per pixel")
     comp = tags.get(259, [1])[0]
-    if comp not in (1, 32773):
+    if comp not in (1, 32773, 5, 8, 32946):
         raise TiffError(f"compression {comp} needs libtiff")
+    predictor = tags.get(317, [1])[0]
+    if predictor not in (1, 2):
+        raise TiffError(f"predictor {predictor} needs libtiff")
     raw = bytearray()
     for off, n in zip(tags[273], tags[279]):
         chunk = data[off:off + n]
         if comp == 1:
             raw += chunk
+        elif comp == 5:
+            raw += lzw_decode(chunk)
+        elif comp in (8, 32946):
+            import zlib
+            raw += zlib.decompress(chunk)
         else:                                   # PackBits
             i = 0
             while i < len(chunk):
@@ -107,14 +195,17 @@ def read(path: str) -> Image:
                     raw += bytes([chunk[i]]) * (1 - c)
                     i += 1
     dt = np.dtype({8: "u1", 16: "u2", 32: "u4", 64: "u8"}[bits]).newbyteorder(bo)
-    px = np.frombuffer(bytes(raw[:rows * cols * bits // 8]), dtype=dt).reshape(rows, cols).astype(np.float64)
+    px = np.frombuffer(bytes(raw[:rows * cols * bits // 8]), dtype=dt).reshape(rows, cols)
+    if predictor == 2:                          # horizontal differencing, modulo 2^bits
+        px = np.cumsum(px.astype(np.uint64), axis=1, dtype=np.uint64) & np.uint64(2 ** bits - 1 if bits < 64 else 2 ** 64 - 1)
+    px = px.astype(np.float64)
     maxv = float(2 ** bits)
     vals = (px if photometric != 0 else maxv - px) / maxv
     return Image(vals, x_res, y_res, tags.get(286, [0.0])[0], tags.get(287, [0.0])[0])
 
 
 def write(path: str, pixels, bits=8, x_res=(10, 1), y_res=(10, 1), x_off=None, y_off=None, photometric=1,
-          packbits=False, big_endian=False, rows_per_strip=None):
+          packbits=False, big_endian=False, rows_per_strip=None, compression=None, predictor=1):
     """Minimal baseline writer for the tests: `pixels` [rows, cols] unsigned integers, resolutions as rationals."""
     bo = ">" if big_endian else "<"
     px = np.asarray(pixels)
@@ -122,8 +213,19 @@ def write(path: str, pixels, bits=8, x_res=(10, 1), y_res=(10, 1), x_off=None, y
     dt = np.dtype({8: "u1", 16: "u2", 32: "u4", 64: "u8"}[bits]).newbyteorder(bo)
     rps = rows_per_strip or rows
     strips = []
+    compression = compression or ("packbits" if packbits else "none")
+    packbits = compression == "packbits"
+    code = {"none": 1, "packbits": 32773, "lzw": 5, "deflate": 8}[compression]
     for r0 in range(0, rows, rps):
-        raw = px[r0:r0 + rps].astype(dt).tobytes()
+        block = px[r0:r0 + rps].astype(np.uint64)
+        if predictor == 2:
+            block = np.concatenate([block[:, :1], (block[:, 1:] - block[:, :-1]) & np.uint64(2 ** bits - 1 if bits < 64 else 2 ** 64 - 1)], axis=1)
+        raw = block.astype(dt).tobytes()
+        if compression == "lzw":
+            raw = lzw_encode(raw)
+        elif compression == "deflate":
+            import zlib
+            raw = zlib.compress(raw)
         if packbits:                            # literal runs only (valid PackBits), 128 bytes at a time
             out = bytearray()
             for i in range(0, len(raw), 128):
@@ -142,9 +244,11 @@ def write(path: str, pixels, bits=8, x_res=(10, 1), y_res=(10, 1), x_off=None, y
             payload = struct.pack(bo + fmt * len(values), *values)
         entries.append((tag, typ, len(values), payload))
 
-    add(256, 4, [cols]); add(257, 4, [rows]); add(258, 3, [bits]); add(259, 3, [32773 if packbits else 1])
+    add(256, 4, [cols]); add(257, 4, [rows]); add(258, 3, [bits]); add(259, 3, [code])
     add(262, 3, [photometric]); add(273, 4, [0] * len(strips)); add(277, 3, [1]); add(278, 4, [rps])
     add(279, 4, [len(s) for s in strips]); add(282, 5, [x_res]); add(283, 5, [y_res])
+    if predictor != 1:
+        add(317, 3, [predictor])
     if x_off is not None:
         add(286, 5, [x_off])
     if y_off is not None:

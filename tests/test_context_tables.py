@@ -254,3 +254,41 @@ def test_reference_tiff_unit_test_restated(tmp_path):
     assert np.abs(u0).max() <= thr and np.array_equal(u0, case.oracle().initial(0.0))
     with pytest.raises(D.DcbError, match="4 bits not implemented"):
         D.Model(D.Config(ini.format(p4, p16)), 2)
+
+
+def test_tiff_readers_against_libtiff_written_files(tmp_path):
+    """A pin against the library the reference reads its images with: Pillow bundles libtiff, so files written by it --
+    uncompressed, PackBits, LZW, Deflate, with and without the horizontal predictor, 8 and 16 bit, 72 dpi -- are real
+    libtiff output.  The oracle's reader must return exactly the pixels that went in, and the product's reader must
+    agree with it at every pixel (sampled through `img(position_x, position_y)` on a lattice of pixel centres)."""
+    PIL = pytest.importorskip("PIL.Image")
+    import dune_copasi_b200 as D
+    from oracle import tiff as TIFF
+    rng = np.random.default_rng(1)
+    rows, cols = 37, 53
+    yy, xx = np.mgrid[0:rows, 0:cols]
+    base = (128 + 90 * np.sin(xx / 8.0) * np.cos(yy / 5.0)).astype(np.int64) + rng.integers(0, 12, (rows, cols))
+    ini = K.EXP.replace("initial.expression = 1", "initial.expression = img(position_x, position_y)")
+    ini += "\n[parser_context.img]\ntype = tiff\npath = {}\n"
+    # vertices at the pixel centres: x = (j + 1/2) / 72, y counted upwards from the last scanline
+    origin, extent = [0.5 / 72, 0.5 / 72], [(cols - 1) / 72, (rows - 1) / 72]
+    mesh = K.OMESH.structured(2, [cols - 1, rows - 1], origin, extent)
+    for bits, arr in ((8, base.astype(np.uint8)), (16, (base * 200).astype(np.uint16))):
+        for comp in ("raw", "packbits", "tiff_lzw", "tiff_adobe_deflate"):
+            for pred in (1, 2):
+                if pred == 2 and comp in ("raw", "packbits"):
+                    continue
+                path = str(tmp_path / f"p{bits}_{comp}_{pred}.tif")
+                kw = {"compression": comp, "dpi": (72, 72)}
+                if pred == 2:
+                    kw["tiffinfo"] = {317: 2}
+                PIL.fromarray(arr).save(path, **kw)
+                im = TIFF.read(path)
+                assert np.array_equal(im.values * 2.0 ** bits, arr.astype(np.float64)), (bits, comp, pred)
+                assert float(im.x_res) == 72.0 and float(im.y_res) == 72.0
+                cfg = D.Config(ini.format(path))
+                model = D.Model(cfg, 2)
+                grid = D.Grid.structured(2, [cols - 1, rows - 1], origin, extent)
+                grid.bind(model)
+                u0 = grid.interpolate(model, 0.0).reshape(rows, cols)           # vertex (j, i): x fastest
+                assert np.array_equal(u0[::-1], arr / 2.0 ** bits), (bits, comp, pred)  # y upwards = scanlines reversed
