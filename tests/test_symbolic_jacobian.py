@@ -113,3 +113,34 @@ def test_differentiator_rules_against_differences():
         for (jac, up, dn), x in zip(out, pts):
             fd = (up - dn) / 2e-6       # both are -R: jm = -dR/du
             assert abs(jac - fd) <= 1e-7 * max(1.0, abs(fd)), (e, x, jac, fd)
+
+
+def test_differentiator_against_sympy():
+    """The derived entries against sympy (the Python sibling of SymEngine, the reference's symbolic backend) evaluated
+    with 30 digits: agreement to rounding, a much tighter pin than the central differences above."""
+    sympy = pytest.importorskip("sympy")
+    import dune_copasi_b200 as D
+    u, x = sympy.symbols("u position_x")
+    fn = {"log10": lambda a: sympy.log(a, 10), "log2": lambda a: sympy.log(a, 2), "exp2": lambda a: 2 ** a,
+          "pow": lambda a, b: a ** b, "hill": lambda s, K_: s ** 2 / (K_ ** 2 + s ** 2), "ln": sympy.log}
+    exprs = ["sqrt(1+u^2) + exp(-u)*sin(3*u) - cos(u)/(2+u)", "log(1+u)^2 + tanh(u) - atan(2*u) + u^2.5",
+             "pow(u, 3) / (1 + pow(2, u)) + 2^u",
+             "sinh(u) - cosh(2*u) + asin(u/2) + acos(u/3) + tan(u/2) + log10(1+u) + log2(2+u) + exp2(u)",
+             "hill(u, 0.5) + position_x*u", "atan2(u, 1+u)",
+             "0.042*(1-u) - u*(0.3+position_x)^2",                                   # Gray-Scott's U equation, V frozen
+             "0.2*((0.5+position_x)*u^2*(1-u)/0.1 - u/60)"]                          # Mitchell-Schaefer's u equation, z frozen
+    pts = [0.23, 0.61, 0.87]
+    for e in exprs:
+        ini = ("[compartments.domain]\nexpression = 1\n[parser_context.hill]\ntype = function\nexpression = s, K: s^2/(K^2 + s^2)\n"
+               "[model]\njacobian.type = symbolic\n[model.scalar_field.u]\ncompartment = domain\nstorage.expression = 1\n"
+               f"reaction.expression = {e}\n")
+        src = D.Model(D.Config(ini), 2).cuda_source().split("// Argument blocks shared")[0]
+        body = [PRELUDE, src, "int main(){ DcCtx c{}; c.pos[0]=0.3; double u[1], g[1][DC_DIM]={{0,0}}, sc[1], jm[1][1];\n"]
+        for p in pts:
+            body.append(f"u[0]={p!r}; DcComp<0>::jac_mass(c,u,g,0.0,1.0,jm); printf(\"%.17g\\n\", jm[0][0]);\n")
+        body.append("return 0; }\n")
+        got = _run("".join(body))
+        d = sympy.diff(sympy.sympify(e.replace("^", "**"), locals=dict(fn, u=u, position_x=x)), u)
+        for jac, p in zip(got, pts):
+            want = -float(d.evalf(30, subs={u: sympy.Float(repr(p), 30), x: sympy.Float("0.3", 30)}))     # jm = -dR/du
+            assert abs(jac - want) <= 2e-14 * max(1.0, abs(want)), (e, p, jac, want)
