@@ -122,6 +122,41 @@ def test_runge_kutta_tables_have_their_order(rk, order):
     assert abs(rate - order) < 0.35, (rk, errs, rate)
 
 
+def _stability_functions():
+    g2 = 1.0 - math.sqrt(2.0) / 2.0                       # Alexander (1977), two-stage L-stable SDIRK
+    g3 = 0.4358665215                                     # root of 1/6 - 3g/2 + 3g^2 - g^3 (three stages, order 3)
+    th = 1.0 - math.sqrt(2.0) / 2.0                       # fractional-step theta (Bristeau, Glowinski, Periaux 1987)
+    thp, al = 1.0 - 2.0 * th, (1.0 - 2.0 * th) / (1.0 - th)
+    be = 1.0 - al
+    return {
+        "ExplicitEuler": lambda z: 1 + z,
+        "ImplicitEuler": lambda z: 1 / (1 - z),
+        "Heun": lambda z: 1 + z + z * z / 2,
+        "Shu3": lambda z: 1 + z + z * z / 2 + z ** 3 / 6,
+        "RungeKutta4": lambda z: 1 + z + z * z / 2 + z ** 3 / 6 + z ** 4 / 24,
+        "Alexander2": lambda z: (1 + (1 - 2 * g2) * z) / (1 - g2 * z) ** 2,
+        "Alexander3": lambda z: (1 + (1 - 3 * g3) * z + (0.5 - 3 * g3 + 3 * g3 * g3) * z * z) / (1 - g3 * z) ** 3,
+        "FractionalStepTheta": lambda z: ((1 + be * th * z) / (1 - al * th * z)) ** 2 * (1 + al * thp * z) / (1 - be * thp * z),
+    }
+
+
+@pytest.mark.parametrize("rk", ["ExplicitEuler", "ImplicitEuler", "Heun", "Shu3", "RungeKutta4", "Alexander2", "Alexander3",
+                                "FractionalStepTheta"])
+def test_runge_kutta_tables_reproduce_the_published_stability_functions(rk):
+    """A pin of the restated PDELab tables that does not come from this repo: one step of u' = -2u (test/exp.ini) must
+    multiply u by the scheme's stability function R(-2 dt) as published (closed forms above, written from the
+    literature, not from oracle.core.rk_table)."""
+    R = _stability_functions()[rk]
+    for dt in (0.1, 0.04):
+        om = K.CASES["exp"].oracle(**{"model.time_step_operator.type": rk,
+                                      "model.time_step_operator.linear_solver.convergence_condition.relative_tolerance": "1e-14"})
+        S = ORC.StepOperator(om)
+        u0 = om.initial(0.0)
+        u1, ok = S.apply(u0, 0.0, dt)
+        assert ok
+        assert np.allclose(u1 / u0, R(-2.0 * dt), rtol=2e-9 if rk == "Alexander3" else 1e-10, atol=0), (rk, dt, (u1 / u0)[0], R(-2.0 * dt))
+
+
 @pytest.mark.parametrize("name", ["advection2d", "advection3d"])
 def test_extended_terms_jacobian_is_the_vertex_swapped_derivative(name):
     """Advection, tensor diffusion and dD/du terms (local_operator.hh:643-700).  The residual is pinned
