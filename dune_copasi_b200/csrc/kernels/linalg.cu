@@ -1,7 +1,8 @@
 // Statically compiled sm_100a kernels of the Krylov solve: SpMV, fused BLAS-1 sweeps, Jacobi and
 // block-Jacobi, Dirichlet masks, halo pack/unpack.  Everything here is HBM-bound fp64 streaming
-// work: vectorised (16-byte) loads where alignment allows, grids sized as multiples of the 148
-// SMs, reductions deterministic (fixed grid, ordered final sum).
+// work: one double per thread and grid stride (coalesced 256-byte requests per warp; measured at the
+// HBM copy bandwidth, profiles/r02_timeline_n1.json), grids sized as multiples of the 148 SMs,
+// reductions deterministic (fixed grid, ordered final sum), collectives fused into the last block.
 #include "linalg.hpp"
 
 #include "peer_device.cuh"

@@ -575,9 +575,9 @@ void DeviceOperator::launch_volume(const char* kind, int mode, double t, double 
       a.rowptr = (const long long*)rowptr.p; a.colidx = colidx.p; a.vals = vals;
       a.bdiag = bdiag ? bdiag + bdiag_shift(c) : nullptr;
       a.cmask = cmask.p;
-      // 16-byte gathers (padded coordinates, double2 dof loads): measured neutral on B200 (cell model on the
-      // nested mesh, 96^3: 0.170 against 0.159 ms per launch) -- the kernel is bound by the fp64 atomics of
-      // its scatter (~130 G RED/s), not by the gather wavefronts; kept as an option
+      // 16-byte gathers (padded coordinates, double2 dof loads): an option, off by default -- measured on B200 (cell
+      // model on the nested mesh, 96^3) neutral while the plain scatter bound the kernel, -2 % with the transposed
+      // scatter at 128 registers, +19 % at 164 registers (profiles/r02_cell10.md)
       if (c < (int)comp_pverts_.size() && comp_pverts_[c].p) { a.pverts = comp_pverts_[c].p; a.pdofs = comp_pdofs_[c].p; }
       a.coords4 = vector_gather_ ? coords4_.p : nullptr;
       a.vec = vector_gather_ && ns % 2 == 0 && dofs_even_ &&
