@@ -1,4 +1,5 @@
-# same-box A/B of the structured apply: commit f6769d9 (worktree ab_old/) against the current tree
+# same-box A/B of the structured apply: commit f6769d9 against the current tree.  Needs the worktree first:
+#   git worktree add ab_old f6769d9 && (cd ab_old && python -c "import sys; sys.path.insert(0, \".\"); from dune_copasi_b200 import build as B; B.build(); import bench; bench.precompile()")
 mkdir -p gpurun_out
 run() {
   name=$1; dir=$2; shift 2
