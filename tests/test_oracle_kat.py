@@ -486,3 +486,36 @@ def test_time_snap_kat():
         tot0 = m0[s::3].sum() + m0[2::3].sum()
         tot1 = m1[s::3].sum() + m1[2::3].sum()
         assert abs(tot1 - tot0) <= 1e-9 * abs(tot0)
+
+
+@pytest.mark.parametrize("name", ["gauss3d", "gauss2d", "poisson", "grayscott3d", "grayscott2d", "mitchell_schaefer"])
+def test_krylov_restatements_against_scipy(name):
+    """dune-istl is not in the reference tree: its CG and BiCGSTAB are restated (oracle.c).  scipy ships
+    independent implementations of the same published algorithms (Hestenes-Stiefel CG; van der Vorst's BiCGSTAB with
+    right preconditioning and the exit after the first half step): with the same Jacobi preconditioner, zero initial
+    guess and relative defect criterion the restatements must produce the same iterates -- identical iteration counts
+    (scipy reports whole iterations = half iterations // 2) and solutions equal to rounding."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    case = K.CASES[name]
+    om = case.oracle()
+    x = K.rand_state(om.ndofs, 12)
+    S = ORC.StepOperator(om)
+    vals = S._stage_jacobian(x, case.t0, 1.0, 0.5 * case.dt)
+    A = sp.csr_matrix((vals, S.colidx, S.rowptr), shape=(om.ndofs, om.ndofs))
+    b = K.rand_state(om.ndofs, 13, -1.0, 1.0)
+    d = A.diagonal()
+    M = spl.LinearOperator(A.shape, matvec=lambda v: v / d)
+    symmetric = abs(A - A.T).max() <= 1e-14 * abs(A).max()
+    for typ, fn in (("CG", spl.cg), ("BiCGSTAB", spl.bicgstab)):
+        if typ == "CG" and not symmetric:
+            continue
+        for tol in (1e-6, 1e-10):
+            zo, ro = ORC.linear_solve(S.rowptr, S.colidx, vals, b, {"type": typ, "preconditioner": {"type": "Jacobi"}}, tol)
+            its = [0]
+            z, info = fn(A, b, rtol=tol, atol=0.0, M=M, maxiter=500, callback=lambda xk: its.__setitem__(0, its[0] + 1))
+            assert info == 0 and ro.converged
+            assert its[0] == ro.iterations_x2 // 2, (name, typ, tol, its[0], ro.iterations_x2)
+            # the same iterates: to rounding on short runs; the dot products are summed in different orders, which
+            # BiCGSTAB amplifies over the ~50 iterations of the Poisson matrix -- still far inside the tolerance
+            assert np.linalg.norm(z - zo) <= max(1e-13, 1e-3 * tol) * np.linalg.norm(zo), (name, typ, tol)
